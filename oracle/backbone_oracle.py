@@ -1,0 +1,106 @@
+"""CPU oracle for the convolutional backbone -- TEST INFRASTRUCTURE ONLY.
+
+A torch-fp32 *functional* restatement of the reference's PoolResnet / Resnet
+forward pass and of the training-step definition (forward, sum of per-image
+``yolo_loss``, backward).  Floating-point kernels keep a torch fp32 reference;
+this is it.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+CPU-baseline legs may import this module.
+
+Parity status: PINNED against the real reference modules run in the build
+container (``tests/golden/make_golden.py`` -> ``tests/golden/backbone_*.npz``,
+checked by ``tests/test_oracle_golden.py``): logits identical (max-abs-diff 0.0,
+same ATen kernels), loss and gradients identical.
+
+Reference citations are ``file:line`` under ``/root/reference``.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+
+def residual_block(x, w1, b1, w2, b2, pool: bool, drop_scale: Optional[torch.Tensor] = None):
+    """models/PoolResnet.py:33-43 (same body in models/Resnet.py:30-40).
+
+    conv3x3 p1 -> LeakyReLU(0.2) -> conv3x3 p1 -> LeakyReLU(0.2) -> Dropout2d -> + skip ->
+    optional MaxPool2d(2).  ``drop_scale`` is an explicit ``[B,C,1,1]`` Dropout2d multiplier
+    (0 or 1/(1-p)); ``None`` = eval mode.
+    """
+    y = F.leaky_relu(F.conv2d(x, w1, b1, padding=1), 0.2)
+    y = F.leaky_relu(F.conv2d(y, w2, b2, padding=1), 0.2)
+    if drop_scale is not None:
+        y = y * drop_scale
+    y = y + x
+    if pool:
+        y = F.max_pool2d(y, 2)
+    return y
+
+
+def poolresnet_forward(x: torch.Tensor, p: Params, num_of_patches: int, num_blocks: int = 10,
+                       input_stride: int = 8, input_kernel_size: int = 10, output_padding: int = 0,
+                       drop_scales: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
+    """models/PoolResnet.py:93-105 with ``predict == 0``.
+
+    stem padding = kernel - stride (PoolResnet.py:75); a block pools iff its (pre-pool)
+    height is > 2*S (PoolResnet.py:41); head = valid conv + sigmoid (PoolResnet.py:83-89,101-102).
+    ``drop_scales``: optional list of ``num_blocks + 1`` multipliers (blocks, then the
+    Dropout2d(0.5) before the head, PoolResnet.py:100).
+    """
+    y = F.conv2d(x, p["conv1.weight"], p["conv1.bias"], stride=input_stride,
+                 padding=input_kernel_size - input_stride)
+    for b in range(num_blocks):
+        pre = f"residual_blocks.{b}."
+        ds = None if drop_scales is None else drop_scales[b]
+        y = residual_block(y, p[pre + "conv1.weight"], p[pre + "conv1.bias"],
+                           p[pre + "conv2.weight"], p[pre + "conv2.bias"],
+                           pool=y.shape[2] > 2 * num_of_patches, drop_scale=ds)
+    if drop_scales is not None and drop_scales[num_blocks] is not None:
+        y = y * drop_scales[num_blocks]
+    y = F.conv2d(y, p["out.weight"], p["out.bias"], padding=output_padding)
+    return torch.sigmoid(y)
+
+
+def resnet_forward(x: torch.Tensor, p: Params, num_of_patches: int, num_blocks: int = 10) -> torch.Tensor:
+    """models/Resnet.py:89-99 (eval): 3x3 s2 p1 stem, blocks pool while H > S (Resnet.py:38),
+    3x3 p1 head + sigmoid."""
+    y = F.conv2d(x, p["conv1.weight"], p["conv1.bias"], stride=2, padding=1)
+    for b in range(num_blocks):
+        pre = f"residual_blocks.{b}."
+        y = residual_block(y, p[pre + "conv1.weight"], p[pre + "conv1.bias"],
+                           p[pre + "conv2.weight"], p[pre + "conv2.bias"],
+                           pool=y.shape[2] > num_of_patches)
+    y = F.conv2d(y, p["out.weight"], p["out.bias"], padding=1)
+    return torch.sigmoid(y)
+
+
+def yolo_loss_torch(pred_fm: torch.Tensor, gt_fm: torch.Tensor) -> torch.Tensor:
+    """losses/YoloLoss.py:4-44 restated for autograd (same op order, same swapped x/y)."""
+    S = pred_fm.shape[1]
+    p = pred_fm.reshape(5, -1)
+    if torch.nansum(p):                                   # YoloLoss.py:8-9
+        p = torch.nan_to_num(p, nan=0.1)
+    g = gt_fm.reshape(5, -1)
+    g0 = g[0]
+    xy = 3 * g0 * ((g[1] - p[2]) ** 2 + (g[2] - p[1]) ** 2)      # YoloLoss.py:17-18,27-29
+    wh = 3 * g0 * ((g[3] ** 0.5 - p[3] ** 0.5) ** 2 + (g[4] ** 0.5 - p[4] ** 0.5) ** 2)
+    cf = (g0 + (1 - g0) * (1 / S)) * (g0 - p[0]) ** 2            # YoloLoss.py:25,36-38
+    return torch.sum(xy + wh + cf)
+
+
+def train_step(x: torch.Tensor, y: torch.Tensor, p: Params, num_of_patches: int,
+               forward=poolresnet_forward, **fw):
+    """The train-step definition (models/ModelMeta.py:141,173-176): ``y_hat = model(x)``;
+    ``loss = sum_i yolo_loss(y_hat[i], y[i])`` (a SUM, ModelMeta.py:215 has the mean commented
+    out); ``loss.backward()``.  Returns (y_hat, loss, grads)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    y_hat = forward(x, leaves, num_of_patches, **fw)
+    loss = 0
+    for i in range(y.shape[0]):                           # per-image python loop, as the reference
+        loss = loss + yolo_loss_torch(y_hat[i], y[i])
+    loss.backward()
+    grads = {k: v.grad.detach() for k, v in leaves.items()}
+    return y_hat.detach(), loss.detach(), grads

@@ -1,0 +1,84 @@
+"""The oracle (oracle/*.py) against golden vectors produced by the REAL reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import torch
+
+from oracle import yolo_oracle as yo
+from oracle import backbone_oracle as bo
+from tests.util import load_golden, seeded_poolresnet_params
+
+
+def test_grid_encode_bit_exact():
+    g = load_golden("grid_encode.npz")
+    pos = 0
+    for c, S in enumerate(g["S"]):
+        b = g["boxes"][g["offsets"][c]:g["offsets"][c + 1]]
+        want = g["fm"][pos:pos + 5 * S * S].reshape(5, S, S); pos += 5 * S * S
+        got = yo.grid_encode(b, int(S), 480, 480)
+        assert got.tobytes() == want.astype(np.float32).tobytes(), f"case {c}"
+
+
+def test_decode_nms_bit_exact():
+    g = load_golden("decode_nms.npz")
+    assert len(g["count"]) > 30
+    for c in range(len(g["count"])):
+        Smap, Sdec, pthr, ithr = g["meta"][c]
+        Smap, Sdec = int(Smap), int(Sdec)
+        x = g["x"][c, :5 * Smap * Smap].reshape(5, Smap, Smap)
+        want = g["out"][c, :g["count"][c]]
+        got = yo.reduce_bounding_boxes(x, pthr, ithr, (3, 480, 480), Sdec)
+        assert got.shape == want.shape, f"case {c}: {got.shape} vs {want.shape}"
+        assert got.tobytes() == want.tobytes(), f"case {c}"
+
+
+def test_nms_indices_bit_exact():
+    g = load_golden("nms.npz")
+    for c in range(len(g["n"])):
+        n = int(g["n"][c])
+        keep = yo.nms(g["boxes"][c, :n], g["scores"][c, :n], float(g["thr"][c]))
+        want = g["keep"][c]; want = want[want >= 0]
+        assert np.array_equal(keep, want), f"case {c}"
+
+
+def test_yolo_loss_value_and_grad():
+    g = load_golden("yolo_loss.npz")
+    for c, S in enumerate(g["S"]):
+        n = 5 * S * S
+        p = g["pred"][c, :n].reshape(5, S, S); gt = g["gt"][c, :n].reshape(5, S, S)
+        loss, d = yo.yolo_loss(p, gt)
+        # the reference evaluates in f32; the oracle in f64: tolerance = f32 rounding of a ~S^2-term sum
+        assert abs(loss - g["loss"][c]) <= 2e-6 * abs(g["loss"][c]) + 1e-6, f"case {c}"
+        want = g["dpred"][c, :n].reshape(5, S, S)
+        np.testing.assert_allclose(d, want, rtol=2e-5, atol=2e-6)
+        # f32 evaluation of the same formula
+        loss32, d32 = yo.yolo_loss(p, gt, dtype=np.float32)
+        assert abs(loss32 - g["loss"][c]) <= 1e-5 * abs(g["loss"][c]) + 1e-6
+
+
+def test_backbone_oracle_matches_reference_seeded():
+    g = load_golden("backbone_seed2.npz")
+    p = seeded_poolresnet_params(64, seed=2)
+    for k, v in p.items():      # same weights as the reference module built under the same seed
+        s = g["w_sum." + k]
+        assert abs(v.double().sum().item() - s[0]) < 1e-9 and abs(v.double().abs().sum().item() - s[1]) < 1e-9, k
+    x = torch.rand(2, 3, 480, 480, generator=torch.Generator().manual_seed(0))
+    y = torch.from_numpy(g["y"])
+    y_hat, loss, grads = bo.train_step(x, y, p, 10)
+    assert torch.equal(y_hat, torch.from_numpy(g["y_hat"]))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    for k in p:
+        assert abs(grads[k].double().norm().item() - float(g["g_norm." + k])) <= 1e-5 * float(g["g_norm." + k]) + 1e-12, k
+        np.testing.assert_allclose(grads[k].reshape(-1)[:64].numpy(), g["g_head." + k], rtol=1e-4, atol=1e-7)
+
+
+def test_backbone_oracle_official_checkpoint_demo_path():
+    g = load_golden("official_medium.npz")
+    p = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    for i in range(len(g["counts"])):
+        x = torch.from_numpy(g["images"][i:i + 1]).float() / 255.0       # PoolResnet.py:94-97
+        x = torch.cat([x, x])                                          # demo_model.py:20 stacks the frame twice
+        head = bo.poolresnet_forward(x, p, 10)
+        assert torch.equal(head[0], torch.from_numpy(g["heads"][i]))
+        boxes = yo.reduce_bounding_boxes(head[0].numpy(), float(g["p_thr"]), float(g["iou_thr"]), (3, 480, 480), 10)
+        want = g["boxes"][i, :g["counts"][i]]
+        assert boxes.tobytes() == want.tobytes()
