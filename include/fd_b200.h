@@ -1,0 +1,149 @@
+/* fd_b200.h -- C ABI of the B200-native detection hot path (libfd_b200.so).
+ *
+ * The reference (smpurkis/PyTorch-Face-Detection-from-Scratch) is pure Python and has no FFI;
+ * every entry point below replaces a *PyTorch call site* of the reference (cited as
+ * file:line under the reference root).  INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 = OK, > 0 = cudaError_t, < 0 = FD_E* argument error;
+ *     nothing throws, nothing allocates device memory, nothing synchronises the device;
+ *   - all data pointers are DEVICE pointers owned by the caller (16-byte aligned);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it (CUDA-graph capturable);
+ *   - activations are NHWC bf16 (`fd_bf16` = uint16_t bit pattern), accumulators / losses /
+ *     gradients of parameters are fp32, indices are int32;
+ *   - functions are stateless and re-entrant.
+ */
+#ifndef FD_B200_H_
+#define FD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t fd_bf16;
+
+#if defined(__GNUC__)
+#define FD_API __attribute__((visibility("default")))
+#else
+#define FD_API
+#endif
+
+#define FD_OK 0
+#define FD_EINVAL (-1)      /* bad argument (shape / null pointer / alignment) */
+#define FD_EUNSUPPORTED (-2) /* shape outside what the kernels are instantiated for */
+#define FD_EDRIVER (-3)     /* could not resolve cuTensorMapEncodeTiled from the driver */
+
+/* epilogue flags for fd_conv3x3 */
+#define FD_EPI_LRELU 1   /* v = v > 0 ? v : slope * v            (PoolResnet.py:36,38) */
+#define FD_DBG_BASE_OFFSET 256 /* debug: set the smem-descriptor base-offset field from the address */
+#define FD_DBG_PLAN_B 512      /* debug: one 1024B-aligned input copy per kx tap (no row-shifted descriptors) */
+
+FD_API int fd_version(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+FD_API long long fd_launch_count(void);
+FD_API const char* fd_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3x3, stride 1, pad 1 convolution, C -> C channels (C = 64), implicit GEMM on tcgen05.
+ * Replaces aten::conv2d + leaky_relu + dropout2d + residual add at models/PoolResnet.py:35-40
+ * (forward) and, called with dgrad-packed weights, the input-gradient of the same conv.
+ *
+ *   acc = conv3x3(x, w)                                   fp32 accumulate in TMEM
+ *   v   = acc + bias[c]            (bias != NULL)
+ *   v   = lrelu(v)                 (flags & FD_EPI_LRELU)
+ *   v  *= chan_scale[n, c]         (chan_scale != NULL; Dropout2d multiplier)
+ *   aux_out = bf16(v)              (aux_out != NULL; pre-residual activation, saved for backward)
+ *   v  += residual                 (residual != NULL)
+ *   out  = bf16(v)                 (out != NULL)
+ *   out2 = bf16(v * chan_scale2[n, c] * (mask_src > 0 ? 1 : slope))   (out2 != NULL; LeakyReLU'
+ *                                   of a saved activation -- the backward chain)
+ *
+ * x, residual, aux_out, out, mask_src, out2: [B,H,W,C] bf16.  w_packed: [9][C][C] bf16 from
+ * fd_pack_conv3x3 (forward or dgrad packing).  bias: [C] fp32.  chan_scale*: [B,C] fp32.
+ */
+FD_API int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, int W, int C,
+               const float* bias, float slope, const float* chan_scale,
+               const fd_bf16* residual, fd_bf16* aux_out, fd_bf16* out,
+               const fd_bf16* mask_src, const float* chan_scale2, fd_bf16* out2,
+               int flags, void* stream);
+
+/* Weight gradient of the same convolution (replaces the wgrad half of autograd's
+ * conv2d backward for models/PoolResnet.py:35,37).
+ *   dw_packed[t][ci][co] += sum_{n,y,x} g[n,y,x,co] * xpad[n,y+ky-1,x+kx-1,ci],  t = ky*3+kx
+ *   dbias[co]            += sum_{n,y,x} g[n,y,x,co]
+ * x, g: [B,H,W,C] bf16; dw_packed: [9][C][C] fp32 and dbias: [C] fp32 are ACCUMULATED into
+ * (zero them first).  fd_unpack_wgrad3x3 converts to the torch layout [co][ci][3][3]. */
+FD_API int fd_conv3x3_wgrad(const fd_bf16* x, const fd_bf16* g, int B, int H, int W, int C,
+                     float* dw_packed, float* dbias, int flags, void* stream);
+
+/* w: [n_layers][C][C][3][3] fp32 (torch layout, PoolResnet.py:15-28) ->
+ *   w_fwd  [n_layers][9][co][ci] bf16,  w_dgrad [n_layers][9][ci][co] bf16 with flipped taps
+ * (either output may be NULL). */
+FD_API int fd_pack_conv3x3(const float* w, int n_layers, int C, fd_bf16* w_fwd, fd_bf16* w_dgrad, void* stream);
+/* dw_packed [n_layers][9][ci][co] fp32 -> dw [n_layers][co][ci][3][3] fp32 (overwrites). */
+FD_API int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, float* dw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stem convolution (models/PoolResnet.py:70-76,98): KxK stride s pad p, Cin(3) -> C, input fp32 NCHW
+ * (or uint8 NCHW with the /255 of PoolResnet.py:95 fused: x_is_u8 = 1), output NHWC bf16, bias added.
+ * w: [C][Cin][K][K] fp32. */
+FD_API int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const float* bias, int B, int Cin, int Hin, int Win,
+                int C, int K, int stride, int pad, fd_bf16* y, void* stream);
+/* dw[C][Cin][K][K] += x (*) g ; dbias[C] += sum g.  g: [B,Ho,Wo,C] bf16. */
+FD_API int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C, int K,
+                  int stride, int pad, float* dw, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Head (models/PoolResnet.py:83-89,100-102): Dropout2d multiplier, KxK stride-1 conv C -> 5 with
+ * padding `pad`, + bias, sigmoid.  x: [B,H,W,C] bf16, w: [5][C][K][K] fp32, y: [B,5,Ho,Wo] fp32. */
+FD_API int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* bias, int B, int H, int W,
+                int C, int K, int pad, float* y, void* stream);
+/* dy: [B,5,Ho,Wo] fp32 gradient w.r.t. the sigmoid OUTPUT y.  Produces
+ *   dx [B,H,W,C] bf16 (gradient w.r.t. the block output, dropout multiplier applied; overwritten) and,
+ *   when dx2 != NULL, dx2 = dx * chan_scale2 * (mask_src > 0 ? 1 : slope),
+ *   dw [5][C][K][K] fp32 (+=), dbias [5] fp32 (+=). */
+FD_API int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* y, const float* dy, int B,
+                int H, int W, int C, int K, int pad, fd_bf16* dx, const fd_bf16* mask_src,
+                const float* chan_scale2, float slope, fd_bf16* dx2, float* dw, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MaxPool2d(2) (models/PoolResnet.py:41-42).  x: [B,H,W,C] bf16 -> y: [B,H/2,W/2,C] bf16. */
+FD_API int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, void* stream);
+/* Backward of the pool fused with the start of the block's backward chain:
+ *   gs  = unpool(gy) routed to the FIRST maximum of each 2x2 window of x (torch tie rule),
+ *   gs2 = gs * chan_scale[n,c] * (mask_src > 0 ? 1 : slope)      (gs2 != NULL)
+ * x, mask_src, gs, gs2: [B,H,W,C] bf16; gy: [B,H/2,W/2,C] bf16. */
+FD_API int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int H, int W, int C, fd_bf16* gs,
+                      const fd_bf16* mask_src, const float* chan_scale, float slope, fd_bf16* gs2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * losses/YoloLoss.py:4-44 for a batch: loss[b] = yolo_loss(pred[b], gt[b]) and, when dpred != NULL,
+ * dpred[b] = dloss_scale[b] * d loss[b] / d pred[b]  (dloss_scale == NULL means 1).
+ * pred, gt, dpred: [B,5,S1,S2] fp32.  The no-object weight is 1/S1 (YoloLoss.py:6,25). */
+FD_API int fd_yolo_loss(const float* pred, const float* gt, int B, int S1, int S2, float* loss, const float* dloss_scale,
+                 float* dpred, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * datasets/utils.py:95-170 ReduceBoundingBoxes.forward for a batch (decode, score threshold,
+ * round, torchvision-compatible NMS).  pred: [B,5,S1,S2] fp32.
+ *   out_boxes [B, S1*S2, 5] fp32: rows (score, x, y, w, h) in keep order (descending score)
+ *   out_cell  [B, S1*S2] int32 (nullable): flat cell index i*S2+j of each kept row
+ *   out_count [B] int32: number of kept rows
+ * patch sizes are width/num_of_patches and height/num_of_patches (utils.py:108-109), NOT derived
+ * from S1/S2.  iou_thr is compared in double like torchvision's CPU kernel. */
+FD_API int fd_decode_nms(const float* pred, int B, int S1, int S2, float p_thr, double iou_thr, int width, int height,
+                  int num_of_patches, float* out_boxes, int32_t* out_cell, int32_t* out_count, void* stream);
+
+/* datasets/WIDERFace/dataset.py:32-64 convert_bbx_to_feature_map for a ragged batch.
+ * boxes: [total,5] fp32 rows (1,x,y,w,h); box_offsets: [B+1] int32; out: [B,5,S,S] fp32 (overwritten).
+ * Later boxes overwrite earlier ones that fall in the same cell. */
+FD_API int fd_grid_encode(const float* boxes, const int32_t* box_offsets, int B, int S, int width, int height, float* out,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FD_B200_H_ */

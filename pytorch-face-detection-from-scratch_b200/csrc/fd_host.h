@@ -1,0 +1,29 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/fd_b200.h"
+
+namespace fd {
+
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// cudaError_t -> ABI return code, consuming the sticky "last error" of a failed launch.
+inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? FD_OK : static_cast<int>(e);
+}
+
+// [B,H,W,C] bf16 tensor as a 4-D tiled TMA map with box {C, boxW, boxH, 1}, 128B swizzle, zero OOB fill.
+int make_tmap_nhwc_bf16(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int boxW, int boxH);
+// [rows, cols] bf16 row-major as a 2-D tiled TMA map with box {boxCols, boxRows}, 128B swizzle.
+int make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, int rows, int cols, int boxRows, int boxCols);
+
+int sm_count();
+
+}  // namespace fd

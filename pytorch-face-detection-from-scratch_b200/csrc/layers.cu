@@ -1,0 +1,558 @@
+// CUDA-core kernels of the backbone that are not 64->64 3x3 convolutions: weight packing,
+// the stem convolution (3 -> C, 10x10 stride 8), the 5-channel head (+ sigmoid) and MaxPool2d(2),
+// each forward and backward.  All are memory- or latency-bound; the tensor-core work lives in
+// conv3x3_tc.cu / wgrad3x3_tc.cu.
+#include "fd_host.h"
+#include "fd_ptx.cuh"
+
+namespace fd {
+namespace {
+
+// ============================================================================ weight packing
+// torch [co][ci][ky][kx] fp32  ->  fwd [t][co][ci] bf16 ; dgrad [t'][ci][co] bf16 with t' = flipped tap
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, int n_layers, int C, __nv_bfloat16* __restrict__ wf,
+                                    __nv_bfloat16* __restrict__ wd) {
+  const long total = static_cast<long>(n_layers) * 9 * C * C;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int b = i % C;
+    const int a = (i / C) % C;
+    const int t = (i / (static_cast<long>(C) * C)) % 9;
+    const long l = i / (9L * C * C);
+    const float* wl = w + l * 9L * C * C;
+    if (wf) wf[i] = __float2bfloat16(wl[(static_cast<long>(a) * C + b) * 9 + t]);          // a = co, b = ci
+    if (wd) wd[i] = __float2bfloat16(wl[(static_cast<long>(b) * C + a) * 9 + (8 - t)]);    // a = ci, b = co
+  }
+}
+
+// packed gradient [t][ci][co] fp32 -> torch [co][ci][ky][kx] fp32
+__global__ void unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, int C, float* __restrict__ dw) {
+  const long total = static_cast<long>(n_layers) * 9 * C * C;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int t = i % 9;
+    const int ci = (i / 9) % C;
+    const int co = (i / (9L * C)) % C;
+    const long l = i / (9L * C * C);
+    dw[i] = dwp[l * 9L * C * C + (static_cast<long>(t) * C + ci) * C + co];
+  }
+}
+
+// ============================================================================ stem
+// One CTA task = one output row (n, oy): Wo x C outputs, K = Cin*Kk*Kk.  256 threads:
+// thread = (cog = tid & 15 -> 4 output channels, oxg = tid >> 4 -> 4 output columns).
+// smem: weights transposed to [k][co] fp32 (persistent), the Kk input rows of every channel.
+constexpr int kStemThreads = 256;
+
+template <typename TIn>
+__device__ __forceinline__ float stem_in(const TIn* p) { return static_cast<float>(*p); }
+template <>
+__device__ __forceinline__ float stem_in<uint8_t>(const uint8_t* p) { return static_cast<float>(*p) / 255.0f; }
+
+template <typename TIn>
+__device__ void stem_load_rows(const TIn* __restrict__ x, float* sIn, int n, int oy, int Cin, int Hin, int Win, int K,
+                               int stride, int pad, int pitch) {
+  // sIn[c][ky][pitch]: column j holds input column j - pad
+  const int rows = Cin * K;
+  for (int idx = threadIdx.x; idx < rows * pitch; idx += blockDim.x) {
+    const int j = idx % pitch;
+    const int r = idx / pitch;
+    const int ky = r % K, c = r / K;
+    const int iy = oy * stride + ky - pad;
+    const int ix = j - pad;
+    float v = 0.f;
+    if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win)
+      v = stem_in<TIn>(x + ((static_cast<size_t>(n) * Cin + c) * Hin + iy) * Win + ix);
+    sIn[idx] = v;
+  }
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B, int Cin,
+                int Hin, int Win, int C, int K, int stride, int pad, int Ho, int Wo, __nv_bfloat16* __restrict__ y) {
+  extern __shared__ float sm[];
+  const int KK = Cin * K * K;
+  const int pitch = (Wo - 1) * stride + K + 1;
+  float* sW = sm;               // [KK][C]
+  float* sIn = sm + KK * C;     // [Cin*K][pitch]
+  for (int i = threadIdx.x; i < KK * C; i += blockDim.x) {
+    const int co = i % C, k = i / C;
+    sW[i] = w[static_cast<size_t>(co) * KK + k];
+  }
+  const int cog = threadIdx.x & 15, oxg = threadIdx.x >> 4;
+  const int ntask = B * Ho;
+  for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+    const int n = task / Ho, oy = task % Ho;
+    __syncthreads();
+    stem_load_rows<TIn>(x, sIn, n, oy, Cin, Hin, Win, K, stride, pad, pitch);
+    __syncthreads();
+    for (int cb = 0; cb < C; cb += 64) {
+      const int co0 = cb + cog * 4;
+      for (int ob = 0; ob < Wo; ob += 64) {
+        const int ox0 = ob + oxg * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        if (ox0 < Wo) {
+          for (int r = 0; r < Cin * K; ++r) {
+            const float* inrow = sIn + r * pitch;
+            const float* wrow = sW + static_cast<size_t>(r) * K * C + co0;
+            for (int kx = 0; kx < K; ++kx) {
+              const float4 wv = *reinterpret_cast<const float4*>(wrow + kx * C);
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const int ox = min(ox0 + a, Wo - 1);
+                const float iv = inrow[ox * stride + kx];
+                acc[a][0] = fmaf(iv, wv.x, acc[a][0]);
+                acc[a][1] = fmaf(iv, wv.y, acc[a][1]);
+                acc[a][2] = fmaf(iv, wv.z, acc[a][2]);
+                acc[a][3] = fmaf(iv, wv.w, acc[a][3]);
+              }
+            }
+          }
+          const float4 bv = *reinterpret_cast<const float4*>(bias + co0);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int ox = ox0 + a;
+            if (ox < Wo) {
+              uint2 o;
+              o.x = pack_bf16x2(acc[a][0] + bv.x, acc[a][1] + bv.y);
+              o.y = pack_bf16x2(acc[a][2] + bv.z, acc[a][3] + bv.w);
+              *reinterpret_cast<uint2*>(y + ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * C + co0) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// wgrad: thread = (cog = tid & 15 -> 4 output channels, kg = tid >> 4 -> KPT consecutive k).
+// Accumulators stay in registers over all row tasks of the persistent CTA, one atomic flush at the end.
+constexpr int kStemKPT = 19;  // ceil(300 / 16)
+
+template <typename TIn>
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_wgrad_kernel(const TIn* __restrict__ x, const __nv_bfloat16* __restrict__ g, int B, int Cin, int Hin, int Win,
+                  int C, int K, int stride, int pad, int Ho, int Wo, float* __restrict__ dw, float* __restrict__ dbias) {
+  extern __shared__ float sm[];
+  const int KK = Cin * K * K;
+  const int pitch = (Wo - 1) * stride + K + 1;
+  float* sG = sm;                 // [Wo][C]
+  float* sIn = sm + Wo * C;       // [Cin*K][pitch]
+  const int cog = threadIdx.x & 15, kg = threadIdx.x >> 4;
+  const int ntask = B * Ho;
+  for (int cb = 0; cb < C; cb += 64) {
+    const int co0 = cb + cog * 4;
+    float acc[kStemKPT][4];
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+    int koff[kStemKPT];
+#pragma unroll
+    for (int i = 0; i < kStemKPT; ++i) {
+      acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      const int k = min(kg * kStemKPT + i, KK - 1);
+      const int kx = k % K, r = k / K;  // r = c*K + ky
+      koff[i] = r * pitch + kx;
+    }
+    for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+      const int n = task / Ho, oy = task % Ho;
+      __syncthreads();
+      stem_load_rows<TIn>(x, sIn, n, oy, Cin, Hin, Win, K, stride, pad, pitch);
+      for (int i = threadIdx.x; i < Wo * C; i += blockDim.x)
+        sG[i] = __bfloat162float(g[(static_cast<size_t>(n) * Ho + oy) * Wo * C + i]);
+      __syncthreads();
+      for (int ox = 0; ox < Wo; ++ox) {
+        const float4 gv = *reinterpret_cast<const float4*>(sG + ox * C + co0);
+        const float* inb = sIn + ox * stride;
+        if (kg == 0) { bacc[0] += gv.x; bacc[1] += gv.y; bacc[2] += gv.z; bacc[3] += gv.w; }
+#pragma unroll
+        for (int i = 0; i < kStemKPT; ++i) {
+          const float iv = inb[koff[i]];
+          acc[i][0] = fmaf(iv, gv.x, acc[i][0]);
+          acc[i][1] = fmaf(iv, gv.y, acc[i][1]);
+          acc[i][2] = fmaf(iv, gv.z, acc[i][2]);
+          acc[i][3] = fmaf(iv, gv.w, acc[i][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kStemKPT; ++i) {
+      const int k = kg * kStemKPT + i;
+      if (k < KK) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) atomicAdd(dw + static_cast<size_t>(co0 + a) * KK + k, acc[i][a]);
+      }
+    }
+    if (kg == 0 && dbias) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) atomicAdd(dbias + co0 + a, bacc[a]);
+    }
+  }
+}
+
+// ============================================================================ head
+// grid = (B, kHeadSplit): each CTA stages one image (bf16, dropout multiplier applied on the fly)
+// and computes a slice of the output pixels, one warp per pixel, lanes over channels.
+constexpr int kHeadThreads = 256;
+constexpr int kHeadSplit = 4;
+
+__global__ void __launch_bounds__(kHeadThreads)
+head_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ w,
+                const float* __restrict__ bias, int B, int H, int W, int C, int K, int pad, int Ho, int Wo,
+                float* __restrict__ y) {
+  extern __shared__ float sm[];
+  float* sW = sm;                                                      // [K*K][5][C]
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sm + K * K * 5 * C);  // [H*W][C]
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < K * K * 5 * C; i += blockDim.x) {
+    const int c = i % C, o = (i / C) % 5, t = i / (5 * C);
+    sW[i] = w[(static_cast<size_t>(o) * C + c) * K * K + t];
+  }
+  const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * H * W * C);
+  for (int i = threadIdx.x; i < H * W * C / 8; i += blockDim.x) reinterpret_cast<uint4*>(sX)[i] = __ldg(xs + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int pix = blockIdx.y * nwarp + warp; pix < Ho * Wo; pix += gridDim.y * nwarp) {
+    const int oy = pix / Wo, ox = pix % Wo;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < C; c += 32) {
+      const float s = cs ? cs[n * C + c] : 1.f;
+      for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy + ky - pad;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < K; ++kx) {
+          const int ix = ox + kx - pad;
+          if (ix < 0 || ix >= W) continue;
+          const float xv = __bfloat162float(sX[(iy * W + ix) * C + c]) * s;
+          const float* wp = sW + (ky * K + kx) * 5 * C + c;
+#pragma unroll
+          for (int o = 0; o < 5; ++o) acc[o] = fmaf(xv, wp[o * C], acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 5; ++o) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
+    }
+    if (lane < 5) {
+      float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : acc[4];
+      v += bias[lane];
+      y[((static_cast<size_t>(n) * 5 + lane) * Ho + oy) * Wo + ox] = 1.f / (1.f + expf(-v));
+    }
+  }
+}
+
+// backward: one CTA per image (loops over images), 256 threads.
+__global__ void __launch_bounds__(kHeadThreads)
+head_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ w,
+                const float* __restrict__ y, const float* __restrict__ dy, int B, int H, int W, int C, int K, int pad,
+                int Ho, int Wo, __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ mask_src,
+                const float* __restrict__ cs2, float slope, __nv_bfloat16* __restrict__ dx2, float* __restrict__ dw,
+                float* __restrict__ dbias) {
+  extern __shared__ float sm[];
+  const int KK = K * K;
+  float* sW = sm;                       // [KK][5][C]
+  float* sDz = sW + KK * 5 * C;         // [5][Ho*Wo]
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sDz + ((5 * Ho * Wo + 3) & ~3));  // [H*W][C]
+  for (int i = threadIdx.x; i < KK * 5 * C; i += blockDim.x) {
+    const int c = i % C, o = (i / C) % 5, t = i / (5 * C);
+    sW[i] = w[(static_cast<size_t>(o) * C + c) * KK + t];
+  }
+  const int c = threadIdx.x % C;        // requires blockDim % C == 0
+  const int grp = threadIdx.x / C, ngrp = blockDim.x / C;
+  for (int n = blockIdx.x; n < B; n += gridDim.x) {
+    __syncthreads();
+    const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * H * W * C);
+    for (int i = threadIdx.x; i < H * W * C / 8; i += blockDim.x) reinterpret_cast<uint4*>(sX)[i] = __ldg(xs + i);
+    for (int i = threadIdx.x; i < 5 * Ho * Wo; i += blockDim.x) {
+      const float yv = y[static_cast<size_t>(n) * 5 * Ho * Wo + i];
+      sDz[i] = dy[static_cast<size_t>(n) * 5 * Ho * Wo + i] * yv * (1.f - yv);
+    }
+    __syncthreads();
+    const float s = cs ? cs[n * C + c] : 1.f;
+    // ---- dbias
+    if (threadIdx.x < 5) {
+      float t = 0.f;
+      for (int i = 0; i < Ho * Wo; ++i) t += sDz[threadIdx.x * Ho * Wo + i];
+      atomicAdd(dbias + threadIdx.x, t);
+    }
+    // ---- dx (and the masked copy that starts the last block's backward chain)
+    const float s2 = cs2 ? cs2[n * C + c] : 1.f;
+    for (int pix = grp; pix < H * W; pix += ngrp) {
+      const int iy = pix / W, ix = pix % W;
+      float acc = 0.f;
+      for (int ky = 0; ky < K; ++ky) {
+        const int oy = iy - ky + pad;
+        if (oy < 0 || oy >= Ho) continue;
+        for (int kx = 0; kx < K; ++kx) {
+          const int ox = ix - kx + pad;
+          if (ox < 0 || ox >= Wo) continue;
+          const float* wp = sW + (ky * K + kx) * 5 * C + c;
+#pragma unroll
+          for (int o = 0; o < 5; ++o) acc = fmaf(sDz[o * Ho * Wo + oy * Wo + ox], wp[o * C], acc);
+        }
+      }
+      acc *= s;
+      const size_t gi = (static_cast<size_t>(n) * H * W + pix) * C + c;
+      if (dx) dx[gi] = __float2bfloat16(acc);
+      if (dx2) {
+        const float m = __bfloat162float(mask_src[gi]) > 0.f ? 1.f : slope;
+        dx2[gi] = __float2bfloat16(acc * m * s2);
+      }
+    }
+    // ---- dw: thread (c, grp) owns taps grp, grp+ngrp, ...
+    for (int t = grp; t < KK; t += ngrp) {
+      const int ky = t / K, kx = t % K;
+      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int oy = 0; oy < Ho; ++oy) {
+        const int iy = oy + ky - pad;
+        if (iy < 0 || iy >= H) continue;
+        for (int ox = 0; ox < Wo; ++ox) {
+          const int ix = ox + kx - pad;
+          if (ix < 0 || ix >= W) continue;
+          const float xv = __bfloat162float(sX[(iy * W + ix) * C + c]) * s;
+#pragma unroll
+          for (int o = 0; o < 5; ++o) acc[o] = fmaf(xv, sDz[o * Ho * Wo + oy * Wo + ox], acc[o]);
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 5; ++o) atomicAdd(dw + (static_cast<size_t>(o) * C + c) * KK + t, acc[o]);
+    }
+  }
+}
+
+// ============================================================================ maxpool 2x2
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+__global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
+                                      __nv_bfloat16* __restrict__ y) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  const long total = static_cast<long>(B) * Ho * Wo * C8;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c8 = i % C8;
+    const int ox = (i / C8) % Wo;
+    const int oy = (i / (static_cast<long>(C8) * Wo)) % Ho;
+    const long n = i / (static_cast<long>(C8) * Wo * Ho);
+    const __nv_bfloat16* base = x + ((n * H + 2 * oy) * W + 2 * ox) * C + c8 * 8;
+    float m[8], f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base)), m);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<long>(W) * C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<long>(W) * C + C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    *reinterpret_cast<uint4*>(y + ((n * Ho + oy) * Wo + ox) * C + c8 * 8) = pack8(m);
+  }
+}
+
+__global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, int B,
+                                      int H, int W, int C, __nv_bfloat16* __restrict__ gs,
+                                      const __nv_bfloat16* __restrict__ mask_src, const float* __restrict__ cs,
+                                      float slope, __nv_bfloat16* __restrict__ gs2) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  const long total = static_cast<long>(B) * Ho * Wo * C8;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c8 = i % C8;
+    const int ox = (i / C8) % Wo;
+    const int oy = (i / (static_cast<long>(C8) * Wo)) % Ho;
+    const long n = i / (static_cast<long>(C8) * Wo * Ho);
+    const long off[4] = {0, C, static_cast<long>(W) * C, static_cast<long>(W) * C + C};
+    const long base = ((n * H + 2 * oy) * W + 2 * ox) * C + c8 * 8;
+    float v[4][8], g[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + off[k])), v[k]);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gy + ((n * Ho + oy) * Wo + ox) * C + c8 * 8)), g);
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // first maximum in (dy,dx) row-major order, like ATen's max_pool2d
+      int a = 0; float m = v[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) if (v[k][j] > m) { m = v[k][j]; a = k; }
+      arg[j] = a;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = arg[j] == k ? g[j] : 0.f;
+      if (gs) *reinterpret_cast<uint4*>(gs + base + off[k]) = pack8(o);
+      if (gs2) {
+        float mk[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(mask_src + base + off[k])), mk);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = o[j] * (mk[j] > 0.f ? 1.f : slope);
+          if (cs) t *= cs[n * C + c8 * 8 + j];
+          o[j] = t;
+        }
+        *reinterpret_cast<uint4*>(gs2 + base + off[k]) = pack8(o);
+      }
+    }
+  }
+}
+
+inline int grid_for(long total, int block, int cap_mult = 8) {
+  long g = (total + block - 1) / block;
+  const long cap = static_cast<long>(sm_count()) * cap_mult;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+}  // namespace fd
+
+using namespace fd;
+
+extern "C" int fd_pack_conv3x3(const float* w, int n_layers, int C, fd_bf16* w_fwd, fd_bf16* w_dgrad, void* stream) {
+  if (!w || n_layers <= 0 || C <= 0 || (!w_fwd && !w_dgrad)) return FD_EINVAL;
+  const long total = static_cast<long>(n_layers) * 9 * C * C;
+  pack_conv3x3_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, n_layers, C, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, float* dw, void* stream) {
+  if (!dw_packed || !dw || n_layers <= 0 || C <= 0) return FD_EINVAL;
+  const long total = static_cast<long>(n_layers) * 9 * C * C;
+  unpack_wgrad3x3_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, C, dw);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const float* bias, int B, int Cin, int Hin,
+                           int Win, int C, int K, int stride, int pad, fd_bf16* y, void* stream) {
+  if (!x || !w || !bias || !y || B <= 0) return FD_EINVAL;
+  if (C % 64 != 0) return FD_EUNSUPPORTED;
+  const int Ho = (Hin + 2 * pad - K) / stride + 1, Wo = (Win + 2 * pad - K) / stride + 1;
+  const int KK = Cin * K * K, pitch = (Wo - 1) * stride + K + 1;
+  const size_t smem = (static_cast<size_t>(KK) * C + static_cast<size_t>(Cin) * K * pitch) * sizeof(float);
+  if (smem > 227 * 1024) return FD_EUNSUPPORTED;
+  const int grid = min(B * Ho, sm_count());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (x_is_u8) {
+    e = cudaFuncSetAttribute(stem_fwd_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    stem_fwd_kernel<uint8_t><<<grid, kStemThreads, smem, st>>>(static_cast<const uint8_t*>(x), w, bias, B, Cin, Hin, Win,
+                                                               C, K, stride, pad, Ho, Wo,
+                                                               reinterpret_cast<__nv_bfloat16*>(y));
+  } else {
+    e = cudaFuncSetAttribute(stem_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    stem_fwd_kernel<float><<<grid, kStemThreads, smem, st>>>(static_cast<const float*>(x), w, bias, B, Cin, Hin, Win, C,
+                                                             K, stride, pad, Ho, Wo,
+                                                             reinterpret_cast<__nv_bfloat16*>(y));
+  }
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C,
+                             int K, int stride, int pad, float* dw, float* dbias, void* stream) {
+  if (!x || !g || !dw || B <= 0) return FD_EINVAL;
+  const int KK = Cin * K * K;
+  if (C % 64 != 0 || KK > 16 * kStemKPT) return FD_EUNSUPPORTED;
+  const int Ho = (Hin + 2 * pad - K) / stride + 1, Wo = (Win + 2 * pad - K) / stride + 1;
+  const int pitch = (Wo - 1) * stride + K + 1;
+  const size_t smem = (static_cast<size_t>(Wo) * C + static_cast<size_t>(Cin) * K * pitch) * sizeof(float);
+  if (smem > 227 * 1024) return FD_EUNSUPPORTED;
+  const int grid = min(B * Ho, sm_count());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (x_is_u8) {
+    e = cudaFuncSetAttribute(stem_wgrad_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    stem_wgrad_kernel<uint8_t><<<grid, kStemThreads, smem, st>>>(static_cast<const uint8_t*>(x),
+                                                                 reinterpret_cast<const __nv_bfloat16*>(g), B, Cin, Hin,
+                                                                 Win, C, K, stride, pad, Ho, Wo, dw, dbias);
+  } else {
+    e = cudaFuncSetAttribute(stem_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    stem_wgrad_kernel<float><<<grid, kStemThreads, smem, st>>>(static_cast<const float*>(x),
+                                                               reinterpret_cast<const __nv_bfloat16*>(g), B, Cin, Hin,
+                                                               Win, C, K, stride, pad, Ho, Wo, dw, dbias);
+  }
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* bias, int B, int H,
+                           int W, int C, int K, int pad, float* y, void* stream) {
+  if (!x || !w || !bias || !y || B <= 0) return FD_EINVAL;
+  if ((H * W * C) % 8 != 0) return FD_EUNSUPPORTED;
+  const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
+  if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
+  const size_t smem = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>(H) * W * C * 2;
+  if (smem > 227 * 1024) return FD_EUNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  head_fwd_kernel<<<dim3(B, kHeadSplit), kHeadThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, bias, B, H, W, C, K, pad, Ho, Wo, y);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* y, const float* dy,
+                           int B, int H, int W, int C, int K, int pad, fd_bf16* dx, const fd_bf16* mask_src,
+                           const float* chan_scale2, float slope, fd_bf16* dx2, float* dw, float* dbias, void* stream) {
+  if (!x || !w || !y || !dy || !dw || !dbias || B <= 0) return FD_EINVAL;
+  if ((dx2 != nullptr) != (mask_src != nullptr)) return FD_EINVAL;
+  if ((H * W * C) % 8 != 0 || kHeadThreads % C != 0) return FD_EUNSUPPORTED;
+  const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
+  if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
+  const size_t smem = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>((5 * Ho * Wo + 3) & ~3) * 4 +
+                      static_cast<size_t>(H) * W * C * 2;
+  if (smem > 227 * 1024) return FD_EUNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  head_bwd_kernel<<<min(B, sm_count()), kHeadThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, y, dy, B, H, W, C, K, pad, Ho, Wo,
+      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(mask_src), chan_scale2, slope,
+      reinterpret_cast<__nv_bfloat16*>(dx2), dw, dbias);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, void* stream) {
+  if (!x || !y || B <= 0) return FD_EINVAL;
+  if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
+  const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2x2_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int H, int W, int C, fd_bf16* gs,
+                                 const fd_bf16* mask_src, const float* chan_scale, float slope, fd_bf16* gs2,
+                                 void* stream) {
+  if (!x || !gy || (!gs && !gs2) || B <= 0) return FD_EINVAL;
+  if ((gs2 != nullptr) != (mask_src != nullptr)) return FD_EINVAL;
+  if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
+  const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2x2_bwd_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gy), B, H, W, C,
+      reinterpret_cast<__nv_bfloat16*>(gs), reinterpret_cast<const __nv_bfloat16*>(mask_src), chan_scale, slope,
+      reinterpret_cast<__nv_bfloat16*>(gs2));
+  count_launch();
+  return launch_status();
+}

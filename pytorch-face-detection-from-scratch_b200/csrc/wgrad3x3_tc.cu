@@ -1,0 +1,250 @@
+// Weight gradient of the 3x3 / stride 1 / pad 1, 64 -> 64 convolution on tcgen05.
+//
+// Replaces the weight-gradient half of autograd's conv2d backward for
+// models/PoolResnet.py:35,37 of the reference.
+//
+//   dW[t][ci][co] = sum_pixels  xpad[p + off_t][ci] * g[p][co],   off_t = ky*Wp + kx
+//
+// is a GEMM whose reduction (K) dimension is the pixel index.  Both operands live in shared memory
+// exactly as TMA delivers NHWC tiles -- one pixel per 128-byte row, channels contiguous -- which is
+// the "MN-major" operand form of tcgen05.mma, so no transposes are needed:
+//   A (M side) = the halo input tile, start address shifted by off_t rows; two taps are stacked
+//                into one M=128 instruction by using the shift difference as the distance between the
+//                two 64-channel atoms (descriptor LBO),
+//   B (N side) = the gradient tile (64 output channels).
+// The halo column of g (x == W) is zero-filled by TMA and the K padding rows are kept zero, so
+// junk rows contribute nothing.  5 stacked-tap MMAs per 16 pixels; the fp32 accumulators
+// (5 x 64 TMEM columns) live in TMEM across ALL tiles of the persistent CTA and are reduced
+// into global memory once per CTA with vector fp32 reductions.  The bias gradient (column sums
+// of g) is accumulated by the otherwise idle epilogue warps from the same smem tiles.
+#include "fd_host.h"
+#include "fd_ptx.cuh"
+
+namespace fd {
+namespace {
+
+constexpr int kC = 64;
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+
+struct WgradParams {
+  int B, H, W, R, Wp, tiles_per_img, num_tiles, ksteps;
+  uint32_t x_bytes, g_bytes;          // bytes delivered by the two TMA boxes
+  uint32_t x_buf_bytes, g_buf_bytes;  // reserved per stage (multiples of 1024)
+  float* dw;                          // [9][ci][co] fp32, accumulated
+  float* dbias;                       // [co] fp32, accumulated (nullable)
+  int flags;
+};
+
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
+                   const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const uint32_t stage_bytes = p.x_buf_bytes + p.g_buf_bytes;
+  uint8_t* sStage = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint64_t* full = bars + 0;      // [2]
+  uint64_t* empty = bars + 2;     // [2]
+  uint64_t* acc_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* sBias = reinterpret_cast<float*>(bars + 6);  // [128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // K-padding rows of g and the over-read tail of x are never written by TMA and must stay zero.
+  for (uint32_t i = threadIdx.x * 16u; i < 2 * stage_bytes; i += kThreads * 16u)
+    *reinterpret_cast<uint4*>(sStage + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_g);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1 + 4);  // MMA commit + the four column-sum warps
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // contiguous chunk of tiles for this CTA
+  const int per = (p.num_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_begin = blockIdx.x * per;
+  const int tile_end = min(p.num_tiles, tile_begin + per);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        const int n = tile / p.tiles_per_img;
+        const int h0 = (tile - n * p.tiles_per_img) * p.R;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, p.x_bytes + p.g_bytes);
+        tma_load_4d(sStage + s * stage_bytes, &tm_x, full + s, 0, -1, h0 - 1, n);
+        tma_load_4d(sStage + s * stage_bytes + p.x_buf_bytes, &tm_g, full + s, 0, 0, h0, n);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, kC, 1, 1);  // both operands MN-major
+    int it = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(full + s, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t x_addr = smem_u32(sStage + s * stage_bytes);
+        const uint32_t g_addr = x_addr + p.x_buf_bytes;
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          const uint64_t bd = make_sdesc_sw128(g_addr + ks * 2048, 1024, 1024, 0);
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            // tap pairs (0,1) (2,3) (4,5) (6,7) (7,8): the last pair recomputes tap 7 (dropped in the
+            // epilogue) so that every instruction is a regular two-atom M=128 MMA
+            const int t0 = (j < 4) ? 2 * j : 7, t1 = t0 + 1;
+            const int off0 = (t0 / 3) * p.Wp + (t0 % 3);
+            const int off1 = (t1 / 3) * p.Wp + (t1 % 3);
+            const uint64_t ad =
+                make_sdesc_sw128(x_addr + static_cast<uint32_t>((off0 + ks * 16) * 128),
+                                 static_cast<uint32_t>((off1 - off0) * 128), 1024, 0);
+            umma_bf16(tmem_base + j * kC, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty + s);
+        if (tile + 1 == tile_end) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue warps: (1) bias gradient from the smem g tiles while the MMAs run
+    const int et = threadIdx.x - 64;      // 0..127
+    const int c = et & 63, rpar = et >> 6;
+    float bsum = 0.f;
+    int it = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(full + s, ph);
+      if (p.dbias) {
+        const uint8_t* g = sStage + s * stage_bytes + p.x_buf_bytes;
+        const int rows = p.R * p.Wp;
+        for (int r = rpar; r < rows; r += 2) {
+          const uint32_t off = r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1));
+          bsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(g + off));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+    // (2) drain the accumulators
+    if (tile_begin < tile_end) {
+      const int q = warp & 3;
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const int row = q * 32 + lane;
+      const int tsel = row >> 6, ci = row & 63;
+#pragma unroll 1
+      for (int j = 0; j < 5; ++j) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(j * kC + half * 32),
+                             acc);
+          tmem_ld_wait();
+          const int tap = ((j < 4) ? 2 * j : 7) + tsel;
+          if (j < 4 || tsel == 1) {
+            float* dst = p.dw + (static_cast<size_t>(tap) * kC + ci) * kC + half * 32;
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]),
+                         __uint_as_float(acc[4 * v + 2]), __uint_as_float(acc[4 * v + 3]));
+          }
+        }
+      }
+      if (p.dbias) {
+        sBias[et] = bsum;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et < 64) atomicAdd(p.dbias + et, sBias[et] + sBias[et + 64]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace
+}  // namespace fd
+
+extern "C" int fd_conv3x3_wgrad(const fd_bf16* x, const fd_bf16* g, int B, int H, int W, int C, float* dw_packed,
+                                float* dbias, int flags, void* stream) {
+  using namespace fd;
+  if (!x || !g || !dw_packed || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
+  if (C != kC || W + 1 > 256) return FD_EUNSUPPORTED;
+  const int nsm = sm_count();
+  const int Wp = W + 1;
+  const size_t smem_cap = 227 * 1024;
+
+  // rows per tile: as many as fit two stages of (x halo tile + g tile) in shared memory
+  int bestR = 0;
+  for (int R = 1; R <= H && R + 2 <= 256; ++R) {
+    const int ksteps = (R * Wp + 15) / 16;
+    const size_t xb = (static_cast<size_t>(ksteps * 16 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024;
+    const size_t gb = (static_cast<size_t>(ksteps * 16) * 128 + 1023) / 1024 * 1024;
+    if (2 * (xb + gb) + 1024 + 1024 > smem_cap) break;
+    bestR = R;
+  }
+  if (bestR == 0) return FD_EUNSUPPORTED;
+  // do not make tiles so tall that the SMs run out of tiles
+  while (bestR > 1 && static_cast<long>(B) * ((H + bestR - 1) / bestR) < nsm &&
+         static_cast<long>(B) * ((H + bestR - 2) / (bestR - 1)) <= 2L * nsm)
+    --bestR;
+
+  WgradParams p;
+  p.B = B; p.H = H; p.W = W; p.R = bestR; p.Wp = Wp;
+  p.tiles_per_img = (H + bestR - 1) / bestR;
+  p.num_tiles = B * p.tiles_per_img;
+  p.ksteps = (bestR * Wp + 15) / 16;
+  p.x_bytes = static_cast<uint32_t>((bestR + 2) * Wp * 128);
+  p.g_bytes = static_cast<uint32_t>(bestR * Wp * 128);
+  p.x_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.ksteps * 16 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024);
+  p.g_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.ksteps * 16) * 128 + 1023) / 1024 * 1024);
+  p.dw = dw_packed; p.dbias = dbias; p.flags = flags;
+
+  CUtensorMap tm_x, tm_g;
+  int rc = make_tmap_nhwc_bf16(&tm_x, x, B, H, W, C, Wp, bestR + 2);
+  if (rc != FD_OK) return rc;
+  rc = make_tmap_nhwc_bf16(&tm_g, g, B, H, W, C, Wp, bestR);
+  if (rc != FD_OK) return rc;
+
+  const size_t smem = 2 * static_cast<size_t>(p.x_buf_bytes + p.g_buf_bytes) + 1024 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  // one contiguous chunk of tiles per CTA; few CTAs when there are few tiles so that the
+  // per-CTA reduction into global memory (36864 fp32 adds) stays amortised
+  int grid = p.num_tiles < nsm ? p.num_tiles : nsm;
+  if (p.num_tiles < 2 * nsm) grid = (p.num_tiles + 3) / 4;
+  if (grid < 1) grid = 1;
+  wgrad3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_x, tm_g, p);
+  count_launch();
+  return launch_status();
+}

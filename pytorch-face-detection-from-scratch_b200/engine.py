@@ -1,0 +1,270 @@
+"""Execution engine of the residual grid backbones (PoolResnet / Resnet of the reference).
+
+Owns the device-resident state the C-ABI kernels work on -- one flat fp32 parameter buffer, one
+flat fp32 gradient buffer (the all-reduce unit for data parallelism), bf16 packed weights, and
+per-batch-size activation plans in NHWC bf16 -- and issues the kernel sequence of a forward pass
+and of the backward pass.  PyTorch is used for memory, streams and CUDA graphs only.
+
+Reference call sites replaced: models/PoolResnet.py:93-105 (forward), the autograd backward of the
+same graph, and models/ModelMeta.py:141,173-176 (train step = forward + summed YoloLoss + backward).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class _Block:
+    __slots__ = ("H", "W", "pool", "a", "b", "s", "out", "G", "gs", "gp1", "gp2")
+
+
+class _Plan:
+    """Activation / gradient buffers for one (batch size, train?) combination."""
+
+    def __init__(self, eng: "BackboneEngine", B: int, train: bool, device):
+        F = eng.F
+        self.B, self.train = B, train
+
+        def bf(h, w):
+            return torch.empty((B, h, w, F), dtype=BF16, device=device)
+
+        H, W = eng.H0, eng.W0
+        self.act0 = bf(H, W)
+        self.blocks: List[_Block] = []
+        for k in range(eng.num_blocks):
+            blk = _Block()
+            blk.H, blk.W, blk.pool = H, W, eng.pools[k]
+            blk.a = bf(H, W)
+            blk.s = bf(H, W)
+            blk.b = bf(H, W) if train else None
+            if blk.pool:
+                H, W = H // 2, W // 2
+                blk.out = bf(H, W)
+            else:
+                blk.out = blk.s
+            if train:
+                blk.G = bf(H, W)
+                blk.gs = bf(blk.H, blk.W) if blk.pool else None
+                blk.gp1 = bf(blk.H, blk.W)
+                blk.gp2 = bf(blk.H, blk.W)
+            self.blocks.append(blk)
+        self.y = torch.empty((B, 5, eng.So_h, eng.So_w), dtype=F32, device=device)
+        if train:
+            self.g_stem = bf(eng.H0, eng.W0)
+            self.loss = torch.empty((B,), dtype=F32, device=device)
+            self.dy = torch.empty_like(self.y)
+        self.drop = None       # [num_blocks+1, B, F] fp32 Dropout2d multipliers (train mode only)
+        self.x = None          # input of the last forward (needed by the stem wgrad)
+
+
+class BackboneEngine:
+    def __init__(self, filters: int, in_ch: int, in_h: int, in_w: int, num_blocks: int, stem_k: int, stem_s: int,
+                 stem_pad: int, head_k: int, head_pad: int, pool_rule: Callable[[int], bool], slope: float = 0.2,
+                 block_drop: float = 0.25, head_drop: float = 0.5):
+        if filters != 64:
+            raise NotImplementedError("the tcgen05 3x3 kernels are instantiated for 64 channels "
+                                      "(the reference's 'medium' checkpoints); got filters=%d" % filters)
+        self.F, self.in_ch, self.in_h, self.in_w = filters, in_ch, in_h, in_w
+        self.num_blocks, self.slope = num_blocks, slope
+        self.stem_k, self.stem_s, self.stem_pad = stem_k, stem_s, stem_pad
+        self.head_k, self.head_pad = head_k, head_pad
+        self.block_drop, self.head_drop = block_drop, head_drop
+        self.H0 = (in_h + 2 * stem_pad - stem_k) // stem_s + 1
+        self.W0 = (in_w + 2 * stem_pad - stem_k) // stem_s + 1
+        self.pools = []
+        H, W = self.H0, self.W0
+        for _ in range(num_blocks):
+            p = bool(pool_rule(H))
+            self.pools.append(p)
+            if p:
+                H, W = H // 2, W // 2
+        self.Hl, self.Wl = H, W
+        self.So_h = H + 2 * head_pad - head_k + 1
+        self.So_w = W + 2 * head_pad - head_k + 1
+        # flat parameter layout (fp32)
+        F = filters
+        self.sections = [
+            ("conv1.weight", (F, in_ch, stem_k, stem_k)), ("conv1.bias", (F,)),
+            ("w3", (2 * num_blocks, F, F, 3, 3)), ("b3", (2 * num_blocks, F)),
+            ("out.weight", (5, F, head_k, head_k)), ("out.bias", (5,)),
+        ]
+        self.offsets, off = {}, 0
+        for name, shape in self.sections:
+            n = 1
+            for s in shape:
+                n *= s
+            self.offsets[name] = (off, n, shape)
+            off += (n + 3) // 4 * 4          # keep every section 16-byte aligned
+        self.n_flat = off
+        self.device = None
+        self.pflat = self.gflat = self.dwp = self.w_fwd = self.w_dgrad = None
+        self.plans: Dict[tuple, _Plan] = {}
+        self.weights_dirty = True
+
+    # ------------------------------------------------------------------ parameters
+    def param_names(self) -> List[str]:
+        names = ["conv1.weight", "conv1.bias"]
+        for k in range(self.num_blocks):
+            for c in ("conv1", "conv2"):
+                names += [f"residual_blocks.{k}.{c}.weight", f"residual_blocks.{k}.{c}.bias"]
+        return names + ["out.weight", "out.bias"]
+
+    def _view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        if name.startswith("residual_blocks."):
+            _, k, c, kind = name.split(".")
+            layer = 2 * int(k) + (0 if c == "conv1" else 1)
+            off, n, shape = self.offsets["w3" if kind == "weight" else "b3"]
+            return flat[off:off + n].view(shape)[layer]
+        off, n, shape = self.offsets[name]
+        return flat[off:off + n].view(shape)
+
+    def section(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        off, n, shape = self.offsets[name]
+        return flat[off:off + n].view(shape)
+
+    def _ensure_device(self, device):
+        if self.device == device and self.pflat is not None:
+            return
+        self.device = device
+        self.pflat = torch.zeros(self.n_flat, dtype=F32, device=device)
+        self.gflat = torch.zeros(self.n_flat, dtype=F32, device=device)
+        n3 = 2 * self.num_blocks * 9 * self.F * self.F
+        self.dwp = torch.zeros(n3, dtype=F32, device=device)
+        self.w_fwd = torch.empty(n3, dtype=BF16, device=device)
+        self.w_dgrad = torch.empty(n3, dtype=BF16, device=device)
+        self.plans.clear()
+
+    def bind(self, params: Dict[str, torch.nn.Parameter]):
+        """Make every nn.Parameter a view of the flat buffer (values are preserved).  Cheap when
+        nothing moved; re-flattens after ``.cuda()`` / ``.to()`` replaced the parameter storages."""
+        dev = params["conv1.weight"].device
+        if dev.type != "cuda":
+            raise RuntimeError("the fd_b200 backbone runs on CUDA only (no CPU fallback): call model.cuda()")
+        self._ensure_device(dev)
+        for name in self.param_names():
+            p = params[name]
+            v = self._view(self.pflat, name)
+            if p.data_ptr() != v.data_ptr():
+                with torch.no_grad():
+                    v.copy_(p.data.to(device=dev, dtype=F32))
+                p.data = v
+                self.weights_dirty = True
+
+    def grad_view(self, name: str) -> torch.Tensor:
+        return self._view(self.gflat, name)
+
+    # ------------------------------------------------------------------ plans
+    def plan(self, B: int, train: bool) -> _Plan:
+        key = (B, train)
+        if key not in self.plans:
+            self.plans[key] = _Plan(self, B, train, self.device)
+        return self.plans[key]
+
+    def pack_weights(self):
+        L = 2 * self.num_blocks
+        ops.pack_conv3x3(self.section(self.pflat, "w3"), self.w_fwd.view(L, 9, self.F, self.F),
+                         self.w_dgrad.view(L, 9, self.F, self.F))
+        self.weights_dirty = False
+
+    def _wf(self, layer):
+        n = 9 * self.F * self.F
+        return self.w_fwd[layer * n:(layer + 1) * n]
+
+    def _wd(self, layer):
+        n = 9 * self.F * self.F
+        return self.w_dgrad[layer * n:(layer + 1) * n]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, train: bool, dropout: bool = False, repack: bool = True) -> _Plan:
+        """x: [B,in_ch,H,W] fp32 in [0,1] (or uint8: /255 fused).  Returns the plan; plan.y is the
+        sigmoid head [B,5,So,So] fp32.  ``dropout`` draws Dropout2d masks (train mode of the reference)."""
+        B = x.shape[0]
+        pl = self.plan(B, train)
+        if repack or self.weights_dirty:
+            self.pack_weights()
+        if dropout:
+            keep_b, keep_h = 1.0 - self.block_drop, 1.0 - self.head_drop
+            r = torch.rand((self.num_blocks + 1, B, self.F), device=x.device)
+            scale = torch.empty_like(r)
+            scale[:-1] = (r[:-1] < keep_b).float() / keep_b
+            scale[-1] = (r[-1] < keep_h).float() / keep_h
+            pl.drop = scale
+        else:
+            pl.drop = None
+        self.run_forward(pl, x)
+        return pl
+
+    def run_forward(self, pl: _Plan, x: torch.Tensor):
+        pl.x = x
+        sb3 = self.section(self.pflat, "b3")
+        ops.stem_fwd(x, self.section(self.pflat, "conv1.weight"), self.section(self.pflat, "conv1.bias"), pl.act0,
+                     self.stem_s, self.stem_pad)
+        cur = pl.act0
+        for k, blk in enumerate(pl.blocks):
+            cs = pl.drop[k] if pl.drop is not None else None
+            ops.conv3x3(cur, self._wf(2 * k), bias=sb3[2 * k], slope=self.slope, lrelu=True, out=blk.a)
+            ops.conv3x3(blk.a, self._wf(2 * k + 1), bias=sb3[2 * k + 1], slope=self.slope, lrelu=True,
+                        chan_scale=cs, residual=cur, aux_out=blk.b, out=blk.s)
+            if blk.pool:
+                ops.maxpool2x2_fwd(blk.s, blk.out)
+            cur = blk.out
+        cs = pl.drop[self.num_blocks] if pl.drop is not None else None
+        ops.head_fwd(cur, cs, self.section(self.pflat, "out.weight"), self.section(self.pflat, "out.bias"), pl.y,
+                     self.head_pad)
+
+    # ------------------------------------------------------------------ backward
+    def run_backward(self, pl: _Plan, dy: torch.Tensor):
+        """dy: gradient w.r.t. plan.y.  Fills self.gflat (overwrites)."""
+        assert pl.train
+        nb = self.num_blocks
+        self.gflat.zero_()
+        self.dwp.zero_()
+        gb3 = self.section(self.gflat, "b3")
+        n3 = 9 * self.F * self.F
+        drop = pl.drop
+        last = pl.blocks[nb - 1]
+        ops.head_bwd(last.out, drop[nb] if drop is not None else None, self.section(self.pflat, "out.weight"), pl.y,
+                     dy, self.head_pad, last.G, None if last.pool else last.b,
+                     None if (last.pool or drop is None) else drop[nb - 1], self.slope,
+                     None if last.pool else last.gp2, self.section(self.gflat, "out.weight"),
+                     self.section(self.gflat, "out.bias"))
+        for k in range(nb - 1, -1, -1):
+            blk = pl.blocks[k]
+            x_in = pl.act0 if k == 0 else pl.blocks[k - 1].out
+            if blk.pool:
+                ops.maxpool2x2_bwd(blk.s, blk.G, blk.gs, blk.b, drop[k] if drop is not None else None, self.slope,
+                                   blk.gp2)
+                GS = blk.gs
+            else:
+                GS = blk.G
+            ops.conv3x3_wgrad(blk.a, blk.gp2, self.dwp[(2 * k + 1) * n3:(2 * k + 2) * n3], gb3[2 * k + 1])
+            ops.conv3x3(blk.gp2, self._wd(2 * k + 1), slope=self.slope, mask_src=blk.a, out2=blk.gp1)
+            ops.conv3x3_wgrad(x_in, blk.gp1, self.dwp[(2 * k) * n3:(2 * k + 1) * n3], gb3[2 * k])
+            if k > 0:
+                prev = pl.blocks[k - 1]
+                if prev.pool:
+                    ops.conv3x3(blk.gp1, self._wd(2 * k), slope=self.slope, residual=GS, out=prev.G)
+                else:
+                    ops.conv3x3(blk.gp1, self._wd(2 * k), slope=self.slope, residual=GS, out=prev.G,
+                                mask_src=prev.b, chan_scale2=drop[k - 1] if drop is not None else None,
+                                out2=prev.gp2)
+            else:
+                ops.conv3x3(blk.gp1, self._wd(0), slope=self.slope, residual=GS, out=pl.g_stem)
+                ops.stem_wgrad(pl.x, pl.g_stem, self.section(self.gflat, "conv1.weight"),
+                               self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad)
+        ops.unpack_wgrad3x3(self.dwp.view(2 * nb, 9, self.F, self.F), self.section(self.gflat, "w3"))
+
+    # ------------------------------------------------------------------ fused train step
+    def train_step(self, x: torch.Tensor, gt: torch.Tensor, dropout: bool = True) -> _Plan:
+        """forward -> per-image YoloLoss (+ its gradient, same kernel) -> backward.
+        Afterwards plan.loss holds the per-image losses and self.gflat the gradient of their SUM
+        (models/ModelMeta.py:173-176,215: the reference sums, it does not average)."""
+        pl = self.forward(x, train=True, dropout=dropout)
+        ops.yolo_loss(pl.y, gt, pl.loss, None, pl.dy)
+        self.run_backward(pl, pl.dy)
+        return pl

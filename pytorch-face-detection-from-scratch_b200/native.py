@@ -1,0 +1,89 @@
+"""ctypes binding of libfd_b200.so (the C ABI declared in include/fd_b200.h).
+
+There is deliberately NO fallback: if the library is missing or a tensor is not a contiguous
+CUDA tensor the call raises.  The product path never imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfd_b200.so")
+
+_c = ctypes
+_P, _I, _F, _D = _c.c_void_p, _c.c_int, _c.c_float, _c.c_double
+
+# name -> argtypes, in the order of include/fd_b200.h (restype is int unless noted)
+SIGNATURES = {
+    "fd_version": [],
+    "fd_launch_count": [],
+    "fd_error_string": [_I],
+    "fd_conv3x3": [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "fd_conv3x3_wgrad": [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
+    "fd_pack_conv3x3": [_P, _I, _I, _P, _P, _P],
+    "fd_unpack_wgrad3x3": [_P, _I, _I, _P, _P],
+    "fd_stem_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fd_stem_wgrad": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "fd_head_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fd_head_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
+    "fd_maxpool2x2_fwd": [_P, _I, _I, _I, _I, _P, _P],
+    "fd_maxpool2x2_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P],
+    "fd_yolo_loss": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "fd_decode_nms": [_P, _I, _I, _I, _F, _D, _I, _I, _I, _P, _P, _P, _P],
+    "fd_grid_encode": [_P, _P, _I, _I, _I, _I, _P, _P],
+}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libfd_b200.so (once).  Raises NativeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or python pytorch-face-detection-from-scratch_b200/csrc/build.py). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError here == header / library out of sync
+            fn.argtypes = args
+            fn.restype = _I
+        L.fd_launch_count.restype = _c.c_longlong
+        L.fd_error_string.restype = _c.c_char_p
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().fd_error_string(rc).decode()
+        raise NativeError(f"{what} failed: {msg} (code {rc})")
+
+
+def launch_count() -> int:
+    return int(lib().fd_launch_count())
+
+
+def dptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("fd_b200 kernels take CUDA tensors only (no CPU fallback); got a CPU tensor")
+    if not t.is_contiguous():
+        raise NativeError("fd_b200 kernels take contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise NativeError(f"expected dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def cur_stream():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,101 @@
+"""Typed Python wrappers over the C ABI -- one function per entry point of include/fd_b200.h.
+Tensors are caller-allocated; nothing here allocates or synchronises."""
+from __future__ import annotations
+
+import torch
+
+from .native import check, cur_stream, dptr, lib
+
+BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
+
+EPI_LRELU = 1
+DBG_BASE_OFFSET = 256
+DBG_PLAN_B = 512
+
+
+def conv3x3(x, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_scale=None, residual=None, aux_out=None,
+            out=None, mask_src=None, chan_scale2=None, out2=None, flags=0):
+    B, H, W, C = x.shape
+    fl = flags | (EPI_LRELU if lrelu else 0)
+    check(lib().fd_conv3x3(dptr(x, BF16), dptr(w_packed, BF16), B, H, W, C, dptr(bias, F32), slope,
+                           dptr(chan_scale, F32), dptr(residual, BF16), dptr(aux_out, BF16), dptr(out, BF16),
+                           dptr(mask_src, BF16), dptr(chan_scale2, F32), dptr(out2, BF16), fl, cur_stream()),
+          "fd_conv3x3")
+
+
+def conv3x3_wgrad(x, g, dw_packed, dbias, flags=0):
+    B, H, W, C = x.shape
+    check(lib().fd_conv3x3_wgrad(dptr(x, BF16), dptr(g, BF16), B, H, W, C, dptr(dw_packed, F32), dptr(dbias, F32),
+                                 flags, cur_stream()), "fd_conv3x3_wgrad")
+
+
+def pack_conv3x3(w, w_fwd, w_dgrad):
+    n, C = (w.shape[0], w.shape[1]) if w.dim() == 5 else (1, w.shape[0])
+    check(lib().fd_pack_conv3x3(dptr(w, F32), n, C, dptr(w_fwd, BF16), dptr(w_dgrad, BF16), cur_stream()),
+          "fd_pack_conv3x3")
+
+
+def unpack_wgrad3x3(dw_packed, dw):
+    n, C = (dw.shape[0], dw.shape[1]) if dw.dim() == 5 else (1, dw.shape[0])
+    check(lib().fd_unpack_wgrad3x3(dptr(dw_packed, F32), n, C, dptr(dw, F32), cur_stream()), "fd_unpack_wgrad3x3")
+
+
+def stem_fwd(x, w, bias, y, stride, pad):
+    B, Cin, Hin, Win = x.shape
+    C, _, K, _ = w.shape
+    is_u8 = 1 if x.dtype == U8 else 0
+    check(lib().fd_stem_fwd(dptr(x, U8 if is_u8 else F32), is_u8, dptr(w, F32), dptr(bias, F32), B, Cin, Hin, Win, C, K,
+                            stride, pad, dptr(y, BF16), cur_stream()), "fd_stem_fwd")
+
+
+def stem_wgrad(x, g, dw, dbias, stride, pad):
+    B, Cin, Hin, Win = x.shape
+    C, _, K, _ = dw.shape
+    is_u8 = 1 if x.dtype == U8 else 0
+    check(lib().fd_stem_wgrad(dptr(x, U8 if is_u8 else F32), is_u8, dptr(g, BF16), B, Cin, Hin, Win, C, K, stride, pad,
+                              dptr(dw, F32), dptr(dbias, F32), cur_stream()), "fd_stem_wgrad")
+
+
+def head_fwd(x, chan_scale, w, bias, y, pad):
+    B, H, W, C = x.shape
+    K = w.shape[2]
+    check(lib().fd_head_fwd(dptr(x, BF16), dptr(chan_scale, F32), dptr(w, F32), dptr(bias, F32), B, H, W, C, K, pad,
+                            dptr(y, F32), cur_stream()), "fd_head_fwd")
+
+
+def head_bwd(x, chan_scale, w, y, dy, pad, dx, mask_src, chan_scale2, slope, dx2, dw, dbias):
+    B, H, W, C = x.shape
+    K = w.shape[2]
+    check(lib().fd_head_bwd(dptr(x, BF16), dptr(chan_scale, F32), dptr(w, F32), dptr(y, F32), dptr(dy, F32), B, H, W, C,
+                            K, pad, dptr(dx, BF16), dptr(mask_src, BF16), dptr(chan_scale2, F32), slope,
+                            dptr(dx2, BF16), dptr(dw, F32), dptr(dbias, F32), cur_stream()), "fd_head_bwd")
+
+
+def maxpool2x2_fwd(x, y):
+    B, H, W, C = x.shape
+    check(lib().fd_maxpool2x2_fwd(dptr(x, BF16), B, H, W, C, dptr(y, BF16), cur_stream()), "fd_maxpool2x2_fwd")
+
+
+def maxpool2x2_bwd(x, gy, gs, mask_src, chan_scale, slope, gs2):
+    B, H, W, C = x.shape
+    check(lib().fd_maxpool2x2_bwd(dptr(x, BF16), dptr(gy, BF16), B, H, W, C, dptr(gs, BF16), dptr(mask_src, BF16),
+                                  dptr(chan_scale, F32), slope, dptr(gs2, BF16), cur_stream()), "fd_maxpool2x2_bwd")
+
+
+def yolo_loss(pred, gt, loss, dloss_scale=None, dpred=None):
+    B, _, S1, S2 = pred.shape
+    check(lib().fd_yolo_loss(dptr(pred, F32), dptr(gt, F32), B, S1, S2, dptr(loss, F32), dptr(dloss_scale, F32),
+                             dptr(dpred, F32), cur_stream()), "fd_yolo_loss")
+
+
+def decode_nms(pred, p_thr, iou_thr, width, height, num_of_patches, out_boxes, out_cell, out_count):
+    B, _, S1, S2 = pred.shape
+    check(lib().fd_decode_nms(dptr(pred, F32), B, S1, S2, float(p_thr), float(iou_thr), int(width), int(height),
+                              int(num_of_patches), dptr(out_boxes, F32), dptr(out_cell, I32), dptr(out_count, I32),
+                              cur_stream()), "fd_decode_nms")
+
+
+def grid_encode(boxes, offsets, S, width, height, out):
+    B = out.shape[0]
+    check(lib().fd_grid_encode(dptr(boxes, F32), dptr(offsets, I32), B, S, int(width), int(height), dptr(out, F32),
+                               cur_stream()), "fd_grid_encode")

@@ -1,0 +1,162 @@
+"""GPU parity of the backbone kernels through the C ABI against torch fp32 on the same bf16-rounded
+inputs.  Tolerances: outputs are stored as bf16 (rel. 2^-8 per element), accumulation is fp32, so
+max-abs error <= 1e-2 * max|ref| and relative L2 error <= 4e-3 are required."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import fd, rel_err, require_cuda
+
+pytestmark = pytest.mark.gpu
+C = 64
+
+
+def _close(got, ref, what, rel=4e-3, mx=1e-2):
+    r = rel_err(got.float(), ref)
+    m = (got.float() - ref).abs().max().item()
+    assert r <= rel, f"{what}: rel L2 {r}"
+    assert m <= mx * max(1.0, ref.abs().max().item()), f"{what}: max abs {m}"
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 15, 15), (3, 30, 30), (2, 60, 60), (1, 7, 9), (5, 16, 8)])
+def test_conv3x3_forward_epilogues(B, H, W):
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(B * 100 + H)
+    dev = "cuda"
+    x = torch.randn(B, H, W, C, device=dev).bfloat16()
+    res = torch.randn(B, H, W, C, device=dev).bfloat16()
+    msk = torch.randn(B, H, W, C, device=dev).bfloat16()
+    w = torch.randn(C, C, 3, 3, device=dev) * 0.05
+    bias = torch.randn(C, device=dev)
+    cs = (torch.rand(B, C, device=dev) < 0.75).float() / 0.75
+    cs2 = (torch.rand(B, C, device=dev) < 0.75).float() / 0.75
+    wf = torch.empty(9, C, C, dtype=torch.bfloat16, device=dev); wd = torch.empty_like(wf)
+    ops.pack_conv3x3(w, wf, wd)
+    wq = w.bfloat16().float()
+    xn = x.float().permute(0, 3, 1, 2)
+    nhwc = lambda t: t.permute(0, 2, 3, 1)
+    # (1) conv + bias + lrelu
+    out = torch.zeros_like(x)
+    ops.conv3x3(x, wf, bias=bias, lrelu=True, out=out)
+    ref1 = nhwc(F.leaky_relu(F.conv2d(xn, wq, bias, padding=1), 0.2))
+    _close(out, ref1, "conv+bias+lrelu")
+    # (2) conv2 of the block: + dropout multiplier, aux (pre-residual), residual add
+    aux = torch.zeros_like(x); out = torch.zeros_like(x)
+    ops.conv3x3(x, wf, bias=bias, lrelu=True, chan_scale=cs, residual=res, aux_out=aux, out=out)
+    refb = ref1 * cs[:, None, None, :]
+    _close(aux, refb, "aux_out")
+    _close(out, refb + res.float(), "residual out")
+    # (3) dgrad packing + masked second output (backward chain)
+    out = torch.zeros_like(x); out2 = torch.zeros_like(x)
+    ops.conv3x3(x, wd, residual=res, out=out, mask_src=msk, chan_scale2=cs2, out2=out2)
+    xin = torch.zeros(B, C, H, W, device=dev, requires_grad=True)
+    (gref,) = torch.autograd.grad(F.conv2d(xin, wq, None, padding=1), xin, xn)
+    G = nhwc(gref) + res.float()
+    _close(out, G, "dgrad + residual")
+    G2 = G * cs2[:, None, None, :] * torch.where(msk.float() > 0, 1.0, 0.2)
+    _close(out2, G2, "masked out2", rel=6e-3)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 15, 15), (3, 30, 30), (2, 60, 60), (1, 7, 9), (64, 15, 15)])
+def test_conv3x3_wgrad(B, H, W):
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(B + H)
+    dev = "cuda"
+    x = torch.randn(B, H, W, C, device=dev).bfloat16()
+    g = (torch.randn(B, H, W, C, device=dev) * 0.1).bfloat16()
+    dwp = torch.zeros(9, C, C, device=dev); db = torch.zeros(C, device=dev)
+    ops.conv3x3_wgrad(x, g, dwp, db)
+    dw = torch.empty(C, C, 3, 3, device=dev)
+    ops.unpack_wgrad3x3(dwp, dw)
+    wz = torch.zeros(C, C, 3, 3, device=dev, requires_grad=True)
+    (dref,) = torch.autograd.grad(F.conv2d(x.float().permute(0, 3, 1, 2), wz, None, padding=1), wz,
+                                  g.float().permute(0, 3, 1, 2))
+    assert rel_err(dw, dref) <= 1e-4            # fp32 accumulate of exact bf16 products
+    assert rel_err(db, g.float().sum(dim=(0, 1, 2))) <= 1e-4
+    # accumulate semantics: a second call doubles
+    ops.conv3x3_wgrad(x, g, dwp, db)
+    ops.unpack_wgrad3x3(dwp, dw)
+    assert rel_err(dw, 2 * dref) <= 1e-4
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_stem_fwd_wgrad(u8):
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(5)
+    dev = "cuda"
+    B = 3
+    if u8:
+        x = torch.randint(0, 256, (B, 3, 480, 480), dtype=torch.uint8, device=dev)
+        xf = x.float() / 255.0
+    else:
+        x = torch.rand(B, 3, 480, 480, device=dev)
+        xf = x
+    w = (torch.randn(C, 3, 10, 10, device=dev) * 0.05).requires_grad_(True)
+    b = torch.randn(C, device=dev).requires_grad_(True)
+    y = torch.zeros(B, 60, 60, C, dtype=torch.bfloat16, device=dev)
+    ops.stem_fwd(x, w.detach(), b.detach(), y, 8, 2)
+    ref = F.conv2d(xf, w, b, stride=8, padding=2)
+    _close(y, ref.detach().permute(0, 2, 3, 1), "stem fwd")
+    g = (torch.randn(B, 60, 60, C, device=dev) * 0.1).bfloat16()
+    dw = torch.zeros(C, 3, 10, 10, device=dev); dbias = torch.zeros(C, device=dev)
+    ops.stem_wgrad(x, g, dw, dbias, 8, 2)
+    ref.backward(g.float().permute(0, 3, 1, 2))
+    assert rel_err(dw, w.grad) <= 1e-4 and rel_err(dbias, b.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("H,K,pad", [(15, 6, 0), (15, 3, 1)])
+def test_head_fwd_bwd(H, K, pad):
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(9)
+    dev = "cuda"
+    B = 5
+    x = torch.randn(B, H, H, C, device=dev).bfloat16()
+    cs = (torch.rand(B, C, device=dev) < 0.5).float() / 0.5
+    cs2 = (torch.rand(B, C, device=dev) < 0.75).float() / 0.75
+    msk = torch.randn(B, H, H, C, device=dev).bfloat16()
+    w = (torch.randn(5, C, K, K, device=dev) * 0.03).requires_grad_(True)
+    b = torch.randn(5, device=dev).requires_grad_(True)
+    Ho = H + 2 * pad - K + 1
+    y = torch.zeros(B, 5, Ho, Ho, device=dev)
+    ops.head_fwd(x, cs, w.detach(), b.detach(), y, pad)
+    xin = (x.float().permute(0, 3, 1, 2)).requires_grad_(True)
+    ref = torch.sigmoid(F.conv2d(xin * cs[:, :, None, None], w, b, padding=pad))
+    assert (y - ref).abs().max().item() <= 2e-5
+    dy = torch.randn_like(y)
+    dx = torch.zeros_like(x); dx2 = torch.zeros_like(x)
+    dw = torch.zeros_like(w); dbias = torch.zeros_like(b)
+    ops.head_bwd(x, cs, w.detach(), y, dy, pad, dx, msk, cs2, 0.2, dx2, dw, dbias)
+    ref.backward(dy)
+    gx = xin.grad.permute(0, 2, 3, 1)
+    _close(dx, gx, "head dx")
+    _close(dx2, gx * cs2[:, None, None, :] * torch.where(msk.float() > 0, 1.0, 0.2), "head dx2", rel=6e-3)
+    assert rel_err(dw, w.grad) <= 1e-4 and rel_err(dbias, b.grad) <= 1e-4
+
+
+def test_maxpool_fwd_bwd_first_max_tie_rule():
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(1)
+    dev = "cuda"
+    B, H = 3, 30
+    x = torch.randn(B, H, H, C, device=dev).bfloat16()
+    x[:, ::2, ::2] = x[:, 1::2, 1::2]            # many exact ties inside windows
+    y = torch.zeros(B, H // 2, H // 2, C, dtype=torch.bfloat16, device=dev)
+    ops.maxpool2x2_fwd(x, y)
+    xin = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.max_pool2d(xin, 2)
+    assert torch.equal(y.float(), ref.detach().permute(0, 2, 3, 1))
+    gy = torch.randn(B, H // 2, H // 2, C, device=dev).bfloat16()
+    msk = torch.randn(B, H, H, C, device=dev).bfloat16()
+    cs = (torch.rand(B, C, device=dev) < 0.75).float() / 0.75
+    gs = torch.zeros_like(x); gs2 = torch.zeros_like(x)
+    ops.maxpool2x2_bwd(x, gy, gs, msk, cs, 0.2, gs2)
+    ref.backward(gy.float().permute(0, 3, 1, 2))
+    gref = xin.grad.permute(0, 2, 3, 1)
+    assert torch.equal(gs.float(), gref)
+    want2 = (gref * cs[:, None, None, :] * torch.where(msk.float() > 0, 1.0, 0.2)).bfloat16()
+    assert rel_err(gs2.float(), want2.float()) <= 4e-3

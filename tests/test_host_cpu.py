@@ -1,0 +1,94 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the module mirrors keep the reference's interface, and there is NO CPU fallback."""
+import importlib
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+fd = importlib.import_module("pytorch-face-detection-from-scratch_b200")
+
+
+def test_library_exports_every_header_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    hdr = open(os.path.join(ROOT, "include", "fd_b200.h")).read()
+    declared = set(re.findall(r"FD_API\s+[\w\s\*]+?\b(fd_\w+)\s*\(", hdr))
+    assert len(declared) >= 16
+    lib = fd.native.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in fd_b200.h but not exported"
+    assert declared == set(fd.native.SIGNATURES), "ctypes table out of sync with the header"
+    assert lib.fd_version() >= 100
+    assert lib.fd_error_string(-2).decode() == "unsupported shape"
+
+
+def test_sass_uses_tcgen05_and_tma():
+    """The conv kernels must be real Blackwell kernels: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM."""
+    import shutil, subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", fd.native.LIB_PATH], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnem in sass, mnem
+
+
+def test_reference_interface_and_state_dict_keys():
+    fd.install_dropin()
+    from models.PoolResnet import PoolResnet          # reference import paths
+    from models.Resnet import Resnet
+    from models import BaseModel, ModelMeta
+    from losses.YoloLoss import yolo_loss
+    from datasets.utils import ReduceBoundingBoxes
+    m = PoolResnet(filters=64, input_shape=(3, 480, 480), num_of_patches=10)
+    assert isinstance(m, BaseModel) and isinstance(m, torch.nn.Module)
+    assert sum(p.numel() for p in m.parameters()) == 769349
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "official_medium.npz"))
+    ref_keys = [k[3:] for k in g.files if k.startswith("sd.")]
+    assert list(m.state_dict().keys()) == ref_keys
+    m.load_state_dict({k: torch.from_numpy(g["sd." + k]) for k in ref_keys}, strict=True)
+    assert m.engine.pools == [True, True] + [False] * 8 and (m.engine.So_h, m.engine.So_w) == (10, 10)
+    r = Resnet(filters=64, input_shape=(3, 480, 480), num_of_patches=15)
+    assert sum(p.numel() for p in r.parameters()) == 743237
+    assert r.engine.pools == [True] * 4 + [False] * 6 and r.engine.So_h == 15
+    assert isinstance(m.reduce_bounding_boxes, ReduceBoundingBoxes)
+    assert callable(yolo_loss) and ModelMeta(m).model is m
+    with pytest.raises(AssertionError):
+        PoolResnet(filters=64, input_shape=(3, 480, 480), num_of_patches=7)   # BaseModel.py:23-26
+
+
+def test_no_cpu_fallback():
+    from importlib import import_module
+    PoolResnet = import_module("pytorch-face-detection-from-scratch_b200.models.PoolResnet").PoolResnet
+    m = PoolResnet(filters=64, input_shape=(3, 480, 480), num_of_patches=10)
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 3, 480, 480))
+    L = import_module("pytorch-face-detection-from-scratch_b200.losses.YoloLoss")
+    with pytest.raises(RuntimeError):
+        L.yolo_loss(torch.rand(5, 10, 10), torch.rand(5, 10, 10))
+    RB = import_module("pytorch-face-detection-from-scratch_b200.datasets.utils").ReduceBoundingBoxes
+    with pytest.raises(RuntimeError):
+        RB(0.5, 0.5, (3, 480, 480), 10)(torch.rand(5, 10, 10))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pytorch-face-detection-from-scratch_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                for line in open(os.path.join(dp, f)):
+                    if re.match(r"\s*(import|from)\s", line):
+                        assert "oracle" not in line, (os.path.join(dp, f), line)
+
+
+def test_flat_parameter_layout():
+    eng = fd.engine.BackboneEngine(64, 3, 480, 480, 10, 10, 8, 2, 6, 0, lambda h: h > 20)
+    total = sum(n for _, n, _ in eng.offsets.values())
+    assert total == 769349
+    for name, (off, n, shape) in eng.offsets.items():
+        assert off % 4 == 0
+    assert len(eng.param_names()) == 44
