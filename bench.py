@@ -1,0 +1,339 @@
+"""Benchmark of the detection hot path (BASELINE.json metric: images/sec of the train step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode train|infer]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic WIDERFace-shaped input:
+PoolResnet-medium (F=64, S=10, 10 blocks) forward + summed YoloLoss + backward (models/ModelMeta.py:141,
+173-176 of the reference), batch 64 per GPU, <=100 boxes/image, Dropout2d active (model.train()), and for
+N>1 the all-reduce of the flat fp32 gradient buffer over NCCL.  Weak scaling: per-GPU work is fixed.
+
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with the inputs resident in HBM;
+`e2e` runs the same step through the public API from pinned HOST buffers (H2D of images + targets and
+D2H of the loss inside the timed region).  `--impl reference` times the reference's CPU path
+(the oracle port, torch fp32 on all host cores) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "pytorch-face-detection-from-scratch_b200"
+
+B_PER_GPU = 64
+S = 10
+FLOPS_FWD_PER_IMG = 1069.4e6          # SURVEY 8d, PoolResnet F=64
+
+
+def synth_batch(B, seed_img=0, seed_box=1):
+    """x = rand(B,3,480,480); K~U{1..100} integer boxes per image, log-uniform sizes."""
+    from tests.util import synth_boxes
+    gx = torch.Generator().manual_seed(seed_img)
+    x = torch.rand(B, 3, 480, 480, generator=gx)
+    gb = torch.Generator().manual_seed(seed_box)
+    boxes = [synth_boxes(gb, 1, 100) for _ in range(B)]
+    return x, boxes
+
+
+def seeded_params():
+    from tests.util import seeded_poolresnet_params
+    return seeded_poolresnet_params(64, seed=2)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
+    def summary(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return
+    from oracle import backbone_oracle as bo
+    from oracle import yolo_oracle as yo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = 16                                             # bounded sample of the batch-64 workload per step
+    x, boxes = synth_batch(Bs)
+    gt = torch.stack([torch.from_numpy(yo.grid_encode(b.numpy(), S, 480, 480)) for b in boxes])
+    p = seeded_params()
+    for _ in range(max(1, min(args.warmup, 2))):
+        bo.train_step(x, gt, p, S)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        bo.train_step(x, gt, p, S)
+    dt = time.perf_counter() - t0
+    v = Bs * steps / dt
+    sample = f"{steps} steps x {Bs} images (of the {B_PER_GPU}-image batch), eval-mode dropout, torch {torch.__version__} CPU fp32"
+    line = {"impl": "reference", "metric": "train_images_per_sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "PoolResnet-medium (filters=64, S=10, 10 blocks, 480x480) train step: forward + summed "
+                        "YoloLoss + backward" + (" + NCCL grad all-reduce" if n > 1 else ""),
+            "global_batch": B_PER_GPU * n, "batch_per_gpu": B_PER_GPU, "boxes_per_image": "1..100",
+            "parallelism": f"dp{n}", "dropout": "train-mode Dropout2d",
+            "l2": "per-step working set (177 MB fp32 images + ~1 GB bf16 activations) exceeds the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    fd = importlib.import_module(PKG)
+    import __graft_entry__ as ge
+    if rank == 0 or not os.path.exists(fd.native.LIB_PATH):
+        ge.build()
+    par = fd.parallel
+    rank, world, local = par.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+
+    # ---------------- model + synthetic data (each rank its own shard: different seeds)
+    torch.manual_seed(2)
+    model = fd.models.PoolResnet.PoolResnet(filters=64, input_shape=(3, 480, 480), num_of_patches=S).to(dev).train()
+    eng = model.engine
+    eng.bind(dict(model.named_parameters()))
+    par.broadcast_flat(eng.pflat)
+    x_cpu, boxes = synth_batch(B_PER_GPU, seed_img=rank * 2, seed_box=rank * 2 + 1)
+    gt = fd.datasets.WIDERFace.dataset.convert_bbx_to_feature_map_batch(boxes, S, (480, 480), device=dev)
+    x = x_cpu.to(dev)
+    B = B_PER_GPU
+
+    def eager_step():
+        pl = eng.train_step(x, gt, dropout=True)
+        par.allreduce_grads(eng.gflat)
+        return pl
+
+    graph = None
+    if args.no_graph:
+        n0 = fd.native.launch_count()
+        pl = eager_step()
+        per_step_launches = fd.native.launch_count() - n0
+        step = eager_step
+    else:
+        graph, pl, per_step_launches = eng.capture_train_step(x, gt, dropout=True)
+
+        def step():
+            graph.replay()
+            par.allreduce_grads(eng.gflat)
+            return pl
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = par.max_over_ranks(e0.elapsed_time(e1), dev)
+    loss_val = float(pl.loss.sum().item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---------------- e2e: public API, pinned host inputs, H2D + D2H inside the timed region
+    xh = x_cpu.pin_memory()
+    gth = gt.cpu().pin_memory()
+    copy_stream = torch.cuda.Stream()
+    xbuf = [torch.empty_like(x), torch.empty_like(x)]
+    gbuf = [torch.empty_like(gt), torch.empty_like(gt)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            xbuf[i].copy_(xh, non_blocking=True)
+            gbuf[i].copy_(gth, non_blocking=True)
+            ready[i].record(copy_stream)
+
+    def e2e_run(nsteps):
+        prefetch(0)
+        for it in range(nsteps):
+            i = it & 1
+            torch.cuda.current_stream().wait_event(ready[i])
+            if it + 1 < nsteps:
+                prefetch(i ^ 1)            # overlap the next batch's H2D with this step's compute
+            loss = model.train_step(xbuf[i], gbuf[i])       # the call a user makes (eager, no graph)
+            par.allreduce_grads(eng.gflat)
+            _ = loss.item()                # D2H of the step's result
+
+    e2e_run(3)
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(5, min(args.steps, 20))
+    e2e_run(n_e2e)
+    barrier()
+    e2e_s = par.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = world * B * n_e2e / e2e_s
+
+    # ---------------- roofline of the dominant kernel (conv3x3_tc: 40 of the ~72 launches, ~85 % of the FLOPs)
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        roof = conv_roofline(fd, eng, pl, dev)
+        if not args.no_cpu_baseline:
+            cpu_base = cpu_baseline()
+    if rank == 0:
+        line = {"metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(world), "loss": loss_val,
+                "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": xh.numel() * 4 + gth.numel() * 4,
+                        "d2h_bytes_per_step": 4, "steps": n_e2e,
+                        "note": "fp32 images from pinned host memory (the reference's training input type), "
+                                "double-buffered H2D overlapped with compute; eager public API model.train_step"},
+                "gpu_launches": per_step_launches * args.steps,
+                "launches_per_step": per_step_launches, "cuda_graph": graph is not None,
+                "achieved_tflops_step": 3 * FLOPS_FWD_PER_IMG * B / (ms / args.steps * 1e-3) / 1e12,
+                "roofline": roof, "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def conv_roofline(fd, eng, pl, dev):
+    """Time every conv3x3_tc launch of one forward+backward with CUDA events on the launching stream."""
+    ops = fd.ops
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = peaks.get("bf16_tflops_sustained")
+    which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    if peak is None:
+        peak, which = 1590.0 * 1409.2 / 1661.6, "fallback"
+    records = []
+    orig = ops.conv3x3
+
+    def timed(x, w, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig(x, w, **kw)
+        b.record()
+        records.append((tuple(x.shape), a, b))
+
+    ops.conv3x3 = timed
+    try:
+        for _ in range(3):
+            records.clear()
+            eng.run_forward(pl, pl.x)
+            eng.run_backward(pl, pl.dy)
+        torch.cuda.synchronize()
+    finally:
+        ops.conv3x3 = orig
+    tot_ms = tot_fl = 0.0
+    by_shape = {}
+    for shp, a, b in records:
+        ms = a.elapsed_time(b)
+        fl = 2.0 * shp[0] * shp[1] * shp[2] * 64 * 64 * 9
+        tot_ms += ms; tot_fl += fl
+        d = by_shape.setdefault(f"{shp[1]}x{shp[2]}", [0, 0.0, 0.0])
+        d[0] += 1; d[1] += ms; d[2] += fl
+    achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+    big = by_shape.get("60x60")
+    return {"kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, fwd + dgrad launches of one step)",
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": which, "traffic": None, "launches": len(records),
+            "avg_launch_us": tot_ms * 1e3 / len(records),
+            "by_shape": {k: {"launches": v[0], "avg_us": v[1] * 1e3 / v[0], "tflops": v[2] / (v[1] * 1e-3) / 1e12}
+                         for k, v in by_shape.items()},
+            "largest_shape_frac": (big[2] / (big[1] * 1e-3) / 1e12 / peak) if big else None}
+
+
+def cpu_baseline():
+    from oracle import backbone_oracle as bo
+    from oracle import yolo_oracle as yo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = 16
+    x, boxes = synth_batch(Bs)
+    gt = torch.stack([torch.from_numpy(yo.grid_encode(b.numpy(), S, 480, 480)) for b in boxes])
+    p = seeded_params()
+    bo.train_step(x, gt, p, S)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 40):
+        bo.train_step(x, gt, p, S)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": Bs * n / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} train steps x {Bs} images of the same synthetic workload (torch CPU fp32 oracle port)"}
+
+
+if __name__ == "__main__":
+    main()

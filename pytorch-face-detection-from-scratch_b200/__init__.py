@@ -27,7 +27,5 @@ def install_dropin():
         sys.modules[name] = importlib.import_module(f"{__name__}.{name}")
 
 
-def __getattr__(name):
-    if name in ("models", "losses", "datasets", "engine", "parallel"):
-        return importlib.import_module(f"{__name__}.{name}")
-    raise AttributeError(name)
+for _m in _DROPIN + ["engine", "parallel"]:
+    importlib.import_module(f"{__name__}.{_m}")

@@ -268,3 +268,22 @@ class BackboneEngine:
         ops.yolo_loss(pl.y, gt, pl.loss, None, pl.dy)
         self.run_backward(pl, pl.dy)
         return pl
+
+    # ------------------------------------------------------------------ CUDA graph of the train step
+    def capture_train_step(self, x_static: torch.Tensor, gt_static: torch.Tensor, dropout: bool = True):
+        """Capture forward + loss + backward on fixed input buffers into one CUDA graph (kills the
+        ~70 launch gaps and all host-side descriptor encoding).  Returns (graph, plan, launches_per_step)."""
+        from .native import launch_count
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.train_step(x_static, gt_static, dropout)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = launch_count()
+        with torch.cuda.graph(graph):
+            pl = self.train_step(x_static, gt_static, dropout)
+        return graph, pl, launch_count() - n0
