@@ -26,4 +26,10 @@ int make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, int rows, int cols, int b
 
 int sm_count();
 
+// tcgen05 stem (stem_tc.cu); FD_EUNSUPPORTED means "not the stride-8 stem shape, use the generic kernel"
+int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, int B, int Cin, int Hin, int Win,
+                int C, int K, int stride, int pad, fd_bf16* y, cudaStream_t st);
+int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C, int K,
+                  int stride, int pad, float* dw, float* dbias, cudaStream_t st);
+
 }  // namespace fd

@@ -442,6 +442,11 @@ extern "C" int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const flo
                            int Win, int C, int K, int stride, int pad, fd_bf16* y, void* stream) {
   if (!x || !w || !bias || !y || B <= 0) return FD_EINVAL;
   if (C % 64 != 0) return FD_EUNSUPPORTED;
+  {
+    const int rc = stem_fwd_tc(x, x_is_u8, w, bias, B, Cin, Hin, Win, C, K, stride, pad, y,
+                               static_cast<cudaStream_t>(stream));
+    if (rc != FD_EUNSUPPORTED) return rc;      // tensor-core stem handled it (or failed for real)
+  }
   const int Ho = (Hin + 2 * pad - K) / stride + 1, Wo = (Win + 2 * pad - K) / stride + 1;
   const int KK = Cin * K * K, pitch = (Wo - 1) * stride + K + 1;
   const size_t smem = (static_cast<size_t>(KK) * C + static_cast<size_t>(Cin) * K * pitch) * sizeof(float);
@@ -469,6 +474,11 @@ extern "C" int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const flo
 extern "C" int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C,
                              int K, int stride, int pad, float* dw, float* dbias, void* stream) {
   if (!x || !g || !dw || B <= 0) return FD_EINVAL;
+  {
+    const int rc = stem_wgrad_tc(x, x_is_u8, g, B, Cin, Hin, Win, C, K, stride, pad, dw, dbias,
+                                 static_cast<cudaStream_t>(stream));
+    if (rc != FD_EUNSUPPORTED) return rc;
+  }
   const int KK = Cin * K * K;
   if (C % 64 != 0 || KK > 16 * kStemKPT) return FD_EUNSUPPORTED;
   const int Ho = (Hin + 2 * pad - K) / stride + 1, Wo = (Win + 2 * pad - K) / stride + 1;
