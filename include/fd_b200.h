@@ -79,6 +79,14 @@ FD_API int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, i
 FD_API int fd_conv3x3_wgrad(const fd_bf16* x, const fd_bf16* g, int B, int H, int W, int C,
                      float* dw_packed, float* dbias, int flags, void* stream);
 
+/* The same for `nprob` independent convolutions of identical shape in ONE launch: x and g hold
+ * nprob stacked [B,H,W,C] tensors; problem q accumulates into dw_packed + q*dw_stride and
+ * dbias + q*dbias_stride (strides in elements).  Used for the run of equal-shape residual blocks,
+ * whose weight gradients are mutually independent once the dgrad chain has finished. */
+FD_API int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int nprob, int B, int H, int W, int C,
+                           float* dw_packed, long dw_stride, float* dbias, long dbias_stride, int flags,
+                           void* stream);
+
 /* w: [n_layers][C][C][3][3] fp32 (torch layout, PoolResnet.py:15-28) ->
  *   w_fwd  [n_layers][9][co][ci] bf16,  w_dgrad [n_layers][9][ci][co] bf16 with flipped taps
  * (either output may be NULL). */

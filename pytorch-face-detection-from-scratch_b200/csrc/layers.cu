@@ -325,6 +325,132 @@ head_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
   }
 }
 
+// Register-tiled head backward for small maps (W, Wo <= 16, C = 64): each thread owns a whole map
+// row (dx) or a whole kernel row (dw) in registers, so the inner loops are FMA-bound instead of
+// shared-memory-bound.  K and PAD are compile-time so that every register index is static.
+template <int K, int PAD>
+__global__ void __launch_bounds__(kHeadThreads)
+head_bwd_small_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ w,
+                      const float* __restrict__ y, const float* __restrict__ dy, int B, int H, int W, int Ho, int Wo,
+                      __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ mask_src,
+                      const float* __restrict__ cs2, float slope, __nv_bfloat16* __restrict__ dx2,
+                      float* __restrict__ dw, float* __restrict__ dbias) {
+  constexpr int C = 64, KK = K * K, MW = 16;
+  extern __shared__ float sm[];
+  float* sW = sm;                         // [KK][5][C]
+  float* sDz = sW + KK * 5 * C;           // [5][Ho][MW] (rows padded to 16, zero filled)
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sDz + 5 * Ho * MW);  // [H*W][C]
+  for (int i = threadIdx.x; i < KK * 5 * C; i += blockDim.x) {
+    const int c = i % C, o = (i / C) % 5, t = i / (5 * C);
+    sW[i] = w[(static_cast<size_t>(o) * C + c) * KK + t];
+  }
+  for (int n = blockIdx.x; n < B; n += gridDim.x) {
+    __syncthreads();
+    const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * H * W * C);
+    for (int i = threadIdx.x; i < H * W * C / 8; i += blockDim.x) reinterpret_cast<uint4*>(sX)[i] = __ldg(xs + i);
+    for (int i = threadIdx.x; i < 5 * Ho * MW; i += blockDim.x) {
+      const int ox = i % MW, r = i / MW;     // r = o*Ho + oy
+      float v = 0.f;
+      if (ox < Wo) {
+        const size_t gi = static_cast<size_t>(n) * 5 * Ho * Wo + static_cast<size_t>(r) * Wo + ox;
+        const float yv = y[gi];
+        v = dy[gi] * yv * (1.f - yv);
+      }
+      sDz[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      float t = 0.f;
+      for (int i = 0; i < Ho * MW; ++i) t += sDz[threadIdx.x * Ho * MW + i];
+      atomicAdd(dbias + threadIdx.x, t);
+    }
+    // ---- dx: task = (c, iy), MW outputs in registers
+    for (int task = threadIdx.x; task < C * H; task += blockDim.x) {
+      const int c = task % C, iy = task / C;
+      float acc[MW];
+#pragma unroll
+      for (int i = 0; i < MW; ++i) acc[i] = 0.f;
+      for (int o = 0; o < 5; ++o) {
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const int oy = iy - ky + PAD;
+          if (oy < 0 || oy >= Ho) continue;
+          float dz[MW];
+          const float4* dzr = reinterpret_cast<const float4*>(sDz + (o * Ho + oy) * MW);
+#pragma unroll
+          for (int i = 0; i < MW / 4; ++i) {
+            const float4 t = dzr[i];
+            dz[4 * i] = t.x; dz[4 * i + 1] = t.y; dz[4 * i + 2] = t.z; dz[4 * i + 3] = t.w;
+          }
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const float wv = sW[((ky * K + kx) * 5 + o) * C + c];
+#pragma unroll
+            for (int ix = 0; ix < MW; ++ix) {
+              constexpr int dummy = 0; (void)dummy;
+              const int ox = ix - kx + PAD;
+              if (ox >= 0 && ox < MW) acc[ix] = fmaf(dz[ox], wv, acc[ix]);   // dz is zero past Wo
+            }
+          }
+        }
+      }
+      const float s = cs ? cs[n * C + c] : 1.f;
+      const float s2 = cs2 ? cs2[n * C + c] : 1.f;
+#pragma unroll
+      for (int ix = 0; ix < MW; ++ix) {
+        if (ix < W) {
+          const size_t gi = (static_cast<size_t>(n) * H * W + iy * W + ix) * C + c;
+          const float v = acc[ix] * s;
+          if (dx) dx[gi] = __float2bfloat16(v);
+          if (dx2) {
+            const float m = __bfloat162float(mask_src[gi]) > 0.f ? 1.f : slope;
+            dx2[gi] = __float2bfloat16(v * m * s2);
+          }
+        }
+      }
+    }
+    // ---- dw: task = (c, ky), K x 5 accumulators in registers
+    for (int task = threadIdx.x; task < C * K; task += blockDim.x) {
+      const int c = task % C, ky = task / C;
+      float acc[K][5];
+#pragma unroll
+      for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int o = 0; o < 5; ++o) acc[a][o] = 0.f;
+      for (int oy = 0; oy < Ho; ++oy) {
+        const int iy = oy + ky - PAD;
+        if (iy < 0 || iy >= H) continue;
+        float xr[MW + K];            // xr[j] = x[iy][j - PAD]
+#pragma unroll
+        for (int j = 0; j < MW + K; ++j) {
+          const int ix = j - PAD;
+          xr[j] = (ix >= 0 && ix < W) ? __bfloat162float(sX[(iy * W + ix) * C + c]) : 0.f;
+        }
+#pragma unroll
+        for (int o = 0; o < 5; ++o) {
+          float dz[MW];
+          const float4* dzr = reinterpret_cast<const float4*>(sDz + (o * Ho + oy) * MW);
+#pragma unroll
+          for (int i = 0; i < MW / 4; ++i) {
+            const float4 t = dzr[i];
+            dz[4 * i] = t.x; dz[4 * i + 1] = t.y; dz[4 * i + 2] = t.z; dz[4 * i + 3] = t.w;
+          }
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int ox = 0; ox < MW; ++ox) acc[kx][o] = fmaf(xr[ox + kx], dz[ox], acc[kx][o]);
+        }
+      }
+      const float s = cs ? cs[n * C + c] : 1.f;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+        for (int o = 0; o < 5; ++o)
+          atomicAdd(dw + (static_cast<size_t>(o) * C + c) * KK + ky * K + kx, acc[kx][o] * s);
+    }
+  }
+}
+
 // ============================================================================ maxpool 2x2
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
@@ -529,6 +655,19 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
   if ((H * W * C) % 8 != 0 || kHeadThreads % C != 0) return FD_EUNSUPPORTED;
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
+  if (C == 64 && W <= 16 && Wo <= 16 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
+    const size_t sm_small = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>(5) * Ho * 16 * 4 +
+                            static_cast<size_t>(H) * W * C * 2;
+    auto kern = (K == 6) ? head_bwd_small_kernel<6, 0> : head_bwd_small_kernel<3, 1>;
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small);
+    if (e2 != cudaSuccess) return (int)e2;
+    kern<<<min(B, 2 * sm_count()), kHeadThreads, sm_small, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, y, dy, B, H, W, Ho, Wo,
+        reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(mask_src), chan_scale2, slope,
+        reinterpret_cast<__nv_bfloat16*>(dx2), dw, dbias);
+    count_launch();
+    return launch_status();
+  }
   const size_t smem = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>((5 * Ho * Wo + 3) & ~3) * 4 +
                       static_cast<size_t>(H) * W * C * 2;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;

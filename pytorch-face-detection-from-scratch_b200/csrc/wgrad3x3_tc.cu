@@ -34,6 +34,10 @@ struct WgradParams {
   float* dw;                          // [9][ci][co] fp32, accumulated
   float* dbias;                       // [co] fp32, accumulated (nullable)
   int flags;
+  // multi-problem launch: x / g hold `nprob` stacked [B,H,W,C] tensors; problem q accumulates into
+  // dw + q * dw_stride and dbias + q * dbias_stride.  A CTA never straddles two problems.
+  int nprob, tiles_per_prob, ctas_per_prob, per;
+  long dw_stride, dbias_stride;
 };
 
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
@@ -84,10 +88,13 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // contiguous chunk of tiles for this CTA
-  const int per = (p.num_tiles + gridDim.x - 1) / gridDim.x;
-  const int tile_begin = blockIdx.x * per;
-  const int tile_end = min(p.num_tiles, tile_begin + per);
+  // contiguous chunk of tiles (of ONE problem) for this CTA
+  const int prob = blockIdx.x / p.ctas_per_prob;
+  const int chunk = blockIdx.x - prob * p.ctas_per_prob;
+  const int tile_begin = prob * p.tiles_per_prob + min(p.tiles_per_prob, chunk * p.per);
+  const int tile_end = prob * p.tiles_per_prob + min(p.tiles_per_prob, (chunk + 1) * p.per);
+  float* const dw_out = p.dw + prob * p.dw_stride;
+  float* const dbias_out = p.dbias ? p.dbias + prob * p.dbias_stride : nullptr;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -170,7 +177,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           tmem_ld_wait();
           const int tap = ((j < 4) ? 2 * j : 7) + tsel;
           if (j < 4 || tsel == 1) {
-            float* dst = p.dw + (static_cast<size_t>(tap) * kC + ci) * kC + half * 32;
+            float* dst = dw_out + (static_cast<size_t>(tap) * kC + ci) * kC + half * 32;
 #pragma unroll
             for (int v = 0; v < 8; ++v)
               red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]),
@@ -181,7 +188,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       if (p.dbias) {
         sBias[et] = bsum;
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et < 64) atomicAdd(p.dbias + et, sBias[et] + sBias[et + 64]);
+        if (et < 64) atomicAdd(dbias_out + et, sBias[et] + sBias[et + 64]);
       }
     }
   }
@@ -194,16 +201,17 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 }  // namespace
 }  // namespace fd
 
-extern "C" int fd_conv3x3_wgrad(const fd_bf16* x, const fd_bf16* g, int B, int H, int W, int C, float* dw_packed,
-                                float* dbias, int flags, void* stream) {
+extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int nprob, int B, int H, int W, int C,
+                                      float* dw_packed, long dw_stride, float* dbias, long dbias_stride, int flags,
+                                      void* stream) {
   using namespace fd;
-  if (!x || !g || !dw_packed || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
+  if (!x || !g || !dw_packed || nprob <= 0 || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
   if (C != kC || W + 1 > 256) return FD_EUNSUPPORTED;
   const int nsm = sm_count();
   const int Wp = W + 1;
   const size_t smem_cap = 227 * 1024;
 
-  // rows per tile: as many as fit two stages of (x halo tile + g tile) in shared memory
+  // rows per tile: as many as fit two stages of (x halo tile + g tile) in shared memory ...
   int bestR = 0;
   for (int R = 1; R <= H && R + 2 <= 256; ++R) {
     const int ksteps = (R * Wp + 15) / 16;
@@ -213,38 +221,49 @@ extern "C" int fd_conv3x3_wgrad(const fd_bf16* x, const fd_bf16* g, int B, int H
     bestR = R;
   }
   if (bestR == 0) return FD_EUNSUPPORTED;
-  // do not make tiles so tall that the SMs run out of tiles
-  while (bestR > 1 && static_cast<long>(B) * ((H + bestR - 1) / bestR) < nsm &&
-         static_cast<long>(B) * ((H + bestR - 2) / (bestR - 1)) <= 2L * nsm)
-    --bestR;
+  // ... but not so tall that the SMs run out of tiles
+  auto total_tiles = [&](int R) { return static_cast<long>(nprob) * B * ((H + R - 1) / R); };
+  while (bestR > 1 && total_tiles(bestR) < nsm && total_tiles(bestR - 1) <= 2L * nsm) --bestR;
 
   WgradParams p;
-  p.B = B; p.H = H; p.W = W; p.R = bestR; p.Wp = Wp;
+  p.B = nprob * B; p.H = H; p.W = W; p.R = bestR; p.Wp = Wp;
   p.tiles_per_img = (H + bestR - 1) / bestR;
-  p.num_tiles = B * p.tiles_per_img;
+  p.num_tiles = p.B * p.tiles_per_img;
   p.ksteps = (bestR * Wp + 15) / 16;
   p.x_bytes = static_cast<uint32_t>((bestR + 2) * Wp * 128);
   p.g_bytes = static_cast<uint32_t>(bestR * Wp * 128);
   p.x_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.ksteps * 16 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024);
   p.g_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.ksteps * 16) * 128 + 1023) / 1024 * 1024);
   p.dw = dw_packed; p.dbias = dbias; p.flags = flags;
+  p.nprob = nprob;
+  p.tiles_per_prob = B * p.tiles_per_img;
+  p.dw_stride = dw_stride; p.dbias_stride = dbias_stride;
+  // CTAs per problem: one wave over the SMs in total; few CTAs when there are few tiles so that the
+  // per-CTA reduction into global memory (36864 fp32 adds) stays amortised (>= 4 tiles per CTA)
+  int cpp = nsm / nprob;
+  if (cpp < 1) cpp = 1;
+  if (cpp > (p.tiles_per_prob + 3) / 4) cpp = (p.tiles_per_prob + 3) / 4;
+  if (cpp < 1) cpp = 1;
+  p.per = (p.tiles_per_prob + cpp - 1) / cpp;
+  p.ctas_per_prob = (p.tiles_per_prob + p.per - 1) / p.per;
 
   CUtensorMap tm_x, tm_g;
-  int rc = make_tmap_nhwc_bf16(&tm_x, x, B, H, W, C, Wp, bestR + 2);
+  int rc = make_tmap_nhwc_bf16(&tm_x, x, p.B, H, W, C, Wp, bestR + 2);
   if (rc != FD_OK) return rc;
-  rc = make_tmap_nhwc_bf16(&tm_g, g, B, H, W, C, Wp, bestR);
+  rc = make_tmap_nhwc_bf16(&tm_g, g, p.B, H, W, C, Wp, bestR);
   if (rc != FD_OK) return rc;
 
   const size_t smem = 2 * static_cast<size_t>(p.x_buf_bytes + p.g_buf_bytes) + 1024 + 1024;
   cudaError_t e = cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  // one contiguous chunk of tiles per CTA; few CTAs when there are few tiles so that the
-  // per-CTA reduction into global memory (36864 fp32 adds) stays amortised
-  int grid = p.num_tiles < nsm ? p.num_tiles : nsm;
-  if (p.num_tiles < 2 * nsm) grid = (p.num_tiles + 3) / 4;
-  if (grid < 1) grid = 1;
+  const int grid = nprob * p.ctas_per_prob;
   wgrad3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_x, tm_g, p);
   count_launch();
   return launch_status();
+}
+
+extern "C" int fd_conv3x3_wgrad(const fd_bf16* x, const fd_bf16* g, int B, int H, int W, int C, float* dw_packed,
+                                float* dbias, int flags, void* stream) {
+  return fd_conv3x3_wgrad_multi(x, g, 1, B, H, W, C, dw_packed, 0, dbias, 0, flags, stream);
 }

@@ -33,25 +33,72 @@ class _Plan:
         def bf(h, w):
             return torch.empty((B, h, w, F), dtype=BF16, device=device)
 
+        # Runs of consecutive non-pooled blocks share one shape; their tensors are allocated STACKED
+        # ([n,B,H,W,F]) so that the weight gradients of the whole run go out as one multi-problem launch.
+        self.groups = []            # (k0, k1, IN_all, A_all, GP1_all, GP2_all)
+        runs, k = [], 0
+        while k < eng.num_blocks:
+            if not eng.pools[k]:
+                k1 = k
+                while k1 + 1 < eng.num_blocks and not eng.pools[k1 + 1]:
+                    k1 += 1
+                if k1 > k:
+                    runs.append((k, k1))
+                k = k1 + 1
+            else:
+                k += 1
+        run_of = {}
+        for (k0, k1) in runs:
+            for k in range(k0, k1 + 1):
+                run_of[k] = (k0, k1)
+
+        def stack(n, h, w):
+            return torch.empty((n, B, h, w, F), dtype=BF16, device=device)
+
         H, W = eng.H0, eng.W0
-        self.act0 = bf(H, W)
+        shapes = []
+        for k in range(eng.num_blocks):
+            shapes.append((H, W))
+            if eng.pools[k]:
+                H, W = H // 2, W // 2
+        stacks = {}
+        for (k0, k1) in runs:
+            n = k1 - k0 + 1
+            h, w = shapes[k0]
+            stacks[k0] = {"IN": stack(n, h, w), "A": stack(n, h, w),
+                          "GP1": stack(n, h, w) if train else None, "GP2": stack(n, h, w) if train else None}
+            self.groups.append((k0, k1, stacks[k0]["IN"], stacks[k0]["A"], stacks[k0]["GP1"], stacks[k0]["GP2"]))
+
+        def out_buffer(k, h, w):
+            """Buffer holding the OUTPUT of block k (k = -1: the stem) = input of block k+1."""
+            nxt = k + 1
+            if nxt in run_of:
+                k0, _ = run_of[nxt]
+                return stacks[k0]["IN"][nxt - k0]
+            return bf(h, w)
+
+        H, W = eng.H0, eng.W0
+        self.act0 = out_buffer(-1, H, W)
         self.blocks: List[_Block] = []
         for k in range(eng.num_blocks):
             blk = _Block()
             blk.H, blk.W, blk.pool = H, W, eng.pools[k]
-            blk.a = bf(H, W)
-            blk.s = bf(H, W)
+            st = stacks[run_of[k][0]] if k in run_of else None
+            i = k - run_of[k][0] if k in run_of else 0
+            blk.a = st["A"][i] if st else bf(H, W)
             blk.b = bf(H, W) if train else None
             if blk.pool:
+                blk.s = bf(H, W)
                 H, W = H // 2, W // 2
-                blk.out = bf(H, W)
+                blk.out = out_buffer(k, H, W)
             else:
+                blk.s = out_buffer(k, H, W)
                 blk.out = blk.s
             if train:
                 blk.G = bf(H, W)
                 blk.gs = bf(blk.H, blk.W) if blk.pool else None
-                blk.gp1 = bf(blk.H, blk.W)
-                blk.gp2 = bf(blk.H, blk.W)
+                blk.gp1 = st["GP1"][i] if st else bf(blk.H, blk.W)
+                blk.gp2 = st["GP2"][i] if st else bf(blk.H, blk.W)
             self.blocks.append(blk)
         self.y = torch.empty((B, 5, eng.So_h, eng.So_w), dtype=F32, device=device)
         if train:
@@ -233,6 +280,11 @@ class BackboneEngine:
                      None if (last.pool or drop is None) else drop[nb - 1], self.slope,
                      None if last.pool else last.gp2, self.section(self.gflat, "out.weight"),
                      self.section(self.gflat, "out.bias"))
+        in_group = {}
+        for grp in pl.groups:
+            for k in range(grp[0], grp[1] + 1):
+                in_group[k] = grp
+        gb3_flat = gb3.reshape(-1)
         for k in range(nb - 1, -1, -1):
             blk = pl.blocks[k]
             x_in = pl.act0 if k == 0 else pl.blocks[k - 1].out
@@ -242,9 +294,12 @@ class BackboneEngine:
                 GS = blk.gs
             else:
                 GS = blk.G
-            ops.conv3x3_wgrad(blk.a, blk.gp2, self.dwp[(2 * k + 1) * n3:(2 * k + 2) * n3], gb3[2 * k + 1])
+            grouped = k in in_group
+            if not grouped:
+                ops.conv3x3_wgrad(blk.a, blk.gp2, self.dwp[(2 * k + 1) * n3:(2 * k + 2) * n3], gb3[2 * k + 1])
             ops.conv3x3(blk.gp2, self._wd(2 * k + 1), slope=self.slope, mask_src=blk.a, out2=blk.gp1)
-            ops.conv3x3_wgrad(x_in, blk.gp1, self.dwp[(2 * k) * n3:(2 * k + 1) * n3], gb3[2 * k])
+            if not grouped:
+                ops.conv3x3_wgrad(x_in, blk.gp1, self.dwp[(2 * k) * n3:(2 * k + 1) * n3], gb3[2 * k])
             if k > 0:
                 prev = pl.blocks[k - 1]
                 if prev.pool:
@@ -257,6 +312,13 @@ class BackboneEngine:
                 ops.conv3x3(blk.gp1, self._wd(0), slope=self.slope, residual=GS, out=pl.g_stem)
                 ops.stem_wgrad(pl.x, pl.g_stem, self.section(self.gflat, "conv1.weight"),
                                self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad)
+            if k in in_group and in_group[k][0] == k:
+                # the dgrad chain of this run is complete: all its weight gradients in two launches
+                k0, k1, IN_all, A_all, GP1_all, GP2_all = in_group[k]
+                ops.conv3x3_wgrad_multi(A_all, GP2_all, self.dwp[(2 * k0 + 1) * n3:], 2 * n3,
+                                        gb3_flat[(2 * k0 + 1) * self.F:], 2 * self.F)
+                ops.conv3x3_wgrad_multi(IN_all, GP1_all, self.dwp[(2 * k0) * n3:], 2 * n3,
+                                        gb3_flat[(2 * k0) * self.F:], 2 * self.F)
         ops.unpack_wgrad3x3(self.dwp.view(2 * nb, 9, self.F, self.F), self.section(self.gflat, "w3"))
 
     # ------------------------------------------------------------------ fused train step

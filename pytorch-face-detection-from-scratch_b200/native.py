@@ -23,6 +23,7 @@ SIGNATURES = {
     "fd_error_string": [_I],
     "fd_conv3x3": [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "fd_conv3x3_wgrad": [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
+    "fd_conv3x3_wgrad_multi": [_P, _P, _I, _I, _I, _I, _I, _P, _c.c_long, _P, _c.c_long, _I, _P],
     "fd_pack_conv3x3": [_P, _I, _I, _P, _P, _P],
     "fd_unpack_wgrad3x3": [_P, _I, _I, _P, _P],
     "fd_stem_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],

@@ -29,6 +29,14 @@ def conv3x3_wgrad(x, g, dw_packed, dbias, flags=0):
                                  flags, cur_stream()), "fd_conv3x3_wgrad")
 
 
+def conv3x3_wgrad_multi(x, g, dw_packed, dw_stride, dbias, dbias_stride, flags=0):
+    """x, g: [nprob,B,H,W,C] stacked problems; problem q accumulates into dw_packed[q*dw_stride:], dbias[q*dbias_stride:]."""
+    nprob, B, H, W, C = x.shape
+    check(lib().fd_conv3x3_wgrad_multi(dptr(x, BF16), dptr(g, BF16), nprob, B, H, W, C, dptr(dw_packed, F32),
+                                       int(dw_stride), dptr(dbias, F32), int(dbias_stride), flags, cur_stream()),
+          "fd_conv3x3_wgrad_multi")
+
+
 def pack_conv3x3(w, w_fwd, w_dgrad):
     n, C = (w.shape[0], w.shape[1]) if w.dim() == 5 else (1, w.shape[0])
     check(lib().fd_pack_conv3x3(dptr(w, F32), n, C, dptr(w_fwd, BF16), dptr(w_dgrad, BF16), cur_stream()),

@@ -104,7 +104,33 @@ def test_stem_fwd_wgrad(u8):
     dw = torch.zeros(C, 3, 10, 10, device=dev); dbias = torch.zeros(C, device=dev)
     ops.stem_wgrad(x, g, dw, dbias, 8, 2)
     ref.backward(g.float().permute(0, 3, 1, 2))
-    assert rel_err(dw, w.grad) <= 1e-4 and rel_err(dbias, b.grad) <= 1e-4
+    # the tensor-core stem rounds the image to bf16 on the way into shared memory: bf16 tolerance
+    # against the fp32 reference, fp32-accumulation tolerance against the same conv on the rounded image
+    assert rel_err(dw, w.grad) <= 4e-3 and rel_err(dbias, b.grad) <= 1e-4
+    wz = torch.zeros_like(w).requires_grad_(True)
+    (dref,) = torch.autograd.grad(F.conv2d(xf.bfloat16().float(), wz, None, stride=8, padding=2), wz,
+                                  g.float().permute(0, 3, 1, 2))
+    assert rel_err(dw, dref) <= 1e-4
+
+
+def test_conv3x3_wgrad_multi_problem():
+    """Eight stacked problems in one launch == eight single launches (strided outputs)."""
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(3)
+    dev = "cuda"
+    P, B, H = 8, 4, 15
+    x = torch.randn(P, B, H, H, C, device=dev).bfloat16()
+    g = (torch.randn(P, B, H, H, C, device=dev) * 0.1).bfloat16()
+    n3 = 9 * C * C
+    dwp = torch.zeros(2 * P * n3, device=dev); db = torch.zeros(2 * P * C, device=dev)
+    ops.conv3x3_wgrad_multi(x, g, dwp[n3:], 2 * n3, db[C:], 2 * C)      # odd layers, like conv2 of a run
+    for q in range(P):
+        one = torch.zeros(n3, device=dev); ob = torch.zeros(C, device=dev)
+        ops.conv3x3_wgrad(x[q], g[q], one, ob)
+        assert rel_err(dwp[(2 * q + 1) * n3:(2 * q + 2) * n3], one) <= 1e-5
+        assert rel_err(db[(2 * q + 1) * C:(2 * q + 2) * C], ob) <= 1e-5
+        assert dwp[(2 * q) * n3:(2 * q + 1) * n3].abs().max().item() == 0.0     # even slots untouched
 
 
 @pytest.mark.parametrize("H,K,pad", [(15, 6, 0), (15, 3, 1)])
