@@ -27,8 +27,13 @@ namespace {
 
 constexpr int kCo = 64;
 constexpr int kRowBytes = 1024;            // one input row in smem: 512 bf16
-constexpr int kLoaderWarps = 8;
-constexpr int kThreads = (kLoaderWarps + 1 + 4) * 32;   // loaders | MMA | epilogue  = 416
+constexpr int kLoaderWarps = 8;             // converter warps: fp32/u8 staging -> bf16 A tile
+constexpr int kMmaWarp = kLoaderWarps;      // MMA issuer + TMEM owner
+constexpr int kTmaWarp = kLoaderWarps + 1;  // TMA producer of the image chunks
+constexpr int kEpiWarp0 = kLoaderWarps + 2; // 4 epilogue warps (10..13 -> TMEM quadrants 2,3,0,1)
+constexpr int kThreads = (kLoaderWarps + 2 + 4) * 32;   // 448
+constexpr int kSlotBytes = 4864;            // one staging slot: K/2 rows x Win/2 pixels (<= 4800 B), 128B aligned
+constexpr int kChunksPerTask = 24;          // 3 ch x 2 img x 2 row groups x 2 column halves
 constexpr int kMaxCK = 30;                 // Cin * K rows per image per task
 
 struct StemParams {
@@ -37,6 +42,7 @@ struct StemParams {
   int npairs;       // ceil(B / 2)
   int ntask;        // npairs * Ho
   uint32_t a_bytes; // CK * 2 * 1024
+  int elem_bytes;   // 4 (fp32 image) or 1 (uint8 image)
   const void* x;
   const float* w;        // [64][Cin][K][K] fp32 (forward)
   const float* bias;     // [64]
@@ -69,81 +75,115 @@ template <typename TIn>
 struct Px4;
 template <>
 struct Px4<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
-    const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+  static __device__ __forceinline__ void load(const uint8_t* slot, int quad, float (&v)[4]) {
+    const float4 f = *reinterpret_cast<const float4*>(slot + quad * 16);
     v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
   }
 };
 template <>
 struct Px4<uint8_t> {
-  static __device__ __forceinline__ void load(const uint8_t* p, float (&v)[4]) {
-    const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p));
+  static __device__ __forceinline__ void load(const uint8_t* slot, int quad, float (&v)[4]) {
+    const uchar4 u = *reinterpret_cast<const uchar4*>(slot + quad * 4);
     v[0] = static_cast<float>(u.x) / 255.0f; v[1] = static_cast<float>(u.y) / 255.0f;   // PoolResnet.py:95
     v[2] = static_cast<float>(u.z) / 255.0f; v[3] = static_cast<float>(u.w) / 255.0f;
   }
 };
 
-// Loader warps: fill one A tile (CK*2 rows) for task (pair, oy).  Element e of a row holds input
-// column e - pad; columns outside the image stay zero from the one-time clear.
-template <typename TIn>
-__device__ __forceinline__ void load_task(const StemParams& p, uint8_t* abuf, int pair, int oy, int ltid) {
-  const TIn* x = static_cast<const TIn*>(p.x);
-  const int q_per_row = p.Win >> 2;                 // 4-pixel chunks per row
-  const int total = p.CK * 2 * q_per_row;
-  constexpr int kBatch = 7;
-  for (int base = ltid; base < total; base += kLoaderWarps * 32 * kBatch) {
-    float v[kBatch][4];
-    int dst[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int idx = base + u * kLoaderWarps * 32;
-      dst[u] = -1;
-      if (idx < total) {
-        const int qx = idx % q_per_row;
-        const int row = idx / q_per_row;              // (c*K + ky)*2 + img
-        const int img = row & 1, cky = row >> 1;
-        const int ky = cky % p.K, c = cky / p.K;
-        const int n = pair * 2 + img;
-        const int iy = oy * p.stride + ky - p.pad;
-        dst[u] = row * kRowBytes + (qx * 4 + p.pad) * 2;
-        if (n < p.B && iy >= 0 && iy < p.Hin) {
-          Px4<TIn>::load(x + ((static_cast<size_t>(n) * p.Cin + c) * p.Hin + iy) * p.Win + qx * 4, v[u]);
-        } else {
-          v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      if (dst[u] >= 0) {
-        uint32_t* d = reinterpret_cast<uint32_t*>(abuf + dst[u]);
-        d[0] = pack_bf16x2(v[u][0], v[u][1]);
-        d[1] = pack_bf16x2(v[u][2], v[u][3]);
-      }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// The image reaches shared memory through a ring of 8 TMA staging slots (one per converter warp):
+// chunk j of a task = (channel c, image img, row group rg, column half) -> one box {Win/2, K/2, 1} of
+// the [B*Cin, Hin, Win] input, zero filled above the image.  Converter warp (j % 8) turns it into
+// bf16 rows of the A tile.  Element e of an A row holds input column e - pad.
+struct ChunkCoord {
+  int c, img, rg, half;
+};
+__device__ __forceinline__ ChunkCoord chunk_coord(int j) {
+  ChunkCoord k;
+  k.half = j & 1; k.rg = (j >> 1) & 1; k.img = (j >> 2) & 1; k.c = j >> 3;
+  return k;
+}
+
+// TMA producer (one thread): stream all chunks of this CTA's tasks through the slots.
+template <typename Sched>
+__device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtensorMap* tm_x, uint8_t* sStage,
+                                               uint64_t* stg_full, uint64_t* stg_empty, Sched sched) {
+  const uint32_t bytes = static_cast<uint32_t>((p.K / 2) * (p.Win / 2) * p.elem_bytes);
+  int it = 0;
+  for (int task = sched.begin; task < sched.end; task += sched.step, ++it) {
+    const int pair = task / p.Ho, oy = task % p.Ho;
+    for (int j = 0; j < kChunksPerTask; ++j) {
+      const int slot = j & 7;
+      const int use = it * (kChunksPerTask / 8) + (j >> 3);      // how many times this slot was used before
+      const ChunkCoord k = chunk_coord(j);
+      mbar_wait(stg_empty + slot, (use & 1) ^ 1);
+      mbar_expect_tx(stg_full + slot, bytes);
+      tma_load_3d(sStage + slot * kSlotBytes, tm_x, stg_full + slot, k.half * (p.Win / 2),
+                  oy * p.stride - p.pad + k.rg * (p.K / 2), (pair * 2 + k.img) * p.Cin + k.c);
     }
   }
 }
 
+// Converter warp `warp`: its chunks of task iteration `it` -> A tile `abuf`.
+template <typename TIn>
+__device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abuf, const uint8_t* sStage,
+                                               uint64_t* stg_full, uint64_t* stg_empty, int it, int warp, int lane) {
+  const int qpr = p.Win / 8;                     // 4-pixel quads per half row
+  const int nquad = (p.K / 2) * qpr;
+#pragma unroll 1
+  for (int jj = 0; jj < kChunksPerTask / 8; ++jj) {
+    const int j = jj * 8 + warp;
+    const int use = it * (kChunksPerTask / 8) + jj;
+    const ChunkCoord k = chunk_coord(j);
+    mbar_wait(stg_full + warp, use & 1);
+    const uint8_t* slot = sStage + warp * kSlotBytes;
+    for (int idx = lane; idx < nquad; idx += 32) {
+      const int r = idx / qpr, q = idx - r * qpr;
+      float v[4];
+      Px4<TIn>::load(slot, idx, v);
+      const int row = ((k.c * p.K + k.rg * (p.K / 2) + r) * 2 + k.img);
+      uint32_t* d = reinterpret_cast<uint32_t*>(abuf + row * kRowBytes + (k.half * (p.Win / 2) + q * 4 + p.pad) * 2);
+      d[0] = pack_bf16x2(v[0], v[1]);
+      d[1] = pack_bf16x2(v[2], v[3]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(stg_empty + warp);
+  }
+}
+
+struct StrideSched { int begin, end, step; };
+
 // ------------------------------------------------------------------------------------- forward
 // smem: [weights CK*2048][A stage 0][A stage 1][slack 64][barriers]
 template <typename TIn>
-__global__ void __launch_bounds__(kThreads, 1) stem_fwd_tc_kernel(const StemParams p) {
+__global__ void __launch_bounds__(kThreads, 1)
+stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sW = smem;
   uint8_t* sA = sW + p.CK * 2048;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 2 * p.a_bytes + 64);
+  uint8_t* sStage = sA + 2 * p.a_bytes + 128;          // 8 staging slots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * kSlotBytes);
   uint64_t* a_full = bars + 0;     // [2] count = loader warps
   uint64_t* a_empty = bars + 2;    // [2]
   uint64_t* acc_full = bars + 4;   // [2]
   uint64_t* acc_empty = bars + 6;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* stg_full = bars + 8;   // [8]
+  uint64_t* stg_empty = bars + 16; // [8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // one-time: zero the A stages (pad columns stay zero forever) and build the bf16 weight operand
-  for (uint32_t i = threadIdx.x * 16u; i < 2 * p.a_bytes + 64; i += kThreads * 16u)
+  for (uint32_t i = threadIdx.x * 16u; i < 2 * p.a_bytes + 128; i += kThreads * 16u)
     *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
   {
     // B operand per (c,ky): [k1 2][co 64][k0 8] bf16  (K-major, no swizzle: LBO = 1024, SBO = 128)
@@ -158,15 +198,20 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fwd_tc_kernel(const StemPara
   }
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
     for (int s = 0; s < 2; ++s) {
       mbar_init(a_full + s, kLoaderWarps);
       mbar_init(a_empty + s, 1);
       mbar_init(acc_full + s, 1);
       mbar_init(acc_empty + s, 4);
     }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(stg_full + s, 1);
+      mbar_init(stg_empty + s, 1);
+    }
     fence_barrier_init();
   }
-  if (warp == kLoaderWarps) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
@@ -180,12 +225,16 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fwd_tc_kernel(const StemPara
     for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       mbar_wait(a_empty + s, ph ^ 1);
-      load_task<TIn>(p, sA + s * p.a_bytes, task / p.Ho, task % p.Ho, threadIdx.x);
+      convert_chunks<TIn>(p, sA + s * p.a_bytes, sStage, stg_full, stg_empty, it, warp, lane);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + s);
     }
-  } else if (warp == kLoaderWarps) {
+  } else if (warp == kTmaWarp) {
+    if (lane == 0)
+      produce_chunks(p, &tm_x, sStage, stg_full, stg_empty,
+                     StrideSched{static_cast<int>(blockIdx.x), p.ntask, static_cast<int>(gridDim.x)});
+  } else if (warp == kMmaWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(128, kCo, 0, 0);
     const uint32_t w_addr = smem_u32(sW);
     int it = 0;
@@ -249,26 +298,30 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fwd_tc_kernel(const StemPara
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kLoaderWarps) tmem_dealloc(tmem_base, 128);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------- weight gradient
 // smem: [A stage 0][A stage 1][slack 1024][g stage 0 (16 KB)][g stage 1][barriers][bias scratch]
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 1)
-stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const StemParams p) {
+stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
+                     const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sG = sA + 2 * p.a_bytes + 1024;
   constexpr uint32_t kGBytes = 128 * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * kGBytes);
+  uint8_t* sStage = sG + 2 * kGBytes;                  // 8 staging slots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * kSlotBytes);
   uint64_t* full = bars + 0;     // [2] count = loader warps + 1 (TMA expect_tx)
   uint64_t* empty = bars + 2;    // [2] count = 1 (MMA commit) + 4 (bias warps)
   uint64_t* acc_full = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  float* sBias = reinterpret_cast<float*>(bars + 6);   // [128]
+  uint64_t* stg_full = bars + 5;   // [8]
+  uint64_t* stg_empty = bars + 13; // [8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  float* sBias = reinterpret_cast<float*>(bars + 22);   // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x * 16u; i < 2 * p.a_bytes + 1024 + 2 * kGBytes; i += kThreads * 16u)
@@ -276,14 +329,19 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const StemParams 
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_x);
     for (int s = 0; s < 2; ++s) {
       mbar_init(full + s, kLoaderWarps + 1);
       mbar_init(empty + s, 1 + 4);
     }
     mbar_init(acc_full, 1);
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(stg_full + s, 1);
+      mbar_init(stg_empty + s, 1);
+    }
     fence_barrier_init();
   }
-  if (warp == kLoaderWarps) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -302,12 +360,14 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const StemParams 
     for (int task = t_begin; task < t_end; ++task, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       mbar_wait(empty + s, ph ^ 1);
-      load_task<TIn>(p, sA + s * p.a_bytes, task / p.Ho, task % p.Ho, threadIdx.x);
+      convert_chunks<TIn>(p, sA + s * p.a_bytes, sStage, stg_full, stg_empty, it, warp, lane);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full + s);
     }
-  } else if (warp == kLoaderWarps) {
+  } else if (warp == kTmaWarp) {
+    if (lane == 0) produce_chunks(p, &tm_x, sStage, stg_full, stg_empty, StrideSched{t_begin, t_end, 1});
+  } else if (warp == kMmaWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(64, 16, 1, 1);
     int it = 0;
     for (int task = t_begin; task < t_end; ++task, ++it) {
@@ -340,7 +400,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const StemParams 
       __syncwarp();
     }
   } else {
-    const int et = threadIdx.x - (kLoaderWarps + 1) * 32;   // 0..127
+    const int et = threadIdx.x - kEpiWarp0 * 32;   // 0..127
     const int c = et & 63, rpar = et >> 6;
     float bsum = 0.f;
     int it = 0;
@@ -384,14 +444,14 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const StemParams 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kLoaderWarps) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 bool tc_shape_ok(int Cin, int Win, int C, int K, int stride, int pad, int Wo) {
   static const bool force_generic = std::getenv("FD_STEM_GENERIC") != nullptr;   // A/B testing only
   if (force_generic) return false;
-  return stride == 8 && K <= 16 && C == kCo && Cin * K <= kMaxCK && Wo <= 64 && (Win % 4) == 0 &&
-         Win + pad <= 510 && (pad % 2) == 0;
+  return stride == 8 && K <= 16 && (K % 2) == 0 && C == kCo && Cin == 3 && Wo <= 64 && (Win % 32) == 0 &&
+         Win / 2 <= 256 && (K / 2) * (Win / 2) * 4 <= kSlotBytes && Win + pad <= 510 && (pad % 2) == 0;
 }
 
 StemParams make_params(const void* x, int B, int Cin, int Hin, int Win, int K, int stride, int pad) {
@@ -407,6 +467,11 @@ StemParams make_params(const void* x, int B, int Cin, int Hin, int Win, int K, i
   return p;
 }
 
+// [B*Cin, Hin, Win] image (fp32 or uint8) as a 3-D tiled map, box {Win/2, K/2, 1}, no swizzle, zero OOB fill
+int make_tmap_image(CUtensorMap* m, const void* x, int is_u8, int planes, int Hin, int Win, int K) {
+  return make_tmap_3d(m, x, is_u8 ? 1 : 4, is_u8, Win, Hin, planes, Win / 2, K / 2);
+}
+
 }  // namespace
 
 // Called from layers.cu's fd_stem_fwd / fd_stem_wgrad; returns FD_EUNSUPPORTED when the shape is
@@ -416,18 +481,24 @@ int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, i
   StemParams p = make_params(x, B, Cin, Hin, Win, K, stride, pad);
   if (!tc_shape_ok(Cin, Win, C, K, stride, pad, p.Wo)) return FD_EUNSUPPORTED;
   p.w = w; p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16*>(y);
-  const size_t smem = static_cast<size_t>(p.CK) * 2048 + 2 * p.a_bytes + 64 + 256 + 1024;
+  p.elem_bytes = x_is_u8 ? 1 : 4;
+  CUtensorMap tm_x;
+  {
+    int rc = make_tmap_image(&tm_x, x, x_is_u8, B * Cin, Hin, Win, K);
+    if (rc != FD_OK) return rc;
+  }
+  const size_t smem = static_cast<size_t>(p.CK) * 2048 + 2 * p.a_bytes + 128 + 8 * kSlotBytes + 512 + 1024;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
   const int grid = min(p.ntask, sm_count());
   cudaError_t e;
   if (x_is_u8) {
     e = cudaFuncSetAttribute(stem_fwd_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    stem_fwd_tc_kernel<uint8_t><<<grid, kThreads, smem, st>>>(p);
+    stem_fwd_tc_kernel<uint8_t><<<grid, kThreads, smem, st>>>(tm_x, p);
   } else {
     e = cudaFuncSetAttribute(stem_fwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    stem_fwd_tc_kernel<float><<<grid, kThreads, smem, st>>>(p);
+    stem_fwd_tc_kernel<float><<<grid, kThreads, smem, st>>>(tm_x, p);
   }
   count_launch();
   return launch_status();
@@ -438,24 +509,29 @@ int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, 
   StemParams p = make_params(x, B, Cin, Hin, Win, K, stride, pad);
   if (!tc_shape_ok(Cin, Win, C, K, stride, pad, p.Wo)) return FD_EUNSUPPORTED;
   p.dw = dw; p.dbias = dbias;
-  CUtensorMap tm_g;
+  p.elem_bytes = x_is_u8 ? 1 : 4;
+  CUtensorMap tm_g, tm_x;
+  {
+    int rc = make_tmap_image(&tm_x, x, x_is_u8, B * Cin, Hin, Win, K);
+    if (rc != FD_OK) return rc;
+  }
   // g: [B,Ho,Wo,64] bf16; box = one output row of one image
   {
     int rc = make_tmap_nhwc_bf16(&tm_g, g, B, p.Ho, p.Wo, C, p.Wo, 1);
     if (rc != FD_OK) return rc;
   }
-  const size_t smem = 2 * static_cast<size_t>(p.a_bytes) + 1024 + 2 * 128 * 128 + 1024 + 1024;
+  const size_t smem = 2 * static_cast<size_t>(p.a_bytes) + 1024 + 2 * 128 * 128 + 8 * kSlotBytes + 1024 + 1024;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
   const int grid = min(p.ntask, sm_count());
   cudaError_t e;
   if (x_is_u8) {
     e = cudaFuncSetAttribute(stem_wgrad_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    stem_wgrad_tc_kernel<uint8_t><<<grid, kThreads, smem, st>>>(tm_g, p);
+    stem_wgrad_tc_kernel<uint8_t><<<grid, kThreads, smem, st>>>(tm_x, tm_g, p);
   } else {
     e = cudaFuncSetAttribute(stem_wgrad_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    stem_wgrad_tc_kernel<float><<<grid, kThreads, smem, st>>>(tm_g, p);
+    stem_wgrad_tc_kernel<float><<<grid, kThreads, smem, st>>>(tm_x, tm_g, p);
   }
   count_launch();
   return launch_status();
