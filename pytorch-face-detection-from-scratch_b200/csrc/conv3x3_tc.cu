@@ -16,8 +16,8 @@
 //     whole persistent CTA.
 //   * rows with x == W or y >= R are junk and are simply not stored.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue (TMEM -> registers -> fused bias/LeakyReLU/dropout/residual/mask -> global).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = epilogue (TMEM -> registers -> fused bias/LeakyReLU/dropout/residual/mask -> global).
 // Input tiles and TMEM accumulators are double buffered so the epilogue of tile i overlaps the
 // MMAs of tile i+1 and the TMA of tile i+2.
 #include "fd_host.h"
@@ -28,7 +28,7 @@ namespace {
 
 constexpr int kC = 64;
 constexpr int kWBytes = 9 * kC * 128;  // 73728: [tap][cout][cin] bf16, K-major, 128B swizzle
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t kTmemCols = 512;
 
 struct ConvParams {
@@ -107,7 +107,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       mbar_init(in_full + s, 1);
       mbar_init(in_empty + s, 1);
       mbar_init(acc_full + s, 1);
-      mbar_init(acc_empty + s, 4);
+      mbar_init(acc_empty + s, 8);
     }
     fence_barrier_init();
   }
@@ -176,31 +176,61 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------------ epilogue warps (8)
+    // warp -> TMEM lane quadrant q (hardware rule: warp % 4) and channel half hf: each thread owns
+    // 32 channels (64 B) of one output row.  Residual / mask rows of the next two blocks are
+    // prefetched into registers so that their L2/HBM latency overlaps the MMAs and the math.
+    const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;
+    const int c0 = hf * 32;
+    const bool need_res = p.residual != nullptr;
+    const bool need_mask = p.out2 != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       const int n = tile / p.tiles_per_img;
       const int h0 = (tile - n * p.tiles_per_img) * p.R;
-      mbar_wait(acc_full + s, ph);
-      tc_fence_after();
-      for (int mb = 0; mb < p.nblk; ++mb) {
+      uint4 pre_r[2][4], pre_m[2][4];
+      auto geometry = [&](int mb, bool& valid, size_t& pix) {
         const int m = mb * 128 + q * 32 + lane;
         const int y = m / p.Wp;
         const int x = m - y * p.Wp;
         const int oy = h0 + y;
-        const bool valid = (y < p.R) && (x < p.W) && (oy < p.H);
-        const size_t pix = (static_cast<size_t>(n) * p.H + oy) * p.W + x;
+        valid = (y < p.R) && (x < p.W) && (oy < p.H);
+        pix = (static_cast<size_t>(n) * p.H + oy) * p.W + x;
+      };
+#define FD_PREFETCH(MB, SLOT)                                                                        \
+  {                                                                                                  \
+    bool v_;                                                                                         \
+    size_t px_;                                                                                      \
+    geometry(MB, v_, px_);                                                                           \
+    if (v_) {                                                                                        \
+      if (need_res) {                                                                                \
+        const uint4* r_ = reinterpret_cast<const uint4*>(p.residual + px_ * kC + c0);                \
+        _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) pre_r[SLOT][i_] = __ldg(r_ + i_);           \
+      }                                                                                              \
+      if (need_mask) {                                                                               \
+        const uint4* m_ = reinterpret_cast<const uint4*>(p.mask_src + px_ * kC + c0);                \
+        _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) pre_m[SLOT][i_] = __ldg(m_ + i_);           \
+      }                                                                                              \
+    }                                                                                                \
+  }
+      FD_PREFETCH(0, 0)
+      if (p.nblk > 1) FD_PREFETCH(1, 1)
+      mbar_wait(acc_full + s, ph);
+      tc_fence_after();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+      for (int mb = 0; mb < 4; ++mb) {
+        if (mb < p.nblk) {
+          bool valid;
+          size_t pix;
+          geometry(mb, valid, pix);
           uint32_t acc[32];
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>((s * p.nblk + mb) * kC + half * 32),
+                                 static_cast<uint32_t>((s * p.nblk + mb) * kC + c0),
                              acc);
           tmem_ld_wait();
           if (valid) {
-            const int c0 = half * 32;
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
@@ -217,27 +247,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
               for (int j = 0; j < 32; ++j) v[j] *= __ldg(p.chan_scale + n * kC + c0 + j);
             }
             if (p.aux_out) store_bf16x32(p.aux_out + pix * kC + c0, v);
-            if (p.residual) {
-              float r[32];
-              load_bf16x32(p.residual + pix * kC + c0, r);
+            if (need_res) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += r[j];
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = pre_r[mb & 1][i];
+                v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
+                v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
+                v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
+                v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
+              }
             }
             if (p.out) store_bf16x32(p.out + pix * kC + c0, v);
-            if (p.out2) {
-              float r[32];
-              load_bf16x32(p.mask_src + pix * kC + c0, r);
+            if (need_mask) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float g = v[j] * (r[j] > 0.f ? 1.f : p.slope);
-                if (p.chan_scale2) g *= __ldg(p.chan_scale2 + n * kC + c0 + j);
-                v[j] = g;
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = pre_m[mb & 1][i];
+                const float mk[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y),
+                                     bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  float g = v[8 * i + e] * (mk[e] > 0.f ? 1.f : p.slope);
+                  if (p.chan_scale2) g *= __ldg(p.chan_scale2 + n * kC + c0 + 8 * i + e);
+                  v[8 * i + e] = g;
+                }
               }
               store_bf16x32(p.out2 + pix * kC + c0, v);
             }
           }
+          if (mb + 2 < p.nblk) FD_PREFETCH(mb + 2, mb & 1)
         }
       }
+#undef FD_PREFETCH
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + s);

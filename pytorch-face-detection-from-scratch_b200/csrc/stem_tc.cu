@@ -112,7 +112,7 @@ __device__ __forceinline__ ChunkCoord chunk_coord(int j) {
 }
 
 // TMA producer (one thread): stream all chunks of this CTA's tasks through the slots.
-template <typename Sched>
+template <int NS, typename Sched>
 __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtensorMap* tm_x, uint8_t* sStage,
                                                uint64_t* stg_full, uint64_t* stg_empty, Sched sched) {
   const uint32_t bytes = static_cast<uint32_t>((p.K / 2) * (p.Win / 2) * p.elem_bytes);
@@ -120,8 +120,9 @@ __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtens
   for (int task = sched.begin; task < sched.end; task += sched.step, ++it) {
     const int pair = task / p.Ho, oy = task % p.Ho;
     for (int j = 0; j < kChunksPerTask; ++j) {
-      const int slot = j & 7;
-      const int use = it * (kChunksPerTask / 8) + (j >> 3);      // how many times this slot was used before
+      const int g = it * kChunksPerTask + j;                     // chunk sequence number of this CTA
+      const int slot = g % NS;
+      const int use = g / NS;                                    // how many times this slot was used before
       const ChunkCoord k = chunk_coord(j);
       mbar_wait(stg_empty + slot, (use & 1) ^ 1);
       mbar_expect_tx(stg_full + slot, bytes);
@@ -132,7 +133,7 @@ __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtens
 }
 
 // Converter warp `warp`: its chunks of task iteration `it` -> A tile `abuf`.
-template <typename TIn>
+template <typename TIn, int NS>
 __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abuf, const uint8_t* sStage,
                                                uint64_t* stg_full, uint64_t* stg_empty, int it, int warp, int lane) {
   const int qpr = p.Win / 8;                     // 4-pixel quads per half row
@@ -140,10 +141,12 @@ __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abu
 #pragma unroll 1
   for (int jj = 0; jj < kChunksPerTask / 8; ++jj) {
     const int j = jj * 8 + warp;
-    const int use = it * (kChunksPerTask / 8) + jj;
+    const int g = it * kChunksPerTask + j;
+    const int sl = g % NS;
+    const int use = g / NS;
     const ChunkCoord k = chunk_coord(j);
-    mbar_wait(stg_full + warp, use & 1);
-    const uint8_t* slot = sStage + warp * kSlotBytes;
+    mbar_wait(stg_full + sl, use & 1);
+    const uint8_t* slot = sStage + sl * kSlotBytes;
     for (int idx = lane; idx < nquad; idx += 32) {
       const int r = idx / qpr, q = idx - r * qpr;
       float v[4];
@@ -154,14 +157,16 @@ __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abu
       d[1] = pack_bf16x2(v[2], v[3]);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(stg_empty + warp);
+    if (lane == 0) mbar_arrive(stg_empty + sl);
   }
 }
 
 struct StrideSched { int begin, end, step; };
 
 // ------------------------------------------------------------------------------------- forward
-// smem: [weights CK*2048][A stage 0][A stage 1][slack 64][barriers]
+// smem: [weights CK*2048][A tile (single stage)][slack 128][16 staging slots][barriers]
+constexpr int kFwdSlots = 16;
+constexpr int kWgSlots = 8;
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 1)
 stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p) {
@@ -170,20 +175,20 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sW = smem;
   uint8_t* sA = sW + p.CK * 2048;
-  uint8_t* sStage = sA + 2 * p.a_bytes + 128;          // 8 staging slots
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * kSlotBytes);
-  uint64_t* a_full = bars + 0;     // [2] count = loader warps
-  uint64_t* a_empty = bars + 2;    // [2]
+  uint8_t* sStage = sA + p.a_bytes + 128;              // staging slots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + kFwdSlots * kSlotBytes);
+  uint64_t* a_full = bars + 0;     // [1] count = loader warps
+  uint64_t* a_empty = bars + 2;    // [1]
   uint64_t* acc_full = bars + 4;   // [2]
   uint64_t* acc_empty = bars + 6;  // [2]
-  uint64_t* stg_full = bars + 8;   // [8]
-  uint64_t* stg_empty = bars + 16; // [8]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* stg_full = bars + 8;               // [kFwdSlots]
+  uint64_t* stg_empty = bars + 8 + kFwdSlots;  // [kFwdSlots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kFwdSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // one-time: zero the A stages (pad columns stay zero forever) and build the bf16 weight operand
-  for (uint32_t i = threadIdx.x * 16u; i < 2 * p.a_bytes + 128; i += kThreads * 16u)
+  for (uint32_t i = threadIdx.x * 16u; i < p.a_bytes + 128; i += kThreads * 16u)
     *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
   {
     // B operand per (c,ky): [k1 2][co 64][k0 8] bf16  (K-major, no swizzle: LBO = 1024, SBO = 128)
@@ -199,13 +204,13 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
+    mbar_init(a_full, kLoaderWarps);
+    mbar_init(a_empty, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(a_full + s, kLoaderWarps);
-      mbar_init(a_empty + s, 1);
       mbar_init(acc_full + s, 1);
       mbar_init(acc_empty + s, 4);
     }
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 0; s < kFwdSlots; ++s) {
       mbar_init(stg_full + s, 1);
       mbar_init(stg_empty + s, 1);
     }
@@ -223,17 +228,17 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   if (warp < kLoaderWarps) {
     int it = 0;
     for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
-      const int s = it & 1, ph = (it >> 1) & 1;
-      mbar_wait(a_empty + s, ph ^ 1);
-      convert_chunks<TIn>(p, sA + s * p.a_bytes, sStage, stg_full, stg_empty, it, warp, lane);
+      // single A stage: the deep staging ring keeps HBM busy while the 30 MMAs of the previous task drain
+      mbar_wait(a_empty, (it & 1) ^ 1);
+      convert_chunks<TIn, kFwdSlots>(p, sA, sStage, stg_full, stg_empty, it, warp, lane);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + s);
+      if (lane == 0) mbar_arrive(a_full);
     }
   } else if (warp == kTmaWarp) {
     if (lane == 0)
-      produce_chunks(p, &tm_x, sStage, stg_full, stg_empty,
-                     StrideSched{static_cast<int>(blockIdx.x), p.ntask, static_cast<int>(gridDim.x)});
+      produce_chunks<kFwdSlots>(p, &tm_x, sStage, stg_full, stg_empty,
+                                StrideSched{static_cast<int>(blockIdx.x), p.ntask, static_cast<int>(gridDim.x)});
   } else if (warp == kMmaWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(128, kCo, 0, 0);
     const uint32_t w_addr = smem_u32(sW);
@@ -241,16 +246,16 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
     for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       mbar_wait(acc_empty + s, ph ^ 1);
-      mbar_wait(a_full + s, ph);
+      mbar_wait(a_full, it & 1);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_addr = smem_u32(sA + s * p.a_bytes);
+        const uint32_t a_addr = smem_u32(sA);
         for (int cky = 0; cky < p.CK; ++cky) {
           const uint64_t ad = make_sdesc_none(a_addr + cky * 2048, 16, 128);
           const uint64_t bd = make_sdesc_none(w_addr + cky * 2048, 1024, 128);
           umma_bf16(tmem_base + s * kCo, ad, bd, idesc, cky != 0 ? 1u : 0u);
         }
-        umma_commit(a_empty + s);
+        umma_commit(a_empty);
         umma_commit(acc_full + s);
       }
       __syncwarp();
@@ -360,13 +365,13 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     for (int task = t_begin; task < t_end; ++task, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       mbar_wait(empty + s, ph ^ 1);
-      convert_chunks<TIn>(p, sA + s * p.a_bytes, sStage, stg_full, stg_empty, it, warp, lane);
+      convert_chunks<TIn, kWgSlots>(p, sA + s * p.a_bytes, sStage, stg_full, stg_empty, it, warp, lane);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full + s);
     }
   } else if (warp == kTmaWarp) {
-    if (lane == 0) produce_chunks(p, &tm_x, sStage, stg_full, stg_empty, StrideSched{t_begin, t_end, 1});
+    if (lane == 0) produce_chunks<kWgSlots>(p, &tm_x, sStage, stg_full, stg_empty, StrideSched{t_begin, t_end, 1});
   } else if (warp == kMmaWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(64, 16, 1, 1);
     int it = 0;
@@ -487,7 +492,7 @@ int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, i
     int rc = make_tmap_image(&tm_x, x, x_is_u8, B * Cin, Hin, Win, K);
     if (rc != FD_OK) return rc;
   }
-  const size_t smem = static_cast<size_t>(p.CK) * 2048 + 2 * p.a_bytes + 128 + 8 * kSlotBytes + 512 + 1024;
+  const size_t smem = static_cast<size_t>(p.CK) * 2048 + p.a_bytes + 128 + kFwdSlots * kSlotBytes + 512 + 1024;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
   const int grid = min(p.ntask, sm_count());
   cudaError_t e;
