@@ -34,6 +34,8 @@ constexpr int kEpiWarp0 = kLoaderWarps + 2; // 4 epilogue warps (10..13 -> TMEM 
 constexpr int kThreads = (kLoaderWarps + 2 + 4) * 32;   // 448
 constexpr int kSlotBytes = 4864;            // one staging slot: K/2 rows x Win/2 pixels (<= 4800 B), 128B aligned
 constexpr int kChunksPerTask = 24;          // 3 ch x 2 img x 2 row groups x 2 column halves
+constexpr int kKH = 5;                      // rows per chunk  (K = 10)
+constexpr int kQPR = 60;                    // 4-pixel quads per half row (Win = 480)
 constexpr int kMaxCK = 30;                 // Cin * K rows per image per task
 
 struct StemParams {
@@ -136,8 +138,6 @@ __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtens
 template <typename TIn, int NS>
 __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abuf, const uint8_t* sStage,
                                                uint64_t* stg_full, uint64_t* stg_empty, int it, int warp, int lane) {
-  const int qpr = p.Win / 8;                     // 4-pixel quads per half row
-  const int nquad = (p.K / 2) * qpr;
 #pragma unroll 1
   for (int jj = 0; jj < kChunksPerTask / 8; ++jj) {
     const int j = jj * 8 + warp;
@@ -147,14 +147,23 @@ __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abu
     const ChunkCoord k = chunk_coord(j);
     mbar_wait(stg_full + sl, use & 1);
     const uint8_t* slot = sStage + sl * kSlotBytes;
-    for (int idx = lane; idx < nquad; idx += 32) {
-      const int r = idx / qpr, q = idx - r * qpr;
-      float v[4];
-      Px4<TIn>::load(slot, idx, v);
-      const int row = ((k.c * p.K + k.rg * (p.K / 2) + r) * 2 + k.img);
-      uint32_t* d = reinterpret_cast<uint32_t*>(abuf + row * kRowBytes + (k.half * (p.Win / 2) + q * 4 + p.pad) * 2);
-      d[0] = pack_bf16x2(v[0], v[1]);
-      d[1] = pack_bf16x2(v[2], v[3]);
+    // kKH rows x kQPR quads, fully unrolled: all shared loads are issued before the first convert
+    float v[kKH][2][4];
+#pragma unroll
+    for (int r = 0; r < kKH; ++r) {
+      Px4<TIn>::load(slot, r * kQPR + lane, v[r][0]);
+      if (lane + 32 < kQPR) Px4<TIn>::load(slot, r * kQPR + lane + 32, v[r][1]);
+    }
+    uint8_t* dst0 = abuf + ((k.c * p.K + k.rg * kKH) * 2 + k.img) * kRowBytes + (k.half * (p.Win / 2) + p.pad) * 2;
+#pragma unroll
+    for (int r = 0; r < kKH; ++r) {
+      uint32_t* d = reinterpret_cast<uint32_t*>(dst0 + r * 2 * kRowBytes + lane * 8);
+      d[0] = pack_bf16x2(v[r][0][0], v[r][0][1]);
+      d[1] = pack_bf16x2(v[r][0][2], v[r][0][3]);
+      if (lane + 32 < kQPR) {
+        d[64] = pack_bf16x2(v[r][1][0], v[r][1][1]);
+        d[65] = pack_bf16x2(v[r][1][2], v[r][1][3]);
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(stg_empty + sl);
@@ -455,7 +464,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 bool tc_shape_ok(int Cin, int Win, int C, int K, int stride, int pad, int Wo) {
   static const bool force_generic = std::getenv("FD_STEM_GENERIC") != nullptr;   // A/B testing only
   if (force_generic) return false;
-  return stride == 8 && K <= 16 && (K % 2) == 0 && C == kCo && Cin == 3 && Wo <= 64 && (Win % 32) == 0 &&
+  return stride == 8 && K == 2 * kKH && Win == 8 * kQPR && C == kCo && Cin == 3 && Wo <= 64 && (Win % 32) == 0 &&
          Win / 2 <= 256 && (K / 2) * (Win / 2) * 4 <= kSlotBytes && Win + pad <= 510 && (pad % 2) == 0;
 }
 
