@@ -38,8 +38,6 @@ typedef uint16_t fd_bf16;
 
 /* epilogue flags for fd_conv3x3 */
 #define FD_EPI_LRELU 1   /* v = v > 0 ? v : slope * v            (PoolResnet.py:36,38) */
-#define FD_DBG_BASE_OFFSET 256 /* debug: set the smem-descriptor base-offset field from the address */
-#define FD_DBG_PLAN_B 512      /* debug: one 1024B-aligned input copy per kx tap (no row-shifted descriptors) */
 
 FD_API int fd_version(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */

@@ -35,7 +35,6 @@ struct ConvParams {
   int B, H, W, R, Wp, nblk, tiles_per_img, num_tiles;
   uint32_t in_bytes;      // bytes delivered by one input TMA box
   uint32_t in_buf_bytes;  // bytes reserved per input copy (multiple of 1024)
-  int ncopies;            // 1 = row-shifted descriptors; 3 = one aligned copy per kx (debug plan B)
   int flags;
   float slope;
   const float* bias;
@@ -79,7 +78,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  const uint32_t stage_bytes = static_cast<uint32_t>(p.ncopies) * p.in_buf_bytes;
+  const uint32_t stage_bytes = p.in_buf_bytes;
   uint8_t* sW = smem;
   uint8_t* sIn = smem + kWBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + 2 * stage_bytes);
@@ -122,7 +121,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(w_full, kWBytes);
       for (int t = 0; t < 9; ++t) tma_load_2d(sW + t * 8192, &tm_w, w_full, 0, t * kC);
       int it = 0;
@@ -131,16 +130,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         const int n = tile / p.tiles_per_img;
         const int h0 = (tile - n * p.tiles_per_img) * p.R;
         mbar_wait(in_empty + s, ph ^ 1);
-        mbar_expect_tx(in_full + s, p.in_bytes * p.ncopies);
-        for (int c = 0; c < p.ncopies; ++c)
-          tma_load_4d(sIn + s * stage_bytes + c * p.in_buf_bytes, &tm_in, in_full + s, 0, -1 + c, h0 - 1, n);
+        mbar_expect_tx(in_full + s, p.in_bytes);
+        tma_load_4d(sIn + s * stage_bytes, &tm_in, in_full + s, 0, -1, h0 - 1, n);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(128, kC, 0, 0);
-    const uint32_t w_addr = smem_u32(sW);
-    const bool dbg_bo = (p.flags & FD_DBG_BASE_OFFSET) != 0;
+    const uint32_t w_lo = sdesc_lo(smem_u32(sW), 16);
     mbar_wait(w_full, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -148,26 +145,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       mbar_wait(acc_empty + s, ph ^ 1);
       mbar_wait(in_full + s, ph);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t in_addr = smem_u32(sIn + s * stage_bytes);
+      if (elect_one_sync()) {
+        const uint32_t in_lo = sdesc_lo(smem_u32(sIn + s * stage_bytes), 16);
         for (int mb = 0; mb < p.nblk; ++mb) {
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((s * p.nblk + mb) * kC);
+          const uint32_t a_blk = in_lo + static_cast<uint32_t>(mb * 128 * 8);   // 128 rows x 128 B, in 16-B units
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int ky = t / 3, kx = t - 3 * ky;
-            uint32_t a_addr;
-            if (p.ncopies == 1)
-              a_addr = in_addr + static_cast<uint32_t>((mb * 128 + ky * p.Wp + kx) * 128);
-            else
-              a_addr = in_addr + kx * p.in_buf_bytes + static_cast<uint32_t>((mb * 128 + ky * p.Wp) * 128);
-            const uint32_t b_addr = w_addr + t * 8192;
-            const uint32_t bo = dbg_bo ? ((a_addr >> 7) & 7u) : 0u;
+            // tap (ky,kx): the same tile, start address shifted by (ky*Wp + kx) rows
+            const uint32_t a_tap = a_blk + static_cast<uint32_t>((ky * p.Wp + kx) * 8);
+            const uint32_t b_tap = w_lo + t * 512;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = make_sdesc_sw128(a_addr + k * 32, 16, 1024, bo);
-              const uint64_t bd = make_sdesc_sw128(b_addr + k * 32, 16, 1024, 0);
-              umma_bf16(d_tmem, ad, bd, idesc, (t | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, sdesc_sw128(a_tap + 2 * k), sdesc_sw128(b_tap + 2 * k), idesc, (t | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(in_empty + s);   // input tile free once these MMAs have read it
@@ -301,10 +292,9 @@ extern "C" int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int 
   if (C != kC || W + 8 > 256) return FD_EUNSUPPORTED;
   if ((out2 != nullptr) != (mask_src != nullptr)) return FD_EINVAL;
   if (!out && !aux_out && !out2) return FD_EINVAL;
-  const bool plan_b = (flags & FD_DBG_PLAN_B) != 0;
   const int nsm = sm_count();
-  const int Wp = plan_b ? ((W + 1 + 7) / 8) * 8 : W + 1;
-  const int ncopies = plan_b ? 3 : 1;
+  const int Wp = W + 1;
+  const int ncopies = 1;
   const size_t smem_cap = 227 * 1024;
 
   // Pick the rows-per-tile R that minimises a simple cycle model: MMA time of the padded
@@ -332,7 +322,6 @@ extern "C" int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int 
   p.num_tiles = B * p.tiles_per_img;
   p.in_bytes = static_cast<uint32_t>((bestR + 2) * Wp * 128);
   p.in_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.nblk * 128 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024);
-  p.ncopies = ncopies;
   p.flags = flags;
   p.slope = slope;
   p.bias = bias; p.chan_scale = chan_scale;

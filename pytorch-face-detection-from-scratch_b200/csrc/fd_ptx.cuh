@@ -13,6 +13,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp.  Branching on elect.sync (instead of `lane == 0`) tells ptxas that the
+// region is executed by exactly one thread, so descriptors stay in uniform registers and every
+// tcgen05.mma / TMA issue is a single UTCHMMA / UTMALDG without a divergence ("waterfall") loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -146,6 +159,14 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
   d |= 2ull << 61;
   return d;
 }
+// Incremental form for the issue loops: constant high word (SBO = 1024 B, version 1, 128B swizzle) and
+// a low word = (address >> 4) | (LBO >> 4) << 16 that is advanced with plain 32-bit adds.
+constexpr uint64_t kSdescHiSw128 = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t sdesc_sw128(uint32_t lo) { return kSdescHiSw128 | static_cast<uint64_t>(lo); }
+
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32.
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4

@@ -113,24 +113,26 @@ __device__ __forceinline__ ChunkCoord chunk_coord(int j) {
   return k;
 }
 
-// TMA producer (one thread): stream all chunks of this CTA's tasks through the slots.
+// TMA producer warp: lane j issues chunk j of every task (24 lanes busy), so the ~100-cycle mbarrier
+// round trips of the slot hand-shake overlap across lanes instead of serialising in one thread.
 template <int NS, typename Sched>
 __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtensorMap* tm_x, uint8_t* sStage,
-                                               uint64_t* stg_full, uint64_t* stg_empty, Sched sched) {
+                                               uint64_t* stg_full, uint64_t* stg_empty, Sched sched, int lane) {
   const uint32_t bytes = static_cast<uint32_t>((p.K / 2) * (p.Win / 2) * p.elem_bytes);
+  const ChunkCoord k = chunk_coord(lane);
   int it = 0;
   for (int task = sched.begin; task < sched.end; task += sched.step, ++it) {
-    const int pair = task / p.Ho, oy = task % p.Ho;
-    for (int j = 0; j < kChunksPerTask; ++j) {
-      const int g = it * kChunksPerTask + j;                     // chunk sequence number of this CTA
+    if (lane < kChunksPerTask) {
+      const int pair = task / p.Ho, oy = task % p.Ho;
+      const int g = it * kChunksPerTask + lane;                  // chunk sequence number of this CTA
       const int slot = g % NS;
       const int use = g / NS;                                    // how many times this slot was used before
-      const ChunkCoord k = chunk_coord(j);
       mbar_wait(stg_empty + slot, (use & 1) ^ 1);
       mbar_expect_tx(stg_full + slot, bytes);
       tma_load_3d(sStage + slot * kSlotBytes, tm_x, stg_full + slot, k.half * (p.Win / 2),
                   oy * p.stride - p.pad + k.rg * (p.K / 2), (pair * 2 + k.img) * p.Cin + k.c);
     }
+    __syncwarp();
   }
 }
 
@@ -245,9 +247,8 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
       if (lane == 0) mbar_arrive(a_full);
     }
   } else if (warp == kTmaWarp) {
-    if (lane == 0)
-      produce_chunks<kFwdSlots>(p, &tm_x, sStage, stg_full, stg_empty,
-                                StrideSched{static_cast<int>(blockIdx.x), p.ntask, static_cast<int>(gridDim.x)});
+    produce_chunks<kFwdSlots>(p, &tm_x, sStage, stg_full, stg_empty,
+                              StrideSched{static_cast<int>(blockIdx.x), p.ntask, static_cast<int>(gridDim.x)}, lane);
   } else if (warp == kMmaWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(128, kCo, 0, 0);
     const uint32_t w_addr = smem_u32(sW);
@@ -257,13 +258,13 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
       mbar_wait(acc_empty + s, ph ^ 1);
       mbar_wait(a_full, it & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(sA);
-        for (int cky = 0; cky < p.CK; ++cky) {
-          const uint64_t ad = make_sdesc_none(a_addr + cky * 2048, 16, 128);
-          const uint64_t bd = make_sdesc_none(w_addr + cky * 2048, 1024, 128);
-          umma_bf16(tmem_base + s * kCo, ad, bd, idesc, cky != 0 ? 1u : 0u);
-        }
+      if (elect_one_sync()) {
+        const uint64_t ad0 = make_sdesc_none(smem_u32(sA), 16, 128);
+        const uint64_t bd0 = make_sdesc_none(w_addr, 1024, 128);
+#pragma unroll 6
+        for (int cky = 0; cky < p.CK; ++cky)    // +2048 B per (c,ky) on both operands = +128 in the address field
+          umma_bf16(tmem_base + s * kCo, ad0 + static_cast<uint64_t>(cky * 128), bd0 + static_cast<uint64_t>(cky * 128),
+                    idesc, cky != 0 ? 1u : 0u);
         umma_commit(a_empty);
         umma_commit(acc_full + s);
       }
@@ -380,13 +381,13 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       if (lane == 0) mbar_arrive(full + s);
     }
   } else if (warp == kTmaWarp) {
-    if (lane == 0) produce_chunks<kWgSlots>(p, &tm_x, sStage, stg_full, stg_empty, StrideSched{t_begin, t_end, 1});
+    produce_chunks<kWgSlots>(p, &tm_x, sStage, stg_full, stg_empty, StrideSched{t_begin, t_end, 1}, lane);
   } else if (warp == kMmaWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(64, 16, 1, 1);
     int it = 0;
     for (int task = t_begin; task < t_end; ++task, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
-      if (lane == 0) {
+      if (elect_one_sync()) {
         mbar_wait(empty + s, ph ^ 1);
         mbar_expect_tx(full + s, 2u * p.Wo * 128u);
         // one box {64 ch, Wo, 1, 1} per image into 64-row slots; rows Wo..63 stay zero; n >= B is zero filled
@@ -396,17 +397,17 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       __syncwarp();
       mbar_wait(full + s, ph);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(sA + s * p.a_bytes);
-        const uint32_t g_addr = smem_u32(sG + s * kGBytes);
+      if (elect_one_sync()) {
+        // A = g^T: MN-major (M = co), 128B swizzle, 16 K-rows (positions) per MMA
+        const uint64_t ad0 = make_sdesc_sw128(smem_u32(sG + s * kGBytes), 1024, 1024, 0);
+        // B = input windows: MN-major (N = kx), no swizzle: kx chunks 16 B apart, 8-position groups 128 B apart
+        const uint64_t bd0 = make_sdesc_none(smem_u32(sA + s * p.a_bytes), 128, 16);
         for (int ks = 0; ks < 8; ++ks) {
-          // A = g^T: MN-major (M = co), 128B swizzle, 16 K-rows (positions) per MMA
-          const uint64_t ad = make_sdesc_sw128(g_addr + ks * 2048, 1024, 1024, 0);
-          for (int cky = 0; cky < p.CK; ++cky) {
-            // B = input windows: MN-major (N = kx), no swizzle: kx chunks 16 B apart, 8-position groups 128 B apart
-            const uint64_t bd = make_sdesc_none(a_addr + cky * 2048 + ks * 256, 128, 16);
-            umma_bf16(tmem_base + cky * 16, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
-          }
+          const uint64_t ad = ad0 + static_cast<uint64_t>(ks * 128);          // +2048 B
+          const uint64_t bdk = bd0 + static_cast<uint64_t>(ks * 16);          // +256 B
+#pragma unroll 6
+          for (int cky = 0; cky < p.CK; ++cky)
+            umma_bf16(tmem_base + cky * 16, ad, bdk + static_cast<uint64_t>(cky * 128), idesc, (it | ks) != 0 ? 1u : 0u);
         }
         umma_commit(empty + s);
         if (task + 1 == t_end) umma_commit(acc_full);

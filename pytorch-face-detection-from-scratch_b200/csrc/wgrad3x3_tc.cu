@@ -97,7 +97,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   float* const dbias_out = p.dbias ? p.dbias + prob * p.dbias_stride : nullptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int it = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
         const int s = it & 1, ph = (it >> 1) & 1;
@@ -116,23 +116,25 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int s = it & 1, ph = (it >> 1) & 1;
       mbar_wait(full + s, ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one_sync()) {
         const uint32_t x_addr = smem_u32(sStage + s * stage_bytes);
-        const uint32_t g_addr = x_addr + p.x_buf_bytes;
-        for (int ks = 0; ks < p.ksteps; ++ks) {
-          const uint64_t bd = make_sdesc_sw128(g_addr + ks * 2048, 1024, 1024, 0);
+        const uint32_t g_lo = sdesc_lo(x_addr + p.x_buf_bytes, 1024);
+        // tap pairs (0,1) (2,3) (4,5) (6,7) (7,8): the last pair recomputes tap 7 (dropped in the
+        // epilogue) so that every instruction is a regular two-atom M=128 MMA.  Pair j reads the
+        // halo tile at row offset off0 with the second atom (off1 - off0) rows further (LBO).
+        uint32_t a_lo[5];
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            // tap pairs (0,1) (2,3) (4,5) (6,7) (7,8): the last pair recomputes tap 7 (dropped in the
-            // epilogue) so that every instruction is a regular two-atom M=128 MMA
-            const int t0 = (j < 4) ? 2 * j : 7, t1 = t0 + 1;
-            const int off0 = (t0 / 3) * p.Wp + (t0 % 3);
-            const int off1 = (t1 / 3) * p.Wp + (t1 % 3);
-            const uint64_t ad =
-                make_sdesc_sw128(x_addr + static_cast<uint32_t>((off0 + ks * 16) * 128),
-                                 static_cast<uint32_t>((off1 - off0) * 128), 1024, 0);
-            umma_bf16(tmem_base + j * kC, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
-          }
+        for (int j = 0; j < 5; ++j) {
+          const int t0 = (j < 4) ? 2 * j : 7, t1 = t0 + 1;
+          const int off0 = (t0 / 3) * p.Wp + (t0 % 3);
+          const int off1 = (t1 / 3) * p.Wp + (t1 % 3);
+          a_lo[j] = sdesc_lo(x_addr + static_cast<uint32_t>(off0 * 128), static_cast<uint32_t>((off1 - off0) * 128));
+        }
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          const uint64_t bd = sdesc_sw128(g_lo + ks * 128);      // 16 pixel rows = 2048 B per K step
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            umma_bf16(tmem_base + j * kC, sdesc_sw128(a_lo[j] + ks * 128), bd, idesc, (it | ks) != 0 ? 1u : 0u);
         }
         umma_commit(empty + s);
         if (tile + 1 == tile_end) umma_commit(acc_full);

@@ -9,8 +9,6 @@ from .native import check, cur_stream, dptr, lib
 BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
 
 EPI_LRELU = 1
-DBG_BASE_OFFSET = 256
-DBG_PLAN_B = 512
 
 
 def conv3x3(x, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_scale=None, residual=None, aux_out=None,
