@@ -119,20 +119,26 @@ template <int NS, typename Sched>
 __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtensorMap* tm_x, uint8_t* sStage,
                                                uint64_t* stg_full, uint64_t* stg_empty, Sched sched, int lane) {
   const uint32_t bytes = static_cast<uint32_t>((p.K / 2) * (p.Win / 2) * p.elem_bytes);
-  const ChunkCoord k = chunk_coord(lane);
   int it = 0;
   for (int task = sched.begin; task < sched.end; task += sched.step, ++it) {
-    if (lane < kChunksPerTask) {
-      const int pair = task / p.Ho, oy = task % p.Ho;
-      const int g = it * kChunksPerTask + lane;                  // chunk sequence number of this CTA
-      const int slot = g % NS;
-      const int use = g / NS;                                    // how many times this slot was used before
-      mbar_wait(stg_empty + slot, (use & 1) ^ 1);
-      mbar_expect_tx(stg_full + slot, bytes);
-      tma_load_3d(sStage + slot * kSlotBytes, tm_x, stg_full + slot, k.half * (p.Win / 2),
-                  oy * p.stride - p.pad + k.rg * (p.K / 2), (pair * 2 + k.img) * p.Cin + k.c);
+    const int pair = task / p.Ho, oy = task % p.Ho;
+    // batches of NS chunks: inside a batch every lane owns a different slot, so no lane ever waits
+    // for a slot that a sibling lane of the same batch still has to fill (that would deadlock the warp)
+#pragma unroll 1
+    for (int j0 = 0; j0 < kChunksPerTask; j0 += NS) {
+      const int j = j0 + lane;
+      if (lane < NS && j < kChunksPerTask) {
+        const ChunkCoord k = chunk_coord(j);
+        const int g = it * kChunksPerTask + j;                   // chunk sequence number of this CTA
+        const int slot = g % NS;
+        const int use = g / NS;                                  // how many times this slot was used before
+        mbar_wait(stg_empty + slot, (use & 1) ^ 1);
+        mbar_expect_tx(stg_full + slot, bytes);
+        tma_load_3d(sStage + slot * kSlotBytes, tm_x, stg_full + slot, k.half * (p.Win / 2),
+                    oy * p.stride - p.pad + k.rg * (p.K / 2), (pair * 2 + k.img) * p.Cin + k.c);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
