@@ -93,6 +93,51 @@ FD_API int fd_pack_conv3x3(const float* w, int n_layers, int C, fd_bf16* w_fwd, 
 FD_API int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, float* dw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * A run of `n_blocks` residual blocks of ONE spatial shape without pooling (blocks 2..9 of the
+ * reference PoolResnet, models/PoolResnet.py:33-43; the 15x15 blocks of models/Resnet.py:27-40) as one
+ * persistent kernel: one CTA per image, activations resident in shared memory across all 2*n_blocks
+ * convolutions, weights streamed from L2.  Arithmetic is identical to the equivalent sequence of
+ * fd_conv3x3 calls (same MMA order, same bf16 rounding points).
+ *
+ * LeakyReLU' masks are exchanged as sign bits: mask[B,H,W,C/32] uint32, bit (c % 32) of word c / 32
+ * is set iff the stored bf16 activation is > 0.
+ * fd_resblock_chain_shape_ok returns 1 when (H, W, C) fits the kernel (whole padded image in smem). */
+typedef struct fd_chain_fwd_block {
+  const float* bias1;       /* [C] conv1 bias                                  (PoolResnet.py:35) */
+  const float* bias2;       /* [C] conv2 bias                                  (PoolResnet.py:37) */
+  const float* chan_scale;  /* [B,C] Dropout2d multiplier of the block or NULL (PoolResnet.py:39) */
+  fd_bf16* a;               /* out [B,H,W,C]: lrelu(conv1), saved for the weight gradient; NULL = not stored */
+  uint32_t* mask_a;         /* out: sign bits of a; NULL = not stored */
+  fd_bf16* b;               /* out [B,H,W,C]: dropout(lrelu(conv2)) before the skip add; NULL = not stored */
+  uint32_t* mask_b;         /* out: sign bits of b; NULL = not stored */
+  fd_bf16* out;             /* out [B,H,W,C]: block output b + input; may be NULL except for the last block */
+} fd_chain_fwd_block;
+/* w_fwd: [2*n_blocks][9][C][C] forward-packed weights of the run (conv1, conv2 of block 0, ...). */
+FD_API int fd_resblock_chain_shape_ok(int H, int W, int C);
+FD_API int fd_resblock_chain_fwd(const fd_bf16* x, const fd_bf16* w_fwd, const fd_chain_fwd_block* blocks, int n_blocks,
+                          int B, int H, int W, int C, float slope, void* stream);
+
+/* Input-gradient chain of the same run (autograd backward of the blocks, without the weight gradients):
+ * for block k = n_blocks-1 .. 0, with G = gradient w.r.t. the block output and gp2 = G * drop * lrelu'(b):
+ *   gp1      = dgrad_conv2(gp2) * lrelu'(a_k)
+ *   G        = dgrad_conv1(gp1) + G                      (skip connection)      -> g_in (if non-NULL)
+ *   gp2_prev = G * chan_scale_prev * lrelu'(b_{k-1})     (k > 0)
+ * blocks[] is in FORWARD order.  g_out, gp2_last: [B,H,W,C] gradient w.r.t. the last block's output and
+ * its gp2 (both produced by fd_head_bwd / fd_maxpool2x2_bwd). */
+typedef struct fd_chain_bwd_block {
+  const uint32_t* mask_a;        /* sign bits of this block's a */
+  fd_bf16* gp1;                  /* out [B,H,W,C] or NULL */
+  fd_bf16* g_in;                 /* out [B,H,W,C]: gradient w.r.t. the block input, or NULL */
+  const uint32_t* mask_b_prev;   /* sign bits of the previous block's b (NULL for block 0) */
+  const float* chan_scale_prev;  /* [B,C] Dropout2d multiplier of the previous block or NULL */
+  fd_bf16* gp2_prev;             /* out [B,H,W,C]: gp2 of the previous block (NULL for block 0) */
+} fd_chain_bwd_block;
+/* w_dgrad: [2*n_blocks][9][C][C] dgrad-packed weights of the run, in FORWARD layer order. */
+FD_API int fd_resblock_chain_bwd(const fd_bf16* g_out, const fd_bf16* gp2_last, const fd_bf16* w_dgrad,
+                          const fd_chain_bwd_block* blocks, int n_blocks, int B, int H, int W, int C, float slope,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Stem convolution (models/PoolResnet.py:70-76,98): KxK stride s pad p, Cin(3) -> C, input fp32 NCHW
  * (or uint8 NCHW with the /255 of PoolResnet.py:95 fused: x_is_u8 = 1), output NHWC bf16, bias added.
  * w: [C][Cin][K][K] fp32. */

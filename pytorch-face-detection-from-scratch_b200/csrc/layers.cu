@@ -204,12 +204,15 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
                 const float* __restrict__ bias, int B, int H, int W, int C, int K, int pad, int Ho, int Wo,
                 float* __restrict__ y) {
   extern __shared__ float sm[];
-  float* sW = sm;                                                      // [K*K][5][C]
-  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sm + K * K * 5 * C);  // [H*W][C]
+  const int CP = C + 1;
+  float* sW = sm;                                                      // [K*K][5][C+1]
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sm + ((K * K * 5 * CP + 3) & ~3));  // [H*W][C]
   const int n = blockIdx.x;
+  // coalesced read of w in its natural [o][c][t] order, transposing scatter into [t][o][c] rows of pitch C+1
+  // (bank stride 5*(C+1) = 5 mod 32 for C = 64: conflict-free)
   for (int i = threadIdx.x; i < K * K * 5 * C; i += blockDim.x) {
-    const int c = i % C, o = (i / C) % 5, t = i / (5 * C);
-    sW[i] = w[(static_cast<size_t>(o) * C + c) * K * K + t];
+    const int t = i % (K * K), c = (i / (K * K)) % C, o = i / (K * K * C);
+    sW[(t * 5 + o) * CP + c] = __ldg(w + i);
   }
   const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * H * W * C);
   for (int i = threadIdx.x; i < H * W * C / 8; i += blockDim.x) reinterpret_cast<uint4*>(sX)[i] = __ldg(xs + i);
@@ -227,9 +230,9 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
           const int ix = ox + kx - pad;
           if (ix < 0 || ix >= W) continue;
           const float xv = __bfloat162float(sX[(iy * W + ix) * C + c]) * s;
-          const float* wp = sW + (ky * K + kx) * 5 * C + c;
+          const float* wp = sW + (ky * K + kx) * 5 * CP + c;
 #pragma unroll
-          for (int o = 0; o < 5; ++o) acc[o] = fmaf(xv, wp[o * C], acc[o]);
+          for (int o = 0; o < 5; ++o) acc[o] = fmaf(xv, wp[o * CP], acc[o]);
         }
       }
     }
@@ -254,13 +257,13 @@ head_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
                 const float* __restrict__ cs2, float slope, __nv_bfloat16* __restrict__ dx2, float* __restrict__ dw,
                 float* __restrict__ dbias) {
   extern __shared__ float sm[];
-  const int KK = K * K;
-  float* sW = sm;                       // [KK][5][C]
-  float* sDz = sW + KK * 5 * C;         // [5][Ho*Wo]
+  const int KK = K * K, CP = C + 1;
+  float* sW = sm;                       // [KK][5][C+1]
+  float* sDz = sW + ((KK * 5 * CP + 3) & ~3);   // [5][Ho*Wo]
   __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sDz + ((5 * Ho * Wo + 3) & ~3));  // [H*W][C]
   for (int i = threadIdx.x; i < KK * 5 * C; i += blockDim.x) {
-    const int c = i % C, o = (i / C) % 5, t = i / (5 * C);
-    sW[i] = w[(static_cast<size_t>(o) * C + c) * KK + t];
+    const int t = i % KK, c = (i / KK) % C, o = i / (KK * C);
+    sW[(t * 5 + o) * CP + c] = __ldg(w + i);
   }
   const int c = threadIdx.x % C;        // requires blockDim % C == 0
   const int grp = threadIdx.x / C, ngrp = blockDim.x / C;
@@ -291,9 +294,9 @@ head_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
         for (int kx = 0; kx < K; ++kx) {
           const int ox = ix - kx + pad;
           if (ox < 0 || ox >= Wo) continue;
-          const float* wp = sW + (ky * K + kx) * 5 * C + c;
+          const float* wp = sW + (ky * K + kx) * 5 * CP + c;
 #pragma unroll
-          for (int o = 0; o < 5; ++o) acc = fmaf(sDz[o * Ho * Wo + oy * Wo + ox], wp[o * C], acc);
+          for (int o = 0; o < 5; ++o) acc = fmaf(sDz[o * Ho * Wo + oy * Wo + ox], wp[o * CP], acc);
         }
       }
       acc *= s;
@@ -335,14 +338,14 @@ head_bwd_small_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
                       __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ mask_src,
                       const float* __restrict__ cs2, float slope, __nv_bfloat16* __restrict__ dx2,
                       float* __restrict__ dw, float* __restrict__ dbias) {
-  constexpr int C = 64, KK = K * K, MW = 16;
+  constexpr int C = 64, KK = K * K, MW = 16, CP = C + 1;
   extern __shared__ float sm[];
-  float* sW = sm;                         // [KK][5][C]
-  float* sDz = sW + KK * 5 * C;           // [5][Ho][MW] (rows padded to 16, zero filled)
+  float* sW = sm;                         // [KK][5][C+1]
+  float* sDz = sW + ((KK * 5 * CP + 3) & ~3);   // [5][Ho][MW] (rows padded to 16, zero filled)
   __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sDz + 5 * Ho * MW);  // [H*W][C]
   for (int i = threadIdx.x; i < KK * 5 * C; i += blockDim.x) {
-    const int c = i % C, o = (i / C) % 5, t = i / (5 * C);
-    sW[i] = w[(static_cast<size_t>(o) * C + c) * KK + t];
+    const int t = i % KK, c = (i / KK) % C, o = i / (KK * C);
+    sW[(t * 5 + o) * CP + c] = __ldg(w + i);
   }
   for (int n = blockIdx.x; n < B; n += gridDim.x) {
     __syncthreads();
@@ -384,7 +387,7 @@ head_bwd_small_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
           }
 #pragma unroll
           for (int kx = 0; kx < K; ++kx) {
-            const float wv = sW[((ky * K + kx) * 5 + o) * C + c];
+            const float wv = sW[((ky * K + kx) * 5 + o) * CP + c];
 #pragma unroll
             for (int ix = 0; ix < MW; ++ix) {
               constexpr int dummy = 0; (void)dummy;
@@ -637,7 +640,7 @@ extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const floa
   if ((H * W * C) % 8 != 0) return FD_EUNSUPPORTED;
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
-  const size_t smem = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>(H) * W * C * 2;
+  const size_t smem = static_cast<size_t>((K * K * 5 * (C + 1) + 3) & ~3) * 4 + static_cast<size_t>(H) * W * C * 2;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -656,7 +659,7 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
   if (C == 64 && W <= 16 && Wo <= 16 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
-    const size_t sm_small = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>(5) * Ho * 16 * 4 +
+    const size_t sm_small = static_cast<size_t>((K * K * 5 * (C + 1) + 3) & ~3) * 4 + static_cast<size_t>(5) * Ho * 16 * 4 +
                             static_cast<size_t>(H) * W * C * 2;
     auto kern = (K == 6) ? head_bwd_small_kernel<6, 0> : head_bwd_small_kernel<3, 1>;
     cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small);
@@ -668,7 +671,7 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
     count_launch();
     return launch_status();
   }
-  const size_t smem = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>((5 * Ho * Wo + 3) & ~3) * 4 +
+  const size_t smem = static_cast<size_t>((K * K * 5 * (C + 1) + 3) & ~3) * 4 + static_cast<size_t>((5 * Ho * Wo + 3) & ~3) * 4 +
                       static_cast<size_t>(H) * W * C * 2;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

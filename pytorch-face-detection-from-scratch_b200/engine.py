@@ -36,6 +36,7 @@ class _Plan:
         # Runs of consecutive non-pooled blocks share one shape; their tensors are allocated STACKED
         # ([n,B,H,W,F]) so that the weight gradients of the whole run go out as one multi-problem launch.
         self.groups = []            # (k0, k1, IN_all, A_all, GP1_all, GP2_all)
+        self.chains = {}            # k0 -> chain record for runs executed by the fused chain kernels
         runs, k = [], 0
         while k < eng.num_blocks:
             if not eng.pools[k]:
@@ -68,6 +69,12 @@ class _Plan:
             stacks[k0] = {"IN": stack(n, h, w), "A": stack(n, h, w),
                           "GP1": stack(n, h, w) if train else None, "GP2": stack(n, h, w) if train else None}
             self.groups.append((k0, k1, stacks[k0]["IN"], stacks[k0]["A"], stacks[k0]["GP1"], stacks[k0]["GP2"]))
+            if eng.use_chain and ops.resblock_chain_ok(h, w, F):
+                # the whole run executes as ONE persistent kernel per direction (csrc/resblock_chain.cu);
+                # LeakyReLU' travels as sign bits instead of bf16 tensors
+                masks = torch.empty((2, n, B, h, w, F // 32), dtype=torch.int32, device=device) if train else None
+                self.chains[k0] = {"k0": k0, "k1": k1, "MA": masks[0] if train else None,
+                                   "MB": masks[1] if train else None}
 
         def out_buffer(k, h, w):
             """Buffer holding the OUTPUT of block k (k = -1: the stem) = input of block k+1."""
@@ -148,6 +155,7 @@ class BackboneEngine:
             self.offsets[name] = (off, n, shape)
             off += (n + 3) // 4 * 4          # keep every section 16-byte aligned
         self.n_flat = off
+        self.use_chain = True        # fuse runs of equal-shape blocks into one kernel when the image fits in smem
         self.device = None
         self.pflat = self.gflat = self.dwp = self.w_fwd = self.w_dgrad = None
         self.plans: Dict[tuple, _Plan] = {}
@@ -252,7 +260,16 @@ class BackboneEngine:
         ops.stem_fwd(x, self.section(self.pflat, "conv1.weight"), self.section(self.pflat, "conv1.bias"), pl.act0,
                      self.stem_s, self.stem_pad)
         cur = pl.act0
+        chain_end = -1
         for k, blk in enumerate(pl.blocks):
+            if k <= chain_end:
+                cur = blk.out
+                continue
+            if k in pl.chains:
+                chain_end = pl.chains[k]["k1"]
+                self._chain_forward(pl, pl.chains[k], cur)
+                cur = blk.out
+                continue
             cs = pl.drop[k] if pl.drop is not None else None
             ops.conv3x3(cur, self._wf(2 * k), bias=sb3[2 * k], slope=self.slope, lrelu=True, out=blk.a)
             ops.conv3x3(blk.a, self._wf(2 * k + 1), bias=sb3[2 * k + 1], slope=self.slope, lrelu=True,
@@ -263,6 +280,41 @@ class BackboneEngine:
         cs = pl.drop[self.num_blocks] if pl.drop is not None else None
         ops.head_fwd(cur, cs, self.section(self.pflat, "out.weight"), self.section(self.pflat, "out.bias"), pl.y,
                      self.head_pad)
+
+    def _chain_forward(self, pl: _Plan, ch, x):
+        k0, k1 = ch["k0"], ch["k1"]
+        sb3 = self.section(self.pflat, "b3")
+        descs = []
+        for k in range(k0, k1 + 1):
+            blk = pl.blocks[k]
+            d = {"bias1": sb3[2 * k], "bias2": sb3[2 * k + 1],
+                 "chan_scale": pl.drop[k] if pl.drop is not None else None}
+            if pl.train:
+                d.update(a=blk.a, mask_a=ch["MA"][k - k0], mask_b=ch["MB"][k - k0], out=blk.s,
+                         b=blk.b if k == k1 else None)      # bf16 b only where a bf16-mask consumer follows
+            elif k == k1:
+                d.update(out=blk.s)
+            descs.append(d)
+        n3 = 9 * self.F * self.F
+        ops.resblock_chain_fwd(x, self.w_fwd[2 * k0 * n3:(2 * k1 + 2) * n3], descs, self.slope)
+
+    def _chain_backward(self, pl: _Plan, ch, g_in):
+        """Input-gradient chain of blocks k1..k0 in one launch; G / gp2 of block k1 are already in place."""
+        k0, k1 = ch["k0"], ch["k1"]
+        drop = pl.drop
+        descs = []
+        for k in range(k0, k1 + 1):
+            blk = pl.blocks[k]
+            d = {"mask_a": ch["MA"][k - k0], "gp1": blk.gp1}
+            if k == k0:
+                d["g_in"] = g_in
+            else:
+                d.update(mask_b_prev=ch["MB"][k - 1 - k0], gp2_prev=pl.blocks[k - 1].gp2,
+                         chan_scale_prev=drop[k - 1] if drop is not None else None)
+            descs.append(d)
+        n3 = 9 * self.F * self.F
+        last = pl.blocks[k1]
+        ops.resblock_chain_bwd(last.G, last.gp2, self.w_dgrad[2 * k0 * n3:(2 * k1 + 2) * n3], descs, self.slope)
 
     # ------------------------------------------------------------------ backward
     def run_backward(self, pl: _Plan, dy: torch.Tensor):
@@ -285,9 +337,28 @@ class BackboneEngine:
             for k in range(grp[0], grp[1] + 1):
                 in_group[k] = grp
         gb3_flat = gb3.reshape(-1)
+        chain_of_last = {ch["k1"]: ch for ch in pl.chains.values()}
+        skip_until = nb
         for k in range(nb - 1, -1, -1):
             blk = pl.blocks[k]
             x_in = pl.act0 if k == 0 else pl.blocks[k - 1].out
+            if k in chain_of_last and not blk.pool:
+                ch = chain_of_last[k]
+                k0 = ch["k0"]
+                self._chain_backward(pl, ch, pl.blocks[k0 - 1].G if k0 > 0 else pl.g_stem)
+                skip_until = k0
+                grp = in_group[k0]
+                _, _, IN_all, A_all, GP1_all, GP2_all = grp
+                ops.conv3x3_wgrad_multi(A_all, GP2_all, self.dwp[(2 * k0 + 1) * n3:], 2 * n3,
+                                        gb3_flat[(2 * k0 + 1) * self.F:], 2 * self.F)
+                ops.conv3x3_wgrad_multi(IN_all, GP1_all, self.dwp[(2 * k0) * n3:], 2 * n3,
+                                        gb3_flat[(2 * k0) * self.F:], 2 * self.F)
+                if k0 == 0:
+                    ops.stem_wgrad(pl.x, pl.g_stem, self.section(self.gflat, "conv1.weight"),
+                                   self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad)
+                continue
+            if k >= skip_until:
+                continue
             if blk.pool:
                 ops.maxpool2x2_bwd(blk.s, blk.G, blk.gs, blk.b, drop[k] if drop is not None else None, self.slope,
                                    blk.gp2)

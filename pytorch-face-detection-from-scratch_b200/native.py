@@ -24,6 +24,9 @@ SIGNATURES = {
     "fd_conv3x3": [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "fd_conv3x3_wgrad": [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
     "fd_conv3x3_wgrad_multi": [_P, _P, _I, _I, _I, _I, _I, _P, _c.c_long, _P, _c.c_long, _I, _P],
+    "fd_resblock_chain_shape_ok": [_I, _I, _I],
+    "fd_resblock_chain_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "fd_resblock_chain_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "fd_pack_conv3x3": [_P, _I, _I, _P, _P, _P],
     "fd_unpack_wgrad3x3": [_P, _I, _I, _P, _P],
     "fd_stem_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
@@ -36,6 +39,20 @@ SIGNATURES = {
     "fd_decode_nms": [_P, _I, _I, _I, _F, _D, _I, _I, _I, _P, _P, _P, _P],
     "fd_grid_encode": [_P, _P, _I, _I, _I, _I, _P, _P],
 }
+
+
+
+class ChainFwdBlock(_c.Structure):
+    """fd_chain_fwd_block of include/fd_b200.h"""
+    _fields_ = [("bias1", _P), ("bias2", _P), ("chan_scale", _P), ("a", _P), ("mask_a", _P), ("b", _P),
+                ("mask_b", _P), ("out", _P)]
+
+
+class ChainBwdBlock(_c.Structure):
+    """fd_chain_bwd_block of include/fd_b200.h"""
+    _fields_ = [("mask_a", _P), ("gp1", _P), ("g_in", _P), ("mask_b_prev", _P), ("chan_scale_prev", _P),
+                ("gp2_prev", _P)]
+
 
 _lib = None
 

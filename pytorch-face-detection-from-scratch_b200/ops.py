@@ -4,7 +4,9 @@ from __future__ import annotations
 
 import torch
 
-from .native import check, cur_stream, dptr, lib
+import ctypes
+
+from .native import ChainBwdBlock, ChainFwdBlock, check, cur_stream, dptr, lib
 
 BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
 
@@ -33,6 +35,36 @@ def conv3x3_wgrad_multi(x, g, dw_packed, dw_stride, dbias, dbias_stride, flags=0
     check(lib().fd_conv3x3_wgrad_multi(dptr(x, BF16), dptr(g, BF16), nprob, B, H, W, C, dptr(dw_packed, F32),
                                        int(dw_stride), dptr(dbias, F32), int(dbias_stride), flags, cur_stream()),
           "fd_conv3x3_wgrad_multi")
+
+
+def resblock_chain_ok(H, W, C):
+    return bool(lib().fd_resblock_chain_shape_ok(int(H), int(W), int(C)))
+
+
+def resblock_chain_fwd(x, w_fwd, blocks, slope=0.2):
+    """blocks: list of dicts with keys bias1, bias2 and optional chan_scale, a, mask_a, b, mask_b, out (tensors).
+    w_fwd: [2*len(blocks), 9, C, C] bf16 forward-packed weights of the run."""
+    B, H, W, C = x.shape
+    arr = (ChainFwdBlock * len(blocks))()
+    for i, d in enumerate(blocks):
+        arr[i] = ChainFwdBlock(dptr(d["bias1"], F32), dptr(d["bias2"], F32), dptr(d.get("chan_scale"), F32),
+                               dptr(d.get("a"), BF16), dptr(d.get("mask_a"), I32), dptr(d.get("b"), BF16),
+                               dptr(d.get("mask_b"), I32), dptr(d.get("out"), BF16))
+    check(lib().fd_resblock_chain_fwd(dptr(x, BF16), dptr(w_fwd, BF16), ctypes.cast(arr, ctypes.c_void_p),
+                                      len(blocks), B, H, W, C, slope, cur_stream()), "fd_resblock_chain_fwd")
+
+
+def resblock_chain_bwd(g_out, gp2_last, w_dgrad, blocks, slope=0.2):
+    """blocks (FORWARD order): dicts with mask_a and optional gp1, g_in, mask_b_prev, chan_scale_prev, gp2_prev."""
+    B, H, W, C = g_out.shape
+    arr = (ChainBwdBlock * len(blocks))()
+    for i, d in enumerate(blocks):
+        arr[i] = ChainBwdBlock(dptr(d["mask_a"], I32), dptr(d.get("gp1"), BF16), dptr(d.get("g_in"), BF16),
+                               dptr(d.get("mask_b_prev"), I32), dptr(d.get("chan_scale_prev"), F32),
+                               dptr(d.get("gp2_prev"), BF16))
+    check(lib().fd_resblock_chain_bwd(dptr(g_out, BF16), dptr(gp2_last, BF16), dptr(w_dgrad, BF16),
+                                      ctypes.cast(arr, ctypes.c_void_p), len(blocks), B, H, W, C, slope,
+                                      cur_stream()), "fd_resblock_chain_bwd")
 
 
 def pack_conv3x3(w, w_fwd, w_dgrad):

@@ -142,3 +142,59 @@ def test_official_checkpoint_demo_path():
         b = boxes.cpu().numpy()
         assert np.abs(b[:, 0] - want[:, 0]).max() <= HEAD_MAX                   # scores
         assert np.abs(b[:, 1:] - want[:, 1:]).max() <= 0.02 * 480 + 1           # pixels: head tol * size, +1 rounding
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_chain_kernels_equal_per_layer_path(dropout):
+    """The fused residual-block chain (csrc/resblock_chain.cu) performs the same arithmetic as the sequence
+    of fd_conv3x3 launches it replaces: activations/head bit-identical, gradients equal up to the
+    reordering of the fp32 atomics in the weight-gradient kernels."""
+    require_cuda()
+    B = 3
+    m = _model(seed=11).cuda()
+    m.train(dropout)
+    eng = m.engine
+    eng.bind(dict(m.named_parameters()))
+    gen = torch.Generator().manual_seed(12)
+    x = torch.rand(B, 3, 480, 480, generator=gen).cuda()
+    gt = torch.stack([torch.from_numpy(yo.grid_encode(synth_boxes(gen, 1, 100).numpy(), 10, 480, 480))
+                      for _ in range(B)]).cuda()
+    res = {}
+    for use_chain in (True, False):
+        eng.use_chain = use_chain
+        eng.plans.clear()
+        torch.manual_seed(1234)            # same Dropout2d masks in both runs
+        pl = eng.train_step(x, gt, dropout=dropout)
+        assert bool(pl.chains) == use_chain
+        res[use_chain] = (pl.y.clone(), pl.loss.clone(), eng.gflat.clone(), pl.blocks[-1].out.clone(),
+                          pl.blocks[1].G.clone())
+    eng.use_chain = True
+    assert torch.equal(res[True][3], res[False][3])          # last block output, bf16 bit-exact
+    assert torch.equal(res[True][0], res[False][0])          # head
+    assert torch.equal(res[True][1], res[False][1])          # per-image loss
+    assert torch.equal(res[True][4], res[False][4])          # gradient leaving the chain (into block 1)
+    assert rel_err(res[True][2], res[False][2]) <= 1e-5
+
+
+def test_chain_forward_many_images_per_cta():
+    """B > number of SMs: every CTA of the chain kernel walks several images (buffer reuse, barrier phases)."""
+    require_cuda()
+    f = fd()
+    ops = f.ops
+    B, H, W, C, nb = 300, 15, 15, 64, 3
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(B, H, W, C, generator=g) * 0.5).cuda().bfloat16()
+    w = (torch.randn(2 * nb, C, C, 3, 3, generator=g) * 0.05).cuda()
+    bias = (torch.randn(2 * nb, C, generator=g) * 0.1).cuda()
+    wf = torch.empty(2 * nb, 9, C, C, dtype=torch.bfloat16, device="cuda")
+    ops.pack_conv3x3(w, wf, None)
+    outs = [torch.empty_like(x) for _ in range(nb)]
+    ops.resblock_chain_fwd(x, wf, [{"bias1": bias[2 * k], "bias2": bias[2 * k + 1], "out": outs[k]}
+                                   for k in range(nb)])
+    cur = x
+    for k in range(nb):
+        a, s = torch.empty_like(x), torch.empty_like(x)
+        ops.conv3x3(cur, wf[2 * k], bias=bias[2 * k], lrelu=True, out=a)
+        ops.conv3x3(a, wf[2 * k + 1], bias=bias[2 * k + 1], lrelu=True, residual=cur, out=s)
+        assert torch.equal(outs[k], s), k
+        cur = s
