@@ -46,26 +46,30 @@ FD_API const char* fd_error_string(int code);
 
 /* ---------------------------------------------------------------------------------------------
  * 3x3, stride 1, pad 1 convolution, C -> C channels (C = 64), implicit GEMM on tcgen05.
- * Replaces aten::conv2d + leaky_relu + dropout2d + residual add at models/PoolResnet.py:35-40
- * (forward) and, called with dgrad-packed weights, the input-gradient of the same conv.
+ * Replaces aten::conv2d + leaky_relu + dropout2d + residual add at models/PoolResnet.py:35-40 /
+ * models/Resnet.py:29-36 (forward) and, called with dgrad-packed weights, the input-gradient of the
+ * same conv.
  *
  *   acc = conv3x3(x, w)                                   fp32 accumulate in TMEM
  *   v   = acc + bias[c]            (bias != NULL)
- *   v   = lrelu(v)                 (flags & FD_EPI_LRELU)
+ *   v   = lrelu(v)                 (flags & FD_EPI_LRELU; requires 0 <= slope <= 1)
  *   v  *= chan_scale[n, c]         (chan_scale != NULL; Dropout2d multiplier)
- *   aux_out = bf16(v)              (aux_out != NULL; pre-residual activation, saved for backward)
+ *   mask_out = sign bits of v      (mask_out != NULL; LeakyReLU' mask saved for the backward pass)
  *   v  += residual                 (residual != NULL)
  *   out  = bf16(v)                 (out != NULL)
- *   out2 = bf16(v * chan_scale2[n, c] * (mask_src > 0 ? 1 : slope))   (out2 != NULL; LeakyReLU'
- *                                   of a saved activation -- the backward chain)
+ *   out2 = bf16(v * (mask_in bit ? 1 : slope) * chan_scale2[n, c])   (out2 != NULL; the backward chain;
+ *                                   mask_in == NULL means all ones, chan_scale2 == NULL means 1)
  *
- * x, residual, aux_out, out, mask_src, out2: [B,H,W,C] bf16.  w_packed: [9][C][C] bf16 from
- * fd_pack_conv3x3 (forward or dgrad packing).  bias: [C] fp32.  chan_scale*: [B,C] fp32.
+ * x, residual, out, out2: [B,H,W,C] bf16.  w_packed: [9][C][C] bf16 from fd_pack_conv3x3 (forward or
+ * dgrad packing).  bias: [C] fp32.  chan_scale*: [B,C] fp32.  Masks: uint32 [B,H,W,C/32], bit (c % 32)
+ * of word c / 32 is set iff the sign bit of the value is clear (v >= +0).  Any H, W (wide images are tiled in 62-column strips).
+ * One of out / out2 leaves through a TMA tensor store (the fast path); if both are given, out2 is
+ * written with plain stores.
  */
 FD_API int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, int W, int C,
                const float* bias, float slope, const float* chan_scale,
-               const fd_bf16* residual, fd_bf16* aux_out, fd_bf16* out,
-               const fd_bf16* mask_src, const float* chan_scale2, fd_bf16* out2,
+               const fd_bf16* residual, uint32_t* mask_out, fd_bf16* out,
+               const uint32_t* mask_in, const float* chan_scale2, fd_bf16* out2,
                int flags, void* stream);
 
 /* Weight gradient of the same convolution (replaces the wgrad half of autograd's
@@ -100,7 +104,7 @@ FD_API int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, float
  * fd_conv3x3 calls (same MMA order, same bf16 rounding points).
  *
  * LeakyReLU' masks are exchanged as sign bits: mask[B,H,W,C/32] uint32, bit (c % 32) of word c / 32
- * is set iff the stored bf16 activation is > 0.
+ * is set iff the sign bit of the activation is clear (v >= +0).
  * fd_resblock_chain_shape_ok returns 1 when (H, W, C) fits the kernel (whole padded image in smem). */
 typedef struct fd_chain_fwd_block {
   const float* bias1;       /* [C] conv1 bias                                  (PoolResnet.py:35) */
@@ -108,8 +112,7 @@ typedef struct fd_chain_fwd_block {
   const float* chan_scale;  /* [B,C] Dropout2d multiplier of the block or NULL (PoolResnet.py:39) */
   fd_bf16* a;               /* out [B,H,W,C]: lrelu(conv1), saved for the weight gradient; NULL = not stored */
   uint32_t* mask_a;         /* out: sign bits of a; NULL = not stored */
-  fd_bf16* b;               /* out [B,H,W,C]: dropout(lrelu(conv2)) before the skip add; NULL = not stored */
-  uint32_t* mask_b;         /* out: sign bits of b; NULL = not stored */
+  uint32_t* mask_b;         /* out: sign bits of b = dropout(lrelu(conv2)) before the skip add; NULL = not stored */
   fd_bf16* out;             /* out [B,H,W,C]: block output b + input; may be NULL except for the last block */
 } fd_chain_fwd_block;
 /* w_fwd: [2*n_blocks][9][C][C] forward-packed weights of the run (conv1, conv2 of block 0, ...). */
@@ -154,10 +157,10 @@ FD_API int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const float* w
                 int C, int K, int pad, float* y, void* stream);
 /* dy: [B,5,Ho,Wo] fp32 gradient w.r.t. the sigmoid OUTPUT y.  Produces
  *   dx [B,H,W,C] bf16 (gradient w.r.t. the block output, dropout multiplier applied; overwritten) and,
- *   when dx2 != NULL, dx2 = dx * chan_scale2 * (mask_src > 0 ? 1 : slope),
+ *   when dx2 != NULL, dx2 = dx * chan_scale2 * (mask_bits bit ? 1 : slope)   (mask_bits: uint32 [B,H,W,C/32]),
  *   dw [5][C][K][K] fp32 (+=), dbias [5] fp32 (+=). */
 FD_API int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* y, const float* dy, int B,
-                int H, int W, int C, int K, int pad, fd_bf16* dx, const fd_bf16* mask_src,
+                int H, int W, int C, int K, int pad, fd_bf16* dx, const uint32_t* mask_bits,
                 const float* chan_scale2, float slope, fd_bf16* dx2, float* dw, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -165,10 +168,10 @@ FD_API int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w
 FD_API int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, void* stream);
 /* Backward of the pool fused with the start of the block's backward chain:
  *   gs  = unpool(gy) routed to the FIRST maximum of each 2x2 window of x (torch tie rule),
- *   gs2 = gs * chan_scale[n,c] * (mask_src > 0 ? 1 : slope)      (gs2 != NULL)
- * x, mask_src, gs, gs2: [B,H,W,C] bf16; gy: [B,H/2,W/2,C] bf16. */
+ *   gs2 = gs * chan_scale[n,c] * (mask_bits bit ? 1 : slope)     (gs2 != NULL)
+ * x, gs, gs2: [B,H,W,C] bf16; gy: [B,H/2,W/2,C] bf16; mask_bits: uint32 [B,H,W,C/32] sign bits. */
 FD_API int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int H, int W, int C, fd_bf16* gs,
-                      const fd_bf16* mask_src, const float* chan_scale, float slope, fd_bf16* gs2, void* stream);
+                      const uint32_t* mask_bits, const float* chan_scale, float slope, fd_bf16* gs2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * losses/YoloLoss.py:4-44 for a batch: loss[b] = yolo_loss(pred[b], gt[b]) and, when dpred != NULL,

@@ -1,113 +1,118 @@
 // 3x3 / stride 1 / pad 1 convolution, 64 -> 64 channels, as an implicit GEMM on the sm_100a
-// tensor cores (tcgen05.mma, fp32 accumulators in TMEM), fed by TMA.
+// tensor cores (tcgen05.mma, fp32 accumulators in TMEM), fed and drained by TMA.
 //
-// Replaces aten::conv2d (+ leaky_relu / dropout2d / residual add) at models/PoolResnet.py:35-40
-// of the reference, and -- with dgrad-packed weights -- the input-gradient half of its backward.
+// Replaces aten::conv2d (+ leaky_relu / dropout2d / residual add) at models/PoolResnet.py:35-40 and
+// models/Resnet.py:29-36 of the reference, and -- with dgrad-packed weights -- the input-gradient
+// half of its backward.
 //
 // "Halo-tile" formulation (no im2col, no per-tap reloads):
-//   * one CTA tile = R output rows x W columns of one image.  ONE TMA box {64ch, Wp=W+1, R+2, 1}
-//     starting at (w=-1, h=h0-1) lands the zero-padded input patch in shared memory as
-//     (R+2)*Wp consecutive 128-byte rows (one pixel = 64 bf16 = one 128B-swizzle row).  The
-//     single halo column serves as right halo of row y and left halo of row y+1.
+//   * one CTA tile = R output rows x TW output columns of one image.  ONE TMA box
+//     {64ch, Wp = TW+2, R+2, 1} starting at (w0-1, h0-1) lands the zero-padded input patch in shared
+//     memory as (R+2)*Wp consecutive 128-byte rows (one pixel = 64 bf16 = one 128B-swizzle row; TMA
+//     zero-fills out-of-bounds pixels = the convolution padding).
 //   * GEMM row m = y*Wp + x.  For tap (ky,kx) the A operand of output row m is input row
 //     m + ky*Wp + kx: the *same* shared-memory tile, read through a matrix descriptor whose start
 //     address is shifted by (ky*Wp+kx)*128 bytes.  9 taps x 4 K-steps = 36 MMAs (M=128,N=64,K=16)
-//     per 128-row block, all operands already resident; weights (72 KB) stay in smem for the
-//     whole persistent CTA.
-//   * rows with x == W or y >= R are junk and are simply not stored.
+//     per 128-row block; weights (72 KB) stay in smem for the whole persistent CTA.
+//   * rows with x >= TW or y >= R are junk and are never stored.
+//   * the epilogue writes the output tile DENSE ([R][TW] pixels, 128B-swizzled) into a staging buffer
+//     that one TMA tensor store moves to HBM; a residual operand is TMA-loaded into the same staging
+//     buffer beforehand and updated in place.  No per-thread global loads/stores of activations: a
+//     row-per-thread access pattern touches 32 different 128-byte lines per instruction and makes
+//     the LSU, not the tensor pipe, the bottleneck.
+//   * LeakyReLU' masks travel as sign bits (uint32[B,H,W,2]) instead of bf16 tensors.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..9 = epilogue (TMEM -> registers -> fused bias/LeakyReLU/dropout/residual/mask -> global).
-// Input tiles and TMEM accumulators are double buffered so the epilogue of tile i overlaps the
-// MMAs of tile i+1 and the TMA of tile i+2.
+// Measured on B200: a M=128,N=64,K=16 SS-mode MMA takes ~53 clk (6 KB of smem operands at 128 B/clk),
+// not the 32 clk of the tensor-pipe floor, i.e. ~60 % of dense peak is the ceiling of this shape.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 =
+// epilogue (TMEM lane quadrant = warp % 4, channel half = (warp - 2) / 4).  Input tiles and TMEM
+// accumulators are double buffered: the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "fd_host.h"
 #include "fd_ptx.cuh"
+#include <cstdlib>
 
 namespace fd {
 namespace {
 
 constexpr int kC = 64;
 constexpr int kWBytes = 9 * kC * 128;  // 73728: [tap][cout][cin] bf16, K-major, 128B swizzle
-constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kStoreWarp = 2 + kEpiWarps;          // warp 0 = loads, 1 = MMA, 2..17 = epilogue, 18 = stores
+constexpr int kThreads = (kStoreWarp + 1) * 32;    // 608
 constexpr uint32_t kTmemCols = 512;
 
 struct ConvParams {
-  int B, H, W, R, Wp, nblk, tiles_per_img, num_tiles;
+  int B, H, W, R, TW, Wp, nblk, tiles_w, tiles_h, num_tiles;
   uint32_t in_bytes;      // bytes delivered by one input TMA box
-  uint32_t in_buf_bytes;  // bytes reserved per input copy (multiple of 1024)
+  uint32_t in_buf_bytes;  // bytes reserved per input stage (multiple of 1024)
+  uint32_t stg_bytes;     // bytes of one dense output / residual tile
+  uint32_t stg_buf_bytes; // the same, rounded up to 1024
+  uint32_t inv_wp;        // ceil(65536 / Wp): m / Wp == (m * inv_wp) >> 16 for m < 512
   int flags;
+  int dbg;
+  int has_res;            // a residual tile is TMA-loaded into the staging buffer
+  int staged_out2;        // the staged (TMA-stored) value is the masked second output, not `out`
   float slope;
   const float* bias;
   const float* chan_scale;
-  const __nv_bfloat16* residual;
-  __nv_bfloat16* aux_out;
-  __nv_bfloat16* out;
-  const __nv_bfloat16* mask_src;
   const float* chan_scale2;
-  __nv_bfloat16* out2;
+  const uint16_t* mask_in;      // sign-bit masks, addressed in 16-channel units: [pixel][4]
+  uint16_t* mask_out;
+  __nv_bfloat16* out2_direct;   // both outputs requested: the second one leaves through plain stores
 };
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-    d[i] = u;
-  }
-}
-__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&v)[32]) {
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u = __ldg(s + i);
-    v[8 * i + 0] = bf16lo(u.x); v[8 * i + 1] = bf16hi(u.x);
-    v[8 * i + 2] = bf16lo(u.y); v[8 * i + 3] = bf16hi(u.y);
-    v[8 * i + 4] = bf16lo(u.z); v[8 * i + 5] = bf16hi(u.z);
-    v[8 * i + 6] = bf16lo(u.w); v[8 * i + 7] = bf16hi(u.w);
-  }
-}
+// Optional per-tile timestamps of CTA 0 (FD_CONV_TIMING=1): [tile iteration][8] clock64 values.
+__device__ unsigned long long g_conv_dbg[64 * 8];
+#define FD_TS(slot) do { if (p.dbg && blockIdx.x == 0 && it < 64) g_conv_dbg[it * 8 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
-                  const ConvParams p) {
+                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_out,
+                  const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
+  // Layout: weights | input stage 0 | input stage 1 | staging 0 | staging 1 | constants | barriers.
+  // The junk rows of the last 128-row block read a few rows BEHIND their input stage (into the next
+  // buffer): harmless, those GEMM rows are never stored, so the stages need no zero-filled tail.
   const uint32_t stage_bytes = p.in_buf_bytes;
   uint8_t* sW = smem;
   uint8_t* sIn = smem + kWBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + 2 * stage_bytes);
+  uint8_t* sStg = sIn + ((2 * stage_bytes + 1023u) & ~1023u);     // staging rows are swizzled by (row & 7): 1024-aligned
+  float* sConst = reinterpret_cast<float*>(sStg + 2 * p.stg_buf_bytes);   // [3][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sConst + 3 * kC);
   uint64_t* w_full = bars + 0;
-  uint64_t* in_full = bars + 1;    // [2]
-  uint64_t* in_empty = bars + 3;   // [2]
-  uint64_t* acc_full = bars + 5;   // [2]
-  uint64_t* acc_empty = bars + 7;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* in_full = bars + 1;     // [2]
+  uint64_t* in_empty = bars + 3;    // [2]
+  uint64_t* acc_empty = bars + 5;   // [2]
+  uint64_t* res_full = bars + 7;    // [2]
+  uint64_t* stg_free = bars + 9;    // [2]
+  uint64_t* stg_ready = bars + 11;  // [2]
+  uint64_t* acc_full = bars + 13;   // [2][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // Rows the TMA never writes (tail of each buffer) must read as zero: the tap (2,2) of the last
-  // valid pixel of a tile wraps onto the first row behind the box.
-  for (uint32_t i = threadIdx.x * 16u; i < 2 * stage_bytes; i += kThreads * 16u)
-    *reinterpret_cast<uint4*>(sIn + i) = make_uint4(0, 0, 0, 0);
-  fence_proxy_async();
-
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_in);
     tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_out);
     mbar_init(w_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(in_full + s, 1);
       mbar_init(in_empty + s, 1);
-      mbar_init(acc_full + s, 1);
-      mbar_init(acc_empty + s, 8);
+      mbar_init(acc_empty + s, 1);
+      mbar_init(res_full + s, 1);
+      mbar_init(stg_free + s, 1);
+      mbar_init(stg_ready + s, 1);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(acc_full + i, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -118,6 +123,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -127,151 +133,157 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int s = it & 1, ph = (it >> 1) & 1;
-        const int n = tile / p.tiles_per_img;
-        const int h0 = (tile - n * p.tiles_per_img) * p.R;
-        mbar_wait(in_empty + s, ph ^ 1);
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int th = rem / p.tiles_w;
+        const int h0 = th * p.R, w0 = (rem - th * p.tiles_w) * p.TW;
+        mbar_wait_sleep(in_empty + s, ph ^ 1);
+        FD_TS(0);
         mbar_expect_tx(in_full + s, p.in_bytes);
-        tma_load_4d(sIn + s * stage_bytes, &tm_in, in_full + s, 0, -1, h0 - 1, n);
+        tma_load_4d(sIn + s * stage_bytes, &tm_in, in_full + s, 0, w0 - 1, h0 - 1, n);
+        if (p.has_res) {
+          mbar_wait_sleep(stg_free + s, ph ^ 1);        // the store of tile it-2 has drained this buffer
+          mbar_expect_tx(res_full + s, p.stg_bytes);
+          tma_load_4d(sStg + s * p.stg_buf_bytes, &tm_res, res_full + s, 0, w0, h0, n);
+        }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(128, kC, 0, 0);
-    const uint32_t w_lo = sdesc_lo(smem_u32(sW), 16);
-    mbar_wait(w_full, 0);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int s = it & 1, ph = (it >> 1) & 1;
-      mbar_wait(acc_empty + s, ph ^ 1);
-      mbar_wait(in_full + s, ph);
-      tc_fence_after();
-      if (elect_one_sync()) {
+    // ------------------------------------------------------------------ MMA issuer (one thread runs the whole loop)
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kC, 0, 0);
+      const uint32_t w_lo = sdesc_lo(smem_u32(sW), 16);
+      const uint32_t wp_units = static_cast<uint32_t>(p.Wp) * 8u;
+      mbar_wait(w_full, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(acc_empty + s, ph ^ 1);
+        FD_TS(1);
+        mbar_wait(in_full + s, ph);
+        tc_fence_after();
+        FD_TS(2);
         const uint32_t in_lo = sdesc_lo(smem_u32(sIn + s * stage_bytes), 16);
+#pragma unroll 1
         for (int mb = 0; mb < p.nblk; ++mb) {
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((s * p.nblk + mb) * kC);
-          const uint32_t a_blk = in_lo + static_cast<uint32_t>(mb * 128 * 8);   // 128 rows x 128 B, in 16-B units
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int ky = t / 3, kx = t - 3 * ky;
-            // tap (ky,kx): the same tile, start address shifted by (ky*Wp + kx) rows
-            const uint32_t a_tap = a_blk + static_cast<uint32_t>((ky * p.Wp + kx) * 8);
-            const uint32_t b_tap = w_lo + t * 512;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, sdesc_sw128(a_tap + 2 * k), sdesc_sw128(b_tap + 2 * k), idesc, (t | k) != 0 ? 1u : 0u);
-          }
+          issue_conv3x3_block(tmem_base + static_cast<uint32_t>((s * 4 + mb) * kC),
+                              in_lo + static_cast<uint32_t>(mb * 1024), w_lo, wp_units, idesc, [](int) {});
+          umma_commit(acc_full + s * 4 + mb);   // this 128-row block is ready for the epilogue
         }
-        umma_commit(in_empty + s);   // input tile free once these MMAs have read it
-        umma_commit(acc_full + s);   // accumulators ready for the epilogue
+        umma_commit(in_empty + s);              // input tile free once these MMAs have read it
+        FD_TS(3);
       }
-      __syncwarp();
     }
+    __syncwarp();
+  } else if (warp == kStoreWarp) {
+    // ------------------------------------------------------------------ TMA store issuer
+    // A thread of its own, because draining a bulk store (wait_group.read) blocks the issuing thread.
+    if (elect_one_sync()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int th = rem / p.tiles_w;
+        const int h0 = th * p.R, w0 = (rem - th * p.tiles_w) * p.TW;
+        mbar_wait_sleep(stg_ready + s, ph);
+        tma_store_4d(&tm_out, sStg + s * p.stg_buf_bytes, 0, w0, h0, n);   // beyond the image: clipped
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(stg_free + s);
+        FD_TS(7);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue warps (8)
-    // warp -> TMEM lane quadrant q (hardware rule: warp % 4) and channel half hf: each thread owns
-    // 32 channels (64 B) of one output row.  Residual / mask rows of the next two blocks are
-    // prefetched into registers so that their L2/HBM latency overlaps the MMAs and the math.
+    // ------------------------------------------------------------------ epilogue warps (16)
+    // One thread = one GEMM row (pixel) x 16 channels.  TMEM lane quadrant = warp % 4 (hardware rule),
+    // channel quarter = (warp - 2) / 4.
     const int q = warp & 3;
-    const int hf = (warp - 2) >> 2;
-    const int c0 = hf * 32;
-    const bool need_res = p.residual != nullptr;
-    const bool need_mask = p.out2 != nullptr;
-    int it = 0;
+    const int cq = (warp - 2) >> 2;
+    const int c0 = cq * 16;
+    const int et = threadIdx.x - 64;
+    const uint64_t slope2 = pk2(p.slope, p.slope);
+    const bool lrelu = (p.flags & FD_EPI_LRELU) != 0;
+    const bool has_cs = p.chan_scale != nullptr, has_cs2 = p.chan_scale2 != nullptr;
+    if (et < kC) sConst[et] = p.bias ? __ldg(p.bias + et) : 0.f;
+    int it = 0, last_n = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
-      const int n = tile / p.tiles_per_img;
-      const int h0 = (tile - n * p.tiles_per_img) * p.R;
-      uint4 pre_r[2][4], pre_m[2][4];
-      auto geometry = [&](int mb, bool& valid, size_t& pix) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int th = rem / p.tiles_w;
+      const int h0 = th * p.R, w0 = (rem - th * p.tiles_w) * p.TW;
+      if (n != last_n) {          // per-image Dropout2d multipliers (uniform branch: n depends on the tile only)
+        bar_sync_epi();           // nobody still reads the previous image's values
+        if (et >= kC && et < 2 * kC) sConst[et] = has_cs ? __ldg(p.chan_scale + n * kC + et - kC) : 1.f;
+        else if (et >= 2 * kC && et < 3 * kC) sConst[et] = has_cs2 ? __ldg(p.chan_scale2 + n * kC + et - 2 * kC) : 1.f;
+        bar_sync_epi();
+        last_n = n;
+      }
+      uint8_t* stg = sStg + s * p.stg_buf_bytes;
+      // staging buffer: either the residual tile has landed in it, or the store of tile it-2 has drained it
+      if (p.has_res) mbar_wait_sleep(res_full + s, ph);
+      else mbar_wait_sleep(stg_free + s, ph ^ 1);
+      if (et == 0) FD_TS(4);
+#pragma unroll 1
+      for (int mb = 0; mb < p.nblk; ++mb) {
         const int m = mb * 128 + q * 32 + lane;
-        const int y = m / p.Wp;
+        const int y = static_cast<int>((static_cast<uint32_t>(m) * p.inv_wp) >> 16);
         const int x = m - y * p.Wp;
-        const int oy = h0 + y;
-        valid = (y < p.R) && (x < p.W) && (oy < p.H);
-        pix = (static_cast<size_t>(n) * p.H + oy) * p.W + x;
-      };
-#define FD_PREFETCH(MB, SLOT)                                                                        \
-  {                                                                                                  \
-    bool v_;                                                                                         \
-    size_t px_;                                                                                      \
-    geometry(MB, v_, px_);                                                                           \
-    if (v_) {                                                                                        \
-      if (need_res) {                                                                                \
-        const uint4* r_ = reinterpret_cast<const uint4*>(p.residual + px_ * kC + c0);                \
-        _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) pre_r[SLOT][i_] = __ldg(r_ + i_);           \
-      }                                                                                              \
-      if (need_mask) {                                                                               \
-        const uint4* m_ = reinterpret_cast<const uint4*>(p.mask_src + px_ * kC + c0);                \
-        _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) pre_m[SLOT][i_] = __ldg(m_ + i_);           \
-      }                                                                                              \
-    }                                                                                                \
-  }
-      FD_PREFETCH(0, 0)
-      if (p.nblk > 1) FD_PREFETCH(1, 1)
-      mbar_wait(acc_full + s, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int mb = 0; mb < 4; ++mb) {
-        if (mb < p.nblk) {
-          bool valid;
-          size_t pix;
-          geometry(mb, valid, pix);
-          uint32_t acc[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>((s * p.nblk + mb) * kC + c0),
-                             acc);
-          tmem_ld_wait();
-          if (valid) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + c0 + j);
-            }
-            if (p.flags & FD_EPI_LRELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
-            }
-            if (p.chan_scale) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= __ldg(p.chan_scale + n * kC + c0 + j);
-            }
-            if (p.aux_out) store_bf16x32(p.aux_out + pix * kC + c0, v);
-            if (need_res) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 u = pre_r[mb & 1][i];
-                v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
-                v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
-                v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
-                v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
-              }
-            }
-            if (p.out) store_bf16x32(p.out + pix * kC + c0, v);
-            if (need_mask) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 u = pre_m[mb & 1][i];
-                const float mk[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y),
-                                     bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  float g = v[8 * i + e] * (mk[e] > 0.f ? 1.f : p.slope);
-                  if (p.chan_scale2) g *= __ldg(p.chan_scale2 + n * kC + c0 + 8 * i + e);
-                  v[8 * i + e] = g;
-                }
-              }
-              store_bf16x32(p.out2 + pix * kC + c0, v);
+        const int oy = h0 + y, ox = w0 + x;
+        const bool valid = (y < p.R) && (x < p.TW) && (oy < p.H) && (ox < p.W);
+        const size_t pix = (static_cast<size_t>(n) * p.H + oy) * p.W + ox;
+        uint32_t mbits = 0xffffu;
+        if (valid && p.mask_in) mbits = __ldg(p.mask_in + pix * 4 + cq);     // latency hidden by the MMA wait
+        const uint32_t d = static_cast<uint32_t>(y * p.TW + x);              // row of the dense staging tile
+        uint8_t* row = stg + d * 128u;
+        const uint32_t ch0 = ((static_cast<uint32_t>(cq) * 2u) ^ (d & 7u)) << 4;
+        const uint32_t ch1 = ((static_cast<uint32_t>(cq) * 2u + 1u) ^ (d & 7u)) << 4;
+        mbar_wait_sleep(acc_full + s * 4 + mb, ph, 1000);
+        tc_fence_after();
+        uint32_t acc[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>((s * 4 + mb) * kC + c0),
+                           acc);
+        tmem_ld_wait();
+        if (valid) {
+          uint64_t v2[8];
+          epi_bias_act16(acc, sConst + c0, sConst + kC + c0, lrelu, has_cs, slope2, v2);
+          if (p.mask_out) p.mask_out[pix * 4 + cq] = static_cast<uint16_t>(epi_sign_bits16(v2));
+          if (p.has_res)
+            epi_add_bf16x16(v2, *reinterpret_cast<const uint4*>(row + ch0), *reinterpret_cast<const uint4*>(row + ch1));
+          uint4 u0, u1;
+          if (!p.staged_out2) {
+            epi_pack16(v2, u0, u1);
+            *reinterpret_cast<uint4*>(row + ch0) = u0;
+            *reinterpret_cast<uint4*>(row + ch1) = u1;
+          }
+          if (p.staged_out2 || p.out2_direct) {
+            uint64_t o2[8];
+            epi_masked16(v2, mbits, p.slope, sConst + 2 * kC + c0, has_cs2, o2);
+            epi_pack16(o2, u0, u1);
+            if (p.staged_out2) {
+              *reinterpret_cast<uint4*>(row + ch0) = u0;
+              *reinterpret_cast<uint4*>(row + ch1) = u1;
+            } else {
+              uint4* gp = reinterpret_cast<uint4*>(p.out2_direct + pix * kC + c0);
+              gp[0] = u0;
+              gp[1] = u1;
             }
           }
-          if (mb + 2 < p.nblk) FD_PREFETCH(mb + 2, mb & 1)
         }
       }
-#undef FD_PREFETCH
+      if (et == 0) FD_TS(5);
+      fence_proxy_async();       // staging writes (generic proxy) -> visible to the TMA store
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + s);
+      bar_sync_epi();
+      if (et == 0) {
+        FD_TS(6);
+        mbar_arrive(acc_empty + s);     // TMEM of this tile has been read by everyone
+        mbar_arrive(stg_ready + s);     // staging tile complete: the store warp takes over
+      }
     }
   }
 
@@ -280,70 +292,98 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// Exactly the TMA box.  The 128B swizzle of TMA and of the UMMA descriptors is a function of the absolute
+// shared-memory address bits, so a stage only needs 128-byte (not 1024-byte) alignment.
+inline size_t in_buf_bytes_for(int R, int Wp) { return static_cast<size_t>((R + 2) * Wp) * 128; }
+inline size_t stg_buf_bytes_for(int R, int TW) { return (static_cast<size_t>(R) * TW * 128 + 1023) / 1024 * 1024; }
+inline size_t smem_for(int nblk, int Wp, int R, int TW) {
+  const size_t in_buf = in_buf_bytes_for(R, Wp);
+  const size_t bufs = (2 * in_buf + 1023) / 1024 * 1024 + 2 * stg_buf_bytes_for(R, TW);
+  // the last 128-row block of stage 1 reads up to row nblk*128 - 1 + 2*Wp + 2 of its stage: the allocation
+  // must cover that (normally it ends inside the staging buffers)
+  const size_t reach = in_buf + static_cast<size_t>(nblk * 128 + 2 * Wp + 2) * 128;
+  const size_t body = bufs + 3 * kC * 4 + 256;
+  return kWBytes + (body > reach ? body : reach) + 1024;
+}
+
 }  // namespace
 }  // namespace fd
 
+extern "C" FD_API int fd_debug_conv_timing(unsigned long long* out, int n) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, fd::g_conv_dbg, sizeof(unsigned long long) * n));
+}
+
 extern "C" int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, int W, int C, const float* bias,
-                          float slope, const float* chan_scale, const fd_bf16* residual, fd_bf16* aux_out,
-                          fd_bf16* out, const fd_bf16* mask_src, const float* chan_scale2, fd_bf16* out2,
+                          float slope, const float* chan_scale, const fd_bf16* residual, uint32_t* mask_out,
+                          fd_bf16* out, const uint32_t* mask_in, const float* chan_scale2, fd_bf16* out2,
                           int flags, void* stream) {
   using namespace fd;
   if (!x || !w_packed || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
-  if (C != kC || W + 8 > 256) return FD_EUNSUPPORTED;
-  if ((out2 != nullptr) != (mask_src != nullptr)) return FD_EINVAL;
-  if (!out && !aux_out && !out2) return FD_EINVAL;
+  if (C != kC) return FD_EUNSUPPORTED;
+  if (!out && !out2) return FD_EINVAL;
+  if (mask_in && !out2) return FD_EINVAL;
+  if (!(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;   // LeakyReLU is evaluated as max(v, slope*v)
   const int nsm = sm_count();
-  const int Wp = W + 1;
-  const int ncopies = 1;
   const size_t smem_cap = 227 * 1024;
 
-  // Pick the rows-per-tile R that minimises a simple cycle model: MMA time of the padded
-  // row blocks plus the TMA fill, times the number of waves over the SMs.
-  int bestR = 0;
+  // Tiling: TW <= 62 output columns (Wp = TW + 2 <= 64 GEMM rows per image row), R rows with R*Wp <= 512.
+  // Pick the (column tiles, R) pair that minimises a simple cycle model: MMA time of the padded 128-row
+  // blocks (smem-operand bound, ~1900 clk each) times the number of waves over the SMs.
+  int bestR = 0, bestTW = 0;
   double best = 1e30;
-  for (int R = 1; R <= H && R + 2 <= 256; ++R) {
-    const int nblk = (R * Wp + 127) / 128;
-    if (nblk > 4) break;
-    const size_t in_buf = (static_cast<size_t>(nblk * 128 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024;
-    const size_t need = kWBytes + 2 * ncopies * in_buf + 256 + 1024;
-    if (need > smem_cap) break;
-    const long tiles = static_cast<long>(B) * ((H + R - 1) / R);
-    const long waves = (tiles + nsm - 1) / nsm;
-    const double per_tile = 1152.0 * nblk + 0.35 * ncopies * (R + 2) * Wp * 128 / 32.0 + 700.0;
-    const double cost = waves * per_tile;
-    if (cost < best) { best = cost; bestR = R; }
+  const int min_tw_tiles = (W + 61) / 62;
+  for (int tw_tiles = min_tw_tiles; tw_tiles <= min_tw_tiles + 1; ++tw_tiles) {
+    const int TW = (W + tw_tiles - 1) / tw_tiles;
+    const int Wp = TW + 2;
+    for (int R = 1; R <= H && R + 2 <= 256; ++R) {
+      const int nblk = (R * Wp + 127) / 128;
+      if (nblk > 4) break;
+      if (smem_for(nblk, Wp, R, TW) > smem_cap) break;
+      const long tiles = static_cast<long>(B) * ((H + R - 1) / R) * tw_tiles;
+      const long waves = (tiles + nsm - 1) / nsm;
+      const double cost = waves * (1900.0 * nblk + 400.0);
+      if (cost < best) { best = cost; bestR = R; bestTW = TW; }
+    }
   }
   if (bestR == 0) return FD_EUNSUPPORTED;
 
   ConvParams p;
-  p.B = B; p.H = H; p.W = W; p.R = bestR; p.Wp = Wp;
-  p.nblk = (bestR * Wp + 127) / 128;
-  p.tiles_per_img = (H + bestR - 1) / bestR;
-  p.num_tiles = B * p.tiles_per_img;
-  p.in_bytes = static_cast<uint32_t>((bestR + 2) * Wp * 128);
-  p.in_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.nblk * 128 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024);
+  p.B = B; p.H = H; p.W = W; p.R = bestR; p.TW = bestTW; p.Wp = bestTW + 2;
+  p.nblk = (bestR * p.Wp + 127) / 128;
+  p.tiles_w = (W + bestTW - 1) / bestTW;
+  p.tiles_h = (H + bestR - 1) / bestR;
+  p.num_tiles = B * p.tiles_w * p.tiles_h;
+  p.in_bytes = static_cast<uint32_t>((bestR + 2) * p.Wp * 128);
+  p.in_buf_bytes = static_cast<uint32_t>(in_buf_bytes_for(bestR, p.Wp));
+  p.stg_bytes = static_cast<uint32_t>(bestR * bestTW * 128);
+  p.stg_buf_bytes = static_cast<uint32_t>(stg_buf_bytes_for(bestR, bestTW));
+  p.inv_wp = static_cast<uint32_t>((65536 + p.Wp - 1) / p.Wp);
   p.flags = flags;
+  { const char* d = getenv("FD_CONV_TIMING"); p.dbg = d ? atoi(d) : 0; }
   p.slope = slope;
-  p.bias = bias; p.chan_scale = chan_scale;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.aux_out = reinterpret_cast<__nv_bfloat16*>(aux_out);
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.mask_src = reinterpret_cast<const __nv_bfloat16*>(mask_src);
-  p.chan_scale2 = chan_scale2;
-  p.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
+  p.bias = bias; p.chan_scale = chan_scale; p.chan_scale2 = chan_scale2;
+  p.mask_in = reinterpret_cast<const uint16_t*>(mask_in); p.mask_out = reinterpret_cast<uint16_t*>(mask_out);
+  p.has_res = residual != nullptr;
+  p.staged_out2 = (out == nullptr);
+  p.out2_direct = (out && out2) ? reinterpret_cast<__nv_bfloat16*>(out2) : nullptr;
+  const size_t smem = smem_for(p.nblk, p.Wp, bestR, bestTW);
 
-  CUtensorMap tm_in, tm_w;
-  int rc = make_tmap_nhwc_bf16(&tm_in, x, B, H, W, C, Wp, bestR + 2);
+  CUtensorMap tm_in, tm_w, tm_res, tm_out;
+  int rc = make_tmap_nhwc_bf16(&tm_in, x, B, H, W, C, p.Wp, bestR + 2);
   if (rc != FD_OK) return rc;
   rc = make_tmap_2d_bf16(&tm_w, w_packed, 9 * kC, kC, kC, kC);
   if (rc != FD_OK) return rc;
+  const fd_bf16* staged = out ? out : out2;
+  rc = make_tmap_nhwc_bf16(&tm_out, staged, B, H, W, C, bestTW, bestR);
+  if (rc != FD_OK) return rc;
+  rc = make_tmap_nhwc_bf16(&tm_res, residual ? residual : staged, B, H, W, C, bestTW, bestR);
+  if (rc != FD_OK) return rc;
 
-  const size_t smem = kWBytes + 2 * static_cast<size_t>(ncopies) * p.in_buf_bytes + 256 + 1024;
   cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = p.num_tiles < nsm ? p.num_tiles : nsm;
-  conv3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_in, tm_w, p);
+  conv3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_in, tm_w, tm_res, tm_out, p);
   count_launch();
   return launch_status();
 }

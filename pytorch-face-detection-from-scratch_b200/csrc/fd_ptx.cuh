@@ -62,6 +62,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, with a suspend-time hint: the waiting warp sleeps in hardware (up to `ns`) instead of re-issuing
+// try_wait every few cycles and stealing issue slots from the warps that have work.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 4000) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -138,6 +156,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- descriptors
@@ -174,6 +201,141 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// The 36 MMAs (9 taps x 4 K-steps, M=128, N=64, K=16) of one 128-row block of a 3x3 convolution in the
+// halo-tile formulation: tap (ky,kx) reads the A tile shifted by (ky*Wp + kx) rows (128 B = 8 descriptor
+// units each), B = tap t of the packed weights (8 KB = 512 units apart).  Loops over the taps stay ROLLED
+// and the descriptors advance incrementally: ptxas otherwise precomputes all 72 descriptors, runs out of
+// uniform registers and spills (MOV.SPILL / R2UR), and the single issuing thread - not the tensor pipe -
+// becomes the bottleneck.  `after_tap(t)` runs after the MMAs of tap t (commit hooks).
+template <typename F>
+__device__ __forceinline__ void issue_conv3x3_block(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t wp_units,
+                                                    uint32_t idesc, F&& after_tap) {
+  uint32_t acc = 0;
+  int t = 0;
+#pragma unroll 1
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll 1
+    for (int kx = 0; kx < 3; ++kx, ++t) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        umma_bf16(d_tmem, sdesc_sw128(a_lo + 2 * k), sdesc_sw128(b_lo + 2 * k), idesc, acc);
+        acc = 1;
+      }
+      after_tap(t);
+      a_lo += 8;
+      b_lo += 512;
+    }
+    a_lo += wp_units - 24;      // next tap row: + Wp rows, minus the 3 columns already walked
+  }
+}
+
+// ----------------------------------------------------------------------------- packed fp32x2 math (FADD2 / FMUL2)
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// ----------------------------------------------------------------------------- epilogue building blocks
+// One thread = one output pixel x 16 channels (8 packed pairs).  Shared by conv3x3_tc.cu and
+// resblock_chain.cu so that both paths round identically.
+//   v = acc + bias ; v = max(v, slope*v) (LeakyReLU, 0 <= slope <= 1) ; v *= chan_scale
+__device__ __forceinline__ void epi_bias_act16(const uint32_t (&acc)[16], const float* s_bias, const float* s_cs,
+                                               bool lrelu, bool has_cs, uint64_t slope2, uint64_t (&v2)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 4 * i);
+    v2[2 * i] = add2(pk2u(acc[4 * i], acc[4 * i + 1]), pk2(b4.x, b4.y));
+    v2[2 * i + 1] = add2(pk2u(acc[4 * i + 2], acc[4 * i + 3]), pk2(b4.z, b4.w));
+  }
+  if (lrelu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a0, a1, t0, t1;
+      upk2(v2[i], a0, a1);
+      upk2(mul2(v2[i], slope2), t0, t1);
+      v2[i] = pk2(fmaxf(a0, t0), fmaxf(a1, t1));
+    }
+  }
+  if (has_cs) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 s4 = *reinterpret_cast<const float4*>(s_cs + 4 * i);
+      v2[2 * i] = mul2(v2[2 * i], pk2(s4.x, s4.y));
+      v2[2 * i + 1] = mul2(v2[2 * i + 1], pk2(s4.z, s4.w));
+    }
+  }
+}
+// 16 sign bits, bit j set iff the sign bit of channel j is clear (v >= +0; -0 and negatives -> 0).
+// One funnel shift per element: m = (m << 1) | (bits(v) >> 31), walked from channel 15 down to 0.
+__device__ __forceinline__ uint32_t epi_sign_bits16(const uint64_t (&v2)[8]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 7; i >= 0; --i) {
+    const uint32_t lo = static_cast<uint32_t>(v2[i]), hi = static_cast<uint32_t>(v2[i] >> 32);
+    m = __funnelshift_l(hi, m, 1);
+    m = __funnelshift_l(lo, m, 1);
+  }
+  return (~m) & 0xFFFFu;
+}
+// v += bf16 residual (two 16-byte chunks = 16 channels)
+__device__ __forceinline__ void epi_add_bf16x16(uint64_t (&v2)[8], const uint4& u0, const uint4& u1) {
+  v2[0] = add2(v2[0], pk2u(u0.x << 16, u0.x & 0xFFFF0000u));
+  v2[1] = add2(v2[1], pk2u(u0.y << 16, u0.y & 0xFFFF0000u));
+  v2[2] = add2(v2[2], pk2u(u0.z << 16, u0.z & 0xFFFF0000u));
+  v2[3] = add2(v2[3], pk2u(u0.w << 16, u0.w & 0xFFFF0000u));
+  v2[4] = add2(v2[4], pk2u(u1.x << 16, u1.x & 0xFFFF0000u));
+  v2[5] = add2(v2[5], pk2u(u1.y << 16, u1.y & 0xFFFF0000u));
+  v2[6] = add2(v2[6], pk2u(u1.z << 16, u1.z & 0xFFFF0000u));
+  v2[7] = add2(v2[7], pk2u(u1.w << 16, u1.w & 0xFFFF0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi);
+__device__ __forceinline__ void epi_pack16(const uint64_t (&v2)[8], uint4& u0, uint4& u1) {
+  float a0, a1;
+  upk2(v2[0], a0, a1); u0.x = pack_bf16x2(a0, a1);
+  upk2(v2[1], a0, a1); u0.y = pack_bf16x2(a0, a1);
+  upk2(v2[2], a0, a1); u0.z = pack_bf16x2(a0, a1);
+  upk2(v2[3], a0, a1); u0.w = pack_bf16x2(a0, a1);
+  upk2(v2[4], a0, a1); u1.x = pack_bf16x2(a0, a1);
+  upk2(v2[5], a0, a1); u1.y = pack_bf16x2(a0, a1);
+  upk2(v2[6], a0, a1); u1.z = pack_bf16x2(a0, a1);
+  upk2(v2[7], a0, a1); u1.w = pack_bf16x2(a0, a1);
+}
+// o = v * (mask bit ? 1 : slope) * chan_scale2   (the LeakyReLU' + Dropout2d step of the backward chain)
+__device__ __forceinline__ void epi_masked16(const uint64_t (&v2)[8], uint32_t mbits, float slope, const float* s_cs2,
+                                             bool has_cs2, uint64_t (&o2)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a0, a1;
+    upk2(v2[i], a0, a1);
+    a0 = ((mbits >> (2 * i)) & 1u) ? a0 : a0 * slope;
+    a1 = ((mbits >> (2 * i + 1)) & 1u) ? a1 : a1 * slope;
+    o2[i] = pk2(a0, a1);
+    if (has_cs2) {
+      const float2 s2 = *reinterpret_cast<const float2*>(s_cs2 + 2 * i);
+      o2[i] = mul2(o2[i], pk2(s2.x, s2.y));
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------- small helpers

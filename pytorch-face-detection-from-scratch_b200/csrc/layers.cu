@@ -253,7 +253,7 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
 __global__ void __launch_bounds__(kHeadThreads)
 head_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ w,
                 const float* __restrict__ y, const float* __restrict__ dy, int B, int H, int W, int C, int K, int pad,
-                int Ho, int Wo, __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ mask_src,
+                int Ho, int Wo, __nv_bfloat16* __restrict__ dx, const uint32_t* __restrict__ mask_bits,
                 const float* __restrict__ cs2, float slope, __nv_bfloat16* __restrict__ dx2, float* __restrict__ dw,
                 float* __restrict__ dbias) {
   extern __shared__ float sm[];
@@ -303,7 +303,7 @@ head_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
       const size_t gi = (static_cast<size_t>(n) * H * W + pix) * C + c;
       if (dx) dx[gi] = __float2bfloat16(acc);
       if (dx2) {
-        const float m = __bfloat162float(mask_src[gi]) > 0.f ? 1.f : slope;
+        const float m = ((mask_bits[gi >> 5] >> (gi & 31)) & 1u) ? 1.f : slope;
         dx2[gi] = __float2bfloat16(acc * m * s2);
       }
     }
@@ -335,7 +335,7 @@ template <int K, int PAD>
 __global__ void __launch_bounds__(kHeadThreads)
 head_bwd_small_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ w,
                       const float* __restrict__ y, const float* __restrict__ dy, int B, int H, int W, int Ho, int Wo,
-                      __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ mask_src,
+                      __nv_bfloat16* __restrict__ dx, const uint32_t* __restrict__ mask_bits,
                       const float* __restrict__ cs2, float slope, __nv_bfloat16* __restrict__ dx2,
                       float* __restrict__ dw, float* __restrict__ dbias) {
   constexpr int C = 64, KK = K * K, MW = 16, CP = C + 1;
@@ -406,7 +406,7 @@ head_bwd_small_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
           const float v = acc[ix] * s;
           if (dx) dx[gi] = __float2bfloat16(v);
           if (dx2) {
-            const float m = __bfloat162float(mask_src[gi]) > 0.f ? 1.f : slope;
+            const float m = ((mask_bits[gi >> 5] >> (gi & 31)) & 1u) ? 1.f : slope;
             dx2[gi] = __float2bfloat16(v * m * s2);
           }
         }
@@ -494,7 +494,7 @@ __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B
 
 __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, int B,
                                       int H, int W, int C, __nv_bfloat16* __restrict__ gs,
-                                      const __nv_bfloat16* __restrict__ mask_src, const float* __restrict__ cs,
+                                      const uint32_t* __restrict__ mask_bits, const float* __restrict__ cs,
                                       float slope, __nv_bfloat16* __restrict__ gs2) {
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
   const long total = static_cast<long>(B) * Ho * Wo * C8;
@@ -525,11 +525,11 @@ __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const
       for (int j = 0; j < 8; ++j) o[j] = arg[j] == k ? g[j] : 0.f;
       if (gs) *reinterpret_cast<uint4*>(gs + base + off[k]) = pack8(o);
       if (gs2) {
-        float mk[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(mask_src + base + off[k])), mk);
+        const long e0 = base + off[k];                 // element index; C % 32 == 0 keeps 8 channels in one word
+        const uint32_t mk = __ldg(mask_bits + (e0 >> 5)) >> (e0 & 31);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float t = o[j] * (mk[j] > 0.f ? 1.f : slope);
+          float t = o[j] * (((mk >> j) & 1u) ? 1.f : slope);
           if (cs) t *= cs[n * C + c8 * 8 + j];
           o[j] = t;
         }
@@ -651,10 +651,11 @@ extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const floa
 }
 
 extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* y, const float* dy,
-                           int B, int H, int W, int C, int K, int pad, fd_bf16* dx, const fd_bf16* mask_src,
+                           int B, int H, int W, int C, int K, int pad, fd_bf16* dx, const uint32_t* mask_bits,
                            const float* chan_scale2, float slope, fd_bf16* dx2, float* dw, float* dbias, void* stream) {
   if (!x || !w || !y || !dy || !dw || !dbias || B <= 0) return FD_EINVAL;
-  if ((dx2 != nullptr) != (mask_src != nullptr)) return FD_EINVAL;
+  if ((dx2 != nullptr) != (mask_bits != nullptr)) return FD_EINVAL;
+  if (C % 32 != 0) return FD_EUNSUPPORTED;
   if ((H * W * C) % 8 != 0 || kHeadThreads % C != 0) return FD_EUNSUPPORTED;
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
@@ -666,7 +667,7 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
     if (e2 != cudaSuccess) return (int)e2;
     kern<<<min(B, 2 * sm_count()), kHeadThreads, sm_small, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, y, dy, B, H, W, Ho, Wo,
-        reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(mask_src), chan_scale2, slope,
+        reinterpret_cast<__nv_bfloat16*>(dx), mask_bits, chan_scale2, slope,
         reinterpret_cast<__nv_bfloat16*>(dx2), dw, dbias);
     count_launch();
     return launch_status();
@@ -678,7 +679,7 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
   if (e != cudaSuccess) return (int)e;
   head_bwd_kernel<<<min(B, sm_count()), kHeadThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, y, dy, B, H, W, C, K, pad, Ho, Wo,
-      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(mask_src), chan_scale2, slope,
+      reinterpret_cast<__nv_bfloat16*>(dx), mask_bits, chan_scale2, slope,
       reinterpret_cast<__nv_bfloat16*>(dx2), dw, dbias);
   count_launch();
   return launch_status();
@@ -695,15 +696,16 @@ extern "C" int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, f
 }
 
 extern "C" int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int H, int W, int C, fd_bf16* gs,
-                                 const fd_bf16* mask_src, const float* chan_scale, float slope, fd_bf16* gs2,
+                                 const uint32_t* mask_bits, const float* chan_scale, float slope, fd_bf16* gs2,
                                  void* stream) {
   if (!x || !gy || (!gs && !gs2) || B <= 0) return FD_EINVAL;
-  if ((gs2 != nullptr) != (mask_src != nullptr)) return FD_EINVAL;
+  if ((gs2 != nullptr) != (mask_bits != nullptr)) return FD_EINVAL;
+  if (gs2 && C % 32 != 0) return FD_EUNSUPPORTED;
   if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
   const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
   maxpool2x2_bwd_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gy), B, H, W, C,
-      reinterpret_cast<__nv_bfloat16*>(gs), reinterpret_cast<const __nv_bfloat16*>(mask_src), chan_scale, slope,
+      reinterpret_cast<__nv_bfloat16*>(gs), mask_bits, chan_scale, slope,
       reinterpret_cast<__nv_bfloat16*>(gs2));
   count_launch();
   return launch_status();

@@ -57,6 +57,10 @@ struct ChainParams {
   CUtensorMap maps[kMaxMaps];
 };
 
+// Optional per-layer timestamps of CTA 0 (FD_CHAIN_TIMING=1): [layer][16] clock64 values.
+__device__ unsigned long long g_chain_dbg[kMaxLayers * 16];
+#define FD_TS(slot) do { if (p.dbg && blockIdx.x == 0 && (lane == 0 || warp == 1)) g_chain_dbg[l * 16 + (slot)] = clock64(); } while (0)
+
 __device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 __device__ __forceinline__ uint32_t sign_bits(const float (&v)[32]) {
@@ -97,10 +101,8 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_in0);
-    for (int t = 0; t < 9; ++t) {
-      mbar_init(w_full + t, 1);
-      mbar_init(w_empty + t, 1);
-    }
+    mbar_init(w_full, 1);
+    for (int t = 0; t < 9; ++t) mbar_init(w_empty + t, 1);
     mbar_init(in_full, 1);
     mbar_init(act_ready, 1);
     for (int m = 0; m < 4; ++m) mbar_init(acc_full + m, 1);
@@ -123,13 +125,13 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         for (int l = 0; l < p.n_layers; ++l, ++g) {
           const int row0 = p.L[l].w_row;
           for (int t = 0; t < 9; ++t) {
-            mbar_wait(w_empty + t, (g & 1) ^ 1);
-            mbar_expect_tx(w_full + t, kTapBytes);
-            tma_load_2d(sW + t * kTapBytes, &tm_w, w_full + t, 0, row0 + t * kC);
+            mbar_wait_sleep(w_empty + t, (g & 1) ^ 1);
+            if (t == 0) mbar_expect_tx(w_full, kWBytes);      // one "weights of this layer landed" barrier
+            tma_load_2d(sW + t * kTapBytes, &tm_w, w_full, 0, row0 + t * kC);
           }
           if (l == 0) {
             // the buffers are free once the last epilogue of the previous image (and its stores) are done
-            if (g > 0) mbar_wait(act_ready, (g - 1) & 1);
+            if (g > 0) mbar_wait_sleep(act_ready, (g - 1) & 1);
             mbar_expect_tx(in_full, p.box_bytes * p.n_init);
             tma_load_4d(sBuf, &tm_in0, in_full, 0, -1, -1, n);
             if (p.n_init > 1) tma_load_4d(sBuf + p.buf_bytes, &tm_in1, in_full, 0, -1, -1, n);
@@ -138,163 +140,189 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(128, kC, 0, 0);
-    const uint32_t w_lo = sdesc_lo(smem_u32(sW), 16);
-    int g = 0, it = 0;
-    for (int n = blockIdx.x; n < p.B; n += gridDim.x, ++it) {
-      for (int l = 0; l < p.n_layers; ++l, ++g) {
-        if (l == 0) mbar_wait(in_full, it & 1);
-        if (g > 0) mbar_wait(act_ready, (g - 1) & 1);
-        tc_fence_after();
-        if (elect_one_sync()) {
+    // ------------------------------------------------------------------ MMA issuer (one thread runs the whole loop nest)
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kC, 0, 0);
+      const uint32_t w_lo = sdesc_lo(smem_u32(sW), 16);
+      const uint32_t wp_units = static_cast<uint32_t>(p.Wp) * 8u;
+      const int last_mb = p.nblk - 1;
+      int g = 0, it = 0;
+      for (int n = blockIdx.x; n < p.B; n += gridDim.x, ++it) {
+        for (int l = 0; l < p.n_layers; ++l, ++g) {
+          if (l == 0) mbar_wait(in_full, it & 1);
+          if (g > 0) mbar_wait(act_ready, (g - 1) & 1);
+          mbar_wait(w_full, g & 1);
+          tc_fence_after();
+          FD_TS(0);
           const uint32_t in_lo = sdesc_lo(smem_u32(sBuf + p.L[l].in_buf * p.buf_bytes), 16);
+#pragma unroll 1
           for (int mb = 0; mb < p.nblk; ++mb) {
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mb * kC);
-            const uint32_t a_blk = in_lo + static_cast<uint32_t>(mb * 128 * 8);
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              const int ky = t / 3, kx = t - 3 * ky;
-              if (mb == 0) mbar_wait(w_full + t, g & 1);
-              const uint32_t a_tap = a_blk + static_cast<uint32_t>((ky * p.Wp + kx) * 8);
-              const uint32_t b_tap = w_lo + t * (kTapBytes / 16);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, sdesc_sw128(a_tap + 2 * k), sdesc_sw128(b_tap + 2 * k), idesc, (t | k) != 0 ? 1u : 0u);
-              if (mb == p.nblk - 1) umma_commit(w_empty + t);   // slot t may be refilled with the next layer's tap
-            }
+            const bool release = (mb == last_mb);
+            issue_conv3x3_block(tmem_base + static_cast<uint32_t>(mb * kC), in_lo + static_cast<uint32_t>(mb * 1024),
+                                w_lo, wp_units, idesc, [&](int t) {
+                                  if (release) umma_commit(w_empty + t);   // slot t may be refilled
+                                });
             umma_commit(acc_full + mb);
           }
+          FD_TS(1);
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps (8)
+    // Issue-slot bound (4 SMSPs x 1 instr/clk), so the arithmetic runs on packed fp32x2 (FADD2/FMUL2),
+    // LeakyReLU is max(v, slope*v) (0 <= slope <= 1) and the mb loop is rolled (I-cache).
     const int q = warp & 3;
     const int hf = (warp - 2) >> 2;
     const int c0 = hf * 32;
     const int et = threadIdx.x - 64;
+    const uint64_t slope2 = pk2(p.slope, p.slope);
+    const float4* sBias4 = reinterpret_cast<const float4*>(sConst + c0);
+    const float4* sCs4 = reinterpret_cast<const float4*>(sConst + kC + c0);
     int g = 0, it = 0;
     for (int n = blockIdx.x; n < p.B; n += gridDim.x, ++it) {
-      mbar_wait(in_full, it & 1);
+      mbar_wait_sleep(in_full, it & 1);
       for (int l = 0; l < p.n_layers; ++l, ++g) {
         const ChainLayer& L = p.L[l];
         // stores issued two layers ago have finished reading the buffers this layer overwrites
+        if (warp == 2) FD_TS(2);
         if (et == 0) tma_store_wait_read<1>();
         if (et < kC) sConst[et] = L.bias ? __ldg(L.bias + et) : 0.f;
         else if (et < 2 * kC) sConst[et] = L.chan_scale ? __ldg(L.chan_scale + n * kC + et - kC) : 1.f;
         else if (et < 3 * kC) sConst[et] = L.chan_scale2 ? __ldg(L.chan_scale2 + n * kC + et - 2 * kC) : 1.f;
-        uint32_t mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-        if (L.mask_in) {
-#pragma unroll
-          for (int mb = 0; mb < 4; ++mb) {
-            const int m = mb * 128 + q * 32 + lane;
-            const int y = m / p.Wp, x = m - y * p.Wp;
-            if (mb < p.nblk && y < p.H && x < p.W)
-              mk[mb] = __ldg(L.mask_in + ((static_cast<size_t>(n) * p.H + y) * p.W + x) * 2 + hf);
-          }
-        }
         bar_sync_epi();
         uint8_t* vbuf = L.v_buf >= 0 ? sBuf + L.v_buf * p.buf_bytes : nullptr;
         uint8_t* rbuf = L.res_buf >= 0 ? sBuf + L.res_buf * p.buf_bytes : nullptr;
         uint8_t* obuf = L.out2_buf >= 0 ? sBuf + L.out2_buf * p.buf_bytes : nullptr;
+        const bool lrelu = (L.flags & FD_EPI_LRELU) != 0;
+        const bool has_cs = L.chan_scale != nullptr, has_cs2 = L.chan_scale2 != nullptr;
+#pragma unroll 1
+        for (int mb = 0; mb < p.nblk; ++mb) {
+          const int m = mb * 128 + q * 32 + lane;
+          const int y = m / p.Wp, x = m - y * p.Wp;
+          const bool valid = y < p.H && x < p.W;
+          const size_t mword = ((static_cast<size_t>(n) * p.H + y) * p.W + x) * 2 + hf;
+          uint32_t mbits = 0xffffffffu;
+          if (valid && L.mask_in) mbits = __ldg(L.mask_in + mword);      // latency hidden by the MMA wait
+          const uint32_t r = static_cast<uint32_t>(m + p.Wp + 1);         // smem row of pixel (y, x)
+          const uint32_t roff = r * 128u;
+          const uint32_t sw = r & 7u;
+          mbar_wait_sleep(acc_full + mb, g & 1, 1000);
+          tc_fence_after();
+          if (warp == 2) FD_TS(3 + 4 * mb);
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mb * kC + c0),
+                             acc);
+          tmem_ld_wait();
+          if (warp == 2) FD_TS(4 + 4 * mb);
+          if (valid) {
+            uint64_t v2[16];
 #pragma unroll
-        for (int mb = 0; mb < 4; ++mb) {
-          if (mb < p.nblk) {
-            const int m = mb * 128 + q * 32 + lane;
-            const int y = m / p.Wp, x = m - y * p.Wp;
-            const bool valid = y < p.H && x < p.W;
-            const uint32_t r = static_cast<uint32_t>(m + p.Wp + 1);      // smem row of pixel (y, x)
-            const uint32_t roff = r * 128u;
-            const uint32_t sw = r & 7u;
-            mbar_wait(acc_full + mb, g & 1);
-            tc_fence_after();
-            uint32_t acc[32];
-            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mb * kC + c0),
-                               acc);
-            tmem_ld_wait();
-            if (valid) {
-              float v[32];
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = sBias4[i];
+              v2[2 * i] = add2(pk2u(acc[4 * i], acc[4 * i + 1]), pk2(b4.x, b4.y));
+              v2[2 * i + 1] = add2(pk2u(acc[4 * i + 2], acc[4 * i + 3]), pk2(b4.z, b4.w));
+            }
+            if (lrelu) {
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(sConst + c0 + 4 * j4);
-                v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b4.x;
-                v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b4.y;
-                v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b4.z;
-                v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b4.w;
+              for (int i = 0; i < 16; ++i) {
+                float a0, a1, t0, t1;
+                upk2(v2[i], a0, a1);
+                upk2(mul2(v2[i], slope2), t0, t1);
+                v2[i] = pk2(fmaxf(a0, t0), fmaxf(a1, t1));
               }
-              if (L.flags & FD_EPI_LRELU) {
+            }
+            if (has_cs) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+              for (int i = 0; i < 8; ++i) {
+                const float4 s4 = sCs4[i];
+                v2[2 * i] = mul2(v2[2 * i], pk2(s4.x, s4.y));
+                v2[2 * i + 1] = mul2(v2[2 * i + 1], pk2(s4.z, s4.w));
               }
-              if (L.chan_scale) {
+            }
+            if (L.mask_v) {
+              uint32_t mv = 0;
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 s4 = *reinterpret_cast<const float4*>(sConst + kC + c0 + 4 * j4);
-                  v[4 * j4 + 0] *= s4.x; v[4 * j4 + 1] *= s4.y; v[4 * j4 + 2] *= s4.z; v[4 * j4 + 3] *= s4.w;
-                }
+              for (int i = 0; i < 16; ++i) {
+                float a0, a1;
+                upk2(v2[i], a0, a1);
+                mv |= (__float_as_uint(a0) >> 31) << (2 * i);
+                mv |= (__float_as_uint(a1) >> 31) << (2 * i + 1);
               }
-              if (L.mask_v) L.mask_v[((static_cast<size_t>(n) * p.H + y) * p.W + x) * 2 + hf] = sign_bits(v);
-              if (vbuf) {
+              L.mask_v[mword] = ~mv;      // bit set iff the sign bit is clear (same rule as conv3x3_tc.cu)
+            }
+            if (vbuf) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  uint4 u;
-                  u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                  u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                  *reinterpret_cast<uint4*>(vbuf + roff + (((hf * 4 + i) ^ sw) << 4)) = u;
-                }
+              for (int i = 0; i < 4; ++i) {
+                uint4 u;
+                float a0, a1;
+                upk2(v2[4 * i + 0], a0, a1); u.x = pack_bf16x2(a0, a1);
+                upk2(v2[4 * i + 1], a0, a1); u.y = pack_bf16x2(a0, a1);
+                upk2(v2[4 * i + 2], a0, a1); u.z = pack_bf16x2(a0, a1);
+                upk2(v2[4 * i + 3], a0, a1); u.w = pack_bf16x2(a0, a1);
+                *reinterpret_cast<uint4*>(vbuf + roff + (((hf * 4 + i) ^ sw) << 4)) = u;
               }
-              if (rbuf) {
+            }
+            if (rbuf) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  uint4* rp = reinterpret_cast<uint4*>(rbuf + roff + (((hf * 4 + i) ^ sw) << 4));
-                  uint4 u = *rp;
-                  v[8 * i + 0] += bf16lo(u.x); v[8 * i + 1] += bf16hi(u.x);
-                  v[8 * i + 2] += bf16lo(u.y); v[8 * i + 3] += bf16hi(u.y);
-                  v[8 * i + 4] += bf16lo(u.z); v[8 * i + 5] += bf16hi(u.z);
-                  v[8 * i + 6] += bf16lo(u.w); v[8 * i + 7] += bf16hi(u.w);
-                  u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                  u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                  *rp = u;
-                }
+              for (int i = 0; i < 4; ++i) {
+                uint4* rp = reinterpret_cast<uint4*>(rbuf + roff + (((hf * 4 + i) ^ sw) << 4));
+                uint4 u = *rp;
+                v2[4 * i + 0] = add2(v2[4 * i + 0], pk2u(u.x << 16, u.x & 0xFFFF0000u));
+                v2[4 * i + 1] = add2(v2[4 * i + 1], pk2u(u.y << 16, u.y & 0xFFFF0000u));
+                v2[4 * i + 2] = add2(v2[4 * i + 2], pk2u(u.z << 16, u.z & 0xFFFF0000u));
+                v2[4 * i + 3] = add2(v2[4 * i + 3], pk2u(u.w << 16, u.w & 0xFFFF0000u));
+                float a0, a1;
+                upk2(v2[4 * i + 0], a0, a1); u.x = pack_bf16x2(a0, a1);
+                upk2(v2[4 * i + 1], a0, a1); u.y = pack_bf16x2(a0, a1);
+                upk2(v2[4 * i + 2], a0, a1); u.z = pack_bf16x2(a0, a1);
+                upk2(v2[4 * i + 3], a0, a1); u.w = pack_bf16x2(a0, a1);
+                *rp = u;
               }
-              if (obuf) {
-                const uint32_t mbits = mk[mb];
+            }
+            if (obuf) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 s0 = *reinterpret_cast<const float4*>(sConst + 2 * kC + c0 + 8 * i);
-                  const float4 s1 = *reinterpret_cast<const float4*>(sConst + 2 * kC + c0 + 8 * i + 4);
-                  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                  float o[8];
+              for (int i = 0; i < 4; ++i) {
+                uint32_t w[4];
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    float t = v[8 * i + e] * (((mbits >> (8 * i + e)) & 1u) ? 1.f : p.slope);
-                    if (L.chan_scale2) t *= sc[e];
-                    o[e] = t;
+                for (int e = 0; e < 4; ++e) {
+                  float a0, a1;
+                  upk2(v2[4 * i + e], a0, a1);
+                  const int j = 8 * i + 2 * e;
+                  a0 = ((mbits >> j) & 1u) ? a0 : a0 * p.slope;
+                  a1 = ((mbits >> (j + 1)) & 1u) ? a1 : a1 * p.slope;
+                  if (has_cs2) {
+                    const float2 s2 = *reinterpret_cast<const float2*>(sConst + 2 * kC + c0 + j);
+                    float b0, b1;
+                    upk2(mul2(pk2(a0, a1), pk2(s2.x, s2.y)), b0, b1);
+                    a0 = b0; a1 = b1;
                   }
-                  uint4 u;
-                  u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
-                  u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-                  *reinterpret_cast<uint4*>(obuf + roff + (((hf * 4 + i) ^ sw) << 4)) = u;
+                  w[e] = pack_bf16x2(a0, a1);
                 }
+                *reinterpret_cast<uint4*>(obuf + roff + (((hf * 4 + i) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
               }
             }
           }
         }
+        if (warp == 2) FD_TS(11);
         fence_proxy_async();     // generic-proxy smem writes -> visible to tcgen05.mma and the TMA stores
         tc_fence_before();
+        if (warp == 2) FD_TS(12);
         bar_sync_epi();
+        if (warp == 2) FD_TS(13);
         if (et == 0) {
-          if (!(p.dbg & 1)) {
+          const bool last_layer = (l == p.n_layers - 1);
+          if (!last_layer) mbar_arrive(act_ready);             // the MMAs only read the buffers, like the stores
           const uint32_t o0 = static_cast<uint32_t>(p.Wp + 1) * 128u;   // smem row of pixel (0,0)
           if (L.map_v >= 0) tma_store_4d(&p.maps[L.map_v], vbuf + o0, 0, 0, 0, n);
           if (L.map_res >= 0) tma_store_4d(&p.maps[L.map_res], rbuf + o0, 0, 0, 0, n);
           if (L.map_out2 >= 0) tma_store_4d(&p.maps[L.map_out2], obuf + o0, 0, 0, 0, n);
-          }
           tma_store_commit();
-          if (l == p.n_layers - 1) tma_store_wait_read<0>();   // the next image reloads the buffers
-          mbar_arrive(act_ready);
+          if (last_layer) {
+            tma_store_wait_read<0>();   // the next image reloads the buffers
+            mbar_arrive(act_ready);
+          }
         }
       }
     }
@@ -324,6 +352,7 @@ struct ChainBuilder {
 int launch_chain(ChainBuilder& cb, const fd_bf16* w, int w_layers, const fd_bf16* in0, const fd_bf16* in1, int B, int H,
                  int W, float slope, cudaStream_t st) {
   if (cb.rc != FD_OK) return cb.rc;
+  if (!(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;   // LeakyReLU is evaluated as max(v, slope*v)
   ChainParams& p = cb.p;
   const int Wp = W + 1;
   p.B = B; p.H = H; p.W = W; p.Wp = Wp;
@@ -333,7 +362,7 @@ int launch_chain(ChainBuilder& cb, const fd_bf16* w, int w_layers, const fd_bf16
   p.box_bytes = static_cast<uint32_t>((H + 2) * Wp * 128);
   p.buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.nblk * 128 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024);
   p.slope = slope;
-  { const char* d = getenv("FD_CHAIN_DBG"); p.dbg = d ? atoi(d) : 0; }
+  { const char* d = getenv("FD_CHAIN_TIMING"); p.dbg = d ? atoi(d) : 0; }
   const size_t smem = kWBytes + static_cast<size_t>(kNumBufs) * p.buf_bytes + 3 * kC * 4 + 256 + 1024;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
   CUtensorMap tm_w, tm_in0, tm_in1;
@@ -356,6 +385,10 @@ int launch_chain(ChainBuilder& cb, const fd_bf16* w, int w_layers, const fd_bf16
 }  // namespace
 }  // namespace fd
 
+extern "C" FD_API int fd_debug_chain_timing(unsigned long long* out, int n) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, fd::g_chain_dbg, sizeof(unsigned long long) * n));
+}
+
 extern "C" int fd_resblock_chain_shape_ok(int H, int W, int C) {
   using namespace fd;
   if (C != kC || H <= 0 || W <= 0 || W + 1 > 256 || H + 2 > 256) return 0;
@@ -376,8 +409,7 @@ extern "C" int fd_resblock_chain_fwd(const fd_bf16* x, const fd_bf16* w_fwd, con
   cb.B = B; cb.H = H; cb.W = W;
   ChainParams& p = cb.p;
   p.n_layers = 2 * n_blocks;
-  // buffers: 0 = X (block input / running residual / block output), 1 = a, 2 = b (pre-residual, only
-  // materialised when it has to be stored)
+  // buffers: 0 = X (block input / running residual / block output), 1 = a
   for (int k = 0; k < n_blocks; ++k) {
     const fd_chain_fwd_block& bk = blocks[k];
     ChainLayer& c1 = p.L[2 * k];
@@ -390,8 +422,8 @@ extern "C" int fd_resblock_chain_fwd(const fd_bf16* x, const fd_bf16* w_fwd, con
     c2 = ChainLayer{};
     c2.bias = bk.bias2; c2.chan_scale = bk.chan_scale; c2.mask_v = bk.mask_b;
     c2.w_row = (2 * k + 1) * 9 * kC; c2.flags = FD_EPI_LRELU;
-    c2.in_buf = 1; c2.res_buf = 0; c2.v_buf = bk.b ? 2 : -1; c2.out2_buf = -1;
-    c2.map_v = static_cast<int8_t>(cb.add_map(bk.b)); c2.map_res = static_cast<int8_t>(cb.add_map(bk.out));
+    c2.in_buf = 1; c2.res_buf = 0; c2.v_buf = -1; c2.out2_buf = -1;
+    c2.map_v = -1; c2.map_res = static_cast<int8_t>(cb.add_map(bk.out));
     c2.map_out2 = -1;
   }
   return launch_chain(cb, w_fwd, 2 * n_blocks, x, nullptr, B, H, W, slope, static_cast<cudaStream_t>(stream));

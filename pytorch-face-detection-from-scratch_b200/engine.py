@@ -20,7 +20,7 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 
 class _Block:
-    __slots__ = ("H", "W", "pool", "a", "b", "s", "out", "G", "gs", "gp1", "gp2")
+    __slots__ = ("H", "W", "pool", "a", "ma", "mb", "s", "out", "G", "gs", "gp1", "gp2")
 
 
 class _Plan:
@@ -72,9 +72,7 @@ class _Plan:
             if eng.use_chain and ops.resblock_chain_ok(h, w, F):
                 # the whole run executes as ONE persistent kernel per direction (csrc/resblock_chain.cu);
                 # LeakyReLU' travels as sign bits instead of bf16 tensors
-                masks = torch.empty((2, n, B, h, w, F // 32), dtype=torch.int32, device=device) if train else None
-                self.chains[k0] = {"k0": k0, "k1": k1, "MA": masks[0] if train else None,
-                                   "MB": masks[1] if train else None}
+                self.chains[k0] = {"k0": k0, "k1": k1}
 
         def out_buffer(k, h, w):
             """Buffer holding the OUTPUT of block k (k = -1: the stem) = input of block k+1."""
@@ -93,7 +91,9 @@ class _Plan:
             st = stacks[run_of[k][0]] if k in run_of else None
             i = k - run_of[k][0] if k in run_of else 0
             blk.a = st["A"][i] if st else bf(H, W)
-            blk.b = bf(H, W) if train else None
+            # LeakyReLU' masks of a (conv1 activation) and b (conv2 activation after Dropout2d) as sign bits
+            blk.ma = torch.empty((B, H, W, F // 32), dtype=torch.int32, device=device) if train else None
+            blk.mb = torch.empty((B, H, W, F // 32), dtype=torch.int32, device=device) if train else None
             if blk.pool:
                 blk.s = bf(H, W)
                 H, W = H // 2, W // 2
@@ -271,9 +271,10 @@ class BackboneEngine:
                 cur = blk.out
                 continue
             cs = pl.drop[k] if pl.drop is not None else None
-            ops.conv3x3(cur, self._wf(2 * k), bias=sb3[2 * k], slope=self.slope, lrelu=True, out=blk.a)
+            ops.conv3x3(cur, self._wf(2 * k), bias=sb3[2 * k], slope=self.slope, lrelu=True, mask_out=blk.ma,
+                        out=blk.a)
             ops.conv3x3(blk.a, self._wf(2 * k + 1), bias=sb3[2 * k + 1], slope=self.slope, lrelu=True,
-                        chan_scale=cs, residual=cur, aux_out=blk.b, out=blk.s)
+                        chan_scale=cs, residual=cur, mask_out=blk.mb, out=blk.s)
             if blk.pool:
                 ops.maxpool2x2_fwd(blk.s, blk.out)
             cur = blk.out
@@ -290,8 +291,7 @@ class BackboneEngine:
             d = {"bias1": sb3[2 * k], "bias2": sb3[2 * k + 1],
                  "chan_scale": pl.drop[k] if pl.drop is not None else None}
             if pl.train:
-                d.update(a=blk.a, mask_a=ch["MA"][k - k0], mask_b=ch["MB"][k - k0], out=blk.s,
-                         b=blk.b if k == k1 else None)      # bf16 b only where a bf16-mask consumer follows
+                d.update(a=blk.a, mask_a=blk.ma, mask_b=blk.mb, out=blk.s)
             elif k == k1:
                 d.update(out=blk.s)
             descs.append(d)
@@ -305,11 +305,11 @@ class BackboneEngine:
         descs = []
         for k in range(k0, k1 + 1):
             blk = pl.blocks[k]
-            d = {"mask_a": ch["MA"][k - k0], "gp1": blk.gp1}
+            d = {"mask_a": blk.ma, "gp1": blk.gp1}
             if k == k0:
                 d["g_in"] = g_in
             else:
-                d.update(mask_b_prev=ch["MB"][k - 1 - k0], gp2_prev=pl.blocks[k - 1].gp2,
+                d.update(mask_b_prev=pl.blocks[k - 1].mb, gp2_prev=pl.blocks[k - 1].gp2,
                          chan_scale_prev=drop[k - 1] if drop is not None else None)
             descs.append(d)
         n3 = 9 * self.F * self.F
@@ -328,7 +328,7 @@ class BackboneEngine:
         drop = pl.drop
         last = pl.blocks[nb - 1]
         ops.head_bwd(last.out, drop[nb] if drop is not None else None, self.section(self.pflat, "out.weight"), pl.y,
-                     dy, self.head_pad, last.G, None if last.pool else last.b,
+                     dy, self.head_pad, last.G, None if last.pool else last.mb,
                      None if (last.pool or drop is None) else drop[nb - 1], self.slope,
                      None if last.pool else last.gp2, self.section(self.gflat, "out.weight"),
                      self.section(self.gflat, "out.bias"))
@@ -360,7 +360,7 @@ class BackboneEngine:
             if k >= skip_until:
                 continue
             if blk.pool:
-                ops.maxpool2x2_bwd(blk.s, blk.G, blk.gs, blk.b, drop[k] if drop is not None else None, self.slope,
+                ops.maxpool2x2_bwd(blk.s, blk.G, blk.gs, blk.mb, drop[k] if drop is not None else None, self.slope,
                                    blk.gp2)
                 GS = blk.gs
             else:
@@ -368,7 +368,7 @@ class BackboneEngine:
             grouped = k in in_group
             if not grouped:
                 ops.conv3x3_wgrad(blk.a, blk.gp2, self.dwp[(2 * k + 1) * n3:(2 * k + 2) * n3], gb3[2 * k + 1])
-            ops.conv3x3(blk.gp2, self._wd(2 * k + 1), slope=self.slope, mask_src=blk.a, out2=blk.gp1)
+            ops.conv3x3(blk.gp2, self._wd(2 * k + 1), slope=self.slope, mask_in=blk.ma, out2=blk.gp1)
             if not grouped:
                 ops.conv3x3_wgrad(x_in, blk.gp1, self.dwp[(2 * k) * n3:(2 * k + 1) * n3], gb3[2 * k])
             if k > 0:
@@ -377,7 +377,7 @@ class BackboneEngine:
                     ops.conv3x3(blk.gp1, self._wd(2 * k), slope=self.slope, residual=GS, out=prev.G)
                 else:
                     ops.conv3x3(blk.gp1, self._wd(2 * k), slope=self.slope, residual=GS, out=prev.G,
-                                mask_src=prev.b, chan_scale2=drop[k - 1] if drop is not None else None,
+                                mask_in=prev.mb, chan_scale2=drop[k - 1] if drop is not None else None,
                                 out2=prev.gp2)
             else:
                 ops.conv3x3(blk.gp1, self._wd(0), slope=self.slope, residual=GS, out=pl.g_stem)

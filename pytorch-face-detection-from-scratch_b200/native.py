@@ -44,8 +44,8 @@ SIGNATURES = {
 
 class ChainFwdBlock(_c.Structure):
     """fd_chain_fwd_block of include/fd_b200.h"""
-    _fields_ = [("bias1", _P), ("bias2", _P), ("chan_scale", _P), ("a", _P), ("mask_a", _P), ("b", _P),
-                ("mask_b", _P), ("out", _P)]
+    _fields_ = [("bias1", _P), ("bias2", _P), ("chan_scale", _P), ("a", _P), ("mask_a", _P), ("mask_b", _P),
+                ("out", _P)]
 
 
 class ChainBwdBlock(_c.Structure):

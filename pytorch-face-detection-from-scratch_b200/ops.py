@@ -13,13 +13,14 @@ BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
 EPI_LRELU = 1
 
 
-def conv3x3(x, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_scale=None, residual=None, aux_out=None,
-            out=None, mask_src=None, chan_scale2=None, out2=None, flags=0):
+def conv3x3(x, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_scale=None, residual=None, mask_out=None,
+            out=None, mask_in=None, chan_scale2=None, out2=None, flags=0):
+    """mask_out / mask_in: int32 [B,H,W,C//32] sign-bit masks (see include/fd_b200.h)."""
     B, H, W, C = x.shape
     fl = flags | (EPI_LRELU if lrelu else 0)
     check(lib().fd_conv3x3(dptr(x, BF16), dptr(w_packed, BF16), B, H, W, C, dptr(bias, F32), slope,
-                           dptr(chan_scale, F32), dptr(residual, BF16), dptr(aux_out, BF16), dptr(out, BF16),
-                           dptr(mask_src, BF16), dptr(chan_scale2, F32), dptr(out2, BF16), fl, cur_stream()),
+                           dptr(chan_scale, F32), dptr(residual, BF16), dptr(mask_out, I32), dptr(out, BF16),
+                           dptr(mask_in, I32), dptr(chan_scale2, F32), dptr(out2, BF16), fl, cur_stream()),
           "fd_conv3x3")
 
 
@@ -42,14 +43,14 @@ def resblock_chain_ok(H, W, C):
 
 
 def resblock_chain_fwd(x, w_fwd, blocks, slope=0.2):
-    """blocks: list of dicts with keys bias1, bias2 and optional chan_scale, a, mask_a, b, mask_b, out (tensors).
+    """blocks: list of dicts with keys bias1, bias2 and optional chan_scale, a, mask_a, mask_b, out (tensors).
     w_fwd: [2*len(blocks), 9, C, C] bf16 forward-packed weights of the run."""
     B, H, W, C = x.shape
     arr = (ChainFwdBlock * len(blocks))()
     for i, d in enumerate(blocks):
         arr[i] = ChainFwdBlock(dptr(d["bias1"], F32), dptr(d["bias2"], F32), dptr(d.get("chan_scale"), F32),
-                               dptr(d.get("a"), BF16), dptr(d.get("mask_a"), I32), dptr(d.get("b"), BF16),
-                               dptr(d.get("mask_b"), I32), dptr(d.get("out"), BF16))
+                               dptr(d.get("a"), BF16), dptr(d.get("mask_a"), I32), dptr(d.get("mask_b"), I32),
+                               dptr(d.get("out"), BF16))
     check(lib().fd_resblock_chain_fwd(dptr(x, BF16), dptr(w_fwd, BF16), ctypes.cast(arr, ctypes.c_void_p),
                                       len(blocks), B, H, W, C, slope, cur_stream()), "fd_resblock_chain_fwd")
 
@@ -101,11 +102,11 @@ def head_fwd(x, chan_scale, w, bias, y, pad):
                             dptr(y, F32), cur_stream()), "fd_head_fwd")
 
 
-def head_bwd(x, chan_scale, w, y, dy, pad, dx, mask_src, chan_scale2, slope, dx2, dw, dbias):
+def head_bwd(x, chan_scale, w, y, dy, pad, dx, mask_bits, chan_scale2, slope, dx2, dw, dbias):
     B, H, W, C = x.shape
     K = w.shape[2]
     check(lib().fd_head_bwd(dptr(x, BF16), dptr(chan_scale, F32), dptr(w, F32), dptr(y, F32), dptr(dy, F32), B, H, W, C,
-                            K, pad, dptr(dx, BF16), dptr(mask_src, BF16), dptr(chan_scale2, F32), slope,
+                            K, pad, dptr(dx, BF16), dptr(mask_bits, I32), dptr(chan_scale2, F32), slope,
                             dptr(dx2, BF16), dptr(dw, F32), dptr(dbias, F32), cur_stream()), "fd_head_bwd")
 
 
@@ -114,9 +115,9 @@ def maxpool2x2_fwd(x, y):
     check(lib().fd_maxpool2x2_fwd(dptr(x, BF16), B, H, W, C, dptr(y, BF16), cur_stream()), "fd_maxpool2x2_fwd")
 
 
-def maxpool2x2_bwd(x, gy, gs, mask_src, chan_scale, slope, gs2):
+def maxpool2x2_bwd(x, gy, gs, mask_bits, chan_scale, slope, gs2):
     B, H, W, C = x.shape
-    check(lib().fd_maxpool2x2_bwd(dptr(x, BF16), dptr(gy, BF16), B, H, W, C, dptr(gs, BF16), dptr(mask_src, BF16),
+    check(lib().fd_maxpool2x2_bwd(dptr(x, BF16), dptr(gy, BF16), B, H, W, C, dptr(gs, BF16), dptr(mask_bits, I32),
                                   dptr(chan_scale, F32), slope, dptr(gs2, BF16), cur_stream()), "fd_maxpool2x2_bwd")
 
 

@@ -11,6 +11,13 @@ pytestmark = pytest.mark.gpu
 C = 64
 
 
+def _bits(t):
+    """sign-bit mask of a [B,H,W,C] tensor in the library's layout: int32 [B,H,W,C/32], bit c%32 of word c/32."""
+    b = (t.float() > 0).to(torch.int64).reshape(*t.shape[:-1], t.shape[-1] // 32, 32)
+    w = (b << torch.arange(32, device=t.device, dtype=torch.int64)).sum(-1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
+
+
 def _close(got, ref, what, rel=4e-3, mx=1e-2):
     r = rel_err(got.float(), ref)
     m = (got.float() - ref).abs().max().item()
@@ -18,7 +25,8 @@ def _close(got, ref, what, rel=4e-3, mx=1e-2):
     assert m <= mx * max(1.0, ref.abs().max().item()), f"{what}: max abs {m}"
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 15, 15), (3, 30, 30), (2, 60, 60), (1, 7, 9), (5, 16, 8)])
+@pytest.mark.parametrize("B,H,W", [(2, 15, 15), (3, 30, 30), (2, 60, 60), (1, 7, 9), (5, 16, 8), (2, 120, 120),
+                                   (1, 64, 125), (160, 15, 15)])
 def test_conv3x3_forward_epilogues(B, H, W):
     require_cuda()
     ops = fd().ops
@@ -41,15 +49,21 @@ def test_conv3x3_forward_epilogues(B, H, W):
     ops.conv3x3(x, wf, bias=bias, lrelu=True, out=out)
     ref1 = nhwc(F.leaky_relu(F.conv2d(xn, wq, bias, padding=1), 0.2))
     _close(out, ref1, "conv+bias+lrelu")
-    # (2) conv2 of the block: + dropout multiplier, aux (pre-residual), residual add
-    aux = torch.zeros_like(x); out = torch.zeros_like(x)
-    ops.conv3x3(x, wf, bias=bias, lrelu=True, chan_scale=cs, residual=res, aux_out=aux, out=out)
+    # (2) conv2 of the block: + dropout multiplier, sign bits of the pre-residual value, residual add
+    mo = torch.zeros(B, H, W, C // 32, dtype=torch.int32, device=dev); out = torch.zeros_like(x)
+    ops.conv3x3(x, wf, bias=bias, lrelu=True, chan_scale=cs, residual=res, mask_out=mo, out=out)
     refb = ref1 * cs[:, None, None, :]
-    _close(aux, refb, "aux_out")
     _close(out, refb + res.float(), "residual out")
-    # (3) dgrad packing + masked second output (backward chain)
+    # sign bits, compared where the value is not within rounding distance of zero
+    got_bits = ((mo.to(torch.int64)[..., None] >> torch.arange(32, device=dev)) & 1).reshape(B, H, W, C).bool()
+    sure = refb.abs() > 1e-3
+    assert torch.equal(got_bits[sure], (refb > 0)[sure]) and sure.float().mean().item() > 0.5
+    # (3) dgrad packing + masked second output (backward chain): both outputs, then out2 alone (staged path)
     out = torch.zeros_like(x); out2 = torch.zeros_like(x)
-    ops.conv3x3(x, wd, residual=res, out=out, mask_src=msk, chan_scale2=cs2, out2=out2)
+    ops.conv3x3(x, wd, residual=res, out=out, mask_in=_bits(msk), chan_scale2=cs2, out2=out2)
+    only2 = torch.zeros_like(x)
+    ops.conv3x3(x, wd, residual=res, mask_in=_bits(msk), chan_scale2=cs2, out2=only2)
+    assert torch.equal(only2, out2)
     xin = torch.zeros(B, C, H, W, device=dev, requires_grad=True)
     (gref,) = torch.autograd.grad(F.conv2d(xin, wq, None, padding=1), xin, xn)
     G = nhwc(gref) + res.float()
@@ -155,7 +169,7 @@ def test_head_fwd_bwd(H, K, pad):
     dy = torch.randn_like(y)
     dx = torch.zeros_like(x); dx2 = torch.zeros_like(x)
     dw = torch.zeros_like(w); dbias = torch.zeros_like(b)
-    ops.head_bwd(x, cs, w.detach(), y, dy, pad, dx, msk, cs2, 0.2, dx2, dw, dbias)
+    ops.head_bwd(x, cs, w.detach(), y, dy, pad, dx, _bits(msk), cs2, 0.2, dx2, dw, dbias)
     ref.backward(dy)
     gx = xin.grad.permute(0, 2, 3, 1)
     _close(dx, gx, "head dx")
@@ -180,7 +194,7 @@ def test_maxpool_fwd_bwd_first_max_tie_rule():
     msk = torch.randn(B, H, H, C, device=dev).bfloat16()
     cs = (torch.rand(B, C, device=dev) < 0.75).float() / 0.75
     gs = torch.zeros_like(x); gs2 = torch.zeros_like(x)
-    ops.maxpool2x2_bwd(x, gy, gs, msk, cs, 0.2, gs2)
+    ops.maxpool2x2_bwd(x, gy, gs, _bits(msk), cs, 0.2, gs2)
     ref.backward(gy.float().permute(0, 3, 1, 2))
     gref = xin.grad.permute(0, 2, 3, 1)
     assert torch.equal(gs.float(), gref)

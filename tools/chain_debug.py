@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 fd = importlib.import_module("pytorch-face-detection-from-scratch_b200")
 ops = fd.ops
 mode = sys.argv[1] if len(sys.argv) > 1 else "infer"
-B, H, W, C, nb = 4, 15, 15, 64, 2
+B, H, W, C, nb = 64, 15, 15, 64, int(os.environ.get("NB", "2"))
 g = torch.Generator().manual_seed(3)
 x = (torch.randn(B, H, W, C, generator=g) * 0.5).cuda().bfloat16()
 w = (torch.randn(2 * nb, C, C, 3, 3, generator=g) * 0.05).cuda()
@@ -39,3 +39,16 @@ for k in range(nb):
 torch.cuda.synchronize()
 print("ref abs sum", cur.float().abs().sum().item(), "equal:", torch.equal(cur, outs[-1]),
       "max diff", (cur.float() - outs[-1].float()).abs().max().item())
+
+if os.environ.get("FD_CHAIN_TIMING"):
+    import ctypes
+    import numpy as np
+    nl = 2 * nb
+    buf = (ctypes.c_ulonglong * (nl * 16))()
+    fd.native.lib().fd_debug_chain_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    fd.native.lib().fd_debug_chain_timing(buf, nl * 16)
+    t = np.array(buf[:], dtype=np.int64).reshape(nl, 16)
+    t0 = t[0, 0]
+    names = {0: "mma_go", 1: "mma_issued", 2: "epi_top", 3: "acc0", 4: "ld0", 7: "acc1", 8: "ld1", 11: "math_done", 12: "fenced", 13: "bar"}
+    for l in range(nl):
+        print(l, " ".join(f"{names[k]}={t[l, k] - t0}" for k in sorted(names)))
