@@ -140,6 +140,12 @@ FD_API int fd_resblock_chain_bwd(const fd_bf16* g_out, const fd_bf16* gp2_last, 
                           const fd_chain_bwd_block* blocks, int n_blocks, int B, int H, int W, int C, float slope,
                           void* stream);
 
+/* Dropout2d multipliers (models/PoolResnet.py:39,100; nn.Dropout2d zeroes whole channels and rescales):
+ * out[i] = r[i] < keep ? 1/keep : 0 with keep = keep_block for i < n_block and keep_head otherwise.
+ * r: n uniform randoms in [0,1) (one per (layer, image, channel)), produced by the caller's generator. */
+FD_API int fd_dropout_scale(const float* r, long n, long n_block, float keep_block, float keep_head, float* out,
+                     void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stem convolution (models/PoolResnet.py:70-76,98): KxK stride s pad p, Cin(3) -> C, input fp32 NCHW
  * (or uint8 NCHW with the /255 of PoolResnet.py:95 fused: x_is_u8 = 1), output NHWC bf16, bias added.

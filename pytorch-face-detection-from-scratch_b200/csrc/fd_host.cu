@@ -54,6 +54,20 @@ int make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, int rows, int cols, int b
   return r == CUDA_SUCCESS ? FD_OK : FD_EINVAL;
 }
 
+int make_tmap_2d_f32(CUtensorMap* m, const void* ptr, long rows, int cols, int boxRows, int boxCols) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return FD_EDRIVER;
+  if (boxCols * 4 > 128 || boxRows > 256) return FD_EUNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)boxCols, (cuuint32_t)boxRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FD_OK : FD_EINVAL;
+}
+
 int make_tmap_3d(CUtensorMap* m, const void* ptr, int elem_bytes, int is_u8, int d0, int d1, int d2, int box0,
                  int box1) {
   PFN_encodeTiled enc = get_encode_tiled();

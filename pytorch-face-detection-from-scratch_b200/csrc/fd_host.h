@@ -24,6 +24,9 @@ int make_tmap_nhwc_bf16(CUtensorMap* m, const void* ptr, int B, int H, int W, in
 // [rows, cols] bf16 row-major as a 2-D tiled TMA map with box {boxCols, boxRows}, 128B swizzle.
 int make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, int rows, int cols, int boxRows, int boxCols);
 
+// [rows, cols] fp32 row-major as a 2-D tiled map with box {boxCols (<= 32), boxRows}, 128B swizzle
+int make_tmap_2d_f32(CUtensorMap* m, const void* ptr, long rows, int cols, int boxRows, int boxCols);
+
 // [d2, d1, d0] tensor of 1- or 4-byte elements (uint8 / fp32) as a 3-D tiled map, box {box0, box1, 1}, no swizzle
 int make_tmap_3d(CUtensorMap* m, const void* ptr, int elem_bytes, int is_u8, int d0, int d1, int d2, int box0, int box1);
 

@@ -9,32 +9,59 @@ namespace fd {
 namespace {
 
 // ============================================================================ weight packing
-// torch [co][ci][ky][kx] fp32  ->  fwd [t][co][ci] bf16 ; dgrad [t'][ci][co] bf16 with t' = flipped tap
-__global__ void pack_conv3x3_kernel(const float* __restrict__ w, int n_layers, int C, __nv_bfloat16* __restrict__ wf,
-                                    __nv_bfloat16* __restrict__ wd) {
-  const long total = static_cast<long>(n_layers) * 9 * C * C;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int b = i % C;
-    const int a = (i / C) % C;
-    const int t = (i / (static_cast<long>(C) * C)) % 9;
-    const long l = i / (9L * C * C);
-    const float* wl = w + l * 9L * C * C;
-    if (wf) wf[i] = __float2bfloat16(wl[(static_cast<long>(a) * C + b) * 9 + t]);          // a = co, b = ci
-    if (wd) wd[i] = __float2bfloat16(wl[(static_cast<long>(b) * C + a) * 9 + (8 - t)]);    // a = ci, b = co
+// torch [co][ci][ky][kx] fp32  ->  fwd [t][co][ci] bf16 ; dgrad [t'][ci][co] bf16 with t' = flipped tap.
+// One CTA = (layer, 16 output channels): 16 x 576 contiguous floats in, transposed through shared memory.
+constexpr int kPackCo = 16;
+__global__ void __launch_bounds__(256)
+pack_conv3x3_kernel(const float* __restrict__ w, int n_layers, int C, __nv_bfloat16* __restrict__ wf,
+                    __nv_bfloat16* __restrict__ wd) {
+  extern __shared__ float sm[];                      // [kPackCo][C*9 + 1]
+  const int tiles = C / kPackCo;
+  const int l = blockIdx.x / tiles, co0 = (blockIdx.x % tiles) * kPackCo;
+  const int row = C * 9, pitch = row + 1;
+  const float* src = w + (static_cast<long>(l) * C + co0) * row;
+  for (int i = threadIdx.x; i < kPackCo * row; i += blockDim.x) sm[(i / row) * pitch + i % row] = __ldg(src + i);
+  __syncthreads();
+  const long lbase = static_cast<long>(l) * 9 * C * C;
+  if (wf) {                                          // wf[l][t][co][ci]: ci fastest
+    for (int i = threadIdx.x; i < 9 * kPackCo * C; i += blockDim.x) {
+      const int ci = i % C, co = (i / C) % kPackCo, t = i / (C * kPackCo);
+      wf[lbase + (static_cast<long>(t) * C + co0 + co) * C + ci] = __float2bfloat16(sm[co * pitch + ci * 9 + t]);
+    }
+  }
+  if (wd) {                                          // wd[l][8-t][ci][co]: co fastest
+    for (int i = threadIdx.x; i < 9 * kPackCo * C; i += blockDim.x) {
+      const int co = i % kPackCo, ci = (i / kPackCo) % C, t = i / (C * kPackCo);
+      wd[lbase + (static_cast<long>(8 - t) * C + ci) * C + co0 + co] = __float2bfloat16(sm[co * pitch + ci * 9 + t]);
+    }
   }
 }
 
-// packed gradient [t][ci][co] fp32 -> torch [co][ci][ky][kx] fp32
-__global__ void unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, int C, float* __restrict__ dw) {
-  const long total = static_cast<long>(n_layers) * 9 * C * C;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+// packed gradient [t][ci][co] fp32 -> torch [co][ci][ky][kx] fp32 (same tiling, contiguous 576-float rows out)
+__global__ void __launch_bounds__(256)
+unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, int C, float* __restrict__ dw) {
+  extern __shared__ float sm[];                      // [kPackCo][C*9 + 1]
+  const int tiles = C / kPackCo;
+  const int l = blockIdx.x / tiles, co0 = (blockIdx.x % tiles) * kPackCo;
+  const int row = C * 9, pitch = row + 1;
+  const long lbase = static_cast<long>(l) * 9 * C * C;
+  for (int i = threadIdx.x; i < 9 * kPackCo * C; i += blockDim.x) {
+    const int co = i % kPackCo, ci = (i / kPackCo) % C, t = i / (C * kPackCo);
+    sm[co * pitch + ci * 9 + t] = __ldg(dwp + lbase + (static_cast<long>(t) * C + ci) * C + co0 + co);
+  }
+  __syncthreads();
+  float* dst = dw + (static_cast<long>(l) * C + co0) * row;
+  for (int i = threadIdx.x; i < kPackCo * row; i += blockDim.x) dst[i] = sm[(i / row) * pitch + i % row];
+}
+
+// Dropout2d multipliers from uniform randoms: rows [0, n_block_rows) use keep_b, the rest keep_h
+// (models/PoolResnet.py:39 Dropout2d(0.25) per block, :100 Dropout2d(0.5) before the head).
+__global__ void dropout_scale_kernel(const float* __restrict__ r, long n, long n_block, float keep_b, float keep_h,
+                                     float* __restrict__ out) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int t = i % 9;
-    const int ci = (i / 9) % C;
-    const int co = (i / (9L * C)) % C;
-    const long l = i / (9L * C * C);
-    dw[i] = dwp[l * 9L * C * C + (static_cast<long>(t) * C + ci) * C + co];
+    const float keep = i < n_block ? keep_b : keep_h;
+    out[i] = r[i] < keep ? 1.f / keep : 0.f;
   }
 }
 
@@ -553,7 +580,12 @@ using namespace fd;
 extern "C" int fd_pack_conv3x3(const float* w, int n_layers, int C, fd_bf16* w_fwd, fd_bf16* w_dgrad, void* stream) {
   if (!w || n_layers <= 0 || C <= 0 || (!w_fwd && !w_dgrad)) return FD_EINVAL;
   const long total = static_cast<long>(n_layers) * 9 * C * C;
-  pack_conv3x3_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (C % kPackCo != 0) return FD_EUNSUPPORTED;
+  (void)total;
+  const size_t smem = static_cast<size_t>(kPackCo) * (C * 9 + 1) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(pack_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  pack_conv3x3_kernel<<<n_layers * (C / kPackCo), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       w, n_layers, C, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
   count_launch();
   return launch_status();
@@ -562,7 +594,21 @@ extern "C" int fd_pack_conv3x3(const float* w, int n_layers, int C, fd_bf16* w_f
 extern "C" int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, float* dw, void* stream) {
   if (!dw_packed || !dw || n_layers <= 0 || C <= 0) return FD_EINVAL;
   const long total = static_cast<long>(n_layers) * 9 * C * C;
-  unpack_wgrad3x3_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, C, dw);
+  if (C % kPackCo != 0) return FD_EUNSUPPORTED;
+  (void)total;
+  const size_t smem = static_cast<size_t>(kPackCo) * (C * 9 + 1) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(unpack_wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  unpack_wgrad3x3_kernel<<<n_layers * (C / kPackCo), 256, smem, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, C, dw);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_dropout_scale(const float* r, long n, long n_block, float keep_block, float keep_head, float* out,
+                                void* stream) {
+  if (!r || !out || n <= 0 || keep_block <= 0.f || keep_head <= 0.f) return FD_EINVAL;
+  dropout_scale_kernel<<<grid_for(n, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(r, n, n_block, keep_block,
+                                                                                          keep_head, out);
   count_launch();
   return launch_status();
 }

@@ -19,6 +19,7 @@
 // of g) is accumulated by the otherwise idle epilogue warps from the same smem tiles.
 #include "fd_host.h"
 #include "fd_ptx.cuh"
+#include <cstdlib>
 
 namespace fd {
 namespace {
@@ -33,12 +34,18 @@ struct WgradParams {
   uint32_t x_buf_bytes, g_buf_bytes;  // reserved per stage (multiples of 1024)
   float* dw;                          // [9][ci][co] fp32, accumulated
   float* dbias;                       // [co] fp32, accumulated (nullable)
-  int flags;
+  int flags, dbg;
   // multi-problem launch: x / g hold `nprob` stacked [B,H,W,C] tensors; problem q accumulates into
   // dw + q * dw_stride and dbias + q * dbias_stride.  A CTA never straddles two problems.
   int nprob, tiles_per_prob, ctas_per_prob, per;
   long dw_stride, dbias_stride;
+  uint32_t bar_off;                   // barriers live behind max(stages, drain staging tiles)
+  int dw_row0, dw_rows_per_prob;      // rows of the [.,64] fp32 view of dw: first row, rows between problems
 };
+
+// Optional timestamps of CTA 0 (FD_WGRAD_TIMING=1).
+__device__ unsigned long long g_wgrad_dbg[16];
+#define FD_WTS(slot) do { if (p.dbg && blockIdx.x == 0) g_wgrad_dbg[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -47,14 +54,14 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
-                   const WgradParams p) {
+                   const __grid_constant__ CUtensorMap tm_dw, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   const uint32_t stage_bytes = p.x_buf_bytes + p.g_buf_bytes;
   uint8_t* sStage = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
   uint64_t* full = bars + 0;      // [2]
   uint64_t* empty = bars + 2;     // [2]
   uint64_t* acc_full = bars + 4;
@@ -63,6 +70,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) FD_WTS(0);
 
   // K-padding rows of g and the over-read tail of x are never written by TMA and must stay zero.
   for (uint32_t i = threadIdx.x * 16u; i < 2 * stage_bytes; i += kThreads * 16u)
@@ -87,13 +95,13 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) FD_WTS(1);
 
   // contiguous chunk of tiles (of ONE problem) for this CTA
   const int prob = blockIdx.x / p.ctas_per_prob;
   const int chunk = blockIdx.x - prob * p.ctas_per_prob;
   const int tile_begin = prob * p.tiles_per_prob + min(p.tiles_per_prob, chunk * p.per);
   const int tile_end = prob * p.tiles_per_prob + min(p.tiles_per_prob, (chunk + 1) * p.per);
-  float* const dw_out = p.dw + prob * p.dw_stride;
   float* const dbias_out = p.dbias ? p.dbias + prob * p.dbias_stride : nullptr;
 
   if (warp == 0) {
@@ -164,12 +172,20 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // (2) drain the accumulators
     if (tile_begin < tile_end) {
       const int q = warp & 3;
+      if (et == 0) FD_WTS(2);
       mbar_wait(acc_full, 0);
       tc_fence_after();
-      const int row = q * 32 + lane;
-      const int tsel = row >> 6, ci = row & 63;
+      if (et == 0) FD_WTS(3);
+      // TMEM -> registers -> fp32 staging tiles in shared memory (the stage buffers are free now) -> TMA tensor
+      // REDUCE-stores (cp.reduce.async.bulk.tensor .add: the fp32 adds happen in L2, 16 KB per instruction)
+      // instead of 41k per-thread red.global.add per CTA.  Staging tile = [128 rows][32 fp32] with the 128B
+      // swizzle of the tensor map, so the row-per-thread writes are bank-conflict free.
+      const int row = q * 32 + lane;           // = tsel * 64 + ci: row of the [2 taps][64 ci] block
+      const uint32_t sw = static_cast<uint32_t>(row) & 7u;
 #pragma unroll 1
       for (int j = 0; j < 5; ++j) {
+        // pairs 0..3 = taps (2j, 2j+1); pair 4 = taps (7, 8) where tap 7 was already produced by pair 3: add zeros
+        const bool dup = (j == 4) && (row < 64);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t acc[32];
@@ -177,16 +193,31 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                                  static_cast<uint32_t>(j * kC + half * 32),
                              acc);
           tmem_ld_wait();
-          const int tap = ((j < 4) ? 2 * j : 7) + tsel;
-          if (j < 4 || tsel == 1) {
-            float* dst = dw_out + (static_cast<size_t>(tap) * kC + ci) * kC + half * 32;
+          uint8_t* tile = sStage + static_cast<size_t>(j * 2 + half) * (128 * 128) + row * 128;
 #pragma unroll
-            for (int v = 0; v < 8; ++v)
-              red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]),
-                         __uint_as_float(acc[4 * v + 2]), __uint_as_float(acc[4 * v + 3]));
+          for (int v = 0; v < 8; ++v) {
+            uint4 u = make_uint4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+            if (dup) u = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(tile + ((static_cast<uint32_t>(v) ^ sw) << 4)) = u;
           }
         }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const int tap0 = (j < 4) ? 2 * j : 7;
+          const int grow = p.dw_row0 + prob * p.dw_rows_per_prob + tap0 * kC;
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+            asm volatile(
+                "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(&tm_dw)),
+                "r"(smem_u32(sStage + static_cast<size_t>(j * 2 + half) * (128 * 128))), "r"(half * 32), "r"(grow)
+                : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
+      if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (et == 0) FD_WTS(4);
       if (p.dbias) {
         sBias[et] = bsum;
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -197,11 +228,16 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FD_WTS(5);
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace
 }  // namespace fd
+
+extern "C" FD_API int fd_debug_wgrad_timing(unsigned long long* out, int n) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, fd::g_wgrad_dbg, sizeof(unsigned long long) * n));
+}
 
 extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int nprob, int B, int H, int W, int C,
                                       float* dw_packed, long dw_stride, float* dbias, long dbias_stride, int flags,
@@ -213,19 +249,27 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
   const int Wp = W + 1;
   const size_t smem_cap = 227 * 1024;
 
-  // rows per tile: as many as fit two stages of (x halo tile + g tile) in shared memory ...
+  // Rows per tile: among the heights whose two stages of (x halo tile + g tile) fit in shared memory, pick the
+  // one that minimises the work of the busiest CTA (tiles per CTA x max(MMA time, TMA fill time) per tile).
+  // Measured: one M=128,N=64,K=16 MMA with MN-major operands takes ~73 clk; five of them per 16 pixels.
   int bestR = 0;
+  double best = 1e30;
   for (int R = 1; R <= H && R + 2 <= 256; ++R) {
     const int ksteps = (R * Wp + 15) / 16;
     const size_t xb = (static_cast<size_t>(ksteps * 16 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024;
     const size_t gb = (static_cast<size_t>(ksteps * 16) * 128 + 1023) / 1024 * 1024;
     if (2 * (xb + gb) + 1024 + 1024 > smem_cap) break;
-    bestR = R;
+    const long tiles_per_prob = static_cast<long>(B) * ((H + R - 1) / R);
+    long cpp = nsm / nprob;
+    if (cpp < 1) cpp = 1;
+    if (cpp > tiles_per_prob) cpp = tiles_per_prob;
+    const long per = (tiles_per_prob + cpp - 1) / cpp;
+    const double mma = ksteps * 5 * 73.0;
+    const double fill = static_cast<double>(2 * R + 2) * Wp * 128 / 48.0;
+    const double cost = per * ((mma > fill ? mma : fill) + 500.0);
+    if (cost < best) { best = cost; bestR = R; }
   }
   if (bestR == 0) return FD_EUNSUPPORTED;
-  // ... but not so tall that the SMs run out of tiles
-  auto total_tiles = [&](int R) { return static_cast<long>(nprob) * B * ((H + R - 1) / R); };
-  while (bestR > 1 && total_tiles(bestR) < nsm && total_tiles(bestR - 1) <= 2L * nsm) --bestR;
 
   WgradParams p;
   p.B = nprob * B; p.H = H; p.W = W; p.R = bestR; p.Wp = Wp;
@@ -237,15 +281,15 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
   p.x_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.ksteps * 16 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024);
   p.g_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.ksteps * 16) * 128 + 1023) / 1024 * 1024);
   p.dw = dw_packed; p.dbias = dbias; p.flags = flags;
+  { const char* d = getenv("FD_WGRAD_TIMING"); p.dbg = d ? atoi(d) : 0; }
   p.nprob = nprob;
   p.tiles_per_prob = B * p.tiles_per_img;
   p.dw_stride = dw_stride; p.dbias_stride = dbias_stride;
   // CTAs per problem: one wave over the SMs in total; few CTAs when there are few tiles so that the
   // per-CTA reduction into global memory (36864 fp32 adds) stays amortised (>= 4 tiles per CTA)
-  int cpp = nsm / nprob;
+  int cpp = nsm / nprob;                       // one wave over all SMs; the drain is a handful of TMA reduces per CTA
   if (cpp < 1) cpp = 1;
-  if (cpp > (p.tiles_per_prob + 3) / 4) cpp = (p.tiles_per_prob + 3) / 4;
-  if (cpp < 1) cpp = 1;
+  if (cpp > p.tiles_per_prob) cpp = p.tiles_per_prob;
   p.per = (p.tiles_per_prob + cpp - 1) / cpp;
   p.ctas_per_prob = (p.tiles_per_prob + p.per - 1) / p.per;
 
@@ -255,12 +299,22 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
   rc = make_tmap_nhwc_bf16(&tm_g, g, p.B, H, W, C, Wp, bestR);
   if (rc != FD_OK) return rc;
 
-  const size_t smem = 2 * static_cast<size_t>(p.x_buf_bytes + p.g_buf_bytes) + 1024 + 1024;
+  if (nprob > 1 && dw_stride % kC != 0) return FD_EINVAL;
+  CUtensorMap tm_dw;
+  p.dw_row0 = 0;
+  p.dw_rows_per_prob = static_cast<int>(dw_stride / kC);
+  rc = make_tmap_2d_f32(&tm_dw, dw_packed, static_cast<long>(nprob - 1) * p.dw_rows_per_prob + 9 * kC, kC, 128, 32);
+  if (rc != FD_OK) return rc;
+  const size_t stages = 2 * static_cast<size_t>(p.x_buf_bytes + p.g_buf_bytes);
+  const size_t drain = 10 * 128 * 128;          // 5 tap pairs x 2 column halves x [128 rows][128 B]
+  p.bar_off = static_cast<uint32_t>(stages > drain ? stages : drain);
+  const size_t smem = p.bar_off + 1024 + 1024;
+  if (smem > smem_cap) return FD_EUNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = nprob * p.ctas_per_prob;
-  wgrad3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_x, tm_g, p);
+  wgrad3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_x, tm_g, tm_dw, p);
   count_launch();
   return launch_status();
 }

@@ -187,9 +187,11 @@ class BackboneEngine:
             return
         self.device = device
         self.pflat = torch.zeros(self.n_flat, dtype=F32, device=device)
-        self.gflat = torch.zeros(self.n_flat, dtype=F32, device=device)
         n3 = 2 * self.num_blocks * 9 * self.F * self.F
-        self.dwp = torch.zeros(n3, dtype=F32, device=device)
+        # gradient buffer and the packed 3x3 weight-gradient accumulators share one allocation: one fill per step
+        self.gzero = torch.zeros(self.n_flat + n3, dtype=F32, device=device)
+        self.gflat = self.gzero[:self.n_flat]
+        self.dwp = self.gzero[self.n_flat:]
         self.w_fwd = torch.empty(n3, dtype=BF16, device=device)
         self.w_dgrad = torch.empty(n3, dtype=BF16, device=device)
         self.plans.clear()
@@ -243,11 +245,10 @@ class BackboneEngine:
         if repack or self.weights_dirty:
             self.pack_weights()
         if dropout:
-            keep_b, keep_h = 1.0 - self.block_drop, 1.0 - self.head_drop
+            # one torch.rand (the caller's generator decides the masks) + one kernel for the multipliers
             r = torch.rand((self.num_blocks + 1, B, self.F), device=x.device)
             scale = torch.empty_like(r)
-            scale[:-1] = (r[:-1] < keep_b).float() / keep_b
-            scale[-1] = (r[-1] < keep_h).float() / keep_h
+            ops.dropout_scale(r, self.num_blocks * B * self.F, 1.0 - self.block_drop, 1.0 - self.head_drop, scale)
             pl.drop = scale
         else:
             pl.drop = None
@@ -321,8 +322,7 @@ class BackboneEngine:
         """dy: gradient w.r.t. plan.y.  Fills self.gflat (overwrites)."""
         assert pl.train
         nb = self.num_blocks
-        self.gflat.zero_()
-        self.dwp.zero_()
+        self.gzero.zero_()
         gb3 = self.section(self.gflat, "b3")
         n3 = 9 * self.F * self.F
         drop = pl.drop

@@ -29,6 +29,7 @@ SIGNATURES = {
     "fd_resblock_chain_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "fd_pack_conv3x3": [_P, _I, _I, _P, _P, _P],
     "fd_unpack_wgrad3x3": [_P, _I, _I, _P, _P],
+    "fd_dropout_scale": [_P, _c.c_long, _c.c_long, _F, _F, _P, _P],
     "fd_stem_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "fd_stem_wgrad": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "fd_head_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],

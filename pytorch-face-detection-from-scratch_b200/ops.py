@@ -79,6 +79,11 @@ def unpack_wgrad3x3(dw_packed, dw):
     check(lib().fd_unpack_wgrad3x3(dptr(dw_packed, F32), n, C, dptr(dw, F32), cur_stream()), "fd_unpack_wgrad3x3")
 
 
+def dropout_scale(r, n_block, keep_block, keep_head, out):
+    check(lib().fd_dropout_scale(dptr(r, F32), r.numel(), int(n_block), float(keep_block), float(keep_head),
+                                 dptr(out, F32), cur_stream()), "fd_dropout_scale")
+
+
 def stem_fwd(x, w, bias, y, stride, pad):
     B, Cin, Hin, Win = x.shape
     C, _, K, _ = w.shape
