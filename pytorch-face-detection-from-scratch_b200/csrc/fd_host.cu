@@ -41,6 +41,21 @@ int make_tmap_nhwc_bf16(CUtensorMap* m, const void* ptr, int B, int H, int W, in
   return r == CUDA_SUCCESS ? FD_OK : FD_EINVAL;
 }
 
+int make_tmap_nhwc_bf16_strided(CUtensorMap* m, const void* ptr, int B, int H, int Wext, int Wfull, int C, int boxW,
+                                int boxH) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return FD_EDRIVER;
+  if (C * 2 != 128 || boxW < 1 || boxW > 256 || boxH < 1 || boxH > 256 || Wext < 1) return FD_EUNSUPPORTED;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wext, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wfull * C * 2, (cuuint64_t)H * Wfull * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FD_OK : FD_EINVAL;
+}
+
 int make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, int rows, int cols, int boxRows, int boxCols) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return FD_EDRIVER;

@@ -21,6 +21,10 @@ inline int launch_status() {
 
 // [B,H,W,C] bf16 tensor as a 4-D tiled TMA map with box {C, boxW, boxH, 1}, 128B swizzle, zero OOB fill.
 int make_tmap_nhwc_bf16(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int boxW, int boxH);
+// a W-window [B,H,Wext,C] of a [B,H,Wfull,C] bf16 tensor (ptr = first pixel of the window): columns >= Wext are
+// out of bounds (zero-filled on load) although they exist in memory
+int make_tmap_nhwc_bf16_strided(CUtensorMap* m, const void* ptr, int B, int H, int Wext, int Wfull, int C, int boxW,
+                                int boxH);
 // [rows, cols] bf16 row-major as a 2-D tiled TMA map with box {boxCols, boxRows}, 128B swizzle.
 int make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, int rows, int cols, int boxRows, int boxCols);
 

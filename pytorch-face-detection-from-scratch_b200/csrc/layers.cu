@@ -10,27 +10,28 @@ namespace {
 
 // ============================================================================ weight packing
 // torch [co][ci][ky][kx] fp32  ->  fwd [t][co][ci] bf16 ; dgrad [t'][ci][co] bf16 with t' = flipped tap.
-// One CTA = (layer, 16 output channels): 16 x 576 contiguous floats in, transposed through shared memory.
-constexpr int kPackCo = 16;
+// One CTA = (layer, kPackCo output channels): kPackCo x 576 contiguous floats in, transposed through shared
+// memory.  C is a template constant so that all index arithmetic is shifts / multiplies by constants.
+constexpr int kPackCo = 4;
+template <int C>
 __global__ void __launch_bounds__(256)
-pack_conv3x3_kernel(const float* __restrict__ w, int n_layers, int C, __nv_bfloat16* __restrict__ wf,
+pack_conv3x3_kernel(const float* __restrict__ w, int n_layers, __nv_bfloat16* __restrict__ wf,
                     __nv_bfloat16* __restrict__ wd) {
-  extern __shared__ float sm[];                      // [kPackCo][C*9 + 1]
-  const int tiles = C / kPackCo;
+  constexpr int row = C * 9, pitch = row + 1, tiles = C / kPackCo;
+  __shared__ float sm[kPackCo * pitch];
   const int l = blockIdx.x / tiles, co0 = (blockIdx.x % tiles) * kPackCo;
-  const int row = C * 9, pitch = row + 1;
   const float* src = w + (static_cast<long>(l) * C + co0) * row;
-  for (int i = threadIdx.x; i < kPackCo * row; i += blockDim.x) sm[(i / row) * pitch + i % row] = __ldg(src + i);
+  for (int i = threadIdx.x; i < kPackCo * row; i += 256) sm[(i / row) * pitch + i % row] = __ldg(src + i);
   __syncthreads();
   const long lbase = static_cast<long>(l) * 9 * C * C;
   if (wf) {                                          // wf[l][t][co][ci]: ci fastest
-    for (int i = threadIdx.x; i < 9 * kPackCo * C; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 9 * kPackCo * C; i += 256) {
       const int ci = i % C, co = (i / C) % kPackCo, t = i / (C * kPackCo);
       wf[lbase + (static_cast<long>(t) * C + co0 + co) * C + ci] = __float2bfloat16(sm[co * pitch + ci * 9 + t]);
     }
   }
   if (wd) {                                          // wd[l][8-t][ci][co]: co fastest
-    for (int i = threadIdx.x; i < 9 * kPackCo * C; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 9 * kPackCo * C; i += 256) {
       const int co = i % kPackCo, ci = (i / kPackCo) % C, t = i / (C * kPackCo);
       wd[lbase + (static_cast<long>(8 - t) * C + ci) * C + co0 + co] = __float2bfloat16(sm[co * pitch + ci * 9 + t]);
     }
@@ -38,20 +39,20 @@ pack_conv3x3_kernel(const float* __restrict__ w, int n_layers, int C, __nv_bfloa
 }
 
 // packed gradient [t][ci][co] fp32 -> torch [co][ci][ky][kx] fp32 (same tiling, contiguous 576-float rows out)
+template <int C>
 __global__ void __launch_bounds__(256)
-unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, int C, float* __restrict__ dw) {
-  extern __shared__ float sm[];                      // [kPackCo][C*9 + 1]
-  const int tiles = C / kPackCo;
+unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, float* __restrict__ dw) {
+  constexpr int row = C * 9, pitch = row + 1, tiles = C / kPackCo;
+  __shared__ float sm[kPackCo * pitch];
   const int l = blockIdx.x / tiles, co0 = (blockIdx.x % tiles) * kPackCo;
-  const int row = C * 9, pitch = row + 1;
   const long lbase = static_cast<long>(l) * 9 * C * C;
-  for (int i = threadIdx.x; i < 9 * kPackCo * C; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 9 * kPackCo * C; i += 256) {
     const int co = i % kPackCo, ci = (i / kPackCo) % C, t = i / (C * kPackCo);
     sm[co * pitch + ci * 9 + t] = __ldg(dwp + lbase + (static_cast<long>(t) * C + ci) * C + co0 + co);
   }
   __syncthreads();
   float* dst = dw + (static_cast<long>(l) * C + co0) * row;
-  for (int i = threadIdx.x; i < kPackCo * row; i += blockDim.x) dst[i] = sm[(i / row) * pitch + i % row];
+  for (int i = threadIdx.x; i < kPackCo * row; i += 256) dst[i] = sm[(i / row) * pitch + i % row];
 }
 
 // Dropout2d multipliers from uniform randoms: rows [0, n_block_rows) use keep_b, the rest keep_h
@@ -493,6 +494,199 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
+// ============================================================================ head, C = 64 fast path
+// grid = (B, kHeadParts), 256 threads.  Work item = (pixel, group of 8 channels): every weight fetch is one
+// LDS.128 shared by the lanes of equal channel group, every activation fetch one LDS.128 of 8 bf16, so the
+// inner loop is 40 FMA per 11-15 shared-memory instructions.  The transposed weight tile [tap][o][c] is
+// staged with an XOR swizzle of the 8-channel groups (group ^ ((tap*5+o) & 7)): the transposing scatter of
+// the coalesced [o][c][tap] read then hits 8 instead of 32 lanes per bank.
+constexpr int kHeadParts = 4;
+__device__ __forceinline__ int head_w_index(int to, int c) {      // to = tap*5 + o
+  return to * 64 + ((((c >> 3) ^ to) & 7) << 3) + (c & 7);
+}
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+
+template <int K, int PAD>
+__global__ void __launch_bounds__(256)
+head_fwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ w,
+                    const float* __restrict__ bias, int H, int W, int Ho, int Wo, float* __restrict__ y) {
+  constexpr int C = 64, KK = K * K;
+  extern __shared__ float sm[];
+  float* sW = sm;                                                       // [KK*5][64], pre-scaled by the dropout multiplier
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sm + KK * 5 * C);  // [H*W][64]
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < KK * 5 * C; i += 256) {
+    const int t = i % KK, c = (i / KK) % C, o = i / (KK * C);
+    sW[head_w_index(t * 5 + o, c)] = __ldg(w + i) * (cs ? __ldg(cs + n * C + c) : 1.f);
+  }
+  const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * H * W * C);
+  for (int i = threadIdx.x; i < H * W * C / 8; i += 256) reinterpret_cast<uint4*>(sX)[i] = __ldg(xs + i);
+  __syncthreads();
+  const int npix = Ho * Wo;
+  const int per = (npix + kHeadParts - 1) / kHeadParts;
+  const int p0 = blockIdx.y * per, p1 = min(npix, p0 + per);
+  for (int task = threadIdx.x; task < ((p1 - p0) * 8 + 31) / 32 * 32; task += 256) {
+    const int g = task & 7, pix = p0 + (task >> 3);
+    const bool live = pix < p1;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const int oy = pix / Wo, ox = pix - oy * Wo;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy + ky - PAD;
+        if (PAD > 0 && (iy < 0 || iy >= H)) continue;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int ix = ox + kx - PAD;
+          if (PAD > 0 && (ix < 0 || ix >= W)) continue;
+          float xv[8];
+          bf16x8_to_f32(*reinterpret_cast<const uint4*>(sX + (iy * W + ix) * C + g * 8), xv);
+          const int to0 = (ky * K + kx) * 5;
+#pragma unroll
+          for (int o = 0; o < 5; ++o) {
+            const float4* wp = reinterpret_cast<const float4*>(sW + (to0 + o) * 64 + (((g ^ (to0 + o)) & 7) << 3));
+            const float4 w0 = wp[0], w1 = wp[1];
+            acc[o] = fmaf(xv[0], w0.x, acc[o]); acc[o] = fmaf(xv[1], w0.y, acc[o]);
+            acc[o] = fmaf(xv[2], w0.z, acc[o]); acc[o] = fmaf(xv[3], w0.w, acc[o]);
+            acc[o] = fmaf(xv[4], w1.x, acc[o]); acc[o] = fmaf(xv[5], w1.y, acc[o]);
+            acc[o] = fmaf(xv[6], w1.z, acc[o]); acc[o] = fmaf(xv[7], w1.w, acc[o]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 5; ++o) {
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 4);
+    }
+    if (live && g < 5) {
+      const float v = (g == 0 ? acc[0] : g == 1 ? acc[1] : g == 2 ? acc[2] : g == 3 ? acc[3] : acc[4]) + __ldg(bias + g);
+      y[(static_cast<size_t>(n) * 5 + g) * npix + pix] = 1.f / (1.f + expf(-v));
+    }
+  }
+}
+
+template <int K, int PAD>
+__global__ void __launch_bounds__(256)
+head_bwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ w,
+                    const float* __restrict__ y, const float* __restrict__ dy, int H, int W, int Ho, int Wo,
+                    __nv_bfloat16* __restrict__ dx, const uint32_t* __restrict__ mask_bits,
+                    const float* __restrict__ cs2, float slope, __nv_bfloat16* __restrict__ dx2,
+                    float* __restrict__ dw, float* __restrict__ dbias) {
+  constexpr int C = 64, KK = K * K;
+  constexpr int TPP = (KK + kHeadParts - 1) / kHeadParts;       // taps per part (weight gradient)
+  extern __shared__ float sm[];
+  float* sW = sm;                                   // [KK*5][64] swizzled
+  float* sAcc = sW + KK * 5 * C;                    // [TPP*5][64] weight-gradient partial sums of this CTA
+  float* sDz = sAcc + TPP * 5 * C;                  // [5][Ho*Wo]
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sDz + ((5 * Ho * Wo + 3) & ~3));   // [H*W][64]
+  const int n = blockIdx.x, part = blockIdx.y;
+  const int npo = Ho * Wo;
+  for (int i = threadIdx.x; i < KK * 5 * C; i += 256) {
+    const int t = i % KK, c = (i / KK) % C, o = i / (KK * C);
+    sW[head_w_index(t * 5 + o, c)] = __ldg(w + i);
+  }
+  for (int i = threadIdx.x; i < TPP * 5 * C; i += 256) sAcc[i] = 0.f;
+  for (int i = threadIdx.x; i < 5 * npo; i += 256) {
+    const float yv = y[static_cast<size_t>(n) * 5 * npo + i];
+    sDz[i] = dy[static_cast<size_t>(n) * 5 * npo + i] * yv * (1.f - yv);
+  }
+  const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * H * W * C);
+  for (int i = threadIdx.x; i < H * W * C / 8; i += 256) reinterpret_cast<uint4*>(sX)[i] = __ldg(xs + i);
+  __syncthreads();
+  if (part == 0 && threadIdx.x < 5) {
+    float t = 0.f;
+    for (int i = 0; i < npo; ++i) t += sDz[threadIdx.x * npo + i];
+    atomicAdd(dbias + threadIdx.x, t);
+  }
+  // ---- dx (and the masked copy that starts the last block's backward chain): this CTA's share of the pixels
+  {
+    const int npi = H * W;
+    const int per = (npi + kHeadParts - 1) / kHeadParts;
+    const int p0 = part * per, p1 = min(npi, p0 + per);
+    for (int task = threadIdx.x; task < (p1 - p0) * 8; task += 256) {
+      const int g = task & 7, pix = p0 + (task >> 3);
+      const int iy = pix / W, ix = pix - iy * W;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int oy = iy - ky + PAD;
+        if (oy < 0 || oy >= Ho) continue;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int ox = ix - kx + PAD;
+          if (ox < 0 || ox >= Wo) continue;
+          const int to0 = (ky * K + kx) * 5;
+#pragma unroll
+          for (int o = 0; o < 5; ++o) {
+            const float dz = sDz[o * npo + oy * Wo + ox];
+            const float4* wp = reinterpret_cast<const float4*>(sW + (to0 + o) * 64 + (((g ^ (to0 + o)) & 7) << 3));
+            const float4 w0 = wp[0], w1 = wp[1];
+            acc[0] = fmaf(dz, w0.x, acc[0]); acc[1] = fmaf(dz, w0.y, acc[1]);
+            acc[2] = fmaf(dz, w0.z, acc[2]); acc[3] = fmaf(dz, w0.w, acc[3]);
+            acc[4] = fmaf(dz, w1.x, acc[4]); acc[5] = fmaf(dz, w1.y, acc[5]);
+            acc[6] = fmaf(dz, w1.z, acc[6]); acc[7] = fmaf(dz, w1.w, acc[7]);
+          }
+        }
+      }
+      const size_t gi = (static_cast<size_t>(n) * npi + pix) * C + g * 8;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = acc[e] * (cs ? __ldg(cs + n * C + g * 8 + e) : 1.f);
+      if (dx) *reinterpret_cast<uint4*>(dx + gi) = pack8(v);
+      if (dx2) {
+        const uint32_t mk = __ldg(mask_bits + (gi >> 5)) >> (gi & 31);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          v[e] = v[e] * (((mk >> e) & 1u) ? 1.f : slope) * (cs2 ? __ldg(cs2 + n * C + g * 8 + e) : 1.f);
+        *reinterpret_cast<uint4*>(dx2 + gi) = pack8(v);
+      }
+    }
+  }
+  // ---- dw: this CTA's share of the taps; work item = (tap, channel group, third of the output pixels)
+  {
+    const int t0 = part * TPP, t1 = min(KK, t0 + TPP);
+    const int ntask = (t1 - t0) * 8 * 3;
+    for (int task = threadIdx.x; task < ntask; task += 256) {
+      const int g = task & 7, third = (task >> 3) % 3, tl = task / 24;
+      const int t = t0 + tl, ky = t / K, kx = t - ky * K;
+      float acc[5][8];
+#pragma unroll
+      for (int o = 0; o < 5; ++o)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[o][e] = 0.f;
+      for (int po = third; po < npo; po += 3) {
+        const int oy = po / Wo, ox = po - oy * Wo;
+        const int iy = oy + ky - PAD, ix = ox + kx - PAD;
+        if (PAD > 0 && (iy < 0 || iy >= H || ix < 0 || ix >= W)) continue;
+        float xv[8];
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(sX + (iy * W + ix) * C + g * 8), xv);
+#pragma unroll
+        for (int o = 0; o < 5; ++o) {
+          const float dz = sDz[o * npo + po];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(xv[e], dz, acc[o][e]);
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 5; ++o)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(sAcc + (tl * 5 + o) * C + g * 8 + e, acc[o][e]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (t1 - t0) * 5 * C; i += 256) {
+      const int c = i % C, o = (i / C) % 5, tl = i / (5 * C);
+      const float s = cs ? __ldg(cs + n * C + c) : 1.f;
+      atomicAdd(dw + (static_cast<size_t>(o) * C + c) * KK + t0 + tl, sAcc[i] * s);
+    }
+  }
+}
+
+
 __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
                                       __nv_bfloat16* __restrict__ y) {
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
@@ -580,13 +774,15 @@ using namespace fd;
 extern "C" int fd_pack_conv3x3(const float* w, int n_layers, int C, fd_bf16* w_fwd, fd_bf16* w_dgrad, void* stream) {
   if (!w || n_layers <= 0 || C <= 0 || (!w_fwd && !w_dgrad)) return FD_EINVAL;
   const long total = static_cast<long>(n_layers) * 9 * C * C;
-  if (C % kPackCo != 0) return FD_EUNSUPPORTED;
   (void)total;
-  const size_t smem = static_cast<size_t>(kPackCo) * (C * 9 + 1) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(pack_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  pack_conv3x3_kernel<<<n_layers * (C / kPackCo), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      w, n_layers, C, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
+  if (C == 64)
+    pack_conv3x3_kernel<64><<<n_layers * (64 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, n_layers, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
+  else if (C == 128)
+    pack_conv3x3_kernel<128><<<n_layers * (128 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, n_layers, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
+  else
+    return FD_EUNSUPPORTED;
   count_launch();
   return launch_status();
 }
@@ -594,12 +790,13 @@ extern "C" int fd_pack_conv3x3(const float* w, int n_layers, int C, fd_bf16* w_f
 extern "C" int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, float* dw, void* stream) {
   if (!dw_packed || !dw || n_layers <= 0 || C <= 0) return FD_EINVAL;
   const long total = static_cast<long>(n_layers) * 9 * C * C;
-  if (C % kPackCo != 0) return FD_EUNSUPPORTED;
   (void)total;
-  const size_t smem = static_cast<size_t>(kPackCo) * (C * 9 + 1) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(unpack_wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  unpack_wgrad3x3_kernel<<<n_layers * (C / kPackCo), 256, smem, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, C, dw);
+  if (C == 64)
+    unpack_wgrad3x3_kernel<64><<<n_layers * (64 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, dw);
+  else if (C == 128)
+    unpack_wgrad3x3_kernel<128><<<n_layers * (128 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, dw);
+  else
+    return FD_EUNSUPPORTED;
   count_launch();
   return launch_status();
 }
@@ -686,6 +883,18 @@ extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const floa
   if ((H * W * C) % 8 != 0) return FD_EUNSUPPORTED;
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
+  if (C == 64 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
+    const size_t sm2 = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>(H) * W * C * 2;
+    if (sm2 <= 227 * 1024) {
+      auto kern = (K == 6) ? head_fwd_c64_kernel<6, 0> : head_fwd_c64_kernel<3, 1>;
+      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      if (e2 != cudaSuccess) return (int)e2;
+      kern<<<dim3(B, kHeadParts), 256, sm2, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, bias, H, W, Ho, Wo, y);
+      count_launch();
+      return launch_status();
+    }
+  }
   const size_t smem = static_cast<size_t>((K * K * 5 * (C + 1) + 3) & ~3) * 4 + static_cast<size_t>(H) * W * C * 2;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -705,18 +914,21 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
   if ((H * W * C) % 8 != 0 || kHeadThreads % C != 0) return FD_EUNSUPPORTED;
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
-  if (C == 64 && W <= 16 && Wo <= 16 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
-    const size_t sm_small = static_cast<size_t>((K * K * 5 * (C + 1) + 3) & ~3) * 4 + static_cast<size_t>(5) * Ho * 16 * 4 +
-                            static_cast<size_t>(H) * W * C * 2;
-    auto kern = (K == 6) ? head_bwd_small_kernel<6, 0> : head_bwd_small_kernel<3, 1>;
-    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small);
-    if (e2 != cudaSuccess) return (int)e2;
-    kern<<<min(B, 2 * sm_count()), kHeadThreads, sm_small, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, y, dy, B, H, W, Ho, Wo,
-        reinterpret_cast<__nv_bfloat16*>(dx), mask_bits, chan_scale2, slope,
-        reinterpret_cast<__nv_bfloat16*>(dx2), dw, dbias);
-    count_launch();
-    return launch_status();
+  if (C == 64 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
+    const int KK = K * K, TPP = (KK + kHeadParts - 1) / kHeadParts;
+    const size_t sm2 = static_cast<size_t>(KK) * 5 * C * 4 + static_cast<size_t>(TPP) * 5 * C * 4 +
+                       static_cast<size_t>((5 * Ho * Wo + 3) & ~3) * 4 + static_cast<size_t>(H) * W * C * 2;
+    if (sm2 <= 227 * 1024) {
+      auto kern = (K == 6) ? head_bwd_c64_kernel<6, 0> : head_bwd_c64_kernel<3, 1>;
+      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      if (e2 != cudaSuccess) return (int)e2;
+      kern<<<dim3(B, kHeadParts), 256, sm2, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, y, dy, H, W, Ho, Wo,
+          reinterpret_cast<__nv_bfloat16*>(dx), mask_bits, chan_scale2, slope, reinterpret_cast<__nv_bfloat16*>(dx2),
+          dw, dbias);
+      count_launch();
+      return launch_status();
+    }
   }
   const size_t smem = static_cast<size_t>((K * K * 5 * (C + 1) + 3) & ~3) * 4 + static_cast<size_t>((5 * Ho * Wo + 3) & ~3) * 4 +
                       static_cast<size_t>(H) * W * C * 2;

@@ -29,7 +29,7 @@ constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
 
 struct WgradParams {
-  int B, H, W, R, Wp, tiles_per_img, num_tiles, ksteps;
+  int B, H, W, R, TW, Wp, tiles_w, tiles_per_img, num_tiles, ksteps;
   uint32_t x_bytes, g_bytes;          // bytes delivered by the two TMA boxes
   uint32_t x_buf_bytes, g_buf_bytes;  // reserved per stage (multiples of 1024)
   float* dw;                          // [9][ci][co] fp32, accumulated
@@ -47,13 +47,18 @@ struct WgradParams {
 __device__ unsigned long long g_wgrad_dbg[16];
 #define FD_WTS(slot) do { if (p.dbg && blockIdx.x == 0) g_wgrad_dbg[slot] = clock64(); } while (0)
 
+// One gradient map per column strip: its W extent ends at the strip, so the two junk columns of the
+// K index (x >= TW) are zero-filled by TMA and contribute nothing.
+constexpr int kMaxStrips = 8;
+struct GMaps { CUtensorMap m[kMaxStrips]; };
+
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
+wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ GMaps gmaps,
                    const __grid_constant__ CUtensorMap tm_dw, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -79,7 +84,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
-    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&gmaps.m[0]);
     for (int s = 0; s < 2; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1 + 4);  // MMA commit + the four column-sum warps
@@ -110,11 +115,13 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
         const int s = it & 1, ph = (it >> 1) & 1;
         const int n = tile / p.tiles_per_img;
-        const int h0 = (tile - n * p.tiles_per_img) * p.R;
+        const int rem = tile - n * p.tiles_per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        const int h0 = th * p.R, w0 = tw * p.TW;
         mbar_wait(empty + s, ph ^ 1);
         mbar_expect_tx(full + s, p.x_bytes + p.g_bytes);
-        tma_load_4d(sStage + s * stage_bytes, &tm_x, full + s, 0, -1, h0 - 1, n);
-        tma_load_4d(sStage + s * stage_bytes + p.x_buf_bytes, &tm_g, full + s, 0, 0, h0, n);
+        tma_load_4d(sStage + s * stage_bytes, &tm_x, full + s, 0, w0 - 1, h0 - 1, n);
+        tma_load_4d(sStage + s * stage_bytes + p.x_buf_bytes, &gmaps.m[tw], full + s, 0, 0, h0, n);
       }
     }
   } else if (warp == 1) {
@@ -244,9 +251,13 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
                                       void* stream) {
   using namespace fd;
   if (!x || !g || !dw_packed || nprob <= 0 || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
-  if (C != kC || W + 1 > 256) return FD_EUNSUPPORTED;
+  if (C != kC) return FD_EUNSUPPORTED;
   const int nsm = sm_count();
-  const int Wp = W + 1;
+  // column strips of TW <= 62 pixels; K index p = y*Wp + x with Wp = TW + 2 (two junk columns per row)
+  const int tiles_w = (W + 61) / 62;
+  if (tiles_w > kMaxStrips) return FD_EUNSUPPORTED;
+  const int TW = (W + tiles_w - 1) / tiles_w;
+  const int Wp = TW + 2;
   const size_t smem_cap = 227 * 1024;
 
   // Rows per tile: among the heights whose two stages of (x halo tile + g tile) fit in shared memory, pick the
@@ -259,21 +270,21 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
     const size_t xb = (static_cast<size_t>(ksteps * 16 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024;
     const size_t gb = (static_cast<size_t>(ksteps * 16) * 128 + 1023) / 1024 * 1024;
     if (2 * (xb + gb) + 1024 + 1024 > smem_cap) break;
-    const long tiles_per_prob = static_cast<long>(B) * ((H + R - 1) / R);
+    const long tiles_per_prob = static_cast<long>(B) * ((H + R - 1) / R) * tiles_w;
     long cpp = nsm / nprob;
     if (cpp < 1) cpp = 1;
     if (cpp > tiles_per_prob) cpp = tiles_per_prob;
     const long per = (tiles_per_prob + cpp - 1) / cpp;
     const double mma = ksteps * 5 * 73.0;
     const double fill = static_cast<double>(2 * R + 2) * Wp * 128 / 48.0;
-    const double cost = per * ((mma > fill ? mma : fill) + 500.0);
+    const double cost = per * ((mma > fill ? mma : fill) + 1500.0);   // + per-tile pipeline bubble (measured)
     if (cost < best) { best = cost; bestR = R; }
   }
   if (bestR == 0) return FD_EUNSUPPORTED;
 
   WgradParams p;
-  p.B = nprob * B; p.H = H; p.W = W; p.R = bestR; p.Wp = Wp;
-  p.tiles_per_img = (H + bestR - 1) / bestR;
+  p.B = nprob * B; p.H = H; p.W = W; p.R = bestR; p.TW = TW; p.Wp = Wp; p.tiles_w = tiles_w;
+  p.tiles_per_img = ((H + bestR - 1) / bestR) * tiles_w;
   p.num_tiles = p.B * p.tiles_per_img;
   p.ksteps = (bestR * Wp + 15) / 16;
   p.x_bytes = static_cast<uint32_t>((bestR + 2) * Wp * 128);
@@ -293,11 +304,16 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
   p.per = (p.tiles_per_prob + cpp - 1) / cpp;
   p.ctas_per_prob = (p.tiles_per_prob + p.per - 1) / p.per;
 
-  CUtensorMap tm_x, tm_g;
+  CUtensorMap tm_x;
+  GMaps gmaps;
   int rc = make_tmap_nhwc_bf16(&tm_x, x, p.B, H, W, C, Wp, bestR + 2);
   if (rc != FD_OK) return rc;
-  rc = make_tmap_nhwc_bf16(&tm_g, g, p.B, H, W, C, Wp, bestR);
-  if (rc != FD_OK) return rc;
+  for (int tw = 0; tw < kMaxStrips; ++tw) {
+    const int w0 = (tw < tiles_w ? tw : 0) * TW;
+    const int wext = (W - w0 < TW) ? W - w0 : TW;
+    rc = make_tmap_nhwc_bf16_strided(&gmaps.m[tw], g + static_cast<size_t>(w0) * C, p.B, H, wext, W, C, Wp, bestR);
+    if (rc != FD_OK) return rc;
+  }
 
   if (nprob > 1 && dw_stride % kC != 0) return FD_EINVAL;
   CUtensorMap tm_dw;
@@ -314,7 +330,7 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = nprob * p.ctas_per_prob;
-  wgrad3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_x, tm_g, tm_dw, p);
+  wgrad3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_x, gmaps, tm_dw, p);
   count_launch();
   return launch_status();
 }

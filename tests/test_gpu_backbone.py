@@ -198,3 +198,34 @@ def test_chain_forward_many_images_per_cta():
         ops.conv3x3(a, wf[2 * k + 1], bias=bias[2 * k + 1], lrelu=True, residual=cur, out=s)
         assert torch.equal(outs[k], s), k
         cur = s
+
+
+def test_resnet_standard_train_step_vs_oracle():
+    """models/Resnet.py (3x3 stride-2 stem, pooling while H > S, 3x3 head): 240/120/60/30-wide layers exercise the
+    column-strip tiling of the conv and weight-gradient kernels; the six 15x15 blocks run as one fused chain."""
+    require_cuda()
+    Resnet = fd().models.Resnet.Resnet
+    torch.manual_seed(21)
+    m = Resnet(filters=64, input_shape=(3, 480, 480), num_of_patches=15).cuda().eval()
+    p = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    B = 2
+    gen = torch.Generator().manual_seed(22)
+    x = torch.rand(B, 3, 480, 480, generator=gen)
+    gt = torch.stack([torch.from_numpy(yo.grid_encode(synth_boxes(gen, 101, 400).numpy(), 15, 480, 480))
+                      for _ in range(B)])
+    y_ref, loss_ref, g_ref = bo.train_step(x, gt, p, 15, forward=bo.resnet_forward)
+    loss = m.train_step(x.cuda(), gt.cuda())
+    pl = m.engine.plan(B, True)
+    assert len(pl.chains) == 1
+    d = (pl.y.cpu() - y_ref).abs()
+    print("resnet head max/mean abs err", d.max().item(), d.mean().item())
+    assert d.max().item() <= HEAD_MAX and d.mean().item() <= HEAD_MEAN
+    assert abs(loss.item() - loss_ref.item()) <= LOSS_REL * abs(loss_ref.item())
+    for k, prm in m.named_parameters():
+        e = rel_err(prm.grad.cpu(), g_ref[k])
+        assert e <= GRAD_REL, (k, e)
+    # decode + NMS of the 15x15 head: bit-exact against the oracle on the same head tensor
+    kept = m.non_max_suppression(pl.y)
+    for i in range(B):
+        want = yo.reduce_bounding_boxes(pl.y[i].cpu().numpy(), 0.5, 0.5, (3, 480, 480), 15)
+        assert kept[i].cpu().numpy().tobytes() == want.tobytes()

@@ -72,7 +72,8 @@ def test_conv3x3_forward_epilogues(B, H, W):
     _close(out2, G2, "masked out2", rel=6e-3)
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 15, 15), (3, 30, 30), (2, 60, 60), (1, 7, 9), (64, 15, 15)])
+@pytest.mark.parametrize("B,H,W", [(2, 15, 15), (3, 30, 30), (2, 60, 60), (1, 7, 9), (64, 15, 15), (2, 120, 120),
+                                   (1, 64, 125), (1, 240, 240)])
 def test_conv3x3_wgrad(B, H, W):
     require_cuda()
     ops = fd().ops
