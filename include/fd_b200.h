@@ -203,6 +203,33 @@ FD_API int fd_decode_nms(const float* pred, int B, int S1, int S2, float p_thr, 
 FD_API int fd_grid_encode(const float* boxes, const int32_t* box_offsets, int B, int S, int width, int height, float* out,
                    void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SSD head path.  P = sum(ps*ps) priors over `n_scales` grids of ps x ps cells
+ * (patch_sizes is a HOST array; the reference uses (60, 30, 15, 7) -> 4774, datasets/utils.py:15).
+ *
+ * fd_ssd_grid_encode: datasets/WIDERFace/dataset_ssd.py:36-76,134-139 for a ragged batch.
+ *   boxes [total,5] fp32 rows (1,x,y,w,h) in pixels; box_offsets [B+1] int32; out [B,P,5] fp32 (overwritten),
+ *   rows = scale-major, then cell (i,j) row-major; later boxes overwrite earlier ones of the same cell. */
+FD_API int fd_ssd_grid_encode(const float* boxes, const int32_t* box_offsets, int B, const int* patch_sizes, int n_scales,
+                       int width, int height, float* out, void* stream);
+
+/* fd_ssd_decode_nms: datasets/utils.py:56-92 ReduceSSDBoundingBoxes.forward for a batch.
+ *   x [B,P,5] fp32 rows (score,x,y,w,h); with_priors applies the prior scaling/offsets of utils.py:59-64.
+ *   out_boxes [B,P,5] rows (score,x,y,w,h) in keep order (descending score); out_count [B] kept rows. */
+FD_API int fd_ssd_decode_nms(const float* x, int B, const int* patch_sizes, int n_scales, float p_thr, double iou_thr,
+                      int width, int height, int with_priors, float* out_boxes, int32_t* out_count, void* stream);
+
+/* fd_ssd_loss: losses/SSDLoss.py:27-86 (hard-negative mining + clamped BCE + smooth L1), per batch row.
+ *   conf, labels [B,P]; loc, gt_loc [B,P,4] fp32.
+ *   row_sums [B,2]: (sum of BCE over the mined set, sum of smooth-L1 over the positive priors) of each row;
+ *   num_pos [B] int32: positive priors of each row.  loss = (sum row_sums) / (sum num_pos)  (SSDLoss.py:85-86).
+ *   mask [B,P] uint8 (nullable): the mined set.  dconf [B,P], dloc [B,P,4] (nullable): gradients of the
+ *   UN-normalised sums; the caller scales them by 1 / sum(num_pos) -- across data-parallel ranks that sum is
+ *   one extra integer all-reduce. */
+FD_API int fd_ssd_loss(const float* conf, const float* loc, const float* labels, const float* gt_loc, int B, int P,
+                int neg_pos_ratio, float* row_sums, int32_t* num_pos, uint8_t* mask, float* dconf, float* dloc,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,8 @@ import sys
 from . import native, ops  # noqa: F401
 
 _DROPIN = ["models", "models.BaseModel", "models.PoolResnet", "models.Resnet", "models.ModelMeta", "losses",
-           "losses.YoloLoss", "datasets", "datasets.utils", "datasets.WIDERFace", "datasets.WIDERFace.dataset"]
+           "losses.YoloLoss", "losses.SSDLoss", "datasets", "datasets.utils", "datasets.WIDERFace",
+           "datasets.WIDERFace.dataset", "datasets.WIDERFace.dataset_ssd"]
 
 
 def install_dropin():

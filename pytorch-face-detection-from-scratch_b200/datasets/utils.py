@@ -58,6 +58,42 @@ class ReduceBoundingBoxes(nn.Module):
         return boxes[0, :k].clone()
 
 
+class ReduceSSDBoundingBoxes(nn.Module):
+    """reference datasets/utils.py:8-92.  ``__call__(x[P,5]) -> [K,5]`` rows (score, x, y, w, h) in NMS keep
+    order; ``P = sum(ps*ps)`` priors; ``with_priors`` applies the prior scaling of utils.py:59-64 (the reference
+    uses it for encoded ground truth, dataset_ssd.py:142-145)."""
+
+    def __init__(self, probability_threshold: float = 0.9, iou_threshold: float = 0.5, input_shape=(3, 320, 240),
+                 patch_sizes=(60, 30, 15, 7), priors=None, with_priors=False):
+        super().__init__()
+        self.probability_threshold = probability_threshold
+        self.iou_threshold = iou_threshold
+        self.input_shape = input_shape
+        _, self.width, self.height = input_shape
+        self.patch_sizes = tuple(patch_sizes)
+        self.with_priors = with_priors
+        self.priors = priors            # kept for interface parity; the kernel derives the priors from patch_sizes
+
+    @torch.no_grad()
+    def batch_forward(self, x: torch.Tensor):
+        """x ``[B,P,5]`` -> (boxes ``[B,P,5]``, counts ``[B]`` int32) on the device, no host synchronisation."""
+        x = x.detach().float().contiguous()
+        B, P, _ = x.shape
+        assert P == sum(ps * ps for ps in self.patch_sizes), "prior count does not match patch_sizes"
+        boxes = torch.empty((B, P, 5), dtype=torch.float32, device=x.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=x.device)
+        ops.ssd_decode_nms(x, self.patch_sizes, self.probability_threshold, self.iou_threshold, self.width,
+                           self.height, self.with_priors, boxes, counts)
+        return boxes, counts
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        boxes, counts = self.batch_forward(x.unsqueeze(0))
+        k = int(counts.item())
+        if k == 0:
+            return torch.empty(0).reshape(0, 5)      # utils.py:92
+        return boxes[0, :k].clone()
+
+
 def convert_bbx_to_xyxy(bbx):
     """reference datasets/utils.py:173-174."""
     return bbx[0], bbx[1], bbx[0] + bbx[2], bbx[1] + bbx[3]

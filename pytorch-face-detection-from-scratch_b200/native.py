@@ -39,6 +39,9 @@ SIGNATURES = {
     "fd_yolo_loss": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "fd_decode_nms": [_P, _I, _I, _I, _F, _D, _I, _I, _I, _P, _P, _P, _P],
     "fd_grid_encode": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "fd_ssd_grid_encode": [_P, _P, _I, _P, _I, _I, _I, _P, _P],
+    "fd_ssd_decode_nms": [_P, _I, _P, _I, _F, _D, _I, _I, _I, _P, _P, _P],
+    "fd_ssd_loss": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
 }
 
 

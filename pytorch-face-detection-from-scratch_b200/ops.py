@@ -143,3 +143,27 @@ def grid_encode(boxes, offsets, S, width, height, out):
     B = out.shape[0]
     check(lib().fd_grid_encode(dptr(boxes, F32), dptr(offsets, I32), B, S, int(width), int(height), dptr(out, F32),
                                cur_stream()), "fd_grid_encode")
+
+
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def ssd_grid_encode(boxes, offsets, patch_sizes, width, height, out):
+    B = out.shape[0]
+    check(lib().fd_ssd_grid_encode(dptr(boxes, F32), dptr(offsets, I32), B, _int_array(patch_sizes), len(patch_sizes),
+                                   int(width), int(height), dptr(out, F32), cur_stream()), "fd_ssd_grid_encode")
+
+
+def ssd_decode_nms(x, patch_sizes, p_thr, iou_thr, width, height, with_priors, out_boxes, out_count):
+    B = x.shape[0]
+    check(lib().fd_ssd_decode_nms(dptr(x, F32), B, _int_array(patch_sizes), len(patch_sizes), float(p_thr),
+                                  float(iou_thr), int(width), int(height), int(bool(with_priors)),
+                                  dptr(out_boxes, F32), dptr(out_count, I32), cur_stream()), "fd_ssd_decode_nms")
+
+
+def ssd_loss(conf, loc, labels, gt_loc, neg_pos_ratio, row_sums, num_pos, mask=None, dconf=None, dloc=None):
+    B, P = conf.shape
+    check(lib().fd_ssd_loss(dptr(conf, F32), dptr(loc, F32), dptr(labels, F32), dptr(gt_loc, F32), B, P,
+                            int(neg_pos_ratio), dptr(row_sums, F32), dptr(num_pos, I32), dptr(mask, U8),
+                            dptr(dconf, F32), dptr(dloc, F32), cur_stream()), "fd_ssd_loss")

@@ -82,3 +82,50 @@ def test_backbone_oracle_official_checkpoint_demo_path():
         boxes = yo.reduce_bounding_boxes(head[0].numpy(), float(g["p_thr"]), float(g["iou_thr"]), (3, 480, 480), 10)
         want = g["boxes"][i, :g["counts"][i]]
         assert boxes.tobytes() == want.tobytes()
+
+
+def test_resnet_oracle_matches_reference_seeded():
+    """oracle resnet_forward (models/Resnet.py:89-99) against the real reference module: identical logits,
+    loss and gradient fingerprints (tests/golden/make_golden_extra.py)."""
+    g = load_golden("resnet_seed3.npz")
+    p = seeded_poolresnet_params(64, seed=3, stem_k=3, stem_s=2, head_k=3)
+    for k, v in p.items():
+        s = g["w_sum." + k]
+        assert abs(v.double().sum().item() - s[0]) < 1e-9 and abs(v.double().abs().sum().item() - s[1]) < 1e-9, k
+    x = torch.rand(1, 3, 480, 480, generator=torch.Generator().manual_seed(4))
+    y = torch.from_numpy(g["y"])
+    y_hat, loss, grads = bo.train_step(x, y, p, 15, forward=bo.resnet_forward)
+    assert torch.equal(y_hat, torch.from_numpy(g["y_hat"]))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    for k in p:
+        assert abs(grads[k].double().norm().item() - float(g["g_norm." + k])) <= 1e-5 * float(g["g_norm." + k]) + 1e-12, k
+        np.testing.assert_allclose(grads[k].reshape(-1)[:64].numpy(), g["g_head." + k], rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------ SSD rows (tests/golden/make_golden_extra.py)
+def test_ssd_grid_encode_bit_exact():
+    from oracle import ssd_oracle as so
+    g = load_golden("ssd_encode.npz")
+    for c in range(g["boxes"].shape[0]):
+        b = g["boxes"][c, :g["counts"][c]]
+        assert so.ssd_grid_encode(b, 480, 480).tobytes() == g["fm"][c].tobytes(), c
+
+
+def test_ssd_decode_nms_bit_exact():
+    from oracle import ssd_oracle as so
+    g = load_golden("ssd_decode.npz")
+    for c in range(g["x"].shape[0]):
+        pthr, ithr, wp = g["cfg"][c]
+        got = so.reduce_ssd_bounding_boxes(g["x"][c], pthr, ithr, (3, 480, 480), with_priors=bool(wp))
+        want = g["out"][c, :g["counts"][c]]
+        assert got.shape == want.shape and got.tobytes() == want.tobytes(), c
+
+
+def test_ssd_loss_value_grad_and_mining_mask():
+    from oracle import ssd_oracle as so
+    g = load_golden("ssd_loss.npz")
+    loss, dconf, dloc, mask = so.ssd_loss(g["conf"], g["loc"], g["labels"], g["gt_loc"], 10)
+    assert np.array_equal(mask, g["mask"])
+    assert abs(loss - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    np.testing.assert_allclose(dconf, g["dconf"], rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(dloc, g["dloc"], rtol=2e-5, atol=1e-9)
