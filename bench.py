@@ -240,6 +240,68 @@ def main():
     e2e_s = par.max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = world * B * n_e2e / e2e_s
 
+    # ---------------- the same end-to-end step fed with uint8 images (dataset.py:146 `img / 255` fused into the stem)
+    xh8 = (x_cpu * 255.0).round().to(torch.uint8).pin_memory()
+    x8buf = [torch.empty((B, 3, 480, 480), dtype=torch.uint8, device=dev) for _ in range(2)]
+
+    def prefetch8(i):
+        with torch.cuda.stream(copy_stream):
+            x8buf[i].copy_(xh8, non_blocking=True)
+            gbuf[i].copy_(gth, non_blocking=True)
+            ready[i].record(copy_stream)
+
+    def e2e8_run(nsteps):
+        prefetch8(0)
+        for it in range(nsteps):
+            i = it & 1
+            torch.cuda.current_stream().wait_event(ready[i])
+            if it + 1 < nsteps:
+                prefetch8(i ^ 1)
+            loss = model.train_step(x8buf[i], gbuf[i])
+            par.allreduce_grads(eng.gflat)
+            _ = loss.item()
+
+    e2e8_run(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e8_run(n_e2e)
+    barrier()
+    e2e8_value = world * B * n_e2e / par.max_over_ranks(time.perf_counter() - t0, dev)
+
+    # ---------------- inference: eval forward + batched decode + NMS (BASELINE metric's second half)
+    model.eval()
+    red = model.reduce_bounding_boxes
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            pli = eng.forward(x, train=False, dropout=False)
+            red.batch_forward(pli.y)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    n0 = fd.native.launch_count()
+    g_inf = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_inf):
+        pli = eng.forward(x, train=False, dropout=False)
+        inf_boxes, inf_counts = red.batch_forward(pli.y)
+    inf_launches = fd.native.launch_count() - n0
+    for _ in range(args.warmup):
+        g_inf.replay()
+    barrier()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(args.steps):
+        g_inf.replay()
+    i1.record()
+    barrier()
+    inf_ms = par.max_over_ranks(i0.elapsed_time(i1), dev)
+    infer = {"metric": "infer_nms_images_per_sec", "value": world * B * args.steps / (inf_ms * 1e-3),
+             "unit": "images/s", "ms_per_step": inf_ms / args.steps, "launches_per_step": inf_launches,
+             "workload": "PoolResnet-medium eval forward + YOLO decode + score threshold (0.5) + IoU NMS (0.5), "
+                         "batch 64 per GPU, inputs resident in HBM, CUDA graph",
+             "kept_boxes_batch": int(inf_counts.sum().item())}
+    model.train()
+
     # ---------------- roofline of the dominant kernel (conv3x3_tc: 40 of the ~72 launches, ~85 % of the FLOPs)
     roof = None
     cpu_base = None
@@ -256,7 +318,13 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": xh.numel() * 4 + gth.numel() * 4,
                         "d2h_bytes_per_step": 4, "steps": n_e2e,
                         "note": "fp32 images from pinned host memory (the reference's training input type), "
-                                "double-buffered H2D overlapped with compute; eager public API model.train_step"},
+                                "double-buffered H2D overlapped with compute; eager public API model.train_step; "
+                                "bounded by the 177 MB/step host->device copy"},
+                "e2e_u8": {"value": e2e8_value, "unit": "images/s", "h2d_bytes_per_step": xh8.numel() + gth.numel() * 4,
+                           "d2h_bytes_per_step": 4, "steps": n_e2e,
+                           "note": "same step fed with the uint8 images the reference's dataset holds before "
+                                   "`img / 255` (datasets/WIDERFace/dataset.py:146); the division is fused into the stem"},
+                "infer": infer,
                 "gpu_launches": per_step_launches * args.steps,
                 "launches_per_step": per_step_launches, "cuda_graph": graph is not None,
                 "achieved_tflops_step": 3 * FLOPS_FWD_PER_IMG * B / (ms / args.steps * 1e-3) / 1e12,
@@ -331,10 +399,17 @@ def conv_roofline(fd, eng, pl, dev):
                                           "tflops": fl / (ms * 1e-3) / 1e12}
     achieved = tot_fl / (tot_ms * 1e-3) / 1e12
     big = by_shape.get("60x60")
+    traffic, traffic_src = None, None
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_conv3x3_traffic.json")))
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:  # noqa: BLE001
+        pass
     return {"kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM; the fwd + dgrad launches of one step outside the "
                       "fused 15x15 chain)",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "peak_source": which, "traffic": None, "launches": len(calls),
+            "peak_source": which, "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
+            "launches": len(calls),
             "avg_launch_us": tot_ms * 1e3 / len(calls), "by_shape": by_shape,
             "largest_shape_frac": (big["tflops"] / peak) if big else None,
             "note": "M=128,N=64,K=16 SS-mode tcgen05.mma is shared-memory-operand bound (6 KB/MMA at 128 B/clk "
