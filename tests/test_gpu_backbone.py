@@ -176,12 +176,14 @@ def test_chain_kernels_equal_per_layer_path(dropout):
     assert rel_err(res[True][2], res[False][2]) <= 1e-5
 
 
-def test_chain_forward_many_images_per_cta():
-    """B > number of SMs: every CTA of the chain kernel walks several images (buffer reuse, barrier phases)."""
+@pytest.mark.parametrize("B,H,W", [(300, 15, 15), (5, 7, 7), (9, 11, 11), (3, 15, 7)])
+def test_chain_forward_many_images_per_cta(B, H, W):
+    """B > number of SMs: every CTA (or 2-CTA cluster) of the chain kernel walks several images (buffer reuse,
+    barrier phases).  15x15 runs in cluster-split mode, the other shapes on the one-CTA-per-image variant."""
     require_cuda()
     f = fd()
     ops = f.ops
-    B, H, W, C, nb = 300, 15, 15, 64, 3
+    C, nb = 64, 3
     g = torch.Generator().manual_seed(3)
     x = (torch.randn(B, H, W, C, generator=g) * 0.5).cuda().bfloat16()
     w = (torch.randn(2 * nb, C, C, 3, 3, generator=g) * 0.05).cuda()

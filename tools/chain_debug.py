@@ -44,11 +44,12 @@ if os.environ.get("FD_CHAIN_TIMING"):
     import ctypes
     import numpy as np
     nl = 2 * nb
-    buf = (ctypes.c_ulonglong * (nl * 16))()
+    buf = (ctypes.c_ulonglong * (2 * 24 * 16))()
     fd.native.lib().fd_debug_chain_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
-    fd.native.lib().fd_debug_chain_timing(buf, nl * 16)
-    t = np.array(buf[:], dtype=np.int64).reshape(nl, 16)
-    t0 = t[0, 0]
-    names = {0: "mma_go", 1: "mma_issued", 2: "epi_top", 3: "acc0", 4: "ld0", 7: "acc1", 8: "ld1", 11: "math_done", 12: "fenced", 13: "bar"}
+    fd.native.lib().fd_debug_chain_timing(buf, 2 * 24 * 16)
+    t = np.array(buf[:], dtype=np.int64).reshape(2, 24, 16)
+    t0 = t[0, 0, 0]
+    names = {4: "woke", 0: "mma_go", 1: "mma_issued", 5: "mma_done", 2: "epi_top", 6: "waited", 7: "topbar", 8: "prepoll", 3: "acc", 11: "math_done", 13: "bar", 14: "arrived"}
     for l in range(nl):
-        print(l, " ".join(f"{names[k]}={t[l, k] - t0}" for k in sorted(names)))
+        for r in range(2):
+            print(l, "rank", r, " ".join(f"{names[k]}={t[r, l, k] - t0}" for k in (0, 1, 5, 2, 6, 7, 8, 3, 11, 13)))
