@@ -159,14 +159,17 @@ FD_API int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B, in
 /* ---------------------------------------------------------------------------------------------
  * Head (models/PoolResnet.py:83-89,100-102): Dropout2d multiplier, KxK stride-1 conv C -> 5 with
  * padding `pad`, + bias, sigmoid.  x: [B,H,W,C] bf16, w: [5][C][K][K] fp32, y: [B,5,Ho,Wo] fp32. */
-FD_API int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* bias, int B, int H, int W,
-                int C, int K, int pad, float* y, void* stream);
+/* w_t (nullable): the same weights pre-arranged by fd_head_pack ([K*K*5][C] fp32, tap-major, swizzled channel
+ * groups); with it the C = 64 fast-path kernels run, without it a generic kernel transposes w itself. */
+FD_API int fd_head_pack(const float* w, int C, int K, float* w_t, void* stream);
+FD_API int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* w_t, const float* bias,
+                int B, int H, int W, int C, int K, int pad, float* y, void* stream);
 /* dy: [B,5,Ho,Wo] fp32 gradient w.r.t. the sigmoid OUTPUT y.  Produces
  *   dx [B,H,W,C] bf16 (gradient w.r.t. the block output, dropout multiplier applied; overwritten) and,
  *   when dx2 != NULL, dx2 = dx * chan_scale2 * (mask_bits bit ? 1 : slope)   (mask_bits: uint32 [B,H,W,C/32]),
  *   dw [5][C][K][K] fp32 (+=), dbias [5] fp32 (+=). */
-FD_API int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* y, const float* dy, int B,
-                int H, int W, int C, int K, int pad, fd_bf16* dx, const uint32_t* mask_bits,
+FD_API int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* w_t, const float* y,
+                const float* dy, int B, int H, int W, int C, int K, int pad, fd_bf16* dx, const uint32_t* mask_bits,
                 const float* chan_scale2, float slope, fd_bf16* dx2, float* dw, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

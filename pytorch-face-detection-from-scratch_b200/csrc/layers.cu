@@ -509,183 +509,258 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
   f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
 }
 
+// weights [5][64][K][K] fp32 -> w_t [K*K*5][64] fp32 in the swizzled layout of head_w_index (done once per
+// step, so that every CTA stages its copy with plain coalesced float4 loads)
+__global__ void head_pack_kernel(const float* __restrict__ w, int KK, float* __restrict__ wt) {
+  const int n = KK * 5 * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int t = i % KK, c = (i / KK) % 64, o = i / (KK * 64);
+    wt[head_w_index(t * 5 + o, c)] = w[i];
+  }
+}
+// channel of element j of the swizzled table
+__device__ __forceinline__ int head_w_channel(int j) {
+  const int to = j >> 6;
+  return (((((j >> 3) & 7) ^ to) & 7) << 3) + (j & 7);
+}
+
+// Forward.  Register tiling: one thread = 5 consecutive output pixels x 5 outputs for one channel group (8 channels)
+// and one tap residue, so each weight fetched from shared memory feeds 5 FMAs (a one-pixel-per-thread layout is
+// bound by the shared-memory bandwidth of the weight reads, 1 FMA per 4 bytes).  One warp = (output row, strip of
+// 5 pixels): lanes = (tap residue ts = lane/8, channel group g = lane%8); the 32 partial sums meet in a shuffle tree.
+constexpr int kHeadStrip = 5;
 template <int K, int PAD>
-__global__ void __launch_bounds__(256)
-head_fwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ w,
-                    const float* __restrict__ bias, int H, int W, int Ho, int Wo, float* __restrict__ y) {
-  constexpr int C = 64, KK = K * K;
+__global__ void __launch_bounds__(512)
+head_fwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ wt,
+                    const float* __restrict__ bias, int H, int W, int Ho, int Wo, int rows_per_cta,
+                    float* __restrict__ y) {
+  constexpr int C = 64, KK = K * K, P = kHeadStrip;
   extern __shared__ float sm[];
   float* sW = sm;                                                       // [KK*5][64], pre-scaled by the dropout multiplier
-  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sm + KK * 5 * C);  // [H*W][64]
-  const int n = blockIdx.x;
-  for (int i = threadIdx.x; i < KK * 5 * C; i += 256) {
-    const int t = i % KK, c = (i / KK) % C, o = i / (KK * C);
-    sW[head_w_index(t * 5 + o, c)] = __ldg(w + i) * (cs ? __ldg(cs + n * C + c) : 1.f);
-  }
-  const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * H * W * C);
-  for (int i = threadIdx.x; i < H * W * C / 8; i += 256) reinterpret_cast<uint4*>(sX)[i] = __ldg(xs + i);
-  __syncthreads();
-  const int npix = Ho * Wo;
-  const int per = (npix + kHeadParts - 1) / kHeadParts;
-  const int p0 = blockIdx.y * per, p1 = min(npix, p0 + per);
-  for (int task = threadIdx.x; task < ((p1 - p0) * 8 + 31) / 32 * 32; task += 256) {
-    const int g = task & 7, pix = p0 + (task >> 3);
-    const bool live = pix < p1;
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    if (live) {
-      const int oy = pix / Wo, ox = pix - oy * Wo;
-#pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int iy = oy + ky - PAD;
-        if (PAD > 0 && (iy < 0 || iy >= H)) continue;
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const int ix = ox + kx - PAD;
-          if (PAD > 0 && (ix < 0 || ix >= W)) continue;
-          float xv[8];
-          bf16x8_to_f32(*reinterpret_cast<const uint4*>(sX + (iy * W + ix) * C + g * 8), xv);
-          const int to0 = (ky * K + kx) * 5;
-#pragma unroll
-          for (int o = 0; o < 5; ++o) {
-            const float4* wp = reinterpret_cast<const float4*>(sW + (to0 + o) * 64 + (((g ^ (to0 + o)) & 7) << 3));
-            const float4 w0 = wp[0], w1 = wp[1];
-            acc[o] = fmaf(xv[0], w0.x, acc[o]); acc[o] = fmaf(xv[1], w0.y, acc[o]);
-            acc[o] = fmaf(xv[2], w0.z, acc[o]); acc[o] = fmaf(xv[3], w0.w, acc[o]);
-            acc[o] = fmaf(xv[4], w1.x, acc[o]); acc[o] = fmaf(xv[5], w1.y, acc[o]);
-            acc[o] = fmaf(xv[6], w1.z, acc[o]); acc[o] = fmaf(xv[7], w1.w, acc[o]);
-          }
-        }
-      }
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sm + KK * 5 * C);  // [rows_per_cta + K - 1][W][64]
+  const int n = blockIdx.x, oy0 = blockIdx.y * rows_per_cta;
+  const int nrows_in = rows_per_cta + K - 1;
+  for (int i = threadIdx.x; i < KK * 5 * C / 4; i += blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(wt) + i);
+    if (cs) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + n * C + head_w_channel(4 * i)));
+      v.x *= s4.x; v.y *= s4.y; v.z *= s4.z; v.w *= s4.w;
     }
+    reinterpret_cast<float4*>(sW)[i] = v;
+  }
+  for (int i = threadIdx.x; i < nrows_in * W * C / 8; i += blockDim.x) {
+    const int r = i / (W * C / 8), rem = i - r * (W * C / 8);
+    const int iy = oy0 + r - PAD;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H) v = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<size_t>(n) * H + iy) * W * C) + rem);
+    reinterpret_cast<uint4*>(sX)[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane & 7, ts = lane >> 3;
+  const int strips = (Wo + P - 1) / P;
+  const int ry = warp / strips, ox0 = (warp - ry * strips) * P;
+  const int oy = oy0 + ry;
+  if (ry >= rows_per_cta || oy >= Ho) return;
+  float acc[P][5];
+#pragma unroll
+  for (int j = 0; j < P; ++j)
+#pragma unroll
+    for (int o = 0; o < 5; ++o) acc[j][o] = 0.f;
+#pragma unroll 1
+  for (int t = ts; t < KK; t += 4) {
+    const int ky = t / K, kx = t - ky * K;
+    float xv[P][8];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int ix = ox0 + j + kx - PAD;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (ix >= 0 && ix < W) u = *reinterpret_cast<const uint4*>(sX + ((ry + ky) * W + ix) * C + g * 8);
+      bf16x8_to_f32(u, xv[j]);
+    }
+    const int to0 = t * 5;
 #pragma unroll
     for (int o = 0; o < 5; ++o) {
-      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
-      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
-      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 4);
+      const float4* wp = reinterpret_cast<const float4*>(sW + (to0 + o) * 64 + (((g ^ (to0 + o)) & 7) << 3));
+      const float4 w0 = wp[0], w1 = wp[1];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        float a = acc[j][o];
+        a = fmaf(xv[j][0], w0.x, a); a = fmaf(xv[j][1], w0.y, a); a = fmaf(xv[j][2], w0.z, a); a = fmaf(xv[j][3], w0.w, a);
+        a = fmaf(xv[j][4], w1.x, a); a = fmaf(xv[j][5], w1.y, a); a = fmaf(xv[j][6], w1.z, a); a = fmaf(xv[j][7], w1.w, a);
+        acc[j][o] = a;
+      }
     }
-    if (live && g < 5) {
-      const float v = (g == 0 ? acc[0] : g == 1 ? acc[1] : g == 2 ? acc[2] : g == 3 ? acc[3] : acc[4]) + __ldg(bias + g);
-      y[(static_cast<size_t>(n) * 5 + g) * npix + pix] = 1.f / (1.f + expf(-v));
+  }
+  float mine = 0.f;
+#pragma unroll
+  for (int j = 0; j < P; ++j)
+#pragma unroll
+    for (int o = 0; o < 5; ++o) {
+      float v = acc[j][o];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == j * 5 + o) mine = v;
+    }
+  if (lane < P * 5) {
+    const int j = lane / 5, o = lane - j * 5;
+    if (ox0 + j < Wo) {
+      const float v = mine + __ldg(bias + o);
+      y[(static_cast<size_t>(n) * 5 + o) * Ho * Wo + oy * Wo + ox0 + j] = 1.f / (1.f + expf(-v));
     }
   }
 }
 
+// Backward.  grid = (B, dx_parts + dw_parts).  CTAs with blockIdx.y < dx_parts produce `rows_per_cta` rows of dx
+// with the register tiling of the forward (thread = 5 input pixels x 8 channels, lanes = (tap residue, channel
+// group)); the others accumulate the weight gradient of kDwTaps taps each (one warp per (tap, half of the output
+// pixels), thread = 5 outputs x 8 channels, lanes = (pixel residue, channel group)).
+constexpr int kDwTaps = 18;
 template <int K, int PAD>
-__global__ void __launch_bounds__(256)
-head_bwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ w,
+__global__ void __launch_bounds__(512)
+head_bwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ wt,
                     const float* __restrict__ y, const float* __restrict__ dy, int H, int W, int Ho, int Wo,
-                    __nv_bfloat16* __restrict__ dx, const uint32_t* __restrict__ mask_bits,
-                    const float* __restrict__ cs2, float slope, __nv_bfloat16* __restrict__ dx2,
-                    float* __restrict__ dw, float* __restrict__ dbias) {
-  constexpr int C = 64, KK = K * K;
-  constexpr int TPP = (KK + kHeadParts - 1) / kHeadParts;       // taps per part (weight gradient)
+                    int rows_per_cta, int dx_parts, __nv_bfloat16* __restrict__ dx,
+                    const uint32_t* __restrict__ mask_bits, const float* __restrict__ cs2, float slope,
+                    __nv_bfloat16* __restrict__ dx2, float* __restrict__ dw, float* __restrict__ dbias) {
+  constexpr int C = 64, KK = K * K, P = kHeadStrip;
   extern __shared__ float sm[];
-  float* sW = sm;                                   // [KK*5][64] swizzled
-  float* sAcc = sW + KK * 5 * C;                    // [TPP*5][64] weight-gradient partial sums of this CTA
-  float* sDz = sAcc + TPP * 5 * C;                  // [5][Ho*Wo]
-  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sDz + ((5 * Ho * Wo + 3) & ~3));   // [H*W][64]
-  const int n = blockIdx.x, part = blockIdx.y;
+  const int n = blockIdx.x;
   const int npo = Ho * Wo;
-  for (int i = threadIdx.x; i < KK * 5 * C; i += 256) {
-    const int t = i % KK, c = (i / KK) % C, o = i / (KK * C);
-    sW[head_w_index(t * 5 + o, c)] = __ldg(w + i);
-  }
-  for (int i = threadIdx.x; i < TPP * 5 * C; i += 256) sAcc[i] = 0.f;
-  for (int i = threadIdx.x; i < 5 * npo; i += 256) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane & 7, ls = lane >> 3;
+  float* sDz = sm;                                  // [5][npo] (+pad)
+  const int dz_words = (5 * npo + 3) & ~3;
+  for (int i = threadIdx.x; i < 5 * npo; i += blockDim.x) {
     const float yv = y[static_cast<size_t>(n) * 5 * npo + i];
     sDz[i] = dy[static_cast<size_t>(n) * 5 * npo + i] * yv * (1.f - yv);
   }
-  const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * H * W * C);
-  for (int i = threadIdx.x; i < H * W * C / 8; i += 256) reinterpret_cast<uint4*>(sX)[i] = __ldg(xs + i);
-  __syncthreads();
-  if (part == 0 && threadIdx.x < 5) {
-    float t = 0.f;
-    for (int i = 0; i < npo; ++i) t += sDz[threadIdx.x * npo + i];
-    atomicAdd(dbias + threadIdx.x, t);
-  }
-  // ---- dx (and the masked copy that starts the last block's backward chain): this CTA's share of the pixels
-  {
-    const int npi = H * W;
-    const int per = (npi + kHeadParts - 1) / kHeadParts;
-    const int p0 = part * per, p1 = min(npi, p0 + per);
-    for (int task = threadIdx.x; task < (p1 - p0) * 8; task += 256) {
-      const int g = task & 7, pix = p0 + (task >> 3);
-      const int iy = pix / W, ix = pix - iy * W;
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (static_cast<int>(blockIdx.y) < dx_parts) {
+    // ------------------------------------------------------------------ dx rows
+    float* sW = sm + dz_words;                      // [KK*5][64] swizzled, unscaled
+    for (int i = threadIdx.x; i < KK * 5 * C / 4; i += blockDim.x)
+      reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
+    __syncthreads();
+    if (blockIdx.y == 0 && threadIdx.x < 5) {
+      float t = 0.f;
+      for (int i = 0; i < npo; ++i) t += sDz[threadIdx.x * npo + i];
+      atomicAdd(dbias + threadIdx.x, t);
+    }
+    const int strips = (W + P - 1) / P;
+    const int ry = warp / strips, ix0 = (warp - ry * strips) * P;
+    const int iy = blockIdx.y * rows_per_cta + ry;
+    if (ry >= rows_per_cta || iy >= H) return;
+    float acc[P][8];
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int oy = iy - ky + PAD;
-        if (oy < 0 || oy >= Ho) continue;
+    for (int j = 0; j < P; ++j)
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const int ox = ix - kx + PAD;
-          if (ox < 0 || ox >= Wo) continue;
-          const int to0 = (ky * K + kx) * 5;
+      for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+#pragma unroll 1
+    for (int t = ls; t < KK; t += 4) {
+      const int ky = t / K, kx = t - ky * K;
+      const int oy = iy - ky + PAD;
+      if (oy < 0 || oy >= Ho) continue;
+      const int to0 = t * 5;
+#pragma unroll
+      for (int o = 0; o < 5; ++o) {
+        const float4* wp = reinterpret_cast<const float4*>(sW + (to0 + o) * 64 + (((g ^ (to0 + o)) & 7) << 3));
+        const float4 w0 = wp[0], w1 = wp[1];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          const int ox = ix0 + j - kx + PAD;
+          const float dz = (ox >= 0 && ox < Wo) ? sDz[o * npo + oy * Wo + ox] : 0.f;
+          acc[j][0] = fmaf(dz, w0.x, acc[j][0]); acc[j][1] = fmaf(dz, w0.y, acc[j][1]);
+          acc[j][2] = fmaf(dz, w0.z, acc[j][2]); acc[j][3] = fmaf(dz, w0.w, acc[j][3]);
+          acc[j][4] = fmaf(dz, w1.x, acc[j][4]); acc[j][5] = fmaf(dz, w1.y, acc[j][5]);
+          acc[j][6] = fmaf(dz, w1.z, acc[j][6]); acc[j][7] = fmaf(dz, w1.w, acc[j][7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        acc[j][e] += __shfl_xor_sync(0xffffffffu, acc[j][e], 8);
+        acc[j][e] += __shfl_xor_sync(0xffffffffu, acc[j][e], 16);
+      }
+    if (ls == 0) {
+      float csv[8], cs2v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        csv[e] = cs ? __ldg(cs + n * C + g * 8 + e) : 1.f;
+        cs2v[e] = cs2 ? __ldg(cs2 + n * C + g * 8 + e) : 1.f;
+      }
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const int ix = ix0 + j;
+        if (ix >= W) break;
+        const size_t gi = ((static_cast<size_t>(n) * H + iy) * W + ix) * C + g * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = acc[j][e] * csv[e];
+        if (dx) *reinterpret_cast<uint4*>(dx + gi) = pack8(v);
+        if (dx2) {
+          const uint32_t mk = __ldg(mask_bits + (gi >> 5)) >> (gi & 31);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = v[e] * (((mk >> e) & 1u) ? 1.f : slope) * cs2v[e];
+          *reinterpret_cast<uint4*>(dx2 + gi) = pack8(v);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ dw of kDwTaps taps
+    const int t0 = (blockIdx.y - dx_parts) * kDwTaps;
+    __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(sm + dz_words);                 // [H*W][64]
+    float* sAcc = reinterpret_cast<float*>(sX + static_cast<size_t>(H) * W * C);          // [kDwTaps][5][64]
+    const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * H * W * C);
+    for (int i = threadIdx.x; i < H * W * C / 8; i += blockDim.x) reinterpret_cast<uint4*>(sX)[i] = __ldg(xs + i);
+    for (int i = threadIdx.x; i < kDwTaps * 5 * C; i += blockDim.x) sAcc[i] = 0.f;
+    __syncthreads();
+    const int nwarps = blockDim.x >> 5;
+    for (int wtask = warp; wtask < 2 * kDwTaps; wtask += nwarps) {      // warp task = (tap, half of the pixels)
+      const int tl = wtask >> 1, half = wtask & 1;
+      const int t = t0 + tl;
+      if (t < KK) {
+        const int ky = t / K, kx = t - ky * K;
+        float acc[5][8];
+#pragma unroll
+        for (int o = 0; o < 5; ++o)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[o][e] = 0.f;
+        for (int po = half * 4 + ls; po < npo; po += 8) {
+          const int oy = po / Wo, ox = po - oy * Wo;
+          const int iy = oy + ky - PAD, ix = ox + kx - PAD;
+          if (PAD > 0 && (iy < 0 || iy >= H || ix < 0 || ix >= W)) continue;
+          float xv[8];
+          bf16x8_to_f32(*reinterpret_cast<const uint4*>(sX + (iy * W + ix) * C + g * 8), xv);
 #pragma unroll
           for (int o = 0; o < 5; ++o) {
-            const float dz = sDz[o * npo + oy * Wo + ox];
-            const float4* wp = reinterpret_cast<const float4*>(sW + (to0 + o) * 64 + (((g ^ (to0 + o)) & 7) << 3));
-            const float4 w0 = wp[0], w1 = wp[1];
-            acc[0] = fmaf(dz, w0.x, acc[0]); acc[1] = fmaf(dz, w0.y, acc[1]);
-            acc[2] = fmaf(dz, w0.z, acc[2]); acc[3] = fmaf(dz, w0.w, acc[3]);
-            acc[4] = fmaf(dz, w1.x, acc[4]); acc[5] = fmaf(dz, w1.y, acc[5]);
-            acc[6] = fmaf(dz, w1.z, acc[6]); acc[7] = fmaf(dz, w1.w, acc[7]);
+            const float dz = sDz[o * npo + po];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(xv[e], dz, acc[o][e]);
           }
         }
+#pragma unroll
+        for (int o = 0; o < 5; ++o)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = acc[o][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (ls == 0) atomicAdd(sAcc + (tl * 5 + o) * C + g * 8 + e, v);
+          }
       }
-      const size_t gi = (static_cast<size_t>(n) * npi + pix) * C + g * 8;
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = acc[e] * (cs ? __ldg(cs + n * C + g * 8 + e) : 1.f);
-      if (dx) *reinterpret_cast<uint4*>(dx + gi) = pack8(v);
-      if (dx2) {
-        const uint32_t mk = __ldg(mask_bits + (gi >> 5)) >> (gi & 31);
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          v[e] = v[e] * (((mk >> e) & 1u) ? 1.f : slope) * (cs2 ? __ldg(cs2 + n * C + g * 8 + e) : 1.f);
-        *reinterpret_cast<uint4*>(dx2 + gi) = pack8(v);
-      }
-    }
-  }
-  // ---- dw: this CTA's share of the taps; work item = (tap, channel group, third of the output pixels)
-  {
-    const int t0 = part * TPP, t1 = min(KK, t0 + TPP);
-    const int ntask = (t1 - t0) * 8 * 3;
-    for (int task = threadIdx.x; task < ntask; task += 256) {
-      const int g = task & 7, third = (task >> 3) % 3, tl = task / 24;
-      const int t = t0 + tl, ky = t / K, kx = t - ky * K;
-      float acc[5][8];
-#pragma unroll
-      for (int o = 0; o < 5; ++o)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[o][e] = 0.f;
-      for (int po = third; po < npo; po += 3) {
-        const int oy = po / Wo, ox = po - oy * Wo;
-        const int iy = oy + ky - PAD, ix = ox + kx - PAD;
-        if (PAD > 0 && (iy < 0 || iy >= H || ix < 0 || ix >= W)) continue;
-        float xv[8];
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(sX + (iy * W + ix) * C + g * 8), xv);
-#pragma unroll
-        for (int o = 0; o < 5; ++o) {
-          const float dz = sDz[o * npo + po];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(xv[e], dz, acc[o][e]);
-        }
-      }
-#pragma unroll
-      for (int o = 0; o < 5; ++o)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(sAcc + (tl * 5 + o) * C + g * 8 + e, acc[o][e]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (t1 - t0) * 5 * C; i += 256) {
+    for (int i = threadIdx.x; i < kDwTaps * 5 * C; i += blockDim.x) {
       const int c = i % C, o = (i / C) % 5, tl = i / (5 * C);
-      const float s = cs ? __ldg(cs + n * C + c) : 1.f;
-      atomicAdd(dw + (static_cast<size_t>(o) * C + c) * KK + t0 + tl, sAcc[i] * s);
+      if (t0 + tl < KK) {
+        const float s = cs ? __ldg(cs + n * C + c) : 1.f;
+        atomicAdd(dw + (static_cast<size_t>(o) * C + c) * KK + t0 + tl, sAcc[i] * s);
+      }
     }
   }
 }
-
 
 __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
                                       __nv_bfloat16* __restrict__ y) {
@@ -877,20 +952,32 @@ extern "C" int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B
   return launch_status();
 }
 
-extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* bias, int B, int H,
-                           int W, int C, int K, int pad, float* y, void* stream) {
+extern "C" int fd_head_pack(const float* w, int C, int K, float* w_t, void* stream) {
+  if (!w || !w_t || K <= 0) return FD_EINVAL;
+  if (C != 64) return FD_EUNSUPPORTED;
+  head_pack_kernel<<<(K * K * 5 * 64 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, K * K, w_t);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* w_t,
+                           const float* bias, int B, int H, int W, int C, int K, int pad, float* y, void* stream) {
   if (!x || !w || !bias || !y || B <= 0) return FD_EINVAL;
   if ((H * W * C) % 8 != 0) return FD_EUNSUPPORTED;
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
-  if (C == 64 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
-    const size_t sm2 = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>(H) * W * C * 2;
-    if (sm2 <= 227 * 1024) {
+  if (w_t && C == 64 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
+    const int strips = (Wo + kHeadStrip - 1) / kHeadStrip;
+    int rows_per_cta = 512 / 32 / strips;                    // one warp per (output row, strip of 5 pixels)
+    if (rows_per_cta > (Ho + 1) / 2) rows_per_cta = (Ho + 1) / 2;
+    const int parts = (Ho + rows_per_cta - 1) / rows_per_cta;
+    const size_t sm2 = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>(rows_per_cta + K - 1) * W * C * 2;
+    if (sm2 <= 227 * 1024 && rows_per_cta >= 1) {
       auto kern = (K == 6) ? head_fwd_c64_kernel<6, 0> : head_fwd_c64_kernel<3, 1>;
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
       if (e2 != cudaSuccess) return (int)e2;
-      kern<<<dim3(B, kHeadParts), 256, sm2, static_cast<cudaStream_t>(stream)>>>(
-          reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, bias, H, W, Ho, Wo, y);
+      kern<<<dim3(B, parts), rows_per_cta * strips * 32, sm2, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w_t, bias, H, W, Ho, Wo, rows_per_cta, y);
       count_launch();
       return launch_status();
     }
@@ -905,7 +992,8 @@ extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const floa
   return launch_status();
 }
 
-extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* y, const float* dy,
+extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* w_t, const float* y,
+                           const float* dy,
                            int B, int H, int W, int C, int K, int pad, fd_bf16* dx, const uint32_t* mask_bits,
                            const float* chan_scale2, float slope, fd_bf16* dx2, float* dw, float* dbias, void* stream) {
   if (!x || !w || !y || !dy || !dw || !dbias || B <= 0) return FD_EINVAL;
@@ -914,16 +1002,23 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
   if ((H * W * C) % 8 != 0 || kHeadThreads % C != 0) return FD_EUNSUPPORTED;
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
-  if (C == 64 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
-    const int KK = K * K, TPP = (KK + kHeadParts - 1) / kHeadParts;
-    const size_t sm2 = static_cast<size_t>(KK) * 5 * C * 4 + static_cast<size_t>(TPP) * 5 * C * 4 +
-                       static_cast<size_t>((5 * Ho * Wo + 3) & ~3) * 4 + static_cast<size_t>(H) * W * C * 2;
-    if (sm2 <= 227 * 1024) {
+  if (w_t && C == 64 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
+    const int KK = K * K, dw_parts = (KK + kDwTaps - 1) / kDwTaps;
+    const int strips = (W + kHeadStrip - 1) / kHeadStrip;
+    int rows_per_cta = 512 / 32 / strips;
+    if (rows_per_cta > (H + 2) / 3) rows_per_cta = (H + 2) / 3;
+    const int dx_parts = (H + rows_per_cta - 1) / rows_per_cta;
+    int threads = rows_per_cta * strips * 32;
+    const size_t dz = static_cast<size_t>((5 * Ho * Wo + 3) & ~3) * 4;
+    const size_t sm_dx = dz + static_cast<size_t>(KK) * 5 * C * 4;
+    const size_t sm_dw = dz + static_cast<size_t>(H) * W * C * 2 + static_cast<size_t>(kDwTaps) * 5 * C * 4;
+    const size_t sm2 = sm_dx > sm_dw ? sm_dx : sm_dw;
+    if (sm2 <= 227 * 1024 && threads <= 512) {
       auto kern = (K == 6) ? head_bwd_c64_kernel<6, 0> : head_bwd_c64_kernel<3, 1>;
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
       if (e2 != cudaSuccess) return (int)e2;
-      kern<<<dim3(B, kHeadParts), 256, sm2, static_cast<cudaStream_t>(stream)>>>(
-          reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, y, dy, H, W, Ho, Wo,
+      kern<<<dim3(B, dx_parts + dw_parts), threads, sm2, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w_t, y, dy, H, W, Ho, Wo, rows_per_cta, dx_parts,
           reinterpret_cast<__nv_bfloat16*>(dx), mask_bits, chan_scale2, slope, reinterpret_cast<__nv_bfloat16*>(dx2),
           dw, dbias);
       count_launch();

@@ -192,6 +192,7 @@ class BackboneEngine:
         self.gzero = torch.zeros(self.n_flat + n3, dtype=F32, device=device)
         self.gflat = self.gzero[:self.n_flat]
         self.dwp = self.gzero[self.n_flat:]
+        self.w_head_t = torch.empty(self.head_k * self.head_k * 5 * self.F, dtype=F32, device=device)
         self.w_fwd = torch.empty(n3, dtype=BF16, device=device)
         self.w_dgrad = torch.empty(n3, dtype=BF16, device=device)
         self.plans.clear()
@@ -226,6 +227,7 @@ class BackboneEngine:
         L = 2 * self.num_blocks
         ops.pack_conv3x3(self.section(self.pflat, "w3"), self.w_fwd.view(L, 9, self.F, self.F),
                          self.w_dgrad.view(L, 9, self.F, self.F))
+        ops.head_pack(self.section(self.pflat, "out.weight"), self.w_head_t)
         self.weights_dirty = False
 
     def _wf(self, layer):
@@ -281,7 +283,7 @@ class BackboneEngine:
             cur = blk.out
         cs = pl.drop[self.num_blocks] if pl.drop is not None else None
         ops.head_fwd(cur, cs, self.section(self.pflat, "out.weight"), self.section(self.pflat, "out.bias"), pl.y,
-                     self.head_pad)
+                     self.head_pad, w_t=self.w_head_t)
 
     def _chain_forward(self, pl: _Plan, ch, x):
         k0, k1 = ch["k0"], ch["k1"]
@@ -331,7 +333,7 @@ class BackboneEngine:
                      dy, self.head_pad, last.G, None if last.pool else last.mb,
                      None if (last.pool or drop is None) else drop[nb - 1], self.slope,
                      None if last.pool else last.gp2, self.section(self.gflat, "out.weight"),
-                     self.section(self.gflat, "out.bias"))
+                     self.section(self.gflat, "out.bias"), w_t=self.w_head_t)
         in_group = {}
         for grp in pl.groups:
             for k in range(grp[0], grp[1] + 1):

@@ -32,8 +32,9 @@ SIGNATURES = {
     "fd_dropout_scale": [_P, _c.c_long, _c.c_long, _F, _F, _P, _P],
     "fd_stem_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "fd_stem_wgrad": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
-    "fd_head_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
-    "fd_head_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
+    "fd_head_pack": [_P, _I, _I, _P, _P],
+    "fd_head_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fd_head_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
     "fd_maxpool2x2_fwd": [_P, _I, _I, _I, _I, _P, _P],
     "fd_maxpool2x2_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P],
     "fd_yolo_loss": [_P, _P, _I, _I, _I, _P, _P, _P, _P],

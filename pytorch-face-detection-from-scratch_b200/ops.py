@@ -100,17 +100,23 @@ def stem_wgrad(x, g, dw, dbias, stride, pad):
                               dptr(dw, F32), dptr(dbias, F32), cur_stream()), "fd_stem_wgrad")
 
 
-def head_fwd(x, chan_scale, w, bias, y, pad):
-    B, H, W, C = x.shape
-    K = w.shape[2]
-    check(lib().fd_head_fwd(dptr(x, BF16), dptr(chan_scale, F32), dptr(w, F32), dptr(bias, F32), B, H, W, C, K, pad,
-                            dptr(y, F32), cur_stream()), "fd_head_fwd")
+def head_pack(w, w_t):
+    C, K = w.shape[1], w.shape[2]
+    check(lib().fd_head_pack(dptr(w, F32), C, K, dptr(w_t, F32), cur_stream()), "fd_head_pack")
 
 
-def head_bwd(x, chan_scale, w, y, dy, pad, dx, mask_bits, chan_scale2, slope, dx2, dw, dbias):
+def head_fwd(x, chan_scale, w, bias, y, pad, w_t=None):
     B, H, W, C = x.shape
     K = w.shape[2]
-    check(lib().fd_head_bwd(dptr(x, BF16), dptr(chan_scale, F32), dptr(w, F32), dptr(y, F32), dptr(dy, F32), B, H, W, C,
+    check(lib().fd_head_fwd(dptr(x, BF16), dptr(chan_scale, F32), dptr(w, F32), dptr(w_t, F32), dptr(bias, F32), B, H, W,
+                            C, K, pad, dptr(y, F32), cur_stream()), "fd_head_fwd")
+
+
+def head_bwd(x, chan_scale, w, y, dy, pad, dx, mask_bits, chan_scale2, slope, dx2, dw, dbias, w_t=None):
+    B, H, W, C = x.shape
+    K = w.shape[2]
+    check(lib().fd_head_bwd(dptr(x, BF16), dptr(chan_scale, F32), dptr(w, F32), dptr(w_t, F32), dptr(y, F32),
+                            dptr(dy, F32), B, H, W, C,
                             K, pad, dptr(dx, BF16), dptr(mask_bits, I32), dptr(chan_scale2, F32), slope,
                             dptr(dx2, BF16), dptr(dw, F32), dptr(dbias, F32), cur_stream()), "fd_head_bwd")
 

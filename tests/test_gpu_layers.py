@@ -163,14 +163,19 @@ def test_head_fwd_bwd(H, K, pad):
     b = torch.randn(5, device=dev).requires_grad_(True)
     Ho = H + 2 * pad - K + 1
     y = torch.zeros(B, 5, Ho, Ho, device=dev)
-    ops.head_fwd(x, cs, w.detach(), b.detach(), y, pad)
+    wt = torch.empty(K * K * 5 * C, device=dev)
+    ops.head_pack(w.detach(), wt)
+    ops.head_fwd(x, cs, w.detach(), b.detach(), y, pad, w_t=wt)
+    y_generic = torch.zeros_like(y)
+    ops.head_fwd(x, cs, w.detach(), b.detach(), y_generic, pad)          # generic kernel (no packed weights)
+    assert (y - y_generic).abs().max().item() <= 2e-5
     xin = (x.float().permute(0, 3, 1, 2)).requires_grad_(True)
     ref = torch.sigmoid(F.conv2d(xin * cs[:, :, None, None], w, b, padding=pad))
     assert (y - ref).abs().max().item() <= 2e-5
     dy = torch.randn_like(y)
     dx = torch.zeros_like(x); dx2 = torch.zeros_like(x)
     dw = torch.zeros_like(w); dbias = torch.zeros_like(b)
-    ops.head_bwd(x, cs, w.detach(), y, dy, pad, dx, _bits(msk), cs2, 0.2, dx2, dw, dbias)
+    ops.head_bwd(x, cs, w.detach(), y, dy, pad, dx, _bits(msk), cs2, 0.2, dx2, dw, dbias, w_t=wt)
     ref.backward(dy)
     gx = xin.grad.permute(0, 2, 3, 1)
     _close(dx, gx, "head dx")
