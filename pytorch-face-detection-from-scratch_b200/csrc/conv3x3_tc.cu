@@ -124,6 +124,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  pdl_trigger();
+  pdl_wait();          // everything above overlapped the tail of the previous kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -383,7 +385,9 @@ extern "C" int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int 
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = p.num_tiles < nsm ? p.num_tiles : nsm;
-  conv3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_in, tm_w, tm_res, tm_out, p);
+  e = launch_k(conv3x3_tc_kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), tm_in, tm_w, tm_res,
+               tm_out, p);
+  if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   return launch_status();
 }

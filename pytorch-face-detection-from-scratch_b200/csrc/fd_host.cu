@@ -2,6 +2,7 @@
 // error strings.
 #include "fd_host.h"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace fd {
@@ -96,6 +97,11 @@ int make_tmap_3d(CUtensorMap* m, const void* ptr, int elem_bytes, int is_u8, int
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? FD_OK : FD_EINVAL;
+}
+
+bool pdl_enabled() {
+  static const bool on = std::getenv("FD_NO_PDL") == nullptr;
+  return on;
 }
 
 int sm_count() {

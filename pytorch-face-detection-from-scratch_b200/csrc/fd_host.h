@@ -19,6 +19,26 @@ inline int launch_status() {
   return e == cudaSuccess ? FD_OK : static_cast<int>(e);
 }
 
+// Launch with programmatic dependent launch (PDL): the kernel may start (prologue: barrier init, TMEM alloc,
+// shared-memory clears) while the tail of the previous kernel of the stream is still running; every kernel calls
+// griddepcontrol.wait before its first global-memory access.  Captured into CUDA graphs as programmatic edges.
+// FD_NO_PDL=1 falls back to ordinary stream order.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // [B,H,W,C] bf16 tensor as a 4-D tiled TMA map with box {C, boxW, boxH, 1}, 128B swizzle, zero OOB fill.
 int make_tmap_nhwc_bf16(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int boxW, int boxH);
 // a W-window [B,H,Wext,C] of a [B,H,Wfull,C] bf16 tensor (ptr = first pixel of the window): columns >= Wext are

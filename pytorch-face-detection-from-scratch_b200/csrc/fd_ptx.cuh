@@ -26,6 +26,13 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// pdl_trigger: the next kernel of the stream may be scheduled (its CTAs start as SMs free up);
+// pdl_wait   : returns once the previous kernel has completed and its memory is visible.  Both are no-ops for a
+// kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -17,6 +17,8 @@ template <int C>
 __global__ void __launch_bounds__(256)
 pack_conv3x3_kernel(const float* __restrict__ w, int n_layers, __nv_bfloat16* __restrict__ wf,
                     __nv_bfloat16* __restrict__ wd) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int row = C * 9, pitch = row + 1, tiles = C / kPackCo;
   __shared__ float sm[kPackCo * pitch];
   const int l = blockIdx.x / tiles, co0 = (blockIdx.x % tiles) * kPackCo;
@@ -42,6 +44,8 @@ pack_conv3x3_kernel(const float* __restrict__ w, int n_layers, __nv_bfloat16* __
 template <int C>
 __global__ void __launch_bounds__(256)
 unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, float* __restrict__ dw) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int row = C * 9, pitch = row + 1, tiles = C / kPackCo;
   __shared__ float sm[kPackCo * pitch];
   const int l = blockIdx.x / tiles, co0 = (blockIdx.x % tiles) * kPackCo;
@@ -59,6 +63,8 @@ unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, float* __res
 // (models/PoolResnet.py:39 Dropout2d(0.25) per block, :100 Dropout2d(0.5) before the head).
 __global__ void dropout_scale_kernel(const float* __restrict__ r, long n, long n_block, float keep_b, float keep_h,
                                      float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float keep = i < n_block ? keep_b : keep_h;
@@ -512,6 +518,8 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
 // weights [5][64][K][K] fp32 -> w_t [K*K*5][64] fp32 in the swizzled layout of head_w_index (done once per
 // step, so that every CTA stages its copy with plain coalesced float4 loads)
 __global__ void head_pack_kernel(const float* __restrict__ w, int KK, float* __restrict__ wt) {
+  pdl_trigger();
+  pdl_wait();
   const int n = KK * 5 * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int t = i % KK, c = (i / KK) % 64, o = i / (KK * 64);
@@ -534,6 +542,8 @@ __global__ void __launch_bounds__(512)
 head_fwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ wt,
                     const float* __restrict__ bias, int H, int W, int Ho, int Wo, int rows_per_cta,
                     float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int C = 64, KK = K * K, P = kHeadStrip;
   extern __shared__ float sm[];
   float* sW = sm;                                                       // [KK*5][64], pre-scaled by the dropout multiplier
@@ -623,6 +633,8 @@ head_bwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
                     int rows_per_cta, int dx_parts, __nv_bfloat16* __restrict__ dx,
                     const uint32_t* __restrict__ mask_bits, const float* __restrict__ cs2, float slope,
                     __nv_bfloat16* __restrict__ dx2, float* __restrict__ dw, float* __restrict__ dbias) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int C = 64, KK = K * K, P = kHeadStrip;
   extern __shared__ float sm[];
   const int n = blockIdx.x;
@@ -764,6 +776,8 @@ head_bwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 
 __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
                                       __nv_bfloat16* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
   const long total = static_cast<long>(B) * Ho * Wo * C8;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -792,6 +806,8 @@ __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const
                                       int H, int W, int C, __nv_bfloat16* __restrict__ gs,
                                       const uint32_t* __restrict__ mask_bits, const float* __restrict__ cs,
                                       float slope, __nv_bfloat16* __restrict__ gs2) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
   const long total = static_cast<long>(B) * Ho * Wo * C8;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -851,8 +867,8 @@ extern "C" int fd_pack_conv3x3(const float* w, int n_layers, int C, fd_bf16* w_f
   const long total = static_cast<long>(n_layers) * 9 * C * C;
   (void)total;
   if (C == 64)
-    pack_conv3x3_kernel<64><<<n_layers * (64 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        w, n_layers, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
+    launch_k(pack_conv3x3_kernel<64>, dim3(n_layers * (64 / kPackCo)), dim3(256), 0, static_cast<cudaStream_t>(stream), w,
+             n_layers, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
   else if (C == 128)
     pack_conv3x3_kernel<128><<<n_layers * (128 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         w, n_layers, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
@@ -867,7 +883,8 @@ extern "C" int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, f
   const long total = static_cast<long>(n_layers) * 9 * C * C;
   (void)total;
   if (C == 64)
-    unpack_wgrad3x3_kernel<64><<<n_layers * (64 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, dw);
+    launch_k(unpack_wgrad3x3_kernel<64>, dim3(n_layers * (64 / kPackCo)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             dw_packed, n_layers, dw);
   else if (C == 128)
     unpack_wgrad3x3_kernel<128><<<n_layers * (128 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, dw);
   else
@@ -879,8 +896,8 @@ extern "C" int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, f
 extern "C" int fd_dropout_scale(const float* r, long n, long n_block, float keep_block, float keep_head, float* out,
                                 void* stream) {
   if (!r || !out || n <= 0 || keep_block <= 0.f || keep_head <= 0.f) return FD_EINVAL;
-  dropout_scale_kernel<<<grid_for(n, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(r, n, n_block, keep_block,
-                                                                                          keep_head, out);
+  launch_k(dropout_scale_kernel, dim3(grid_for(n, 256, 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), r, n, n_block,
+           keep_block, keep_head, out);
   count_launch();
   return launch_status();
 }
@@ -955,7 +972,8 @@ extern "C" int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B
 extern "C" int fd_head_pack(const float* w, int C, int K, float* w_t, void* stream) {
   if (!w || !w_t || K <= 0) return FD_EINVAL;
   if (C != 64) return FD_EUNSUPPORTED;
-  head_pack_kernel<<<(K * K * 5 * 64 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, K * K, w_t);
+  launch_k(head_pack_kernel, dim3((K * K * 5 * 64 + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), w, K * K,
+           w_t);
   count_launch();
   return launch_status();
 }
@@ -976,8 +994,8 @@ extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const floa
       auto kern = (K == 6) ? head_fwd_c64_kernel<6, 0> : head_fwd_c64_kernel<3, 1>;
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
       if (e2 != cudaSuccess) return (int)e2;
-      kern<<<dim3(B, parts), rows_per_cta * strips * 32, sm2, static_cast<cudaStream_t>(stream)>>>(
-          reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w_t, bias, H, W, Ho, Wo, rows_per_cta, y);
+      launch_k(kern, dim3(B, parts), dim3(rows_per_cta * strips * 32), sm2, static_cast<cudaStream_t>(stream),
+               reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w_t, bias, H, W, Ho, Wo, rows_per_cta, y);
       count_launch();
       return launch_status();
     }
@@ -1017,10 +1035,10 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
       auto kern = (K == 6) ? head_bwd_c64_kernel<6, 0> : head_bwd_c64_kernel<3, 1>;
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
       if (e2 != cudaSuccess) return (int)e2;
-      kern<<<dim3(B, dx_parts + dw_parts), threads, sm2, static_cast<cudaStream_t>(stream)>>>(
-          reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w_t, y, dy, H, W, Ho, Wo, rows_per_cta, dx_parts,
-          reinterpret_cast<__nv_bfloat16*>(dx), mask_bits, chan_scale2, slope, reinterpret_cast<__nv_bfloat16*>(dx2),
-          dw, dbias);
+      launch_k(kern, dim3(B, dx_parts + dw_parts), dim3(threads), sm2, static_cast<cudaStream_t>(stream),
+               reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w_t, y, dy, H, W, Ho, Wo, rows_per_cta, dx_parts,
+               reinterpret_cast<__nv_bfloat16*>(dx), mask_bits, chan_scale2, slope, reinterpret_cast<__nv_bfloat16*>(dx2),
+               dw, dbias);
       count_launch();
       return launch_status();
     }
@@ -1042,8 +1060,8 @@ extern "C" int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, f
   if (!x || !y || B <= 0) return FD_EINVAL;
   if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
   const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2x2_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
+  launch_k(maxpool2x2_fwd_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+           reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
   count_launch();
   return launch_status();
 }
@@ -1056,10 +1074,9 @@ extern "C" int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int
   if (gs2 && C % 32 != 0) return FD_EUNSUPPORTED;
   if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
   const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2x2_bwd_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gy), B, H, W, C,
-      reinterpret_cast<__nv_bfloat16*>(gs), mask_bits, chan_scale, slope,
-      reinterpret_cast<__nv_bfloat16*>(gs2));
+  launch_k(maxpool2x2_bwd_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+           reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gy), B, H, W, C,
+           reinterpret_cast<__nv_bfloat16*>(gs), mask_bits, chan_scale, slope, reinterpret_cast<__nv_bfloat16*>(gs2));
   count_launch();
   return launch_status();
 }

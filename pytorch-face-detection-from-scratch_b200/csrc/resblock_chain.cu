@@ -124,6 +124,8 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
   tc_fence_after();
   if (kSplit) cluster_sync_all();     // the peer's barriers and zeroed buffers exist before anyone touches them
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -401,13 +403,15 @@ int launch_chain(ChainBuilder& cb, const fd_bf16* w, int w_layers, const fd_bf16
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     e = cudaLaunchKernelEx(&cfg, resblock_chain_kernel<true>, tm_w, tm_in0, tm_in1, p);
     if (e != cudaSuccess) return static_cast<int>(e);
   } else {
@@ -415,7 +419,8 @@ int launch_chain(ChainBuilder& cb, const fd_bf16* w, int w_layers, const fd_bf16
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     const int grid = B < nsm ? B : nsm;
-    resblock_chain_kernel<false><<<grid, kThreads, smem, st>>>(tm_w, tm_in0, tm_in1, p);
+    e = launch_k(resblock_chain_kernel<false>, dim3(grid), dim3(kThreads), smem, st, tm_w, tm_in0, tm_in1, p);
+    if (e != cudaSuccess) return static_cast<int>(e);
   }
   count_launch();
   return launch_status();

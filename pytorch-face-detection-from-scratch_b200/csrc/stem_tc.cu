@@ -241,6 +241,8 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp < kLoaderWarps) {
     int it = 0;
@@ -370,6 +372,8 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   // contiguous chunk of tasks per CTA
   const int per = (p.ntask + gridDim.x - 1) / gridDim.x;
@@ -515,11 +519,11 @@ int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, i
   if (x_is_u8) {
     e = cudaFuncSetAttribute(stem_fwd_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    stem_fwd_tc_kernel<uint8_t><<<grid, kThreads, smem, st>>>(tm_x, p);
+    e = launch_k(stem_fwd_tc_kernel<uint8_t>, dim3(grid), dim3(kThreads), smem, st, tm_x, p);
   } else {
     e = cudaFuncSetAttribute(stem_fwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    stem_fwd_tc_kernel<float><<<grid, kThreads, smem, st>>>(tm_x, p);
+    e = launch_k(stem_fwd_tc_kernel<float>, dim3(grid), dim3(kThreads), smem, st, tm_x, p);
   }
   count_launch();
   return launch_status();
@@ -548,11 +552,11 @@ int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, 
   if (x_is_u8) {
     e = cudaFuncSetAttribute(stem_wgrad_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    stem_wgrad_tc_kernel<uint8_t><<<grid, kThreads, smem, st>>>(tm_x, tm_g, p);
+    e = launch_k(stem_wgrad_tc_kernel<uint8_t>, dim3(grid), dim3(kThreads), smem, st, tm_x, tm_g, p);
   } else {
     e = cudaFuncSetAttribute(stem_wgrad_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    stem_wgrad_tc_kernel<float><<<grid, kThreads, smem, st>>>(tm_x, tm_g, p);
+    e = launch_k(stem_wgrad_tc_kernel<float>, dim3(grid), dim3(kThreads), smem, st, tm_x, tm_g, p);
   }
   count_launch();
   return launch_status();

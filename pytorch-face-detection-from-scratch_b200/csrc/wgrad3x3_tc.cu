@@ -100,6 +100,8 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0) FD_WTS(1);
 
   // contiguous chunk of tiles (of ONE problem) for this CTA
@@ -330,7 +332,8 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = nprob * p.ctas_per_prob;
-  wgrad3x3_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_x, gmaps, tm_dw, p);
+  e = launch_k(wgrad3x3_tc_kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), tm_x, gmaps, tm_dw, p);
+  if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   return launch_status();
 }

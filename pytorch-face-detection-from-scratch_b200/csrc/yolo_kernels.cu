@@ -29,6 +29,8 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
 __global__ void __launch_bounds__(kYoloThreads)
 yolo_loss_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int S1, int S2,
                  float* __restrict__ loss, const float* __restrict__ dscale, float* __restrict__ dpred) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __shared__ float scratch[kYoloThreads / 32];
   const int b = blockIdx.x;
   const int ncell = S1 * S2;
@@ -91,6 +93,8 @@ __global__ void __launch_bounds__(kYoloThreads)
 decode_nms_kernel(const float* __restrict__ pred, int S1, int S2, float p_thr, double iou_thr, float psx, float psy,
                   float width, float height, float* __restrict__ out_boxes, int* __restrict__ out_cell,
                   int* __restrict__ out_count) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   extern __shared__ uint8_t smraw[];
   const int ncell = S1 * S2;
   const int nw = (ncell + 31) / 32;
@@ -265,7 +269,8 @@ using namespace fd;
 extern "C" int fd_yolo_loss(const float* pred, const float* gt, int B, int S1, int S2, float* loss,
                             const float* dloss_scale, float* dpred, void* stream) {
   if (!pred || !gt || !loss || B <= 0 || S1 <= 0 || S2 <= 0) return FD_EINVAL;
-  yolo_loss_kernel<<<B, kYoloThreads, 0, static_cast<cudaStream_t>(stream)>>>(pred, gt, S1, S2, loss, dloss_scale, dpred);
+  launch_k(yolo_loss_kernel, dim3(B), dim3(kYoloThreads), 0, static_cast<cudaStream_t>(stream), pred, gt, S1, S2, loss,
+           dloss_scale, dpred);
   count_launch();
   return launch_status();
 }
@@ -283,9 +288,8 @@ extern "C" int fd_decode_nms(const float* pred, int B, int S1, int S2, float p_t
   // utils.py:108-109: python floats width/num_of_patches, rounded to f32 when they meet the f32 tensor
   const float psx = static_cast<float>(static_cast<double>(width) / num_of_patches);
   const float psy = static_cast<float>(static_cast<double>(height) / num_of_patches);
-  decode_nms_kernel<<<B, kYoloThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      pred, S1, S2, p_thr, iou_thr, psx, psy, static_cast<float>(width), static_cast<float>(height), out_boxes,
-      out_cell, out_count);
+  launch_k(decode_nms_kernel, dim3(B), dim3(kYoloThreads), smem, static_cast<cudaStream_t>(stream), pred, S1, S2, p_thr,
+           iou_thr, psx, psy, static_cast<float>(width), static_cast<float>(height), out_boxes, out_cell, out_count);
   count_launch();
   return launch_status();
 }
