@@ -149,12 +149,17 @@ FD_API int fd_dropout_scale(const float* r, long n, long n_block, float keep_blo
 /* ---------------------------------------------------------------------------------------------
  * Stem convolution (models/PoolResnet.py:70-76,98): KxK stride s pad p, Cin(3) -> C, input fp32 NCHW
  * (or uint8 NCHW with the /255 of PoolResnet.py:95 fused: x_is_u8 = 1), output NHWC bf16, bias added.
- * w: [C][Cin][K][K] fp32. */
+ * w: [C][Cin][K][K] fp32.
+ * x_cache (nullable): a ZERO-INITIALISED buffer of fd_stem_cache_elems(...) bf16 elements.  The forward fills it
+ * with the bf16-converted images in the operand layout of its tensor-core tile; passing the same buffer to
+ * fd_stem_wgrad makes the weight gradient read 2 B/pixel through TMA instead of re-reading and re-converting the
+ * fp32 images.  fd_stem_cache_elems returns 0 for shapes that do not use the cache (generic stem kernel). */
+FD_API long fd_stem_cache_elems(int B, int Cin, int Hin, int Win, int C, int K, int stride, int pad);
 FD_API int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const float* bias, int B, int Cin, int Hin, int Win,
-                int C, int K, int stride, int pad, fd_bf16* y, void* stream);
+                int C, int K, int stride, int pad, fd_bf16* y, fd_bf16* x_cache, void* stream);
 /* dw[C][Cin][K][K] += x (*) g ; dbias[C] += sum g.  g: [B,Ho,Wo,C] bf16. */
 FD_API int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C, int K,
-                  int stride, int pad, float* dw, float* dbias, void* stream);
+                  int stride, int pad, float* dw, float* dbias, const fd_bf16* x_cache, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Head (models/PoolResnet.py:83-89,100-102): Dropout2d multiplier, KxK stride-1 conv C -> 5 with

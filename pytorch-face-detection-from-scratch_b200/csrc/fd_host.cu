@@ -84,6 +84,20 @@ int make_tmap_2d_f32(CUtensorMap* m, const void* ptr, long rows, int cols, int b
   return r == CUDA_SUCCESS ? FD_OK : FD_EINVAL;
 }
 
+int make_tmap_xbf(CUtensorMap* m, const void* ptr, int planes, int Hin, int K) {
+  // [planes][Hin][img 2][512] bf16 viewed as 5-D {256, 2, 2, Hin, planes}; box {256, 2, 2, K, 1}, no swizzle, zero OOB fill
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return FD_EDRIVER;
+  cuuint64_t dims[5] = {256, 2, 2, (cuuint64_t)Hin, (cuuint64_t)planes};
+  cuuint64_t strides[4] = {512, 1024, 2048, (cuuint64_t)Hin * 2048};
+  cuuint32_t box[5] = {256, 2, 2, (cuuint32_t)K, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FD_OK : FD_EINVAL;
+}
+
 int make_tmap_3d(CUtensorMap* m, const void* ptr, int elem_bytes, int is_u8, int d0, int d1, int d2, int box0,
                  int box1) {
   PFN_encodeTiled enc = get_encode_tiled();

@@ -54,12 +54,17 @@ int make_tmap_2d_f32(CUtensorMap* m, const void* ptr, long rows, int cols, int b
 // [d2, d1, d0] tensor of 1- or 4-byte elements (uint8 / fp32) as a 3-D tiled map, box {box0, box1, 1}, no swizzle
 int make_tmap_3d(CUtensorMap* m, const void* ptr, int elem_bytes, int is_u8, int d0, int d1, int d2, int box0, int box1);
 
+// the stem's bf16 image copy [planes][Hin][2][512] as a 5-D map, box = K rows of one plane (both image slots)
+int make_tmap_xbf(CUtensorMap* m, const void* ptr, int planes, int Hin, int K);
+
+long stem_cache_elems(int B, int Cin, int Hin, int Win, int C, int K, int stride, int pad);
+
 int sm_count();
 
 // tcgen05 stem (stem_tc.cu); FD_EUNSUPPORTED means "not the stride-8 stem shape, use the generic kernel"
 int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, int B, int Cin, int Hin, int Win,
-                int C, int K, int stride, int pad, fd_bf16* y, cudaStream_t st);
+                int C, int K, int stride, int pad, fd_bf16* y, fd_bf16* xbf, cudaStream_t st);
 int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C, int K,
-                  int stride, int pad, float* dw, float* dbias, cudaStream_t st);
+                  int stride, int pad, float* dw, float* dbias, const fd_bf16* xbf, cudaStream_t st);
 
 }  // namespace fd

@@ -902,12 +902,16 @@ extern "C" int fd_dropout_scale(const float* r, long n, long n_block, float keep
   return launch_status();
 }
 
+extern "C" long fd_stem_cache_elems(int B, int Cin, int Hin, int Win, int C, int K, int stride, int pad) {
+  return stem_cache_elems(B, Cin, Hin, Win, C, K, stride, pad);
+}
+
 extern "C" int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const float* bias, int B, int Cin, int Hin,
-                           int Win, int C, int K, int stride, int pad, fd_bf16* y, void* stream) {
+                           int Win, int C, int K, int stride, int pad, fd_bf16* y, fd_bf16* x_cache, void* stream) {
   if (!x || !w || !bias || !y || B <= 0) return FD_EINVAL;
   if (C % 64 != 0) return FD_EUNSUPPORTED;
   {
-    const int rc = stem_fwd_tc(x, x_is_u8, w, bias, B, Cin, Hin, Win, C, K, stride, pad, y,
+    const int rc = stem_fwd_tc(x, x_is_u8, w, bias, B, Cin, Hin, Win, C, K, stride, pad, y, x_cache,
                                static_cast<cudaStream_t>(stream));
     if (rc != FD_EUNSUPPORTED) return rc;      // tensor-core stem handled it (or failed for real)
   }
@@ -936,10 +940,10 @@ extern "C" int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const flo
 }
 
 extern "C" int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C,
-                             int K, int stride, int pad, float* dw, float* dbias, void* stream) {
+                             int K, int stride, int pad, float* dw, float* dbias, const fd_bf16* x_cache, void* stream) {
   if (!x || !g || !dw || B <= 0) return FD_EINVAL;
   {
-    const int rc = stem_wgrad_tc(x, x_is_u8, g, B, Cin, Hin, Win, C, K, stride, pad, dw, dbias,
+    const int rc = stem_wgrad_tc(x, x_is_u8, g, B, Cin, Hin, Win, C, K, stride, pad, dw, dbias, x_cache,
                                  static_cast<cudaStream_t>(stream));
     if (rc != FD_EUNSUPPORTED) return rc;
   }

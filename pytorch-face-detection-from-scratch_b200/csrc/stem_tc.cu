@@ -51,6 +51,10 @@ struct StemParams {
   __nv_bfloat16* y;      // [B,Ho,Wo,64]
   float* dw;             // [64][Cin][K][K] fp32, accumulated (wgrad)
   float* dbias;          // [64] accumulated (wgrad)
+  // bf16 copy of the images in the operand layout of the A tile: [pair][c][y][img][512] (element e = column e - pad,
+  // pad columns zero).  Written by the forward converter warps, TMA-loaded by the weight-gradient kernel, so the
+  // fp32 images are read from HBM once per step and converted once.
+  __nv_bfloat16* xbf;
 };
 
 // no-swizzle descriptor (layout type 0)
@@ -145,7 +149,8 @@ __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtens
 // Converter warp `warp`: its chunks of task iteration `it` -> A tile `abuf`.
 template <typename TIn, int NS>
 __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abuf, const uint8_t* sStage,
-                                               uint64_t* stg_full, uint64_t* stg_empty, int it, int warp, int lane) {
+                                               uint64_t* stg_full, uint64_t* stg_empty, int it, int warp, int lane,
+                                               int task = 0) {
 #pragma unroll 1
   for (int jj = 0; jj < kChunksPerTask / 8; ++jj) {
     const int j = jj * 8 + warp;
@@ -163,14 +168,36 @@ __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abu
       if (lane + 32 < kQPR) Px4<TIn>::load(slot, r * kQPR + lane + 32, v[r][1]);
     }
     uint8_t* dst0 = abuf + ((k.c * p.K + k.rg * kKH) * 2 + k.img) * kRowBytes + (k.half * (p.Win / 2) + p.pad) * 2;
+    // global bf16 copy (forward only): row y of plane (pair, c), image slot img
+    const int pair = task / p.Ho, oy = task - pair * p.Ho;
+    const int y0 = oy * p.stride - p.pad + k.rg * kKH;
+    uint8_t* gdst0 = p.xbf == nullptr ? nullptr
+                                      : reinterpret_cast<uint8_t*>(p.xbf) +
+                                            ((static_cast<size_t>(pair) * p.Cin + k.c) * p.Hin * 2 + k.img) * kRowBytes +
+                                            (k.half * (p.Win / 2) + p.pad) * 2 + lane * 8;
 #pragma unroll
     for (int r = 0; r < kKH; ++r) {
       uint32_t* d = reinterpret_cast<uint32_t*>(dst0 + r * 2 * kRowBytes + lane * 8);
-      d[0] = pack_bf16x2(v[r][0][0], v[r][0][1]);
-      d[1] = pack_bf16x2(v[r][0][2], v[r][0][3]);
+      const uint32_t a0 = pack_bf16x2(v[r][0][0], v[r][0][1]), a1 = pack_bf16x2(v[r][0][2], v[r][0][3]);
+      d[0] = a0;
+      d[1] = a1;
+      uint32_t b0 = 0, b1 = 0;
       if (lane + 32 < kQPR) {
-        d[64] = pack_bf16x2(v[r][1][0], v[r][1][1]);
-        d[65] = pack_bf16x2(v[r][1][2], v[r][1][3]);
+        b0 = pack_bf16x2(v[r][1][0], v[r][1][1]);
+        b1 = pack_bf16x2(v[r][1][2], v[r][1][3]);
+        d[64] = b0;
+        d[65] = b1;
+      }
+      const int y = y0 + r;
+      if (gdst0 != nullptr && y >= 0 && y < p.Hin) {
+        uint8_t* grow = gdst0 + static_cast<size_t>(y) * 2 * kRowBytes;
+        uint32_t* gw = reinterpret_cast<uint32_t*>(grow);      // rows start 2 pad elements in: 4-byte aligned only
+        gw[0] = a0;
+        gw[1] = a1;
+        if (lane + 32 < kQPR) {
+          gw[64] = b0;
+          gw[65] = b1;
+        }
       }
     }
     __syncwarp();
@@ -249,7 +276,7 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
     for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
       // single A stage: the deep staging ring keeps HBM busy while the 30 MMAs of the previous task drain
       mbar_wait(a_empty, (it & 1) ^ 1);
-      convert_chunks<TIn, kFwdSlots>(p, sA, sStage, stg_full, stg_empty, it, warp, lane);
+      convert_chunks<TIn, kFwdSlots>(p, sA, sStage, stg_full, stg_empty, it, warp, lane, task);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
@@ -472,6 +499,162 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------- weight gradient from the bf16 copy
+// Same MMAs as stem_wgrad_tc_kernel, but the A-tile rows arrive as three TMA boxes per task ({512 e, 2 img, K rows} of
+// plane (pair, c)) straight from the bf16 image copy the forward wrote: no fp32 re-read, no converter warps, no
+// staging ring.  Warps: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = bias sums + drain.
+constexpr int kWg2Threads = 6 * 32;
+__global__ void __launch_bounds__(kWg2Threads, 1)
+stem_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tm_xb, const __grid_constant__ CUtensorMap tm_g,
+                       const StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr uint32_t kGBytes = 128 * 128;
+  uint8_t* sA = smem;                                   // 2 stages x a_bytes
+  uint8_t* sG = sA + 2 * p.a_bytes + 1024;              // 2 stages x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * kGBytes);
+  uint64_t* full = bars + 0;     // [2]
+  uint64_t* empty = bars + 2;    // [2] count = 1 (MMA commit) + 4 (bias warps)
+  uint64_t* acc_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* sBias = reinterpret_cast<float*>(bars + 6);    // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // g rows Wo..63 of each 64-row slot and the slack behind the A stages are never written by TMA: keep them zero
+  for (uint32_t i = threadIdx.x * 16u; i < 2 * p.a_bytes + 1024 + 2 * kGBytes; i += kWg2Threads * 16u)
+    *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_xb);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1 + 4);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  const int per = (p.ntask + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per;
+  const int t_end = min(p.ntask, t_begin + per);
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int it = 0;
+      for (int task = t_begin; task < t_end; ++task, ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        const int pair = task / p.Ho, oy = task - pair * p.Ho;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, p.a_bytes + 2u * p.Wo * 128u);
+        for (int c = 0; c < p.Cin; ++c)       // {256 e, 2 halves, 2 img, K rows, 1 plane}; rows above the image: zero fill
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+              "[%2];" ::"r"(smem_u32(sA + s * p.a_bytes + c * p.K * 2 * kRowBytes)),
+              "l"(reinterpret_cast<uint64_t>(&tm_xb)), "r"(smem_u32(full + s)), "r"(0), "r"(0), "r"(0),
+              "r"(oy * p.stride - p.pad), "r"(pair * p.Cin + c)
+              : "memory");
+        tma_load_4d(sG + s * kGBytes, &tm_g, full + s, 0, 0, oy, pair * 2);
+        tma_load_4d(sG + s * kGBytes + 64 * 128, &tm_g, full + s, 0, 0, oy, pair * 2 + 1);
+      }
+    }
+  } else if (warp == 1) {
+    // D[(c,ky,kx), co] = sum_pos win[pos][(c,ky,kx)] * g[pos][co] with M = 128 = 16 (c,ky) rows x 8 kx:
+    //   A (MN-major, no swizzle): the raw bf16 rows again -- 8-element MN groups are the rows (c,ky) of ONE image
+    //     slot, 2048 B apart (SBO); the K index (position = img*64 + ox) advances 16 B, 8-position groups 128 B (LBO);
+    //     kx 8..15 is the same operand started 16 B further;
+    //   B (MN-major, 128B swizzle): the gradient tile [position][co], N = 64.
+    // 2 row blocks x 2 kx chunks = 4 MMAs (128x64x16) per 16 positions instead of 30 MMAs (64x16x16).
+    constexpr uint32_t idesc = make_idesc_bf16(128, kCo, 1, 1);
+    if (elect_one_sync()) {
+      int it = 0;
+      for (int task = t_begin; task < t_end; ++task, ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint64_t bd0 = make_sdesc_sw128(smem_u32(sG + s * kGBytes), 1024, 1024, 0);
+        const uint32_t a_addr = smem_u32(sA + s * p.a_bytes);
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t bd = bd0 + static_cast<uint64_t>(ks * 128);          // +2048 B: 16 positions
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int blk = a >> 1, chunk = a & 1;
+            const uint64_t ad = make_sdesc_none(a_addr + blk * 16 * 2 * kRowBytes + chunk * 16 + ks * 256, 128,
+                                                2 * kRowBytes);
+            umma_bf16(tmem_base + a * kCo, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty + s);
+        if (task + 1 == t_end) umma_commit(acc_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int et = threadIdx.x - 64;   // 0..127
+    const int c = et & 63, rpar = et >> 6;
+    float bsum = 0.f;
+    int it = 0;
+    for (int task = t_begin; task < t_end; ++task, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(full + s, ph);
+      if (p.dbias) {
+        const uint8_t* g = sG + s * kGBytes;
+        for (int r = rpar; r < 128; r += 2) {
+          const uint32_t off = r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1));
+          bsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(g + off));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+    if (t_begin < t_end) {
+      const int q = warp & 3;
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      // accumulator a = (row block, kx chunk); TMEM lane r = 8 * (row within block) + (kx within chunk)
+      const int r = q * 32 + lane;
+      const int KK = p.CK * p.K;
+#pragma unroll 1
+      for (int a = 0; a < 4; ++a) {
+        const int cky = (a >> 1) * 16 + (r >> 3), kx = (a & 1) * 8 + (r & 7);
+        const bool valid = cky < p.CK && kx < p.K;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * kCo + half * 32, acc);
+          tmem_ld_wait();
+          if (valid) {
+            float* dst = p.dw + static_cast<size_t>(half * 32) * KK + cky * p.K + kx;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + static_cast<size_t>(j) * KK, __uint_as_float(acc[j]));
+          }
+        }
+      }
+      if (p.dbias) {
+        sBias[et] = bsum;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et < 64) atomicAdd(p.dbias + et, sBias[et] + sBias[et + 64]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 bool tc_shape_ok(int Cin, int Win, int C, int K, int stride, int pad, int Wo) {
   static const bool force_generic = std::getenv("FD_STEM_GENERIC") != nullptr;   // A/B testing only
   if (force_generic) return false;
@@ -499,13 +682,21 @@ int make_tmap_image(CUtensorMap* m, const void* x, int is_u8, int planes, int Hi
 
 }  // namespace
 
+// Elements of the bf16 image cache ([pairs][Cin][Hin][2][512]) for a shape the tensor-core stem handles, else 0.
+long stem_cache_elems(int B, int Cin, int Hin, int Win, int C, int K, int stride, int pad) {
+  const int Wo = (Win + 2 * pad - K) / stride + 1;
+  if (!tc_shape_ok(Cin, Win, C, K, stride, pad, Wo)) return 0;
+  return static_cast<long>((B + 1) / 2) * Cin * Hin * 2 * 512;
+}
+
 // Called from layers.cu's fd_stem_fwd / fd_stem_wgrad; returns FD_EUNSUPPORTED when the shape is
 // not the stride-8 stem this kernel is built for (the caller then uses the generic kernel).
 int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, int B, int Cin, int Hin, int Win,
-                int C, int K, int stride, int pad, fd_bf16* y, cudaStream_t st) {
+                int C, int K, int stride, int pad, fd_bf16* y, fd_bf16* xbf, cudaStream_t st) {
   StemParams p = make_params(x, B, Cin, Hin, Win, K, stride, pad);
   if (!tc_shape_ok(Cin, Win, C, K, stride, pad, p.Wo)) return FD_EUNSUPPORTED;
   p.w = w; p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.xbf = reinterpret_cast<__nv_bfloat16*>(xbf);
   p.elem_bytes = x_is_u8 ? 1 : 4;
   CUtensorMap tm_x;
   {
@@ -530,10 +721,27 @@ int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, i
 }
 
 int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C, int K,
-                  int stride, int pad, float* dw, float* dbias, cudaStream_t st) {
+                  int stride, int pad, float* dw, float* dbias, const fd_bf16* xbf, cudaStream_t st) {
   StemParams p = make_params(x, B, Cin, Hin, Win, K, stride, pad);
   if (!tc_shape_ok(Cin, Win, C, K, stride, pad, p.Wo)) return FD_EUNSUPPORTED;
   p.dw = dw; p.dbias = dbias;
+  if (xbf != nullptr) {
+    // fast path: operand rows come from the bf16 copy written by the forward pass
+    CUtensorMap tm_g, tm_xb;
+    int rc = make_tmap_nhwc_bf16(&tm_g, g, B, p.Ho, p.Wo, C, p.Wo, 1);
+    if (rc != FD_OK) return rc;
+    rc = make_tmap_xbf(&tm_xb, xbf, p.npairs * Cin, Hin, K);
+    if (rc != FD_OK) return rc;
+    const size_t smem2 = 2 * static_cast<size_t>(p.a_bytes) + 1024 + 2 * 128 * 128 + 1024 + 1024;
+    if (smem2 > 227 * 1024) return FD_EUNSUPPORTED;
+    cudaError_t e2 = cudaFuncSetAttribute(stem_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e2 != cudaSuccess) return (int)e2;
+    const int grid2 = min(p.ntask, sm_count());
+    e2 = launch_k(stem_wgrad_bf16_kernel, dim3(grid2), dim3(kWg2Threads), smem2, st, tm_xb, tm_g, p);
+    if (e2 != cudaSuccess) return (int)e2;
+    count_launch();
+    return launch_status();
+  }
   p.elem_bytes = x_is_u8 ? 1 : 4;
   CUtensorMap tm_g, tm_x;
   {

@@ -109,6 +109,9 @@ class _Plan:
             self.blocks.append(blk)
         self.y = torch.empty((B, 5, eng.So_h, eng.So_w), dtype=F32, device=device)
         if train:
+            # bf16 copy of the images in the stem's operand layout (written by the forward, read by the stem wgrad)
+            n_cache = ops.stem_cache_elems(B, eng.in_ch, eng.in_h, eng.in_w, F, eng.stem_k, eng.stem_s, eng.stem_pad)
+            self.x_cache = torch.zeros(n_cache, dtype=BF16, device=device) if n_cache else None
             self.g_stem = bf(eng.H0, eng.W0)
             self.loss = torch.empty((B,), dtype=F32, device=device)
             self.dy = torch.empty_like(self.y)
@@ -261,7 +264,7 @@ class BackboneEngine:
         pl.x = x
         sb3 = self.section(self.pflat, "b3")
         ops.stem_fwd(x, self.section(self.pflat, "conv1.weight"), self.section(self.pflat, "conv1.bias"), pl.act0,
-                     self.stem_s, self.stem_pad)
+                     self.stem_s, self.stem_pad, x_cache=getattr(pl, "x_cache", None))
         cur = pl.act0
         chain_end = -1
         for k, blk in enumerate(pl.blocks):
@@ -357,7 +360,8 @@ class BackboneEngine:
                                         gb3_flat[(2 * k0) * self.F:], 2 * self.F)
                 if k0 == 0:
                     ops.stem_wgrad(pl.x, pl.g_stem, self.section(self.gflat, "conv1.weight"),
-                                   self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad)
+                                   self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad,
+                                   x_cache=getattr(pl, "x_cache", None))
                 continue
             if k >= skip_until:
                 continue
@@ -384,7 +388,8 @@ class BackboneEngine:
             else:
                 ops.conv3x3(blk.gp1, self._wd(0), slope=self.slope, residual=GS, out=pl.g_stem)
                 ops.stem_wgrad(pl.x, pl.g_stem, self.section(self.gflat, "conv1.weight"),
-                               self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad)
+                               self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad,
+                               x_cache=getattr(pl, "x_cache", None))
             if k in in_group and in_group[k][0] == k:
                 # the dgrad chain of this run is complete: all its weight gradients in two launches
                 k0, k1, IN_all, A_all, GP1_all, GP2_all = in_group[k]

@@ -30,8 +30,9 @@ SIGNATURES = {
     "fd_pack_conv3x3": [_P, _I, _I, _P, _P, _P],
     "fd_unpack_wgrad3x3": [_P, _I, _I, _P, _P],
     "fd_dropout_scale": [_P, _c.c_long, _c.c_long, _F, _F, _P, _P],
-    "fd_stem_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
-    "fd_stem_wgrad": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "fd_stem_cache_elems": [_I, _I, _I, _I, _I, _I, _I, _I],
+    "fd_stem_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "fd_stem_wgrad": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "fd_head_pack": [_P, _I, _I, _P, _P],
     "fd_head_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "fd_head_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
@@ -80,6 +81,7 @@ def lib():
             fn.argtypes = args
             fn.restype = _I
         L.fd_launch_count.restype = _c.c_longlong
+        L.fd_stem_cache_elems.restype = _c.c_long
         L.fd_error_string.restype = _c.c_char_p
         _lib = L
     return _lib

@@ -84,20 +84,24 @@ def dropout_scale(r, n_block, keep_block, keep_head, out):
                                  dptr(out, F32), cur_stream()), "fd_dropout_scale")
 
 
-def stem_fwd(x, w, bias, y, stride, pad):
+def stem_cache_elems(B, Cin, Hin, Win, C, K, stride, pad):
+    return int(lib().fd_stem_cache_elems(B, Cin, Hin, Win, C, K, stride, pad))
+
+
+def stem_fwd(x, w, bias, y, stride, pad, x_cache=None):
     B, Cin, Hin, Win = x.shape
     C, _, K, _ = w.shape
     is_u8 = 1 if x.dtype == U8 else 0
     check(lib().fd_stem_fwd(dptr(x, U8 if is_u8 else F32), is_u8, dptr(w, F32), dptr(bias, F32), B, Cin, Hin, Win, C, K,
-                            stride, pad, dptr(y, BF16), cur_stream()), "fd_stem_fwd")
+                            stride, pad, dptr(y, BF16), dptr(x_cache, BF16), cur_stream()), "fd_stem_fwd")
 
 
-def stem_wgrad(x, g, dw, dbias, stride, pad):
+def stem_wgrad(x, g, dw, dbias, stride, pad, x_cache=None):
     B, Cin, Hin, Win = x.shape
     C, _, K, _ = dw.shape
     is_u8 = 1 if x.dtype == U8 else 0
     check(lib().fd_stem_wgrad(dptr(x, U8 if is_u8 else F32), is_u8, dptr(g, BF16), B, Cin, Hin, Win, C, K, stride, pad,
-                              dptr(dw, F32), dptr(dbias, F32), cur_stream()), "fd_stem_wgrad")
+                              dptr(dw, F32), dptr(dbias, F32), dptr(x_cache, BF16), cur_stream()), "fd_stem_wgrad")
 
 
 def head_pack(w, w_t):

@@ -126,6 +126,20 @@ def test_stem_fwd_wgrad(u8):
     (dref,) = torch.autograd.grad(F.conv2d(xf.bfloat16().float(), wz, None, stride=8, padding=2), wz,
                                   g.float().permute(0, 3, 1, 2))
     assert rel_err(dw, dref) <= 1e-4
+    # bf16 image cache: the forward fills it, the weight gradient reads it instead of the fp32 / uint8 images
+    n_cache = ops.stem_cache_elems(B, 3, 480, 480, C, 10, 8, 2)
+    assert n_cache == 2 * 3 * 480 * 2 * 512          # B = 3 -> two image pairs, the odd slot stays zero
+    cache = torch.zeros(n_cache, dtype=torch.bfloat16, device=dev)
+    y2 = torch.zeros_like(y)
+    ops.stem_fwd(x, w.detach(), b.detach(), y2, 8, 2, x_cache=cache)
+    assert torch.equal(y2, y)
+    want = torch.zeros(2, 3, 480, 2, 512, device=dev)
+    xp = torch.cat([xf, torch.zeros(1, 3, 480, 480, device=dev)]).reshape(2, 2, 3, 480, 480)
+    want[:, :, :, :, 2:482] = xp.permute(0, 2, 3, 1, 4)
+    assert torch.equal(cache.view(2, 3, 480, 2, 512).float(), want.bfloat16().float())
+    dw2 = torch.zeros_like(dw); dbias2 = torch.zeros_like(dbias)
+    ops.stem_wgrad(x, g, dw2, dbias2, 8, 2, x_cache=cache)
+    assert rel_err(dw2, dw) <= 1e-5 and rel_err(dbias2, dbias) <= 1e-5     # same MMAs, fp32 atomics reorder sums
 
 
 def test_conv3x3_wgrad_multi_problem():
