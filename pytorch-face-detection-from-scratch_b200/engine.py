@@ -33,21 +33,25 @@ class _Plan:
         def bf(h, w):
             return torch.empty((B, h, w, F), dtype=BF16, device=device)
 
-        # Runs of consecutive non-pooled blocks share one shape; their tensors are allocated STACKED
-        # ([n,B,H,W,F]) so that the weight gradients of the whole run go out as one multi-problem launch.
-        self.groups = []            # (k0, k1, IN_all, A_all, GP1_all, GP2_all)
+        # Blocks are grouped into maximal runs of equal (pre-pool) shape -- a pooled block is a run of its own.  Per
+        # run the operands of the weight gradients are allocated STACKED and INTERLEAVED:
+        #   XA[2i] = input of block k0+i, XA[2i+1] = its conv1 activation a;  GP[2i] = gp1, GP[2i+1] = gp2
+        # so that problem j of ONE multi-problem wgrad launch is layer 2*k0 + j (uniform strides in dw / dbias).
+        self.groups = []            # (k0, k1, XA_all, GP_all)
         self.chains = {}            # k0 -> chain record for runs executed by the fused chain kernels
+        H, W = eng.H0, eng.W0
+        shapes = []
+        for k in range(eng.num_blocks):
+            shapes.append((H, W))
+            if eng.pools[k]:
+                H, W = H // 2, W // 2
         runs, k = [], 0
         while k < eng.num_blocks:
-            if not eng.pools[k]:
-                k1 = k
-                while k1 + 1 < eng.num_blocks and not eng.pools[k1 + 1]:
-                    k1 += 1
-                if k1 > k:
-                    runs.append((k, k1))
-                k = k1 + 1
-            else:
-                k += 1
+            k1 = k
+            while (not eng.pools[k1]) and k1 + 1 < eng.num_blocks and shapes[k1 + 1] == shapes[k]:
+                k1 += 1
+            runs.append((k, k1))
+            k = k1 + 1
         run_of = {}
         for (k0, k1) in runs:
             for k in range(k0, k1 + 1):
@@ -56,22 +60,14 @@ class _Plan:
         def stack(n, h, w):
             return torch.empty((n, B, h, w, F), dtype=BF16, device=device)
 
-        H, W = eng.H0, eng.W0
-        shapes = []
-        for k in range(eng.num_blocks):
-            shapes.append((H, W))
-            if eng.pools[k]:
-                H, W = H // 2, W // 2
         stacks = {}
         for (k0, k1) in runs:
             n = k1 - k0 + 1
             h, w = shapes[k0]
-            stacks[k0] = {"IN": stack(n, h, w), "A": stack(n, h, w),
-                          "GP1": stack(n, h, w) if train else None, "GP2": stack(n, h, w) if train else None}
-            self.groups.append((k0, k1, stacks[k0]["IN"], stacks[k0]["A"], stacks[k0]["GP1"], stacks[k0]["GP2"]))
-            if eng.use_chain and ops.resblock_chain_ok(h, w, F):
-                # the whole run executes as ONE persistent kernel per direction (csrc/resblock_chain.cu);
-                # LeakyReLU' travels as sign bits instead of bf16 tensors
+            stacks[k0] = {"XA": stack(2 * n, h, w), "GP": stack(2 * n, h, w) if train else None}
+            self.groups.append((k0, k1, stacks[k0]["XA"], stacks[k0]["GP"]))
+            if n > 1 and eng.use_chain and ops.resblock_chain_ok(h, w, F):
+                # the whole run executes as ONE persistent kernel per direction (csrc/resblock_chain.cu)
                 self.chains[k0] = {"k0": k0, "k1": k1}
 
         def out_buffer(k, h, w):
@@ -79,7 +75,7 @@ class _Plan:
             nxt = k + 1
             if nxt in run_of:
                 k0, _ = run_of[nxt]
-                return stacks[k0]["IN"][nxt - k0]
+                return stacks[k0]["XA"][2 * (nxt - k0)]
             return bf(h, w)
 
         H, W = eng.H0, eng.W0
@@ -88,9 +84,9 @@ class _Plan:
         for k in range(eng.num_blocks):
             blk = _Block()
             blk.H, blk.W, blk.pool = H, W, eng.pools[k]
-            st = stacks[run_of[k][0]] if k in run_of else None
-            i = k - run_of[k][0] if k in run_of else 0
-            blk.a = st["A"][i] if st else bf(H, W)
+            st = stacks[run_of[k][0]]
+            i = k - run_of[k][0]
+            blk.a = st["XA"][2 * i + 1]
             # LeakyReLU' masks of a (conv1 activation) and b (conv2 activation after Dropout2d) as sign bits
             blk.ma = torch.empty((B, H, W, F // 32), dtype=torch.int32, device=device) if train else None
             blk.mb = torch.empty((B, H, W, F // 32), dtype=torch.int32, device=device) if train else None
@@ -104,8 +100,8 @@ class _Plan:
             if train:
                 blk.G = bf(H, W)
                 blk.gs = bf(blk.H, blk.W) if blk.pool else None
-                blk.gp1 = st["GP1"][i] if st else bf(blk.H, blk.W)
-                blk.gp2 = st["GP2"][i] if st else bf(blk.H, blk.W)
+                blk.gp1 = st["GP"][2 * i]
+                blk.gp2 = st["GP"][2 * i + 1]
             self.blocks.append(blk)
         self.y = torch.empty((B, 5, eng.So_h, eng.So_w), dtype=F32, device=device)
         if train:
@@ -337,27 +333,24 @@ class BackboneEngine:
                      None if (last.pool or drop is None) else drop[nb - 1], self.slope,
                      None if last.pool else last.gp2, self.section(self.gflat, "out.weight"),
                      self.section(self.gflat, "out.bias"), w_t=self.w_head_t)
-        in_group = {}
-        for grp in pl.groups:
-            for k in range(grp[0], grp[1] + 1):
-                in_group[k] = grp
+        group_of_first = {grp[0]: grp for grp in pl.groups}
         gb3_flat = gb3.reshape(-1)
+
+        def group_wgrad(k0):
+            """All weight gradients of the run starting at block k0 (2 per block) in ONE multi-problem launch."""
+            _, _, XA_all, GP_all = group_of_first[k0]
+            ops.conv3x3_wgrad_multi(XA_all, GP_all, self.dwp[(2 * k0) * n3:], n3, gb3_flat[(2 * k0) * self.F:], self.F)
+
         chain_of_last = {ch["k1"]: ch for ch in pl.chains.values()}
         skip_until = nb
         for k in range(nb - 1, -1, -1):
             blk = pl.blocks[k]
-            x_in = pl.act0 if k == 0 else pl.blocks[k - 1].out
             if k in chain_of_last and not blk.pool:
                 ch = chain_of_last[k]
                 k0 = ch["k0"]
                 self._chain_backward(pl, ch, pl.blocks[k0 - 1].G if k0 > 0 else pl.g_stem)
                 skip_until = k0
-                grp = in_group[k0]
-                _, _, IN_all, A_all, GP1_all, GP2_all = grp
-                ops.conv3x3_wgrad_multi(A_all, GP2_all, self.dwp[(2 * k0 + 1) * n3:], 2 * n3,
-                                        gb3_flat[(2 * k0 + 1) * self.F:], 2 * self.F)
-                ops.conv3x3_wgrad_multi(IN_all, GP1_all, self.dwp[(2 * k0) * n3:], 2 * n3,
-                                        gb3_flat[(2 * k0) * self.F:], 2 * self.F)
+                group_wgrad(k0)
                 if k0 == 0:
                     ops.stem_wgrad(pl.x, pl.g_stem, self.section(self.gflat, "conv1.weight"),
                                    self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad,
@@ -371,12 +364,7 @@ class BackboneEngine:
                 GS = blk.gs
             else:
                 GS = blk.G
-            grouped = k in in_group
-            if not grouped:
-                ops.conv3x3_wgrad(blk.a, blk.gp2, self.dwp[(2 * k + 1) * n3:(2 * k + 2) * n3], gb3[2 * k + 1])
             ops.conv3x3(blk.gp2, self._wd(2 * k + 1), slope=self.slope, mask_in=blk.ma, out2=blk.gp1)
-            if not grouped:
-                ops.conv3x3_wgrad(x_in, blk.gp1, self.dwp[(2 * k) * n3:(2 * k + 1) * n3], gb3[2 * k])
             if k > 0:
                 prev = pl.blocks[k - 1]
                 if prev.pool:
@@ -390,13 +378,8 @@ class BackboneEngine:
                 ops.stem_wgrad(pl.x, pl.g_stem, self.section(self.gflat, "conv1.weight"),
                                self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad,
                                x_cache=getattr(pl, "x_cache", None))
-            if k in in_group and in_group[k][0] == k:
-                # the dgrad chain of this run is complete: all its weight gradients in two launches
-                k0, k1, IN_all, A_all, GP1_all, GP2_all = in_group[k]
-                ops.conv3x3_wgrad_multi(A_all, GP2_all, self.dwp[(2 * k0 + 1) * n3:], 2 * n3,
-                                        gb3_flat[(2 * k0 + 1) * self.F:], 2 * self.F)
-                ops.conv3x3_wgrad_multi(IN_all, GP1_all, self.dwp[(2 * k0) * n3:], 2 * n3,
-                                        gb3_flat[(2 * k0) * self.F:], 2 * self.F)
+            if k in group_of_first:
+                group_wgrad(k)          # gp1 / gp2 of every block of the run are final now
         ops.unpack_wgrad3x3(self.dwp.view(2 * nb, 9, self.F, self.F), self.section(self.gflat, "w3"))
 
     # ------------------------------------------------------------------ fused train step
