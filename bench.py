@@ -6,7 +6,8 @@
 One "step" = one pass of the hot path over one batch of synthetic WIDERFace-shaped input:
 PoolResnet-medium (F=64, S=10, 10 blocks) forward + summed YoloLoss + backward (models/ModelMeta.py:141,
 173-176 of the reference), batch 64 per GPU, <=100 boxes/image, Dropout2d active (model.train()), and for
-N>1 the all-reduce of the flat fp32 gradient buffer over NCCL.  Weak scaling: per-GPU work is fixed.
+N>1 the all-reduce of the flat fp32 gradient buffer (one NVLink peer-memory kernel, csrc/comm.cu), then the Adam
+step (models/ModelMeta.py:104-112) -- all inside one CUDA graph.  Weak scaling: per-GPU work is fixed.
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with the inputs resident in HBM;
 `e2e` runs the same step through the public API from pinned HOST buffers (H2D of images + targets and
@@ -32,6 +33,7 @@ PKG = "pytorch-face-detection-from-scratch_b200"
 B_PER_GPU = 64
 S = 10
 FLOPS_FWD_PER_IMG = 1069.4e6          # SURVEY 8d, PoolResnet F=64
+LR = 1e-4                             # models/ModelMeta.py:86
 
 
 def synth_batch(B, seed_img=0, seed_box=1):
@@ -100,12 +102,18 @@ def run_reference(args, rank, world):
     x, boxes = synth_batch(Bs)
     gt = torch.stack([torch.from_numpy(yo.grid_encode(b.numpy(), S, 480, 480)) for b in boxes])
     p = seeded_params()
+    ost = {}
+
+    def ref_step():
+        _, _, grads = bo.train_step(x, gt, p, S)
+        bo.adam_update(p, grads, ost, lr=LR)
+
     for _ in range(max(1, min(args.warmup, 2))):
-        bo.train_step(x, gt, p, S)
+        ref_step()
     steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(steps):
-        bo.train_step(x, gt, p, S)
+        ref_step()
     dt = time.perf_counter() - t0
     v = Bs * steps / dt
     sample = f"{steps} steps x {Bs} images (of the {B_PER_GPU}-image batch), eval-mode dropout, torch {torch.__version__} CPU fp32"
@@ -121,7 +129,7 @@ def run_reference(args, rank, world):
 
 def workload_config(n):
     return {"workload": "PoolResnet-medium (filters=64, S=10, 10 blocks, 480x480) train step: forward + summed "
-                        "YoloLoss + backward" + (" + NCCL grad all-reduce" if n > 1 else ""),
+                        "YoloLoss + backward" + (" + gradient all-reduce" if n > 1 else "") + " + Adam step",
             "global_batch": B_PER_GPU * n, "batch_per_gpu": B_PER_GPU, "boxes_per_image": "1..100",
             "parallelism": f"dp{n}", "dropout": "train-mode Dropout2d",
             "l2": "per-step working set (177 MB fp32 images + ~1 GB bf16 activations) exceeds the 126 MB L2; no flush needed"}
@@ -135,6 +143,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N>1: use the NCCL all-reduce instead of the peer-memory kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -165,10 +174,18 @@ def main():
     x = x_cpu.to(dev)
     B = B_PER_GPU
 
+    # Adam (the reference's optimizer, ModelMeta.py:104-112) is part of the step: one kernel over the flat buffers,
+    # step count on the device so that it replays from the graph.  N > 1: the gradient all-reduce is ONE peer-memory
+    # kernel inside the same graph (csrc/comm.cu); NCCL only if peer memory cannot be mapped on this box.
+    opt = fd.optim.FlatAdam(eng, lr=LR, capturable=True)
+    peer_ar = None
+    if world > 1 and not args.nccl:
+        peer_ar = par.PeerAllReduce.create(eng.n_flat, dev)
+    collective = "none" if world == 1 else ("nvlink peer-memory kernel (in graph)" if peer_ar else "nccl all_reduce")
+    eager_ar = peer_ar if peer_ar is not None else (par.allreduce_grads if world > 1 else None)
+
     def eager_step():
-        pl = eng.train_step(x, gt, dropout=True)
-        par.allreduce_grads(eng.gflat)
-        return pl
+        return eng.train_step(x, gt, dropout=True, allreduce=eager_ar, optimizer=opt)
 
     graph = None
     if args.no_graph:
@@ -176,12 +193,20 @@ def main():
         pl = eager_step()
         per_step_launches = fd.native.launch_count() - n0
         step = eager_step
-    else:
+    elif world > 1 and peer_ar is None:
         graph, pl, per_step_launches = eng.capture_train_step(x, gt, dropout=True)
+        per_step_launches += 1
 
         def step():
             graph.replay()
             par.allreduce_grads(eng.gflat)
+            opt.step()
+            return pl
+    else:
+        graph, pl, per_step_launches = eng.capture_train_step(x, gt, dropout=True, allreduce=peer_ar, optimizer=opt)
+
+        def step():
+            graph.replay()
             return pl
 
     def barrier():
@@ -227,8 +252,7 @@ def main():
             torch.cuda.current_stream().wait_event(ready[i])
             if it + 1 < nsteps:
                 prefetch(i ^ 1)            # overlap the next batch's H2D with this step's compute
-            loss = model.train_step(xbuf[i], gbuf[i])       # the call a user makes (eager, no graph)
-            par.allreduce_grads(eng.gflat)
+            loss = model.train_step(xbuf[i], gbuf[i], optimizer=opt, allreduce=eager_ar)   # the call a user makes (eager)
             _ = loss.item()                # D2H of the step's result
 
     e2e_run(3)
@@ -257,8 +281,7 @@ def main():
             torch.cuda.current_stream().wait_event(ready[i])
             if it + 1 < nsteps:
                 prefetch8(i ^ 1)
-            loss = model.train_step(x8buf[i], gbuf[i])
-            par.allreduce_grads(eng.gflat)
+            loss = model.train_step(x8buf[i], gbuf[i], optimizer=opt, allreduce=eager_ar)
             _ = loss.item()
 
     e2e8_run(3)
@@ -313,7 +336,8 @@ def main():
         line = {"metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(world), "loss": loss_val,
+                "config": workload_config(world), "loss": loss_val, "collective": collective,
+                "optimizer_steps": opt.device_steps(),
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": xh.numel() * 4 + gth.numel() * 4,
                         "d2h_bytes_per_step": 4, "steps": n_e2e,
@@ -330,6 +354,8 @@ def main():
                 "achieved_tflops_step": 3 * FLOPS_FWD_PER_IMG * B / (ms / args.steps * 1e-3) / 1e12,
                 "roofline": roof, "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
+    if peer_ar is not None:
+        peer_ar.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -425,10 +451,16 @@ def cpu_baseline():
     x, boxes = synth_batch(Bs)
     gt = torch.stack([torch.from_numpy(yo.grid_encode(b.numpy(), S, 480, 480)) for b in boxes])
     p = seeded_params()
-    bo.train_step(x, gt, p, S)
+    ost = {}
+
+    def ref_step():
+        _, _, grads = bo.train_step(x, gt, p, S)
+        bo.adam_update(p, grads, ost, lr=LR)
+
+    ref_step()
     n, t0 = 0, time.perf_counter()
     while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 40):
-        bo.train_step(x, gt, p, S)
+        ref_step()
         n += 1
     dt = time.perf_counter() - t0
     return {"value": Bs * n / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",

@@ -140,6 +140,35 @@ FD_API int fd_resblock_chain_bwd(const fd_bf16* g_out, const fd_bf16* gp2_last, 
                           const fd_chain_bwd_block* blocks, int n_blocks, int B, int H, int W, int C, float slope,
                           void* stream);
 
+/* Adam step on flat fp32 buffers of n elements (n % 4 == 0), torch.optim.Adam semantics without amsgrad
+ * (models/ModelMeta.py:104-112: the reference's SAMSGD is numerically plain Adam).  One launch for all parameters
+ * (the reference's _multi_tensor Adam issues ~10 foreach kernels over 44 tensors).
+ * state == NULL: `step` is the 1-based step count used for the bias corrections and `lr` the learning rate.
+ * state != NULL (device, int32[4], zero-initialised): the step count (state[0]) and the learning rate (state[2], fp32
+ * bits) live on the device and the kernel advances the count itself, so the launch can be replayed from a CUDA
+ * graph; `step` and `lr` are ignored. */
+FD_API int fd_adam_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int step, int32_t* state, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory (csrc/comm.cu).  The reference is single-GPU
+ * (train_model.py:47-53); its loss is a SUM over the batch (models/ModelMeta.py:173-176,215), so the exchanged
+ * quantity is the plain sum of the per-rank flat gradient buffers.  One process per GPU; every rank allocates a
+ * window (fd_comm_alloc, a cudaMalloc allocation, zero-filled), exports it (64-byte CUDA IPC handle), exchanges the
+ * handles through its host-side plumbing (torch.distributed all_gather), imports the peers' windows, synchronises
+ * once on the host, and from then on calls fd_allreduce_sum_f32 -- ONE kernel per call, no host involvement,
+ * CUDA-graph capturable, bit-identical results on every rank.  These are the only entry points that allocate. */
+FD_API long fd_comm_window_bytes(long n, int world);              /* window size for n fp32 elements (n % 4 == 0), world <= 8 */
+FD_API int fd_comm_alloc(long bytes, void** ptr);
+FD_API int fd_comm_free(void* ptr);
+FD_API int fd_comm_export(void* ptr, unsigned char* handle64);
+FD_API int fd_comm_import(const unsigned char* handle64, void** peer_ptr);
+FD_API int fd_comm_release(void* peer_ptr);
+FD_API int fd_comm_error_offset(void);                            /* byte offset of the u32 status word in a window (0 = ok) */
+/* windows: HOST array of `world` device pointers (entry `rank` = the local window, the rest imported);
+ * data: the local flat fp32 buffer of n elements, summed over ranks in place. */
+FD_API int fd_allreduce_sum_f32(void* const* windows, int rank, int world, float* data, long n, void* stream);
+
 /* Dropout2d multipliers (models/PoolResnet.py:39,100; nn.Dropout2d zeroes whole channels and rescales):
  * out[i] = r[i] < keep ? 1/keep : 0 with keep = keep_block for i < n_block and keep_head otherwise.
  * r: n uniform randoms in [0,1) (one per (layer, image, channel)), produced by the caller's generator. */
@@ -204,6 +233,13 @@ FD_API int fd_yolo_loss(const float* pred, const float* gt, int B, int S1, int S
  * from S1/S2.  iou_thr is compared in double like torchvision's CPU kernel. */
 FD_API int fd_decode_nms(const float* pred, int B, int S1, int S2, float p_thr, double iou_thr, int width, int height,
                   int num_of_patches, float* out_boxes, int32_t* out_cell, int32_t* out_count, void* stream);
+
+/* models/ModelMeta.py:184-214 step metrics for a batch, without host synchronisation: for every image the IoU
+ * matrix (torchvision.ops.box_iou, nan -> 0) of the decoded ground-truth rows against the decoded prediction rows.
+ * gt_boxes / pred_boxes: [B, cap, 5] fp32 rows (score, x, y, w, h) as written by fd_decode_nms, with row counts
+ * gt_count / pred_count [B] int32.  out: [B,4] fp32 = (#pairs with IoU > iou_thr, sum of IoUs, n_gt, n_pred). */
+FD_API int fd_box_metrics(const float* gt_boxes, const int32_t* gt_count, const float* pred_boxes, const int32_t* pred_count,
+                   int B, int cap, float iou_thr, float* out, void* stream);
 
 /* datasets/WIDERFace/dataset.py:32-64 convert_bbx_to_feature_map for a ragged batch.
  * boxes: [total,5] fp32 rows (1,x,y,w,h); box_offsets: [B+1] int32; out: [B,5,S,S] fp32 (overwritten).

@@ -104,3 +104,19 @@ def train_step(x: torch.Tensor, y: torch.Tensor, p: Params, num_of_patches: int,
     loss.backward()
     grads = {k: v.grad.detach() for k, v in leaves.items()}
     return y_hat.detach(), loss.detach(), grads
+
+
+def adam_update(p: Params, grads: Params, state: dict, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+    """The reference's optimizer step (models/ModelMeta.py:104-112, 12-82): ``SAMSGD`` perturbs the weights by
+    ``rho * g / |g|`` and immediately removes the perturbation again WITHOUT re-evaluating the closure, so the update
+    that remains is its base ``torch.optim._multi_tensor.Adam(lr)``.  Restated with torch.optim.Adam
+    on the same tensors; ``state`` carries the optimizer between calls.  Updates ``p`` in place."""
+    if "opt" not in state:
+        state["leaves"] = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+        state["opt"] = torch.optim.Adam(list(state["leaves"].values()), lr=lr, betas=betas, eps=eps)
+    for k, leaf in state["leaves"].items():
+        leaf.grad = grads[k].detach().clone()
+    state["opt"].step()
+    for k, leaf in state["leaves"].items():
+        p[k] = leaf.detach().clone()
+    return p

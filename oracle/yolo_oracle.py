@@ -207,3 +207,33 @@ def yolo_loss(pred: np.ndarray, gt: np.ndarray, dtype=np.float64):
         d[4] = -3 * g0 * (sg4 - sp4) / sp4
     d[nanmask] = 0
     return loss, d.reshape(np.asarray(pred).shape)
+
+
+def step_metrics(gt_rows: np.ndarray, pred_rows: np.ndarray, iou_thr: float = 0.5):
+    """Per-image detection metrics of the reference's train/validation step (models/ModelMeta.py:184-214).
+
+    gt_rows / pred_rows: ``[K,5]`` rows (score, x, y, w, h) as returned by ``reduce_bounding_boxes``.  Restates
+    ``torchvision.ops.box_iou`` on the xyxy boxes built at ModelMeta.py:201-205 (x2 = w + x, y2 = h + y), with
+    ``nan_to_num(., 0)`` (:206), in IEEE f32 like the tensor ops.  Returns (hits, iou_sum): the number of
+    (gt, pred) pairs with IoU > iou_thr (:210-212) and the sum of all IoUs (:214).  The caller applies the
+    reference's bookkeeping (nothing is accumulated for an image without predictions, :200).
+    """
+    f = np.float32
+    g = gt_rows.astype(f).reshape(-1, 5)
+    p = pred_rows.astype(f).reshape(-1, 5)
+    if g.shape[0] == 0 or p.shape[0] == 0:
+        return 0, f(0.0)
+    gx1, gy1 = g[:, 1], g[:, 2]
+    gx2, gy2 = (g[:, 3] + gx1).astype(f), (g[:, 4] + gy1).astype(f)
+    px1, py1 = p[:, 1], p[:, 2]
+    px2, py2 = (p[:, 3] + px1).astype(f), (p[:, 4] + py1).astype(f)
+    ag = ((gx2 - gx1).astype(f) * (gy2 - gy1).astype(f)).astype(f)
+    ap = ((px2 - px1).astype(f) * (py2 - py1).astype(f)).astype(f)
+    w = np.maximum(f(0), (np.minimum(gx2[:, None], px2[None]) - np.maximum(gx1[:, None], px1[None])).astype(f))
+    h = np.maximum(f(0), (np.minimum(gy2[:, None], py2[None]) - np.maximum(gy1[:, None], py1[None])).astype(f))
+    inter = (w * h).astype(f)
+    union = ((ag[:, None] + ap[None]).astype(f) - inter).astype(f)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = (inter / union).astype(f)
+    iou = np.where(np.isnan(iou), f(0), iou)
+    return int((iou > f(iou_thr)).sum()), iou.astype(np.float64).sum()

@@ -28,5 +28,5 @@ def install_dropin():
         sys.modules[name] = importlib.import_module(f"{__name__}.{name}")
 
 
-for _m in _DROPIN + ["engine", "parallel"]:
+for _m in _DROPIN + ["engine", "parallel", "optim"]:
     importlib.import_module(f"{__name__}.{_m}")

@@ -1,0 +1,199 @@
+// Gradient all-reduce of the data-parallel train step over NVLink peer memory (one process per GPU).
+//
+// The reference trains on one GPU (train_model.py:47-53, Trainer(gpus=1)); its loss is a SUM over the batch
+// (models/ModelMeta.py:173-176,215), so the data-parallel gradient is the plain sum of the shard gradients.
+// The unit of exchange is the engine's flat fp32 gradient buffer (3 MB): far below the size where a ring pays,
+// so this is a latency problem.  ONE kernel, no host involvement, capturable in the step's CUDA graph:
+//
+//   phase 1  scatter-push : rank r stores slice p of its local gradient into peer p's window, slot r   (NVLink writes)
+//   barrier  (per-CTA flags in peer memory, st.release.sys / ld.acquire.sys)
+//   phase 2  reduce + broadcast-push : rank r sums the `world` slots of its slice in rank order (every rank gets
+//            bit-identical results: each element is summed exactly once, by its owner) and stores the sum into the
+//            result window of every peer
+//   barrier
+//   phase 3  copy the result window back into the local gradient buffer (local HBM traffic only)
+//
+// CTA b of every rank touches the same element subset in every phase, so the two barriers are between CTA b of
+// all ranks only -- no grid-wide synchronisation and no co-residency requirement.  No barrier is needed at entry:
+// a peer's scatter window is free once the previous call's second barrier passed, and its result window is only
+// written after the next call's first barrier, by which time that peer finished its phase 3.
+#include "fd_host.h"
+#include "fd_ptx.cuh"
+
+namespace fd {
+namespace {
+
+constexpr int kMaxPeers = 8;
+constexpr int kCommBlocks = 64;
+constexpr int kCommThreads = 512;
+// window layout (bytes): [flags: 2 phases x kCommBlocks x kMaxPeers u32 | epoch counters: kCommBlocks u32 | pad to 8 KB]
+//                        [scatter slots: world x chunk floats][result: world x chunk floats]
+constexpr size_t kFlagBytes = 8192;
+constexpr int kErrWord = 2 * kCommBlocks * kMaxPeers + kCommBlocks;      // u32 index: 0 = ok, 1 + peer = timed out on peer
+constexpr long long kSpinLimitClk = 8000000000LL;                        // ~4 s at 2 GHz
+
+struct Peers {
+  unsigned char* win[kMaxPeers];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// L1-bypassing load of data that a peer GPU wrote into this GPU's memory
+__device__ __forceinline__ float4 ld_peer_written(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void cta_barrier_across_ranks(const Peers& pp, int phase, int rank, int world, unsigned epoch) {
+  __threadfence_system();            // this thread's peer stores are performed before the CTA's flag goes out
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < world) {
+    const int peer = threadIdx.x;
+    const size_t slot = (static_cast<size_t>(phase) * kCommBlocks + blockIdx.x) * kMaxPeers;
+    st_release_sys(reinterpret_cast<unsigned*>(pp.win[peer]) + slot + rank, epoch);
+    const unsigned* mine = reinterpret_cast<const unsigned*>(pp.win[rank]) + slot + peer;
+    const long long t_start = clock64();
+    while (static_cast<int>(ld_acquire_sys(mine) - epoch) < 0) {
+      if (clock64() - t_start > kSpinLimitClk) {        // a peer never arrived (died / not launched): do not hang the GPU
+        reinterpret_cast<unsigned*>(pp.win[rank])[kErrWord] = 1u + peer;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kCommThreads)
+allreduce_sum_kernel(Peers pp, float* __restrict__ data, long n4, long chunk4, int rank, int world) {
+  pdl_trigger();
+  pdl_wait();                        // the local gradient is complete
+  __shared__ unsigned s_epoch;
+  unsigned char* my = pp.win[rank];
+  if (threadIdx.x == 0) {
+    unsigned* ctr = reinterpret_cast<unsigned*>(my) + 2 * kCommBlocks * kMaxPeers + blockIdx.x;
+    s_epoch = *ctr + 1;
+    *ctr = s_epoch;
+  }
+  __syncthreads();
+  const unsigned epoch = s_epoch;
+  const long t0 = static_cast<long>(blockIdx.x) * kCommThreads + threadIdx.x;
+  const long stride = static_cast<long>(gridDim.x) * kCommThreads;
+  float4* data4 = reinterpret_cast<float4*>(data);
+
+  // phase 1: scatter-push (destinations staggered so that the ranks do not all hit the same peer at once)
+  for (int k = 0; k < world; ++k) {
+    const int p = (rank + k) % world;
+    const long lo = p * chunk4, len = min(chunk4, n4 - lo);
+    float4* dst = reinterpret_cast<float4*>(pp.win[p] + kFlagBytes) + rank * chunk4;
+    for (long j = t0; j < len; j += stride) dst[j] = data4[lo + j];
+  }
+  cta_barrier_across_ranks(pp, 0, rank, world, epoch);
+
+  // phase 2: reduce my slice in rank order, push the sum into every peer's result window
+  {
+    const long lo = rank * chunk4, len = min(chunk4, n4 - lo);
+    const float4* slots = reinterpret_cast<const float4*>(my + kFlagBytes);
+    for (long j = t0; j < len; j += stride) {
+      float4 acc = ld_peer_written(slots + j);
+      for (int q = 1; q < world; ++q) {
+        const float4 v = ld_peer_written(slots + q * chunk4 + j);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      for (int k = 0; k < world; ++k) {
+        const int p = (rank + k) % world;
+        reinterpret_cast<float4*>(pp.win[p] + kFlagBytes)[world * chunk4 + lo + j] = acc;
+      }
+    }
+  }
+  cta_barrier_across_ranks(pp, 1, rank, world, epoch);
+
+  // phase 3: result window -> local gradient buffer
+  const float4* res = reinterpret_cast<const float4*>(my + kFlagBytes) + world * chunk4;
+  for (int q = 0; q < world; ++q) {
+    const long lo = q * chunk4, len = min(chunk4, n4 - lo);
+    for (long j = t0; j < len; j += stride) data4[lo + j] = ld_peer_written(res + lo + j);
+  }
+}
+
+inline long chunk4_of(long n, int world) { return ((n / 4) + world - 1) / world; }
+
+}  // namespace
+}  // namespace fd
+
+using namespace fd;
+
+extern "C" long fd_comm_window_bytes(long n, int world) {
+  if (n <= 0 || n % 4 != 0 || world < 1 || world > kMaxPeers) return -1;
+  return static_cast<long>(kFlagBytes) + 2L * world * chunk4_of(n, world) * 16;
+}
+
+extern "C" int fd_comm_alloc(long bytes, void** ptr) {
+  if (!ptr || bytes <= 0) return FD_EINVAL;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, static_cast<size_t>(bytes));      // a plain cudaMalloc allocation: IPC-exportable
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+  e = cudaMemset(p, 0, static_cast<size_t>(bytes));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(p); return static_cast<int>(e); }
+  *ptr = p;
+  return FD_OK;
+}
+
+extern "C" int fd_comm_free(void* ptr) {
+  if (!ptr) return FD_OK;
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) (void)cudaGetLastError();
+  return e == cudaSuccess ? FD_OK : static_cast<int>(e);
+}
+
+extern "C" int fd_comm_export(void* ptr, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (!ptr || !handle64) return FD_EINVAL;
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+  memcpy(handle64, &h, 64);
+  return FD_OK;
+}
+
+extern "C" int fd_comm_import(const unsigned char* handle64, void** peer_ptr) {
+  if (!handle64 || !peer_ptr) return FD_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+  *peer_ptr = p;
+  return FD_OK;
+}
+
+extern "C" int fd_comm_release(void* peer_ptr) {
+  if (!peer_ptr) return FD_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+  if (e != cudaSuccess) (void)cudaGetLastError();
+  return e == cudaSuccess ? FD_OK : static_cast<int>(e);
+}
+
+extern "C" int fd_comm_error_offset(void) { return kErrWord * 4; }
+
+extern "C" int fd_allreduce_sum_f32(void* const* windows, int rank, int world, float* data, long n, void* stream) {
+  if (!windows || !data || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || n <= 0) return FD_EINVAL;
+  if (n % 4 != 0) return FD_EUNSUPPORTED;
+  if (world == 1) return FD_OK;
+  Peers pp = {};
+  for (int i = 0; i < world; ++i) {
+    if (!windows[i]) return FD_EINVAL;
+    pp.win[i] = static_cast<unsigned char*>(windows[i]);
+  }
+  launch_k(allreduce_sum_kernel, dim3(kCommBlocks), dim3(kCommThreads), 0, static_cast<cudaStream_t>(stream), pp, data,
+           n / 4, chunk4_of(n, world), rank, world);
+  count_launch();
+  return launch_status();
+}

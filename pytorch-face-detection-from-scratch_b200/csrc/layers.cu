@@ -2,6 +2,8 @@
 // the stem convolution (3 -> C, 10x10 stride 8), the 5-channel head (+ sigmoid) and MaxPool2d(2),
 // each forward and backward.  All are memory- or latency-bound; the tensor-core work lives in
 // conv3x3_tc.cu / wgrad3x3_tc.cu.
+#include <cmath>
+
 #include "fd_host.h"
 #include "fd_ptx.cuh"
 
@@ -57,6 +59,54 @@ unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, float* __res
   __syncthreads();
   float* dst = dw + (static_cast<long>(l) * C + co0) * row;
   for (int i = threadIdx.x; i < kPackCo * row; i += 256) dst[i] = sm[(i / row) * pitch + i % row];
+}
+
+// Adam on the flat parameter / gradient buffers (models/ModelMeta.py:104-112: the reference's SAMSGD never
+// recomputes gradients, i.e. it is plain torch Adam).  Same update as torch.optim.Adam (no amsgrad, L2 weight decay):
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
+// `state` (nullable, device): int32 {step count, CTA ticket} + fp32 {learning rate} -- with it the step count and
+// the learning rate live on the device, so the launch can be replayed from a CUDA graph; the last CTA to have read
+// the count publishes count + 1.
+__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
+                                 int step, int* __restrict__ state) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float s_hyper[2];
+  if (threadIdx.x == 0) {
+    if (state) {
+      step = state[0] + 1;
+      lr = __int_as_float(state[2]);
+      __threadfence();
+      if (atomicAdd(state + 1, 1) == static_cast<int>(gridDim.x) - 1) {      // every CTA has read state[0]
+        state[1] = 0;
+        state[0] = step;
+      }
+    }
+    const double bc1 = 1.0 - pow(static_cast<double>(b1), static_cast<double>(step));
+    const double bc2 = 1.0 - pow(static_cast<double>(b2), static_cast<double>(step));
+    s_hyper[0] = static_cast<float>(static_cast<double>(lr) / bc1);
+    s_hyper[1] = static_cast<float>(sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_hyper[0], bc2_sqrt = s_hyper[1];
+  for (long i = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) * 4; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x * 4) {
+    float4 pv = *reinterpret_cast<float4*>(p + i), gv = *reinterpret_cast<const float4*>(g + i);
+    float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+    float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gg = gp[e] + wd * pp[e];
+      mp[e] = b1 * mp[e] + (1.f - b1) * gg;
+      vp[e] = b2 * vp[e] + (1.f - b2) * gg * gg;
+      const float denom = sqrtf(vp[e]) / bc2_sqrt + eps;
+      pp[e] -= step_size * (mp[e] / denom);
+    }
+    *reinterpret_cast<float4*>(p + i) = pv;
+    *reinterpret_cast<float4*>(m + i) = mv;
+    *reinterpret_cast<float4*>(v + i) = vv;
+  }
 }
 
 // Dropout2d multipliers from uniform randoms: rows [0, n_block_rows) use keep_b, the rest keep_h
@@ -889,6 +939,16 @@ extern "C" int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, f
     unpack_wgrad3x3_kernel<128><<<n_layers * (128 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, dw);
   else
     return FD_EUNSUPPORTED;
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_adam_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                            float eps, float weight_decay, int step, int32_t* state, void* stream) {
+  if (!p || !g || !m || !v || n <= 0 || (!state && step <= 0)) return FD_EINVAL;
+  if (n % 4 != 0) return FD_EUNSUPPORTED;              // the flat buffers are padded to 16 bytes per section
+  launch_k(adam_flat_kernel, dim3(grid_for(n / 4, 256, 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g, m, v, n,
+           lr, beta1, beta2, eps, weight_decay, step, state);
   count_launch();
   return launch_status();
 }

@@ -261,8 +261,57 @@ grid_encode_kernel(const float* __restrict__ boxes, const int* __restrict__ offs
   }
 }
 
+// ---------------------------------------------------------------------------- step metrics
+// models/ModelMeta.py:184-214: IoU matrix of the decoded ground-truth boxes against the decoded predictions
+// (torchvision.ops.box_iou on xyxy built from the (x, y, w, h) rows), nan -> 0; per image the number of pairs with
+// IoU > thr and the sum of all IoUs.  One CTA per image, no host synchronisation.
+__global__ void __launch_bounds__(kYoloThreads)
+box_metrics_kernel(const float* __restrict__ gt, const int* __restrict__ gt_count, const float* __restrict__ pred,
+                   const int* __restrict__ pred_count, int cap, float thr, float* __restrict__ out) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __shared__ float s_red[kYoloThreads / 32];
+  const int b = blockIdx.x;
+  const int ng = gt_count[b], np = pred_count[b];
+  const float* G = gt + static_cast<size_t>(b) * cap * 5;
+  const float* P = pred + static_cast<size_t>(b) * cap * 5;
+  float hits = 0.f, sum = 0.f;
+  for (int idx = threadIdx.x; idx < ng * np; idx += blockDim.x) {
+    const int i = idx / np, j = idx - i * np;
+    const float ax1 = G[i * 5 + 1], ay1 = G[i * 5 + 2], ax2 = __fadd_rn(G[i * 5 + 3], ax1), ay2 = __fadd_rn(G[i * 5 + 4], ay1);
+    const float bx1 = P[j * 5 + 1], by1 = P[j * 5 + 2], bx2 = __fadd_rn(P[j * 5 + 3], bx1), by2 = __fadd_rn(P[j * 5 + 4], by1);
+    const float aa = __fmul_rn(__fsub_rn(ax2, ax1), __fsub_rn(ay2, ay1));
+    const float ab = __fmul_rn(__fsub_rn(bx2, bx1), __fsub_rn(by2, by1));
+    const float w = fmaxf(0.f, __fsub_rn(fminf(ax2, bx2), fmaxf(ax1, bx1)));
+    const float h = fmaxf(0.f, __fsub_rn(fminf(ay2, by2), fmaxf(ay1, by1)));
+    const float inter = __fmul_rn(w, h);
+    float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+    if (iou != iou) iou = 0.f;                       // nan_to_num(.., 0)
+    hits += iou > thr ? 1.f : 0.f;
+    sum += iou;
+  }
+  const float th = block_sum(hits, s_red);
+  const float ts = block_sum(sum, s_red);
+  if (threadIdx.x == 0) {
+    out[b * 4 + 0] = th;
+    out[b * 4 + 1] = ts;
+    out[b * 4 + 2] = static_cast<float>(ng);
+    out[b * 4 + 3] = static_cast<float>(np);
+  }
+}
+
 }  // namespace
 }  // namespace fd
+
+extern "C" int fd_box_metrics(const float* gt_boxes, const int32_t* gt_count, const float* pred_boxes,
+                              const int32_t* pred_count, int B, int cap, float iou_thr, float* out, void* stream) {
+  using namespace fd;
+  if (!gt_boxes || !gt_count || !pred_boxes || !pred_count || !out || B <= 0 || cap <= 0) return FD_EINVAL;
+  launch_k(box_metrics_kernel, dim3(B), dim3(kYoloThreads), 0, static_cast<cudaStream_t>(stream), gt_boxes, gt_count,
+           pred_boxes, pred_count, cap, iou_thr, out);
+  count_launch();
+  return launch_status();
+}
 
 using namespace fd;
 

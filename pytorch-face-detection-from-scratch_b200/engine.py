@@ -383,30 +383,40 @@ class BackboneEngine:
         ops.unpack_wgrad3x3(self.dwp.view(2 * nb, 9, self.F, self.F), self.section(self.gflat, "w3"))
 
     # ------------------------------------------------------------------ fused train step
-    def train_step(self, x: torch.Tensor, gt: torch.Tensor, dropout: bool = True) -> _Plan:
-        """forward -> per-image YoloLoss (+ its gradient, same kernel) -> backward.
-        Afterwards plan.loss holds the per-image losses and self.gflat the gradient of their SUM
-        (models/ModelMeta.py:173-176,215: the reference sums, it does not average)."""
+    def train_step(self, x: torch.Tensor, gt: torch.Tensor, dropout: bool = True, allreduce=None,
+                   optimizer=None) -> _Plan:
+        """forward -> per-image YoloLoss (+ its gradient, same kernel) -> backward [-> gradient all-reduce over the
+        data-parallel ranks -> optimizer step].  Afterwards plan.loss holds the per-image losses and self.gflat the
+        gradient of their SUM (models/ModelMeta.py:173-176,215: the reference sums, it does not average).
+        ``allreduce``: callable on the flat gradient buffer (parallel.PeerAllReduce or parallel.allreduce_grads);
+        ``optimizer``: optim.FlatAdam (models/ModelMeta.py:104-112)."""
         pl = self.forward(x, train=True, dropout=dropout)
         ops.yolo_loss(pl.y, gt, pl.loss, None, pl.dy)
         self.run_backward(pl, pl.dy)
+        if allreduce is not None:
+            allreduce(self.gflat)
+        if optimizer is not None:
+            optimizer.step()
         return pl
 
     # ------------------------------------------------------------------ CUDA graph of the train step
-    def capture_train_step(self, x_static: torch.Tensor, gt_static: torch.Tensor, dropout: bool = True):
-        """Capture forward + loss + backward on fixed input buffers into one CUDA graph (kills the
-        ~70 launch gaps and all host-side descriptor encoding).  Returns (graph, plan, launches_per_step)."""
+    def capture_train_step(self, x_static: torch.Tensor, gt_static: torch.Tensor, dropout: bool = True,
+                           allreduce=None, optimizer=None):
+        """Capture forward + loss + backward (+ peer-memory all-reduce + Adam) on fixed input buffers into one CUDA
+        graph (kills the launch gaps and all host-side descriptor encoding).  Returns (graph, plan,
+        launches_per_step).  An optimizer inside a graph must keep its step count on the device
+        (optim.FlatAdam(capturable=True))."""
         from .native import launch_count
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(2):
-                self.train_step(x_static, gt_static, dropout)
+                self.train_step(x_static, gt_static, dropout, allreduce, optimizer)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         n0 = launch_count()
         with torch.cuda.graph(graph):
-            pl = self.train_step(x_static, gt_static, dropout)
+            pl = self.train_step(x_static, gt_static, dropout, allreduce, optimizer)
         return graph, pl, launch_count() - n0

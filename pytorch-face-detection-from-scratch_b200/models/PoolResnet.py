@@ -92,15 +92,24 @@ class GridBackbone(BaseModel):
         return y
 
     # ---- fused fast path (one call = forward + summed YoloLoss + backward), see engine.train_step
-    def train_step(self, x: torch.Tensor, gt: torch.Tensor):
+    def train_step(self, x: torch.Tensor, gt: torch.Tensor, optimizer=None, allreduce=None):
         """Returns the summed loss (0-d device tensor); gradients land in ``p.grad`` (views of the flat
-        gradient buffer ``self.engine.gflat``)."""
+        gradient buffer ``self.engine.gflat``).  ``allreduce`` (parallel.PeerAllReduce / parallel.allreduce_grads)
+        sums the gradient over the data-parallel ranks; ``optimizer`` (``self.flat_optimizer()``) then applies the
+        reference's Adam update (models/ModelMeta.py:104-112) in the same call."""
         params = dict(self.named_parameters())
         self.engine.bind(params)
-        pl = self.engine.train_step(self._prep_input(x, False), gt.float().contiguous(), dropout=self.training)
+        pl = self.engine.train_step(self._prep_input(x, False), gt.float().contiguous(), dropout=self.training,
+                                    allreduce=allreduce, optimizer=optimizer)
         for n, p in params.items():
             p.grad = self.engine.grad_view(n)
         return pl.loss.sum()
+
+    def flat_optimizer(self, lr: float = 1e-4, capturable: bool = False):
+        """One-kernel Adam over the flat parameter buffer (optim.FlatAdam); lr default = ModelMeta's (ModelMeta.py:86)."""
+        from ..optim import FlatAdam
+        self.engine.bind(dict(self.named_parameters()))
+        return FlatAdam(self.engine, lr=lr, capturable=capturable)
 
 
 class PoolResnet(GridBackbone):

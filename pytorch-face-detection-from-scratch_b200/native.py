@@ -29,6 +29,15 @@ SIGNATURES = {
     "fd_resblock_chain_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "fd_pack_conv3x3": [_P, _I, _I, _P, _P, _P],
     "fd_unpack_wgrad3x3": [_P, _I, _I, _P, _P],
+    "fd_adam_flat": [_P, _P, _P, _P, _c.c_long, _F, _F, _F, _F, _F, _I, _P, _P],
+    "fd_comm_window_bytes": [_c.c_long, _I],
+    "fd_comm_error_offset": [],
+    "fd_comm_alloc": [_c.c_long, _P],
+    "fd_comm_free": [_P],
+    "fd_comm_export": [_P, _P],
+    "fd_comm_import": [_P, _P],
+    "fd_comm_release": [_P],
+    "fd_allreduce_sum_f32": [_P, _I, _I, _P, _c.c_long, _P],
     "fd_dropout_scale": [_P, _c.c_long, _c.c_long, _F, _F, _P, _P],
     "fd_stem_cache_elems": [_I, _I, _I, _I, _I, _I, _I, _I],
     "fd_stem_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
@@ -40,6 +49,7 @@ SIGNATURES = {
     "fd_maxpool2x2_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P],
     "fd_yolo_loss": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "fd_decode_nms": [_P, _I, _I, _I, _F, _D, _I, _I, _I, _P, _P, _P, _P],
+    "fd_box_metrics": [_P, _P, _P, _P, _I, _I, _F, _P, _P],
     "fd_grid_encode": [_P, _P, _I, _I, _I, _I, _P, _P],
     "fd_ssd_grid_encode": [_P, _P, _I, _P, _I, _I, _I, _P, _P],
     "fd_ssd_decode_nms": [_P, _I, _P, _I, _F, _D, _I, _I, _I, _P, _P, _P],
@@ -82,6 +92,7 @@ def lib():
             fn.restype = _I
         L.fd_launch_count.restype = _c.c_longlong
         L.fd_stem_cache_elems.restype = _c.c_long
+        L.fd_comm_window_bytes.restype = _c.c_long
         L.fd_error_string.restype = _c.c_char_p
         _lib = L
     return _lib

@@ -79,6 +79,13 @@ def unpack_wgrad3x3(dw_packed, dw):
     check(lib().fd_unpack_wgrad3x3(dptr(dw_packed, F32), n, C, dptr(dw, F32), cur_stream()), "fd_unpack_wgrad3x3")
 
 
+def adam_flat(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, state=None):
+    """state: int32[4] device tensor (step count, ticket, lr bits, -) for graph-replayable launches, else None."""
+    check(lib().fd_adam_flat(dptr(p, F32), dptr(g, F32), dptr(m, F32), dptr(v, F32), p.numel(), float(lr), float(beta1),
+                             float(beta2), float(eps), float(weight_decay), int(step), dptr(state, I32), cur_stream()),
+          "fd_adam_flat")
+
+
 def dropout_scale(r, n_block, keep_block, keep_head, out):
     check(lib().fd_dropout_scale(dptr(r, F32), r.numel(), int(n_block), float(keep_block), float(keep_head),
                                  dptr(out, F32), cur_stream()), "fd_dropout_scale")
@@ -147,6 +154,12 @@ def decode_nms(pred, p_thr, iou_thr, width, height, num_of_patches, out_boxes, o
     check(lib().fd_decode_nms(dptr(pred, F32), B, S1, S2, float(p_thr), float(iou_thr), int(width), int(height),
                               int(num_of_patches), dptr(out_boxes, F32), dptr(out_cell, I32), dptr(out_count, I32),
                               cur_stream()), "fd_decode_nms")
+
+
+def box_metrics(gt_boxes, gt_count, pred_boxes, pred_count, iou_thr, out):
+    B, cap, _ = gt_boxes.shape
+    check(lib().fd_box_metrics(dptr(gt_boxes, F32), dptr(gt_count, I32), dptr(pred_boxes, F32), dptr(pred_count, I32),
+                               B, cap, float(iou_thr), dptr(out, F32), cur_stream()), "fd_box_metrics")
 
 
 def grid_encode(boxes, offsets, S, width, height, out):

@@ -7,6 +7,7 @@ gradients -- no 1/world_size scaling.  Inference needs no collective.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
@@ -44,6 +45,78 @@ def allreduce_grads(gflat: torch.Tensor):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(gflat, op=dist.ReduceOp.SUM)
     return gflat
+
+
+class PeerAllReduce:
+    """Sum-all-reduce of a flat fp32 CUDA buffer through NVLink peer memory: ONE kernel per call
+    (csrc/comm.cu), no NCCL and no host work on the data path, so it is captured inside the train step's CUDA graph.
+
+    torch.distributed is the plumbing only: it carries the 64-byte CUDA IPC handles of the per-rank windows at
+    start-up.  ``PeerAllReduce.create`` returns None when peer memory cannot be set up on this box (all ranks
+    agree on that through one MIN all-reduce); callers then use the NCCL all-reduce of ``allreduce_grads``.
+    """
+
+    def __init__(self, numel: int, rank: int, world: int, windows, own):
+        self.numel, self.rank, self.world, self._own = numel, rank, world, own
+        self._windows = windows                      # python ints, entry `rank` is the local window
+        self._array = (ctypes.c_void_p * world)(*windows)
+
+    @classmethod
+    def create(cls, numel: int, device) -> "PeerAllReduce | None":
+        if not (dist.is_initialized() and dist.get_world_size() > 1):
+            return None
+        from .native import lib
+        L = lib()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ok, own, handle = 1, ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        nbytes = L.fd_comm_window_bytes(numel, world)
+        if nbytes <= 0 or L.fd_comm_alloc(nbytes, ctypes.byref(own)) != 0 or L.fd_comm_export(own, handle) != 0:
+            ok = 0
+        every = [None] * world
+        dist.all_gather_object(every, (ok, bytes(handle)))           # plumbing only: 64-byte handles
+        windows = [None] * world
+        if ok and all(o for o, _ in every):
+            for r in range(world):
+                if r == rank:
+                    windows[r] = own.value
+                    continue
+                peer = ctypes.c_void_p()
+                h = (ctypes.c_ubyte * 64)(*every[r][1])
+                if L.fd_comm_import(h, ctypes.byref(peer)) != 0:
+                    ok = 0
+                    break
+                windows[r] = peer.value
+        else:
+            ok = 0
+        flags = [None] * world
+        dist.all_gather_object(flags, ok)                            # also the "every window is zeroed and mapped" barrier
+        if not all(flags):
+            for r, w in enumerate(windows):
+                if w is not None and r != rank:
+                    L.fd_comm_release(ctypes.c_void_p(w))
+            if own.value:
+                L.fd_comm_free(own)
+            return None
+        return cls(numel, rank, world, windows, own)
+
+    def __call__(self, flat: torch.Tensor) -> torch.Tensor:
+        from .native import check, cur_stream, dptr, lib
+        assert flat.numel() == self.numel and flat.dtype == torch.float32
+        check(lib().fd_allreduce_sum_f32(self._array, self.rank, self.world, dptr(flat, torch.float32), self.numel,
+                                         cur_stream()), "fd_allreduce_sum_f32")
+        return flat
+
+    def close(self):
+        from .native import lib
+        L = lib()
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()                                   # nobody unmaps a window a peer may still write
+        for r, w in enumerate(self._windows):
+            if r != self.rank and w:
+                L.fd_comm_release(ctypes.c_void_p(w))
+        L.fd_comm_free(self._own)
+        self._windows = []
 
 
 def max_over_ranks(value: float, device=None) -> float:

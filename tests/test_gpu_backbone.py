@@ -231,3 +231,51 @@ def test_resnet_standard_train_step_vs_oracle():
     for i in range(B):
         want = yo.reduce_bounding_boxes(pl.y[i].cpu().numpy(), 0.5, 0.5, (3, 480, 480), 15)
         assert kept[i].cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_train_step_with_flat_adam_matches_torch_adam_and_graph_replay():
+    """The optimizer inside the step (models/ModelMeta.py:104-112 == plain Adam): after every fused
+    train_step(optimizer=FlatAdam) the parameters equal torch.optim.Adam fed with the SAME gradients, the nn.Parameters
+    (views of the flat buffer) see the update, and 3 replays of the captured forward+loss+backward+Adam graph equal 3
+    eager steps (eval mode: no dropout randomness)."""
+    require_cuda()
+    pkg = fd()
+    gen = torch.Generator().manual_seed(5)
+    B, S = 4, 10
+    x = torch.rand(B, 3, 480, 480, generator=gen).cuda()
+    boxes = [synth_boxes(gen, 1, 30) for _ in range(B)]
+    gt = pkg.datasets.WIDERFace.dataset.convert_bbx_to_feature_map_batch(boxes, S, (480, 480), device=torch.device("cuda"))
+    m = _model().cuda().eval()
+    opt = m.flat_optimizer(lr=1e-3)
+    eng = m.engine
+    mirror = eng.pflat.clone().requires_grad_(True)
+    topt = torch.optim.Adam([mirror], lr=1e-3)
+    losses = []
+    for _ in range(3):
+        losses.append(m.train_step(x, gt, optimizer=opt).item())
+        mirror.grad = eng.gflat.clone()
+        topt.step()
+        assert (eng.pflat - mirror.detach()).abs().max().item() <= 2e-6
+    assert m.conv1.weight.data_ptr() == eng.section(eng.pflat, "conv1.weight").data_ptr()
+    assert losses[2] < losses[0], losses                  # three Adam steps on one batch reduce its loss
+    p_eager = eng.pflat.clone()
+
+    m2 = _model().cuda().eval()
+    eng2 = m2.engine
+    eng2.bind(dict(m2.named_parameters()))
+    opt2 = pkg.optim.FlatAdam(eng2, lr=1e-3, capturable=True)
+    graph, pl, launches = eng2.capture_train_step(x, gt, dropout=False, optimizer=opt2)
+    # the two warm-up runs of the capture already stepped the optimizer: restart from the seeded weights
+    eng2.pflat.copy_(_flat_of(_model(), eng2)); opt2.m.zero_(); opt2.v.zero_(); opt2.state[0] = 0
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert opt2.device_steps() == 3
+    assert (eng2.pflat - p_eager).abs().max().item() <= 1e-6
+
+
+def _flat_of(model, eng):
+    flat = torch.zeros(eng.n_flat, device="cuda")
+    for name, p in model.named_parameters():
+        eng._view(flat, name).copy_(p.data.to("cuda"))
+    return flat

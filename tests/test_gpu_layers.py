@@ -220,3 +220,54 @@ def test_maxpool_fwd_bwd_first_max_tie_rule():
     assert torch.equal(gs.float(), gref)
     want2 = (gref * cs[:, None, None, :] * torch.where(msk.float() > 0, 1.0, 0.2)).bfloat16()
     assert rel_err(gs2.float(), want2.float()) <= 4e-3
+
+
+def test_flat_adam_matches_torch_adam():
+    """fd_adam_flat on the flat buffer == torch.optim.Adam over the same elements (models/ModelMeta.py:104-112)."""
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(3)
+    n = 769352
+    p0 = torch.randn(n, device="cuda") * 0.1
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn(n, device="cuda") * (0.01 * step)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_flat(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.0, step)
+    assert (p - ref.detach()).abs().max().item() <= 2e-6
+    assert rel_err(p - p0, ref.detach() - p0) <= 1e-5
+
+
+def test_flat_adam_device_step_count_replays_from_a_graph():
+    """state != NULL: the kernel keeps the step count / lr on the device; 5 replays of ONE captured launch equal 5
+    torch.optim.Adam steps (same gradient buffer, refreshed between replays)."""
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(4)
+    n = 40000
+    p0 = torch.randn(n, device="cuda") * 0.1
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=2e-3)
+    p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p); g = torch.zeros_like(p)
+    lr_bits = torch.tensor([2e-3], dtype=torch.float32).view(torch.int32).item()
+    state = torch.tensor([0, 0, lr_bits, 0], dtype=torch.int32, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            ops.adam_flat(p, g, m, v, 0.0, 0.9, 0.999, 1e-8, 0.0, 0, state)
+    torch.cuda.current_stream().wait_stream(side)
+    for step in range(1, 6):
+        gn = torch.randn(n, device="cuda") * (0.01 * step)
+        g.copy_(gn)
+        ref.grad = gn.clone()
+        opt.step()
+        graph.replay()
+    torch.cuda.synchronize()
+    assert state[:2].tolist() == [5, 0]
+    assert (p - ref.detach()).abs().max().item() <= 2e-6
+    assert rel_err(p - p0, ref.detach() - p0) <= 1e-5

@@ -142,3 +142,51 @@ def test_grid_encode_ragged_batch_and_roundtrip():
         want = yo.grid_encode(b.numpy(), S, 480, 480)
         occupied = int((want[0] > 0.5).sum())
         assert counts[i] == occupied
+
+
+def test_step_metrics_batch_vs_oracle_and_reference_loop():
+    """fd_box_metrics (ModelMeta.py:184-214 batched): hit counts bit-exact against the oracle restatement of
+    torchvision.box_iou, IoU sums to 1e-5; ModelMeta.step's batched metrics == the reference's per-image loop."""
+    require_cuda()
+    pkg = fd()
+    ops, RB = pkg.ops, pkg.datasets.utils.ReduceBoundingBoxes
+    gen = torch.Generator().manual_seed(21)
+    B, S = 48, 10
+    boxes = [synth_boxes(gen, 1, 100) for _ in range(B - 2)] + [torch.zeros((0, 5)), synth_boxes(gen, 1, 2)]
+    y = pkg.datasets.WIDERFace.dataset.convert_bbx_to_feature_map_batch(boxes, S, (480, 480), device=torch.device("cuda"))
+    noise = torch.rand(y.shape, generator=gen).cuda()
+    y_hat = (y * (0.75 + 0.25 * noise) + (1 - y[:, :1]) * noise * 0.6).clamp(0, 1)   # jittered boxes + false positives
+    y_hat[3] = 0.0                                                                  # an image without predictions
+    rb = RB(0.5, 0.5, (3, 480, 480), S)
+    gb, gn = rb.batch_forward(y)
+    pb, pn = rb.batch_forward(y_hat)
+    m = torch.empty((B, 4), device="cuda")
+    ops.box_metrics(gb, gn, pb, pn, 0.5, m)
+    m = m.cpu().numpy()
+    gb, gn, pb, pn = gb.cpu().numpy(), gn.cpu().numpy(), pb.cpu().numpy(), pn.cpu().numpy()
+    for i in range(B):
+        hits, s = yo.step_metrics(gb[i, :gn[i]], pb[i, :pn[i]], 0.5)
+        assert int(m[i, 0]) == hits, f"image {i}"
+        assert abs(m[i, 1] - s) <= 1e-5 * max(1.0, abs(s)), f"image {i}"
+        assert (int(m[i, 2]), int(m[i, 3])) == (gn[i], pn[i])
+    assert pn[3] == 0 and m[3, 0] == 0
+
+    class _Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.reduce_bounding_boxes = rb
+            self.w = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, x):
+            return y_hat + 0 * self.w
+
+        def non_max_suppression(self, x):
+            bx, n = rb.batch_forward(x)
+            return rb.batch_to_tuple(bx, n)
+
+    meta = pkg.models.ModelMeta.ModelMeta(_Holder().cuda())
+    out = meta.step((None, y, None), 1)
+    ti, tr, tp = meta._metrics_per_image(y, y_hat)
+    n = B
+    assert abs(out["total_recall"] - tr / n) <= 1e-9 and abs(out["total_precision"] - tp / n) <= 1e-9
+    assert abs(float(out["total_iou"]) - float(ti) / n) <= 1e-4 * max(1.0, float(ti) / n)

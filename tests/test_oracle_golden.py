@@ -129,3 +129,32 @@ def test_ssd_loss_value_grad_and_mining_mask():
     assert abs(loss - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
     np.testing.assert_allclose(dconf, g["dconf"], rtol=2e-5, atol=1e-9)
     np.testing.assert_allclose(dloc, g["dloc"], rtol=2e-5, atol=1e-9)
+
+
+def test_step_metrics_oracle_vs_torchvision_box_iou():
+    """oracle.step_metrics restates ModelMeta.py:201-214 (third-party torchvision.ops.box_iou): pinned against the
+    installed CPU op on integer-valued decoded rows, incl. zero-area boxes (0/0 -> nan -> 0) and empty sides."""
+    import torch
+    from torchvision.ops import box_iou
+    from oracle import yolo_oracle as yo
+    rng = np.random.default_rng(5)
+    for case in range(20):
+        ng, npred = int(rng.integers(0, 40)), int(rng.integers(0, 40))
+        def rows(n):
+            r = np.zeros((n, 5), np.float32)
+            r[:, 0] = rng.random(n)
+            r[:, 1:3] = rng.integers(0, 400, (n, 2))
+            r[:, 3:5] = rng.integers(0, 120, (n, 2))        # zero widths/heights occur
+            return r
+        g, p = rows(ng), rows(npred)
+        if case % 5 == 0 and ng and npred:
+            p[0] = g[0]; g[0, 3:5] = 0; p[0, 3:5] = 0        # identical zero-area pair: 0/0
+        hits, s = yo.step_metrics(g, p, 0.5)
+        if ng == 0 or npred == 0:
+            assert hits == 0 and s == 0
+            continue
+        gt, pt = torch.from_numpy(g[:, 1:].copy()), torch.from_numpy(p[:, 1:].copy())
+        gt[:, 2] += gt[:, 0]; gt[:, 3] += gt[:, 1]; pt[:, 2] += pt[:, 0]; pt[:, 3] += pt[:, 1]
+        iou = torch.nan_to_num(box_iou(gt, pt), 0)
+        assert hits == torch.where(iou > 0.5)[0].shape[0]
+        assert abs(s - float(iou.double().sum())) <= 1e-6 * max(1.0, s)
