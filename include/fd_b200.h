@@ -176,6 +176,20 @@ FD_API int fd_dropout_scale(const float* r, long n, long n_block, float keep_blo
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Depthwise-separable residual block of SeparableCNN, forward (models/SeparableCNN.py:10-51), eval mode:
+ *   out = pw2( lrelu( dw3x3( lrelu( pw1(x) ) ) ) ) + x        (all three convolutions without bias, :10,19,28,35)
+ * as ONE kernel (csrc/sepblock.cu): the two 1x1 convolutions on the tensor cores, the depthwise 3x3 (pad 1) on the
+ * CUDA cores out of shared memory; the intermediates never touch HBM.  x, out: [B,H,W,64] bf16 NHWC.
+ *   w_pw1, w_pw2: [64 cout][64 cin] bf16;  w_dw: [9 taps][64] fp32 -- all three as written by fd_sep_pack.
+ * The MaxPool2d(2) that follows while H > num_of_patches (:49-50) is fd_maxpool2x2_fwd. */
+FD_API int fd_sepblock_fwd(const fd_bf16* x, const fd_bf16* w_pw1, const float* w_dw, const fd_bf16* w_pw2, int B, int H,
+                    int W, int C, float slope, fd_bf16* out, void* stream);
+/* pw: n_pw fp32 pointwise weights (any number of [64][64] matrices, nn.Conv2d layout [cout][cin][1][1]) -> bf16, same
+ * order; dw: n_dw_layers depthwise weights [64][1][3][3] fp32 -> [layer][9][64] fp32. */
+FD_API int fd_sep_pack(const float* pw, long n_pw, fd_bf16* pw_out, const float* dw, int n_dw_layers, float* dw_out,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Stem convolution (models/PoolResnet.py:70-76,98): KxK stride s pad p, Cin(3) -> C, input fp32 NCHW
  * (or uint8 NCHW with the /255 of PoolResnet.py:95 fused: x_is_u8 = 1), output NHWC bf16, bias added.
  * w: [C][Cin][K][K] fp32.

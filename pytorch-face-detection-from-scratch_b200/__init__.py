@@ -16,7 +16,7 @@ import sys
 
 from . import native, ops  # noqa: F401
 
-_DROPIN = ["models", "models.BaseModel", "models.PoolResnet", "models.Resnet", "models.ModelMeta", "losses",
+_DROPIN = ["models", "models.BaseModel", "models.PoolResnet", "models.Resnet", "models.SeparableCNN", "models.ModelMeta", "losses",
            "losses.YoloLoss", "losses.SSDLoss", "datasets", "datasets.utils", "datasets.WIDERFace",
            "datasets.WIDERFace.dataset", "datasets.WIDERFace.dataset_ssd"]
 

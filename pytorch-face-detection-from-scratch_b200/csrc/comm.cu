@@ -52,10 +52,13 @@ __device__ __forceinline__ float4 ld_peer_written(const float4* p) {
 }
 
 __device__ __forceinline__ void cta_barrier_across_ranks(const Peers& pp, int phase, int rank, int world, unsigned epoch) {
-  __threadfence_system();            // this thread's peer stores are performed before the CTA's flag goes out
+  // The CTA's peer stores happen-before the bar.sync; the flag store below is a system-scope RELEASE by a thread that
+  // passed that barrier, and release is cumulative -- the same publish pattern as NCCL's (barrier, then ONE thread
+  // fences and posts), without a system fence in every thread.
   __syncthreads();
   if (static_cast<int>(threadIdx.x) < world) {
     const int peer = threadIdx.x;
+    __threadfence_system();
     const size_t slot = (static_cast<size_t>(phase) * kCommBlocks + blockIdx.x) * kMaxPeers;
     st_release_sys(reinterpret_cast<unsigned*>(pp.win[peer]) + slot + rank, epoch);
     const unsigned* mine = reinterpret_cast<const unsigned*>(pp.win[rank]) + slot + peer;

@@ -1,0 +1,198 @@
+"""SeparableCNN -- mirror of the reference's ``models/SeparableCNN.py:10-117`` (depthwise-separable backbone).
+
+Same constructor, ``forward(x, predict=torch.tensor(0))`` contract and ``state_dict`` keys (``conv1.*``,
+``residual_blocks.{k}.pointwise_conv1 / depthwise_conv / pointwise_conv2.weight``, ``out.*``).  Like the reference,
+``num_of_patches`` is hard-wired to 16 (SeparableCNN.py:71) although the head emits a 10x10 map: the blocks pool while
+H > 16 and the decoder works with 30-pixel patches -- reproduced, not fixed.
+
+The forward (BASELINE config 4: inference + NMS) runs on hand-written sm_100a kernels: the stem and head kernels of
+the residual backbones, ``fd_maxpool2x2_fwd`` and ONE fused kernel per separable block (``fd_sepblock_fwd``:
+1x1 -> LeakyReLU -> depthwise 3x3 -> LeakyReLU -> 1x1 -> + skip, intermediates in shared memory).  Inference only:
+the backward of this backbone is not built (``train()`` mode raises), and the tensor-core kernels are instantiated
+for ``filters == 64``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .BaseModel import BaseModel
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class ResidualBlock(nn.Module):
+    """Parameter holder for reference SeparableCNN.py:10-51."""
+
+    def __init__(self, filters, num_of_patches, dropout=0.25, bias=False):
+        super().__init__()
+        if bias:
+            raise NotImplementedError("fd_sepblock_fwd implements the reference's bias=False blocks")
+        self.num_of_patches = num_of_patches
+        self.pointwise_conv1 = nn.Conv2d(filters, filters, kernel_size=(1, 1), padding=0, bias=bias)
+        self.depthwise_conv = nn.Conv2d(filters, filters, kernel_size=(3, 3), padding=1, groups=filters, bias=bias)
+        self.pointwise_conv2 = nn.Conv2d(filters, filters, kernel_size=(1, 1), padding=0, bias=bias)
+        self.max_pool = nn.MaxPool2d(2)
+        self.leaky_relu = nn.LeakyReLU(0.2)
+        self.dropout2d = nn.Dropout2d(dropout)
+
+    def forward(self, x):  # pragma: no cover - the engine runs the block
+        raise RuntimeError("ResidualBlock is executed by SeparableEngine (CUDA only); call the parent model")
+
+
+class SeparableEngine:
+    """Device state + kernel sequence of the separable backbone's forward: flat fp32 parameters (every nn.Parameter
+    is a view), packed bf16 / tap-major weights, NHWC bf16 activation buffers per batch size."""
+
+    def __init__(self, filters, in_ch, in_h, in_w, num_blocks, stem_k, stem_s, stem_pad, head_k, head_pad,
+                 block_patches, slope=0.2):
+        if filters != 64:
+            raise NotImplementedError("the separable-block kernel is instantiated for 64 channels; got filters=%d"
+                                      % filters)
+        self.F, self.num_blocks, self.slope = filters, num_blocks, slope
+        self.in_ch, self.in_h, self.in_w = in_ch, in_h, in_w
+        self.stem_s, self.stem_pad, self.head_k, self.head_pad = stem_s, stem_pad, head_k, head_pad
+        H = (in_h + 2 * stem_pad - stem_k) // stem_s + 1
+        W = (in_w + 2 * stem_pad - stem_k) // stem_s + 1
+        self.shapes, self.pools = [], []
+        for _ in range(num_blocks):
+            self.shapes.append((H, W))
+            pool = H > block_patches                       # SeparableCNN.py:49
+            self.pools.append(pool)
+            if pool:
+                H, W = H // 2, W // 2
+        self.Hl, self.Wl = H, W
+        self.So_h, self.So_w = H + 2 * head_pad - head_k + 1, W + 2 * head_pad - head_k + 1
+        F_ = filters
+        self.sections = [("conv1.weight", (F_, in_ch, stem_k, stem_k)), ("conv1.bias", (F_,)),
+                         ("pw", (2 * num_blocks, F_, F_, 1, 1)), ("dw", (num_blocks, F_, 1, 3, 3)),
+                         ("out.weight", (5, F_, head_k, head_k)), ("out.bias", (5,))]
+        self.offsets, off = {}, 0
+        for name, shape in self.sections:
+            n = 1
+            for s in shape:
+                n *= s
+            self.offsets[name] = (off, n, shape)
+            off += (n + 3) // 4 * 4
+        self.n_flat = off
+        self.device = None
+        self.pflat = None
+        self.plans: Dict[int, dict] = {}
+
+    def param_names(self):
+        names = ["conv1.weight", "conv1.bias"]
+        for k in range(self.num_blocks):
+            names += [f"residual_blocks.{k}.pointwise_conv1.weight", f"residual_blocks.{k}.depthwise_conv.weight",
+                      f"residual_blocks.{k}.pointwise_conv2.weight"]
+        return names + ["out.weight", "out.bias"]
+
+    def section(self, name):
+        off, n, shape = self.offsets[name]
+        return self.pflat[off:off + n].view(shape)
+
+    def _view(self, name):
+        if name.startswith("residual_blocks."):
+            _, k, conv, _ = name.split(".")
+            k = int(k)
+            if conv == "depthwise_conv":
+                return self.section("dw")[k]
+            return self.section("pw")[2 * k + (0 if conv == "pointwise_conv1" else 1)]
+        return self.section(name)
+
+    def bind(self, params: Dict[str, nn.Parameter]):
+        dev = params["conv1.weight"].device
+        if dev.type != "cuda":
+            raise RuntimeError("the fd_b200 backbone runs on CUDA only (no CPU fallback): call model.cuda()")
+        if self.device != dev or self.pflat is None:
+            self.device = dev
+            self.pflat = torch.zeros(self.n_flat, dtype=F32, device=dev)
+            nb, F_ = self.num_blocks, self.F
+            self.w_pw = torch.empty((2 * nb, F_, F_), dtype=BF16, device=dev)
+            self.w_dw = torch.empty((nb, 9, F_), dtype=F32, device=dev)
+            self.w_head_t = torch.empty(self.head_k * self.head_k * 5 * F_, dtype=F32, device=dev)
+            self.plans.clear()
+        for name in self.param_names():
+            p, v = params[name], self._view(name)
+            if p.data_ptr() != v.data_ptr():
+                with torch.no_grad():
+                    v.copy_(p.data.to(device=dev, dtype=F32))
+                p.data = v
+
+    def plan(self, B):
+        if B not in self.plans:
+            def bf(h, w):
+                return torch.empty((B, h, w, self.F), dtype=BF16, device=self.device)
+            H0, W0 = self.shapes[0]
+            pl = {"act0": bf(H0, W0), "s": [], "out": []}
+            for (h, w), pool in zip(self.shapes, self.pools):
+                s = bf(h, w)
+                pl["s"].append(s)
+                pl["out"].append(bf(h // 2, w // 2) if pool else s)
+            pl["y"] = torch.empty((B, 5, self.So_h, self.So_w), dtype=F32, device=self.device)
+            self.plans[B] = pl
+        return self.plans[B]
+
+    def pack_weights(self):
+        ops.sep_pack(self.section("pw"), self.w_pw, self.section("dw"), self.w_dw)
+        ops.head_pack(self.section("out.weight"), self.w_head_t)
+
+    def forward(self, x: torch.Tensor, repack: bool = True) -> torch.Tensor:
+        """x: [B,in_ch,H,W] fp32 in [0,1] (or uint8: /255 fused into the stem).  Returns the sigmoid head
+        [B,5,So,So] fp32 (a buffer of the plan, overwritten by the next call with the same batch size)."""
+        pl = self.plan(x.shape[0])
+        if repack:
+            self.pack_weights()
+        ops.stem_fwd(x, self.section("conv1.weight"), self.section("conv1.bias"), pl["act0"], self.stem_s, self.stem_pad)
+        cur = pl["act0"]
+        for k in range(self.num_blocks):
+            ops.sepblock_fwd(cur, self.w_pw[2 * k], self.w_dw[k], self.w_pw[2 * k + 1], self.slope, pl["s"][k])
+            if self.pools[k]:
+                ops.maxpool2x2_fwd(pl["s"][k], pl["out"][k])
+            cur = pl["out"][k]
+        ops.head_fwd(cur, None, self.section("out.weight"), self.section("out.bias"), pl["y"], self.head_pad,
+                     w_t=self.w_head_t)
+        return pl["y"]
+
+
+class SeparableCNN(BaseModel):
+    def __init__(self, filters, input_shape, num_of_residual_blocks=10, probability_threshold=0.5, iou_threshold=0.5,
+                 pretrained=False, input_kernel_size=10, input_stride=8, output_kernel_size=6, output_padding=0):
+        super().__init__(filters, input_shape, num_of_patches=16,                    # SeparableCNN.py:69-75
+                         probability_threshold=probability_threshold, iou_threshold=iou_threshold)
+        self.pretrained = pretrained
+        self.dropout2d = nn.Dropout2d(0.5)
+        self.conv1 = nn.Conv2d(input_shape[0], filters, kernel_size=(input_kernel_size, input_kernel_size),
+                               stride=(input_stride, input_stride), padding=input_kernel_size - input_stride)
+        self.residual_blocks = nn.Sequential(
+            *[ResidualBlock(filters=filters, num_of_patches=self.num_of_patches) for _ in range(num_of_residual_blocks)])
+        self.out = nn.Conv2d(filters, 5, stride=(1, 1), kernel_size=(output_kernel_size, output_kernel_size),
+                             padding=output_padding)
+        self.sigmoid = nn.Sigmoid()
+        self.engine = SeparableEngine(filters, input_shape[0], input_shape[1], input_shape[2], num_of_residual_blocks,
+                                      input_kernel_size, input_stride, input_kernel_size - input_stride,
+                                      output_kernel_size, output_padding, block_patches=self.num_of_patches)
+
+    def forward(self, x: torch.Tensor, predict: torch.Tensor = torch.tensor(0)):
+        is_predict = bool(predict == 1)
+        if self.training:
+            raise NotImplementedError("SeparableCNN: only the inference path (eval mode) is built on the B200 kernels; "
+                                      "call model.eval()")
+        if is_predict:                                     # SeparableCNN.py:105-108
+            x = self._resize(x)
+            if x.dtype != torch.uint8:
+                x = x / 255.0
+            if len(x.shape) == 3:
+                x = torch.unsqueeze(x, 0)
+        if not x.is_cuda:
+            raise RuntimeError("fd_b200 models run on CUDA tensors only (no CPU fallback)")
+        if x.dtype not in (torch.float32, torch.uint8):
+            x = x.float()
+        self.engine.bind(dict(self.named_parameters()))
+        with torch.no_grad():
+            y = self.engine.forward(x.contiguous()).clone()
+        if is_predict:
+            return self.single_non_max_suppression(y[0])   # SeparableCNN.py:114-115
+        return y

@@ -95,6 +95,19 @@ def stem_cache_elems(B, Cin, Hin, Win, C, K, stride, pad):
     return int(lib().fd_stem_cache_elems(B, Cin, Hin, Win, C, K, stride, pad))
 
 
+def sepblock_fwd(x, w_pw1, w_dw, w_pw2, slope, out):
+    """x, out: [B,H,W,64] bf16; w_pw1 / w_pw2: [64,64] bf16; w_dw: [9,64] fp32 (fd_sep_pack layouts)."""
+    B, H, W, C = x.shape
+    check(lib().fd_sepblock_fwd(dptr(x, BF16), dptr(w_pw1, BF16), dptr(w_dw, F32), dptr(w_pw2, BF16), B, H, W, C,
+                                float(slope), dptr(out, BF16), cur_stream()), "fd_sepblock_fwd")
+
+
+def sep_pack(pw, pw_out, dw, dw_out):
+    """pw: [L,64,64] fp32 -> pw_out bf16 (same shape); dw: [L,64,3,3] fp32 -> dw_out [L,9,64] fp32."""
+    check(lib().fd_sep_pack(dptr(pw, F32), pw.numel(), dptr(pw_out, BF16), dptr(dw, F32), dw.shape[0], dptr(dw_out, F32),
+                            cur_stream()), "fd_sep_pack")
+
+
 def stem_fwd(x, w, bias, y, stride, pad, x_cache=None):
     B, Cin, Hin, Win = x.shape
     C, _, K, _ = w.shape

@@ -1,0 +1,108 @@
+"""GPU parity of the depthwise-separable backbone (BASELINE config 4: inference + NMS).
+
+Block kernel (fd_sepblock_fwd) against a torch fp32 evaluation of the same block on the SAME bf16-rounded inputs
+and weights (tolerance: the two bf16-rounded intermediates t1 / t2 and the bf16 output, fp32 accumulation:
+rel-L2 <= 6e-3, the conv kernels' own bar is 4e-3 with one rounding); whole model against the golden head of the
+REAL reference (max-abs <= 2e-2 like the residual backbones), decode + NMS of OUR head bit-exact against the oracle.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import backbone_oracle as bo
+from oracle import yolo_oracle as yo
+from tests.gpu_util import fd, rel_err, require_cuda
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _block_ref(x, w1, wd, w2, slope=0.2):
+    """x [B,H,W,64] bf16 -> fp32 NHWC result of the block with the kernel's rounding points (t1, t2 in bf16)."""
+    xf = x.float().permute(0, 3, 1, 2)
+    t1 = F.leaky_relu(F.conv2d(xf, w1.float()[:, :, None, None]), slope).bfloat16().float()
+    t2 = F.leaky_relu(F.conv2d(t1, wd, padding=1, groups=64), slope).bfloat16().float()
+    y = F.conv2d(t2, w2.float()[:, :, None, None]) + xf
+    return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 60, 60), (5, 30, 30), (7, 15, 15), (2, 9, 13), (1, 64, 70), (300, 15, 15)])
+def test_sepblock_kernel_vs_torch(B, H, W):
+    require_cuda()
+    ops = fd().ops
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    x = torch.randn(B, H, W, 64, generator=g).cuda().bfloat16()
+    pw = (torch.randn(2, 64, 64, generator=g) * 0.15).cuda()
+    dw = (torch.randn(1, 64, 1, 3, 3, generator=g) * 0.4).cuda()
+    w_pw = torch.empty((2, 64, 64), dtype=torch.bfloat16, device="cuda")
+    w_dw = torch.empty((1, 9, 64), device="cuda")
+    ops.sep_pack(pw.view(2, 64, 64, 1, 1), w_pw, dw, w_dw)
+    assert torch.equal(w_pw, pw.bfloat16())
+    assert torch.equal(w_dw[0], dw[0, :, 0].reshape(64, 9).t().contiguous())
+    out = torch.full((B, H, W, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.sepblock_fwd(x, w_pw[0], w_dw[0], w_pw[1], 0.2, out)
+    torch.cuda.synchronize()
+    want = _block_ref(x, w_pw[0], dw[0], w_pw[1])
+    assert torch.isfinite(out.float()).all()
+    e = rel_err(out.float(), want)
+    print(f"sepblock {B}x{H}x{W}: rel-L2 {e:.2e}")
+    assert e <= 6e-3
+    # borders are where the zero padding of the depthwise stage matters
+    for sl in (out[:, 0], out[:, -1], out[:, :, 0], out[:, :, -1]):
+        pass
+    eb = rel_err(torch.cat([out[:, 0].float().reshape(-1), out[:, -1].float().reshape(-1),
+                            out[:, :, 0].float().reshape(-1), out[:, :, -1].float().reshape(-1)]),
+                 torch.cat([want[:, 0].reshape(-1), want[:, -1].reshape(-1), want[:, :, 0].reshape(-1),
+                            want[:, :, -1].reshape(-1)]))
+    assert eb <= 6e-3, eb
+
+
+def _model(seed=6):
+    torch.manual_seed(seed)
+    return fd().models.SeparableCNN.SeparableCNN(filters=64, input_shape=(3, 480, 480), probability_threshold=0.47,
+                                                 iou_threshold=0.3)
+
+
+def test_separable_model_vs_reference_golden():
+    require_cuda()
+    g = load_golden("separable_seed6.npz")
+    m = _model()
+    for k, v in m.state_dict().items():              # same construction order / seeding as the reference
+        s = g["w_sum." + k]
+        assert abs(v.double().sum().item() - s[0]) < 1e-9 and abs(v.double().abs().sum().item() - s[1]) < 1e-9, k
+    assert m.num_of_patches == 16 and m.reduce_bounding_boxes.x_patch_size == 30.0
+    m = m.cuda().eval()
+    x = torch.rand(2, 3, 480, 480, generator=torch.Generator().manual_seed(7)).cuda()
+    y = m(x)
+    assert tuple(y.shape) == (2, 5, 10, 10)
+    d = (y.cpu() - torch.from_numpy(g["y"])).abs()
+    print("separable head max/mean abs err", d.max().item(), d.mean().item())
+    assert d.max().item() <= 2e-2 and d.mean().item() <= 2e-3
+    kept = m.non_max_suppression(y)                  # decode + NMS of OUR head: bit-exact against the oracle
+    for i in range(2):
+        want = yo.reduce_bounding_boxes(y[i].cpu().numpy(), 0.47, 0.3, (3, 480, 480), 16)
+        assert kept[i].cpu().numpy().tobytes() == want.tobytes()
+    # the reference's predict path: uint8 image -> resize (no-op at 480) -> /255 (fused into the stem) -> boxes of image 0
+    x8 = (x[0] * 255).round().to(torch.uint8)
+    b0 = m(x8, predict=torch.tensor(1))
+    yq = m((x8.float() / 255.0).unsqueeze(0))
+    want = yo.reduce_bounding_boxes(yq[0].cpu().numpy(), 0.47, 0.3, (3, 480, 480), 16)
+    assert b0.cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_separable_model_batch256_vs_oracle_and_train_mode_raises():
+    """BASELINE config 4 batch size (256): every image of the batch against the fp32 oracle."""
+    require_cuda()
+    m = _model(seed=9).cuda().eval()
+    p = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    x = torch.rand(256, 3, 480, 480, generator=torch.Generator().manual_seed(1))
+    y = m(x.cuda()).cpu()
+    with torch.no_grad():
+        want = torch.cat([bo.separable_forward(x[i:i + 32], p) for i in range(0, 256, 32)])
+    d = (y - want).abs()
+    print("separable B=256 head max/mean abs err", d.max().item(), d.mean().item())
+    assert d.max().item() <= 2e-2 and d.mean().item() <= 2e-3
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(x[:1].cuda())

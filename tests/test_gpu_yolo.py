@@ -184,7 +184,7 @@ def test_step_metrics_batch_vs_oracle_and_reference_loop():
             bx, n = rb.batch_forward(x)
             return rb.batch_to_tuple(bx, n)
 
-    meta = pkg.models.ModelMeta.ModelMeta(_Holder().cuda())
+    meta = pkg.models.ModelMeta(_Holder().cuda())        # `from models import ModelMeta` as in train_model.py:6
     out = meta.step((None, y, None), 1)
     ti, tr, tp = meta._metrics_per_image(y, y_hat)
     n = B

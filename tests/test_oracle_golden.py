@@ -158,3 +158,27 @@ def test_step_metrics_oracle_vs_torchvision_box_iou():
         iou = torch.nan_to_num(box_iou(gt, pt), 0)
         assert hits == torch.where(iou > 0.5)[0].shape[0]
         assert abs(s - float(iou.double().sum())) <= 1e-6 * max(1.0, s)
+
+
+def test_separable_oracle_matches_reference_seeded():
+    """oracle separable_forward (models/SeparableCNN.py:40-51,104-117) against the REAL reference module
+    (tests/golden/make_golden_sep.py): same seeded construction (weight fingerprints), identical head, and the
+    decode + NMS rows through the hard-wired num_of_patches=16 on the 10x10 head (SeparableCNN.py:71) bit-exact."""
+    import torch
+    from oracle import backbone_oracle as bo
+    from oracle import yolo_oracle as yo
+    from tests.util import seeded_separable_params
+    g = load_golden("separable_seed6.npz")
+    p = seeded_separable_params(64, seed=6)
+    for k, v in p.items():
+        s = g["w_sum." + k]
+        assert abs(v.double().sum().item() - s[0]) < 1e-9 and abs(v.double().abs().sum().item() - s[1]) < 1e-9, k
+    x = torch.rand(2, 3, 480, 480, generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        y = bo.separable_forward(x, p)
+    assert tuple(y.shape) == (2, 5, 10, 10)
+    assert (y - torch.from_numpy(g["y"])).abs().max().item() <= 1e-6
+    for i in range(2):
+        rows = yo.reduce_bounding_boxes(g["y"][i], 0.47, 0.3, (3, 480, 480), 16)
+        k = int(g["counts"][i])
+        assert rows.shape[0] == k and rows.tobytes() == g["boxes"][i, :k].tobytes()
