@@ -181,9 +181,10 @@ FD_API int fd_dropout_scale(const float* r, long n, long n_block, float keep_blo
  * as ONE kernel (csrc/sepblock.cu): the two 1x1 convolutions on the tensor cores, the depthwise 3x3 (pad 1) on the
  * CUDA cores out of shared memory; the intermediates never touch HBM.  x, out: [B,H,W,64] bf16 NHWC.
  *   w_pw1, w_pw2: [64 cout][64 cin] bf16;  w_dw: [9 taps][64] fp32 -- all three as written by fd_sep_pack.
- * The MaxPool2d(2) that follows while H > num_of_patches (:49-50) is fd_maxpool2x2_fwd. */
+ * pool != 0 fuses the MaxPool2d(2) that follows while H > num_of_patches (:49-50): out is then [B,H/2,W/2,64] and
+ * the un-pooled sum never reaches HBM (bit-identical to fd_sepblock_fwd + fd_maxpool2x2_fwd). */
 FD_API int fd_sepblock_fwd(const fd_bf16* x, const fd_bf16* w_pw1, const float* w_dw, const fd_bf16* w_pw2, int B, int H,
-                    int W, int C, float slope, fd_bf16* out, void* stream);
+                    int W, int C, float slope, int pool, fd_bf16* out, void* stream);
 /* pw: n_pw fp32 pointwise weights (any number of [64][64] matrices, nn.Conv2d layout [cout][cin][1][1]) -> bf16, same
  * order; dw: n_dw_layers depthwise weights [64][1][3][3] fp32 -> [layer][9][64] fp32. */
 FD_API int fd_sep_pack(const float* pw, long n_pw, fd_bf16* pw_out, const float* dw, int n_dw_layers, float* dw_out,

@@ -23,6 +23,7 @@
 // tile's halo patch is prefetched into the second input stage while the current tile is processed.
 #include "fd_host.h"
 #include "fd_ptx.cuh"
+#include <cstdlib>
 
 namespace fd {
 namespace {
@@ -30,6 +31,7 @@ namespace {
 constexpr int kC = 64;
 constexpr int kWorkWarps = 16;
 constexpr int kThreads = (1 + kWorkWarps) * 32;      // warp 0: TMA + MMA issue; warps 1..16: epilogues + depthwise
+constexpr uint32_t kT1Pitch = 144;                   // bytes between t1 pixel rows (128 + 16: no swizzle needed)
 constexpr uint32_t kConstBytes = 3072;               // depthwise weights [9][64] fp32 + mbarriers + TMEM slot
 
 struct SepParams {
@@ -41,9 +43,15 @@ struct SepParams {
   uint32_t t1_rows;
   uint32_t inv_wp;          // ceil(65536 / Wp)
   uint32_t tmem_cols;
+  int dbg;
+  int pool;                 // fuse MaxPool2d(2): `out` is [B,H/2,W/2,64]
   float slope;
   const float* dw;          // [9][64] fp32, tap-major
 };
+
+// Optional per-tile timestamps of CTA 0 (FD_SEP_TIMING=1): [tile iteration][8] clock64 values.
+__device__ unsigned long long g_sep_dbg[64 * 8];
+#define SEP_TS(slot) do { if (p.dbg && blockIdx.x == 0 && it < 64) g_sep_dbg[it * 8 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
 
@@ -106,8 +114,10 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     h0 = th * p.R;
     w0 = (rem - th * p.tiles_w) * p.TW;
   };
-  const bool issuer = (warp == 0) && elect_one_sync();
-  if (issuer) {
+  // Every single-thread region branches on elect.sync directly: ptxas then knows it is executed by one thread, keeps
+  // descriptors in uniform registers and emits each tcgen05.mma / TMA as ONE instruction (a `lane == 0` or a saved
+  // bool costs a divergence loop per instruction: measured 1200 clk for the 8 MMAs of phase 0).
+  if (warp == 0 && elect_one_sync()) {
     mbar_expect_tx(w_full, 16384);
     tma_load_2d(sW1, &tm_w1, w_full, 0, 0);
     tma_load_2d(sW2, &tm_w2, w_full, 0, 0);
@@ -125,6 +135,7 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   const int q = warp & 3;                  // TMEM lane quadrant of this warp (hardware rule: warp % 4)
   const int cq = wk >> 2;                  // 16-channel quarter handled in the epilogues
   const float slope = p.slope;
+  const uint64_t slope2 = pk2(slope, slope);
 
   int it = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -135,7 +146,11 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 
     // ------------------------------------------------------------------ phase 0: pw1 on every halo pixel
     if (warp == 0) {
-      if (issuer) {
+      if (elect_one_sync()) {
+        // the previous tile's store has finished reading its source (the t2 / staging tile, or -- pooled -- stage s^1)
+        SEP_TS(0);
+        tma_store_wait_read<0>();
+        SEP_TS(1);
         const int next = tile + gridDim.x;
         if (next < p.num_tiles) {          // stage s^1 was last read by the skip-add of tile it-1 (behind a CTA barrier)
           int nn, nh0, nw0;
@@ -144,7 +159,7 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
           tma_load_4d(sX + (s ^ 1) * p.in_buf_bytes, &tm_x, x_full + (s ^ 1), 0, nw0 - 1, nh0 - 1, nn);
         }
         if (it == 0) mbar_wait(w_full, 0);
-        mbar_wait_sleep(x_full + s, (it >> 1) & 1);
+        mbar_wait(x_full + s, (it >> 1) & 1);
         tc_fence_after();
         const uint32_t a_lo = sdesc_lo(smem_u32(xs), 16), b_lo = sdesc_lo(smem_u32(sW1), 16);
 #pragma unroll 1
@@ -155,13 +170,19 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                       sdesc_sw128(b_lo + 2 * k), idesc, k > 0 ? 1u : 0u);
         }
         umma_commit(acc1_full);
+        SEP_TS(2);
+        // ONE thread polls the MMA-completion barrier; the 16 working warps sleep in the hardware CTA barrier below.
+        // (512 threads polling try_wait starve this warp of issue slots -- measured 1000 clk to issue 8 MMAs -- and a
+        // suspend-time hint costs microseconds per wait.)
+        mbar_wait(acc1_full, it & 1);
       }
       __syncwarp();
-    } else {
-      if (threadIdx.x == 32) tma_store_wait_read<0>();    // the previous tile's store has drained the t2 / staging buffer
-      __syncwarp();
-      mbar_wait_sleep(acc1_full, it & 1);
-      tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp != 0) {
+      if (threadIdx.x == 32) SEP_TS(3);
 #pragma unroll 1
       for (int mb = 0; mb < p.nblk1; ++mb) {
         uint32_t acc[16];
@@ -170,14 +191,17 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         uint32_t u[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float a = __uint_as_float(acc[2 * i]), b = __uint_as_float(acc[2 * i + 1]);
-          u[i] = pack_bf16x2(fmaxf(a, a * slope), fmaxf(b, b * slope));
+          float a, b, ta, tb;
+          const uint64_t v = pk2u(acc[2 * i], acc[2 * i + 1]);
+          upk2(v, a, b);
+          upk2(mul2(v, slope2), ta, tb);
+          u[i] = pack_bf16x2(fmaxf(a, ta), fmaxf(b, tb));
         }
         const uint32_t r = static_cast<uint32_t>(mb * 128 + q * 32 + lane);
-        if (r < p.t1_rows) {
-          const uint32_t row = r * 128u;
-          *reinterpret_cast<uint4*>(sT1 + swz(row + cq * 32u)) = make_uint4(u[0], u[1], u[2], u[3]);
-          *reinterpret_cast<uint4*>(sT1 + swz(row + cq * 32u + 16u)) = make_uint4(u[4], u[5], u[6], u[7]);
+        if (r < p.t1_rows) {             // t1 rows are kT1Pitch = 144 B apart: conflict-free here AND for the row-wide reads below
+          uint8_t* row = sT1 + r * kT1Pitch + cq * 32u;
+          *reinterpret_cast<uint4*>(row) = make_uint4(u[0], u[1], u[2], u[3]);
+          *reinterpret_cast<uint4*>(row + 16) = make_uint4(u[4], u[5], u[6], u[7]);
         }
         __syncwarp();
       }
@@ -187,42 +211,49 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     tc_fence_after();
 
     // ------------------------------------------------------------------ phase 1: depthwise 3x3 + LeakyReLU, t1 -> t2
+    if (threadIdx.x == 32) SEP_TS(4);
     if (warp != 0) {
-      float2 w9[9];
+      uint64_t w9[9];             // packed fp32x2 weights of this lane's channel pair: FFMA2 does both channels at once
 #pragma unroll
-      for (int t = 0; t < 9; ++t) w9[t] = *reinterpret_cast<const float2*>(sDw + t * kC + 2 * lane);
+      for (int t = 0; t < 9; ++t) {
+        const float2 w = *reinterpret_cast<const float2*>(sDw + t * kC + 2 * lane);
+        w9[t] = pk2(w.x, w.y);
+      }
+      // One item = 8 consecutive output pixels of one row; lane = channel pair.  The 10 x 3 input columns are loaded
+      // with immediate offsets (no address arithmetic, no swizzle: pitch-144 rows) and the 3x3 window rotates through
+      // registers by full unrolling.  Columns beyond the tile are junk reads; their results are not stored.
       const int items = p.R * p.nseg;
       for (int item = wk; item < items; item += kWorkWarps) {
         const int y = item / p.nseg;
         const int x0 = (item - y * p.nseg) * 8;
-        const int xe = min(x0 + 8, p.TW);
-        float2 c[3][3];
-        auto load_col = [&](int xx, int slot) {
+        const uint8_t* src = sT1 + static_cast<uint32_t>(y * p.Wp + x0) * kT1Pitch + 4u * lane;
+        const uint32_t wp_b = static_cast<uint32_t>(p.Wp) * kT1Pitch;
+        const uint32_t row0 = static_cast<uint32_t>(y * p.Wp + x0);
+        uint64_t c[3][3];
+        auto load_col = [&](int j, int slot) {
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const uint32_t off = static_cast<uint32_t>((y + ky) * p.Wp + xx) * 128u + 4u * lane;
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(sT1 + swz(off));
-            c[ky][slot] = make_float2(bf16lo(v), bf16hi(v));
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(src + ky * wp_b + j * kT1Pitch);
+            c[ky][slot] = pk2u(v << 16, v & 0xFFFF0000u);
           }
         };
-        load_col(x0, 0);
-        load_col(x0 + 1, 1);
-        for (int x = x0; x < xe; ++x) {
-          load_col(x + 2, 2);
-          float2 a = make_float2(0.f, 0.f);
+        load_col(0, 0);
+        load_col(1, 1);
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              a.x = fmaf(w9[ky * 3 + kx].x, c[ky][kx].x, a.x);
-              a.y = fmaf(w9[ky * 3 + kx].y, c[ky][kx].y, a.y);
-            }
-          const uint32_t o = static_cast<uint32_t>(y * p.Wp + x) * 128u + 4u * lane;
-          *reinterpret_cast<uint32_t*>(sT2 + swz(o)) = pack_bf16x2(fmaxf(a.x, a.x * slope), fmaxf(a.y, a.y * slope));
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            c[ky][0] = c[ky][1];
-            c[ky][1] = c[ky][2];
+        for (int j = 0; j < 8; ++j) {
+          const int s0 = j % 3, s1 = (j + 1) % 3, s2 = (j + 2) % 3;
+          load_col(j + 2, s2);
+          // three independent accumulation chains (one per kernel row), summed at the end
+          uint64_t a0 = mul2(w9[0], c[0][s0]), a1 = mul2(w9[3], c[1][s0]), a2 = mul2(w9[6], c[2][s0]);
+          a0 = fma2(w9[1], c[0][s1], a0); a1 = fma2(w9[4], c[1][s1], a1); a2 = fma2(w9[7], c[2][s1], a2);
+          a0 = fma2(w9[2], c[0][s2], a0); a1 = fma2(w9[5], c[1][s2], a1); a2 = fma2(w9[8], c[2][s2], a2);
+          const uint64_t v = add2(add2(a0, a1), a2);
+          float ax, ay, tx, ty;
+          upk2(v, ax, ay);
+          upk2(mul2(v, slope2), tx, ty);
+          if (x0 + j < p.TW) {
+            const uint32_t o = (row0 + j) * 128u + 4u * lane;
+            *reinterpret_cast<uint32_t*>(sT2 + swz(o)) = pack_bf16x2(fmaxf(ax, tx), fmaxf(ay, ty));
           }
         }
       }
@@ -233,8 +264,9 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     tc_fence_after();
 
     // ------------------------------------------------------------------ phase 2: pw2 + skip -> dense staging tile
+    if (threadIdx.x == 32) SEP_TS(5);
     if (warp == 0) {
-      if (issuer) {
+      if (elect_one_sync()) {
         const uint32_t a_lo = sdesc_lo(smem_u32(sT2), 16), b_lo = sdesc_lo(smem_u32(sW2), 16);
 #pragma unroll 1
         for (int mb = 0; mb < p.nblk3; ++mb) {
@@ -244,12 +276,16 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                       sdesc_sw128(b_lo + 2 * k), idesc, k > 0 ? 1u : 0u);
         }
         umma_commit(acc2_full);
+        mbar_wait(acc2_full, it & 1);            // also: the MMAs have finished reading t2, it may become the staging tile
       }
       __syncwarp();
-    } else {
-      mbar_wait_sleep(acc2_full, it & 1);        // also: the MMAs have finished reading t2, it may become the staging tile
-      mbar_wait_sleep(x_full + s, (it >> 1) & 1);   // (completed long ago) acquire the TMA-written halo patch for the skip reads
-      tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp != 0) {
+      if (threadIdx.x == 32) SEP_TS(6);
+      mbar_wait(x_full + s, (it >> 1) & 1);         // (completed long ago) acquire the TMA-written halo patch for the skip reads
       // all accumulator blocks into registers first: the staging tile aliases t2 rows of OTHER threads' blocks only
       // after every MMA has completed (acc2_full), so writes may start right away
 #pragma unroll 1
@@ -283,12 +319,49 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (threadIdx.x == 32) {
-      tma_store_4d(&tm_out, sT2, 0, w0, h0, n);            // beyond the image: clipped
-      tma_store_commit();
+    if (threadIdx.x == 32) SEP_TS(7);
+    if (!p.pool) {
+      if (warp == 0) {
+        if (elect_one_sync()) {
+          tma_store_4d(&tm_out, sT2, 0, w0, h0, n);        // beyond the image: clipped
+          tma_store_commit();
+        }
+        __syncwarp();
+      }
+    } else {
+      // ---------------------------------------------------------------- phase 3: MaxPool2d(2) of the staged tile
+      // (models/SeparableCNN.py:49-50).  Pooled pixels go, densely and swizzled, into input stage s (dead: its last
+      // readers were the skip reads above); lane = channel pair, one pooled pixel per warp iteration.
+      if (warp != 0) {
+        const int PW = p.TW >> 1, npool = (p.R >> 1) * PW;
+        for (int i = wk; i < npool; i += kWorkWarps) {
+          const int py = i / PW, px = i - py * PW;
+          const uint32_t r00 = static_cast<uint32_t>((2 * py) * p.TW + 2 * px) * 128u + 4u * lane;
+          const uint32_t r10 = r00 + static_cast<uint32_t>(p.TW) * 128u;
+          const uint32_t a = *reinterpret_cast<const uint32_t*>(sT2 + swz(r00));
+          const uint32_t b = *reinterpret_cast<const uint32_t*>(sT2 + swz(r00 + 128u));
+          const uint32_t c = *reinterpret_cast<const uint32_t*>(sT2 + swz(r10));
+          const uint32_t d = *reinterpret_cast<const uint32_t*>(sT2 + swz(r10 + 128u));
+          const float lo = fmaxf(fmaxf(bf16lo(a), bf16lo(b)), fmaxf(bf16lo(c), bf16lo(d)));
+          const float hi = fmaxf(fmaxf(bf16hi(a), bf16hi(b)), fmaxf(bf16hi(c), bf16hi(d)));
+          *reinterpret_cast<uint32_t*>(xs + swz(static_cast<uint32_t>(i) * 128u + 4u * lane)) = pack_bf16x2(lo, hi);
+        }
+        fence_proxy_async();
+      }
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one_sync()) {
+          tma_store_4d(&tm_out, xs, 0, w0 >> 1, h0 >> 1, n);
+          tma_store_commit();
+        }
+        __syncwarp();
+      }
     }
   }
-  if (threadIdx.x == 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (warp == 0) {
+    if (elect_one_sync()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
@@ -315,10 +388,13 @@ __global__ void sep_pack_kernel(const float* __restrict__ pw, long n_pw, __nv_bf
 inline uint32_t round1k(size_t v) { return static_cast<uint32_t>((v + 1023) / 1024 * 1024); }
 
 // dynamic shared memory of a tile shape (incl. 1 KB alignment slack); covers the junk-row over-reads of both GEMMs
+// t1: (R+2)*Wp rows of kT1Pitch bytes + slack for the junk-column reads of the last 8-pixel segment (up to 8 rows past)
+inline uint32_t t1_bytes_for(int R, int Wp) { return round1k(static_cast<size_t>((R + 2) * Wp + 10) * kT1Pitch); }
+
 inline size_t smem_for(int R, int Wp) {
   const int nblk1 = ((R + 2) * Wp + 127) / 128, nblk3 = (R * Wp + 127) / 128;
   const size_t in_buf = round1k(static_cast<size_t>(R + 2) * Wp * 128);
-  const size_t t2 = round1k(static_cast<size_t>(R) * Wp * 128), t1 = round1k(static_cast<size_t>(R + 2) * Wp * 128);
+  const size_t t2 = round1k(static_cast<size_t>(R) * Wp * 128), t1 = t1_bytes_for(R, Wp);
   const size_t x0 = 16384 + kConstBytes;
   size_t end = x0 + 2 * in_buf + t2 + t1;
   const size_t reach1 = x0 + in_buf + static_cast<size_t>(nblk1) * 16384;      // pw1 over stage 1
@@ -333,6 +409,10 @@ inline size_t smem_for(int R, int Wp) {
 
 using namespace fd;
 
+extern "C" FD_API int fd_debug_sep_timing(unsigned long long* out, int n) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, fd::g_sep_dbg, sizeof(unsigned long long) * n));
+}
+
 extern "C" int fd_sep_pack(const float* pw, long n_pw, fd_bf16* pw_out, const float* dw, int n_dw_layers, float* dw_out,
                            void* stream) {
   if ((n_pw > 0 && (!pw || !pw_out)) || (n_dw_layers > 0 && (!dw || !dw_out)) || (n_pw <= 0 && n_dw_layers <= 0))
@@ -344,19 +424,22 @@ extern "C" int fd_sep_pack(const float* pw, long n_pw, fd_bf16* pw_out, const fl
 }
 
 extern "C" int fd_sepblock_fwd(const fd_bf16* x, const fd_bf16* w_pw1, const float* w_dw, const fd_bf16* w_pw2, int B,
-                               int H, int W, int C, float slope, fd_bf16* out, void* stream) {
+                               int H, int W, int C, float slope, int pool, fd_bf16* out, void* stream) {
   if (!x || !w_pw1 || !w_dw || !w_pw2 || !out || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
   if (C != kC) return FD_EUNSUPPORTED;
   if (!(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;
+  if (pool && (H < 2 || W < 2)) return FD_EINVAL;
   const int nsm = sm_count();
   const size_t smem_cap = 113 * 1024;              // two CTAs per SM
   int bestR = 0, bestTW = 0;
   double best = 1e30;
   const int min_tw_tiles = (W + 61) / 62;
   for (int tw_tiles = min_tw_tiles; tw_tiles <= min_tw_tiles + 2; ++tw_tiles) {
-    const int TW = (W + tw_tiles - 1) / tw_tiles;
+    int TW = (W + tw_tiles - 1) / tw_tiles;
+    if (pool) TW = (TW + 1) & ~1;                  // pooled tiles start on even rows / columns
+    if (TW > 62) continue;
     const int Wp = TW + 2;
-    for (int R = 1; R <= H; ++R) {
+    for (int R = pool ? 2 : 1; R <= (pool ? H + 1 : H); R += pool ? 2 : 1) {
       const int nblk1 = ((R + 2) * Wp + 127) / 128, nblk3 = (R * Wp + 127) / 128;
       if (nblk1 + nblk3 > 4) break;
       if (smem_for(R, Wp) > smem_cap) break;
@@ -380,12 +463,14 @@ extern "C" int fd_sepblock_fwd(const fd_bf16* x, const fd_bf16* w_pw1, const flo
   p.in_bytes = static_cast<uint32_t>((bestR + 2) * p.Wp * 128);
   p.in_buf_bytes = round1k(p.in_bytes);
   p.t1_rows = static_cast<uint32_t>((bestR + 2) * p.Wp);
-  p.t1_bytes = round1k(static_cast<size_t>(p.t1_rows) * 128);
+  p.t1_bytes = t1_bytes_for(bestR, p.Wp);
   p.t2_bytes = round1k(static_cast<size_t>(bestR) * p.Wp * 128);
   p.inv_wp = static_cast<uint32_t>((65536 + p.Wp - 1) / p.Wp);
   const int cols = (p.nblk1 + p.nblk3) * kC;
   p.tmem_cols = cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
   p.slope = slope;
+  p.pool = pool ? 1 : 0;
+  { const char* d = getenv("FD_SEP_TIMING"); p.dbg = d ? atoi(d) : 0; }
   p.dw = w_dw;
   const size_t smem = smem_for(bestR, p.Wp);
 
@@ -396,7 +481,8 @@ extern "C" int fd_sepblock_fwd(const fd_bf16* x, const fd_bf16* w_pw1, const flo
   if (rc != FD_OK) return rc;
   rc = make_tmap_2d_bf16(&tm_w2, w_pw2, kC, kC, kC, kC);
   if (rc != FD_OK) return rc;
-  rc = make_tmap_nhwc_bf16(&tm_out, out, B, H, W, C, bestTW, bestR);
+  rc = pool ? make_tmap_nhwc_bf16(&tm_out, out, B, H / 2, W / 2, C, bestTW / 2, bestR / 2)
+            : make_tmap_nhwc_bf16(&tm_out, out, B, H, W, C, bestTW, bestR);
   if (rc != FD_OK) return rc;
 
   cudaError_t e = cudaFuncSetAttribute(sepblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -6,8 +6,8 @@ Same constructor, ``forward(x, predict=torch.tensor(0))`` contract and ``state_d
 H > 16 and the decoder works with 30-pixel patches -- reproduced, not fixed.
 
 The forward (BASELINE config 4: inference + NMS) runs on hand-written sm_100a kernels: the stem and head kernels of
-the residual backbones, ``fd_maxpool2x2_fwd`` and ONE fused kernel per separable block (``fd_sepblock_fwd``:
-1x1 -> LeakyReLU -> depthwise 3x3 -> LeakyReLU -> 1x1 -> + skip, intermediates in shared memory).  Inference only:
+the residual backbones, and ONE fused kernel per separable block (``fd_sepblock_fwd``: 1x1 -> LeakyReLU -> depthwise 3x3 ->
+LeakyReLU -> 1x1 -> + skip -> MaxPool2d(2) where the block pools; intermediates in shared memory).  Inference only:
 the backward of this backbone is not built (``train()`` mode raises), and the tensor-core kernels are instantiated
 for ``filters == 64``.  There is no CPU path.
 """
@@ -126,11 +126,9 @@ class SeparableEngine:
             def bf(h, w):
                 return torch.empty((B, h, w, self.F), dtype=BF16, device=self.device)
             H0, W0 = self.shapes[0]
-            pl = {"act0": bf(H0, W0), "s": [], "out": []}
+            pl = {"act0": bf(H0, W0), "out": []}
             for (h, w), pool in zip(self.shapes, self.pools):
-                s = bf(h, w)
-                pl["s"].append(s)
-                pl["out"].append(bf(h // 2, w // 2) if pool else s)
+                pl["out"].append(bf(h // 2, w // 2) if pool else bf(h, w))
             pl["y"] = torch.empty((B, 5, self.So_h, self.So_w), dtype=F32, device=self.device)
             self.plans[B] = pl
         return self.plans[B]
@@ -148,9 +146,9 @@ class SeparableEngine:
         ops.stem_fwd(x, self.section("conv1.weight"), self.section("conv1.bias"), pl["act0"], self.stem_s, self.stem_pad)
         cur = pl["act0"]
         for k in range(self.num_blocks):
-            ops.sepblock_fwd(cur, self.w_pw[2 * k], self.w_dw[k], self.w_pw[2 * k + 1], self.slope, pl["s"][k])
-            if self.pools[k]:
-                ops.maxpool2x2_fwd(pl["s"][k], pl["out"][k])
+            # the MaxPool2d(2) of a pooling block is fused: the un-pooled sum never reaches HBM
+            ops.sepblock_fwd(cur, self.w_pw[2 * k], self.w_dw[k], self.w_pw[2 * k + 1], self.slope, pl["out"][k],
+                             pool=self.pools[k])
             cur = pl["out"][k]
         ops.head_fwd(cur, None, self.section("out.weight"), self.section("out.bias"), pl["y"], self.head_pad,
                      w_t=self.w_head_t)

@@ -95,11 +95,13 @@ def stem_cache_elems(B, Cin, Hin, Win, C, K, stride, pad):
     return int(lib().fd_stem_cache_elems(B, Cin, Hin, Win, C, K, stride, pad))
 
 
-def sepblock_fwd(x, w_pw1, w_dw, w_pw2, slope, out):
-    """x, out: [B,H,W,64] bf16; w_pw1 / w_pw2: [64,64] bf16; w_dw: [9,64] fp32 (fd_sep_pack layouts)."""
+def sepblock_fwd(x, w_pw1, w_dw, w_pw2, slope, out, pool=False):
+    """x: [B,H,W,64] bf16; out: [B,H,W,64] (or [B,H/2,W/2,64] with the fused MaxPool2d(2)); w_pw1 / w_pw2: [64,64]
+    bf16; w_dw: [9,64] fp32 (fd_sep_pack layouts)."""
     B, H, W, C = x.shape
+    assert tuple(out.shape) == ((B, H // 2, W // 2, C) if pool else (B, H, W, C))
     check(lib().fd_sepblock_fwd(dptr(x, BF16), dptr(w_pw1, BF16), dptr(w_dw, F32), dptr(w_pw2, BF16), B, H, W, C,
-                                float(slope), dptr(out, BF16), cur_stream()), "fd_sepblock_fwd")
+                                float(slope), int(bool(pool)), dptr(out, BF16), cur_stream()), "fd_sepblock_fwd")
 
 
 def sep_pack(pw, pw_out, dw, dw_out):

@@ -58,6 +58,32 @@ def test_sepblock_kernel_vs_torch(B, H, W):
     assert eb <= 6e-3, eb
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 60, 60), (5, 30, 30), (2, 13, 9), (2, 64, 70), (150, 30, 30)])
+def test_sepblock_fused_pool_equals_block_then_maxpool(B, H, W):
+    """pool=1 (MaxPool2d(2) fused, SeparableCNN.py:49-50) is bit-identical to the block kernel followed by
+    fd_maxpool2x2_fwd, and matches torch max_pool2d of the fp32 block result (floor semantics on odd sizes)."""
+    require_cuda()
+    ops = fd().ops
+    g = torch.Generator().manual_seed(B * 77 + W)
+    x = torch.randn(B, H, W, 64, generator=g).cuda().bfloat16()
+    w_pw = (torch.randn(2, 64, 64, generator=g) * 0.15).cuda().bfloat16()
+    dw = (torch.randn(64, 1, 3, 3, generator=g) * 0.4).cuda()
+    w_dw = dw[:, 0].reshape(64, 9).t().contiguous()
+    full = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device="cuda")
+    ops.sepblock_fwd(x, w_pw[0], w_dw, w_pw[1], 0.2, full)
+    fused = torch.full((B, H // 2, W // 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.sepblock_fwd(x, w_pw[0], w_dw, w_pw[1], 0.2, fused, pool=True)
+    torch.cuda.synchronize()
+    want = F.max_pool2d(full.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(fused.float(), want)
+    if H % 2 == 0 and W % 2 == 0:
+        two = torch.empty_like(fused)
+        ops.maxpool2x2_fwd(full, two)
+        assert torch.equal(fused, two)
+    ref = F.max_pool2d(_block_ref(x, w_pw[0], dw, w_pw[1]).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert rel_err(fused.float(), ref) <= 6e-3
+
+
 def _model(seed=6):
     torch.manual_seed(seed)
     return fd().models.SeparableCNN.SeparableCNN(filters=64, input_shape=(3, 480, 480), probability_threshold=0.47,
