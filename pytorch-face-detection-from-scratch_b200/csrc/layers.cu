@@ -824,78 +824,85 @@ head_bwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
   }
 }
 
+// One CTA walks pooled rows (row = n * Ho + oy); its threads cover the (ox, 8-channel group) pairs of the row, so the
+// only division per thread is the 32-bit row / Ho -- the former flat 64-bit index cost ~5 64-bit divisions per
+// element and made these HBM-bound kernels instruction-bound.  C8 = C / 8 as a template constant (0 = runtime).
+template <int kC8>
 __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
                                       __nv_bfloat16* __restrict__ y) {
   pdl_trigger();
   pdl_wait();
-  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
-  const long total = static_cast<long>(B) * Ho * Wo * C8;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int c8 = i % C8;
-    const int ox = (i / C8) % Wo;
-    const int oy = (i / (static_cast<long>(C8) * Wo)) % Ho;
-    const long n = i / (static_cast<long>(C8) * Wo * Ho);
-    const __nv_bfloat16* base = x + ((n * H + 2 * oy) * W + 2 * ox) * C + c8 * 8;
-    float m[8], f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base)), m);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base + C)), f);
+  const int Ho = H / 2, Wo = W / 2, C8 = kC8 ? kC8 : C / 8;
+  const int rows = B * Ho, per_row = Wo * C8;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, oy = row - n * Ho;
+    const __nv_bfloat16* xrow = x + (static_cast<size_t>(n) * H + 2 * oy) * W * C;
+    __nv_bfloat16* yrow = y + static_cast<size_t>(row) * Wo * C;
+    for (int idx = threadIdx.x; idx < per_row; idx += blockDim.x) {
+      const int ox = idx / C8, c8 = idx - ox * C8;
+      const __nv_bfloat16* base = xrow + (2 * ox) * C + c8 * 8;
+      float m[8], f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base)), m);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + C)), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<long>(W) * C)), f);
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(W) * C)), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<long>(W) * C + C)), f);
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(W) * C + C)), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
-    *reinterpret_cast<uint4*>(y + ((n * Ho + oy) * Wo + ox) * C + c8 * 8) = pack8(m);
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      *reinterpret_cast<uint4*>(yrow + ox * C + c8 * 8) = pack8(m);
+    }
   }
 }
 
+template <int kC8>
 __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, int B,
                                       int H, int W, int C, __nv_bfloat16* __restrict__ gs,
                                       const uint32_t* __restrict__ mask_bits, const float* __restrict__ cs,
                                       float slope, __nv_bfloat16* __restrict__ gs2) {
   pdl_trigger();
   pdl_wait();
-  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
-  const long total = static_cast<long>(B) * Ho * Wo * C8;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int c8 = i % C8;
-    const int ox = (i / C8) % Wo;
-    const int oy = (i / (static_cast<long>(C8) * Wo)) % Ho;
-    const long n = i / (static_cast<long>(C8) * Wo * Ho);
-    const long off[4] = {0, C, static_cast<long>(W) * C, static_cast<long>(W) * C + C};
-    const long base = ((n * H + 2 * oy) * W + 2 * ox) * C + c8 * 8;
-    float v[4][8], g[8];
+  const int Ho = H / 2, Wo = W / 2, C8 = kC8 ? kC8 : C / 8;
+  const int rows = B * Ho, per_row = Wo * C8;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, oy = row - n * Ho;
+    const size_t row_base = (static_cast<size_t>(n) * H + 2 * oy) * W * C;
+    for (int idx = threadIdx.x; idx < per_row; idx += blockDim.x) {
+      const int ox = idx / C8, c8 = idx - ox * C8;
+      const size_t off[4] = {0, static_cast<size_t>(C), static_cast<size_t>(W) * C, static_cast<size_t>(W) * C + C};
+      const size_t base = row_base + static_cast<size_t>(2 * ox) * C + c8 * 8;
+      float v[4][8], g[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + off[k])), v[k]);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(gy + ((n * Ho + oy) * Wo + ox) * C + c8 * 8)), g);
-    int arg[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {  // first maximum in (dy,dx) row-major order, like ATen's max_pool2d
-      int a = 0; float m = v[0][j];
-#pragma unroll
-      for (int k = 1; k < 4; ++k) if (v[k][j] > m) { m = v[k][j]; a = k; }
-      arg[j] = a;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = arg[j] == k ? g[j] : 0.f;
-      if (gs) *reinterpret_cast<uint4*>(gs + base + off[k]) = pack8(o);
+      for (int k = 0; k < 4; ++k) unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + off[k])), v[k]);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gy + (static_cast<size_t>(row) * Wo + ox) * C + c8 * 8)), g);
+      float sc[8];
       if (gs2) {
-        const long e0 = base + off[k];                 // element index; C % 32 == 0 keeps 8 channels in one word
-        const uint32_t mk = __ldg(mask_bits + (e0 >> 5)) >> (e0 & 31);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float t = o[j] * (((mk >> j) & 1u) ? 1.f : slope);
-          if (cs) t *= cs[n * C + c8 * 8 + j];
-          o[j] = t;
+        for (int j = 0; j < 8; ++j) sc[j] = cs ? __ldg(cs + n * C + c8 * 8 + j) : 1.f;
+      }
+      int arg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // first maximum in (dy,dx) row-major order, like ATen's max_pool2d
+        int a = 0; float m = v[0][j];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) if (v[k][j] > m) { m = v[k][j]; a = k; }
+        arg[j] = a;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = arg[j] == k ? g[j] : 0.f;
+        if (gs) *reinterpret_cast<uint4*>(gs + base + off[k]) = pack8(o);
+        if (gs2) {
+          const size_t e0 = base + off[k];               // element index; C % 32 == 0 keeps 8 channels in one word
+          const uint32_t mk = __ldg(mask_bits + (e0 >> 5)) >> (e0 & 31);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = o[j] * (((mk >> j) & 1u) ? 1.f : slope) * sc[j];
+          *reinterpret_cast<uint4*>(gs2 + base + off[k]) = pack8(o);
         }
-        *reinterpret_cast<uint4*>(gs2 + base + off[k]) = pack8(o);
       }
     }
   }
@@ -1123,9 +1130,13 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
 extern "C" int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, void* stream) {
   if (!x || !y || B <= 0) return FD_EINVAL;
   if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
-  const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  launch_k(maxpool2x2_fwd_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-           reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
+  const long rows = static_cast<long>(B) * (H / 2);
+  if (rows > 0x7fffffffL) return FD_EUNSUPPORTED;
+  const int per_row = (W / 2) * (C / 8);
+  const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
+  launch_k(C == 64 ? maxpool2x2_fwd_kernel<8> : maxpool2x2_fwd_kernel<0>, dim3(grid_for(rows, 1, 16)), dim3(threads), 0,
+           static_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C,
+           reinterpret_cast<__nv_bfloat16*>(y));
   count_launch();
   return launch_status();
 }
@@ -1137,9 +1148,12 @@ extern "C" int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int
   if ((gs2 != nullptr) != (mask_bits != nullptr)) return FD_EINVAL;
   if (gs2 && C % 32 != 0) return FD_EUNSUPPORTED;
   if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
-  const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  launch_k(maxpool2x2_bwd_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-           reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gy), B, H, W, C,
+  const long rows = static_cast<long>(B) * (H / 2);
+  if (rows > 0x7fffffffL) return FD_EUNSUPPORTED;
+  const int per_row = (W / 2) * (C / 8);
+  const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
+  launch_k(C == 64 ? maxpool2x2_bwd_kernel<8> : maxpool2x2_bwd_kernel<0>, dim3(grid_for(rows, 1, 16)), dim3(threads), 0,
+           static_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gy), B, H, W, C,
            reinterpret_cast<__nv_bfloat16*>(gs), mask_bits, chan_scale, slope, reinterpret_cast<__nv_bfloat16*>(gs2));
   count_launch();
   return launch_status();

@@ -150,7 +150,6 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         // the previous tile's store has finished reading its source (the t2 / staging tile, or -- pooled -- stage s^1)
         SEP_TS(0);
         tma_store_wait_read<0>();
-        SEP_TS(1);
         const int next = tile + gridDim.x;
         if (next < p.num_tiles) {          // stage s^1 was last read by the skip-add of tile it-1 (behind a CTA barrier)
           int nn, nh0, nw0;
@@ -160,6 +159,7 @@ sepblock_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         }
         if (it == 0) mbar_wait(w_full, 0);
         mbar_wait(x_full + s, (it >> 1) & 1);
+        SEP_TS(1);
         tc_fence_after();
         const uint32_t a_lo = sdesc_lo(smem_u32(xs), 16), b_lo = sdesc_lo(smem_u32(sW1), 16);
 #pragma unroll 1

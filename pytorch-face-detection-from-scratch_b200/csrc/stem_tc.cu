@@ -32,6 +32,17 @@ constexpr int kMmaWarp = kLoaderWarps;      // MMA issuer + TMEM owner
 constexpr int kTmaWarp = kLoaderWarps + 1;  // TMA producer of the image chunks
 constexpr int kEpiWarp0 = kLoaderWarps + 2; // 4 epilogue warps (10..13 -> TMEM quadrants 2,3,0,1)
 constexpr int kThreads = (kLoaderWarps + 2 + 4) * 32;   // 448
+// Converter warps of the forward.  Measured (FD_STEM_TIMING=1, tools/stem_debug.py): a converter warp needs ~2000 clk
+// per chunk once its data has landed, 3 chunks per task in sequence -> 7500 clk per task, 2.4 TB/s: the converters,
+// not HBM, set the pace.  Every warp needs >= 2 staging slots of its own (one converting, one in flight: with 12
+// warps x 1 slot the HBM round trip is exposed per chunk, 79 us) and a slot must always be drained by the SAME warp
+// (mbarrier parity waits only distinguish adjacent phases: 24 warps sharing 16 slots -> launch failure), so the
+// 227 KB of shared memory (61 KB weights + 61 KB A tile) allow 8 warps x 2 slots.
+constexpr int kFwdLoaders = 8;
+constexpr int kFwdMmaWarp = kFwdLoaders;
+constexpr int kFwdTmaWarp = kFwdLoaders + 1;
+constexpr int kFwdEpiWarp0 = kFwdLoaders + 2;           // 10..13 -> TMEM quadrants 2,3,0,1
+constexpr int kFwdThreads = (kFwdLoaders + 2 + 4) * 32; // 448
 constexpr int kSlotBytes = 4864;            // one staging slot: K/2 rows x Win/2 pixels (<= 4800 B), 128B aligned
 constexpr int kChunksPerTask = 24;          // 3 ch x 2 img x 2 row groups x 2 column halves
 constexpr int kKH = 5;                      // rows per chunk  (K = 10)
@@ -45,6 +56,7 @@ struct StemParams {
   int ntask;        // npairs * Ho
   uint32_t a_bytes; // CK * 2 * 1024
   int elem_bytes;   // 4 (fp32 image) or 1 (uint8 image)
+  int dbg;
   const void* x;
   const float* w;        // [64][Cin][K][K] fp32 (forward)
   const float* bias;     // [64]
@@ -90,8 +102,14 @@ template <>
 struct Px4<uint8_t> {
   static __device__ __forceinline__ void load(const uint8_t* slot, int quad, float (&v)[4]) {
     const uchar4 u = *reinterpret_cast<const uchar4*>(slot + quad * 4);
-    v[0] = static_cast<float>(u.x) / 255.0f; v[1] = static_cast<float>(u.y) / 255.0f;   // PoolResnet.py:95
-    v[2] = static_cast<float>(u.z) / 255.0f; v[3] = static_cast<float>(u.w) / 255.0f;
+    v[0] = div255(u.x); v[1] = div255(u.y); v[2] = div255(u.z); v[3] = div255(u.w);         // PoolResnet.py:95
+  }
+  // x / 255.0f, correctly rounded, without the ~12-instruction IEEE division: q = x * (1/255), one FMA residual and
+  // one FMA correction.  Bit-identical to the division for all 256 inputs (tests/test_host_cpu.py checks the table).
+  static __device__ __forceinline__ float div255(unsigned char b) {
+    const float x = static_cast<float>(b), r = 1.0f / 255.0f;
+    const float q = x * r;
+    return fmaf(fmaf(-q, 255.0f, x), r, q);
   }
 };
 
@@ -108,6 +126,10 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 // chunk j of a task = (channel c, image img, row group rg, column half) -> one box {Win/2, K/2, 1} of
 // the [B*Cin, Hin, Win] input, zero filled above the image.  Converter warp (j % 8) turns it into
 // bf16 rows of the A tile.  Element e of an A row holds input column e - pad.
+// Optional timestamps of CTA 0 (FD_STEM_TIMING=1): [task iteration][16] clock64 values.
+__device__ unsigned long long g_stem_dbg[32 * 16];
+#define STEM_TS(slot) do { if (p.dbg && blockIdx.x == 0 && it < 32) g_stem_dbg[it * 16 + (slot)] = clock64(); } while (0)
+
 struct ChunkCoord {
   int c, img, rg, half;
 };
@@ -126,6 +148,7 @@ __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtens
   int it = 0;
   for (int task = sched.begin; task < sched.end; task += sched.step, ++it) {
     const int pair = task / p.Ho, oy = task % p.Ho;
+    if (lane == 0) STEM_TS(10);
     // batches of NS chunks: inside a batch every lane owns a different slot, so no lane ever waits
     // for a slot that a sibling lane of the same batch still has to fill (that would deadlock the warp)
 #pragma unroll 1
@@ -142,23 +165,26 @@ __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtens
                     oy * p.stride - p.pad + k.rg * (p.K / 2), (pair * 2 + k.img) * p.Cin + k.c);
       }
       __syncwarp();
+      if (lane == 0) STEM_TS(j0 == 0 ? 11 : 12);
     }
   }
 }
 
 // Converter warp `warp`: its chunks of task iteration `it` -> A tile `abuf`.
-template <typename TIn, int NS>
+template <typename TIn, int NS, int NW = kLoaderWarps>
 __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abuf, const uint8_t* sStage,
                                                uint64_t* stg_full, uint64_t* stg_empty, int it, int warp, int lane,
-                                               int task = 0) {
+                                               int task = 0, uint64_t* grp_full = nullptr, uint64_t* grp_empty = nullptr) {
 #pragma unroll 1
-  for (int jj = 0; jj < kChunksPerTask / 8; ++jj) {
-    const int j = jj * 8 + warp;
+  for (int jj = 0; jj < kChunksPerTask / NW; ++jj) {
+    const int j = jj * NW + warp;
     const int g = it * kChunksPerTask + j;
     const int sl = g % NS;
     const int use = g / NS;
     const ChunkCoord k = chunk_coord(j);
+    if (warp == 0 && lane == 0 && jj == 0) STEM_TS(0);
     mbar_wait(stg_full + sl, use & 1);
+    if (warp == 0 && lane == 0 && jj == 0) STEM_TS(1);
     const uint8_t* slot = sStage + sl * kSlotBytes;
     // kKH rows x kQPR quads, fully unrolled: all shared loads are issued before the first convert
     float v[kKH][2][4];
@@ -168,6 +194,10 @@ __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abu
       if (lane + 32 < kQPR) Px4<TIn>::load(slot, r * kQPR + lane + 32, v[r][1]);
     }
     uint8_t* dst0 = abuf + ((k.c * p.K + k.rg * kKH) * 2 + k.img) * kRowBytes + (k.half * (p.Win / 2) + p.pad) * 2;
+    // Row-group hand-off (forward): the 5 A rows of group (c, rg) may be overwritten as soon as the 5 MMAs of the
+    // PREVIOUS task that read them have completed -- not only after all 30.
+    if (grp_empty != nullptr) mbar_wait(grp_empty + k.c * 2 + k.rg, (it & 1) ^ 1);
+    if (warp == 0 && lane == 0 && jj == 0) STEM_TS(2);
     // global bf16 copy (forward only): row y of plane (pair, c), image slot img
     const int pair = task / p.Ho, oy = task - pair * p.Ho;
     const int y0 = oy * p.stride - p.pad + k.rg * kKH;
@@ -200,19 +230,25 @@ __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abu
         }
       }
     }
+    if (grp_full != nullptr) fence_proxy_async();     // A rows (generic proxy) -> visible to the tensor core
     __syncwarp();
-    if (lane == 0) mbar_arrive(stg_empty + sl);
+    if (lane == 0) {
+      mbar_arrive(stg_empty + sl);
+      if (grp_full != nullptr) mbar_arrive(grp_full + k.c * 2 + k.rg);
+    }
+    if (warp == 0 && lane == 0) STEM_TS(jj == 0 ? 3 : 4);
   }
 }
 
 struct StrideSched { int begin, end, step; };
 
+
 // ------------------------------------------------------------------------------------- forward
 // smem: [weights CK*2048][A tile (single stage)][slack 128][16 staging slots][barriers]
-constexpr int kFwdSlots = 16;
+constexpr int kFwdSlots = 16;               // 2 per converter warp (slot = chunk % 16, warp = chunk % 8)
 constexpr int kWgSlots = 8;
 template <typename TIn>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -228,17 +264,23 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   uint64_t* stg_full = bars + 8;               // [kFwdSlots]
   uint64_t* stg_empty = bars + 8 + kFwdSlots;  // [kFwdSlots]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kFwdSlots);
+  // The A tile is handed over per ROW GROUP g = (c, rg) = 5 of the 30 (c,ky) rows x 2 images (4 chunks, 4 converter
+  // warps): grp_full[g] (count 4) releases the 5 MMAs of the group, grp_empty[g] (their commit) lets the converters
+  // refill those rows for the next task.  With one barrier for the whole tile the converters idled during the 30
+  // MMAs, the staging ring filled up, and every task exposed one HBM round trip (11 k clk per task, 74 us).
+  uint64_t* grp_full = bars + 8 + 2 * kFwdSlots + 2;     // [6]
+  uint64_t* grp_empty = grp_full + 6;                    // [6]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // one-time: zero the A stages (pad columns stay zero forever) and build the bf16 weight operand
-  for (uint32_t i = threadIdx.x * 16u; i < p.a_bytes + 128; i += kThreads * 16u)
+  for (uint32_t i = threadIdx.x * 16u; i < p.a_bytes + 128; i += kFwdThreads * 16u)
     *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
   {
     // B operand per (c,ky): [k1 2][co 64][k0 8] bf16  (K-major, no swizzle: LBO = 1024, SBO = 128)
     __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(sW);
     const int KK = p.CK * p.K;
-    for (int i = threadIdx.x; i < p.CK * 1024; i += kThreads) {
+    for (int i = threadIdx.x; i < p.CK * 1024; i += kFwdThreads) {
       const int k0 = i & 7, co = (i >> 3) & 63, k1 = (i >> 9) & 1, cky = i >> 10;
       const int kx = k1 * 8 + k0;
       const float v = kx < p.K ? p.w[static_cast<size_t>(co) * KK + cky * p.K + kx] : 0.f;
@@ -248,8 +290,12 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
-    mbar_init(a_full, kLoaderWarps);
+    mbar_init(a_full, kFwdLoaders);
     mbar_init(a_empty, 1);
+    for (int g = 0; g < 6; ++g) {
+      mbar_init(grp_full + g, 4);
+      mbar_init(grp_empty + g, 1);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full + s, 1);
       mbar_init(acc_empty + s, 4);
@@ -260,7 +306,7 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
     }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) {
+  if (warp == kFwdMmaWarp) {
     tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
@@ -271,37 +317,42 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   pdl_trigger();
   pdl_wait();
 
-  if (warp < kLoaderWarps) {
+  if (warp < kFwdLoaders) {
     int it = 0;
     for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
-      // single A stage: the deep staging ring keeps HBM busy while the 30 MMAs of the previous task drain
-      mbar_wait(a_empty, (it & 1) ^ 1);
-      convert_chunks<TIn, kFwdSlots>(p, sA, sStage, stg_full, stg_empty, it, warp, lane, task);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full);
+      // single A stage, handed over per row group (see grp_full / grp_empty above)
+      convert_chunks<TIn, kFwdSlots, kFwdLoaders>(p, sA, sStage, stg_full, stg_empty, it, warp, lane, task, grp_full, grp_empty);
     }
-  } else if (warp == kTmaWarp) {
+  } else if (warp == kFwdTmaWarp) {
     produce_chunks<kFwdSlots>(p, &tm_x, sStage, stg_full, stg_empty,
                               StrideSched{static_cast<int>(blockIdx.x), p.ntask, static_cast<int>(gridDim.x)}, lane);
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kFwdMmaWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(128, kCo, 0, 0);
     const uint32_t w_addr = smem_u32(sW);
     int it = 0;
     for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       mbar_wait(acc_empty + s, ph ^ 1);
-      mbar_wait(a_full, it & 1);
       tc_fence_after();
       if (elect_one_sync()) {
+        STEM_TS(5);
         const uint64_t ad0 = make_sdesc_none(smem_u32(sA), 16, 128);
         const uint64_t bd0 = make_sdesc_none(w_addr, 1024, 128);
-#pragma unroll 6
-        for (int cky = 0; cky < p.CK; ++cky)    // +2048 B per (c,ky) on both operands = +128 in the address field
-          umma_bf16(tmem_base + s * kCo, ad0 + static_cast<uint64_t>(cky * 128), bd0 + static_cast<uint64_t>(cky * 128),
-                    idesc, cky != 0 ? 1u : 0u);
-        umma_commit(a_empty);
+#pragma unroll 1
+        for (int g = 0; g < 6; ++g) {
+          mbar_wait(grp_full + g, it & 1);
+          if (g == 0) STEM_TS(6);
+          tc_fence_after();
+#pragma unroll
+          for (int r = 0; r < kKH; ++r) {       // +2048 B per (c,ky) on both operands = +128 in the address field
+            const int cky = g * kKH + r;
+            umma_bf16(tmem_base + s * kCo, ad0 + static_cast<uint64_t>(cky * 128), bd0 + static_cast<uint64_t>(cky * 128),
+                      idesc, cky != 0 ? 1u : 0u);
+          }
+          umma_commit(grp_empty + g);            // these 5 A rows may be refilled
+        }
         umma_commit(acc_full + s);
+        STEM_TS(7);
       }
       __syncwarp();
     }
@@ -312,6 +363,7 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
       const int s = it & 1, ph = (it >> 1) & 1;
       const int pair = task / p.Ho, oy = task % p.Ho;
       mbar_wait(acc_full + s, ph);
+      if (q == 0 && lane == 0) STEM_TS(8);
       tc_fence_after();
       const int r = q * 32 + lane;
       const int img = r >> 6, ox = r & 63;
@@ -344,11 +396,12 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + s);
+      if (q == 0 && lane == 0) STEM_TS(9);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 128);
+  if (warp == kFwdMmaWarp) tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------- weight gradient
@@ -698,6 +751,7 @@ int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, i
   p.w = w; p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.xbf = reinterpret_cast<__nv_bfloat16*>(xbf);
   p.elem_bytes = x_is_u8 ? 1 : 4;
+  { const char* d = getenv("FD_STEM_TIMING"); p.dbg = d ? atoi(d) : 0; }
   CUtensorMap tm_x;
   {
     int rc = make_tmap_image(&tm_x, x, x_is_u8, B * Cin, Hin, Win, K);
@@ -710,11 +764,11 @@ int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, i
   if (x_is_u8) {
     e = cudaFuncSetAttribute(stem_fwd_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = launch_k(stem_fwd_tc_kernel<uint8_t>, dim3(grid), dim3(kThreads), smem, st, tm_x, p);
+    e = launch_k(stem_fwd_tc_kernel<uint8_t>, dim3(grid), dim3(kFwdThreads), smem, st, tm_x, p);
   } else {
     e = cudaFuncSetAttribute(stem_fwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = launch_k(stem_fwd_tc_kernel<float>, dim3(grid), dim3(kThreads), smem, st, tm_x, p);
+    e = launch_k(stem_fwd_tc_kernel<float>, dim3(grid), dim3(kFwdThreads), smem, st, tm_x, p);
   }
   count_launch();
   return launch_status();
@@ -771,3 +825,7 @@ int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, 
 }
 
 }  // namespace fd
+
+extern "C" FD_API int fd_debug_stem_timing(unsigned long long* out, int n) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, fd::g_stem_dbg, sizeof(unsigned long long) * n));
+}

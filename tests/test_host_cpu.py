@@ -92,3 +92,23 @@ def test_flat_parameter_layout():
     for name, (off, n, shape) in eng.offsets.items():
         assert off % 4 == 0
     assert len(eng.param_names()) == 44
+
+
+def test_div255_fma_sequence_is_the_ieee_quotient():
+    """csrc/stem_tc.cu Px4<uint8_t>::div255 replaces `x / 255.0f` (models/PoolResnet.py:95) by q = x * (1/255),
+    q' = fma(fma(-q, 255, x), 1/255, q).  Emulated here in exact arithmetic (fp64 holds the fp32 products exactly):
+    bit-identical to the fp32 division for all 256 uint8 inputs, while the plain reciprocal multiply is not."""
+    import numpy as np
+    f = np.float32
+    v = np.arange(256, dtype=np.float32)
+    want = (v / f(255.0)).astype(np.float32)
+    r = f(1.0) / f(255.0)
+    q = (v * r).astype(np.float32)
+
+    def fma(a, b, c):
+        return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
+
+    e = np.array([fma(-q[i], f(255.0), v[i]) for i in range(256)], dtype=np.float32)
+    q2 = np.array([fma(e[i], r, q[i]) for i in range(256)], dtype=np.float32)
+    assert (q2 == want).all()
+    assert (q != want).any()

@@ -24,7 +24,7 @@ buf = (ctypes.c_ulonglong * n)()
 L = fd.native.lib()
 L.fd_debug_sep_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert L.fd_debug_sep_timing(buf, n) == 0
-names = ["start", "store_drained", "pw1_issued", "acc1_ready", "dw_start", "pw2_phase", "acc2_ready", "epiB_done"]
+names = ["start", "x_tile_ready", "pw1_issued", "acc1_ready", "dw_start", "pw2_phase", "acc2_ready", "epiB_done"]
 print("tile", *[f"{s:>14s}" for s in names[1:]], "  next_start")
 for it in range(1, 12):
     t = [buf[it * 8 + k] for k in range(8)]
