@@ -982,6 +982,11 @@ extern "C" int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const flo
                                static_cast<cudaStream_t>(stream));
     if (rc != FD_EUNSUPPORTED) return rc;      // tensor-core stem handled it (or failed for real)
   }
+  {
+    const int rc = stem_s2_fwd_tc(x, x_is_u8, w, bias, B, Cin, Hin, Win, C, K, stride, pad, y,
+                                  static_cast<cudaStream_t>(stream));
+    if (rc != FD_EUNSUPPORTED) return rc;      // the standard Resnet's 3x3 / stride-2 stem
+  }
   const int Ho = (Hin + 2 * pad - K) / stride + 1, Wo = (Win + 2 * pad - K) / stride + 1;
   const int KK = Cin * K * K, pitch = (Wo - 1) * stride + K + 1;
   const size_t smem = (static_cast<size_t>(KK) * C + static_cast<size_t>(Cin) * K * pitch) * sizeof(float);
@@ -1012,6 +1017,11 @@ extern "C" int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B
   {
     const int rc = stem_wgrad_tc(x, x_is_u8, g, B, Cin, Hin, Win, C, K, stride, pad, dw, dbias, x_cache,
                                  static_cast<cudaStream_t>(stream));
+    if (rc != FD_EUNSUPPORTED) return rc;
+  }
+  {
+    const int rc = stem_s2_wgrad_tc(x, x_is_u8, g, B, Cin, Hin, Win, C, K, stride, pad, dw, dbias,
+                                    static_cast<cudaStream_t>(stream));
     if (rc != FD_EUNSUPPORTED) return rc;
   }
   const int KK = Cin * K * K;

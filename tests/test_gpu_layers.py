@@ -271,3 +271,42 @@ def test_flat_adam_device_step_count_replays_from_a_graph():
     assert state[:2].tolist() == [5, 0]
     assert (p - ref.detach()).abs().max().item() <= 2e-6
     assert rel_err(p - p0, ref.detach() - p0) <= 1e-5
+
+
+@pytest.mark.parametrize("u8,B,Hin,Win", [(False, 3, 480, 480), (True, 2, 480, 480), (False, 5, 62, 100), (False, 1, 7, 8)])
+def test_stem_stride2_tensor_core_fwd_wgrad(u8, B, Hin, Win):
+    """Stem of the standard Resnet (models/Resnet.py:64-70: 3x3, stride 2, pad 1, 3 -> 64) on tcgen05 (csrc/stem_s2_tc.cu):
+    forward (bias rides on the ones column of the in-smem im2col tile) and weight / bias gradient against torch fp32.
+    The image and the weights are rounded to bf16 on the way into shared memory: bf16 tolerance against the fp32
+    reference, fp32-accumulation tolerance against the same convolution on the rounded operands."""
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(B * 100 + Win)
+    dev = "cuda"
+    if u8:
+        x = torch.randint(0, 256, (B, 3, Hin, Win), dtype=torch.uint8, device=dev)
+        xf = x.float() / 255.0
+    else:
+        x = torch.rand(B, 3, Hin, Win, device=dev)
+        xf = x
+    w = (torch.randn(C, 3, 3, 3, device=dev) * 0.2).requires_grad_(True)
+    b = torch.randn(C, device=dev).requires_grad_(True)
+    Ho, Wo = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1
+    y = torch.full((B, Ho, Wo, C), float("nan"), dtype=torch.bfloat16, device=dev)
+    ops.stem_fwd(x, w.detach(), b.detach(), y, 2, 1)
+    ref = F.conv2d(xf, w, b, stride=2, padding=1)
+    assert tuple(ref.shape) == (B, C, Ho, Wo)
+    _close(y, ref.detach().permute(0, 2, 3, 1), "stem s2 fwd", rel=6e-3, mx=2e-2)
+    ref_r = F.conv2d(xf.bfloat16().float(), w.detach().bfloat16().float(), b.detach().bfloat16().float(), stride=2, padding=1)
+    assert rel_err(y.float(), ref_r.permute(0, 2, 3, 1).bfloat16().float()) <= 2e-3
+    g = (torch.randn(B, Ho, Wo, C, device=dev) * 0.1).bfloat16()
+    dw = torch.zeros(C, 3, 3, 3, device=dev); dbias = torch.zeros(C, device=dev)
+    ops.stem_wgrad(x, g, dw, dbias, 2, 1)
+    ref.backward(g.float().permute(0, 3, 1, 2))
+    assert rel_err(dw, w.grad) <= 4e-3 and rel_err(dbias, b.grad) <= 1e-4
+    wz = torch.zeros_like(w).requires_grad_(True)
+    (dref,) = torch.autograd.grad(F.conv2d(xf.bfloat16().float(), wz, None, stride=2, padding=1), wz,
+                                  g.float().permute(0, 3, 1, 2))
+    assert rel_err(dw, dref) <= 1e-4
+    ops.stem_wgrad(x, g, dw, dbias, 2, 1)            # accumulates
+    assert rel_err(dw, 2 * dref) <= 1e-4
