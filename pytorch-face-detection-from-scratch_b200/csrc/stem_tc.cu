@@ -32,17 +32,20 @@ constexpr int kMmaWarp = kLoaderWarps;      // MMA issuer + TMEM owner
 constexpr int kTmaWarp = kLoaderWarps + 1;  // TMA producer of the image chunks
 constexpr int kEpiWarp0 = kLoaderWarps + 2; // 4 epilogue warps (10..13 -> TMEM quadrants 2,3,0,1)
 constexpr int kThreads = (kLoaderWarps + 2 + 4) * 32;   // 448
-// Converter warps of the forward.  Measured (FD_STEM_TIMING=1, tools/stem_debug.py): a converter warp needs ~2000 clk
-// per chunk once its data has landed, 3 chunks per task in sequence -> 7500 clk per task, 2.4 TB/s: the converters,
-// not HBM, set the pace.  Every warp needs >= 2 staging slots of its own (one converting, one in flight: with 12
-// warps x 1 slot the HBM round trip is exposed per chunk, 79 us) and a slot must always be drained by the SAME warp
-// (mbarrier parity waits only distinguish adjacent phases: 24 warps sharing 16 slots -> launch failure), so the
-// 227 KB of shared memory (61 KB weights + 61 KB A tile) allow 8 warps x 2 slots.
-constexpr int kFwdLoaders = 8;
+// Converter warps of the forward.  Measured (FD_STEM_TIMING=1, tools/stem_debug.py) history of this kernel:
+//  * the converters set the pace, not HBM: ~1400-2800 clk per chunk (TMA wait, dependent LDS -> F2FP -> STS/STG
+//    chains, hand-over of the A rows), 3 chunks per warp with 8 warps = 7500 clk per task = 74 us;
+//  * every converter warp now issues the TMA for ITS OWN slot right after it has pulled the slot's data into
+//    registers (program order = the hand-shake: no "empty" barrier, no producer warp whose per-lane issues
+//    serialise), division-free;
+//  * 16 converter warps, one slot each (slot = chunk % 16 = warp; warps 0..7 drain chunks j and j + 16 of a task).
+//    A slot must always be drained by the SAME warp: mbarrier parity waits only distinguish adjacent phases
+//    (24 warps sharing 16 slots: launch failure).
+constexpr int kFwdLoaders = 16;
 constexpr int kFwdMmaWarp = kFwdLoaders;
 constexpr int kFwdTmaWarp = kFwdLoaders + 1;
-constexpr int kFwdEpiWarp0 = kFwdLoaders + 2;           // 10..13 -> TMEM quadrants 2,3,0,1
-constexpr int kFwdThreads = (kFwdLoaders + 2 + 4) * 32; // 448
+constexpr int kFwdEpiWarp0 = kFwdLoaders + 2;           // 18..21 -> TMEM quadrants 2,3,0,1
+constexpr int kFwdThreads = (kFwdLoaders + 2 + 4) * 32; // 704
 constexpr int kSlotBytes = 4864;            // one staging slot: K/2 rows x Win/2 pixels (<= 4800 B), 128B aligned
 constexpr int kChunksPerTask = 24;          // 3 ch x 2 img x 2 row groups x 2 column halves
 constexpr int kKH = 5;                      // rows per chunk  (K = 10)
@@ -170,19 +173,35 @@ __device__ __forceinline__ void produce_chunks(const StemParams& p, const CUtens
   }
 }
 
+// Self-service TMA of the forward: chunk j of the task (pair, oy) into staging slot `slot`.  Called by ONE elected
+// lane of the converter warp that owns the slot, after it has emptied the slot.  No divisions on this path: it sits in
+// the converters' critical loop (measured 550 clk per issue with the chunk number decoded by / and %).
+__device__ __forceinline__ void issue_chunk(const StemParams& p, const CUtensorMap* tm_x, uint8_t* sStage,
+                                            uint64_t* stg_full, int j, int pair, int oy, int slot) {
+  const ChunkCoord k = chunk_coord(j);
+  mbar_expect_tx(stg_full + slot, static_cast<uint32_t>((p.K / 2) * (p.Win / 2) * p.elem_bytes));
+  tma_load_3d(sStage + slot * kSlotBytes, tm_x, stg_full + slot, k.half * (p.Win / 2),
+              oy * p.stride - p.pad + k.rg * (p.K / 2), (pair * 2 + k.img) * p.Cin + k.c);
+}
+
 // Converter warp `warp`: its chunks of task iteration `it` -> A tile `abuf`.
 template <typename TIn, int NS, int NW = kLoaderWarps>
 __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abuf, const uint8_t* sStage,
                                                uint64_t* stg_full, uint64_t* stg_empty, int it, int warp, int lane,
-                                               int task = 0, uint64_t* grp_full = nullptr, uint64_t* grp_empty = nullptr) {
+                                               int task = 0, uint64_t* grp_full = nullptr, uint64_t* grp_empty = nullptr,
+                                               const CUtensorMap* self_tm = nullptr, int next_pair = -1, int next_oy = 0) {
+  const int task_pair = task / p.Ho, task_oy = task - task_pair * p.Ho;
+  // NS == NW == 16 (forward): slot = chunk % 16 = the owning warp, warps 0..7 drain two chunks per task (j, j + 16)
+  constexpr bool kOwnSlot = (NS == 16 && NW == 16);
 #pragma unroll 1
-  for (int jj = 0; jj < kChunksPerTask / NW; ++jj) {
-    const int j = jj * NW + warp;
+  for (int j = warp; j < kChunksPerTask; j += NW) {
+    const int jj = j / NW;
     const int g = it * kChunksPerTask + j;
-    const int sl = g % NS;
-    const int use = g / NS;
+    const int sl = kOwnSlot ? (j & 15) : g % NS;
+    const int use = kOwnSlot ? ((j & 15) < 8 ? 2 * it + (j >> 4) : it) : g / NS;
     const ChunkCoord k = chunk_coord(j);
     if (warp == 0 && lane == 0 && jj == 0) STEM_TS(0);
+    if (warp == 0 && lane == 0 && jj == 1) STEM_TS(15);
     mbar_wait(stg_full + sl, use & 1);
     if (warp == 0 && lane == 0 && jj == 0) STEM_TS(1);
     const uint8_t* slot = sStage + sl * kSlotBytes;
@@ -193,13 +212,39 @@ __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abu
       Px4<TIn>::load(slot, r * kQPR + lane, v[r][0]);
       if (lane + 32 < kQPR) Px4<TIn>::load(slot, r * kQPR + lane + 32, v[r][1]);
     }
+    // The staging slot is free as soon as its data sits in registers: release it NOW so that the producer's next TMA
+    // into this slot overlaps the conversion and the stores below (released at the end of the chunk, the HBM round
+    // trip of the next chunk was exposed).  The MOVs make every lane wait for its last (in-order) shared load.
+    {
+      uint32_t sink;
+      asm volatile("mov.b32 %0, %1;" : "=r"(sink) : "r"(__float_as_uint(v[kKH - 1][0][3])) : "memory");
+      if (lane + 32 < kQPR) asm volatile("mov.b32 %0, %1;" : "=r"(sink) : "r"(__float_as_uint(v[kKH - 1][1][3])) : "memory");
+      __syncwarp();
+      if (warp == 0 && lane == 0 && jj == 1) STEM_TS(10);
+      if (self_tm != nullptr) {
+        // the next user of this slot is chunk j + NS of this task, or chunk j + NS - 24 of the CTA's next task
+        if (elect_one_sync()) {
+          if (j + NS < kChunksPerTask) {
+            issue_chunk(p, self_tm, const_cast<uint8_t*>(sStage), stg_full, j + NS, task_pair, task_oy, sl);
+          } else if (next_pair >= 0) {
+            issue_chunk(p, self_tm, const_cast<uint8_t*>(sStage), stg_full, kOwnSlot ? (j & 15) : j + NS - kChunksPerTask,
+                        next_pair, next_oy, sl);
+          }
+        }
+        __syncwarp();
+      } else if (lane == 0) {
+        mbar_arrive(stg_empty + sl);
+      }
+      if (warp == 0 && lane == 0 && jj == 1) STEM_TS(11);
+    }
     uint8_t* dst0 = abuf + ((k.c * p.K + k.rg * kKH) * 2 + k.img) * kRowBytes + (k.half * (p.Win / 2) + p.pad) * 2;
     // Row-group hand-off (forward): the 5 A rows of group (c, rg) may be overwritten as soon as the 5 MMAs of the
     // PREVIOUS task that read them have completed -- not only after all 30.
     if (grp_empty != nullptr) mbar_wait(grp_empty + k.c * 2 + k.rg, (it & 1) ^ 1);
     if (warp == 0 && lane == 0 && jj == 0) STEM_TS(2);
+    if (warp == 0 && lane == 0 && jj == 1) STEM_TS(14);
     // global bf16 copy (forward only): row y of plane (pair, c), image slot img
-    const int pair = task / p.Ho, oy = task - pair * p.Ho;
+    const int pair = task_pair, oy = task_oy;
     const int y0 = oy * p.stride - p.pad + k.rg * kKH;
     uint8_t* gdst0 = p.xbf == nullptr ? nullptr
                                       : reinterpret_cast<uint8_t*>(p.xbf) +
@@ -230,12 +275,11 @@ __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abu
         }
       }
     }
+    if (warp == 0 && lane == 0 && jj == 1) STEM_TS(12);
     if (grp_full != nullptr) fence_proxy_async();     // A rows (generic proxy) -> visible to the tensor core
+    if (warp == 0 && lane == 0 && jj == 1) STEM_TS(13);
     __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(stg_empty + sl);
-      if (grp_full != nullptr) mbar_arrive(grp_full + k.c * 2 + k.rg);
-    }
+    if (lane == 0 && grp_full != nullptr) mbar_arrive(grp_full + k.c * 2 + k.rg);
     if (warp == 0 && lane == 0) STEM_TS(jj == 0 ? 3 : 4);
   }
 }
@@ -245,7 +289,7 @@ struct StrideSched { int begin, end, step; };
 
 // ------------------------------------------------------------------------------------- forward
 // smem: [weights CK*2048][A tile (single stage)][slack 128][16 staging slots][barriers]
-constexpr int kFwdSlots = 16;               // 2 per converter warp (slot = chunk % 16, warp = chunk % 8)
+constexpr int kFwdSlots = 16;               // one per converter warp
 constexpr int kWgSlots = 8;
 template <typename TIn>
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -318,14 +362,23 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   pdl_wait();
 
   if (warp < kFwdLoaders) {
+    // prologue: this warp's first two chunks (slots warp and warp + 8); afterwards every chunk's successor in the same
+    // slot is issued by convert_chunks itself
+    if (lane == 0 && static_cast<int>(blockIdx.x) < p.ntask) {
+      const int pair0 = blockIdx.x / p.Ho, oy0 = blockIdx.x - pair0 * p.Ho;
+      issue_chunk(p, &tm_x, sStage, stg_full, warp, pair0, oy0, warp);        // one slot per warp: its first chunk
+    }
+    __syncwarp();
     int it = 0;
     for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
       // single A stage, handed over per row group (see grp_full / grp_empty above)
-      convert_chunks<TIn, kFwdSlots, kFwdLoaders>(p, sA, sStage, stg_full, stg_empty, it, warp, lane, task, grp_full, grp_empty);
+      const int nt = task + gridDim.x;
+      const int np = nt < p.ntask ? nt / p.Ho : -1;
+      convert_chunks<TIn, kFwdSlots, kFwdLoaders>(p, sA, sStage, stg_full, stg_empty, it, warp, lane, task, grp_full,
+                                                  grp_empty, &tm_x, np, nt - np * p.Ho);
     }
   } else if (warp == kFwdTmaWarp) {
-    produce_chunks<kFwdSlots>(p, &tm_x, sStage, stg_full, stg_empty,
-                              StrideSched{static_cast<int>(blockIdx.x), p.ntask, static_cast<int>(gridDim.x)}, lane);
+    // (idle: the converter warps issue their own TMA loads)
   } else if (warp == kFwdMmaWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(128, kCo, 0, 0);
     const uint32_t w_addr = smem_u32(sW);

@@ -26,8 +26,8 @@ L = fd.native.lib()
 L.fd_debug_stem_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert L.fd_debug_stem_timing(buf, n) == 0
 names = ["cv_wait_stg", "cv_stg_ok", "cv_grp_ok", "cv_chunk0_end", "cv_task_end", "mma_start", "mma_grp0_ok", "mma_issued",
-         "epi_acc_ok", "epi_end", "tma_start", "tma_batch0", "tma_batch1"]
+         "epi_acc_ok", "epi_end", "c1_regs", "c1_tma", "c1_stored", "c1_fenced", "c1_grp_ok", "c1_start"]
 t00 = buf[1 * 16 + 0]
 print("task " + " ".join(f"{s:>13s}" for s in names))
 for it in range(1, 9):
-    print(f"{it:4d} " + " ".join(f"{buf[it * 16 + k] - t00:13d}" for k in range(13)))
+    print(f"{it:4d} " + " ".join(f"{buf[it * 16 + k] - t00:13d}" for k in range(16)))
