@@ -73,4 +73,9 @@ int stem_s2_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias
 int stem_s2_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C, int K,
                      int stride, int pad, float* dw, float* dbias, cudaStream_t st);
 
+// tcgen05 backward of the 64 -> 5 head (head_tc.cu); FD_EUNSUPPORTED = shape not instantiated
+int head_bwd_tc(const fd_bf16* x, const float* chan_scale, const float* w, const float* y, const float* dy, int B, int H,
+                int W, int C, int K, int pad, fd_bf16* dx, const uint32_t* mask_bits, const float* chan_scale2, float slope,
+                fd_bf16* dx2, float* dw, float* dbias, cudaStream_t st);
+
 }  // namespace fd

@@ -3,6 +3,7 @@
 // each forward and backward.  All are memory- or latency-bound; the tensor-core work lives in
 // conv3x3_tc.cu / wgrad3x3_tc.cu.
 #include <cmath>
+#include <cstdlib>
 
 #include "fd_host.h"
 #include "fd_ptx.cuh"
@@ -1101,6 +1102,14 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
   if ((H * W * C) % 8 != 0 || kHeadThreads % C != 0) return FD_EUNSUPPORTED;
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
+  {
+    static const bool cuda_core_only = std::getenv("FD_HEAD_BWD_CUDA_CORES") != nullptr;     // A/B switch for tests
+    if (!cuda_core_only) {
+      const int rc = head_bwd_tc(x, chan_scale, w, y, dy, B, H, W, C, K, pad, dx, mask_bits, chan_scale2, slope, dx2, dw,
+                                 dbias, static_cast<cudaStream_t>(stream));
+      if (rc != FD_EUNSUPPORTED) return rc;      // the tensor-core kernel handled it (or failed for real)
+    }
+  }
   if (w_t && C == 64 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
     const int KK = K * K, dw_parts = (KK + kDwTaps - 1) / kDwTaps;
     const int strips = (W + kHeadStrip - 1) / kHeadStrip;

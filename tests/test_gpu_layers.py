@@ -192,9 +192,20 @@ def test_head_fwd_bwd(H, K, pad):
     ops.head_bwd(x, cs, w.detach(), y, dy, pad, dx, _bits(msk), cs2, 0.2, dx2, dw, dbias, w_t=wt)
     ref.backward(dy)
     gx = xin.grad.permute(0, 2, 3, 1)
-    _close(dx, gx, "head dx")
-    _close(dx2, gx * cs2[:, None, None, :] * torch.where(msk.float() > 0, 1.0, 0.2), "head dx2", rel=6e-3)
-    assert rel_err(dw, w.grad) <= 1e-4 and rel_err(dbias, b.grad) <= 1e-4
+    # tensor-core backward (csrc/head_tc.cu): dz and the weights enter the MMAs in bf16 -> bf16 tolerance
+    _close(dx, gx, "head dx", rel=6e-3)
+    _close(dx2, gx * cs2[:, None, None, :] * torch.where(msk.float() > 0, 1.0, 0.2), "head dx2", rel=8e-3)
+    print("head dw rel", rel_err(dw, w.grad), "dbias rel", rel_err(dbias, b.grad))
+    assert rel_err(dw, w.grad) <= 4e-3 and rel_err(dbias, b.grad) <= 1e-4
+    # ... and against the same gradients computed in fp32 from the bf16-rounded dz / weights: accumulation-order level
+    dz = (dy * y * (1 - y)).bfloat16().float()
+    xs = (x.float() * cs[:, None, None, :]).permute(0, 3, 1, 2)
+    dw_r = torch.nn.grad.conv2d_weight(xs, w.shape, dz, padding=pad)
+    dx_r = torch.nn.grad.conv2d_input(xin.shape, w.detach().bfloat16().float(), dz, padding=pad) * cs[:, :, None, None]
+    assert rel_err(dw, dw_r) <= 1e-4
+    assert rel_err(dx.float(), dx_r.permute(0, 2, 3, 1).bfloat16().float()) <= 2e-3
+    ops.head_bwd(x, cs, w.detach(), y, dy, pad, dx, _bits(msk), cs2, 0.2, dx2, dw, dbias, w_t=wt)    # accumulates
+    assert rel_err(dw, 2 * dw_r) <= 1e-4
 
 
 def test_maxpool_fwd_bwd_first_max_tie_rule():
