@@ -186,6 +186,18 @@ extern "C" int fd_comm_release(void* peer_ptr) {
 
 extern "C" int fd_comm_error_offset(void) { return kErrWord * 4; }
 
+// Status word of the LOCAL window: 0 = every barrier of every call completed; 1 + r = a wait on rank r ran into the
+// 4 s spin limit (the peer died or never launched its kernel) and the sums of that call are garbage.  Synchronises the
+// device (host-side health check, not on the data path).
+extern "C" int fd_comm_status(void* window, int* status) {
+  if (!window || !status) return FD_EINVAL;
+  unsigned v = 0;
+  cudaError_t e = cudaMemcpy(&v, static_cast<unsigned char*>(window) + kErrWord * 4, 4, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+  *status = static_cast<int>(v);
+  return FD_OK;
+}
+
 extern "C" int fd_allreduce_sum_f32(void* const* windows, int rank, int world, float* data, long n, void* stream) {
   if (!windows || !data || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || n <= 0) return FD_EINVAL;
   if (n % 4 != 0) return FD_EUNSUPPORTED;

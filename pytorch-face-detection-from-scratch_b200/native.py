@@ -32,6 +32,7 @@ SIGNATURES = {
     "fd_adam_flat": [_P, _P, _P, _P, _c.c_long, _F, _F, _F, _F, _F, _I, _P, _P],
     "fd_comm_window_bytes": [_c.c_long, _I],
     "fd_comm_error_offset": [],
+    "fd_comm_status": [_P, _P],
     "fd_comm_alloc": [_c.c_long, _P],
     "fd_comm_free": [_P],
     "fd_comm_export": [_P, _P],

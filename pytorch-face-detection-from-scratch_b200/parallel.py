@@ -106,10 +106,21 @@ class PeerAllReduce:
                                          cur_stream()), "fd_allreduce_sum_f32")
         return flat
 
+    def status(self) -> int:
+        """0 = every exchange completed; 1 + r = a wait on rank r timed out (the peer died or never launched)."""
+        from .native import check, lib
+        st = ctypes.c_int(0)
+        check(lib().fd_comm_status(self._own, ctypes.byref(st)), "fd_comm_status")
+        return int(st.value)
+
     def close(self):
         from .native import lib
         L = lib()
         torch.cuda.synchronize()
+        bad = self.status()
+        if bad:
+            raise RuntimeError(f"peer all-reduce: rank {self.rank} timed out waiting for rank {bad - 1}; "
+                               "gradients of at least one step were not reduced")
         if dist.is_initialized():
             dist.barrier()                                   # nobody unmaps a window a peer may still write
         for r, w in enumerate(self._windows):

@@ -67,6 +67,7 @@ def _worker(rank, world, port, ndev, q):
             for r in range(1, world):
                 want = want + _data(r, call, n)
             ok = ok and torch.equal(flat.cpu(), want)
+        ok = ok and ar.status() == 0
         ar.close()
         dist.destroy_process_group()
         q.put((rank, "ok" if ok else "mismatch"))
