@@ -49,31 +49,61 @@ __device__ __forceinline__ float div255(unsigned char b) {
   return fmaf(fmaf(-q, 255.0f, x), r, q);
 }
 
-// 9 input rows (c, ky) of output row oy -> sRows[r][kRowElems] bf16, element j = input column j - 2 (zeros outside)
+// 9 input rows (c, ky) of output row oy -> sRows[r][kRowElems] bf16, element j = input column j - 2 (zeros outside).
+// All global loads of a thread are issued before the first conversion (5 independent 16-byte loads in flight per
+// thread; a rolled load -> convert -> store loop exposed one HBM round trip per iteration: 4000 clk per task).
+constexpr int kStageIters = (9 * (kRowElems / 4) + kBuildWarps * 32 - 1) / (kBuildWarps * 32);      // 5 for Win <= 512
 template <typename TIn>
 __device__ __forceinline__ void stage_rows(const S2Params& p, int n, int oy, uint8_t* sRows, int tid) {
   const int quads = p.Win >> 2;
-  for (int idx = tid; idx < 9 * quads; idx += kBuildWarps * 32) {
-    const int r = idx / quads, qd = idx - r * quads;
-    const int c = r / 3, ky = r - c * 3;
-    const int iy = 2 * oy + ky - 1;
+  const int total = 9 * quads;
+  uint4 raw[kStageIters];
+  int dst[kStageIters];
+#pragma unroll
+  for (int t = 0; t < kStageIters; ++t) {
+    const int idx = tid + t * kBuildWarps * 32;
+    dst[t] = -1;
+    raw[t] = make_uint4(0, 0, 0, 0);
+    if (idx < total) {
+      const int r = idx / quads, qd = idx - r * quads;
+      const int c = r / 3, ky = r - c * 3;
+      const int iy = 2 * oy + ky - 1;
+      dst[t] = r * (kRowElems * 2) + (4 * qd + 2) * 2;
+      if (iy >= 0 && iy < p.Hin) {
+        const size_t off = ((static_cast<size_t>(n) * 3 + c) * p.Hin + iy) * p.Win + 4 * qd;
+        if constexpr (sizeof(TIn) == 4) {
+          raw[t] = __ldg(reinterpret_cast<const uint4*>(static_cast<const float*>(p.x) + off));
+        } else {
+          raw[t].x = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.x) + off));
+          raw[t].y = 1u;            // marks "loaded" for the uint8 path (a zero word is a valid pixel quad)
+        }
+      } else {
+        dst[t] = -2 - dst[t];       // out-of-image row: store zeros
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kStageIters; ++t) {
+    if (dst[t] == -1) continue;
     uint32_t a0 = 0, a1 = 0;
-    if (iy >= 0 && iy < p.Hin) {
-      const size_t off = ((static_cast<size_t>(n) * 3 + c) * p.Hin + iy) * p.Win + 4 * qd;
+    int d = dst[t];
+    if (d >= 0) {
       float v0, v1, v2, v3;
       if constexpr (sizeof(TIn) == 4) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + off));
-        v0 = f.x; v1 = f.y; v2 = f.z; v3 = f.w;
+        v0 = __uint_as_float(raw[t].x); v1 = __uint_as_float(raw[t].y);
+        v2 = __uint_as_float(raw[t].z); v3 = __uint_as_float(raw[t].w);
       } else {
-        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(static_cast<const uint8_t*>(p.x) + off));
-        v0 = div255(u.x); v1 = div255(u.y); v2 = div255(u.z); v3 = div255(u.w);
+        const uint32_t u = raw[t].x;
+        v0 = div255(u & 0xFF); v1 = div255((u >> 8) & 0xFF); v2 = div255((u >> 16) & 0xFF); v3 = div255(u >> 24);
       }
       a0 = pack_bf16x2(v0, v1);
       a1 = pack_bf16x2(v2, v3);
+    } else {
+      d = -2 - d;
     }
-    uint32_t* d = reinterpret_cast<uint32_t*>(sRows + r * (kRowElems * 2) + (4 * qd + 2) * 2);
-    d[0] = a0;
-    d[1] = a1;
+    uint32_t* q = reinterpret_cast<uint32_t*>(sRows + d);
+    q[0] = a0;
+    q[1] = a1;
   }
 }
 
@@ -113,7 +143,7 @@ __device__ __forceinline__ void build_patch(const S2Params& p, const uint8_t* sR
 // smem: [W 8 KB][A0 16 KB][A1 16 KB][rows 9 KB][barriers]
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 2)
-stem_s2_fwd_kernel(const S2Params p) {
+stem_s2_fwd_kernel(const __grid_constant__ CUtensorMap tm_y, const S2Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -126,6 +156,7 @@ stem_s2_fwd_kernel(const S2Params p) {
 
   if (warp == kBuildWarps) {
     if (lane == 0) {
+      tma_prefetch_desc(&tm_y);
       mbar_init(acc_full, 1);
       fence_barrier_init();
     }
@@ -162,7 +193,12 @@ stem_s2_fwd_kernel(const S2Params p) {
   int it = 0;
   for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
     const int n = task / p.Ho, oy = task - n * p.Ho;
-    if (warp < kBuildWarps) stage_rows<TIn>(p, n, oy, sRows, threadIdx.x);
+    if (warp < kBuildWarps) {
+      stage_rows<TIn>(p, n, oy, sRows, threadIdx.x);
+    } else {
+      if (elect_one_sync()) tma_store_wait_read<0>();   // the previous task's output stores have drained the A tiles
+      __syncwarp();
+    }
     __syncthreads();
     if (warp < kBuildWarps) {
       if (warp < 4) build_patch<0>(p, sRows, sA, threadIdx.x & 127);
@@ -190,32 +226,46 @@ stem_s2_fwd_kernel(const S2Params p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // epilogue: the patch tiles are dead (MMAs complete) -> they become the dense, swizzled staging tiles of the output
+    // rows, which leave through TMA stores (a row-per-thread global store touches 32 lines per instruction)
     if (warp < kBuildWarps) {
       const int q = warp & 3, h = warp >> 2;     // TMEM lane quadrant (= warp % 4), 32-channel half
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
-        const int px = blk * 128 + q * 32 + lane;
+        const uint32_t row = static_cast<uint32_t>(q * 32 + lane) * 128u;
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * kC + h * 32, acc);
         tmem_ld_wait();
-        if (px < p.Wo) {
-          uint4* d = reinterpret_cast<uint4*>(p.y + ((static_cast<size_t>(n) * p.Ho + oy) * p.Wo + px) * kC + h * 32);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(acc[8 * i + 0]), __uint_as_float(acc[8 * i + 1]));
-            u.y = pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3]));
-            u.z = pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5]));
-            u.w = pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7]));
-            d[i] = u;
-          }
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(acc[8 * i + 0]), __uint_as_float(acc[8 * i + 1]));
+          u.y = pack_bf16x2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3]));
+          u.z = pack_bf16x2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5]));
+          u.w = pack_bf16x2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7]));
+          *reinterpret_cast<uint4*>(sA + blk * kTile + swz(row + (h * 4 + i) * 16u)) = u;
         }
       }
+      fence_proxy_async();
     }
     tc_fence_before();
-    __syncthreads();               // accumulators, patch tiles and staged rows are free for the next task
+    __syncthreads();               // accumulators and staged rows are free; the A tiles hold the output rows
     tc_fence_after();
+    if (warp == kBuildWarps) {
+      if (elect_one_sync()) {
+        tma_store_4d(&tm_y, sA, 0, 0, oy, n);                        // pixels 0..127 of the row
+        if (p.Wo > 128) tma_store_4d(&tm_y, sA + kTile, 0, 128, oy, n);   // pixels >= Wo: clipped
+        tma_store_commit();
+      }
+      __syncwarp();
+    }
   }
+  if (warp == kBuildWarps) {
+    if (elect_one_sync()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
   if (warp == kBuildWarps) tmem_dealloc(tmem_base, 128);
 }
 
@@ -346,17 +396,22 @@ int stem_s2_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias
   if (!s2_shape_ok(Cin, Hin, Win, C, K, stride, pad)) return FD_EUNSUPPORTED;
   S2Params p = s2_params(x, B, Hin, Win);
   p.w = w; p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  CUtensorMap tm_y;
+  {
+    const int rc = make_tmap_nhwc_bf16(&tm_y, y, B, p.Ho, p.Wo, kC, 128, 1);     // box = 128 pixels of one output row
+    if (rc != FD_OK) return rc;
+  }
   const size_t smem = 8192 + 2 * kTile + 9 * kRowElems * 2 + 64 + 1024;
   const int grid = min(p.ntask, 2 * sm_count());
   cudaError_t e;
   if (x_is_u8) {
     e = cudaFuncSetAttribute(stem_s2_fwd_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = launch_k(stem_s2_fwd_kernel<uint8_t>, dim3(grid), dim3(kThreads), smem, st, p);
+    e = launch_k(stem_s2_fwd_kernel<uint8_t>, dim3(grid), dim3(kThreads), smem, st, tm_y, p);
   } else {
     e = cudaFuncSetAttribute(stem_s2_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = launch_k(stem_s2_fwd_kernel<float>, dim3(grid), dim3(kThreads), smem, st, p);
+    e = launch_k(stem_s2_fwd_kernel<float>, dim3(grid), dim3(kThreads), smem, st, tm_y, p);
   }
   if (e != cudaSuccess) return (int)e;
   count_launch();
