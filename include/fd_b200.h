@@ -225,14 +225,18 @@ FD_API int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w
                 const float* chan_scale2, float slope, fd_bf16* dx2, float* dw, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * MaxPool2d(2) (models/PoolResnet.py:41-42).  x: [B,H,W,C] bf16 -> y: [B,H/2,W/2,C] bf16. */
-FD_API int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, void* stream);
+ * MaxPool2d(2) (models/PoolResnet.py:41-42).  x: [B,H,W,C] bf16 -> y: [B,H/2,W/2,C] bf16.
+ * argmax (nullable, training): uint16 [B,H/2,W/2,C/8], 2 bits per channel = position dy*2+dx of the FIRST maximum of
+ * the window (torch's tie rule); with it the backward does not re-read x. */
+FD_API int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, uint16_t* argmax, void* stream);
 /* Backward of the pool fused with the start of the block's backward chain:
  *   gs  = unpool(gy) routed to the FIRST maximum of each 2x2 window of x (torch tie rule),
  *   gs2 = gs * chan_scale[n,c] * (mask_bits bit ? 1 : slope)     (gs2 != NULL)
- * x, gs, gs2: [B,H,W,C] bf16; gy: [B,H/2,W/2,C] bf16; mask_bits: uint32 [B,H,W,C/32] sign bits. */
+ * x, gs, gs2: [B,H,W,C] bf16; gy: [B,H/2,W/2,C] bf16; mask_bits: uint32 [B,H,W,C/32] sign bits.
+ * argmax (nullable): the positions written by fd_maxpool2x2_fwd; when given, x is not read (and may be NULL). */
 FD_API int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int H, int W, int C, fd_bf16* gs,
-                      const uint32_t* mask_bits, const float* chan_scale, float slope, fd_bf16* gs2, void* stream);
+                      const uint32_t* mask_bits, const float* chan_scale, float slope, fd_bf16* gs2,
+                      const uint16_t* argmax, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * losses/YoloLoss.py:4-44 for a batch: loss[b] = yolo_loss(pred[b], gt[b]) and, when dpred != NULL,

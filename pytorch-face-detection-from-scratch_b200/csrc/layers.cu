@@ -830,7 +830,7 @@ head_bwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 // element and made these HBM-bound kernels instruction-bound.  C8 = C / 8 as a template constant (0 = runtime).
 template <int kC8>
 __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
-                                      __nv_bfloat16* __restrict__ y) {
+                                      __nv_bfloat16* __restrict__ y, uint16_t* __restrict__ amax) {
   pdl_trigger();
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2, C8 = kC8 ? kC8 : C / 8;
@@ -843,16 +843,18 @@ __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B
       const int ox = idx / C8, c8 = idx - ox * C8;
       const __nv_bfloat16* base = xrow + (2 * ox) * C + c8 * 8;
       float m[8], f[8];
+      uint32_t arg = 0;                           // 2 bits per channel: position (dy*2 + dx) of the FIRST maximum
       unpack8(__ldg(reinterpret_cast<const uint4*>(base)), m);
       unpack8(__ldg(reinterpret_cast<const uint4*>(base + C)), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      for (int j = 0; j < 8; ++j) if (f[j] > m[j]) { m[j] = f[j]; arg = (arg & ~(3u << (2 * j))) | (1u << (2 * j)); }
       unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(W) * C)), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      for (int j = 0; j < 8; ++j) if (f[j] > m[j]) { m[j] = f[j]; arg = (arg & ~(3u << (2 * j))) | (2u << (2 * j)); }
       unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(W) * C + C)), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      for (int j = 0; j < 8; ++j) if (f[j] > m[j]) { m[j] = f[j]; arg = (arg & ~(3u << (2 * j))) | (3u << (2 * j)); }
+      if (amax) amax[(static_cast<size_t>(row) * Wo + ox) * C8 + c8] = static_cast<uint16_t>(arg);
       *reinterpret_cast<uint4*>(yrow + ox * C + c8 * 8) = pack8(m);
     }
   }
@@ -862,7 +864,7 @@ template <int kC8>
 __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, int B,
                                       int H, int W, int C, __nv_bfloat16* __restrict__ gs,
                                       const uint32_t* __restrict__ mask_bits, const float* __restrict__ cs,
-                                      float slope, __nv_bfloat16* __restrict__ gs2) {
+                                      float slope, __nv_bfloat16* __restrict__ gs2, const uint16_t* __restrict__ amax) {
   pdl_trigger();
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2, C8 = kC8 ? kC8 : C / 8;
@@ -874,9 +876,7 @@ __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const
       const int ox = idx / C8, c8 = idx - ox * C8;
       const size_t off[4] = {0, static_cast<size_t>(C), static_cast<size_t>(W) * C, static_cast<size_t>(W) * C + C};
       const size_t base = row_base + static_cast<size_t>(2 * ox) * C + c8 * 8;
-      float v[4][8], g[8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + off[k])), v[k]);
+      float g[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(gy + (static_cast<size_t>(row) * Wo + ox) * C + c8 * 8)), g);
       float sc[8];
       if (gs2) {
@@ -884,12 +884,21 @@ __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const
         for (int j = 0; j < 8; ++j) sc[j] = cs ? __ldg(cs + n * C + c8 * 8 + j) : 1.f;
       }
       int arg[8];
+      if (amax) {                    // positions recorded by the forward: the pre-pool tensor is not read again
+        const uint32_t a = __ldg(amax + (static_cast<size_t>(row) * Wo + ox) * C8 + c8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {  // first maximum in (dy,dx) row-major order, like ATen's max_pool2d
-        int a = 0; float m = v[0][j];
+        for (int j = 0; j < 8; ++j) arg[j] = (a >> (2 * j)) & 3;
+      } else {
+        float v[4][8];
 #pragma unroll
-        for (int k = 1; k < 4; ++k) if (v[k][j] > m) { m = v[k][j]; a = k; }
-        arg[j] = a;
+        for (int k = 0; k < 4; ++k) unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + off[k])), v[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // first maximum in (dy,dx) row-major order, like ATen's max_pool2d
+          int a = 0; float m = v[0][j];
+#pragma unroll
+          for (int k = 1; k < 4; ++k) if (v[k][j] > m) { m = v[k][j]; a = k; }
+          arg[j] = a;
+        }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -1146,7 +1155,8 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
   return launch_status();
 }
 
-extern "C" int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, void* stream) {
+extern "C" int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, uint16_t* argmax,
+                                 void* stream) {
   if (!x || !y || B <= 0) return FD_EINVAL;
   if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
   const long rows = static_cast<long>(B) * (H / 2);
@@ -1155,15 +1165,15 @@ extern "C" int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, f
   const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
   launch_k(C == 64 ? maxpool2x2_fwd_kernel<8> : maxpool2x2_fwd_kernel<0>, dim3(grid_for(rows, 1, 16)), dim3(threads), 0,
            static_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C,
-           reinterpret_cast<__nv_bfloat16*>(y));
+           reinterpret_cast<__nv_bfloat16*>(y), argmax);
   count_launch();
   return launch_status();
 }
 
 extern "C" int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int H, int W, int C, fd_bf16* gs,
                                  const uint32_t* mask_bits, const float* chan_scale, float slope, fd_bf16* gs2,
-                                 void* stream) {
-  if (!x || !gy || (!gs && !gs2) || B <= 0) return FD_EINVAL;
+                                 const uint16_t* argmax, void* stream) {
+  if ((!x && !argmax) || !gy || (!gs && !gs2) || B <= 0) return FD_EINVAL;
   if ((gs2 != nullptr) != (mask_bits != nullptr)) return FD_EINVAL;
   if (gs2 && C % 32 != 0) return FD_EUNSUPPORTED;
   if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
@@ -1173,7 +1183,8 @@ extern "C" int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int
   const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
   launch_k(C == 64 ? maxpool2x2_bwd_kernel<8> : maxpool2x2_bwd_kernel<0>, dim3(grid_for(rows, 1, 16)), dim3(threads), 0,
            static_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gy), B, H, W, C,
-           reinterpret_cast<__nv_bfloat16*>(gs), mask_bits, chan_scale, slope, reinterpret_cast<__nv_bfloat16*>(gs2));
+           reinterpret_cast<__nv_bfloat16*>(gs), mask_bits, chan_scale, slope, reinterpret_cast<__nv_bfloat16*>(gs2),
+           argmax);
   count_launch();
   return launch_status();
 }

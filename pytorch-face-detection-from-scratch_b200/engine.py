@@ -20,7 +20,7 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 
 class _Block:
-    __slots__ = ("H", "W", "pool", "a", "ma", "mb", "s", "out", "G", "gs", "gp1", "gp2")
+    __slots__ = ("H", "W", "pool", "a", "ma", "mb", "s", "out", "G", "gs", "gp1", "gp2", "amax")
 
 
 class _Plan:
@@ -90,10 +90,13 @@ class _Plan:
             # LeakyReLU' masks of a (conv1 activation) and b (conv2 activation after Dropout2d) as sign bits
             blk.ma = torch.empty((B, H, W, F // 32), dtype=torch.int32, device=device) if train else None
             blk.mb = torch.empty((B, H, W, F // 32), dtype=torch.int32, device=device) if train else None
+            blk.amax = None
             if blk.pool:
                 blk.s = bf(H, W)
                 H, W = H // 2, W // 2
                 blk.out = out_buffer(k, H, W)
+                if train:           # 2-bit positions of the window maxima: the un-pool does not re-read blk.s
+                    blk.amax = torch.empty((B, H, W, F // 8), dtype=torch.int16, device=device)
             else:
                 blk.s = out_buffer(k, H, W)
                 blk.out = blk.s
@@ -278,7 +281,7 @@ class BackboneEngine:
             ops.conv3x3(blk.a, self._wf(2 * k + 1), bias=sb3[2 * k + 1], slope=self.slope, lrelu=True,
                         chan_scale=cs, residual=cur, mask_out=blk.mb, out=blk.s)
             if blk.pool:
-                ops.maxpool2x2_fwd(blk.s, blk.out)
+                ops.maxpool2x2_fwd(blk.s, blk.out, blk.amax)
             cur = blk.out
         cs = pl.drop[self.num_blocks] if pl.drop is not None else None
         ops.head_fwd(cur, cs, self.section(self.pflat, "out.weight"), self.section(self.pflat, "out.bias"), pl.y,
@@ -360,7 +363,7 @@ class BackboneEngine:
                 continue
             if blk.pool:
                 ops.maxpool2x2_bwd(blk.s, blk.G, blk.gs, blk.mb, drop[k] if drop is not None else None, self.slope,
-                                   blk.gp2)
+                                   blk.gp2, argmax=blk.amax)
                 GS = blk.gs
             else:
                 GS = blk.G

@@ -48,8 +48,8 @@ SIGNATURES = {
     "fd_head_pack": [_P, _I, _I, _P, _P],
     "fd_head_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "fd_head_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
-    "fd_maxpool2x2_fwd": [_P, _I, _I, _I, _I, _P, _P],
-    "fd_maxpool2x2_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P],
+    "fd_maxpool2x2_fwd": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "fd_maxpool2x2_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P],
     "fd_yolo_loss": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "fd_decode_nms": [_P, _I, _I, _I, _F, _D, _I, _I, _I, _P, _P, _P, _P],
     "fd_box_metrics": [_P, _P, _P, _P, _I, _I, _F, _P, _P],

@@ -147,15 +147,19 @@ def head_bwd(x, chan_scale, w, y, dy, pad, dx, mask_bits, chan_scale2, slope, dx
                             dptr(dx2, BF16), dptr(dw, F32), dptr(dbias, F32), cur_stream()), "fd_head_bwd")
 
 
-def maxpool2x2_fwd(x, y):
+def maxpool2x2_fwd(x, y, argmax=None):
+    """argmax: int16 [B,H/2,W/2,C/8] (2 bits per channel) filled for the backward, or None."""
     B, H, W, C = x.shape
-    check(lib().fd_maxpool2x2_fwd(dptr(x, BF16), B, H, W, C, dptr(y, BF16), cur_stream()), "fd_maxpool2x2_fwd")
+    check(lib().fd_maxpool2x2_fwd(dptr(x, BF16), B, H, W, C, dptr(y, BF16), dptr(argmax, torch.int16), cur_stream()),
+          "fd_maxpool2x2_fwd")
 
 
-def maxpool2x2_bwd(x, gy, gs, mask_bits, chan_scale, slope, gs2):
+def maxpool2x2_bwd(x, gy, gs, mask_bits, chan_scale, slope, gs2, argmax=None):
+    """With ``argmax`` (written by maxpool2x2_fwd) the pre-pool tensor ``x`` is not read (only its shape is used)."""
     B, H, W, C = x.shape
-    check(lib().fd_maxpool2x2_bwd(dptr(x, BF16), dptr(gy, BF16), B, H, W, C, dptr(gs, BF16), dptr(mask_bits, I32),
-                                  dptr(chan_scale, F32), slope, dptr(gs2, BF16), cur_stream()), "fd_maxpool2x2_bwd")
+    check(lib().fd_maxpool2x2_bwd(None if argmax is not None else dptr(x, BF16), dptr(gy, BF16), B, H, W, C,
+                                  dptr(gs, BF16), dptr(mask_bits, I32), dptr(chan_scale, F32), slope, dptr(gs2, BF16),
+                                  dptr(argmax, torch.int16), cur_stream()), "fd_maxpool2x2_bwd")
 
 
 def yolo_loss(pred, gt, loss, dloss_scale=None, dpred=None):

@@ -226,11 +226,17 @@ def test_maxpool_fwd_bwd_first_max_tie_rule():
     cs = (torch.rand(B, C, device=dev) < 0.75).float() / 0.75
     gs = torch.zeros_like(x); gs2 = torch.zeros_like(x)
     ops.maxpool2x2_bwd(x, gy, gs, _bits(msk), cs, 0.2, gs2)
+    # the same through the 2-bit positions recorded by the forward (x is not read by the backward)
+    amax = torch.empty((B, H // 2, H // 2, C // 8), dtype=torch.int16, device=dev)
+    y_b = torch.empty_like(y); ops.maxpool2x2_fwd(x, y_b, amax)
+    gs_b = torch.zeros_like(gs); gs2_b = torch.zeros_like(gs2)
+    ops.maxpool2x2_bwd(x, gy, gs_b, _bits(msk), cs, 0.2, gs2_b, argmax=amax)
     ref.backward(gy.float().permute(0, 3, 1, 2))
     gref = xin.grad.permute(0, 2, 3, 1)
     assert torch.equal(gs.float(), gref)
     want2 = (gref * cs[:, None, None, :] * torch.where(msk.float() > 0, 1.0, 0.2)).bfloat16()
     assert rel_err(gs2.float(), want2.float()) <= 4e-3
+    assert torch.equal(y_b, y) and torch.equal(gs_b, gs) and torch.equal(gs2_b, gs2)
 
 
 def test_flat_adam_matches_torch_adam():
