@@ -2,9 +2,10 @@
 // tensor cores.  The CUDA-core kernel in layers.cu needed 42 us for 0.3 GFLOP (8 % of the PoolResnet train step).
 //
 // With dz = dy * y * (1 - y) (5 x Ho x Wo values per image), both gradients are GEMMs over ONE im2col "patch tile" that
-// is built in shared memory per image -- row = input pixel px, column k = (tap, o):
+// is built in shared memory per image -- row = input pixel px, column k = (o, tap), o-major so that four consecutive
+// columns are four consecutive taps of one dw[o][c][:] row (16-byte vector reductions in the drain):
 //
-//     P[px][tap*5 + o] = dz[o][iy + pad - ky][ix + pad - kx]        (0 outside the output map / beyond the image)
+//     P[px][o*K*K + tap] = dz[o][iy + pad - ky][ix + pad - kx]      (0 outside the output map / beyond the image)
 //
 //   dx[px][c]       = sum_k P[px][k] * Wt[c][k]          K-major A (P) x K-major B (weights):  M=128, N=64
 //   dw[c][(tap,o)]  = sum_px x[px][c] * P[px][k]         MN-major A (x tile, TMA) x MN-major B (P):  M=64, N=64 per atom
@@ -79,12 +80,12 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const HeadParams p)
   __syncthreads();
   pdl_trigger();
   pdl_wait();
-  // weights Wt[c][k] = w[o][c][tap], k = tap*5 + o, bf16, K-major rows of 128 B per atom, 128B swizzle.  Read in w's own
+  // weights Wt[c][k] = w[o][c][tap], k = o*K*K + tap, bf16, K-major rows of 128 B per atom, 128B swizzle.  Read in w's own
   // memory order (coalesced), scattered into shared memory with 2-byte stores; k >= 5*K*K stays zero from the clear.
   for (int i = threadIdx.x; i < 5 * kC * KK; i += kThreads) {
     const int oc = i / KK, tap = i - oc * KK;
     const int o = oc / kC, c = oc - o * kC;
-    const int k = tap * 5 + o;
+    const int k = o * KK + tap;
     *reinterpret_cast<uint16_t*>(sWt + (k >> 6) * 8192 + swz(static_cast<uint32_t>(c) * 128u + (k & 63) * 2u)) =
         __bfloat16_as_ushort(__float2bfloat16_rn(__ldg(p.w + i)));
   }
@@ -150,7 +151,7 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const HeadParams p)
           for (int i = 0; i < 8; ++i) {
             const int k = a * 64 + j * 8 + i;
             if (k < NK) {
-              const int tap = k / 5, o = k - tap * 5, ky = tap / K, kx = tap - ky * K;
+              const int o = k / KK, tap = k - o * KK, ky = tap / K, kx = tap - ky * K;
               uint32_t v = 0;
               if (rowoff[ky] >= 0 && colok[kx]) v = sDz[o * p.npo + rowoff[ky] + colx[kx]];
               u[i >> 1] |= v << ((i & 1) * 16);
@@ -248,11 +249,25 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const HeadParams p)
           const int c = q * 16 + lane;
           const float s = csn ? __ldg(csn + c) : 1.f;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
+          for (int e = 0; e < 32; e += 4) {        // 4 consecutive k = 4 consecutive taps of dw[o][c][:] (KK % 4 == 0)
             const int k = a * 64 + h * 32 + e;
             if (k < NK) {
-              const int tap = k / 5, o = k - tap * 5;
-              atomicAdd(p.dw + (static_cast<size_t>(o) * kC + c) * KK + tap, __uint_as_float(acc[e]) * s);
+              const int o = k / KK, tap = k - o * KK;
+              float* dst = p.dw + (static_cast<size_t>(o) * kC + c) * KK + tap;
+              if constexpr (KK % 4 == 0) {
+                atomicAdd(reinterpret_cast<float4*>(dst),
+                          make_float4(__uint_as_float(acc[e]) * s, __uint_as_float(acc[e + 1]) * s,
+                                      __uint_as_float(acc[e + 2]) * s, __uint_as_float(acc[e + 3]) * s));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int ki = k + i;
+                  if (ki < NK) {
+                    const int oi = ki / KK, ti = ki - oi * KK;
+                    atomicAdd(p.dw + (static_cast<size_t>(oi) * kC + c) * KK + ti, __uint_as_float(acc[e + i]) * s);
+                  }
+                }
+              }
             }
           }
         }
