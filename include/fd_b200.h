@@ -165,7 +165,7 @@ FD_API int fd_comm_export(void* ptr, unsigned char* handle64);
 FD_API int fd_comm_import(const unsigned char* handle64, void** peer_ptr);
 FD_API int fd_comm_release(void* peer_ptr);
 FD_API int fd_comm_error_offset(void);                            /* byte offset of the u32 status word in a window (0 = ok) */
-/* status of the LOCAL window: 0 = ok, 1 + r = a barrier wait on rank r timed out (4 s) and that call's result is invalid.
+/* status of the LOCAL window: 0 = ok, 1 + r = a barrier wait on rank r timed out (20 s) and that call's result is invalid.
  * Synchronises the device: a host-side health check, not part of the data path. */
 FD_API int fd_comm_status(void* window, int* status);
 /* windows: HOST array of `world` device pointers (entry `rank` = the local window, the rest imported);

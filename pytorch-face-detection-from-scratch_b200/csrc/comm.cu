@@ -30,7 +30,7 @@ constexpr int kCommThreads = 512;
 //                        [scatter slots: world x chunk floats][result: world x chunk floats]
 constexpr size_t kFlagBytes = 8192;
 constexpr int kErrWord = 2 * kCommBlocks * kMaxPeers + kCommBlocks;      // u32 index: 0 = ok, 1 + peer = timed out on peer
-constexpr long long kSpinLimitClk = 8000000000LL;                        // ~4 s at 2 GHz
+constexpr long long kSpinLimitClk = 40000000000LL;                       // ~20 s at 2 GHz: start-up skew between ranks is fine, a dead peer is not
 
 struct Peers {
   unsigned char* win[kMaxPeers];
@@ -187,7 +187,7 @@ extern "C" int fd_comm_release(void* peer_ptr) {
 extern "C" int fd_comm_error_offset(void) { return kErrWord * 4; }
 
 // Status word of the LOCAL window: 0 = every barrier of every call completed; 1 + r = a wait on rank r ran into the
-// 4 s spin limit (the peer died or never launched its kernel) and the sums of that call are garbage.  Synchronises the
+// 20 s spin limit (the peer died or never launched its kernel) and the sums of that call are garbage.  Synchronises the
 // device (host-side health check, not on the data path).
 extern "C" int fd_comm_status(void* window, int* status) {
   if (!window || !status) return FD_EINVAL;

@@ -301,8 +301,7 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   uint8_t* sA = sW + p.CK * 2048;
   uint8_t* sStage = sA + p.a_bytes + 128;              // staging slots
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + kFwdSlots * kSlotBytes);
-  uint64_t* a_full = bars + 0;     // [1] count = loader warps
-  uint64_t* a_empty = bars + 2;    // [1]
+  // bars + 0..3: unused (the A tile is handed over per row group, see grp_full / grp_empty)
   uint64_t* acc_full = bars + 4;   // [2]
   uint64_t* acc_empty = bars + 6;  // [2]
   uint64_t* stg_full = bars + 8;               // [kFwdSlots]
@@ -334,8 +333,6 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
-    mbar_init(a_full, kFwdLoaders);
-    mbar_init(a_empty, 1);
     for (int g = 0; g < 6; ++g) {
       mbar_init(grp_full + g, 4);
       mbar_init(grp_empty + g, 1);
