@@ -172,6 +172,17 @@ FD_API int fd_comm_status(void* window, int* status);
  * data: the local flat fp32 buffer of n elements, summed over ranks in place. */
 FD_API int fd_allreduce_sum_f32(void* const* windows, int rank, int world, float* data, long n, void* stream);
 
+/* Elementwise halves of a residual block for backbones wider than the 64-channel tensor-core kernels (filters = 128
+ * = two 64-channel planes per tensor, engine.PlanarEngine).  A 128 -> 128 convolution is evaluated as the sum of two
+ * 64 -> 64 convolutions per output plane (the second fd_conv3x3 call takes the first one's raw output as `residual`,
+ * without FD_EPI_LRELU), so the activation of models/PoolResnet.py:35-40 runs here on 64-channel planes [B,HW,64]:
+ *   fd_act_mask : out = lrelu(x) * chan_scale[n,c] + residual ; mask_out bit = sign bit of x clear (nullable operands)
+ *   fd_grad_mask: out = g * (mask bit ? 1 : slope) * chan_scale[n,c]   (mask_bits NULL = all ones) */
+FD_API int fd_act_mask(const fd_bf16* x, int B, int HW, int C, float slope, const float* chan_scale, const fd_bf16* residual,
+                uint32_t* mask_out, fd_bf16* out, void* stream);
+FD_API int fd_grad_mask(const fd_bf16* g, int B, int HW, int C, float slope, const uint32_t* mask_bits, const float* chan_scale,
+                 fd_bf16* out, void* stream);
+
 /* Dropout2d multipliers (models/PoolResnet.py:39,100; nn.Dropout2d zeroes whole channels and rescales):
  * out[i] = r[i] < keep ? 1/keep : 0 with keep = keep_block for i < n_block and keep_head otherwise.
  * r: n uniform randoms in [0,1) (one per (layer, image, channel)), produced by the caller's generator. */

@@ -918,6 +918,64 @@ __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Elementwise halves of a residual block for backbones wider than the 64-channel tensor-core kernels (filters = 128:
+// two 64-channel planes per tensor, engine.PlanarEngine).  A 128 -> 128 convolution is the SUM of two 64 -> 64
+// convolutions per output plane (chained through the conv kernel's raw residual add), so the activation cannot ride in
+// the conv epilogue and runs here:
+//   act_mask  : out = lrelu(x) * chan_scale[n,c] + residual ; mask bit = sign bit of x clear   (PoolResnet.py:35-40)
+//   grad_mask : out = g * (mask bit ? 1 : slope) * chan_scale[n,c]                              (its backward)
+// x, g, residual, out: [B,HW,64] bf16 planes; mask: uint32 [B,HW,2]; 8 channels per thread.
+__global__ void act_mask_kernel(const __nv_bfloat16* __restrict__ x, long n8, int hw, float slope,
+                                const float* __restrict__ cs, const __nv_bfloat16* __restrict__ res,
+                                uint8_t* __restrict__ mask_out, __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
+    const int c8 = static_cast<int>(i & 7);
+    const long n = i / (8L * hw);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bits |= (__float_as_uint(v[j]) >> 31 ? 0u : 1u) << j;
+      v[j] = fmaxf(v[j], v[j] * slope);
+      if (cs) v[j] *= __ldg(cs + n * 64 + c8 * 8 + j);
+    }
+    if (res) {
+      float r[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(res) + i), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (mask_out) mask_out[i] = static_cast<uint8_t>(bits);     // byte i = channels 8*c8.. of pixel i/8 (little endian words)
+    reinterpret_cast<uint4*>(out)[i] = pack8(v);
+  }
+}
+
+__global__ void grad_mask_kernel(const __nv_bfloat16* __restrict__ g, long n8, int hw, float slope,
+                                 const uint8_t* __restrict__ mask, const float* __restrict__ cs,
+                                 __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(g) + i), v);
+    const int c8 = static_cast<int>(i & 7);
+    const long n = i / (8L * hw);
+    const uint32_t bits = mask ? mask[i] : 0xFFu;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] *= ((bits >> j) & 1u) ? 1.f : slope;
+      if (cs) v[j] *= __ldg(cs + n * 64 + c8 * 8 + j);
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(v);
+  }
+}
+
 inline int grid_for(long total, int block, int cap_mult = 8) {
   long g = (total + block - 1) / block;
   const long cap = static_cast<long>(sm_count()) * cap_mult;
@@ -966,6 +1024,31 @@ extern "C" int fd_adam_flat(float* p, const float* g, float* m, float* v, long n
   if (n % 4 != 0) return FD_EUNSUPPORTED;              // the flat buffers are padded to 16 bytes per section
   launch_k(adam_flat_kernel, dim3(grid_for(n / 4, 256, 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g, m, v, n,
            lr, beta1, beta2, eps, weight_decay, step, state);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_act_mask(const fd_bf16* x, int B, int HW, int C, float slope, const float* chan_scale,
+                           const fd_bf16* residual, uint32_t* mask_out, fd_bf16* out, void* stream) {
+  if (!x || !out || B <= 0 || HW <= 0) return FD_EINVAL;
+  if (C != 64 || !(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;
+  const long n8 = static_cast<long>(B) * HW * 8;
+  launch_k(act_mask_kernel, dim3(grid_for(n8, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+           reinterpret_cast<const __nv_bfloat16*>(x), n8, HW, slope, chan_scale,
+           reinterpret_cast<const __nv_bfloat16*>(residual), reinterpret_cast<uint8_t*>(mask_out),
+           reinterpret_cast<__nv_bfloat16*>(out));
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_grad_mask(const fd_bf16* g, int B, int HW, int C, float slope, const uint32_t* mask_bits,
+                            const float* chan_scale, fd_bf16* out, void* stream) {
+  if (!g || !out || B <= 0 || HW <= 0) return FD_EINVAL;
+  if (C != 64) return FD_EUNSUPPORTED;
+  const long n8 = static_cast<long>(B) * HW * 8;
+  launch_k(grad_mask_kernel, dim3(grid_for(n8, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+           reinterpret_cast<const __nv_bfloat16*>(g), n8, HW, slope, reinterpret_cast<const uint8_t*>(mask_bits),
+           chan_scale, reinterpret_cast<__nv_bfloat16*>(out));
   count_launch();
   return launch_status();
 }

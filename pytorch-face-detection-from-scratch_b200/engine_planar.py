@@ -1,0 +1,304 @@
+"""Residual grid backbones wider than the 64-channel tensor-core kernels (``filters = 128``: the width
+``train_model.py:16`` trains) on G = filters / 64 channel PLANES.
+
+Every activation / gradient tensor is stored as G separate NHWC tensors of 64 channels, so that the sm_100a kernels
+instantiated for 64 channels (``fd_conv3x3``, ``fd_conv3x3_wgrad``, ``fd_stem_*``, ``fd_maxpool2x2_*``) are reused as
+they are:
+
+* a 64G -> 64G 3x3 convolution is, per output plane g, the SUM over input planes h of 64 -> 64 convolutions with the
+  weight sub-block ``W[64g:64g+64, 64h:64h+64]``.  The sum is chained through the conv kernel's raw residual add (second
+  call: ``residual`` = the first call's output, no activation), and the activation of models/PoolResnet.py:35-40 runs
+  in ``fd_act_mask`` (LeakyReLU + sign-bit mask + Dropout2d multiplier + skip) / ``fd_grad_mask`` (its backward);
+* the weight gradient of sub-block (g, h) is ``fd_conv3x3_wgrad(x plane h, gradient plane g)``;
+* the stem runs once per output plane (the bf16 image cache is written by the first launch), the head on the
+  re-interleaved ``[B,H,W,64G]`` tensor through the generic head kernels.
+
+This is the FUNCTIONAL path for the wide models (same parity bar as the 64-channel engine; one more bf16 rounding per
+convolution for the chained partial sum) -- about 4x the launches of the fused 64-channel step and no fused block
+chain.  A native 128-channel instantiation (N = 128 MMAs, streamed weights) is the next kernel.
+Parameters stay ordinary ``nn.Parameter`` tensors; gradients land in one flat fp32 buffer (``gflat``, the all-reduce
+unit) of which every ``p.grad`` is a view.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List
+
+import torch
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class _PBlock:
+    __slots__ = ("H", "W", "pool", "inp", "T", "T2", "a", "ma", "mb", "s", "out", "amax", "G", "gs", "gp1", "gp2", "U")
+
+
+class _PPlan:
+    def __init__(self, eng: "PlanarEngine", B: int, train: bool, device):
+        G = eng.G
+        self.B, self.train = B, train
+
+        def planes(h, w):
+            return [torch.empty((B, h, w, 64), dtype=BF16, device=device) for _ in range(G)]
+
+        def masks(h, w):
+            return [torch.empty((B, h, w, 2), dtype=torch.int32, device=device) for _ in range(G)]
+
+        H, W = eng.H0, eng.W0
+        self.act0 = planes(H, W)
+        self.blocks: List[_PBlock] = []
+        cur = self.act0
+        for k in range(eng.num_blocks):
+            b = _PBlock()
+            b.H, b.W, b.pool = H, W, eng.pools[k]
+            b.inp = cur
+            b.T, b.T2, b.a = planes(H, W), planes(H, W), planes(H, W)
+            b.ma = masks(H, W) if train else [None] * G
+            b.mb = masks(H, W) if train else [None] * G
+            b.s = planes(H, W)
+            b.amax = [None] * G
+            if b.pool:
+                H, W = H // 2, W // 2
+                b.out = planes(H, W)
+                if train:
+                    b.amax = [torch.empty((B, H, W, 8), dtype=torch.int16, device=device) for _ in range(G)]
+            else:
+                b.out = b.s
+            if train:
+                b.G = planes(H, W)                      # gradient w.r.t. the block OUTPUT (post-pool resolution)
+                b.gs = planes(b.H, b.W) if b.pool else None
+                b.gp1, b.gp2, b.U = planes(b.H, b.W), planes(b.H, b.W), planes(b.H, b.W)
+            self.blocks.append(b)
+            cur = b.out
+        self.y = torch.empty((B, 5, eng.So_h, eng.So_w), dtype=F32, device=device)
+        if train:
+            n_cache = ops.stem_cache_elems(B, eng.in_ch, eng.in_h, eng.in_w, 64, eng.stem_k, eng.stem_s, eng.stem_pad)
+            self.x_cache = torch.zeros(n_cache, dtype=BF16, device=device) if n_cache else None
+            self.g_stem = planes(eng.H0, eng.W0)
+            self.loss = torch.empty((B,), dtype=F32, device=device)
+            self.dy = torch.empty_like(self.y)
+        else:
+            self.x_cache = None
+        self.drop = None
+        self.x = self.xh = self.cs_head = None
+
+
+class PlanarEngine:
+    def __init__(self, filters: int, in_ch: int, in_h: int, in_w: int, num_blocks: int, stem_k: int, stem_s: int,
+                 stem_pad: int, head_k: int, head_pad: int, pool_rule: Callable[[int], bool], slope: float = 0.2,
+                 block_drop: float = 0.25, head_drop: float = 0.5):
+        if filters % 64 != 0 or filters < 128:
+            raise NotImplementedError("PlanarEngine handles filters = 64 * G with G >= 2; got %d" % filters)
+        self.F, self.G = filters, filters // 64
+        self.in_ch, self.in_h, self.in_w = in_ch, in_h, in_w
+        self.num_blocks, self.slope = num_blocks, slope
+        self.stem_k, self.stem_s, self.stem_pad, self.head_k, self.head_pad = stem_k, stem_s, stem_pad, head_k, head_pad
+        self.block_drop, self.head_drop = block_drop, head_drop
+        self.H0 = (in_h + 2 * stem_pad - stem_k) // stem_s + 1
+        self.W0 = (in_w + 2 * stem_pad - stem_k) // stem_s + 1
+        self.pools = []
+        H, W = self.H0, self.W0
+        for _ in range(num_blocks):
+            p = bool(pool_rule(H))
+            self.pools.append(p)
+            if p:
+                H, W = H // 2, W // 2
+        self.Hl, self.Wl = H, W
+        self.So_h, self.So_w = H + 2 * head_pad - head_k + 1, W + 2 * head_pad - head_k + 1
+        F_ = filters
+        self.sections = [("conv1.weight", (F_, in_ch, stem_k, stem_k)), ("conv1.bias", (F_,)),
+                         ("w3", (2 * num_blocks, F_, F_, 3, 3)), ("b3", (2 * num_blocks, F_)),
+                         ("out.weight", (5, F_, head_k, head_k)), ("out.bias", (5,))]
+        self.offsets, off = {}, 0
+        for name, shape in self.sections:
+            n = 1
+            for s in shape:
+                n *= s
+            self.offsets[name] = (off, n, shape)
+            off += (n + 3) // 4 * 4
+        self.n_flat = off
+        self.device = None
+        self.gflat = None
+        self.plans: Dict[tuple, _PPlan] = {}
+
+    # ------------------------------------------------------------------ parameters / gradients
+    def param_names(self) -> List[str]:
+        names = ["conv1.weight", "conv1.bias"]
+        for k in range(self.num_blocks):
+            for c in ("conv1", "conv2"):
+                names += [f"residual_blocks.{k}.{c}.weight", f"residual_blocks.{k}.{c}.bias"]
+        return names + ["out.weight", "out.bias"]
+
+    def section(self, flat, name):
+        off, n, shape = self.offsets[name]
+        return flat[off:off + n].view(shape)
+
+    def grad_view(self, name: str) -> torch.Tensor:
+        if name.startswith("residual_blocks."):
+            _, k, c, kind = name.split(".")
+            layer = 2 * int(k) + (0 if c == "conv1" else 1)
+            return self.section(self.gflat, "w3" if kind == "weight" else "b3")[layer]
+        return self.section(self.gflat, name)
+
+    def bind(self, params):
+        dev = params["conv1.weight"].device
+        if dev.type != "cuda":
+            raise RuntimeError("the fd_b200 backbone runs on CUDA only (no CPU fallback): call model.cuda()")
+        if self.device != dev or self.gflat is None:
+            self.device = dev
+            G, L = self.G, 2 * self.num_blocks
+            self.gflat = torch.zeros(self.n_flat, dtype=F32, device=dev)
+            self.dwp = torch.zeros((L * G * G, 9 * 64 * 64), dtype=F32, device=dev)        # packed accumulators
+            self.dw_sub = torch.empty((L * G * G, 64, 64, 3, 3), dtype=F32, device=dev)
+            self.gb3 = torch.zeros((L, G, 64), dtype=F32, device=dev)
+            self.w_fwd = torch.empty((L * G * G, 9, 64, 64), dtype=BF16, device=dev)
+            self.w_dgrad = torch.empty((L * G * G, 9, 64, 64), dtype=BF16, device=dev)
+            self.plans.clear()
+        self.params = params
+
+    def plan(self, B, train):
+        key = (B, train)
+        if key not in self.plans:
+            self.plans[key] = _PPlan(self, B, train, self.device)
+        return self.plans[key]
+
+    def _sub(self, layer, g, h):
+        return (layer * self.G + g) * self.G + h
+
+    def pack_weights(self):
+        """[L,64G,64G,3,3] fp32 -> sub-blocks [(L,g,h),64,64,3,3] (torch data movement) -> bf16 forward / dgrad packing."""
+        G, L = self.G, 2 * self.num_blocks
+        P = self.params
+        ws, bs = [], []
+        for k in range(self.num_blocks):
+            for c in ("conv1", "conv2"):
+                ws.append(P[f"residual_blocks.{k}.{c}.weight"].detach())
+                bs.append(P[f"residual_blocks.{k}.{c}.bias"].detach())
+        w3 = torch.stack(ws).float().view(L, G, 64, G, 64, 3, 3).permute(0, 1, 3, 2, 4, 5, 6).contiguous()
+        ops.pack_conv3x3(w3.view(L * G * G, 64, 64, 3, 3), self.w_fwd, self.w_dgrad)
+        self.b3 = torch.stack(bs).float().view(L, G, 64).contiguous()
+
+    # ------------------------------------------------------------------ forward
+    def _conv_sum(self, srcs, wsel, layer, g, bias, dst_a, dst_b, **last_kw):
+        """sum_h conv(srcs[h], W[layer][g][h]) (+ bias) as a chain of 64-channel convolutions; returns the raw sum's
+        buffer (or None when the last call wrote a masked out2 via last_kw)."""
+        prev = None
+        for h in range(self.G):
+            last = h == self.G - 1
+            dst = dst_b if (h % 2) else dst_a
+            kw = dict(bias=bias if h == 0 else None, slope=self.slope, lrelu=False, residual=prev)
+            if last and last_kw:
+                kw.update(last_kw)
+            else:
+                kw["out"] = dst
+            ops.conv3x3(srcs[h], wsel[self._sub(layer, g, h)], **kw)
+            prev = dst
+        return prev
+
+    def forward(self, x, train: bool, dropout: bool = False):
+        B = x.shape[0]
+        pl = self.plan(B, train)
+        G, nb, P = self.G, self.num_blocks, self.params
+        self.pack_weights()
+        if dropout:
+            r = torch.rand((nb + 1, G, B, 64), device=x.device)
+            scale = torch.empty_like(r)
+            ops.dropout_scale(r, nb * G * B * 64, 1.0 - self.block_drop, 1.0 - self.head_drop, scale)
+            pl.drop = scale
+        else:
+            pl.drop = None
+        pl.x = x
+        w1, b1 = P["conv1.weight"].detach().float(), P["conv1.bias"].detach().float()
+        for g in range(G):
+            ops.stem_fwd(x, w1[g * 64:(g + 1) * 64], b1[g * 64:(g + 1) * 64], pl.act0[g], self.stem_s, self.stem_pad,
+                         x_cache=pl.x_cache if g == 0 else None)
+        cur = pl.act0
+        for k, blk in enumerate(pl.blocks):
+            for g in range(G):
+                raw = self._conv_sum(cur, self.w_fwd, 2 * k, g, self.b3[2 * k, g], blk.T[g], blk.T2[g])
+                ops.act_mask(raw, self.slope, None, None, blk.ma[g], blk.a[g])
+            for g in range(G):
+                raw = self._conv_sum(blk.a, self.w_fwd, 2 * k + 1, g, self.b3[2 * k + 1, g], blk.T[g], blk.T2[g])
+                ops.act_mask(raw, self.slope, pl.drop[k, g] if pl.drop is not None else None, cur[g], blk.mb[g],
+                             blk.s[g])
+                if blk.pool:
+                    ops.maxpool2x2_fwd(blk.s[g], blk.out[g], blk.amax[g])
+            cur = blk.out
+        pl.xh = torch.cat(cur, dim=3)                                            # [B,H,W,64G] for the head kernels
+        pl.cs_head = (pl.drop[nb].permute(1, 0, 2).reshape(B, self.F).contiguous() if pl.drop is not None else None)
+        ops.head_fwd(pl.xh, pl.cs_head, P["out.weight"].detach().float(), P["out.bias"].detach().float(), pl.y,
+                     self.head_pad)
+        return pl
+
+    # ------------------------------------------------------------------ backward
+    def run_backward(self, pl: _PPlan, dy: torch.Tensor):
+        assert pl.train
+        G, nb, P = self.G, self.num_blocks, self.params
+        drop = pl.drop
+        self.gflat.zero_()
+        self.dwp.zero_()
+        self.gb3.zero_()
+        dxh = torch.empty_like(pl.xh)
+        ops.head_bwd(pl.xh, pl.cs_head, P["out.weight"].detach().float(), pl.y, dy, self.head_pad, dxh, None, None,
+                     self.slope, None, self.section(self.gflat, "out.weight"), self.section(self.gflat, "out.bias"))
+        last = pl.blocks[nb - 1]
+        for g in range(G):
+            last.G[g].copy_(dxh[..., g * 64:(g + 1) * 64])
+        for k in range(nb - 1, -1, -1):
+            blk = pl.blocks[k]
+            L1, L2 = 2 * k, 2 * k + 1
+            for g in range(G):
+                cs = drop[k, g] if drop is not None else None
+                if blk.pool:
+                    ops.maxpool2x2_bwd(blk.s[g], blk.G[g], blk.gs[g], blk.mb[g], cs, self.slope, blk.gp2[g],
+                                       argmax=blk.amax[g])
+                else:
+                    ops.grad_mask(blk.G[g], self.slope, blk.mb[g], cs, blk.gp2[g])
+            GS = blk.gs if blk.pool else blk.G
+            # gp1[h] = (sum_g dgrad(gp2[g], W2[g][h])) * lrelu'(a[h])
+            for h in range(G):
+                prev = None
+                for g in range(G):
+                    w = self.w_dgrad[self._sub(L2, g, h)]
+                    if g < G - 1:
+                        dst = blk.U[h] if (g % 2 == 0) else blk.T[h]
+                        ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, out=dst)
+                        prev = dst
+                    else:
+                        ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, mask_in=blk.ma[h], out2=blk.gp1[h])
+            # G_{k-1}[h] = sum_g dgrad(gp1[g], W1[g][h]) + GS[h]
+            gprev = pl.blocks[k - 1].G if k > 0 else pl.g_stem
+            for h in range(G):
+                prev = GS[h]
+                for g in range(G):
+                    w = self.w_dgrad[self._sub(L1, g, h)]
+                    dst = gprev[h] if g == G - 1 else (blk.U[h] if (g % 2 == 0) else blk.T[h])
+                    ops.conv3x3(blk.gp1[g], w, slope=self.slope, residual=prev, out=dst)
+                    prev = dst
+            # weight / bias gradients of the 2 x G x G sub-blocks
+            for g in range(G):
+                for h in range(G):
+                    ops.conv3x3_wgrad(blk.inp[h], blk.gp1[g], self.dwp[self._sub(L1, g, h)],
+                                      self.gb3[L1, g] if h == 0 else None)
+                    ops.conv3x3_wgrad(blk.a[h], blk.gp2[g], self.dwp[self._sub(L2, g, h)],
+                                      self.gb3[L2, g] if h == 0 else None)
+        gw1, gb1 = self.section(self.gflat, "conv1.weight"), self.section(self.gflat, "conv1.bias")
+        for g in range(G):
+            ops.stem_wgrad(pl.x, pl.g_stem[g], gw1[g * 64:(g + 1) * 64], gb1[g * 64:(g + 1) * 64], self.stem_s,
+                           self.stem_pad, x_cache=pl.x_cache)
+        L = 2 * nb
+        ops.unpack_wgrad3x3(self.dwp.view(L * G * G, 9, 64, 64), self.dw_sub)
+        self.section(self.gflat, "w3").copy_(
+            self.dw_sub.view(L, G, G, 64, 64, 3, 3).permute(0, 1, 3, 2, 4, 5, 6).reshape(L, self.F, self.F, 3, 3))
+        self.section(self.gflat, "b3").copy_(self.gb3.view(L, self.F))
+
+    def train_step(self, x, gt, dropout: bool = True, allreduce=None, optimizer=None):
+        pl = self.forward(x, train=True, dropout=dropout)
+        ops.yolo_loss(pl.y, gt, pl.loss, None, pl.dy)
+        self.run_backward(pl, pl.dy)
+        if allreduce is not None:
+            allreduce(self.gflat)
+        if optimizer is not None:
+            optimizer.step()
+        return pl

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from ..engine import BackboneEngine
+from ..engine_planar import PlanarEngine
 from .BaseModel import BaseModel
 
 
@@ -61,8 +62,10 @@ class GridBackbone(BaseModel):
             *[ResidualBlock(filters=filters, num_of_patches=block_patches) for _ in range(num_of_residual_blocks)])
         self.out = nn.Conv2d(filters, 5, stride=(1, 1), kernel_size=(head_k, head_k), padding=head_pad)
         self.sigmoid = nn.Sigmoid()
-        self.engine = BackboneEngine(filters, input_shape[0], input_shape[1], input_shape[2], num_of_residual_blocks,
-                                     stem_k, stem_s, stem_pad, head_k, head_pad, pool_rule)
+        # 64 channels: the fused tensor-core engine; 128, 192, ...: the same kernels on 64-channel planes (engine_planar)
+        Engine = BackboneEngine if filters == 64 else PlanarEngine
+        self.engine = Engine(filters, input_shape[0], input_shape[1], input_shape[2], num_of_residual_blocks,
+                             stem_k, stem_s, stem_pad, head_k, head_pad, pool_rule)
 
     def _prep_input(self, x: torch.Tensor, predict: bool) -> torch.Tensor:
         if predict:
@@ -108,6 +111,9 @@ class GridBackbone(BaseModel):
     def flat_optimizer(self, lr: float = 1e-4, capturable: bool = False):
         """One-kernel Adam over the flat parameter buffer (optim.FlatAdam); lr default = ModelMeta's (ModelMeta.py:86)."""
         from ..optim import FlatAdam
+        if not isinstance(self.engine, BackboneEngine):
+            raise NotImplementedError("flat_optimizer needs the flat parameter buffer of the 64-channel engine; use "
+                                      "torch.optim.Adam(model.parameters()) (ModelMeta.configure_optimizers) for wider models")
         self.engine.bind(dict(self.named_parameters()))
         return FlatAdam(self.engine, lr=lr, capturable=capturable)
 

@@ -86,6 +86,20 @@ def adam_flat(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, state=None)
           "fd_adam_flat")
 
 
+def act_mask(x, slope, chan_scale, residual, mask_out, out):
+    """64-channel plane: out = lrelu(x) * chan_scale + residual, mask_out = sign bits of x (nullable operands)."""
+    B, H, W, C = x.shape
+    check(lib().fd_act_mask(dptr(x, BF16), B, H * W, C, float(slope), dptr(chan_scale, F32), dptr(residual, BF16),
+                            dptr(mask_out, I32), dptr(out, BF16), cur_stream()), "fd_act_mask")
+
+
+def grad_mask(g, slope, mask_bits, chan_scale, out):
+    """64-channel plane: out = g * (mask bit ? 1 : slope) * chan_scale."""
+    B, H, W, C = g.shape
+    check(lib().fd_grad_mask(dptr(g, BF16), B, H * W, C, float(slope), dptr(mask_bits, I32), dptr(chan_scale, F32),
+                             dptr(out, BF16), cur_stream()), "fd_grad_mask")
+
+
 def dropout_scale(r, n_block, keep_block, keep_head, out):
     check(lib().fd_dropout_scale(dptr(r, F32), r.numel(), int(n_block), float(keep_block), float(keep_head),
                                  dptr(out, F32), cur_stream()), "fd_dropout_scale")

@@ -284,3 +284,50 @@ def _flat_of(model, eng):
     for name, p in model.named_parameters():
         eng._view(flat, name).copy_(p.data.to("cuda"))
     return flat
+
+
+def test_poolresnet_filters128_train_step_vs_oracle():
+    """train_model.py:16 trains PoolResnet(filters=128): the 64-channel tensor-core kernels on two channel planes
+    (engine_planar.PlanarEngine).  Head, summed loss, every parameter gradient and the decoded boxes against the fp32
+    oracle; same tolerances as the 64-channel engine (one more bf16 rounding per convolution for the chained partial
+    sums of the two input planes)."""
+    require_cuda()
+    PoolResnet = fd().models.PoolResnet.PoolResnet
+    p = seeded_poolresnet_params(128, seed=12)
+    m = PoolResnet(filters=128, input_shape=(3, 480, 480), num_of_patches=10)
+    m.load_state_dict(p, strict=True)
+    m = m.cuda().eval()
+    assert type(m.engine).__name__ == "PlanarEngine" and sum(q.numel() for q in m.parameters()) == 3013253
+    B = 2
+    gen = torch.Generator().manual_seed(13)
+    x = torch.rand(B, 3, 480, 480, generator=gen)
+    gt = torch.stack([torch.from_numpy(yo.grid_encode(synth_boxes(gen, 1, 100).numpy(), 10, 480, 480)) for _ in range(B)])
+    y_ref, loss_ref, g_ref = bo.train_step(x, gt, p, 10)
+    with torch.no_grad():
+        y_inf = m(x.cuda())                                   # inference path (no masks / argmax / cache)
+    d = (y_inf.cpu() - y_ref).abs()
+    print("F=128 head max/mean abs err", d.max().item(), d.mean().item())
+    assert d.max().item() <= HEAD_MAX and d.mean().item() <= HEAD_MEAN
+    loss = m.train_step(x.cuda(), gt.cuda())
+    assert abs(loss.item() - loss_ref.item()) <= LOSS_REL * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    worst = 0.0
+    for k, prm in m.named_parameters():
+        e = rel_err(prm.grad.cpu(), g_ref[k])
+        worst = max(worst, e)
+        assert e <= GRAD_REL, (k, e)
+    print("F=128 worst per-tensor gradient rel-L2", worst)
+    # autograd path (forward + loss.backward()) gives the same gradients as the fused call
+    fused = {k: prm.grad.clone() for k, prm in m.named_parameters()}
+    m.zero_grad()
+    y_hat = m(x.cuda())
+    L = fd().losses.YoloLoss
+    tot = 0
+    for i in range(B):
+        tot = tot + L.yolo_loss(y_hat[i], gt[i].cuda())
+    tot.backward()
+    for k, prm in m.named_parameters():
+        assert rel_err(prm.grad, fused[k]) <= 1e-3, k
+    kept = m.non_max_suppression(y_inf)
+    for i in range(B):
+        want = yo.reduce_bounding_boxes(y_inf[i].cpu().numpy(), 0.5, 0.5, (3, 480, 480), 10)
+        assert kept[i].cpu().numpy().tobytes() == want.tobytes()
