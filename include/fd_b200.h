@@ -224,6 +224,8 @@ FD_API int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B, in
  * padding `pad`, + bias, sigmoid.  x: [B,H,W,C] bf16, w: [5][C][K][K] fp32, y: [B,5,Ho,Wo] fp32. */
 /* w_t (nullable): the same weights pre-arranged by fd_head_pack ([K*K*5][C] fp32, tap-major, swizzled channel
  * groups); with it the C = 64 fast-path kernels run, without it a generic kernel transposes w itself. */
+/* bias == NULL (64-channel fast path only): y receives the PARTIAL LOGITS of this 64-channel plane -- no bias, no
+ * sigmoid -- for heads wider than 64 channels evaluated plane by plane (engine_planar.PlanarEngine). */
 FD_API int fd_head_pack(const float* w, int C, int K, float* w_t, void* stream);
 FD_API int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* w_t, const float* bias,
                 int B, int H, int W, int C, int K, int pad, float* y, void* stream);

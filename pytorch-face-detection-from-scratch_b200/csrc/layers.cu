@@ -666,8 +666,9 @@ head_fwd_c64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
   if (lane < P * 5) {
     const int j = lane / 5, o = lane - j * 5;
     if (ox0 + j < Wo) {
-      const float v = mine + __ldg(bias + o);
-      y[(static_cast<size_t>(n) * 5 + o) * Ho * Wo + oy * Wo + ox0 + j] = 1.f / (1.f + expf(-v));
+      // bias == NULL: partial logits of one 64-channel plane of a wider head (no bias, no sigmoid; engine_planar sums them)
+      y[(static_cast<size_t>(n) * 5 + o) * Ho * Wo + oy * Wo + ox0 + j] =
+          bias ? 1.f / (1.f + expf(-(mine + __ldg(bias + o)))) : mine;
     }
   }
 }
@@ -1154,10 +1155,11 @@ extern "C" int fd_head_pack(const float* w, int C, int K, float* w_t, void* stre
 
 extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const float* w, const float* w_t,
                            const float* bias, int B, int H, int W, int C, int K, int pad, float* y, void* stream) {
-  if (!x || !w || !bias || !y || B <= 0) return FD_EINVAL;
+  if (!x || !w || !y || B <= 0) return FD_EINVAL;
   if ((H * W * C) % 8 != 0) return FD_EUNSUPPORTED;
   const int Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1;
   if (Ho <= 0 || Wo <= 0) return FD_EINVAL;
+  if (!bias && !(w_t && C == 64)) return FD_EUNSUPPORTED;      // partial-logit mode: 64-channel fast path only
   if (w_t && C == 64 && ((K == 6 && pad == 0) || (K == 3 && pad == 1))) {
     const int strips = (Wo + kHeadStrip - 1) / kHeadStrip;
     int rows_per_cta = 512 / 32 / strips;                    // one warp per (output row, strip of 5 pixels)

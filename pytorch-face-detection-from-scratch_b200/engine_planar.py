@@ -11,7 +11,7 @@ they are:
   in ``fd_act_mask`` (LeakyReLU + sign-bit mask + Dropout2d multiplier + skip) / ``fd_grad_mask`` (its backward);
 * the weight gradient of sub-block (g, h) is ``fd_conv3x3_wgrad(x plane h, gradient plane g)``;
 * the stem runs once per output plane (the bf16 image cache is written by the first launch), the head on the
-  re-interleaved ``[B,H,W,64G]`` tensor through the generic head kernels.
+  64-channel head kernels plane by plane (partial logits summed before the sigmoid; tensor-core backward per plane).
 
 This is the FUNCTIONAL path for the wide models (same parity bar as the 64-channel engine; one more bf16 rounding per
 convolution for the chained partial sum) -- about 4x the launches of the fused 64-channel step and no fused block
@@ -81,7 +81,7 @@ class _PPlan:
         else:
             self.x_cache = None
         self.drop = None
-        self.x = self.xh = self.cs_head = None
+        self.x = self.head_in = self.w_head = None
 
 
 class PlanarEngine:
@@ -225,10 +225,19 @@ class PlanarEngine:
                 if blk.pool:
                     ops.maxpool2x2_fwd(blk.s[g], blk.out[g], blk.amax[g])
             cur = blk.out
-        pl.xh = torch.cat(cur, dim=3)                                            # [B,H,W,64G] for the head kernels
-        pl.cs_head = (pl.drop[nb].permute(1, 0, 2).reshape(B, self.F).contiguous() if pl.drop is not None else None)
-        ops.head_fwd(pl.xh, pl.cs_head, P["out.weight"].detach().float(), P["out.bias"].detach().float(), pl.y,
-                     self.head_pad)
+        # head: partial logits per plane through the 64-channel kernel (bias=None), summed + bias + sigmoid on [B,5,S,S]
+        wo = P["out.weight"].detach().float()
+        pl.head_in = cur
+        pl.w_head = [wo[:, g * 64:(g + 1) * 64].contiguous() for g in range(G)]
+        logits = None
+        for g in range(G):
+            wt = torch.empty(self.head_k * self.head_k * 5 * 64, dtype=F32, device=x.device)
+            ops.head_pack(pl.w_head[g], wt)
+            part = torch.empty_like(pl.y)
+            ops.head_fwd(cur[g], pl.drop[nb, g] if pl.drop is not None else None, pl.w_head[g], None, part, self.head_pad,
+                         w_t=wt)
+            logits = part if logits is None else logits + part
+        torch.sigmoid(logits + P["out.bias"].detach().float().view(1, 5, 1, 1), out=pl.y)
         return pl
 
     # ------------------------------------------------------------------ backward
@@ -239,12 +248,14 @@ class PlanarEngine:
         self.gflat.zero_()
         self.dwp.zero_()
         self.gb3.zero_()
-        dxh = torch.empty_like(pl.xh)
-        ops.head_bwd(pl.xh, pl.cs_head, P["out.weight"].detach().float(), pl.y, dy, self.head_pad, dxh, None, None,
-                     self.slope, None, self.section(self.gflat, "out.weight"), self.section(self.gflat, "out.bias"))
         last = pl.blocks[nb - 1]
-        for g in range(G):
-            last.G[g].copy_(dxh[..., g * 64:(g + 1) * 64])
+        gw_out = self.section(self.gflat, "out.weight")
+        for g in range(G):          # tensor-core head backward per plane; dbias is the same for every plane: count it once
+            dwg = torch.zeros_like(pl.w_head[g])
+            dbg = self.section(self.gflat, "out.bias") if g == 0 else torch.zeros(5, dtype=F32, device=dy.device)
+            ops.head_bwd(pl.head_in[g], drop[nb, g] if drop is not None else None, pl.w_head[g], pl.y, dy, self.head_pad,
+                         last.G[g], None, None, self.slope, None, dwg, dbg)
+            gw_out[:, g * 64:(g + 1) * 64].copy_(dwg)
         for k in range(nb - 1, -1, -1):
             blk = pl.blocks[k]
             L1, L2 = 2 * k, 2 * k + 1

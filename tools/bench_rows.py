@@ -80,6 +80,30 @@ def main():
     del m, eng, x, gt, opt
     torch.cuda.empty_cache()
 
+    # ---- rows 1/2 at the width train_model.py trains: PoolResnet(filters=128) on two 64-channel planes (PlanarEngine)
+    B = 64
+    torch.manual_seed(4)
+    m = fd.models.PoolResnet.PoolResnet(filters=128, input_shape=(3, 480, 480), num_of_patches=10).cuda().train()
+    eng = m.engine
+    eng.bind(dict(m.named_parameters()))
+    x = torch.rand(B, 3, 480, 480, generator=gen).cuda()
+    gt = fd.datasets.WIDERFace.dataset.convert_bbx_to_feature_map_batch([synth_boxes(gen, 1, 100) for _ in range(B)], 10,
+                                                                        (480, 480), device=dev)
+    topt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
+    for prm in m.parameters():
+        prm.grad = eng.grad_view([n for n, q in m.named_parameters() if q is prm][0])
+    us, n = timed(lambda: eng.train_step(x, gt, dropout=True, optimizer=topt), reps=10)
+    emit(row="1,2", what="PoolResnet(filters=128, S=10) train step: forward + summed YoloLoss + backward + torch Adam, batch 64, "
+                         "train-mode dropout (PlanarEngine: 64-channel kernels on two channel planes)", us=us, launches=n,
+         images_per_s=B / us * 1e6, tflops=3 * 3.997e9 * B / us / 1e6)
+    m.eval()
+    red = m.reduce_bounding_boxes
+    us, n = timed(lambda: red.batch_forward(eng.forward(x, train=False, dropout=False).y), reps=10)
+    emit(row="1,2", what="PoolResnet(filters=128, S=10) inference + decode + NMS, batch 64", us=us, launches=n,
+         images_per_s=B / us * 1e6, tflops=3.997e9 * B / us / 1e6)
+    del m, eng, x, gt, topt
+    torch.cuda.empty_cache()
+
     # ---- row 9: SeparableCNN
     B = 256
     torch.manual_seed(6)
