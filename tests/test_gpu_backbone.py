@@ -331,3 +331,25 @@ def test_poolresnet_filters128_train_step_vs_oracle():
     for i in range(B):
         want = yo.reduce_bounding_boxes(y_inf[i].cpu().numpy(), 0.5, 0.5, (3, 480, 480), 10)
         assert kept[i].cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_resnet_filters128_planar_vs_oracle():
+    """Resnet(filters=128) (3x3 stride-2 stem, 3x3 head, pooling while H > S) through PlanarEngine, B = 1."""
+    require_cuda()
+    Resnet = fd().models.Resnet.Resnet
+    p = seeded_poolresnet_params(128, seed=14, stem_k=3, stem_s=2, head_k=3)
+    m = Resnet(filters=128, input_shape=(3, 480, 480), num_of_patches=15)
+    m.load_state_dict(p, strict=True)
+    m = m.cuda().eval()
+    gen = torch.Generator().manual_seed(15)
+    x = torch.rand(1, 3, 480, 480, generator=gen)
+    gt = torch.stack([torch.from_numpy(yo.grid_encode(synth_boxes(gen, 101, 300).numpy(), 15, 480, 480))])
+    y_ref, loss_ref, g_ref = bo.train_step(x, gt, p, 15, forward=bo.resnet_forward)
+    loss = m.train_step(x.cuda(), gt.cuda())
+    pl = m.engine.plan(1, True)
+    d = (pl.y.cpu() - y_ref).abs()
+    print("Resnet F=128 head max/mean abs err", d.max().item(), d.mean().item())
+    assert d.max().item() <= HEAD_MAX and d.mean().item() <= HEAD_MEAN
+    assert abs(loss.item() - loss_ref.item()) <= LOSS_REL * abs(loss_ref.item())
+    for k, prm in m.named_parameters():
+        assert rel_err(prm.grad.cpu(), g_ref[k]) <= GRAD_REL, k
