@@ -45,30 +45,68 @@ class _PPlan:
         def masks(h, w):
             return [torch.empty((B, h, w, 2), dtype=torch.int32, device=device) for _ in range(G)]
 
+        # Runs of equal-shape blocks (a pooled block is a run of its own).  Per run and plane the weight-gradient
+        # operands are STACKED and interleaved like in BackboneEngine -- XA[2i] = input of block k0+i, XA[2i+1] = its a,
+        # GP[2i] = gp1, GP[2i+1] = gp2 -- so that ONE multi-problem launch per (gradient plane, input plane) covers all
+        # 2n layers of the run (12 weight-gradient launches per step instead of 80).
+        shapes, H, W = [], eng.H0, eng.W0
+        for k in range(eng.num_blocks):
+            shapes.append((H, W))
+            if eng.pools[k]:
+                H, W = H // 2, W // 2
+        runs, k = [], 0
+        while k < eng.num_blocks:
+            k1 = k
+            while (not eng.pools[k1]) and k1 + 1 < eng.num_blocks and shapes[k1 + 1] == shapes[k]:
+                k1 += 1
+            runs.append((k, k1))
+            k = k1 + 1
+        self.runs = runs
+        run_of, self.XA, self.GP = {}, {}, {}
+        for (k0, k1) in runs:
+            n = k1 - k0 + 1
+            h, w = shapes[k0]
+            self.XA[k0] = [torch.empty((2 * n, B, h, w, 64), dtype=BF16, device=device) for _ in range(G)]
+            self.GP[k0] = [torch.empty((2 * n, B, h, w, 64), dtype=BF16, device=device) for _ in range(G)] if train else None
+            for kk in range(k0, k1 + 1):
+                run_of[kk] = k0
+
+        def input_planes(kk):
+            """Planes holding the INPUT of block kk (= output of block kk-1 / the stem)."""
+            k0 = run_of[kk]
+            return [self.XA[k0][g][2 * (kk - k0)] for g in range(G)]
+
         H, W = eng.H0, eng.W0
-        self.act0 = planes(H, W)
+        self.act0 = input_planes(0)
         self.blocks: List[_PBlock] = []
         cur = self.act0
         for k in range(eng.num_blocks):
             b = _PBlock()
             b.H, b.W, b.pool = H, W, eng.pools[k]
             b.inp = cur
-            b.T, b.T2, b.a = planes(H, W), planes(H, W), planes(H, W)
+            k0 = run_of[k]
+            i = k - k0
+            b.T, b.T2 = planes(H, W), planes(H, W)
+            b.a = [self.XA[k0][g][2 * i + 1] for g in range(G)]
             b.ma = masks(H, W) if train else [None] * G
             b.mb = masks(H, W) if train else [None] * G
-            b.s = planes(H, W)
+            nxt = input_planes(k + 1) if k + 1 < eng.num_blocks else None
             b.amax = [None] * G
             if b.pool:
+                b.s = planes(H, W)
                 H, W = H // 2, W // 2
-                b.out = planes(H, W)
+                b.out = nxt if nxt is not None else planes(H, W)
                 if train:
                     b.amax = [torch.empty((B, H, W, 8), dtype=torch.int16, device=device) for _ in range(G)]
             else:
+                b.s = nxt if nxt is not None else planes(H, W)
                 b.out = b.s
             if train:
                 b.G = planes(H, W)                      # gradient w.r.t. the block OUTPUT (post-pool resolution)
                 b.gs = planes(b.H, b.W) if b.pool else None
-                b.gp1, b.gp2, b.U = planes(b.H, b.W), planes(b.H, b.W), planes(b.H, b.W)
+                b.gp1 = [self.GP[k0][g][2 * i] for g in range(G)]
+                b.gp2 = [self.GP[k0][g][2 * i + 1] for g in range(G)]
+                b.U = planes(b.H, b.W)
             self.blocks.append(b)
             cur = b.out
         self.y = torch.empty((B, 5, eng.So_h, eng.So_w), dtype=F32, device=device)
@@ -287,13 +325,15 @@ class PlanarEngine:
                     dst = gprev[h] if g == G - 1 else (blk.U[h] if (g % 2 == 0) else blk.T[h])
                     ops.conv3x3(blk.gp1[g], w, slope=self.slope, residual=prev, out=dst)
                     prev = dst
-            # weight / bias gradients of the 2 x G x G sub-blocks
-            for g in range(G):
-                for h in range(G):
-                    ops.conv3x3_wgrad(blk.inp[h], blk.gp1[g], self.dwp[self._sub(L1, g, h)],
-                                      self.gb3[L1, g] if h == 0 else None)
-                    ops.conv3x3_wgrad(blk.a[h], blk.gp2[g], self.dwp[self._sub(L2, g, h)],
-                                      self.gb3[L2, g] if h == 0 else None)
+            # weight / bias gradients: once per run, when the gp1 / gp2 of all its blocks are final
+            if k in pl.XA:
+                n3 = 9 * 64 * 64
+                dwp_flat, gb3_flat = self.dwp.view(-1), self.gb3.view(-1)
+                for g in range(G):
+                    for h in range(G):
+                        first = self._sub(2 * k, g, h)
+                        ops.conv3x3_wgrad_multi(pl.XA[k][h], pl.GP[k][g], dwp_flat[first * n3:], G * G * n3,
+                                                gb3_flat[(2 * k * G + g) * 64:] if h == 0 else None, G * 64)
         gw1, gb1 = self.section(self.gflat, "conv1.weight"), self.section(self.gflat, "conv1.bias")
         for g in range(G):
             ops.stem_wgrad(pl.x, pl.g_stem[g], gw1[g * 64:(g + 1) * 64], gb1[g * 64:(g + 1) * 64], self.stem_s,
