@@ -38,6 +38,8 @@ typedef uint16_t fd_bf16;
 
 /* epilogue flags for fd_conv3x3 */
 #define FD_EPI_LRELU 1   /* v = v > 0 ? v : slope * v            (PoolResnet.py:36,38) */
+#define FD_CONV_1X1 2    /* fd_conv3x3: use only the centre tap of the packed weights = a 1x1 convolution
+                          * (models/SeparableCNN.py:13-19,29-35 on 64-channel planes) */
 
 FD_API int fd_version(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
@@ -178,6 +180,11 @@ FD_API int fd_allreduce_sum_f32(void* const* windows, int rank, int world, float
  * without FD_EPI_LRELU), so the activation of models/PoolResnet.py:35-40 runs here on 64-channel planes [B,HW,64]:
  *   fd_act_mask : out = lrelu(x) * chan_scale[n,c] + residual ; mask_out bit = sign bit of x clear (nullable operands)
  *   fd_grad_mask: out = g * (mask bit ? 1 : slope) * chan_scale[n,c]   (mask_bits NULL = all ones) */
+/* Depthwise 3x3 (pad 1, no bias) + LeakyReLU on one 64-channel plane [B,H,W,64] (models/SeparableCNN.py:20-27,45-46);
+ * w_dw: [9 taps][64] fp32 as written by fd_sep_pack.  Used by the separable backbone on channel planes (filters = 128);
+ * the 64-channel model runs the fused fd_sepblock_fwd. */
+FD_API int fd_dwconv3x3_lrelu(const fd_bf16* x, const float* w_dw, int B, int H, int W, int C, float slope, fd_bf16* out,
+                       void* stream);
 FD_API int fd_act_mask(const fd_bf16* x, int B, int HW, int C, float slope, const float* chan_scale, const fd_bf16* residual,
                 uint32_t* mask_out, fd_bf16* out, void* stream);
 FD_API int fd_grad_mask(const fd_bf16* g, int B, int HW, int C, float slope, const uint32_t* mask_bits, const float* chan_scale,

@@ -168,8 +168,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         const uint32_t in_lo = sdesc_lo(smem_u32(sIn + s * stage_bytes), 16);
 #pragma unroll 1
         for (int mb = 0; mb < p.nblk; ++mb) {
-          issue_conv3x3_block(tmem_base + static_cast<uint32_t>((s * 4 + mb) * kC),
-                              in_lo + static_cast<uint32_t>(mb * 1024), w_lo, wp_units, idesc, [](int) {});
+          if (p.flags & FD_CONV_1X1) {
+            // 1x1 convolution (pointwise layers of the separable backbone on channel planes): only the centre tap --
+            // A rows shifted by Wp + 1, B = tap 4 of the packed weights -- 4 MMAs instead of 36
+            const uint32_t a_c = in_lo + static_cast<uint32_t>(mb * 1024) + wp_units + 8u, b_c = w_lo + 4u * 512u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + static_cast<uint32_t>((s * 4 + mb) * kC), sdesc_sw128(a_c + 2 * k),
+                        sdesc_sw128(b_c + 2 * k), idesc, k != 0 ? 1u : 0u);
+          } else {
+            issue_conv3x3_block(tmem_base + static_cast<uint32_t>((s * 4 + mb) * kC),
+                                in_lo + static_cast<uint32_t>(mb * 1024), w_lo, wp_units, idesc, [](int) {});
+          }
           umma_commit(acc_full + s * 4 + mb);   // this 128-row block is ready for the epilogue
         }
         umma_commit(in_empty + s);              // input tile free once these MMAs have read it

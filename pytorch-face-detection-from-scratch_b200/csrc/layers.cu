@@ -977,6 +977,45 @@ __global__ void grad_mask_kernel(const __nv_bfloat16* __restrict__ g, long n8, i
   }
 }
 
+// Depthwise 3x3 (pad 1, no bias) + LeakyReLU on one 64-channel plane (models/SeparableCNN.py:20-27,45-46) for the
+// separable backbone on channel planes (filters = 128); the 64-channel model runs the fused fd_sepblock_fwd instead.
+// Thread = 8 channels of one pixel; the 9 x 64 tap-major fp32 weights sit in shared memory.
+__global__ void __launch_bounds__(256)
+dwconv3x3_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, int B, int H, int W, float slope,
+                       __nv_bfloat16* __restrict__ out) {
+  __shared__ float sW[9 * 64];
+  pdl_trigger();
+  pdl_wait();
+  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sW[i] = __ldg(w + i);
+  __syncthreads();
+  const int rows = B * H, per_row = W * 8;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, y = row - n * H;
+    for (int idx = threadIdx.x; idx < per_row; idx += blockDim.x) {
+      const int xx = idx >> 3, c8 = idx & 7;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = y + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = xx + kx - 1;
+          if (ix < 0 || ix >= W) continue;
+          float v[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + iy) * W + ix) * 64 + c8 * 8)), v);
+          const float* wt = sW + (ky * 3 + kx) * 64 + c8 * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt[j], v[j], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], acc[j] * slope);
+      *reinterpret_cast<uint4*>(out + (static_cast<size_t>(row) * W + xx) * 64 + c8 * 8) = pack8(acc);
+    }
+  }
+}
+
 inline int grid_for(long total, int block, int cap_mult = 8) {
   long g = (total + block - 1) / block;
   const long cap = static_cast<long>(sm_count()) * cap_mult;
@@ -1025,6 +1064,17 @@ extern "C" int fd_adam_flat(float* p, const float* g, float* m, float* v, long n
   if (n % 4 != 0) return FD_EUNSUPPORTED;              // the flat buffers are padded to 16 bytes per section
   launch_k(adam_flat_kernel, dim3(grid_for(n / 4, 256, 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g, m, v, n,
            lr, beta1, beta2, eps, weight_decay, step, state);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_dwconv3x3_lrelu(const fd_bf16* x, const float* w_dw, int B, int H, int W, int C, float slope, fd_bf16* out,
+                                 void* stream) {
+  if (!x || !w_dw || !out || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
+  if (C != 64 || !(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;
+  launch_k(dwconv3x3_lrelu_kernel, dim3(grid_for(static_cast<long>(B) * H, 1, 16)), dim3(256), 0,
+           static_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), w_dw, B, H, W, slope,
+           reinterpret_cast<__nv_bfloat16*>(out));
   count_launch();
   return launch_status();
 }

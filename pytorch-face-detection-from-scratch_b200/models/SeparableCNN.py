@@ -8,8 +8,8 @@ H > 16 and the decoder works with 30-pixel patches -- reproduced, not fixed.
 The forward (BASELINE config 4: inference + NMS) runs on hand-written sm_100a kernels: the stem and head kernels of
 the residual backbones, and ONE fused kernel per separable block (``fd_sepblock_fwd``: 1x1 -> LeakyReLU -> depthwise 3x3 ->
 LeakyReLU -> 1x1 -> + skip -> MaxPool2d(2) where the block pools; intermediates in shared memory).  Inference only:
-the backward of this backbone is not built (``train()`` mode raises), and the tensor-core kernels are instantiated
-for ``filters == 64``.  There is no CPU path.
+the backward of this backbone is not built (``train()`` mode raises).  ``filters == 64`` runs the fused block kernel,
+``filters == 128`` (the reference's ``__main__``) the 64-channel kernels on two channel planes.  There is no CPU path.
 """
 from __future__ import annotations
 
@@ -155,6 +155,123 @@ class SeparableEngine:
         return pl["y"]
 
 
+class SeparablePlanarEngine:
+    """``filters = 64 * G`` (the reference's ``__main__`` builds 128, SeparableCNN.py:124) on G channel planes with the
+    64-channel kernels: a pointwise 64G -> 64G convolution is, per output plane, a chain of G ``fd_conv3x3`` calls in
+    centre-tap (``FD_CONV_1X1``) mode whose raw partial sums ride on the residual input (the skip connection is the
+    first addend of the pw2 chain); LeakyReLU after pw1 in ``fd_act_mask``, depthwise 3x3 + LeakyReLU per plane in
+    ``fd_dwconv3x3_lrelu``, pooling, stem and head (partial logits per plane) as in engine_planar.PlanarEngine.
+    Functional path (the fused ``fd_sepblock_fwd`` is the 64-channel fast path); inference only."""
+
+    def __init__(self, filters, in_ch, in_h, in_w, num_blocks, stem_k, stem_s, stem_pad, head_k, head_pad,
+                 block_patches, slope=0.2):
+        if filters % 64 != 0 or filters < 128:
+            raise NotImplementedError("SeparableCNN kernels exist for filters = 64 (fused) and 64 * G (channel planes); "
+                                      "got filters=%d" % filters)
+        self.F, self.G, self.num_blocks, self.slope = filters, filters // 64, num_blocks, slope
+        self.in_ch, self.in_h, self.in_w, self.stem_k = in_ch, in_h, in_w, stem_k
+        self.stem_s, self.stem_pad, self.head_k, self.head_pad = stem_s, stem_pad, head_k, head_pad
+        H = (in_h + 2 * stem_pad - stem_k) // stem_s + 1
+        W = (in_w + 2 * stem_pad - stem_k) // stem_s + 1
+        self.shapes, self.pools = [], []
+        for _ in range(num_blocks):
+            self.shapes.append((H, W))
+            pool = H > block_patches
+            self.pools.append(pool)
+            if pool:
+                H, W = H // 2, W // 2
+        self.So_h, self.So_w = H + 2 * head_pad - head_k + 1, W + 2 * head_pad - head_k + 1
+        self.device, self.params, self.plans = None, None, {}
+
+    def bind(self, params):
+        dev = params["conv1.weight"].device
+        if dev.type != "cuda":
+            raise RuntimeError("the fd_b200 backbone runs on CUDA only (no CPU fallback): call model.cuda()")
+        if dev != self.device:
+            self.device = dev
+            self.plans.clear()
+        self.params = params
+
+    def plan(self, B):
+        if B not in self.plans:
+            G, dev = self.G, self.device
+
+            def planes(h, w):
+                return [torch.empty((B, h, w, 64), dtype=BF16, device=dev) for _ in range(G)]
+            H0, W0 = self.shapes[0]
+            pl = {"act0": planes(H0, W0), "blocks": []}
+            for (h, w), pool in zip(self.shapes, self.pools):
+                b = {"T": planes(h, w), "T2": planes(h, w), "t1": planes(h, w), "t2": planes(h, w)}
+                b["s"] = planes(h, w)
+                b["out"] = planes(h // 2, w // 2) if pool else b["s"]
+                pl["blocks"].append(b)
+            pl["y"] = torch.empty((B, 5, self.So_h, self.So_w), dtype=F32, device=dev)
+            self.plans[B] = pl
+        return self.plans[B]
+
+    def _sub(self, layer, g, h):
+        return (layer * self.G + g) * self.G + h
+
+    def pack_weights(self):
+        G, nb, P = self.G, self.num_blocks, self.params
+        pw, dw = [], []
+        for k in range(nb):
+            pre = f"residual_blocks.{k}."
+            pw += [P[pre + "pointwise_conv1.weight"].detach(), P[pre + "pointwise_conv2.weight"].detach()]
+            dw.append(P[pre + "depthwise_conv.weight"].detach())
+        L = 2 * nb
+        sub = torch.stack(pw).float().view(L, G, 64, G, 64).permute(0, 1, 3, 2, 4).reshape(L * G * G, 64, 64)
+        self.w_pk = torch.zeros((L * G * G, 9, 64, 64), dtype=BF16, device=self.device)      # only the centre tap is read
+        self.w_pk[:, 4] = sub.to(BF16)
+        self.w_dw = torch.stack(dw).float().view(nb, G, 64, 9).permute(0, 1, 3, 2).contiguous()     # [nb, G, 9, 64]
+
+    def _pw_chain(self, srcs, layer, g, first_residual, dst_a, dst_b):
+        prev = first_residual
+        for h in range(self.G):
+            dst = dst_b if (h % 2) else dst_a
+            ops.conv3x3(srcs[h], self.w_pk[self._sub(layer, g, h)], slope=self.slope, lrelu=False, residual=prev, out=dst,
+                        flags=ops.CONV_1X1)
+            prev = dst
+        return prev
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        G, nb, P = self.G, self.num_blocks, self.params
+        pl = self.plan(x.shape[0])
+        self.pack_weights()
+        w1, b1 = P["conv1.weight"].detach().float(), P["conv1.bias"].detach().float()
+        for g in range(G):
+            ops.stem_fwd(x, w1[g * 64:(g + 1) * 64], b1[g * 64:(g + 1) * 64], pl["act0"][g], self.stem_s, self.stem_pad)
+        cur = pl["act0"]
+        for k, b in enumerate(pl["blocks"]):
+            for g in range(G):
+                raw = self._pw_chain(cur, 2 * k, g, None, b["T"][g], b["T2"][g])
+                ops.act_mask(raw, self.slope, None, None, None, b["t1"][g])
+            for g in range(G):
+                ops.dwconv3x3_lrelu(b["t1"][g], self.w_dw[k, g], self.slope, b["t2"][g])
+            for g in range(G):
+                # pw2 + skip: the block input is the first addend of the chain; the last call writes the sum
+                prev = cur[g]
+                for h in range(G):
+                    dst = b["s"][g] if h == G - 1 else (b["T"][g] if (h % 2 == 0) else b["T2"][g])
+                    ops.conv3x3(b["t2"][h], self.w_pk[self._sub(2 * k + 1, g, h)], slope=self.slope, lrelu=False,
+                                residual=prev, out=dst, flags=ops.CONV_1X1)
+                    prev = dst
+                if self.pools[k]:
+                    ops.maxpool2x2_fwd(b["s"][g], b["out"][g])
+            cur = b["out"]
+        wo = P["out.weight"].detach().float()
+        logits = None
+        for g in range(G):
+            wg = wo[:, g * 64:(g + 1) * 64].contiguous()
+            wt = torch.empty(self.head_k * self.head_k * 5 * 64, dtype=F32, device=x.device)
+            ops.head_pack(wg, wt)
+            part = torch.empty_like(pl["y"])
+            ops.head_fwd(cur[g], None, wg, None, part, self.head_pad, w_t=wt)
+            logits = part if logits is None else logits + part
+        torch.sigmoid(logits + P["out.bias"].detach().float().view(1, 5, 1, 1), out=pl["y"])
+        return pl["y"]
+
+
 class SeparableCNN(BaseModel):
     def __init__(self, filters, input_shape, num_of_residual_blocks=10, probability_threshold=0.5, iou_threshold=0.5,
                  pretrained=False, input_kernel_size=10, input_stride=8, output_kernel_size=6, output_padding=0):
@@ -169,9 +286,10 @@ class SeparableCNN(BaseModel):
         self.out = nn.Conv2d(filters, 5, stride=(1, 1), kernel_size=(output_kernel_size, output_kernel_size),
                              padding=output_padding)
         self.sigmoid = nn.Sigmoid()
-        self.engine = SeparableEngine(filters, input_shape[0], input_shape[1], input_shape[2], num_of_residual_blocks,
-                                      input_kernel_size, input_stride, input_kernel_size - input_stride,
-                                      output_kernel_size, output_padding, block_patches=self.num_of_patches)
+        Engine = SeparableEngine if filters == 64 else SeparablePlanarEngine       # fused kernel / channel planes
+        self.engine = Engine(filters, input_shape[0], input_shape[1], input_shape[2], num_of_residual_blocks,
+                             input_kernel_size, input_stride, input_kernel_size - input_stride,
+                             output_kernel_size, output_padding, block_patches=self.num_of_patches)
 
     def forward(self, x: torch.Tensor, predict: torch.Tensor = torch.tensor(0)):
         is_predict = bool(predict == 1)

@@ -11,6 +11,7 @@ from .native import ChainBwdBlock, ChainFwdBlock, check, cur_stream, dptr, lib
 BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
 
 EPI_LRELU = 1
+CONV_1X1 = 2          # fd_conv3x3: centre tap only (FD_CONV_1X1)
 
 
 def conv3x3(x, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_scale=None, residual=None, mask_out=None,
@@ -84,6 +85,13 @@ def adam_flat(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, state=None)
     check(lib().fd_adam_flat(dptr(p, F32), dptr(g, F32), dptr(m, F32), dptr(v, F32), p.numel(), float(lr), float(beta1),
                              float(beta2), float(eps), float(weight_decay), int(step), dptr(state, I32), cur_stream()),
           "fd_adam_flat")
+
+
+def dwconv3x3_lrelu(x, w_dw, slope, out):
+    """64-channel plane: out = lrelu(depthwise3x3(x)); w_dw [9,64] fp32 (fd_sep_pack layout)."""
+    B, H, W, C = x.shape
+    check(lib().fd_dwconv3x3_lrelu(dptr(x, BF16), dptr(w_dw, F32), B, H, W, C, float(slope), dptr(out, BF16), cur_stream()),
+          "fd_dwconv3x3_lrelu")
 
 
 def act_mask(x, slope, chan_scale, residual, mask_out, out):

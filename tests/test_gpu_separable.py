@@ -132,3 +132,39 @@ def test_separable_model_batch256_vs_oracle_and_train_mode_raises():
     m.train()
     with pytest.raises(NotImplementedError):
         m(x[:1].cuda())
+
+
+def test_separable_filters128_planar_vs_oracle():
+    """SeparableCNN(filters=128) (the width of the reference's __main__, SeparableCNN.py:124) on two channel planes:
+    centre-tap fd_conv3x3 chains for the pointwise convolutions, fd_dwconv3x3_lrelu, planar head."""
+    require_cuda()
+    from tests.util import seeded_separable_params
+    p = seeded_separable_params(128, seed=11)
+    m = fd().models.SeparableCNN.SeparableCNN(filters=128, input_shape=(3, 480, 480))
+    m.load_state_dict(p, strict=True)
+    m = m.cuda().eval()
+    assert type(m.engine).__name__ == "SeparablePlanarEngine" and sum(q.numel() for q in m.parameters()) == 400773
+    x = torch.rand(3, 3, 480, 480, generator=torch.Generator().manual_seed(2))
+    y = m(x.cuda()).cpu()
+    with torch.no_grad():
+        want = bo.separable_forward(x, p)
+    d = (y - want).abs()
+    print("separable F=128 head max/mean abs err", d.max().item(), d.mean().item())
+    assert d.max().item() <= 2e-2 and d.mean().item() <= 2e-3
+    kept = m.non_max_suppression(y.cuda())
+    for i in range(3):
+        ref = yo.reduce_bounding_boxes(y[i].numpy(), 0.5, 0.5, (3, 480, 480), 16)
+        assert kept[i].cpu().numpy().tobytes() == ref.tobytes()
+
+
+def test_depthwise_plane_kernel_vs_torch():
+    require_cuda()
+    ops = fd().ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 13, 9, 64, generator=g).cuda().bfloat16()
+    dw = (torch.randn(64, 1, 3, 3, generator=g) * 0.4).cuda()
+    w_dw = dw[:, 0].reshape(64, 9).t().contiguous()
+    out = torch.empty_like(x)
+    ops.dwconv3x3_lrelu(x, w_dw, 0.2, out)
+    want = F.leaky_relu(F.conv2d(x.float().permute(0, 3, 1, 2), dw, padding=1, groups=64), 0.2).permute(0, 2, 3, 1)
+    assert rel_err(out.float(), want) <= 4e-3
