@@ -115,6 +115,13 @@ def main():
     emit(row=9, what="SeparableCNN(filters=64) inference + decode + NMS, batch 256, fp32 images resident in HBM", us=us,
          launches=n, images_per_s=B / us * 1e6,
          hbm_floor_us=(B * 3 * 480 * 480 * 4 + 2 * B * 128 * (3600 + 900 + 8 * 225)) / HBM / 1e3)
+    del sm
+    torch.manual_seed(7)
+    sm = fd.models.SeparableCNN.SeparableCNN(filters=128, input_shape=(3, 480, 480)).cuda().eval()
+    sm.engine.bind(dict(sm.named_parameters()))
+    us, n = timed(lambda: red.batch_forward(sm.engine.forward(x)), reps=5)
+    emit(row=9, what="SeparableCNN(filters=128) inference + decode + NMS, batch 256 (channel planes: 1x1-mode fd_conv3x3 "
+                     "chains + fd_dwconv3x3_lrelu)", us=us, launches=n, images_per_s=B / us * 1e6)
     w_pw = (torch.randn(2, 64, 64, device=dev) * 0.1).bfloat16()
     w_dw = torch.randn(9, 64, device=dev) * 0.3
     for H in (60, 30, 15):
