@@ -353,3 +353,36 @@ def test_resnet_filters128_planar_vs_oracle():
     assert abs(loss.item() - loss_ref.item()) <= LOSS_REL * abs(loss_ref.item())
     for k, prm in m.named_parameters():
         assert rel_err(prm.grad.cpu(), g_ref[k]) <= GRAD_REL, k
+
+
+@pytest.mark.parametrize("filters", [64, 128])
+def test_modelmeta_training_loop_like_train_model_py(filters):
+    """train_model.py:27-53 without Lightning: ModelMeta(model).configure_optimizers() + training_step() + backward +
+    optimizer.step(), through the reference's import paths (install_dropin).  Four steps on one batch reduce its loss;
+    the step metrics are finite; filters=128 is the width the script trains."""
+    require_cuda()
+    fd().install_dropin()
+    from models import ModelMeta
+    from models.PoolResnet import PoolResnet
+    from datasets.WIDERFace.dataset import convert_bbx_to_feature_map_batch
+    torch.manual_seed(0)
+    model = PoolResnet(filters=filters, input_shape=(3, 480, 480), num_of_patches=10, num_of_residual_blocks=10).cuda()
+    meta = ModelMeta(model=model, lr=1e-4)           # the reference's learning rate (train_model.py:18)
+    (opt,), _ = meta.configure_optimizers()
+    gen = torch.Generator().manual_seed(3)
+    B = 4
+    x = torch.rand(B, 3, 480, 480, generator=gen).cuda()
+    boxes = [synth_boxes(gen, 1, 40) for _ in range(B)]
+    y = convert_bbx_to_feature_map_batch(boxes, 10, (480, 480), device=torch.device("cuda"))
+    model.eval()                                   # deterministic (no dropout) so that the loss must go down
+    losses = []
+    for it in range(4):
+        opt.zero_grad()
+        out = meta.training_step((x, y, boxes), it)
+        out["loss"].backward()
+        opt.step()
+        losses.append(float(out["loss"].detach()))
+        assert all(map(lambda v: torch.isfinite(torch.as_tensor(float(v))), (out["total_iou"], out["total_recall"],
+                                                                               out["total_precision"])))
+    print("ModelMeta loop losses", losses)
+    assert losses[3] < losses[0] and losses[1] < losses[0]
