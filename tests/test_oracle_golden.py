@@ -182,3 +182,36 @@ def test_separable_oracle_matches_reference_seeded():
         rows = yo.reduce_bounding_boxes(g["y"][i], 0.47, 0.3, (3, 480, 480), 16)
         k = int(g["counts"][i])
         assert rows.shape[0] == k and rows.tobytes() == g["boxes"][i, :k].tobytes()
+
+
+def test_wide_models_oracle_matches_reference_seeded():
+    """The 128-channel models (train_model.py:27-32 PoolResnet(filters=128); SeparableCNN.py:124 SeparableCNN(128))
+    against the REAL reference (tests/golden/make_golden_wide.py): same seeded construction, identical head, loss and
+    gradient norms -- pins the oracle the channel-plane engines are tested against."""
+    import torch
+    from oracle import backbone_oracle as bo
+    from oracle import yolo_oracle as yo
+    from tests.util import seeded_poolresnet_params, seeded_separable_params, synth_boxes
+    g = load_golden("wide_seed12.npz")
+    p = seeded_poolresnet_params(128, seed=12)
+    for k, v in p.items():
+        s = g["pool_w_sum." + k]
+        assert abs(v.double().sum().item() - s[0]) < 1e-9 and abs(v.double().abs().sum().item() - s[1]) < 1e-9, k
+    x = torch.rand(1, 3, 480, 480, generator=torch.Generator().manual_seed(13))
+    boxes = synth_boxes(torch.Generator().manual_seed(14), 1, 100)
+    y = torch.from_numpy(yo.grid_encode(boxes.numpy(), 10, 480, 480))[None]
+    assert y.numpy().tobytes() == g["pool_y"].tobytes()
+    y_hat, loss, grads = bo.train_step(x, y, p, 10)
+    assert (y_hat - torch.from_numpy(g["pool_y_hat"])).abs().max().item() <= 1e-6
+    assert abs(loss.item() - float(g["pool_loss"])) <= 1e-5 * abs(float(g["pool_loss"]))
+    for k, v in grads.items():
+        n = float(g["pool_g_norm." + k])
+        assert abs(v.double().norm().item() - n) <= 1e-4 * max(n, 1e-12), k
+    ps = seeded_separable_params(128, seed=11)
+    for k, v in ps.items():
+        s = g["sep_w_sum." + k]
+        assert abs(v.double().sum().item() - s[0]) < 1e-9 and abs(v.double().abs().sum().item() - s[1]) < 1e-9, k
+    xs = torch.rand(1, 3, 480, 480, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ys = bo.separable_forward(xs, ps)
+    assert (ys - torch.from_numpy(g["sep_y_hat"])).abs().max().item() <= 1e-6
