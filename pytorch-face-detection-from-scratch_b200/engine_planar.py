@@ -192,6 +192,7 @@ class PlanarEngine:
             self.gb3 = torch.zeros((L, G, 64), dtype=F32, device=dev)
             self.w_fwd = torch.empty((L * G * G, 9, 64, 64), dtype=BF16, device=dev)
             self.w_dgrad = torch.empty((L * G * G, 9, 64, 64), dtype=BF16, device=dev)
+            self.sides = [torch.cuda.Stream(device=dev) for _ in range(self.G - 1)]
             self.plans.clear()
         self.params = params
 
@@ -203,6 +204,22 @@ class PlanarEngine:
 
     def _sub(self, layer, g, h):
         return (layer * self.G + g) * self.G + h
+
+    # The per-plane chains of a layer are independent of each other and, behind the last pooling stage, each of their
+    # launches fills less than half of the GPU (one tile per image): plane g > 0 runs on a side stream, forked from and
+    # joined into the main stream around every group of chains (captured into the CUDA graph as parallel branches).
+    def _fork(self):
+        main = torch.cuda.current_stream()
+        for s_ in self.sides:
+            s_.wait_stream(main)
+        return main
+
+    def _join(self, main):
+        for s_ in self.sides:
+            main.wait_stream(s_)
+
+    def _on(self, main, g):
+        return torch.cuda.stream(main if g == 0 else self.sides[g - 1])
 
     def pack_weights(self):
         """[L,64G,64G,3,3] fp32 -> sub-blocks [(L,g,h),64,64,3,3] (torch data movement) -> bf16 forward / dgrad packing."""
@@ -253,15 +270,21 @@ class PlanarEngine:
                          x_cache=pl.x_cache if g == 0 else None)
         cur = pl.act0
         for k, blk in enumerate(pl.blocks):
+            main = self._fork()
             for g in range(G):
-                raw = self._conv_sum(cur, self.w_fwd, 2 * k, g, self.b3[2 * k, g], blk.T[g], blk.T2[g])
-                ops.act_mask(raw, self.slope, None, None, blk.ma[g], blk.a[g])
+                with self._on(main, g):
+                    raw = self._conv_sum(cur, self.w_fwd, 2 * k, g, self.b3[2 * k, g], blk.T[g], blk.T2[g])
+                    ops.act_mask(raw, self.slope, None, None, blk.ma[g], blk.a[g])
+            self._join(main)
+            main = self._fork()
             for g in range(G):
-                raw = self._conv_sum(blk.a, self.w_fwd, 2 * k + 1, g, self.b3[2 * k + 1, g], blk.T[g], blk.T2[g])
-                ops.act_mask(raw, self.slope, pl.drop[k, g] if pl.drop is not None else None, cur[g], blk.mb[g],
-                             blk.s[g])
-                if blk.pool:
-                    ops.maxpool2x2_fwd(blk.s[g], blk.out[g], blk.amax[g])
+                with self._on(main, g):
+                    raw = self._conv_sum(blk.a, self.w_fwd, 2 * k + 1, g, self.b3[2 * k + 1, g], blk.T[g], blk.T2[g])
+                    ops.act_mask(raw, self.slope, pl.drop[k, g] if pl.drop is not None else None, cur[g], blk.mb[g],
+                                 blk.s[g])
+                    if blk.pool:
+                        ops.maxpool2x2_fwd(blk.s[g], blk.out[g], blk.amax[g])
+            self._join(main)
             cur = blk.out
         # head: partial logits per plane through the 64-channel kernel (bias=None), summed + bias + sigmoid on [B,5,S,S]
         wo = P["out.weight"].detach().float()
@@ -297,34 +320,44 @@ class PlanarEngine:
         for k in range(nb - 1, -1, -1):
             blk = pl.blocks[k]
             L1, L2 = 2 * k, 2 * k + 1
+            main = self._fork()
             for g in range(G):
-                cs = drop[k, g] if drop is not None else None
-                if blk.pool:
-                    ops.maxpool2x2_bwd(blk.s[g], blk.G[g], blk.gs[g], blk.mb[g], cs, self.slope, blk.gp2[g],
-                                       argmax=blk.amax[g])
-                else:
-                    ops.grad_mask(blk.G[g], self.slope, blk.mb[g], cs, blk.gp2[g])
+                with self._on(main, g):
+                    cs = drop[k, g] if drop is not None else None
+                    if blk.pool:
+                        ops.maxpool2x2_bwd(blk.s[g], blk.G[g], blk.gs[g], blk.mb[g], cs, self.slope, blk.gp2[g],
+                                           argmax=blk.amax[g])
+                    else:
+                        ops.grad_mask(blk.G[g], self.slope, blk.mb[g], cs, blk.gp2[g])
+            self._join(main)
             GS = blk.gs if blk.pool else blk.G
             # gp1[h] = (sum_g dgrad(gp2[g], W2[g][h])) * lrelu'(a[h])
+            main = self._fork()
             for h in range(G):
-                prev = None
-                for g in range(G):
-                    w = self.w_dgrad[self._sub(L2, g, h)]
-                    if g < G - 1:
-                        dst = blk.U[h] if (g % 2 == 0) else blk.T[h]
-                        ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, out=dst)
-                        prev = dst
-                    else:
-                        ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, mask_in=blk.ma[h], out2=blk.gp1[h])
+                with self._on(main, h):
+                    prev = None
+                    for g in range(G):
+                        w = self.w_dgrad[self._sub(L2, g, h)]
+                        if g < G - 1:
+                            dst = blk.U[h] if (g % 2 == 0) else blk.T[h]
+                            ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, out=dst)
+                            prev = dst
+                        else:
+                            ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, mask_in=blk.ma[h],
+                                        out2=blk.gp1[h])
+            self._join(main)
             # G_{k-1}[h] = sum_g dgrad(gp1[g], W1[g][h]) + GS[h]
             gprev = pl.blocks[k - 1].G if k > 0 else pl.g_stem
+            main = self._fork()
             for h in range(G):
-                prev = GS[h]
-                for g in range(G):
-                    w = self.w_dgrad[self._sub(L1, g, h)]
-                    dst = gprev[h] if g == G - 1 else (blk.U[h] if (g % 2 == 0) else blk.T[h])
-                    ops.conv3x3(blk.gp1[g], w, slope=self.slope, residual=prev, out=dst)
-                    prev = dst
+                with self._on(main, h):
+                    prev = GS[h]
+                    for g in range(G):
+                        w = self.w_dgrad[self._sub(L1, g, h)]
+                        dst = gprev[h] if g == G - 1 else (blk.U[h] if (g % 2 == 0) else blk.T[h])
+                        ops.conv3x3(blk.gp1[g], w, slope=self.slope, residual=prev, out=dst)
+                        prev = dst
+            self._join(main)
             # weight / bias gradients: once per run, when the gp1 / gp2 of all its blocks are final
             if k in pl.XA:
                 n3 = 9 * 64 * 64
