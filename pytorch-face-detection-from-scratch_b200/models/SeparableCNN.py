@@ -189,8 +189,23 @@ class SeparablePlanarEngine:
             raise RuntimeError("the fd_b200 backbone runs on CUDA only (no CPU fallback): call model.cuda()")
         if dev != self.device:
             self.device = dev
+            self.sides = [torch.cuda.Stream(device=dev) for _ in range(self.G - 1)]
             self.plans.clear()
         self.params = params
+
+    # the per-plane chains of a block are independent: plane g > 0 runs on a side stream (parallel graph branches)
+    def _fork(self):
+        main = torch.cuda.current_stream()
+        for s_ in self.sides:
+            s_.wait_stream(main)
+        return main
+
+    def _join(self, main):
+        for s_ in self.sides:
+            main.wait_stream(s_)
+
+    def _on(self, main, g):
+        return torch.cuda.stream(main if g == 0 else self.sides[g - 1])
 
     def plan(self, B):
         if B not in self.plans:
@@ -243,21 +258,26 @@ class SeparablePlanarEngine:
             ops.stem_fwd(x, w1[g * 64:(g + 1) * 64], b1[g * 64:(g + 1) * 64], pl["act0"][g], self.stem_s, self.stem_pad)
         cur = pl["act0"]
         for k, b in enumerate(pl["blocks"]):
+            main = self._fork()
             for g in range(G):
-                raw = self._pw_chain(cur, 2 * k, g, None, b["T"][g], b["T2"][g])
-                ops.act_mask(raw, self.slope, None, None, None, b["t1"][g])
+                with self._on(main, g):
+                    raw = self._pw_chain(cur, 2 * k, g, None, b["T"][g], b["T2"][g])
+                    ops.act_mask(raw, self.slope, None, None, None, b["t1"][g])
+                    ops.dwconv3x3_lrelu(b["t1"][g], self.w_dw[k, g], self.slope, b["t2"][g])
+            self._join(main)
+            main = self._fork()
             for g in range(G):
-                ops.dwconv3x3_lrelu(b["t1"][g], self.w_dw[k, g], self.slope, b["t2"][g])
-            for g in range(G):
-                # pw2 + skip: the block input is the first addend of the chain; the last call writes the sum
-                prev = cur[g]
-                for h in range(G):
-                    dst = b["s"][g] if h == G - 1 else (b["T"][g] if (h % 2 == 0) else b["T2"][g])
-                    ops.conv3x3(b["t2"][h], self.w_pk[self._sub(2 * k + 1, g, h)], slope=self.slope, lrelu=False,
-                                residual=prev, out=dst, flags=ops.CONV_1X1)
-                    prev = dst
-                if self.pools[k]:
-                    ops.maxpool2x2_fwd(b["s"][g], b["out"][g])
+                with self._on(main, g):
+                    # pw2 + skip: the block input is the first addend of the chain; the last call writes the sum
+                    prev = cur[g]
+                    for h in range(G):
+                        dst = b["s"][g] if h == G - 1 else (b["T"][g] if (h % 2 == 0) else b["T2"][g])
+                        ops.conv3x3(b["t2"][h], self.w_pk[self._sub(2 * k + 1, g, h)], slope=self.slope, lrelu=False,
+                                    residual=prev, out=dst, flags=ops.CONV_1X1)
+                        prev = dst
+                    if self.pools[k]:
+                        ops.maxpool2x2_fwd(b["s"][g], b["out"][g])
+            self._join(main)
             cur = b["out"]
         wo = P["out.weight"].detach().float()
         logits = None
