@@ -1,15 +1,17 @@
 """CPU oracle for the convolutional backbone -- TEST INFRASTRUCTURE ONLY.
 
-A torch-fp32 *functional* restatement of the reference's PoolResnet / Resnet
-forward pass and of the training-step definition (forward, sum of per-image
-``yolo_loss``, backward).  Floating-point kernels keep a torch fp32 reference;
+A torch-fp32 *functional* restatement of the reference's PoolResnet / Resnet /
+SeparableCNN forward passes, of the training-step definition (forward, sum of
+per-image ``yolo_loss``, backward) and of the optimizer update (``adam_update``).  Floating-point kernels keep a torch fp32 reference;
 this is it.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 CPU-baseline legs may import this module.
 
 Parity status: PINNED against the real reference modules run in the build
 container (``tests/golden/make_golden.py`` -> ``tests/golden/backbone_*.npz``,
 checked by ``tests/test_oracle_golden.py``): logits identical (max-abs-diff 0.0,
-same ATen kernels), loss and gradients identical.
+same ATen kernels), loss and gradients identical; likewise Resnet
+(``make_golden_extra.py``), SeparableCNN (``make_golden_sep.py``) and the
+128-channel PoolResnet / SeparableCNN (``make_golden_wide.py``).
 
 Reference citations are ``file:line`` under ``/root/reference``.
 """
