@@ -316,6 +316,48 @@ FD_API int fd_ssd_loss(const float* conf, const float* loc, const float* labels,
                 int neg_pos_ratio, float* row_sums, int32_t* num_pos, uint8_t* mask, float* dconf, float* dloc,
                 void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * MobilenetV3 backbone, inference (models/MobilenetV3Backbone.py:33-60; the timm tf_mobilenetv3_small_100 graph as
+ * stored in the official TorchScript archive).  BatchNorm (eval, eps 1e-3) is folded into the preceding convolution by
+ * the caller: every entry point takes a per-output-channel `scale` at pack time and a fused bias.  Activations are
+ * NHWC bf16 with the network's own channel counts (multiples of 8, not padded).  act: 0 none, 1 ReLU, 2 Hardswish.
+ *
+ * fd_pw_conv: 1x1 convolution as a tcgen05 GEMM over pixels (conv_pw / conv_pwl / ConvBnAct / SE-free 1x1 layers):
+ *   out[m, n] = act(sum_k x[m, k] * w[n, k] + bias[n]) (+ residual[m, n]);  x [M, K], out / residual [M, N] bf16.
+ *   w_packed: fd_pw_packed_elems(N, K) bf16 written by fd_pw_pack from w [N][K] fp32 (* scale[n], nullable);
+ *   bias_padded: fd_pw_padded_n(N) fp32 (entries >= N zero). */
+FD_API long fd_pw_packed_elems(int N, int K);
+FD_API int fd_pw_padded_n(int N);
+FD_API int fd_pw_pack(const float* w, const float* scale, int N, int K, fd_bf16* out, void* stream);
+FD_API int fd_pw_conv(const fd_bf16* x, const fd_bf16* w_packed, const float* bias_padded, long M, int K, int N, int act,
+               const fd_bf16* residual, fd_bf16* out, void* stream);
+/* Conv2dSame 3x3 stride 2, 3 -> 16, + bias + Hardswish (feature_extractor.0-2 of the archive).  x: fp32 (or uint8 with
+ * the /255 of MobilenetV3Backbone.py:52 fused) NCHW [B,3,H,W]; w [16][3][3][3] fp32 (BatchNorm folded); out NHWC bf16
+ * [B,Ho,Wo,16].  pad_t / pad_l: the TF "SAME" leading padding (0 for even sizes). */
+FD_API int fd_mbv3_stem(const void* x, int x_is_u8, const float* w, const float* bias, int B, int H, int W, int pad_t, int pad_l,
+                 int Ho, int Wo, fd_bf16* out, void* stream);
+/* Depthwise KxK (K = 3 | 5) stride 1 | 2 convolution + bias + act.  w_packed [K*K][C] fp32 from fd_dw_pack (w [C][1][K][K]
+ * * scale[c]).  se_sum (nullable): fp32 [B,C], += the channel sums of the bf16 output (SqueezeExcite's mean). */
+FD_API int fd_dw_pack(const float* w, const float* scale, int C, int K, float* out, void* stream);
+FD_API int fd_dwconv(const fd_bf16* x, const float* w_packed, const float* bias, int B, int H, int W, int C, int K, int stride,
+              int pad_t, int pad_l, int Ho, int Wo, int act, fd_bf16* out, float* se_sum, void* stream);
+/* SqueezeExcite gate (efficientnet_blocks.py SqueezeExcite): gate[n,c] = hardsigmoid(W2 relu(W1 mean + b1) + b2) with
+ * mean = se_sum / HW.  w1 [R][C], w2 [C][R] fp32.  se_sum is zeroed after it has been read. */
+FD_API int fd_se_gate(float* se_sum, int B, int HW, const float* w1, const float* b1, const float* w2, const float* b2, int C,
+               int R, float* gate, void* stream);
+/* x[n,p,c] *= gate[n,c] in place. */
+FD_API int fd_scale_channels(fd_bf16* x, const float* gate, int B, int HW, int C, void* stream);
+/* 3x3 pad-1 convolution C -> 5 + bias + sigmoid (MobilenetV3Backbone.py:40-46,57-58).  y [B,5,H,W] fp32. */
+FD_API int fd_head3x3_fwd(const fd_bf16* x, const float* w, const float* bias, int B, int H, int W, int C, float* y, void* stream);
+
+/* transforms.Resize of the `predict == 1` branch (models/PoolResnet.py:94-95, models/BaseModel.py:64): bilinear,
+ * align_corners = False, no antialias.  x, out: `planes` images of h x w / H x W, uint8 (rounded half to even) or fp32. */
+FD_API int fd_resize_bilinear(const void* x, int is_u8, long planes, int h, int w, int H, int W, void* out, void* stream);
+/* scatter != 0: dst[idx[i]] = src[i];  else dst[i] = src[idx[i]]   (i < n).  Parameters of models narrower than the
+ * 64-channel kernel planes are scattered into zero-padded planes and their gradients gathered back. */
+FD_API int fd_index_copy_f32(float* dst, const float* src, const int32_t* idx, long n, int scatter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

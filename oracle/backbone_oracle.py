@@ -66,17 +66,36 @@ def poolresnet_forward(x: torch.Tensor, p: Params, num_of_patches: int, num_bloc
     return torch.sigmoid(y)
 
 
-def resnet_forward(x: torch.Tensor, p: Params, num_of_patches: int, num_blocks: int = 10) -> torch.Tensor:
-    """models/Resnet.py:89-99 (eval): 3x3 s2 p1 stem, blocks pool while H > S (Resnet.py:38),
-    3x3 p1 head + sigmoid."""
+def resnet_forward(x: torch.Tensor, p: Params, num_of_patches: int, num_blocks: int = 10,
+                   drop_scales: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
+    """models/Resnet.py:89-99: 3x3 s2 p1 stem, blocks pool while H > S (Resnet.py:38), Dropout2d(0.5) (:95),
+    3x3 p1 head + sigmoid.  ``drop_scales`` as in ``poolresnet_forward`` (None = eval mode)."""
     y = F.conv2d(x, p["conv1.weight"], p["conv1.bias"], stride=2, padding=1)
     for b in range(num_blocks):
         pre = f"residual_blocks.{b}."
+        ds = None if drop_scales is None else drop_scales[b]
         y = residual_block(y, p[pre + "conv1.weight"], p[pre + "conv1.bias"],
                            p[pre + "conv2.weight"], p[pre + "conv2.bias"],
-                           pool=y.shape[2] > num_of_patches)
+                           pool=y.shape[2] > num_of_patches, drop_scale=ds)
+    if drop_scales is not None and drop_scales[num_blocks] is not None:
+        y = y * drop_scales[num_blocks]
     y = F.conv2d(y, p["out.weight"], p["out.bias"], padding=1)
     return torch.sigmoid(y)
+
+
+def resize_bilinear(x: torch.Tensor, size) -> torch.Tensor:
+    """``transforms.Resize(size)`` of models/PoolResnet.py:91,95 / models/BaseModel.py:64 under the reference's pinned
+    torchvision 0.11.2 (and inside the official TorchScript archives, whose antialias branch is dead): bilinear,
+    align_corners=False, no antialias; uint8 goes through float32, ``round`` and back (functional_tensor.py resize ->
+    _cast_squeeze_in / _cast_squeeze_out)."""
+    squeeze = x.dim() == 3
+    xb = x.unsqueeze(0) if squeeze else x
+    if tuple(xb.shape[-2:]) == tuple(size):
+        return x
+    y = F.interpolate(xb.float(), size=tuple(size), mode="bilinear", align_corners=False)
+    if x.dtype == torch.uint8:
+        y = torch.round(y).to(torch.uint8)
+    return y[0] if squeeze else y
 
 
 def yolo_loss_torch(pred_fm: torch.Tensor, gt_fm: torch.Tensor) -> torch.Tensor:
@@ -145,3 +164,87 @@ def separable_forward(x: torch.Tensor, p: Params, num_blocks: int = 10, block_pa
                             p[pre + "pointwise_conv2.weight"], pool=y.shape[2] > block_patches)
     y = F.conv2d(y, p["out.weight"], p["out.bias"])
     return torch.sigmoid(y)
+
+
+# ------------------------------------------------------------------------------------------------ MobilenetV3 backbone
+# timm 0.5.4 `tf_mobilenetv3_small_100` minus its last five children (models/MobilenetV3Backbone.py:33-39) + the
+# Conv2d(576 -> 5, 3x3, pad 1) head + sigmoid (:40-46,57-58).  timm is not installed; the graph below restates the
+# code stored in the official TorchScript archive (saved_models/official/MobilenetV3Backbone/medium_model_15x15_480.pth:
+# code/__torch__/timm/models/efficientnet_blocks.py, .../layers/conv2d_same.py, .../layers/padding.py).
+# (kind, kernel, stride, expanded channels, out channels, activation, SE reduced channels or 0)
+MBV3_STAGES = (
+    (("ds", 3, 2, 16, 16, "relu", 8),),
+    (("ir", 3, 2, 72, 24, "relu", 0), ("ir", 3, 1, 88, 24, "relu", 0)),
+    (("ir", 5, 2, 96, 40, "hswish", 24), ("ir", 5, 1, 240, 40, "hswish", 64), ("ir", 5, 1, 240, 40, "hswish", 64)),
+    (("ir", 5, 1, 120, 48, "hswish", 32), ("ir", 5, 1, 144, 48, "hswish", 40)),
+    (("ir", 5, 2, 288, 96, "hswish", 72), ("ir", 5, 1, 576, 96, "hswish", 144), ("ir", 5, 1, 576, 96, "hswish", 144)),
+    (("cba", 1, 1, 576, 576, "hswish", 0),),
+)
+MBV3_BN_EPS = 1e-3
+
+
+def _same_pad(size: int, k: int, s: int):
+    """timm layers/padding.py get_same_padding + pad_same: TF 'SAME' -- total = max((ceil(i/s)-1)*s + k - i, 0), the
+    extra pixel goes to the bottom / right."""
+    total = max((-(-size // s) - 1) * s + k - size, 0)
+    return total // 2, total - total // 2
+
+
+def _conv_same(x, w, stride, groups=1):
+    """Conv2dSame.forward (stride-2 layers of the tf_ variant); stride-1 layers are plain Conv2d(padding=k//2)."""
+    k = w.shape[-1]
+    if stride == 1:
+        return F.conv2d(x, w, None, 1, k // 2, 1, groups)
+    pt, pb = _same_pad(x.shape[-2], k, stride)
+    pl, pr = _same_pad(x.shape[-1], k, stride)
+    return F.conv2d(F.pad(x, [pl, pr, pt, pb]), w, None, stride, 0, 1, groups)
+
+
+def _bn(x, p: Params, pre: str):
+    return F.batch_norm(x, p[pre + "running_mean"], p[pre + "running_var"], p[pre + "weight"], p[pre + "bias"],
+                        False, 0.0, MBV3_BN_EPS)
+
+
+def _act(x, name):
+    return F.relu(x) if name == "relu" else F.hardswish(x) if name == "hswish" else x
+
+
+def _se(x, p: Params, pre: str):
+    """efficientnet_blocks.py SqueezeExcite: mean over (H, W) -> conv_reduce -> ReLU -> conv_expand -> Hardsigmoid gate."""
+    s = x.mean((2, 3), keepdim=True)
+    s = F.relu(F.conv2d(s, p[pre + "conv_reduce.weight"], p[pre + "conv_reduce.bias"]))
+    s = F.conv2d(s, p[pre + "conv_expand.weight"], p[pre + "conv_expand.bias"])
+    return x * F.hardsigmoid(s)
+
+
+def mobilenetv3_features(x: torch.Tensor, p: Params) -> torch.Tensor:
+    """feature_extractor of models/MobilenetV3Backbone.py:33-39 in eval mode -> [B,576,H/32,W/32]."""
+    fe = "feature_extractor."
+    y = _act(_bn(_conv_same(x, p[fe + "0.weight"], 2), p, fe + "1."), "hswish")
+    for si, stage in enumerate(MBV3_STAGES):
+        for bi, (kind, k, s, cexp, cout, act, se) in enumerate(stage):
+            pre = f"{fe}3.{si}.{bi}."
+            inp = y
+            if kind == "cba":
+                y = _act(_bn(F.conv2d(y, p[pre + "conv.weight"]), p, pre + "bn1."), act)
+                continue
+            if kind == "ds":        # DepthwiseSeparableConv: dw -> bn -> act -> se -> pw -> bn (no act), skip if same shape
+                y = _act(_bn(_conv_same(y, p[pre + "conv_dw.weight"], s, groups=y.shape[1]), p, pre + "bn1."), act)
+                if se:
+                    y = _se(y, p, pre + "se.")
+                y = _bn(F.conv2d(y, p[pre + "conv_pw.weight"]), p, pre + "bn2.")
+            else:                   # InvertedResidual: pw -> bn -> act -> dw -> bn -> act -> se -> pwl -> bn, skip
+                y = _act(_bn(F.conv2d(y, p[pre + "conv_pw.weight"]), p, pre + "bn1."), act)
+                y = _act(_bn(_conv_same(y, p[pre + "conv_dw.weight"], s, groups=y.shape[1]), p, pre + "bn2."), act)
+                if se:
+                    y = _se(y, p, pre + "se.")
+                y = _bn(F.conv2d(y, p[pre + "conv_pwl.weight"]), p, pre + "bn3.")
+            if s == 1 and inp.shape[1] == y.shape[1]:
+                y = y + inp
+    return y
+
+
+def mobilenetv3_forward(x: torch.Tensor, p: Params) -> torch.Tensor:
+    """models/MobilenetV3Backbone.py:50-60 with predict == 0, eval mode: features -> 3x3 pad-1 head -> sigmoid."""
+    y = mobilenetv3_features(x, p)
+    return torch.sigmoid(F.conv2d(y, p["out.weight"], p["out.bias"], padding=1))

@@ -51,7 +51,8 @@ __device__ __forceinline__ float4 ld_peer_written(const float4* p) {
   return v;
 }
 
-__device__ __forceinline__ void cta_barrier_across_ranks(const Peers& pp, int phase, int rank, int world, unsigned epoch) {
+__device__ __forceinline__ void cta_barrier_across_ranks(const Peers& pp, int phase, int rank, int world, unsigned epoch,
+                                                         unsigned* s_bad) {
   // The CTA's peer stores happen-before the bar.sync; the flag store below is a system-scope RELEASE by a thread that
   // passed that barrier, and release is cumulative -- the same publish pattern as NCCL's (barrier, then ONE thread
   // fences and posts), without a system fence in every thread.
@@ -66,6 +67,7 @@ __device__ __forceinline__ void cta_barrier_across_ranks(const Peers& pp, int ph
     while (static_cast<int>(ld_acquire_sys(mine) - epoch) < 0) {
       if (clock64() - t_start > kSpinLimitClk) {        // a peer never arrived (died / not launched): do not hang the GPU
         reinterpret_cast<unsigned*>(pp.win[rank])[kErrWord] = 1u + peer;
+        *s_bad = 1u + peer;          // this call's sums are invalid: phase 3 poisons the gradient instead of copying them
         break;
       }
     }
@@ -77,12 +79,15 @@ __global__ void __launch_bounds__(kCommThreads)
 allreduce_sum_kernel(Peers pp, float* __restrict__ data, long n4, long chunk4, int rank, int world) {
   pdl_trigger();
   pdl_wait();                        // the local gradient is complete
-  __shared__ unsigned s_epoch;
+  __shared__ unsigned s_epoch, s_bad;
   unsigned char* my = pp.win[rank];
   if (threadIdx.x == 0) {
     unsigned* ctr = reinterpret_cast<unsigned*>(my) + 2 * kCommBlocks * kMaxPeers + blockIdx.x;
     s_epoch = *ctr + 1;
     *ctr = s_epoch;
+    // sticky: once an exchange of this window failed, the ranks' epochs may be out of step -- every later call is
+    // poisoned too until the host notices (fd_comm_status) and rebuilds the windows
+    s_bad = *reinterpret_cast<volatile unsigned*>(reinterpret_cast<unsigned*>(my) + kErrWord);
   }
   __syncthreads();
   const unsigned epoch = s_epoch;
@@ -97,7 +102,7 @@ allreduce_sum_kernel(Peers pp, float* __restrict__ data, long n4, long chunk4, i
     float4* dst = reinterpret_cast<float4*>(pp.win[p] + kFlagBytes) + rank * chunk4;
     for (long j = t0; j < len; j += stride) dst[j] = data4[lo + j];
   }
-  cta_barrier_across_ranks(pp, 0, rank, world, epoch);
+  cta_barrier_across_ranks(pp, 0, rank, world, epoch, &s_bad);
 
   // phase 2: reduce my slice in rank order, push the sum into every peer's result window
   {
@@ -115,13 +120,18 @@ allreduce_sum_kernel(Peers pp, float* __restrict__ data, long n4, long chunk4, i
       }
     }
   }
-  cta_barrier_across_ranks(pp, 1, rank, world, epoch);
+  cta_barrier_across_ranks(pp, 1, rank, world, epoch, &s_bad);
 
-  // phase 3: result window -> local gradient buffer
+  // phase 3: result window -> local gradient buffer.  After a barrier time-out the sums are garbage: the gradient is
+  // POISONED with NaN instead, so that the optimizer step / the loss surface the failure in the same step (a silent
+  // update with un-reduced gradients would let the replicas drift apart); the host reads the cause via fd_comm_status.
   const float4* res = reinterpret_cast<const float4*>(my + kFlagBytes) + world * chunk4;
+  const bool bad = s_bad != 0u;
+  const float qnan = __int_as_float(0x7fc00000);
   for (int q = 0; q < world; ++q) {
     const long lo = q * chunk4, len = min(chunk4, n4 - lo);
-    for (long j = t0; j < len; j += stride) data4[lo + j] = ld_peer_written(res + lo + j);
+    for (long j = t0; j < len; j += stride)
+      data4[lo + j] = bad ? make_float4(qnan, qnan, qnan, qnan) : ld_peer_written(res + lo + j);
   }
 }
 

@@ -51,11 +51,15 @@ class ReduceBoundingBoxes(nn.Module):
         return tuple(boxes[i, :n[i]].clone() for i in range(len(n)))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        boxes, counts = self.batch_forward(x.unsqueeze(0))
+        """Host tensors (the reference decodes CPU ground-truth maps in its dataset and in ``draw_bbx``) are copied to
+        the current CUDA device, decoded by the same kernel, and the rows copied back -- there is no CPU arithmetic."""
+        on_host = not x.is_cuda
+        boxes, counts = self.batch_forward((x.cuda() if on_host else x).unsqueeze(0))
         k = int(counts.item())
         if k == 0:
             return torch.empty(0).reshape(0, 5)      # reference returns a CPU tensor here (utils.py:170)
-        return boxes[0, :k].clone()
+        out = boxes[0, :k].clone()
+        return out.cpu() if on_host else out
 
 
 class ReduceSSDBoundingBoxes(nn.Module):
@@ -87,11 +91,13 @@ class ReduceSSDBoundingBoxes(nn.Module):
         return boxes, counts
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        boxes, counts = self.batch_forward(x.unsqueeze(0))
+        on_host = not x.is_cuda                      # see ReduceBoundingBoxes.forward
+        boxes, counts = self.batch_forward((x.cuda() if on_host else x).unsqueeze(0))
         k = int(counts.item())
         if k == 0:
             return torch.empty(0).reshape(0, 5)      # utils.py:92
-        return boxes[0, :k].clone()
+        out = boxes[0, :k].clone()
+        return out.cpu() if on_host else out
 
 
 def convert_bbx_to_xyxy(bbx):

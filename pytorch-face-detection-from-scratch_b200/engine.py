@@ -114,6 +114,7 @@ class _Plan:
             self.g_stem = bf(eng.H0, eng.W0)
             self.loss = torch.empty((B,), dtype=F32, device=device)
             self.dy = torch.empty_like(self.y)
+        self.generation = 0    # bumped by every forward that overwrites this plan (stale-backward detection)
         self.drop = None       # [num_blocks+1, B, F] fp32 Dropout2d multipliers (train mode only)
         self.x = None          # input of the last forward (needed by the stem wgrad)
 
@@ -126,6 +127,7 @@ class BackboneEngine:
             raise NotImplementedError("the tcgen05 3x3 kernels are instantiated for 64 channels "
                                       "(the reference's 'medium' checkpoints); got filters=%d" % filters)
         self.F, self.in_ch, self.in_h, self.in_w = filters, in_ch, in_h, in_w
+        self.F_logical = filters
         self.num_blocks, self.slope = num_blocks, slope
         self.stem_k, self.stem_s, self.stem_pad = stem_k, stem_s, stem_pad
         self.head_k, self.head_pad = head_k, head_pad
@@ -246,6 +248,7 @@ class BackboneEngine:
         sigmoid head [B,5,So,So] fp32.  ``dropout`` draws Dropout2d masks (train mode of the reference)."""
         B = x.shape[0]
         pl = self.plan(B, train)
+        pl.generation += 1
         if repack or self.weights_dirty:
             self.pack_weights()
         if dropout:
@@ -393,14 +396,28 @@ class BackboneEngine:
         gradient of their SUM (models/ModelMeta.py:173-176,215: the reference sums, it does not average).
         ``allreduce``: callable on the flat gradient buffer (parallel.PeerAllReduce or parallel.allreduce_grads);
         ``optimizer``: optim.FlatAdam (models/ModelMeta.py:104-112)."""
+        with torch.cuda.device(x.device):
+            return self._train_step(x, gt, dropout, allreduce, optimizer)
+
+    def _train_step(self, x, gt, dropout, allreduce, optimizer) -> _Plan:
         pl = self.forward(x, train=True, dropout=dropout)
+        if tuple(gt.shape) != tuple(pl.y.shape) or gt.device != pl.y.device:
+            raise ValueError(f"target map {tuple(gt.shape)} on {gt.device} does not match the head "
+                             f"{tuple(pl.y.shape)} on {pl.y.device}")
         ops.yolo_loss(pl.y, gt, pl.loss, None, pl.dy)
         self.run_backward(pl, pl.dy)
         if allreduce is not None:
-            allreduce(self.gflat)
+            allreduce(self.opt_grads())
         if optimizer is not None:
             optimizer.step()
         return pl
+
+    # flat buffers the optimizer and the data-parallel all-reduce work on (PaddedBackboneEngine: the un-padded ones)
+    def opt_params(self) -> torch.Tensor:
+        return self.pflat
+
+    def opt_grads(self) -> torch.Tensor:
+        return self.gflat
 
     # ------------------------------------------------------------------ CUDA graph of the train step
     def capture_train_step(self, x_static: torch.Tensor, gt_static: torch.Tensor, dropout: bool = True,
@@ -423,3 +440,104 @@ class BackboneEngine:
         with torch.cuda.graph(graph):
             pl = self.train_step(x_static, gt_static, dropout, allreduce, optimizer)
         return graph, pl, launch_count() - n0
+
+
+class PaddedBackboneEngine(BackboneEngine):
+    """Backbones NARROWER than the 64-channel kernel planes (the reference's "small" checkpoint is filters = 32,
+    saved_models/official/PoolResnet/small_model_10x10_480.pth) on the 64-channel engine: every weight tensor is
+    embedded in a zero-padded 64-channel one.  Padded channels stay exactly zero through LeakyReLU / skip / pooling and
+    their weight gradients are exactly zero, so the arithmetic of the logical channels is unchanged.  The
+    ``nn.Parameter`` tensors are views of an un-padded flat buffer ``psmall`` (source of truth, optimizer / all-reduce
+    unit); one ``fd_index_copy_f32`` scatters it into the padded buffer before a forward pass and one gathers the
+    gradients back after a backward pass."""
+
+    def __init__(self, filters: int, in_ch, in_h, in_w, num_blocks, stem_k, stem_s, stem_pad, head_k, head_pad, pool_rule,
+                 **kw):
+        if not (0 < filters < 64):
+            raise NotImplementedError("PaddedBackboneEngine handles 0 < filters < 64")
+        super().__init__(64, in_ch, in_h, in_w, num_blocks, stem_k, stem_s, stem_pad, head_k, head_pad, pool_rule, **kw)
+        f = self.F_logical = filters
+        self.small_sections = [
+            ("conv1.weight", (f, in_ch, stem_k, stem_k)), ("conv1.bias", (f,)),
+            ("w3", (2 * num_blocks, f, f, 3, 3)), ("b3", (2 * num_blocks, f)),
+            ("out.weight", (5, f, head_k, head_k)), ("out.bias", (5,)),
+        ]
+        self.small_offsets, off = {}, 0
+        for name, shape in self.small_sections:
+            n = 1
+            for d in shape:
+                n *= d
+            self.small_offsets[name] = (off, n, shape)
+            off += (n + 3) // 4 * 4
+        self.n_small = off
+        self.psmall = self.gsmall = self.index = None
+
+    def _small_view(self, flat, name):
+        if name.startswith("residual_blocks."):
+            _, k, c, kind = name.split(".")
+            layer = 2 * int(k) + (0 if c == "conv1" else 1)
+            off, n, shape = self.small_offsets["w3" if kind == "weight" else "b3"]
+            return flat[off:off + n].view(shape)[layer]
+        off, n, shape = self.small_offsets[name]
+        return flat[off:off + n].view(shape)
+
+    def _ensure_device(self, device):
+        if self.device == device and self.pflat is not None and self.psmall is not None:
+            return
+        super()._ensure_device(device)
+        f = self.F_logical
+        self.psmall = torch.zeros(self.n_small, dtype=F32, device=device)
+        self.gsmall = torch.zeros(self.n_small, dtype=F32, device=device)
+        # index[i] = position of small element i in the padded flat buffer (alignment gaps map onto themselves' twin:
+        # they point at padded zeros of the same section and carry zeros)
+        big = torch.arange(self.n_flat, dtype=torch.int32, device=device)
+        idx = torch.zeros(self.n_small, dtype=torch.int32, device=device)
+        sel = {"conv1.weight": lambda v: v[:f], "conv1.bias": lambda v: v[:f], "w3": lambda v: v[:, :f, :f],
+               "b3": lambda v: v[:, :f], "out.weight": lambda v: v[:, :f], "out.bias": lambda v: v}
+        for name, _ in self.small_sections:
+            off, n, shape = self.small_offsets[name]
+            boff, bn, bshape = self.offsets[name]
+            src = sel[name](big[boff:boff + bn].view(bshape)).reshape(-1)
+            idx[off:off + n] = src
+            gap = (n + 3) // 4 * 4 - n
+            if gap:       # alignment gap of the small buffer (holds zeros): aim at the padded buffer's own gap, or at the
+                          # section's last element, which belongs to a padded (zero) channel
+                big_gap = (bn + 3) // 4 * 4 - bn
+                for j in range(gap):
+                    idx[off + n + j] = boff + bn + j if j < big_gap else boff + bn - 1
+                assert big_gap >= gap or name != "out.bias"
+        self.index = idx.contiguous()
+
+    def bind(self, params):
+        dev = params["conv1.weight"].device
+        if dev.type != "cuda":
+            raise RuntimeError("the fd_b200 backbone runs on CUDA only (no CPU fallback): call model.cuda()")
+        self._ensure_device(dev)
+        for name in self.param_names():
+            p = params[name]
+            v = self._small_view(self.psmall, name)
+            if p.data_ptr() != v.data_ptr():
+                with torch.no_grad():
+                    v.copy_(p.data.to(device=dev, dtype=F32))
+                p.data = v
+        self.weights_dirty = True
+
+    def grad_view(self, name):
+        return self._small_view(self.gsmall, name)
+
+    def opt_params(self):
+        return self.psmall
+
+    def opt_grads(self):
+        return self.gsmall
+
+    def pack_weights(self):
+        ops.index_copy(self.pflat, self.psmall, self.index, scatter=True)     # padded positions stay zero
+        super().pack_weights()
+
+    def forward(self, x, train, dropout=False, repack=True):
+        return super().forward(x, train, dropout=dropout, repack=True)
+
+    def run_backward(self, pl, dy):
+        super().run_backward(pl, dy)
+        ops.index_copy(self.gsmall, self.gflat, self.index, scatter=False)

@@ -119,6 +119,7 @@ class _PPlan:
         else:
             self.x_cache = None
         self.drop = None
+        self.generation = 0
         self.x = self.head_in = self.w_head = None
 
 
@@ -254,6 +255,7 @@ class PlanarEngine:
     def forward(self, x, train: bool, dropout: bool = False):
         B = x.shape[0]
         pl = self.plan(B, train)
+        pl.generation += 1
         G, nb, P = self.G, self.num_blocks, self.params
         self.pack_weights()
         if dropout:
@@ -379,6 +381,9 @@ class PlanarEngine:
 
     def train_step(self, x, gt, dropout: bool = True, allreduce=None, optimizer=None):
         pl = self.forward(x, train=True, dropout=dropout)
+        if tuple(gt.shape) != tuple(pl.y.shape) or gt.device != pl.y.device:
+            raise ValueError(f"target map {tuple(gt.shape)} on {gt.device} does not match the head "
+                             f"{tuple(pl.y.shape)} on {pl.y.device}")
         ops.yolo_loss(pl.y, gt, pl.loss, None, pl.dy)
         self.run_backward(pl, pl.dy)
         if allreduce is not None:

@@ -7,6 +7,8 @@ step are replaced by a per-row radix select in shared memory (``fd_ssd_loss``).
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from .. import ops
@@ -46,14 +48,21 @@ def ssd_loss(confidence, predicted_locations, labels, gt_locations, neg_pos_rati
 
 @torch.no_grad()
 def hard_negative_mining(loss, labels, neg_pos_ratio):
-    """Reference signature (losses/SSDLoss.py:27): ``loss = -log(confidence)``; returns the bool mask.  The
-    kernel ranks by confidence (ascending) which is the same order as ``-log`` descending."""
-    conf = torch.exp(-loss.detach().float()).contiguous()
-    B, P = conf.shape
+    """Reference signature (losses/SSDLoss.py:27-53): ranks the negatives by the SUPPLIED ``loss`` (descending) and
+    returns the bool mask; like the reference it also overwrites ``loss[labels > 0]`` with ``-inf`` in place (:45).
+    The kernel selects on the raw key bits in ascending order, so ``loss`` is mapped to a key that is ascending in
+    descending loss with an exact, order-preserving bit transform (no ``exp``/``log`` round trip that could merge or
+    reorder near-tied losses): flip all bits of a negative float, the sign bit of a non-negative one, then invert."""
+    lf = loss.detach().float().contiguous()
+    B, P = lf.shape
     lb = labels.detach().float().contiguous()
-    z4 = torch.zeros((B, P, 4), dtype=torch.float32, device=conf.device)
-    sums = torch.empty((B, 2), dtype=torch.float32, device=conf.device)
-    npos = torch.empty((B,), dtype=torch.int32, device=conf.device)
-    mask = torch.empty((B, P), dtype=torch.uint8, device=conf.device)
-    ops.ssd_loss(conf, z4, lb, z4, int(neg_pos_ratio), sums, npos, mask, None, None)
+    loss[labels > 0] = -math.inf                                  # SSDLoss.py:45 (in-place side effect)
+    bits = lf.view(torch.int32)
+    asc = torch.where(bits < 0, ~bits, bits ^ (-0x80000000))      # unsigned-ascending in ascending loss
+    key = (~asc).view(torch.float32)                              # unsigned-ascending in DESCENDING loss
+    z4 = torch.zeros((B, P, 4), dtype=torch.float32, device=lf.device)
+    sums = torch.empty((B, 2), dtype=torch.float32, device=lf.device)
+    npos = torch.empty((B,), dtype=torch.int32, device=lf.device)
+    mask = torch.empty((B, P), dtype=torch.uint8, device=lf.device)
+    ops.ssd_loss(key, z4, lb, z4, int(neg_pos_ratio), sums, npos, mask, None, None)
     return mask.bool()

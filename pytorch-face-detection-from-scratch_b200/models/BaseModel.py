@@ -5,7 +5,28 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .. import ops
 from ..datasets.utils import ReduceBoundingBoxes
+
+
+def resize_to(x: torch.Tensor, size) -> torch.Tensor:
+    """``transforms.Resize(size)(x)`` of models/BaseModel.py:64 / PoolResnet.py:94 as one CUDA kernel (``fd_resize_bilinear``):
+    bilinear, align_corners=False, no antialias (the pinned torchvision 0.11.2 semantics, which are also what the
+    official TorchScript archives execute); uint8 in -> uint8 out (round half to even), float in -> float32 out.
+    ``x``: ``[3,h,w]`` or ``[B,3,h,w]``.  Same size -> returned unchanged, like the reference's no-op resize."""
+    size = tuple(int(s) for s in size)
+    if tuple(x.shape[-2:]) == size:
+        return x
+    if not x.is_cuda:
+        raise RuntimeError("fd_b200 resize runs on CUDA tensors only (no CPU fallback)")
+    squeeze = x.dim() == 3
+    xb = x.unsqueeze(0) if squeeze else x
+    if xb.dtype != torch.uint8:
+        xb = xb.float()
+    xb = xb.contiguous()
+    out = torch.empty((xb.shape[0], xb.shape[1], size[0], size[1]), dtype=xb.dtype, device=xb.device)
+    ops.resize_bilinear(xb, out)
+    return out[0] if squeeze else out
 
 
 class BaseModel(nn.Module):
@@ -48,11 +69,14 @@ class BaseModel(nn.Module):
         return self.reduce_bounding_boxes(x)
 
     def _resize(self, x):
-        size = tuple(self.input_shape[1:])
-        if tuple(x.shape[-2:]) == size:
-            return x
-        from torchvision.transforms import transforms
-        return transforms.Resize(size=size)(x)
+        return resize_to(x, tuple(self.input_shape[1:]))
+
+    def _to_model_device(self, x):
+        """Host images are copied to the parameters' device (plumbing; the arithmetic has no CPU path)."""
+        p = next(self.parameters(), None)
+        if p is not None and p.is_cuda and not x.is_cuda:
+            return x.to(p.device, non_blocking=True)
+        return x
 
     @torch.no_grad()
     def predict(self, x, probability_threshold=0.5, iou_threshold=0.5):
@@ -63,7 +87,7 @@ class BaseModel(nn.Module):
             input_shape=self.input_shape,
             num_of_patches=self.num_of_patches,
         )
-        x = self._resize(x)
+        x = self._resize(self._to_model_device(x))
         x = x / 255.0
         image = x
         if len(x.shape) == 3:

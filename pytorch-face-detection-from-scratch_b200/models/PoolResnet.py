@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ..engine import BackboneEngine
+from ..engine import BackboneEngine, PaddedBackboneEngine
 from ..engine_planar import PlanarEngine
 from .BaseModel import BaseModel
 
@@ -39,15 +39,58 @@ class _BackboneFn(torch.autograd.Function):
     def forward(ctx, model, x, *params):
         eng = model.engine
         pl = eng.forward(x, train=True, dropout=model.training)
-        ctx.eng, ctx.pl = eng, pl
+        ctx.eng, ctx.pl, ctx.generation = eng, pl, pl.generation
         return pl.y.clone()
 
     @staticmethod
     def backward(ctx, dy):
         eng, pl = ctx.eng, ctx.pl
+        if pl.generation != ctx.generation:
+            # the saved activations / masks live in the engine's per-batch-size plan, not in the autograd graph
+            raise RuntimeError(
+                "fd_b200 backbone: backward() after ANOTHER forward of the same batch size overwrote the saved "
+                "activations (gradient accumulation over micro-batches / SAM closures: call backward() before the "
+                "next forward, or run the intermediate forward under torch.no_grad())")
         eng.run_backward(pl, dy.contiguous().float())
         grads = [eng.grad_view(n).clone() for n in eng.param_names()]
         return (None, None, *grads)
+
+
+class GraphedTrainStep:
+    """See ``GridBackbone.graphed_train_step``."""
+
+    def __init__(self, model, B, image_dtype, optimizer, allreduce, n_buffers):
+        eng = model.engine
+        dev = next(model.parameters()).device
+        C, H, W = model.input_shape
+        if optimizer is not None and not getattr(optimizer, "capturable", False):
+            raise ValueError("an optimizer inside a CUDA graph must keep its step count on the device: "
+                             "use model.flat_optimizer(capturable=True)")
+        with torch.cuda.device(dev):
+            self.x = [torch.zeros((B, C, H, W), dtype=image_dtype, device=dev) for _ in range(n_buffers)]
+            self.gt = [torch.zeros((B, 5, eng.So_h, eng.So_w), dtype=torch.float32, device=dev) for _ in range(n_buffers)]
+            if optimizer is not None:
+                optimizer._ensure_state()
+            dropout = model.training
+            # warm-up (plan allocation, tensor-map encoding) WITHOUT the optimizer / exchange: the weights are untouched
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                eng.train_step(self.x[0], self.gt[0], dropout=dropout)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            self.graphs, self.plan = [], None
+            for i in range(n_buffers):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.plan = eng.train_step(self.x[i], self.gt[i], dropout=dropout, allreduce=allreduce,
+                                               optimizer=optimizer)
+                self.graphs.append(g)
+
+    def replay(self, i: int = 0) -> torch.Tensor:
+        self.graphs[i].replay()
+        return self.plan.loss
 
 
 class GridBackbone(BaseModel):
@@ -63,13 +106,14 @@ class GridBackbone(BaseModel):
         self.out = nn.Conv2d(filters, 5, stride=(1, 1), kernel_size=(head_k, head_k), padding=head_pad)
         self.sigmoid = nn.Sigmoid()
         # 64 channels: the fused tensor-core engine; 128, 192, ...: the same kernels on 64-channel planes (engine_planar)
-        Engine = BackboneEngine if filters == 64 else PlanarEngine
+        # fewer than 64 (the 'small' checkpoint is 32): the 64-channel engine on zero-padded weights
+        Engine = BackboneEngine if filters == 64 else PaddedBackboneEngine if filters < 64 else PlanarEngine
         self.engine = Engine(filters, input_shape[0], input_shape[1], input_shape[2], num_of_residual_blocks,
                              stem_k, stem_s, stem_pad, head_k, head_pad, pool_rule)
 
     def _prep_input(self, x: torch.Tensor, predict: bool) -> torch.Tensor:
         if predict:
-            x = self._resize(x)                       # PoolResnet.py:94-95
+            x = self._resize(self._to_model_device(x))   # PoolResnet.py:94-95
             if x.dtype != torch.uint8:
                 x = x / 255.0
             if len(x.shape) == 3:
@@ -108,10 +152,25 @@ class GridBackbone(BaseModel):
             p.grad = self.engine.grad_view(n)
         return pl.loss.sum()
 
+    def graphed_train_step(self, batch_size: int, image_dtype=torch.float32, optimizer=None, allreduce=None,
+                           n_buffers: int = 2):
+        """The train step (forward + summed YoloLoss + backward [+ all-reduce] [+ Adam]) captured ONCE per static input
+        buffer into a CUDA graph: ``step.x[i]`` / ``step.gt[i]`` are device buffers the caller fills (e.g. with
+        ``copy_(pinned_host_batch, non_blocking=True)`` on a copy stream), ``step.replay(i)`` launches the whole step
+        as one graph and returns the per-image losses ``[B]`` (device tensor, valid until the next replay).  With
+        ``n_buffers = 2`` the copy of batch k+1 overlaps the compute of batch k.  ``optimizer`` must be
+        ``flat_optimizer(capturable=True)``; gradients land in ``p.grad`` (views of the flat gradient buffer)."""
+        params = dict(self.named_parameters())
+        self.engine.bind(params)
+        step = GraphedTrainStep(self, batch_size, image_dtype, optimizer, allreduce, n_buffers)
+        for n, p in params.items():
+            p.grad = self.engine.grad_view(n)
+        return step
+
     def flat_optimizer(self, lr: float = 1e-4, capturable: bool = False):
         """One-kernel Adam over the flat parameter buffer (optim.FlatAdam); lr default = ModelMeta's (ModelMeta.py:86)."""
         from ..optim import FlatAdam
-        if not isinstance(self.engine, BackboneEngine):
+        if not isinstance(self.engine, BackboneEngine):        # PaddedBackboneEngine is a BackboneEngine
             raise NotImplementedError("flat_optimizer needs the flat parameter buffer of the 64-channel engine; use "
                                       "torch.optim.Adam(model.parameters()) (ModelMeta.configure_optimizers) for wider models")
         self.engine.bind(dict(self.named_parameters()))

@@ -60,6 +60,18 @@ SIGNATURES = {
     "fd_ssd_grid_encode": [_P, _P, _I, _P, _I, _I, _I, _P, _P],
     "fd_ssd_decode_nms": [_P, _I, _P, _I, _F, _D, _I, _I, _I, _P, _P, _P],
     "fd_ssd_loss": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "fd_pw_packed_elems": [_I, _I],
+    "fd_pw_padded_n": [_I],
+    "fd_pw_pack": [_P, _P, _I, _I, _P, _P],
+    "fd_pw_conv": [_P, _P, _P, _c.c_long, _I, _I, _I, _P, _P, _P],
+    "fd_mbv3_stem": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fd_dw_pack": [_P, _P, _I, _I, _P, _P],
+    "fd_dwconv": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "fd_se_gate": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P],
+    "fd_scale_channels": [_P, _P, _I, _I, _I, _P],
+    "fd_head3x3_fwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "fd_resize_bilinear": [_P, _I, _c.c_long, _I, _I, _I, _I, _P, _P],
+    "fd_index_copy_f32": [_P, _P, _P, _c.c_long, _I, _P],
 }
 
 
@@ -99,6 +111,7 @@ def lib():
         L.fd_launch_count.restype = _c.c_longlong
         L.fd_stem_cache_elems.restype = _c.c_long
         L.fd_comm_window_bytes.restype = _c.c_long
+        L.fd_pw_packed_elems.restype = _c.c_long
         L.fd_error_string.restype = _c.c_char_p
         _lib = L
     return _lib
@@ -124,6 +137,10 @@ def dptr(t, dtype=None):
         raise NativeError("fd_b200 kernels take contiguous tensors")
     if dtype is not None and t.dtype != dtype:
         raise NativeError(f"expected dtype {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's stream: a tensor of another device would fault asynchronously
+        raise NativeError(f"tensor lives on cuda:{t.device.index} but the current device is "
+                          f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device(tensor.device)")
     return t.data_ptr()
 
 

@@ -231,3 +231,84 @@ def ssd_loss(conf, loc, labels, gt_loc, neg_pos_ratio, row_sums, num_pos, mask=N
     check(lib().fd_ssd_loss(dptr(conf, F32), dptr(loc, F32), dptr(labels, F32), dptr(gt_loc, F32), B, P,
                             int(neg_pos_ratio), dptr(row_sums, F32), dptr(num_pos, I32), dptr(mask, U8),
                             dptr(dconf, F32), dptr(dloc, F32), cur_stream()), "fd_ssd_loss")
+
+
+# ---------------------------------------------------------------------------------------------- MobilenetV3 path
+ACT_NONE, ACT_RELU, ACT_HSWISH = 0, 1, 2
+
+
+def pw_packed_elems(N, K):
+    return int(lib().fd_pw_packed_elems(int(N), int(K)))
+
+
+def pw_padded_n(N):
+    return int(lib().fd_pw_padded_n(int(N)))
+
+
+def pw_pack(w, scale, out):
+    """w [N,K] fp32 (* scale [N], folded BatchNorm) -> packed bf16 operand tiles of fd_pw_conv."""
+    N, K = w.shape
+    check(lib().fd_pw_pack(dptr(w, F32), dptr(scale, F32), N, K, dptr(out, BF16), cur_stream()), "fd_pw_pack")
+
+
+def pw_conv(x, w_packed, bias_padded, N, act, out, residual=None):
+    """x [..., K] bf16 NHWC -> out [..., N] bf16: 1x1 convolution + bias + act (+ residual) as a tcgen05 GEMM."""
+    K = x.shape[-1]
+    M = x.numel() // K
+    assert out.numel() == M * N and (residual is None or residual.numel() == M * N)
+    check(lib().fd_pw_conv(dptr(x, BF16), dptr(w_packed, BF16), dptr(bias_padded, F32), M, K, int(N), int(act),
+                           dptr(residual, BF16), dptr(out, BF16), cur_stream()), "fd_pw_conv")
+
+
+def mbv3_stem(x, w, bias, pad_t, pad_l, out):
+    B, _, H, W = x.shape
+    _, Ho, Wo, _ = out.shape
+    is_u8 = 1 if x.dtype == U8 else 0
+    check(lib().fd_mbv3_stem(dptr(x, U8 if is_u8 else F32), is_u8, dptr(w, F32), dptr(bias, F32), B, H, W, int(pad_t),
+                             int(pad_l), Ho, Wo, dptr(out, BF16), cur_stream()), "fd_mbv3_stem")
+
+
+def dw_pack(w, scale, out):
+    C, _, K, _ = w.shape
+    check(lib().fd_dw_pack(dptr(w, F32), dptr(scale, F32), C, K, dptr(out, F32), cur_stream()), "fd_dw_pack")
+
+
+def dwconv(x, w_packed, bias, K, stride, pad_t, pad_l, act, out, se_sum=None):
+    B, H, W, C = x.shape
+    _, Ho, Wo, _ = out.shape
+    check(lib().fd_dwconv(dptr(x, BF16), dptr(w_packed, F32), dptr(bias, F32), B, H, W, C, int(K), int(stride), int(pad_t),
+                          int(pad_l), Ho, Wo, int(act), dptr(out, BF16), dptr(se_sum, F32), cur_stream()), "fd_dwconv")
+
+
+def se_gate(se_sum, HW, w1, b1, w2, b2, gate):
+    B, C = se_sum.shape
+    R = w1.shape[0]
+    check(lib().fd_se_gate(dptr(se_sum, F32), B, int(HW), dptr(w1, F32), dptr(b1, F32), dptr(w2, F32), dptr(b2, F32), C, R,
+                           dptr(gate, F32), cur_stream()), "fd_se_gate")
+
+
+def scale_channels(x, gate):
+    B, H, W, C = x.shape
+    check(lib().fd_scale_channels(dptr(x, BF16), dptr(gate, F32), B, H * W, C, cur_stream()), "fd_scale_channels")
+
+
+def head3x3_fwd(x, w, bias, y):
+    B, H, W, C = x.shape
+    check(lib().fd_head3x3_fwd(dptr(x, BF16), dptr(w, F32), dptr(bias, F32), B, H, W, C, dptr(y, F32), cur_stream()),
+          "fd_head3x3_fwd")
+
+
+def resize_bilinear(x, out):
+    """x [B,C,h,w] -> out [B,C,H,W], both uint8 or both fp32 (transforms.Resize, bilinear, no antialias)."""
+    assert x.dtype == out.dtype and x.dtype in (U8, F32)
+    B, C, h, w = x.shape
+    H, W = out.shape[-2:]
+    is_u8 = 1 if x.dtype == U8 else 0
+    check(lib().fd_resize_bilinear(dptr(x, x.dtype), is_u8, B * C, h, w, H, W, dptr(out, out.dtype), cur_stream()),
+          "fd_resize_bilinear")
+
+
+def index_copy(dst, src, idx, scatter):
+    """scatter: dst[idx[i]] = src[i]; gather: dst[i] = src[idx[i]]  (flat fp32 buffers, int32 index)."""
+    check(lib().fd_index_copy_f32(dptr(dst, F32), dptr(src, F32), dptr(idx, I32), idx.numel(), int(bool(scatter)),
+                                  cur_stream()), "fd_index_copy_f32")

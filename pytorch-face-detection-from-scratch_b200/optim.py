@@ -36,18 +36,18 @@ class FlatAdam:
 
     def _ensure_state(self):
         eng = self.engine
-        if self.m is None or self.m.device != eng.pflat.device:
-            self.m = torch.zeros_like(eng.pflat)
-            self.v = torch.zeros_like(eng.pflat)
+        if self.m is None or self.m.device != eng.opt_params().device:
+            self.m = torch.zeros_like(eng.opt_params())
+            self.v = torch.zeros_like(eng.opt_params())
             if self.capturable:
                 bits = torch.tensor([self._lr], dtype=torch.float32).view(torch.int32).item()
-                self.state = torch.tensor([self.steps, 0, bits, 0], dtype=torch.int32, device=eng.pflat.device)
+                self.state = torch.tensor([self.steps, 0, bits, 0], dtype=torch.int32, device=eng.opt_params().device)
 
     def step(self):
         eng = self.engine
         self._ensure_state()
         self.steps += 1                    # host-side mirror; under graph replay the device count is authoritative
-        ops.adam_flat(eng.pflat, eng.gflat, self.m, self.v, self._lr, self.betas[0], self.betas[1], self.eps,
+        ops.adam_flat(eng.opt_params(), eng.opt_grads(), self.m, self.v, self._lr, self.betas[0], self.betas[1], self.eps,
                       self.weight_decay, self.steps, self.state)
         eng.weights_dirty = True          # the packed bf16 weights are rebuilt by the next forward
 

@@ -67,6 +67,7 @@ class PeerAllReduce:
             return None
         from .native import lib
         L = lib()
+        torch.cuda.set_device(torch.device(device))      # fd_comm_alloc allocates on the CURRENT device
         rank, world = dist.get_rank(), dist.get_world_size()
         ok, own, handle = 1, ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
         nbytes = L.fd_comm_window_bytes(numel, world)
@@ -88,6 +89,7 @@ class PeerAllReduce:
                 windows[r] = peer.value
         else:
             ok = 0
+        torch.cuda.synchronize()
         flags = [None] * world
         dist.all_gather_object(flags, ok)                            # also the "every window is zeroed and mapped" barrier
         if not all(flags):
