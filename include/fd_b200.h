@@ -338,14 +338,16 @@ FD_API int fd_pw_conv(const fd_bf16* x, const fd_bf16* w_packed, const float* bi
 FD_API int fd_mbv3_stem(const void* x, int x_is_u8, const float* w, const float* bias, int B, int H, int W, int pad_t, int pad_l,
                  int Ho, int Wo, fd_bf16* out, void* stream);
 /* Depthwise KxK (K = 3 | 5) stride 1 | 2 convolution + bias + act.  w_packed [K*K][C] fp32 from fd_dw_pack (w [C][1][K][K]
- * * scale[c]).  se_sum (nullable): fp32 [B,C], += the channel sums of the bf16 output (SqueezeExcite's mean). */
+ * * scale[c]).  se_partial (nullable): fp32 [B][fd_dwconv_se_blocks(Ho,Wo,C)][C], receives per-thread-block channel sums
+ * of the bf16 output (SqueezeExcite's mean; plain stores in a fixed order -- inference is bit-reproducible). */
 FD_API int fd_dw_pack(const float* w, const float* scale, int C, int K, float* out, void* stream);
+FD_API int fd_dwconv_se_blocks(int Ho, int Wo, int C);
 FD_API int fd_dwconv(const fd_bf16* x, const float* w_packed, const float* bias, int B, int H, int W, int C, int K, int stride,
-              int pad_t, int pad_l, int Ho, int Wo, int act, fd_bf16* out, float* se_sum, void* stream);
+              int pad_t, int pad_l, int Ho, int Wo, int act, fd_bf16* out, float* se_partial, void* stream);
 /* SqueezeExcite gate (efficientnet_blocks.py SqueezeExcite): gate[n,c] = hardsigmoid(W2 relu(W1 mean + b1) + b2) with
- * mean = se_sum / HW.  w1 [R][C], w2 [C][R] fp32.  se_sum is zeroed after it has been read. */
-FD_API int fd_se_gate(float* se_sum, int B, int HW, const float* w1, const float* b1, const float* w2, const float* b2, int C,
-               int R, float* gate, void* stream);
+ * mean = (sum of the nblk block partials written by fd_dwconv) / HW.  w1 [R][C], w2 [C][R] fp32. */
+FD_API int fd_se_gate(const float* se_partial, int nblk, int B, int HW, const float* w1, const float* b1, const float* w2,
+               const float* b2, int C, int R, float* gate, void* stream);
 /* x[n,p,c] *= gate[n,c] in place. */
 FD_API int fd_scale_channels(fd_bf16* x, const float* gate, int B, int HW, int C, void* stream);
 /* 3x3 pad-1 convolution C -> 5 + bias + sigmoid (MobilenetV3Backbone.py:40-46,57-58).  y [B,5,H,W] fp32. */
@@ -357,6 +359,19 @@ FD_API int fd_resize_bilinear(const void* x, int is_u8, long planes, int h, int 
 /* scatter != 0: dst[idx[i]] = src[i];  else dst[i] = src[idx[i]]   (i < n).  Parameters of models narrower than the
  * 64-channel kernel planes are scattered into zero-padded planes and their gradients gathered back. */
 FD_API int fd_index_copy_f32(float* dst, const float* src, const int32_t* idx, long n, int scatter, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Prediction heads of the SSD model (models/SSD.py:174-177,238-254 + apply_priors :206-220): Linear(C -> 5) on every
+ * pixel of one scale's feature map, sigmoid on column 0, columns 1-2 times `mult` (1 / ps), columns 1-4 plus `priors`,
+ * written into rows [prior_off, prior_off + HW) of out [B,P,5] fp32.  The map is given as G 64-channel NHWC bf16 planes
+ * (HOST array of G device pointers; C <= 64 * G real channels); w [5][C], bias [5] fp32; mult [P], priors [P,4] fp32.
+ * Backward: dout [B,P,5] = gradient w.r.t. out; dx planes are overwritten, dw [5][C] and db [5] accumulated into. */
+FD_API int fd_ssd_head_fwd(const fd_bf16* const* x_planes, int G, const float* w, const float* bias, int B, int HW, int C,
+                    const float* mult, const float* priors, int prior_off, int P, float* out, void* stream);
+FD_API int fd_ssd_head_bwd(const fd_bf16* const* x_planes, fd_bf16* const* dx_planes, int G, const float* w, int B, int HW,
+                    int C, const float* mult, int prior_off, int P, const float* out, const float* dout, float* dw,
+                    float* db, void* stream);
 
 #ifdef __cplusplus
 }

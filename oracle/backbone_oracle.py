@@ -248,3 +248,89 @@ def mobilenetv3_forward(x: torch.Tensor, p: Params) -> torch.Tensor:
     """models/MobilenetV3Backbone.py:50-60 with predict == 0, eval mode: features -> 3x3 pad-1 head -> sigmoid."""
     y = mobilenetv3_features(x, p)
     return torch.sigmoid(F.conv2d(y, p["out.weight"], p["out.bias"], padding=1))
+
+
+# ------------------------------------------------------------------------------------------------ SSD model
+SSD_PATCH_SIZES = (60, 30, 15, 7)
+
+
+def ssd_block(x, p: Params, pre: str, pool: bool, drop_scale: Optional[torch.Tensor] = None):
+    """models/SSD.py:63-81 SeparableResidualBlock.forward: optional 1x1 skip conv, conv3x3 -> lrelu -> conv3x3 -> lrelu ->
+    Dropout2d (explicit [B,C,1,1] multiplier or None = eval) -> + skip -> optional MaxPool2d(2)."""
+    skip = x
+    if (pre + "pointwise_conv_skip.weight") in p:
+        skip = F.conv2d(x, p[pre + "pointwise_conv_skip.weight"], p[pre + "pointwise_conv_skip.bias"])
+    y = F.leaky_relu(F.conv2d(x, p[pre + "conv1.weight"], p[pre + "conv1.bias"], padding=1), 0.2)
+    y = F.leaky_relu(F.conv2d(y, p[pre + "conv2.weight"], p[pre + "conv2.bias"], padding=1), 0.2)
+    if drop_scale is not None:
+        y = y * drop_scale
+    y = y + skip
+    return F.max_pool2d(y, 2) if pool else y
+
+
+def ssd_priors_torch():
+    """models/SSD.py:111-116,192-204: (multiply_priors [P,1], priors [P,4])."""
+    mult = torch.unsqueeze(torch.cat([torch.tensor(1 / ps).repeat(ps * ps) for ps in SSD_PATCH_SIZES]), dim=1)
+    pri = []
+    for ps in SSD_PATCH_SIZES:
+        t = torch.zeros((4, ps, ps))
+        i, j = torch.where(t[0] >= 0)
+        t[0, i, j] = t[0, i, j] + 1 / ps * i
+        t[1, i, j] = t[1, i, j] + 1 / ps * j
+        pri.append(t.permute(1, 2, 0).reshape(ps * ps, 4))
+    return mult, torch.cat(pri, dim=0)
+
+
+def ssd_forward(x: torch.Tensor, p: Params, drop_scales: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
+    """models/SSD.py:222-255 with predict == 0 -> [B,4774,5] rows (sigmoid score, x/ps + i/ps, y/ps + j/ps, w, h).
+    ``drop_scales``: 13 Dropout2d multipliers (9 feature-extractor blocks, then the 4 continue blocks) or None."""
+    bs = x.shape[0]
+    y = F.conv2d(x, p["input_normalizer.weight"], p["input_normalizer.bias"], stride=2, padding=1)
+    k = 0
+    for b in range(9):
+        y = ssd_block(y, p, f"feature_extractor.{b}.", pool=b < 2, drop_scale=None if drop_scales is None else drop_scales[k])
+        k += 1
+    scores, bbxs = [], []
+    for i in range(4):
+        y = ssd_block(y, p, f"continue_layers.{i}.0.", pool=i != 0, drop_scale=None if drop_scales is None else drop_scales[k])
+        k += 1
+        z = F.linear(y.permute(0, 2, 3, 1).contiguous(), p[f"extracting_layers.{i}.0.weight"], p[f"extracting_layers.{i}.0.bias"])
+        z = z.reshape(bs, -1, 5)
+        scores.append(z[..., :1])
+        bbxs.append(z[..., 1:5])
+    out = torch.cat([torch.sigmoid(torch.cat(scores, dim=1)), torch.cat(bbxs, dim=1)], dim=2)
+    mult, pri = ssd_priors_torch()
+    s = torch.clone(out).float()                                        # apply_priors, SSD.py:206-220
+    s[..., 1:2] = s[..., 1:2] * mult.repeat(repeats=(bs, 1, 1))
+    s[..., 2:3] = s[..., 2:3] * mult.repeat(repeats=(bs, 1, 1))
+    s[..., 1:5] = s[..., 1:5] + pri.repeat(repeats=(bs, 1, 1))
+    return s
+
+
+def ssd_loss_torch(confidence, predicted_locations, labels, gt_locations, neg_pos_ratio):
+    """losses/SSDLoss.py:27-86 restated for autograd (hard-negative mining, clamped BCE, smooth L1, / num_pos)."""
+    import math
+    with torch.no_grad():
+        loss = -torch.log(confidence)
+        pos_mask = labels > 0
+        num_neg = pos_mask.long().sum(dim=1, keepdim=True) * neg_pos_ratio
+        loss[pos_mask] = -math.inf
+        _, indexes = loss.sort(dim=1, descending=True, stable=True)
+        _, orders = indexes.sort(dim=1)
+        mask = pos_mask | (orders < num_neg)
+    c = confidence[mask].clamp(1e-7, 1 - 1e-7)
+    t = torch.round(labels[mask])
+    cls = torch.sum(-1 * (t * torch.log(c) + (1 - t) * torch.log(1 - c)))
+    pl = predicted_locations[pos_mask, :].reshape(-1, 4)
+    gl = gt_locations[pos_mask, :].reshape(-1, 4)
+    return (F.smooth_l1_loss(pl, gl, reduction="sum") + cls) / gl.size(0)
+
+
+def ssd_train_step(x, y, p: Params, neg_pos_ratio: int = 10, drop_scales=None):
+    """models/ModelMetaSSD.py:143,175: y_hat = model(x); loss = ssd_loss(y_hat[:,:,0], y_hat[:,:,1:], y[:,:,0], y[:,:,1:], 10);
+    loss.backward().  Returns (y_hat, loss, grads)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    y_hat = ssd_forward(x, leaves, drop_scales)
+    loss = ssd_loss_torch(y_hat[:, :, 0], y_hat[:, :, 1:], y[:, :, 0], y[:, :, 1:], neg_pos_ratio)
+    loss.backward()
+    return y_hat.detach(), loss.detach(), {k: v.grad.detach() for k, v in leaves.items()}

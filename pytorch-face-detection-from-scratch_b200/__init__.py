@@ -29,7 +29,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 # reference module name -> implemented here (hot path).  Everything else falls through to the reference tree.
 _DROPIN = ["models", "models.BaseModel", "models.BaseSSDModel", "models.PoolResnet", "models.Resnet",
-           "models.SeparableCNN", "models.MobilenetV3Backbone", "models.ModelMeta", "losses",
+           "models.SeparableCNN", "models.MobilenetV3Backbone", "models.SSD", "models.ModelMeta", "losses",
            "losses.YoloLoss", "losses.SSDLoss", "datasets", "datasets.utils", "datasets.WIDERFace",
            "datasets.WIDERFace.dataset", "datasets.WIDERFace.dataset_ssd"]
 _PACKAGES = ["models", "losses", "datasets", "datasets.WIDERFace"]

@@ -95,18 +95,18 @@ template <int K, int S>
 __global__ void __launch_bounds__(256)
 mbv3_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int H,
                int W, int C, int Ho, int Wo, int pad_t, int pad_l, int act, __nv_bfloat16* __restrict__ out,
-               float* __restrict__ se_sum) {
+               float* __restrict__ se_partial) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float s_sum[];            // [C] when se_sum != null
+  __shared__ float s_val[256 * 8];            // this block's bf16-rounded outputs (SqueezeExcite partial sums)
   const int n = blockIdx.y;
   const int C8 = C >> 3;
-  if (se_sum) {
-    for (int i = threadIdx.x; i < C; i += 256) s_sum[i] = 0.f;
-    __syncthreads();
-  }
   const long items = static_cast<long>(Ho) * Wo * C8;
   const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (se_partial) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_val[threadIdx.x * 8 + e] = 0.f;
+  }
   if (idx < items) {
     const int cg = static_cast<int>(idx % C8);
     const long pix = idx / C8;
@@ -143,29 +143,37 @@ mbv3_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
     o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]);
     o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
     *reinterpret_cast<uint4*>(out + (static_cast<long>(n) * Ho * Wo + pix) * C + c0) = o;
-    if (se_sum) {
+    if (se_partial) {
       // SqueezeExcite averages the tensor the next layer READS, i.e. the bf16-rounded values
-      atomicAdd(s_sum + c0 + 0, bf16lo(o.x)); atomicAdd(s_sum + c0 + 1, bf16hi(o.x));
-      atomicAdd(s_sum + c0 + 2, bf16lo(o.y)); atomicAdd(s_sum + c0 + 3, bf16hi(o.y));
-      atomicAdd(s_sum + c0 + 4, bf16lo(o.z)); atomicAdd(s_sum + c0 + 5, bf16hi(o.z));
-      atomicAdd(s_sum + c0 + 6, bf16lo(o.w)); atomicAdd(s_sum + c0 + 7, bf16hi(o.w));
+      float* sv = s_val + threadIdx.x * 8;
+      sv[0] = bf16lo(o.x); sv[1] = bf16hi(o.x); sv[2] = bf16lo(o.y); sv[3] = bf16hi(o.y);
+      sv[4] = bf16lo(o.z); sv[5] = bf16hi(o.z); sv[6] = bf16lo(o.w); sv[7] = bf16hi(o.w);
     }
   }
-  if (se_sum) {
+  if (se_partial) {
+    // DETERMINISTIC block partial (no atomics: inference must be bit-reproducible run to run): channel c is summed over
+    // the block's threads that hold channel group c / 8, in thread order; se_partial[n][block][c] is a plain store and
+    // fd_se_gate adds the blocks in block order.
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += 256) {
-      const float v = s_sum[i];
-      if (v != 0.f) atomicAdd(se_sum + static_cast<long>(n) * C + i, v);
+    const int first_cg = static_cast<int>((blockIdx.x * 256L) % C8);      // channel group of thread 0
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const int cg = c >> 3, e = c & 7;
+      int t = cg - first_cg;
+      if (t < 0) t += C8;
+      float a = 0.f;
+      for (; t < 256; t += C8) a += s_val[t * 8 + e];
+      se_partial[(static_cast<long>(n) * gridDim.x + blockIdx.x) * C + c] = a;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ SqueezeExcite gate
-// one CTA per image: mean[c] = sum[c] / HW ; r = relu(W1 mean + b1) ; gate = hardsigmoid(W2 r + b2).
-// sum is ZEROED after it has been read, ready for the next forward pass.
+// one CTA per image: mean[c] = (sum over the depthwise kernel's block partials) / HW ; r = relu(W1 mean + b1) ;
+// gate = hardsigmoid(W2 r + b2).
 __global__ void __launch_bounds__(256)
-mbv3_se_kernel(float* __restrict__ sum, float inv_hw, const float* __restrict__ w1, const float* __restrict__ b1,
-               const float* __restrict__ w2, const float* __restrict__ b2, int C, int R, float* __restrict__ gate) {
+mbv3_se_kernel(const float* __restrict__ partial, int nblk, float inv_hw, const float* __restrict__ w1,
+               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int C, int R,
+               float* __restrict__ gate) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];          // mean[C] | r[R]
@@ -173,8 +181,10 @@ mbv3_se_kernel(float* __restrict__ sum, float inv_hw, const float* __restrict__ 
   float* s_r = sm + C;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += 256) {
-    s_mean[c] = sum[static_cast<long>(n) * C + c] * inv_hw;
-    sum[static_cast<long>(n) * C + c] = 0.f;
+    const float* pp = partial + static_cast<long>(n) * nblk * C + c;
+    float a = 0.f;
+    for (int k = 0; k < nblk; ++k) a += pp[static_cast<long>(k) * C];      // fixed order: deterministic
+    s_mean[c] = a * inv_hw;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -308,6 +318,11 @@ extern "C" int fd_dw_pack(const float* w, const float* scale, int C, int K, floa
   return launch_status();
 }
 
+extern "C" int fd_dwconv_se_blocks(int Ho, int Wo, int C) {
+  if (Ho <= 0 || Wo <= 0 || C <= 0 || C % 8) return -1;
+  return static_cast<int>((static_cast<long>(Ho) * Wo * (C / 8) + 255) / 256);
+}
+
 extern "C" int fd_dwconv(const fd_bf16* x, const float* w_packed, const float* bias, int B, int H, int W, int C, int K,
                          int stride, int pad_t, int pad_l, int Ho, int Wo, int act, fd_bf16* out, float* se_sum,
                          void* stream) {
@@ -315,7 +330,7 @@ extern "C" int fd_dwconv(const fd_bf16* x, const float* w_packed, const float* b
   if (C % 8 || (K != 3 && K != 5) || (stride != 1 && stride != 2) || act < 0 || act > 2 || B > 65535) return FD_EUNSUPPORTED;
   const long items = static_cast<long>(Ho) * Wo * (C / 8);
   const dim3 grid(static_cast<unsigned>((items + 255) / 256), B);
-  const size_t smem = se_sum ? static_cast<size_t>(C) * 4 : 0;
+  const size_t smem = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
@@ -330,11 +345,11 @@ extern "C" int fd_dwconv(const fd_bf16* x, const float* w_packed, const float* b
   return launch_status();
 }
 
-extern "C" int fd_se_gate(float* se_sum, int B, int HW, const float* w1, const float* b1, const float* w2, const float* b2,
-                          int C, int R, float* gate, void* stream) {
-  if (!se_sum || !w1 || !b1 || !w2 || !b2 || !gate || B <= 0 || HW <= 0 || C <= 0 || R <= 0) return FD_EINVAL;
-  launch_k(mbv3_se_kernel, dim3(B), dim3(256), static_cast<size_t>(C + R) * 4, static_cast<cudaStream_t>(stream), se_sum,
-           1.f / static_cast<float>(HW), w1, b1, w2, b2, C, R, gate);
+extern "C" int fd_se_gate(const float* se_partial, int nblk, int B, int HW, const float* w1, const float* b1, const float* w2,
+                          const float* b2, int C, int R, float* gate, void* stream) {
+  if (!se_partial || !w1 || !b1 || !w2 || !b2 || !gate || B <= 0 || HW <= 0 || C <= 0 || R <= 0 || nblk <= 0) return FD_EINVAL;
+  launch_k(mbv3_se_kernel, dim3(B), dim3(256), static_cast<size_t>(C + R) * 4, static_cast<cudaStream_t>(stream), se_partial,
+           nblk, 1.f / static_cast<float>(HW), w1, b1, w2, b2, C, R, gate);
   count_launch();
   return launch_status();
 }

@@ -193,7 +193,7 @@ class MobilenetV3Engine:
                 st["pad"] = (_same_pad_lo(h, k, s), _same_pad_lo(w, k, s)) if s > 1 else (k // 2, k // 2)
                 st["dw"] = buf(ho, wo, cdw)
                 if "se" in blk:
-                    st["sum"] = torch.zeros((B, cdw), dtype=F32, device=dev)
+                    st["sum"] = torch.empty((B, ops.dwconv_se_blocks(ho, wo, cdw), cdw), dtype=F32, device=dev)
                     st["gate"] = torch.empty((B, cdw), dtype=F32, device=dev)
                 st["out"] = buf(ho, wo, blk["cout"])
                 st["skip"] = s == 1 and cin == blk["cout"]
@@ -222,7 +222,7 @@ class MobilenetV3Engine:
                 ops.pw_conv(cur, blk["pw"]["w"], blk["pw"]["b"], blk["pw"]["N"], blk["act"], st["exp"])
                 t = st["exp"]
             ops.dwconv(t, blk["dw"]["w"], blk["dw"]["b"], blk["k"], blk["s"], st["pad"][0], st["pad"][1], blk["act"],
-                       st["dw"], se_sum=st.get("sum"))
+                       st["dw"], se_partial=st.get("sum"))
             if "se" in blk:
                 se = blk["se"]
                 ops.se_gate(st["sum"], st["dw"].shape[1] * st["dw"].shape[2], se["w1"], se["b1"], se["w2"], se["b2"],

@@ -67,11 +67,14 @@ SIGNATURES = {
     "fd_mbv3_stem": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "fd_dw_pack": [_P, _P, _I, _I, _P, _P],
     "fd_dwconv": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
-    "fd_se_gate": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P],
+    "fd_se_gate": [_P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P],
+    "fd_dwconv_se_blocks": [_I, _I, _I],
     "fd_scale_channels": [_P, _P, _I, _I, _I, _P],
     "fd_head3x3_fwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "fd_resize_bilinear": [_P, _I, _c.c_long, _I, _I, _I, _I, _P, _P],
     "fd_index_copy_f32": [_P, _P, _P, _c.c_long, _I, _P],
+    "fd_ssd_head_fwd": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P],
+    "fd_ssd_head_bwd": [_P, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P],
 }
 
 

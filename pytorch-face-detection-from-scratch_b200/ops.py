@@ -273,18 +273,24 @@ def dw_pack(w, scale, out):
     check(lib().fd_dw_pack(dptr(w, F32), dptr(scale, F32), C, K, dptr(out, F32), cur_stream()), "fd_dw_pack")
 
 
-def dwconv(x, w_packed, bias, K, stride, pad_t, pad_l, act, out, se_sum=None):
+def dwconv_se_blocks(Ho, Wo, C):
+    return int(lib().fd_dwconv_se_blocks(int(Ho), int(Wo), int(C)))
+
+
+def dwconv(x, w_packed, bias, K, stride, pad_t, pad_l, act, out, se_partial=None):
+    """se_partial: fp32 [B, dwconv_se_blocks(Ho, Wo, C), C] -- per-block channel sums of the output (SqueezeExcite)."""
     B, H, W, C = x.shape
     _, Ho, Wo, _ = out.shape
+    assert se_partial is None or tuple(se_partial.shape) == (B, dwconv_se_blocks(Ho, Wo, C), C)
     check(lib().fd_dwconv(dptr(x, BF16), dptr(w_packed, F32), dptr(bias, F32), B, H, W, C, int(K), int(stride), int(pad_t),
-                          int(pad_l), Ho, Wo, int(act), dptr(out, BF16), dptr(se_sum, F32), cur_stream()), "fd_dwconv")
+                          int(pad_l), Ho, Wo, int(act), dptr(out, BF16), dptr(se_partial, F32), cur_stream()), "fd_dwconv")
 
 
-def se_gate(se_sum, HW, w1, b1, w2, b2, gate):
-    B, C = se_sum.shape
+def se_gate(se_partial, HW, w1, b1, w2, b2, gate):
+    B, nblk, C = se_partial.shape
     R = w1.shape[0]
-    check(lib().fd_se_gate(dptr(se_sum, F32), B, int(HW), dptr(w1, F32), dptr(b1, F32), dptr(w2, F32), dptr(b2, F32), C, R,
-                           dptr(gate, F32), cur_stream()), "fd_se_gate")
+    check(lib().fd_se_gate(dptr(se_partial, F32), nblk, B, int(HW), dptr(w1, F32), dptr(b1, F32), dptr(w2, F32),
+                           dptr(b2, F32), C, R, dptr(gate, F32), cur_stream()), "fd_se_gate")
 
 
 def scale_channels(x, gate):
@@ -312,3 +318,24 @@ def index_copy(dst, src, idx, scatter):
     """scatter: dst[idx[i]] = src[i]; gather: dst[i] = src[idx[i]]  (flat fp32 buffers, int32 index)."""
     check(lib().fd_index_copy_f32(dptr(dst, F32), dptr(src, F32), dptr(idx, I32), idx.numel(), int(bool(scatter)),
                                   cur_stream()), "fd_index_copy_f32")
+
+
+def _ptr_array(tensors, dtype):
+    return (ctypes.c_void_p * len(tensors))(*[dptr(t, dtype) for t in tensors])
+
+
+def ssd_head_fwd(x_planes, w, bias, mult, priors, prior_off, out):
+    """x_planes: list of [B,H,W,64] bf16 planes of one scale; out [B,P,5] fp32 (rows prior_off .. prior_off + H*W)."""
+    B, H, W, _ = x_planes[0].shape
+    C = w.shape[1]
+    check(lib().fd_ssd_head_fwd(_ptr_array(x_planes, BF16), len(x_planes), dptr(w, F32), dptr(bias, F32), B, H * W, C,
+                                dptr(mult, F32), dptr(priors, F32), int(prior_off), out.shape[1], dptr(out, F32),
+                                cur_stream()), "fd_ssd_head_fwd")
+
+
+def ssd_head_bwd(x_planes, dx_planes, w, mult, prior_off, out, dout, dw, db):
+    B, H, W, _ = x_planes[0].shape
+    C = w.shape[1]
+    check(lib().fd_ssd_head_bwd(_ptr_array(x_planes, BF16), _ptr_array(dx_planes, BF16), len(x_planes), dptr(w, F32), B,
+                                H * W, C, dptr(mult, F32), int(prior_off), out.shape[1], dptr(out, F32), dptr(dout, F32),
+                                dptr(dw, F32), dptr(db, F32), cur_stream()), "fd_ssd_head_bwd")

@@ -1,11 +1,13 @@
 """The oracle (oracle/*.py) against golden vectors produced by the REAL reference
 (tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import torch
 
 from oracle import yolo_oracle as yo
 from oracle import backbone_oracle as bo
-from tests.util import load_golden, seeded_poolresnet_params
+from tests.util import GOLDEN, load_golden, seeded_poolresnet_params
 
 
 def test_grid_encode_bit_exact():
@@ -215,3 +217,66 @@ def test_wide_models_oracle_matches_reference_seeded():
     with torch.no_grad():
         ys = bo.separable_forward(xs, ps)
     assert (ys - torch.from_numpy(g["sep_y_hat"])).abs().max().item() <= 1e-6
+
+
+def test_mobilenetv3_oracle_matches_archive_golden():
+    """oracle.backbone_oracle.mobilenetv3_forward (restated from the code stored in the official TorchScript archive, timm
+    absent) == the archive's own heads on three of the 24 frames (make_golden_official.py): max-abs-diff <= 1e-6."""
+    import cv2
+    from oracle import backbone_oracle as bo
+    g = np.load(os.path.join(GOLDEN, "official_mobilenetv3.npz"))
+    im = np.load(os.path.join(GOLDEN, "official_images.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    for i in (0, 11, 23):
+        rgb = cv2.imdecode(im["png"][im["offsets"][i]:im["offsets"][i + 1]], cv2.IMREAD_UNCHANGED)
+        t = torch.from_numpy(rgb).permute(2, 0, 1)
+        x = torch.stack([t, t]).float() / 255.0
+        with torch.no_grad():
+            y = bo.mobilenetv3_forward(x, sd)
+        assert (y[0] - torch.from_numpy(g["heads"][i])).abs().max().item() <= 1e-6
+        got = yo.reduce_bounding_boxes(g["heads"][i], float(g["p_thr"]), float(g["iou_thr"]), (3, 480, 480), 15)
+        want = g["boxes"][i, :g["counts"][i]]
+        assert got.shape == want.shape and got.tobytes() == want.tobytes()
+
+
+def test_official_checkpoint_goldens_decode_with_oracle():
+    """All 24 frames x (PoolResnet medium / small, Resnet medium): the oracle decode + NMS of the stored reference heads
+    reproduces the stored demo-path boxes bit for bit; the backbone oracle reproduces two heads per model exactly."""
+    import cv2
+    from oracle import backbone_oracle as bo
+    im = np.load(os.path.join(GOLDEN, "official_images.npz"))
+    med = np.load(os.path.join(GOLDEN, "official_medium.npz"))
+    for name, S, fwd in (("official_poolresnet_medium.npz", 10, bo.poolresnet_forward),
+                         ("official_poolresnet_small.npz", 10, bo.poolresnet_forward),
+                         ("official_resnet_medium.npz", 15, bo.resnet_forward)):
+        g = np.load(os.path.join(GOLDEN, name))
+        for i in range(24):
+            got = yo.reduce_bounding_boxes(g["heads"][i], float(g["p_thr"]), float(g["iou_thr"]), (3, 480, 480), S)
+            want = g["boxes"][i, :g["counts"][i]]
+            assert got.shape == want.shape and got.tobytes() == want.tobytes(), (name, i)
+        src = med if name == "official_poolresnet_medium.npz" else g
+        sd = {k[3:]: torch.from_numpy(src[k]) for k in src.files if k.startswith("sd.")}
+        for i in (3, 17):
+            rgb = cv2.imdecode(im["png"][im["offsets"][i]:im["offsets"][i + 1]], cv2.IMREAD_UNCHANGED)
+            t = torch.from_numpy(rgb).permute(2, 0, 1)
+            x = torch.stack([t, t]).float() / 255.0
+            with torch.no_grad():
+                y = fwd(x, sd, S)
+            assert (y[0] - torch.from_numpy(g["heads"][i])).abs().max().item() <= 1e-6, (name, i)
+
+
+def test_ssd_model_oracle_matches_reference_golden():
+    """oracle ssd_forward / ssd_train_step == the real reference's SSD model, loss and gradient norms (make_golden_ssd_model.py)."""
+    from oracle import backbone_oracle as bo
+    from tests.gpu_util import fd
+    g = np.load(os.path.join(GOLDEN, "ssd_model_seed2.npz"))
+    torch.manual_seed(2)
+    m = fd().models.SSD.SSD(filters=16, input_shape=(3, 480, 480))          # the mirror's construction order == the reference's
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    for k, v in p.items():
+        assert abs(v.double().sum().item() - g["w_sum." + k][0]) < 1e-9, k
+    x = torch.rand(2, 3, 480, 480, generator=torch.Generator().manual_seed(0))
+    y_hat, loss, grads = bo.ssd_train_step(x[:1], torch.from_numpy(g["y"][:1]), p)      # one image keeps the CPU suite fast
+    assert (y_hat - torch.from_numpy(g["y_hat"][:1])).abs().max().item() <= 1e-6
+    y_hat2 = bo.ssd_forward(x[1:], p)
+    assert (y_hat2 - torch.from_numpy(g["y_hat"][1:])).abs().max().item() <= 1e-6
