@@ -245,7 +245,8 @@ FD_API int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const float* w
                 const float* chan_scale2, float slope, fd_bf16* dx2, float* dw, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * MaxPool2d(2) (models/PoolResnet.py:41-42).  x: [B,H,W,C] bf16 -> y: [B,H/2,W/2,C] bf16.
+ * MaxPool2d(2) (models/PoolResnet.py:41-42; floor mode for odd H / W, models/SSD.py:80 pools 15 -> 7).
+ * x: [B,H,W,C] bf16 -> y: [B,H/2,W/2,C] bf16.
  * argmax (nullable, training): uint16 [B,H/2,W/2,C/8], 2 bits per channel = position dy*2+dx of the FIRST maximum of
  * the window (torch's tie rule); with it the backward does not re-read x. */
 FD_API int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, uint16_t* argmax, void* stream);

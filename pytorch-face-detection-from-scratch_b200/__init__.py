@@ -132,5 +132,5 @@ def uninstall_dropin():
                 sys.modules.pop(name, None)
 
 
-for _m in _DROPIN + ["engine", "parallel", "optim"]:
+for _m in _DROPIN + ["engine", "parallel", "optim", "export"]:
     importlib.import_module(f"{__name__}.{_m}")

@@ -1293,7 +1293,7 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
 extern "C" int fd_maxpool2x2_fwd(const fd_bf16* x, int B, int H, int W, int C, fd_bf16* y, uint16_t* argmax,
                                  void* stream) {
   if (!x || !y || B <= 0) return FD_EINVAL;
-  if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
+  if (C % 8 != 0 || H < 2 || W < 2) return FD_EUNSUPPORTED;       // odd H / W: floor mode like nn.MaxPool2d(2) (SSD.py:80, 15 -> 7)
   const long rows = static_cast<long>(B) * (H / 2);
   if (rows > 0x7fffffffL) return FD_EUNSUPPORTED;
   const int per_row = (W / 2) * (C / 8);
@@ -1311,7 +1311,14 @@ extern "C" int fd_maxpool2x2_bwd(const fd_bf16* x, const fd_bf16* gy, int B, int
   if ((!x && !argmax) || !gy || (!gs && !gs2) || B <= 0) return FD_EINVAL;
   if ((gs2 != nullptr) != (mask_bits != nullptr)) return FD_EINVAL;
   if (gs2 && C % 32 != 0) return FD_EUNSUPPORTED;
-  if (C % 8 != 0 || H % 2 != 0 || W % 2 != 0) return FD_EUNSUPPORTED;
+  if (C % 8 != 0 || H < 2 || W < 2) return FD_EUNSUPPORTED;
+  if ((H | W) & 1) {      // floor mode: the last row / column belongs to no window -> zero gradient (the kernel writes windows only)
+    const size_t bytes = static_cast<size_t>(B) * H * W * C * 2;
+    cudaError_t e = cudaSuccess;
+    if (gs) e = cudaMemsetAsync(gs, 0, bytes, static_cast<cudaStream_t>(stream));
+    if (e == cudaSuccess && gs2) e = cudaMemsetAsync(gs2, 0, bytes, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+  }
   const long rows = static_cast<long>(B) * (H / 2);
   if (rows > 0x7fffffffL) return FD_EUNSUPPORTED;
   const int per_row = (W / 2) * (C / 8);

@@ -90,7 +90,11 @@ mbv3_stem_kernel(const void* __restrict__ xin, const float* __restrict__ w, cons
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise
-// thread = one output pixel x 8 channels (one 16-byte vector); grid.y = image.  w: [K*K][C] fp32 tap-major.
+// thread = a strip of kDwT horizontally adjacent output pixels x 8 channels (one 16-byte vector per pixel); grid.y = image.
+// Per kernel row the K weight vectors and the (T-1)*S+K input vectors of the strip are loaded ONCE and reused by all
+// T outputs (a thread-per-pixel version re-loaded 3 vectors per tap and was L1/LSU bound at ~0.07 of HBM).
+// w: [K*K][C] fp32 tap-major.
+constexpr int kDwT = 4;
 template <int K, int S>
 __global__ void __launch_bounds__(256)
 mbv3_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int H,
@@ -98,62 +102,88 @@ mbv3_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                float* __restrict__ se_partial) {
   pdl_trigger();
   pdl_wait();
+  constexpr int T = kDwT, NX = (T - 1) * S + K;
   __shared__ float s_val[256 * 8];            // this block's bf16-rounded outputs (SqueezeExcite partial sums)
   const int n = blockIdx.y;
   const int C8 = C >> 3;
-  const long items = static_cast<long>(Ho) * Wo * C8;
+  const int strips = (Wo + T - 1) / T;
+  const long items = static_cast<long>(Ho) * strips * C8;
   const long idx = blockIdx.x * 256L + threadIdx.x;
-  if (se_partial) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s_val[threadIdx.x * 8 + e] = 0.f;
-  }
+  float ssum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (idx < items) {
     const int cg = static_cast<int>(idx % C8);
-    const long pix = idx / C8;
-    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>(pix / Wo);
+    const long rest = idx / C8;
+    const int strip = static_cast<int>(rest % strips), oy = static_cast<int>(rest / strips);
+    const int ox0 = strip * T;
     const int c0 = cg * 8;
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-    uint64_t a0 = pk2(b0.x, b0.y), a1 = pk2(b0.z, b0.w), a2 = pk2(b1.x, b1.y), a3 = pk2(b1.z, b1.w);
-    const __nv_bfloat16* xn = x + static_cast<long>(n) * H * W * C;
-    const int iy0 = oy * S - pad_t, ix0 = ox * S - pad_l;
+    uint64_t acc[T][4];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      acc[t][0] = pk2(b0.x, b0.y); acc[t][1] = pk2(b0.z, b0.w); acc[t][2] = pk2(b1.x, b1.y); acc[t][3] = pk2(b1.z, b1.w);
+    }
+    const __nv_bfloat16* xn = x + static_cast<long>(n) * H * W * C + c0;
+    const int iy0 = oy * S - pad_t, ix0 = ox0 * S - pad_l;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
       const int iy = iy0 + ky;
       if (iy < 0 || iy >= H) continue;
+      uint64_t wv[K][4];
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
-        const int ix = ix0 + kx;
-        if (ix < 0 || ix >= W) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(xn + (static_cast<long>(iy) * W + ix) * C + c0));
         const float* wp = w + (ky * K + kx) * C + c0;
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
         const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-        a0 = fma2(pk2u(v.x << 16, v.x & 0xFFFF0000u), pk2(w0.x, w0.y), a0);
-        a1 = fma2(pk2u(v.y << 16, v.y & 0xFFFF0000u), pk2(w0.z, w0.w), a1);
-        a2 = fma2(pk2u(v.z << 16, v.z & 0xFFFF0000u), pk2(w1.x, w1.y), a2);
-        a3 = fma2(pk2u(v.w << 16, v.w & 0xFFFF0000u), pk2(w1.z, w1.w), a3);
+        wv[kx][0] = pk2(w0.x, w0.y); wv[kx][1] = pk2(w0.z, w0.w); wv[kx][2] = pk2(w1.x, w1.y); wv[kx][3] = pk2(w1.z, w1.w);
+      }
+      const __nv_bfloat16* xr = xn + static_cast<long>(iy) * W * C;
+      uint4 xv[NX];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        const int ix = ix0 + j;
+        xv[j] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint4*>(xr + static_cast<long>(ix) * C)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        const uint64_t x0 = pk2u(xv[j].x << 16, xv[j].x & 0xFFFF0000u), x1 = pk2u(xv[j].y << 16, xv[j].y & 0xFFFF0000u);
+        const uint64_t x2 = pk2u(xv[j].z << 16, xv[j].z & 0xFFFF0000u), x3 = pk2u(xv[j].w << 16, xv[j].w & 0xFFFF0000u);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int kx = j - t * S;                       // compile-time after unrolling
+          if (kx >= 0 && kx < K) {
+            acc[t][0] = fma2(x0, wv[kx][0], acc[t][0]);
+            acc[t][1] = fma2(x1, wv[kx][1], acc[t][1]);
+            acc[t][2] = fma2(x2, wv[kx][2], acc[t][2]);
+            acc[t][3] = fma2(x3, wv[kx][3], acc[t][3]);
+          }
+        }
       }
     }
-    float r[8];
-    upk2(a0, r[0], r[1]); upk2(a1, r[2], r[3]); upk2(a2, r[4], r[5]); upk2(a3, r[6], r[7]);
+    __nv_bfloat16* orow = out + ((static_cast<long>(n) * Ho + oy) * Wo) * C + c0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = act_apply(r[i], act);
-    uint4 o;
-    o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]);
-    o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
-    *reinterpret_cast<uint4*>(out + (static_cast<long>(n) * Ho * Wo + pix) * C + c0) = o;
-    if (se_partial) {
-      // SqueezeExcite averages the tensor the next layer READS, i.e. the bf16-rounded values
-      float* sv = s_val + threadIdx.x * 8;
-      sv[0] = bf16lo(o.x); sv[1] = bf16hi(o.x); sv[2] = bf16lo(o.y); sv[3] = bf16hi(o.y);
-      sv[4] = bf16lo(o.z); sv[5] = bf16hi(o.z); sv[6] = bf16lo(o.w); sv[7] = bf16hi(o.w);
+    for (int t = 0; t < T; ++t) {
+      if (ox0 + t < Wo) {
+        float r[8];
+        upk2(acc[t][0], r[0], r[1]); upk2(acc[t][1], r[2], r[3]); upk2(acc[t][2], r[4], r[5]); upk2(acc[t][3], r[6], r[7]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = act_apply(r[i], act);
+        uint4 o;
+        o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]);
+        o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
+        *reinterpret_cast<uint4*>(orow + static_cast<long>(ox0 + t) * C) = o;
+        // SqueezeExcite averages the tensor the next layer READS, i.e. the bf16-rounded values
+        ssum[0] += bf16lo(o.x); ssum[1] += bf16hi(o.x); ssum[2] += bf16lo(o.y); ssum[3] += bf16hi(o.y);
+        ssum[4] += bf16lo(o.z); ssum[5] += bf16hi(o.z); ssum[6] += bf16lo(o.w); ssum[7] += bf16hi(o.w);
+      }
     }
   }
   if (se_partial) {
     // DETERMINISTIC block partial (no atomics: inference must be bit-reproducible run to run): channel c is summed over
     // the block's threads that hold channel group c / 8, in thread order; se_partial[n][block][c] is a plain store and
     // fd_se_gate adds the blocks in block order.
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_val[threadIdx.x * 8 + e] = ssum[e];
     __syncthreads();
     const int first_cg = static_cast<int>((blockIdx.x * 256L) % C8);      // channel group of thread 0
     for (int c = threadIdx.x; c < C; c += 256) {
@@ -182,9 +212,15 @@ mbv3_se_kernel(const float* __restrict__ partial, int nblk, float inv_hw, const 
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += 256) {
     const float* pp = partial + static_cast<long>(n) * nblk * C + c;
-    float a = 0.f;
-    for (int k = 0; k < nblk; ++k) a += pp[static_cast<long>(k) * C];      // fixed order: deterministic
-    s_mean[c] = a * inv_hw;
+    // 8 independent chains (8 loads in flight instead of one L2 round trip per block), combined in a FIXED order
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 8 <= nblk; k += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += __ldg(pp + static_cast<long>(k + u) * C);
+    }
+    for (int u = 0; k < nblk; ++k, ++u) a[u] += __ldg(pp + static_cast<long>(k) * C);
+    s_mean[c] = (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) * inv_hw;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -230,7 +266,10 @@ mbv3_scale_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ gate,
 
 // ------------------------------------------------------------------------------------------------ head
 // 3x3 pad-1 conv C -> 5 + bias + sigmoid (MobilenetV3Backbone.py:40-46,57-58).  grid = (B, row groups); one warp per
-// output pixel, lanes over channel pairs; weights bf16 [9][5][C] in shared memory.  y: [B,5,H,W] fp32.
+// strip of 4 horizontally adjacent output pixels, lanes over channel pairs; weights bf16 [9][5][C] in shared memory:
+// the five weight pairs of a (tap, channel pair) are fetched once and feed the four pixels (40 FMAs per 5 LDS + 4 LDG).
+// y: [B,5,H,W] fp32.
+constexpr int kHeadPix = 4;
 __global__ void __launch_bounds__(256)
 mbv3_head_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int H,
                  int W, int C, float* __restrict__ y) {
@@ -244,37 +283,58 @@ mbv3_head_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
   __syncthreads();
   const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __nv_bfloat16* xn = x + static_cast<long>(n) * H * W * C;
-  for (int pix = blockIdx.y * 8 + warp; pix < H * W; pix += gridDim.y * 8) {
-    const int oy = pix / W, ox = pix % W;
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const int strips = (W + kHeadPix - 1) / kHeadPix;
+  for (int item = blockIdx.y * 8 + warp; item < H * strips; item += gridDim.y * 8) {
+    const int oy = item / strips, ox0 = (item - oy * strips) * kHeadPix;
+    float acc[kHeadPix][5];
+#pragma unroll
+    for (int p = 0; p < kHeadPix; ++p)
+#pragma unroll
+      for (int o = 0; o < 5; ++o) acc[p][o] = 0.f;
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = oy + ky - 1;
       if (iy < 0 || iy >= H) continue;
       for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox + kx - 1;
-        if (ix < 0 || ix >= W) continue;
-        const uint32_t* xp = reinterpret_cast<const uint32_t*>(xn + (static_cast<long>(iy) * W + ix) * C);
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_w + (ky * 3 + kx) * 5 * C);
+        const uint32_t* xrow = reinterpret_cast<const uint32_t*>(xn + static_cast<long>(iy) * W * C);
+        bool ok[kHeadPix];
+#pragma unroll
+        for (int p = 0; p < kHeadPix; ++p) {
+          const int ix = ox0 + p + kx - 1;
+          ok[p] = ix >= 0 && ix < W;
+        }
         for (int c2 = lane; c2 < (C >> 1); c2 += 32) {
-          const uint32_t xv = __ldg(xp + c2);
-          const float x0 = bf16lo(xv), x1 = bf16hi(xv);
+          float w0[5], w1[5];
 #pragma unroll
           for (int o = 0; o < 5; ++o) {
             const uint32_t wv = wp[o * (C >> 1) + c2];
-            acc[o] = fmaf(x0, bf16lo(wv), fmaf(x1, bf16hi(wv), acc[o]));
+            w0[o] = bf16lo(wv);
+            w1[o] = bf16hi(wv);
+          }
+#pragma unroll
+          for (int p = 0; p < kHeadPix; ++p) {
+            if (ok[p]) {
+              const uint32_t xv = __ldg(xrow + static_cast<long>(ox0 + p + kx - 1) * (C >> 1) + c2);
+              const float x0 = bf16lo(xv), x1 = bf16hi(xv);
+#pragma unroll
+              for (int o = 0; o < 5; ++o) acc[p][o] = fmaf(x0, w0[o], fmaf(x1, w1[o], acc[p][o]));
+            }
           }
         }
       }
     }
 #pragma unroll
-    for (int o = 0; o < 5; ++o) {
+    for (int p = 0; p < kHeadPix; ++p) {
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
-    }
-    if (lane < 5) {
-      float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : acc[4];
-      v += __ldg(bias + lane);
-      y[((static_cast<long>(n) * 5 + lane) * H + oy) * W + ox] = 1.f / (1.f + expf(-v));
+      for (int o = 0; o < 5; ++o) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[p][o] += __shfl_xor_sync(0xffffffffu, acc[p][o], d);
+      }
+      if (lane < 5 && ox0 + p < W) {
+        float v = lane == 0 ? acc[p][0] : lane == 1 ? acc[p][1] : lane == 2 ? acc[p][2] : lane == 3 ? acc[p][3] : acc[p][4];
+        v += __ldg(bias + lane);
+        y[((static_cast<long>(n) * 5 + lane) * H + oy) * W + ox0 + p] = 1.f / (1.f + expf(-v));
+      }
     }
   }
 }
@@ -320,7 +380,7 @@ extern "C" int fd_dw_pack(const float* w, const float* scale, int C, int K, floa
 
 extern "C" int fd_dwconv_se_blocks(int Ho, int Wo, int C) {
   if (Ho <= 0 || Wo <= 0 || C <= 0 || C % 8) return -1;
-  return static_cast<int>((static_cast<long>(Ho) * Wo * (C / 8) + 255) / 256);
+  return static_cast<int>((static_cast<long>(Ho) * ((Wo + kDwT - 1) / kDwT) * (C / 8) + 255) / 256);
 }
 
 extern "C" int fd_dwconv(const fd_bf16* x, const float* w_packed, const float* bias, int B, int H, int W, int C, int K,
@@ -328,7 +388,7 @@ extern "C" int fd_dwconv(const fd_bf16* x, const float* w_packed, const float* b
                          void* stream) {
   if (!x || !w_packed || !bias || !out || B <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return FD_EINVAL;
   if (C % 8 || (K != 3 && K != 5) || (stride != 1 && stride != 2) || act < 0 || act > 2 || B > 65535) return FD_EUNSUPPORTED;
-  const long items = static_cast<long>(Ho) * Wo * (C / 8);
+  const long items = static_cast<long>(Ho) * ((Wo + kDwT - 1) / kDwT) * (C / 8);
   const dim3 grid(static_cast<unsigned>((items + 255) / 256), B);
   const size_t smem = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

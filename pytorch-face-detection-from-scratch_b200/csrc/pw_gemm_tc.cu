@@ -29,7 +29,7 @@ constexpr int kPwMaxStages = 8;
 
 struct PwParams {
   long M;
-  int K, N, N16, nsplit, kslabs, last_ksteps, stages, nchunks, act;
+  int K, N, N16, nsplit, kslabs, last_ksteps, stages, nchunks, act, out_bufs;
   long num_tiles;
   uint32_t wslab_bytes, stage_bytes, tmem_cols, idesc;
   const float* bias;              // [nsplit * N16] fp32 (zero padded)
@@ -155,8 +155,13 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int nt = static_cast<int>(tile - mt * p.nsplit);
       const long m0 = mt * 128;
       const int n0 = nt * p.N16;
-      if (leader) tma_store_wait_read<0>();            // the previous tile's stores have read the staging tile
+      // staging buffer (it % out_bufs) was last read by the TMA stores of tile it - out_bufs
+      if (leader) {
+        if (p.out_bufs == 2) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
+      }
       epi_bar_sync();
+      uint8_t* stg = staging + static_cast<size_t>(it % p.out_bufs) * p.nchunks * 16384;
       mbar_wait(acc_full + buf, aphase);
       tc_fence_after();
       const int row = q * 32 + lane;
@@ -189,7 +194,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         u0.z = pack_bf16x2(v[4], v[5]);   u0.w = pack_bf16x2(v[6], v[7]);
         u1.x = pack_bf16x2(v[8], v[9]);   u1.y = pack_bf16x2(v[10], v[11]);
         u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
-        uint8_t* chunk = staging + static_cast<size_t>(c16 >> 2) * 16384;
+        uint8_t* chunk = stg + static_cast<size_t>(c16 >> 2) * 16384;
         const uint32_t off = static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>(c16 & 3) * 32u;
         *reinterpret_cast<uint4*>(chunk + pw_swz(off)) = u0;
         *reinterpret_cast<uint4*>(chunk + pw_swz(off + 16u)) = u1;
@@ -200,7 +205,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       if (leader) {
         mbar_arrive(acc_empty + buf);                   // every epilogue thread's TMEM reads are complete
         for (int c = 0; c < p.nchunks; ++c) {
-          if (n0 + c * 64 < p.N) tma_store_2d(&tm_out, staging + static_cast<size_t>(c) * 16384, n0 + c * 64, static_cast<int>(m0));
+          if (n0 + c * 64 < p.N) tma_store_2d(&tm_out, stg + static_cast<size_t>(c) * 16384, n0 + c * 64, static_cast<int>(m0));
         }
         tma_store_commit();
       }
@@ -285,7 +290,10 @@ extern "C" int fd_pw_conv(const fd_bf16* x, const fd_bf16* w_packed, const float
   p.wslab_bytes = static_cast<uint32_t>((p.N16 * 128 + 1023) / 1024 * 1024);
   p.stage_bytes = 16384u + p.wslab_bytes;
   const size_t cap = 225 * 1024;
-  const size_t fixed = kPwCtl + static_cast<size_t>(p.nchunks) * 16384 + 1024;
+  // two output staging tiles (the epilogue of tile i does not wait for the TMA stores of tile i-1) when at least three
+  // ring stages still fit beside them
+  p.out_bufs = (kPwCtl + 2 * static_cast<size_t>(p.nchunks) * 16384 + 1024 + 3 * static_cast<size_t>(p.stage_bytes) <= cap) ? 2 : 1;
+  const size_t fixed = kPwCtl + static_cast<size_t>(p.out_bufs) * p.nchunks * 16384 + 1024;
   int stages = static_cast<int>((cap - fixed) / p.stage_bytes);
   if (stages > kPwMaxStages) stages = kPwMaxStages;
   if (stages < 2) return FD_EUNSUPPORTED;

@@ -78,6 +78,13 @@ class BaseModel(nn.Module):
             return x.to(p.device, non_blocking=True)
         return x
 
+    def to_torchscript(self, file_path=None, method="script", example_inputs=None, **kwargs):
+        """``torch.jit.script(model)`` of demo_scripts/convert_checkpoint_to_scripted_model.py:51 / LightningModule's
+        ``to_torchscript`` (train_model.py:61): a ScriptModule with the same ``forward(x, predict)`` that calls the
+        registered ``fd_b200`` operators (export.py); saved to ``file_path`` when given."""
+        from ..export import to_torchscript
+        return to_torchscript(self, file_path)
+
     @torch.no_grad()
     def predict(self, x, probability_threshold=0.5, iou_threshold=0.5):
         """BaseModel.py:56-71."""

@@ -36,6 +36,10 @@ class BaseSSDModel(nn.Module):
     def single_non_max_suppression(self, x):
         return self.reduce_bounding_boxes(x)
 
+    def to_torchscript(self, file_path=None, method="script", example_inputs=None, **kwargs):
+        from ..export import to_torchscript
+        return to_torchscript(self, file_path)
+
     def _resize(self, x):
         from .BaseModel import resize_to
         return resize_to(x, tuple(self.input_shape[1:]))

@@ -98,6 +98,11 @@ class ModelMeta(nn.Module):
                 total_iou += torch.sum(iou)
         return total_iou, total_recall, total_precision
 
+    def to_torchscript(self, file_path=None, method="script", example_inputs=None, **kwargs):
+        """train_model.py:61 ``model_setup.to_torchscript(model_save_path)`` (LightningModule API): exports the wrapped
+        detector."""
+        return self.model.to_torchscript(file_path)
+
     def training_step(self, batch, batch_idx):
         return self.step(batch, batch_idx)
 

@@ -6,7 +6,7 @@ Stated tolerance (north star: "within a stated bf16/fp32 tolerance"): activation
 between the 22 layers with fp32 accumulation, so
   * head outputs (sigmoid, in [0,1]):  max-abs <= 2e-2, mean-abs <= 2e-3
   * summed loss:                       relative <= 1e-2
-  * parameter gradients:               relative L2 error per tensor <= 5e-2, global <= 3e-2
+  * parameter gradients:               relative L2 error per tensor <= 3e-2, global <= 2e-2 (measured worst ~1e-2)
 Integer work on top of the head (kept cells of NMS) is exact whenever the candidates are the same.
 """
 import numpy as np
@@ -20,7 +20,7 @@ from tests.util import load_golden, seeded_poolresnet_params, synth_boxes
 
 pytestmark = pytest.mark.gpu
 
-HEAD_MAX, HEAD_MEAN, LOSS_REL, GRAD_REL, GRAD_GLOBAL = 2e-2, 2e-3, 1e-2, 5e-2, 3e-2
+HEAD_MAX, HEAD_MEAN, LOSS_REL, GRAD_REL, GRAD_GLOBAL = 2e-2, 2e-3, 1e-2, 3e-2, 2e-2
 
 
 def _model(seed=2, **kw):

@@ -112,3 +112,25 @@ def test_div255_fma_sequence_is_the_ieee_quotient():
     q2 = np.array([fma(e[i], r, q[i]) for i in range(256)], dtype=np.float32)
     assert (q2 == want).all()
     assert (q != want).any()
+
+
+def test_torchscript_export_roundtrip_without_gpu(tmp_path):
+    """torch.jit.script / to_torchscript of the mirror models produce an archive whose forward calls the
+    registered fd_b200 operator; it loads in a fresh module namespace, keeps the reference's forward(x, predict) signature
+    and refuses to run without CUDA (no CPU path)."""
+    PoolResnet = fd.models.PoolResnet.PoolResnet
+    torch.manual_seed(0)
+    m = PoolResnet(filters=64, input_shape=(3, 480, 480), num_of_patches=10, probability_threshold=0.7, iou_threshold=0.01)
+    path = tmp_path / "poolresnet.pth"
+    ts = fd.models.ModelMeta(model=m).to_torchscript(path)          # train_model.py:61
+    assert "fd_b200.detector_forward" in ts.code
+    back = torch.jit.load(str(path))
+    assert back.family == "PoolResnet" and list(back.cfg) == [64, 3, 480, 480, 10, 10]
+    assert abs(back.p_thr - 0.7) < 1e-12 and back.flat_state.numel() == 769349
+    assert torch.equal(back.flat_state, fd.export.flatten_state(m))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            back(torch.zeros(2, 3, 480, 480, dtype=torch.uint8), predict=torch.tensor(1))
+    for cls, args in ((fd.models.SSD.SSD, (16, (3, 480, 480))), (fd.models.MobilenetV3Backbone.MobilenetV3Backbone, (576, (3, 480, 480), 15))):
+        s2 = cls(*args).to_torchscript()
+        assert "fd_b200.detector_forward" in s2.code
