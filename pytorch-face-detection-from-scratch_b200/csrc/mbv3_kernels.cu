@@ -96,7 +96,7 @@ mbv3_stem_kernel(const void* __restrict__ xin, const float* __restrict__ w, cons
 // w: [K*K][C] fp32 tap-major.
 constexpr int kDwT = 4;
 template <int K, int S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 mbv3_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int H,
                int W, int C, int Ho, int Wo, int pad_t, int pad_l, int act, __nv_bfloat16* __restrict__ out,
                float* __restrict__ se_partial) {
@@ -200,7 +200,8 @@ mbv3_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
 // ------------------------------------------------------------------------------------------------ SqueezeExcite gate
 // one CTA per image: mean[c] = (sum over the depthwise kernel's block partials) / HW ; r = relu(W1 mean + b1) ;
 // gate = hardsigmoid(W2 r + b2).
-__global__ void __launch_bounds__(256)
+constexpr int kSeThreads = 512;
+__global__ void __launch_bounds__(kSeThreads)
 mbv3_se_kernel(const float* __restrict__ partial, int nblk, float inv_hw, const float* __restrict__ w1,
                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int C, int R,
                float* __restrict__ gate) {
@@ -210,7 +211,7 @@ mbv3_se_kernel(const float* __restrict__ partial, int nblk, float inv_hw, const 
   float* s_mean = sm;
   float* s_r = sm + C;
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += 256) {
+  for (int c = threadIdx.x; c < C; c += kSeThreads) {
     const float* pp = partial + static_cast<long>(n) * nblk * C + c;
     // 8 independent chains (8 loads in flight instead of one L2 round trip per block), combined in a FIXED order
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -224,7 +225,7 @@ mbv3_se_kernel(const float* __restrict__ partial, int nblk, float inv_hw, const 
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < R; j += 8) {
+  for (int j = warp; j < R; j += kSeThreads / 32) {
     float a = 0.f;
     for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + static_cast<long>(j) * C + c), s_mean[c], a);
 #pragma unroll
@@ -232,7 +233,7 @@ mbv3_se_kernel(const float* __restrict__ partial, int nblk, float inv_hw, const 
     if (lane == 0) s_r[j] = fmaxf(a + __ldg(b1 + j), 0.f);
   }
   __syncthreads();
-  for (int c = warp; c < C; c += 8) {
+  for (int c = warp; c < C; c += kSeThreads / 32) {
     float a = 0.f;
     for (int j = lane; j < R; j += 32) a = fmaf(__ldg(w2 + static_cast<long>(c) * R + j), s_r[j], a);
 #pragma unroll
@@ -408,7 +409,7 @@ extern "C" int fd_dwconv(const fd_bf16* x, const float* w_packed, const float* b
 extern "C" int fd_se_gate(const float* se_partial, int nblk, int B, int HW, const float* w1, const float* b1, const float* w2,
                           const float* b2, int C, int R, float* gate, void* stream) {
   if (!se_partial || !w1 || !b1 || !w2 || !b2 || !gate || B <= 0 || HW <= 0 || C <= 0 || R <= 0 || nblk <= 0) return FD_EINVAL;
-  launch_k(mbv3_se_kernel, dim3(B), dim3(256), static_cast<size_t>(C + R) * 4, static_cast<cudaStream_t>(stream), se_partial,
+  launch_k(mbv3_se_kernel, dim3(B), dim3(kSeThreads), static_cast<size_t>(C + R) * 4, static_cast<cudaStream_t>(stream), se_partial,
            nblk, 1.f / static_cast<float>(HW), w1, b1, w2, b2, C, R, gate);
   count_launch();
   return launch_status();

@@ -128,7 +128,7 @@ class SSDEngine:
         self.n_bias_rows = rows
         self.pad_stem_w_off = self.pad_b3_off + rows * 64
         self.pad_stem_b_off = self.pad_stem_w_off + 64 * in_ch * 9
-        self.n_pad = self.pad_stem_b_off + 64
+        self.n_pad = self.pad_stem_b_off + 64 + 4      # + a spare zero the alignment gaps of the un-padded buffer map to
         self.device = None
         self.pflat = self.gflat = None
         self.plans: Dict[tuple, dict] = {}
@@ -365,24 +365,21 @@ class SSDEngine:
         for (hh, ww) in self.head_hw:
             offs.append(o)
             o += hh * ww
-        n3 = 9 * 64 * 64
+        # ---- the four heads first: their input gradients only need dy and the saved block outputs, and the block loop
+        # below adds head_dx of scale k-1 while it processes continue block k
+        for hi in range(4):
+            i = self.n_fe + hi
+            w = self._view(self.pflat, f"extracting_layers.{hi}.0.weight")
+            ops.ssd_head_bwd(pl["blocks"][i]["out"], pl["head_dx"][hi], w, mult, offs[hi], pl["y"], dy,
+                             self._view(self.gflat, f"extracting_layers.{hi}.0.weight"),
+                             self._view(self.gflat, f"extracting_layers.{hi}.0.bias"))
         for i in range(nb - 1, -1, -1):
             b, d = self.blocks[i], pl["blocks"][i]
             drop = drop_all[i] if drop_all is not None else [None] * b.go
             cur = d["inp"]
-            # ---- gradient w.r.t. the block output: head of this scale (+ what the next block left in G)
-            if i >= self.n_fe:
-                hi = i - self.n_fe
-                w = self._view(self.pflat, f"extracting_layers.{hi}.0.weight")
-                ops.ssd_head_bwd(d["out"], pl["head_dx"][hi], w, mult, offs[hi], pl["y"], dy,
-                                 self._view(self.gflat, f"extracting_layers.{hi}.0.weight"),
-                                 self._view(self.gflat, f"extracting_layers.{hi}.0.bias"))
-                if i == nb - 1:
-                    G = pl["head_dx"][hi]
-                else:
-                    G = d["G"]          # already holds (next block's input gradient + head dx), see below
-            else:
-                G = d["G"]
+            # ---- gradient w.r.t. the block output: the last block only has its head; every other G already holds
+            # (next block's input gradient [+ head dx of this scale]), written by the next block's step below
+            G = pl["head_dx"][3] if i == nb - 1 else d["G"]
             # ---- through pool / dropout / LeakyReLU' of conv2
             if b.pool:
                 for g in range(b.go):
