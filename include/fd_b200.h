@@ -40,6 +40,9 @@ typedef uint16_t fd_bf16;
 #define FD_EPI_LRELU 1   /* v = v > 0 ? v : slope * v            (PoolResnet.py:36,38) */
 #define FD_CONV_1X1 2    /* fd_conv3x3: use only the centre tap of the packed weights = a 1x1 convolution
                           * (models/SeparableCNN.py:13-19,29-35 on 64-channel planes) */
+#define FD_CONV_ONE_TAP 4 /* accepted and ignored (reserved): fd_conv3x3 always issues one tap per MMA.  A tap-row fused variant
+                          * (N = 192 MMAs, the three taps of a kernel row sharing one A operand) was measured in round 2 and
+                          * dropped: it triples the TMEM read traffic and the epilogue becomes the bound. */
 
 FD_API int fd_version(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */

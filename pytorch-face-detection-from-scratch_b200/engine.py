@@ -160,6 +160,7 @@ class BackboneEngine:
             off += (n + 3) // 4 * 4          # keep every section 16-byte aligned
         self.n_flat = off
         self.use_chain = True        # fuse runs of equal-shape blocks into one kernel when the image fits in smem
+        self.conv_flags = 0          # ops.CONV_ONE_TAP: per-layer launches bit-identical to the chain kernels (tests)
         self.device = None
         self.pflat = self.gflat = self.dwp = self.w_fwd = self.w_dgrad = None
         self.plans: Dict[tuple, _Plan] = {}
@@ -280,9 +281,9 @@ class BackboneEngine:
                 continue
             cs = pl.drop[k] if pl.drop is not None else None
             ops.conv3x3(cur, self._wf(2 * k), bias=sb3[2 * k], slope=self.slope, lrelu=True, mask_out=blk.ma,
-                        out=blk.a)
+                        out=blk.a, flags=self.conv_flags)
             ops.conv3x3(blk.a, self._wf(2 * k + 1), bias=sb3[2 * k + 1], slope=self.slope, lrelu=True,
-                        chan_scale=cs, residual=cur, mask_out=blk.mb, out=blk.s)
+                        chan_scale=cs, residual=cur, mask_out=blk.mb, out=blk.s, flags=self.conv_flags)
             if blk.pool:
                 ops.maxpool2x2_fwd(blk.s, blk.out, blk.amax)
             cur = blk.out
@@ -370,17 +371,18 @@ class BackboneEngine:
                 GS = blk.gs
             else:
                 GS = blk.G
-            ops.conv3x3(blk.gp2, self._wd(2 * k + 1), slope=self.slope, mask_in=blk.ma, out2=blk.gp1)
+            cf = self.conv_flags
+            ops.conv3x3(blk.gp2, self._wd(2 * k + 1), slope=self.slope, mask_in=blk.ma, out2=blk.gp1, flags=cf)
             if k > 0:
                 prev = pl.blocks[k - 1]
                 if prev.pool:
-                    ops.conv3x3(blk.gp1, self._wd(2 * k), slope=self.slope, residual=GS, out=prev.G)
+                    ops.conv3x3(blk.gp1, self._wd(2 * k), slope=self.slope, residual=GS, out=prev.G, flags=cf)
                 else:
                     ops.conv3x3(blk.gp1, self._wd(2 * k), slope=self.slope, residual=GS, out=prev.G,
                                 mask_in=prev.mb, chan_scale2=drop[k - 1] if drop is not None else None,
-                                out2=prev.gp2)
+                                out2=prev.gp2, flags=cf)
             else:
-                ops.conv3x3(blk.gp1, self._wd(0), slope=self.slope, residual=GS, out=pl.g_stem)
+                ops.conv3x3(blk.gp1, self._wd(0), slope=self.slope, residual=GS, out=pl.g_stem, flags=cf)
                 ops.stem_wgrad(pl.x, pl.g_stem, self.section(self.gflat, "conv1.weight"),
                                self.section(self.gflat, "conv1.bias"), self.stem_s, self.stem_pad,
                                x_cache=getattr(pl, "x_cache", None))

@@ -12,6 +12,7 @@ BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
 
 EPI_LRELU = 1
 CONV_1X1 = 2          # fd_conv3x3: centre tap only (FD_CONV_1X1)
+CONV_ONE_TAP = 4      # fd_conv3x3: the one-tap-per-MMA kernel (FD_CONV_ONE_TAP); the chain kernels are bit-identical to it
 
 
 def conv3x3(x, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_scale=None, residual=None, mask_out=None,

@@ -162,6 +162,7 @@ def test_chain_kernels_equal_per_layer_path(dropout):
     res = {}
     for use_chain in (True, False):
         eng.use_chain = use_chain
+        eng.conv_flags = fd().ops.CONV_ONE_TAP          # the chain kernels issue one tap per MMA: compare like with like
         eng.plans.clear()
         torch.manual_seed(1234)            # same Dropout2d masks in both runs
         pl = eng.train_step(x, gt, dropout=dropout)
@@ -169,6 +170,7 @@ def test_chain_kernels_equal_per_layer_path(dropout):
         res[use_chain] = (pl.y.clone(), pl.loss.clone(), eng.gflat.clone(), pl.blocks[-1].out.clone(),
                           pl.blocks[1].G.clone())
     eng.use_chain = True
+    eng.conv_flags = 0
     assert torch.equal(res[True][3], res[False][3])          # last block output, bf16 bit-exact
     assert torch.equal(res[True][0], res[False][0])          # head
     assert torch.equal(res[True][1], res[False][1])          # per-image loss
@@ -196,8 +198,8 @@ def test_chain_forward_many_images_per_cta(B, H, W):
     cur = x
     for k in range(nb):
         a, s = torch.empty_like(x), torch.empty_like(x)
-        ops.conv3x3(cur, wf[2 * k], bias=bias[2 * k], lrelu=True, out=a)
-        ops.conv3x3(a, wf[2 * k + 1], bias=bias[2 * k + 1], lrelu=True, residual=cur, out=s)
+        ops.conv3x3(cur, wf[2 * k], bias=bias[2 * k], lrelu=True, out=a, flags=ops.CONV_ONE_TAP)
+        ops.conv3x3(a, wf[2 * k + 1], bias=bias[2 * k + 1], lrelu=True, residual=cur, out=s, flags=ops.CONV_ONE_TAP)
         assert torch.equal(outs[k], s), k
         cur = s
 

@@ -18,17 +18,17 @@ out = torch.empty_like(x)
 mo = torch.empty(B, H, W, 2, dtype=torch.int32, device="cuda")
 for _ in range(3):
     if mode == "conv1":
-        ops.conv3x3(x, wf, bias=bias, lrelu=True, mask_out=mo, out=out)
+        ops.conv3x3(x, wf, bias=bias, lrelu=True, mask_out=mo, out=out, flags=ops.CONV_ONE_TAP)
     else:
-        ops.conv3x3(x, wf, bias=bias, lrelu=True, residual=res, mask_out=mo, out=out)
+        ops.conv3x3(x, wf, bias=bias, lrelu=True, residual=res, mask_out=mo, out=out, flags=ops.CONV_ONE_TAP)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(10):
     if mode == "conv1":
-        ops.conv3x3(x, wf, bias=bias, lrelu=True, mask_out=mo, out=out)
+        ops.conv3x3(x, wf, bias=bias, lrelu=True, mask_out=mo, out=out, flags=ops.CONV_ONE_TAP)
     else:
-        ops.conv3x3(x, wf, bias=bias, lrelu=True, residual=res, mask_out=mo, out=out)
+        ops.conv3x3(x, wf, bias=bias, lrelu=True, residual=res, mask_out=mo, out=out, flags=ops.CONV_ONE_TAP)
 e1.record()
 torch.cuda.synchronize()
 print(mode, H, "avg us (back-to-back, warm L2)", e0.elapsed_time(e1) * 100)
