@@ -336,10 +336,15 @@ def main():
     # step count on the device so that it replays from the graph.  N > 1: the gradient all-reduce is ONE peer-memory
     # kernel inside the same graph (csrc/comm.cu); NCCL only if peer memory cannot be mapped on this box.
     opt = fd.optim.FlatAdam(eng, lr=LR, capturable=True)
-    peer_ar = None
-    if world > 1 and not args.nccl:
-        peer_ar = par.PeerAllReduce.create(eng.n_flat, dev)
-    collective = "none" if world == 1 else ("nvlink peer-memory kernel (in graph)" if peer_ar else "nccl all_reduce")
+    # N > 1: the gradient exchange is TWO peer-memory all-reduce kernels inside the step's graph (csrc/comm.cu,
+    # parallel.SplitAllReduce): the packed accumulators of the fused chain on a side stream, overlapped with the rest of
+    # the backward pass, and the remainder just before Adam; NCCL only if peer memory cannot be mapped on this box.
+    split = None
+    if world > 1:
+        split = par.SplitAllReduce.create(eng, eng.plan(B, True), dev, use_nccl=args.nccl)
+    peer_ar = split if (split is not None and split.peer) else None
+    collective = "none" if world == 1 else ("2 nvlink peer-memory all-reduce kernels in the graph (early one overlapped "
+                                            "with the backward pass)" if peer_ar else "nccl all_reduce")
     eager_ar = peer_ar if peer_ar is not None else (par.allreduce_grads if world > 1 else None)
 
     def eager_step():

@@ -176,6 +176,8 @@ FD_API int fd_comm_status(void* window, int* status);
 /* windows: HOST array of `world` device pointers (entry `rank` = the local window, the rest imported);
  * data: the local flat fp32 buffer of n elements, summed over ranks in place. */
 FD_API int fd_allreduce_sum_f32(void* const* windows, int rank, int world, float* data, long n, void* stream);
+/* the same on `blocks` (1..64) thread blocks -- an exchange overlapped with compute kernels uses few (every rank the same) */
+FD_API int fd_allreduce_sum_f32_blocks(void* const* windows, int rank, int world, float* data, long n, int blocks, void* stream);
 
 /* Elementwise halves of a residual block for backbones wider than the 64-channel tensor-core kernels (filters = 128
  * = two 64-channel planes per tensor, engine.PlanarEngine).  A 128 -> 128 convolution is evaluated as the sum of two

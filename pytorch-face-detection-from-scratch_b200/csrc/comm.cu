@@ -209,7 +209,16 @@ extern "C" int fd_comm_status(void* window, int* status) {
 }
 
 extern "C" int fd_allreduce_sum_f32(void* const* windows, int rank, int world, float* data, long n, void* stream) {
+  return fd_allreduce_sum_f32_blocks(windows, rank, world, data, n, kCommBlocks, stream);
+}
+
+// Same exchange on `blocks` (1..64) thread blocks.  An exchange that runs BESIDE compute kernels (the early half of
+// parallel.SplitAllReduce) uses few blocks: a block that waits for a late peer occupies its SM, and the persistent
+// convolution kernels need a whole SM per CTA.  Every rank must pass the same `blocks` for a given window.
+extern "C" int fd_allreduce_sum_f32_blocks(void* const* windows, int rank, int world, float* data, long n, int blocks,
+                                           void* stream) {
   if (!windows || !data || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || n <= 0) return FD_EINVAL;
+  if (blocks < 1 || blocks > kCommBlocks) return FD_EINVAL;
   if (n % 4 != 0) return FD_EUNSUPPORTED;
   if (world == 1) return FD_OK;
   Peers pp = {};
@@ -217,7 +226,7 @@ extern "C" int fd_allreduce_sum_f32(void* const* windows, int rank, int world, f
     if (!windows[i]) return FD_EINVAL;
     pp.win[i] = static_cast<unsigned char*>(windows[i]);
   }
-  launch_k(allreduce_sum_kernel, dim3(kCommBlocks), dim3(kCommThreads), 0, static_cast<cudaStream_t>(stream), pp, data,
+  launch_k(allreduce_sum_kernel, dim3(blocks), dim3(kCommThreads), 0, static_cast<cudaStream_t>(stream), pp, data,
            n / 4, chunk4_of(n, world), rank, world);
   count_launch();
   return launch_status();

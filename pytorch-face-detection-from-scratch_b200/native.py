@@ -39,6 +39,7 @@ SIGNATURES = {
     "fd_comm_import": [_P, _P],
     "fd_comm_release": [_P],
     "fd_allreduce_sum_f32": [_P, _I, _I, _P, _c.c_long, _P],
+    "fd_allreduce_sum_f32_blocks": [_P, _I, _I, _P, _c.c_long, _I, _P],
     "fd_dwconv3x3_lrelu": [_P, _P, _I, _I, _I, _I, _F, _P, _P],
     "fd_act_mask": [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "fd_grad_mask": [_P, _I, _I, _I, _F, _P, _P, _P, _P],

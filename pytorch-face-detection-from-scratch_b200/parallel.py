@@ -58,6 +58,7 @@ class PeerAllReduce:
 
     def __init__(self, numel: int, rank: int, world: int, windows, own):
         self.numel, self.rank, self.world, self._own = numel, rank, world, own
+        self.blocks = 64                             # thread blocks of the exchange kernel (SplitAllReduce: 16 for the overlapped half)
         self._windows = windows                      # python ints, entry `rank` is the local window
         self._array = (ctypes.c_void_p * world)(*windows)
 
@@ -104,8 +105,8 @@ class PeerAllReduce:
     def __call__(self, flat: torch.Tensor) -> torch.Tensor:
         from .native import check, cur_stream, dptr, lib
         assert flat.numel() == self.numel and flat.dtype == torch.float32
-        check(lib().fd_allreduce_sum_f32(self._array, self.rank, self.world, dptr(flat, torch.float32), self.numel,
-                                         cur_stream()), "fd_allreduce_sum_f32")
+        check(lib().fd_allreduce_sum_f32_blocks(self._array, self.rank, self.world, dptr(flat, torch.float32), self.numel,
+                                                int(self.blocks), cur_stream()), "fd_allreduce_sum_f32")
         return flat
 
     def status(self) -> int:
@@ -130,6 +131,53 @@ class PeerAllReduce:
                 L.fd_comm_release(ctypes.c_void_p(w))
         L.fd_comm_free(self._own)
         self._windows = []
+
+
+class SplitAllReduce:
+    """The data-parallel gradient sum of a BackboneEngine step as TWO exchanges over the engine's gradient allocation
+    (``engine.exchange_regions``): ``early`` -- the packed weight-gradient accumulators of the fused 15x15 chain, final
+    ~2/3 of the backward pass before its end, all-reduced on a side stream while the wide layers are still being
+    differentiated -- and ``late`` -- everything else, just before the accumulators are unpacked.  Each exchange is one
+    ``PeerAllReduce`` kernel with its own peer window (the two may be in flight at the same time); with
+    ``use_nccl=True`` / when peer memory cannot be mapped they are ``dist.all_reduce`` calls (not graph-capturable)."""
+
+    def __init__(self, early_ar, late_ar):
+        self._early, self._late = early_ar, late_ar
+        self.peer = isinstance(late_ar, PeerAllReduce)
+
+    @classmethod
+    def create(cls, engine, plan, device, use_nccl: bool = False) -> "SplitAllReduce | None":
+        if not (dist.is_initialized() and dist.get_world_size() > 1):
+            return None
+        early_t, late_t = engine.exchange_regions(plan)
+        if not use_nccl:
+            late = PeerAllReduce.create(late_t.numel(), device)
+            early = PeerAllReduce.create(early_t.numel(), device) if (late is not None and early_t.numel()) else None
+            if late is not None and (early is not None or early_t.numel() == 0):
+                if early is not None:
+                    early.blocks = 16            # runs beside the convolution kernels: leave them the other 132 SMs
+                return cls(early, late)
+            if late is not None:
+                late.close()
+        return cls(allreduce_grads, allreduce_grads)
+
+    def early(self, t: torch.Tensor):
+        if t.numel():
+            self._early(t)
+
+    def late(self, t: torch.Tensor):
+        self._late(t)
+
+    def status(self) -> int:
+        if not self.peer:
+            return 0
+        return self._late.status() or (self._early.status() if self._early is not None else 0)
+
+    def close(self):
+        if self.peer:
+            if self._early is not None:
+                self._early.close()
+            self._late.close()
 
 
 def max_over_ranks(value: float, device=None) -> float:

@@ -94,3 +94,81 @@ def test_peer_allreduce_two_ranks_exact_sum():
     if any(v == "unavailable" for v in res.values()):
         pytest.skip("CUDA IPC peer windows cannot be mapped on this box (the NCCL path is used instead)")
     assert res == {0: "ok", 1: "ok"}, res
+
+
+def _dp_worker(rank, world, port, ndev, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                          LOCAL_RANK=str(rank % ndev))
+        import torch.distributed as dist
+        fd = importlib.import_module(PKG)
+        par = fd.parallel
+        dev = torch.device("cuda", rank % ndev)
+        torch.cuda.set_device(dev)
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+        torch.manual_seed(3)
+        m = fd.models.PoolResnet.PoolResnet(filters=64, input_shape=(3, 480, 480), num_of_patches=10).to(dev).eval()
+        eng = m.engine
+        eng.bind(dict(m.named_parameters()))
+        B = 2
+        shards = []
+        for r in range(world):
+            g = torch.Generator().manual_seed(50 + r)
+            x = torch.rand(B, 3, 480, 480, generator=g).to(dev)
+            gt = (torch.rand(B, 5, 10, 10, generator=g) * (torch.rand(B, 1, 10, 10, generator=g) < 0.2)).to(dev)
+            gt[:, 0] = (gt[:, 0] > 0).float()
+            shards.append((x, gt))
+        local = []
+        for (x, gt) in shards:                               # every rank differentiates every shard WITHOUT an exchange
+            eng.train_step(x, gt, dropout=False)
+            local.append(eng.gflat.clone())
+        want = local[0]
+        for r in range(1, world):
+            want = want + local[r]
+        split = par.SplitAllReduce.create(eng, eng.plan(B, True), dev)
+        if split is None or not split.peer:
+            q.put((rank, "unavailable"))
+            return
+        early_t, late_t = eng.exchange_regions(eng.plan(B, True))
+        layout_ok = early_t.numel() == 16 * 9 * 64 * 64 and late_t.numel() + early_t.numel() + eng.offsets["w3"][1] == eng.gzero.numel()
+        x, gt = shards[rank]
+        eng.train_step(x, gt, dropout=False, allreduce=split)                # eager, overlapped exchange
+        torch.cuda.synchronize()
+        e1 = ((eng.gflat - want).norm() / want.norm()).item()
+        graph, pl, _ = eng.capture_train_step(x, gt, dropout=False, allreduce=split)
+        eng.gzero.fill_(7.0)
+        graph.replay()
+        graph.replay()
+        torch.cuda.synchronize()
+        e2 = ((eng.gflat - want).norm() / want.norm()).item()
+        ok = layout_ok and e1 <= 1e-5 and e2 <= 1e-5 and split.status() == 0
+        split.close()
+        dist.destroy_process_group()
+        q.put((rank, "ok" if ok else f"mismatch layout={layout_ok} eager={e1:.3g} graph={e2:.3g}"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, f"error: {e!r} {traceback.format_exc()[-600:]}"))
+
+
+def test_data_parallel_step_with_overlapped_split_allreduce():
+    """Two ranks, one shard each: the train step with parallel.SplitAllReduce (the chain's packed weight-gradient
+    accumulators exchanged on a side stream while the backward pass continues, the rest just before the unpack) leaves
+    the SUM of the shard gradients in the flat gradient buffer of both ranks -- eager and replayed from one CUDA graph."""
+    require_cuda()
+    world, ndev = 2, torch.cuda.device_count()
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, ndev, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        res = dict(q.get(timeout=300) for _ in range(world))
+    finally:
+        for p in procs:
+            p.join(30)
+            if p.is_alive():
+                p.kill()
+    if any(v == "unavailable" for v in res.values()):
+        pytest.skip("CUDA IPC peer windows cannot be mapped on this box (the NCCL path is used instead)")
+    assert res == {0: "ok", 1: "ok"}, res
