@@ -77,6 +77,14 @@ FD_API int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, i
                const uint32_t* mask_in, const float* chan_scale2, fd_bf16* out2,
                int flags, void* stream);
 
+/* The same convolution with the block's MaxPool2d(2) fused into the epilogue (models/PoolResnet.py:37-42: conv2 ->
+ * LeakyReLU -> Dropout2d -> + skip -> pool): the un-pooled sum never reaches HBM.  pooled: [B,H/2,W/2,C] bf16;
+ * argmax (nullable): uint16 [B,H/2,W/2,C/8], the window positions of fd_maxpool2x2_fwd (bit-identical to fd_conv3x3
+ * followed by fd_maxpool2x2_fwd).  H and W must be even (odd maps: the two separate calls). */
+FD_API int fd_conv3x3_pool(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, int W, int C, const float* bias,
+                    float slope, const float* chan_scale, const fd_bf16* residual, uint32_t* mask_out,
+                    fd_bf16* pooled, uint16_t* argmax, int flags, void* stream);
+
 /* Weight gradient of the same convolution (replaces the wgrad half of autograd's
  * conv2d backward for models/PoolResnet.py:35,37).
  *   dw_packed[t][ci][co] += sum_{n,y,x} g[n,y,x,co] * xpad[n,y+ky-1,x+kx-1,ci],  t = ky*3+kx

@@ -54,6 +54,8 @@ struct ConvParams {
   int dbg;
   int has_res;            // a residual tile is TMA-loaded into the staging buffer
   int staged_out2;        // the staged (TMA-stored) value is the masked second output, not `out`
+  int pool;               // fuse MaxPool2d(2): the staged tile is max-pooled in place, the POOLED tile is stored
+  uint16_t* amax;         // pooled mode: 2-bit window positions of the maxima [B,H/2,W/2,8] uint16 (nullable)
   float slope;
   const float* bias;
   const float* chan_scale;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
                   const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_out,
                   const __grid_constant__ ConvParams p) {
+  // tm_out: the tensor the staged tile is stored to -- in pooled mode the POOLED output [B,H/2,W/2,64], box {64,TW/2,R/2,1}
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -199,7 +202,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         const int th = rem / p.tiles_w;
         const int h0 = th * p.R, w0 = (rem - th * p.tiles_w) * p.TW;
         mbar_wait_sleep(stg_ready + s, ph);
-        tma_store_4d(&tm_out, sStg + s * p.stg_buf_bytes, 0, w0, h0, n);   // beyond the image: clipped
+        if (p.pool) tma_store_4d(&tm_out, sStg + s * p.stg_buf_bytes, 0, w0 >> 1, h0 >> 1, n);
+        else tma_store_4d(&tm_out, sStg + s * p.stg_buf_bytes, 0, w0, h0, n);   // beyond the image: clipped
         tma_store_commit();
         tma_store_wait_read<0>();
         mbar_arrive(stg_free + s);
@@ -288,12 +292,64 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         }
       }
       if (et == 0) FD_TS(5);
+      if (p.pool) {
+        // MaxPool2d(2) of the staged tile (models/PoolResnet.py:41-42), in place: every warp max-pools its share of the
+        // (R/2) x (TW/2) pooled pixels into registers (lane = channel pair), and only after a barrier -- all reads done --
+        // writes them over rows [0, npool) of the same buffer.  The un-pooled sum never reaches HBM; the positions of the
+        // maxima (first maximum in (dy,dx) order, like ATen) go out as 2 bits per channel for the backward pass.
+        tc_fence_before();
+        bar_sync_epi();                       // the un-pooled tile is complete, every TMEM read of this tile is done
+        if (et == 0) mbar_arrive(acc_empty + s);
+        const int PW = p.TW >> 1, npool = (p.R >> 1) * PW;
+        const int wk = warp - 2;
+        const uint32_t chunk = static_cast<uint32_t>(lane) >> 2, inb = (static_cast<uint32_t>(lane) & 3u) * 4u;
+        uint32_t pooled[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = wk + j * kEpiWarps;
+          pooled[j] = 0;
+          if (i < npool) {
+            const int py = i / PW, px = i - py * PW;
+            const uint32_t d00 = static_cast<uint32_t>((2 * py) * p.TW + 2 * px);
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t dr = d00 + static_cast<uint32_t>((k >> 1) * p.TW + (k & 1));
+              v[k] = *reinterpret_cast<const uint32_t*>(stg + dr * 128u + (((chunk ^ (dr & 7u)) << 4) | inb));
+            }
+            float lo = bf16lo(v[0]), hi = bf16hi(v[0]);
+            uint32_t alo = 0, ahi = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+              const float l2 = bf16lo(v[k]), h2 = bf16hi(v[k]);
+              if (l2 > lo) { lo = l2; alo = k; }
+              if (h2 > hi) { hi = h2; ahi = k; }
+            }
+            pooled[j] = pack_bf16x2(lo, hi);
+            if (p.amax) {
+              uint32_t a = (alo | (ahi << 2)) << (4u * (static_cast<uint32_t>(lane) & 3u));   // channels 2*(lane&3), +1 of the group
+              a |= __shfl_xor_sync(0xffffffffu, a, 1);
+              a |= __shfl_xor_sync(0xffffffffu, a, 2);
+              const int oy = (h0 >> 1) + py, ox = (w0 >> 1) + px;
+              if ((lane & 3) == 0 && oy < (p.H >> 1) && ox < (p.W >> 1))
+                p.amax[((static_cast<size_t>(n) * (p.H >> 1) + oy) * (p.W >> 1) + ox) * 8 + chunk] = static_cast<uint16_t>(a);
+            }
+          }
+        }
+        bar_sync_epi();                       // every read of the un-pooled tile is done: overwrite it
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t i = static_cast<uint32_t>(wk + j * kEpiWarps);
+          if (static_cast<int>(i) < npool)
+            *reinterpret_cast<uint32_t*>(stg + i * 128u + (((chunk ^ (i & 7u)) << 4) | inb)) = pooled[j];
+        }
+      }
       fence_proxy_async();       // staging writes (generic proxy) -> visible to the TMA store
       tc_fence_before();
       bar_sync_epi();
       if (et == 0) {
         FD_TS(6);
-        mbar_arrive(acc_empty + s);     // TMEM of this tile has been read by everyone
+        if (!p.pool) mbar_arrive(acc_empty + s);     // TMEM of this tile has been read by everyone
         mbar_arrive(stg_ready + s);     // staging tile complete: the store warp takes over
       }
     }
@@ -325,14 +381,37 @@ extern "C" FD_API int fd_debug_conv_timing(unsigned long long* out, int n) {
   return static_cast<int>(cudaMemcpyFromSymbol(out, fd::g_conv_dbg, sizeof(unsigned long long) * n));
 }
 
+static int conv3x3_impl(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, int W, int C, const float* bias,
+                        float slope, const float* chan_scale, const fd_bf16* residual, uint32_t* mask_out,
+                        fd_bf16* out, const uint32_t* mask_in, const float* chan_scale2, fd_bf16* out2,
+                        int flags, fd_bf16* pooled, uint16_t* argmax, void* stream);
+
 extern "C" int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, int W, int C, const float* bias,
                           float slope, const float* chan_scale, const fd_bf16* residual, uint32_t* mask_out,
                           fd_bf16* out, const uint32_t* mask_in, const float* chan_scale2, fd_bf16* out2,
                           int flags, void* stream) {
+  return conv3x3_impl(x, w_packed, B, H, W, C, bias, slope, chan_scale, residual, mask_out, out, mask_in, chan_scale2, out2,
+                      flags, nullptr, nullptr, stream);
+}
+
+extern "C" int fd_conv3x3_pool(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, int W, int C, const float* bias,
+                               float slope, const float* chan_scale, const fd_bf16* residual, uint32_t* mask_out,
+                               fd_bf16* pooled, uint16_t* argmax, int flags, void* stream) {
+  if (!pooled) return FD_EINVAL;
+  if ((H | W) & 1) return FD_EUNSUPPORTED;       // floor-mode pooling of odd maps: fd_conv3x3 + fd_maxpool2x2_fwd
+  return conv3x3_impl(x, w_packed, B, H, W, C, bias, slope, chan_scale, residual, mask_out, nullptr, nullptr, nullptr,
+                      nullptr, flags, pooled, argmax, stream);
+}
+
+static int conv3x3_impl(const fd_bf16* x, const fd_bf16* w_packed, int B, int H, int W, int C, const float* bias,
+                        float slope, const float* chan_scale, const fd_bf16* residual, uint32_t* mask_out,
+                        fd_bf16* out, const uint32_t* mask_in, const float* chan_scale2, fd_bf16* out2,
+                        int flags, fd_bf16* pooled, uint16_t* argmax, void* stream) {
   using namespace fd;
   if (!x || !w_packed || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
   if (C != kC) return FD_EUNSUPPORTED;
-  if (!out && !out2) return FD_EINVAL;
+  if (!out && !out2 && !pooled) return FD_EINVAL;
+  const bool pool = pooled != nullptr;
   if (mask_in && !out2) return FD_EINVAL;
   if (!(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;   // LeakyReLU is evaluated as max(v, slope*v)
   const int nsm = sm_count();
@@ -345,9 +424,11 @@ extern "C" int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int 
   double best = 1e30;
   const int min_tw_tiles = (W + 61) / 62;
   for (int tw_tiles = min_tw_tiles; tw_tiles <= min_tw_tiles + 1; ++tw_tiles) {
-    const int TW = (W + tw_tiles - 1) / tw_tiles;
+    int TW = (W + tw_tiles - 1) / tw_tiles;
+    if (pool) TW = (TW + 1) & ~1;                  // pooled tiles start on even rows / columns
+    if (TW > 62) continue;
     const int Wp = TW + 2;
-    for (int R = 1; R <= H && R + 2 <= 256; ++R) {
+    for (int R = pool ? 2 : 1; R <= (pool ? H + 1 : H) && R + 2 <= 256; R += pool ? 2 : 1) {
       const int nblk = (R * Wp + 127) / 128;
       if (nblk > 4) break;
       if (smem_for(nblk, Wp, R, TW) > smem_cap) break;
@@ -376,8 +457,10 @@ extern "C" int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int 
   p.bias = bias; p.chan_scale = chan_scale; p.chan_scale2 = chan_scale2;
   p.mask_in = reinterpret_cast<const uint16_t*>(mask_in); p.mask_out = reinterpret_cast<uint16_t*>(mask_out);
   p.has_res = residual != nullptr;
-  p.staged_out2 = (out == nullptr);
+  p.staged_out2 = (out == nullptr) && !pool;
   p.out2_direct = (out && out2) ? reinterpret_cast<__nv_bfloat16*>(out2) : nullptr;
+  p.pool = pool ? 1 : 0;
+  p.amax = argmax;
   const size_t smem = smem_for(p.nblk, p.Wp, bestR, bestTW);
 
   CUtensorMap tm_in, tm_w, tm_res, tm_out;
@@ -386,9 +469,10 @@ extern "C" int fd_conv3x3(const fd_bf16* x, const fd_bf16* w_packed, int B, int 
   rc = make_tmap_2d_bf16(&tm_w, w_packed, 9 * kC, kC, kC, kC);
   if (rc != FD_OK) return rc;
   const fd_bf16* staged = out ? out : out2;
-  rc = make_tmap_nhwc_bf16(&tm_out, staged, B, H, W, C, bestTW, bestR);
+  rc = pool ? make_tmap_nhwc_bf16(&tm_out, pooled, B, H / 2, W / 2, C, bestTW / 2, bestR / 2)
+            : make_tmap_nhwc_bf16(&tm_out, staged, B, H, W, C, bestTW, bestR);
   if (rc != FD_OK) return rc;
-  rc = make_tmap_nhwc_bf16(&tm_res, residual ? residual : staged, B, H, W, C, bestTW, bestR);
+  rc = make_tmap_nhwc_bf16(&tm_res, residual ? residual : x, B, H, W, C, bestTW, bestR);
   if (rc != FD_OK) return rc;
 
   cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

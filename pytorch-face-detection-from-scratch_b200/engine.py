@@ -162,6 +162,10 @@ class BackboneEngine:
             off += (n + 3) // 4 * 4          # keep every section 16-byte aligned
         self.n_flat = off
         self.use_chain = True        # fuse runs of equal-shape blocks into one kernel when the image fits in smem
+        # MaxPool2d(2) of a pooled block in the conv2 epilogue (fd_conv3x3_pool, bit-identical).  Measured on B200: the step
+        # is 9 us SLOWER with it (502.8 vs 493.6 us) -- the extra barriers sit on the epilogue, which paces the MMA-bound
+        # kernel, while the separate pool kernels are HBM-bound and cost 10 us -- so it is off by default.
+        self.fuse_pool = False
         self.conv_flags = 0          # ops.CONV_ONE_TAP: per-layer launches bit-identical to the chain kernels (tests)
         self.device = None
         self.pflat = self.gflat = self.dwp = self.w_fwd = self.w_dgrad = None
@@ -285,10 +289,16 @@ class BackboneEngine:
             cs = pl.drop[k] if pl.drop is not None else None
             ops.conv3x3(cur, self._wf(2 * k), bias=sb3[2 * k], slope=self.slope, lrelu=True, mask_out=blk.ma,
                         out=blk.a, flags=self.conv_flags)
-            ops.conv3x3(blk.a, self._wf(2 * k + 1), bias=sb3[2 * k + 1], slope=self.slope, lrelu=True,
-                        chan_scale=cs, residual=cur, mask_out=blk.mb, out=blk.s, flags=self.conv_flags)
-            if blk.pool:
-                ops.maxpool2x2_fwd(blk.s, blk.out, blk.amax)
+            if blk.pool and self.fuse_pool and blk.H % 2 == 0 and blk.W % 2 == 0:
+                # MaxPool2d fused into the conv2 epilogue: the un-pooled sum blk.s is never written (the backward pass
+                # un-pools from the recorded window positions)
+                ops.conv3x3_pool(blk.a, self._wf(2 * k + 1), blk.out, bias=sb3[2 * k + 1], slope=self.slope,
+                                 chan_scale=cs, residual=cur, mask_out=blk.mb, argmax=blk.amax)
+            else:
+                ops.conv3x3(blk.a, self._wf(2 * k + 1), bias=sb3[2 * k + 1], slope=self.slope, lrelu=True,
+                            chan_scale=cs, residual=cur, mask_out=blk.mb, out=blk.s, flags=self.conv_flags)
+                if blk.pool:
+                    ops.maxpool2x2_fwd(blk.s, blk.out, blk.amax)
             cur = blk.out
         cs = pl.drop[self.num_blocks] if pl.drop is not None else None
         ops.head_fwd(cur, cs, self.section(self.pflat, "out.weight"), self.section(self.pflat, "out.bias"), pl.y,

@@ -26,6 +26,17 @@ def conv3x3(x, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_scale=None, 
           "fd_conv3x3")
 
 
+def conv3x3_pool(x, w_packed, pooled, *, bias=None, slope=0.2, lrelu=True, chan_scale=None, residual=None, mask_out=None,
+                 argmax=None, flags=0):
+    """conv3x3 (+ bias, LeakyReLU, Dropout2d multiplier, sign-bit mask, skip add) with the MaxPool2d(2) that follows
+    fused: pooled [B,H/2,W/2,C]; argmax int16 [B,H/2,W/2,C/8] (2-bit window positions) or None.  Even H, W only."""
+    B, H, W, C = x.shape
+    fl = flags | (EPI_LRELU if lrelu else 0)
+    check(lib().fd_conv3x3_pool(dptr(x, BF16), dptr(w_packed, BF16), B, H, W, C, dptr(bias, F32), slope,
+                                dptr(chan_scale, F32), dptr(residual, BF16), dptr(mask_out, I32), dptr(pooled, BF16),
+                                dptr(argmax, torch.int16), fl, cur_stream()), "fd_conv3x3_pool")
+
+
 def conv3x3_wgrad(x, g, dw_packed, dbias, flags=0):
     B, H, W, C = x.shape
     check(lib().fd_conv3x3_wgrad(dptr(x, BF16), dptr(g, BF16), B, H, W, C, dptr(dw_packed, F32), dptr(dbias, F32),

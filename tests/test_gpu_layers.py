@@ -72,6 +72,36 @@ def test_conv3x3_forward_epilogues(B, H, W):
     _close(out2, G2, "masked out2", rel=6e-3)
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 60, 60), (2, 30, 30), (5, 16, 8), (1, 240, 240), (2, 120, 120), (70, 30, 30), (1, 64, 126)])
+def test_conv3x3_fused_pool_equals_conv_then_pool(B, H, W):
+    """fd_conv3x3_pool (MaxPool2d(2) in the conv2 epilogue, models/PoolResnet.py:37-42) == fd_conv3x3 followed by
+    fd_maxpool2x2_fwd, bit for bit: pooled activations, window positions and the sign-bit mask of the un-pooled value."""
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(B * 31 + W)
+    dev = "cuda"
+    x = torch.randn(B, H, W, C, device=dev).bfloat16()
+    res = torch.randn(B, H, W, C, device=dev).bfloat16()
+    w = torch.randn(C, C, 3, 3, device=dev) * 0.05
+    bias = torch.randn(C, device=dev)
+    cs = (torch.rand(B, C, device=dev) < 0.75).float() / 0.75
+    wf = torch.empty(9, C, C, dtype=torch.bfloat16, device=dev)
+    ops.pack_conv3x3(w, wf, None)
+    s_ = torch.zeros_like(x); m1 = torch.zeros(B, H, W, C // 32, dtype=torch.int32, device=dev)
+    ops.conv3x3(x, wf, bias=bias, lrelu=True, chan_scale=cs, residual=res, mask_out=m1, out=s_)
+    y1 = torch.zeros(B, H // 2, W // 2, C, dtype=torch.bfloat16, device=dev)
+    a1 = torch.zeros(B, H // 2, W // 2, C // 8, dtype=torch.int16, device=dev)
+    ops.maxpool2x2_fwd(s_, y1, a1)
+    y2 = torch.full_like(y1, 3.0); a2 = torch.full_like(a1, -1); m2 = torch.zeros_like(m1)
+    ops.conv3x3_pool(x, wf, y2, bias=bias, chan_scale=cs, residual=res, mask_out=m2, argmax=a2)
+    assert torch.equal(y1, y2) and torch.equal(a1, a2) and torch.equal(m1, m2)
+    y3 = torch.full_like(y1, 3.0)
+    ops.conv3x3_pool(x, wf, y3, bias=bias, chan_scale=cs, residual=res)          # inference: no mask, no positions
+    assert torch.equal(y1, y3)
+    ref = F.max_pool2d(s_.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(y2.float(), ref)
+
+
 @pytest.mark.parametrize("B,H,W", [(2, 15, 15), (3, 30, 30), (2, 60, 60), (1, 7, 9), (64, 15, 15), (2, 120, 120),
                                    (1, 64, 125), (1, 240, 240)])
 def test_conv3x3_wgrad(B, H, W):
