@@ -387,6 +387,16 @@ FD_API int fd_ssd_head_bwd(const fd_bf16* const* x_planes, fd_bf16* const* dx_pl
                     int C, const float* mult, int prior_off, int P, const float* out, const float* dout, float* dw,
                     float* db, void* stream);
 
+
+/* Backward pieces of the depthwise-separable block (models/SeparableCNN.py:40-51) on 64-channel planes:
+ *   fd_lrelu_bwd: out = g * (ref >= +0 ? 1 : slope), the LeakyReLU' factor taken from the sign of the saved activation
+ *                 (n bf16 elements, n % 8 == 0);
+ *   fd_dwconv3x3_wgrad: dw[c][ky][kx] += sum g[n,y,x,c] * x[n,y+ky-1,x+kx-1,c]  (dw: [64][1][3][3] fp32, accumulated).
+ * The depthwise input gradient is fd_dwconv with the taps flipped; the pointwise gradients are fd_conv3x3 (FD_CONV_1X1,
+ * dgrad packing) and the centre tap of fd_conv3x3_wgrad. */
+FD_API int fd_lrelu_bwd(const fd_bf16* g, const fd_bf16* ref, long n, float slope, fd_bf16* out, void* stream);
+FD_API int fd_dwconv3x3_wgrad(const fd_bf16* x, const fd_bf16* g, int B, int H, int W, int C, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,16 +144,20 @@ def adam_update(p: Params, grads: Params, state: dict, lr: float = 1e-4, betas=(
 
 
 def separable_block(x: torch.Tensor, w_pw1: torch.Tensor, w_dw: torch.Tensor, w_pw2: torch.Tensor, pool: bool,
-                    slope: float = 0.2) -> torch.Tensor:
+                    slope: float = 0.2, drop_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """models/SeparableCNN.py:40-51 (eval: Dropout2d is the identity): 1x1 -> lrelu -> depthwise 3x3 pad 1 -> lrelu ->
     1x1 -> + skip -> MaxPool2d(2) while H > num_of_patches.  All three convolutions have bias=False (:11,19,27,35)."""
     y = F.leaky_relu(F.conv2d(x, w_pw1), slope)
     y = F.leaky_relu(F.conv2d(y, w_dw, padding=1, groups=w_dw.shape[0]), slope)
-    y = F.conv2d(y, w_pw2) + x
+    y = F.conv2d(y, w_pw2)
+    if drop_scale is not None:                     # Dropout2d on the pw2 output, before the skip add (:47-48)
+        y = y * drop_scale
+    y = y + x
     return F.max_pool2d(y, 2) if pool else y
 
 
-def separable_forward(x: torch.Tensor, p: Params, num_blocks: int = 10, block_patches: int = 16) -> torch.Tensor:
+def separable_forward(x: torch.Tensor, p: Params, num_of_patches: int = 16, num_blocks: int = 10, block_patches: int = 16,
+                      drop_scales: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
     """models/SeparableCNN.py:104-117 (eval, predict == 0): 10x10 stride-8 pad-2 stem, blocks that pool while
     H > 16 (the constructor hard-wires num_of_patches=16, :71,87-91), 6x6 valid head, sigmoid."""
     k = p["conv1.weight"].shape[2]
@@ -161,7 +165,10 @@ def separable_forward(x: torch.Tensor, p: Params, num_blocks: int = 10, block_pa
     for b in range(num_blocks):
         pre = f"residual_blocks.{b}."
         y = separable_block(y, p[pre + "pointwise_conv1.weight"], p[pre + "depthwise_conv.weight"],
-                            p[pre + "pointwise_conv2.weight"], pool=y.shape[2] > block_patches)
+                            p[pre + "pointwise_conv2.weight"], pool=y.shape[2] > block_patches,
+                            drop_scale=None if drop_scales is None else drop_scales[b])
+    if drop_scales is not None and drop_scales[num_blocks] is not None:
+        y = y * drop_scales[num_blocks]                                     # Dropout2d(0.5) before the head (:109)
     y = F.conv2d(y, p["out.weight"], p["out.bias"])
     return torch.sigmoid(y)
 

@@ -292,6 +292,28 @@ class SeparablePlanarEngine:
         return pl["y"]
 
 
+class _SeparableFn(torch.autograd.Function):
+    """Autograd bridge: forward / backward of the whole separable backbone as one node (engine_separable)."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        eng = model.train_engine
+        with torch.cuda.device(x.device):
+            pl = eng.forward(x, dropout=model.training)
+        ctx.eng, ctx.pl, ctx.generation = eng, pl, pl["generation"]
+        return pl["y"].clone()
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng, pl = ctx.eng, ctx.pl
+        if pl["generation"] != ctx.generation:
+            raise RuntimeError("fd_b200 SeparableCNN: backward() after ANOTHER forward of the same batch size overwrote the "
+                               "saved activations; call backward() before the next forward")
+        with torch.cuda.device(dy.device):
+            eng.run_backward(pl, dy.contiguous().float())
+        return (None, None, *[eng.grad_view(n).clone() for n in eng.param_names()])
+
+
 class SeparableCNN(BaseModel):
     def __init__(self, filters, input_shape, num_of_residual_blocks=10, probability_threshold=0.5, iou_threshold=0.5,
                  pretrained=False, input_kernel_size=10, input_stride=8, output_kernel_size=6, output_padding=0):
@@ -307,17 +329,16 @@ class SeparableCNN(BaseModel):
                              padding=output_padding)
         self.sigmoid = nn.Sigmoid()
         Engine = SeparableEngine if filters == 64 else SeparablePlanarEngine       # fused kernel / channel planes
-        self.engine = Engine(filters, input_shape[0], input_shape[1], input_shape[2], num_of_residual_blocks,
-                             input_kernel_size, input_stride, input_kernel_size - input_stride,
-                             output_kernel_size, output_padding, block_patches=self.num_of_patches)
+        eargs = (filters, input_shape[0], input_shape[1], input_shape[2], num_of_residual_blocks, input_kernel_size,
+                 input_stride, input_kernel_size - input_stride, output_kernel_size, output_padding)
+        self.engine = Engine(*eargs, block_patches=self.num_of_patches)                       # inference
+        from ..engine_separable import SeparableTrainEngine
+        self.train_engine = SeparableTrainEngine(*eargs, block_patches=self.num_of_patches)   # forward with saved state + backward
 
     def forward(self, x: torch.Tensor, predict: torch.Tensor = torch.tensor(0)):
         is_predict = bool(predict == 1)
-        if self.training:
-            raise NotImplementedError("SeparableCNN: only the inference path (eval mode) is built on the B200 kernels; "
-                                      "call model.eval()")
         if is_predict:                                     # SeparableCNN.py:105-108
-            x = self._resize(x)
+            x = self._resize(self._to_model_device(x))
             if x.dtype != torch.uint8:
                 x = x / 255.0
             if len(x.shape) == 3:
@@ -326,9 +347,36 @@ class SeparableCNN(BaseModel):
             raise RuntimeError("fd_b200 models run on CUDA tensors only (no CPU fallback)")
         if x.dtype not in (torch.float32, torch.uint8):
             x = x.float()
-        self.engine.bind(dict(self.named_parameters()))
-        with torch.no_grad():
-            y = self.engine.forward(x.contiguous()).clone()
+        x = x.contiguous()
+        params = dict(self.named_parameters())
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params.values())
+        if needs_grad or self.training:
+            # training path (Dropout2d active in train mode, activations saved): layer-by-layer engine
+            self.train_engine.bind(params)
+            if needs_grad:
+                y = _SeparableFn.apply(self, x, *[params[n] for n in self.train_engine.param_names()])
+            else:
+                with torch.cuda.device(x.device):
+                    y = self.train_engine.forward(x, dropout=True)["y"].clone()
+        else:
+            self.engine.bind(params)
+            with torch.no_grad():
+                y = self.engine.forward(x).clone()
         if is_predict:
             return self.single_non_max_suppression(y[0])   # SeparableCNN.py:114-115
         return y
+
+    def train_step(self, x: torch.Tensor, gt: torch.Tensor, optimizer=None, allreduce=None):
+        """forward + summed YoloLoss + backward in one call sequence (models/ModelMeta.py:141,173-176); returns the summed
+        loss, gradients land in ``p.grad`` (views of ``self.train_engine.gflat``)."""
+        params = dict(self.named_parameters())
+        self.train_engine.bind(params)
+        if not x.is_cuda:
+            raise RuntimeError("fd_b200 models run on CUDA tensors only (no CPU fallback)")
+        if x.dtype not in (torch.float32, torch.uint8):
+            x = x.float()
+        pl = self.train_engine.train_step(x.contiguous(), gt.float().contiguous(), dropout=self.training,
+                                          allreduce=allreduce, optimizer=optimizer)
+        for n, p in params.items():
+            p.grad = self.train_engine.grad_view(n)
+        return pl["loss"].sum()

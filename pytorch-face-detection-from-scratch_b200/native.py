@@ -75,6 +75,8 @@ SIGNATURES = {
     "fd_head3x3_fwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "fd_resize_bilinear": [_P, _I, _c.c_long, _I, _I, _I, _I, _P, _P],
     "fd_index_copy_f32": [_P, _P, _P, _c.c_long, _I, _P],
+    "fd_lrelu_bwd": [_P, _P, _c.c_long, _F, _P, _P],
+    "fd_dwconv3x3_wgrad": [_P, _P, _I, _I, _I, _I, _P, _P],
     "fd_ssd_head_fwd": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P],
     "fd_ssd_head_bwd": [_P, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P],
 }

@@ -351,3 +351,16 @@ def ssd_head_bwd(x_planes, dx_planes, w, mult, prior_off, out, dout, dw, db):
     check(lib().fd_ssd_head_bwd(_ptr_array(x_planes, BF16), _ptr_array(dx_planes, BF16), len(x_planes), dptr(w, F32), B,
                                 H * W, C, dptr(mult, F32), int(prior_off), out.shape[1], dptr(out, F32), dptr(dout, F32),
                                 dptr(dw, F32), dptr(db, F32), cur_stream()), "fd_ssd_head_bwd")
+
+
+def lrelu_bwd(g, ref, slope, out):
+    """out = g * (ref >= +0 ? 1 : slope)  (bf16, same shape)."""
+    check(lib().fd_lrelu_bwd(dptr(g, BF16), dptr(ref, BF16), g.numel(), float(slope), dptr(out, BF16), cur_stream()),
+          "fd_lrelu_bwd")
+
+
+def dwconv3x3_wgrad(x, g, dw):
+    """dw [64,1,3,3] fp32 += depthwise 3x3 weight gradient of one 64-channel plane (x, g: [B,H,W,64] bf16)."""
+    B, H, W, C = x.shape
+    check(lib().fd_dwconv3x3_wgrad(dptr(x, BF16), dptr(g, BF16), B, H, W, C, dptr(dw, F32), cur_stream()),
+          "fd_dwconv3x3_wgrad")
