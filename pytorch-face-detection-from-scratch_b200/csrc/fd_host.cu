@@ -99,13 +99,13 @@ int make_tmap_xbf(CUtensorMap* m, const void* ptr, int planes, int Hin, int K) {
 }
 
 int make_tmap_3d(CUtensorMap* m, const void* ptr, int elem_bytes, int is_u8, int d0, int d1, int d2, int box0,
-                 int box1) {
+                 int box1, int box2) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return FD_EDRIVER;
-  if (box0 > 256 || box1 > 256 || (box0 * elem_bytes) % 16 != 0) return FD_EUNSUPPORTED;
+  if (box0 > 256 || box1 > 256 || box2 < 1 || box2 > 256 || (box0 * elem_bytes) % 16 != 0) return FD_EUNSUPPORTED;
   cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
   cuuint64_t strides[2] = {(cuuint64_t)d0 * elem_bytes, (cuuint64_t)d0 * d1 * elem_bytes};
-  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, (cuuint32_t)box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, is_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

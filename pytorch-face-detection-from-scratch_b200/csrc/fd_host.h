@@ -52,7 +52,8 @@ int make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, int rows, int cols, int b
 int make_tmap_2d_f32(CUtensorMap* m, const void* ptr, long rows, int cols, int boxRows, int boxCols);
 
 // [d2, d1, d0] tensor of 1- or 4-byte elements (uint8 / fp32) as a 3-D tiled map, box {box0, box1, 1}, no swizzle
-int make_tmap_3d(CUtensorMap* m, const void* ptr, int elem_bytes, int is_u8, int d0, int d1, int d2, int box0, int box1);
+int make_tmap_3d(CUtensorMap* m, const void* ptr, int elem_bytes, int is_u8, int d0, int d1, int d2, int box0, int box1,
+                 int box2 = 1);
 
 // the stem's bf16 image copy [planes][Hin][2][512] as a 5-D map, box = K rows of one plane (both image slots)
 int make_tmap_xbf(CUtensorMap* m, const void* ptr, int planes, int Hin, int K);
@@ -72,6 +73,10 @@ int stem_s2_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias
                    int K, int stride, int pad, fd_bf16* y, cudaStream_t st);
 int stem_s2_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C, int K,
                      int stride, int pad, float* dw, float* dbias, cudaStream_t st);
+
+// tcgen05 stem of the MobilenetV3 backbone (3x3, stride 2, 3 -> 16, Hardswish; mbv3_stem_tc.cu); FD_EUNSUPPORTED = other shape
+int mbv3_stem_tc(const void* x, int x_is_u8, const float* w, const float* bias, int B, int H, int W, int pad_t, int pad_l,
+                 int Ho, int Wo, fd_bf16* out, cudaStream_t st);
 
 // tcgen05 backward of the 64 -> 5 head (head_tc.cu); FD_EUNSUPPORTED = shape not instantiated
 int head_bwd_tc(const fd_bf16* x, const float* chan_scale, const float* w, const float* y, const float* dy, int B, int H,

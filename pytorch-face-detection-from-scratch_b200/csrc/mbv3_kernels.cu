@@ -10,6 +10,8 @@
 //   mbv3_se_kernel     SqueezeExcite gate: mean -> 1x1 reduce + ReLU -> 1x1 expand -> Hardsigmoid
 //   mbv3_scale_kernel  x *= gate[n, c]
 //   mbv3_head_kernel   3x3 pad 1 conv C -> 5 + sigmoid (C = 576 does not fit the shared-memory head of layers.cu)
+#include <cstdlib>
+
 #include "fd_host.h"
 #include "fd_ptx.cuh"
 
@@ -359,6 +361,15 @@ using namespace fd;
 extern "C" int fd_mbv3_stem(const void* x, int x_is_u8, const float* w, const float* bias, int B, int H, int W, int pad_t,
                             int pad_l, int Ho, int Wo, fd_bf16* out, void* stream) {
   if (!x || !w || !bias || !out || B <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return FD_EINVAL;
+  {
+    // tensor-core path (im2col patch tile in shared memory, mbv3_stem_tc.cu); the CUDA-core kernel below serves image
+    // widths whose row pitch TMA cannot address (FD_MBV3_STEM_SIMT=1 forces it, for A/B runs)
+    static const bool simt = getenv("FD_MBV3_STEM_SIMT") != nullptr;
+    if (!simt) {
+      const int rc = mbv3_stem_tc(x, x_is_u8, w, bias, B, H, W, pad_t, pad_l, Ho, Wo, out, static_cast<cudaStream_t>(stream));
+      if (rc != FD_EUNSUPPORTED) return rc;
+    }
+  }
   const long total = static_cast<long>(B) * Ho * Wo;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (x_is_u8)

@@ -401,3 +401,29 @@ def test_torchscript_archive_runs_demo_extract_face(tmp_path):
         n_boxes += b_ts.shape[0]
         assert b_ts.shape[0] == int(g["counts"][i])
     assert n_boxes > 0
+
+
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("B,H,W", [(2, 480, 480), (3, 96, 132), (1, 50, 76), (5, 480, 640)])
+def test_mbv3_stem_tensor_core_vs_torch(u8, B, H, W):
+    """fd_mbv3_stem (Conv2dSame 3x3 stride 2, 3 -> 16, + bias + Hardswish; im2col patch tile + tcgen05, TMA zero fill =
+    the TF "SAME" padding, ragged tiles at the right / bottom edge) against torch fp32 on bf16-rounded operands."""
+    require_cuda()
+    ops = fd().ops
+    g = torch.Generator().manual_seed(B + H + W)
+    if u8:
+        x = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
+        xf = x.float() / 255.0
+    else:
+        x = torch.rand(B, 3, H, W, generator=g)
+        xf = x
+    w = torch.randn(16, 3, 3, 3, generator=g) * 0.3
+    bias = torch.randn(16, generator=g) * 0.2
+    ref = torch.nn.functional.hardswish(bo._conv_same(xf.bfloat16().float(), w.bfloat16().float(), 2)
+                                        + bias.bfloat16().float().view(1, -1, 1, 1))
+    Ho, Wo = ref.shape[-2:]
+    out = torch.full((B, Ho, Wo, 16), 9.0, dtype=torch.bfloat16, device="cuda")
+    ops.mbv3_stem(x.cuda(), w.cuda(), bias.cuda(), bo._same_pad(H, 3, 2)[0], bo._same_pad(W, 3, 2)[0], out)
+    got = out.float().permute(0, 3, 1, 2).cpu()
+    assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    assert rel_err(got, ref) <= 5e-3
