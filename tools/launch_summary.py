@@ -10,7 +10,12 @@ def main(path, steps):
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
         name = row["Kernel Name"].split("(")[0][-60:]
-        v = float(row["Metric Value"].replace(",", ""))
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        if v != v:                      # "nan": a launch the profiler could not time
+            continue
         unit = row["Metric Unit"]
         v = v / 1000 if unit in ("ns", "nsecond") else v * 1000 if unit in ("ms", "msecond") else v
         a = agg.setdefault(name, [0, 0.0])

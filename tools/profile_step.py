@@ -1,3 +1,5 @@
+import os
+os.environ.setdefault("FD_NO_PDL", "1")   # programmatic dependent launch lets a kernel start (and be timed) while its predecessor runs: per-kernel durations are only meaningful without it
 """Warm, in-graph per-kernel durations of one train step (torch.profiler / CUPTI around graph replays)."""
 import collections, importlib, os, sys
 import torch
