@@ -85,6 +85,27 @@ FD_API int fd_conv3x3_pool(const fd_bf16* x, const fd_bf16* w_packed, int B, int
                     float slope, const float* chan_scale, const fd_bf16* residual, uint32_t* mask_out,
                     fd_bf16* pooled, uint16_t* argmax, int flags, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The same convolution for the WIDE models (filters = 128: the width train_model.py:17 trains; the 128- / 256-channel
+ * blocks of models/SSD.py:164-189) on channel PLANES: every activation tensor is a set of [B,H,W,64] bf16 planes.
+ * One launch computes 128 output channels (two planes) from 64*gin input channels (gin <= 4 planes) with
+ * tcgen05.mma.cta_group::2 (the two SMs of a TPC on one M=256, N=128 tile, B operand split between their shared
+ * memories), partial sums over input planes in TMEM, weights streamed from L2.  Epilogue exactly as fd_conv3x3, per
+ * output plane: x[gin], residual[2], mask_out[2], out[2], mask_in[2], chan_scale[2] ([B,64] each), chan_scale2[2],
+ * out2[2] are arrays of per-plane device pointers (NULL array = absent); bias is [128].  Exactly one of out / out2.
+ * w_packed: bf16 [gin][9][128][64] (tap-major chunks of 128 couts x 64 cins) as written by fd_pack_conv3x3_wide for
+ * this launch's group of 128 output channels.  FD_CONV_1X1: centre tap only (pointwise convolution). */
+FD_API int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* w_packed, int B, int H, int W,
+                    const float* bias, float slope, const float* const* chan_scale,
+                    const fd_bf16* const* residual, uint32_t* const* mask_out, fd_bf16* const* out,
+                    const uint32_t* const* mask_in, const float* const* chan_scale2, fd_bf16* const* out2,
+                    int flags, void* stream);
+/* w: [n_layers][Cout][Cin][3][3] fp32 (torch layout) -> w_fwd [n_layers][Cout/128][Cin/64][9][128][64] bf16 (forward)
+ * and w_dgrad [n_layers][Cin/128][Cout/64][9][128][64] bf16 (input gradient: taps flipped, channel roles swapped).
+ * Either output may be NULL.  Cout (w_fwd) / Cin (w_dgrad) must be multiples of 128, the other a multiple of 64. */
+FD_API int fd_pack_conv3x3_wide(const float* w, int n_layers, int Cout, int Cin, fd_bf16* w_fwd, fd_bf16* w_dgrad,
+                         void* stream);
+
 /* Weight gradient of the same convolution (replaces the wgrad half of autograd's
  * conv2d backward for models/PoolResnet.py:35,37).
  *   dw_packed[t][ci][co] += sum_{n,y,x} g[n,y,x,co] * xpad[n,y+ky-1,x+kx-1,ci],  t = ky*3+kx

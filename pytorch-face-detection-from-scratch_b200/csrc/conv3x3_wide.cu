@@ -1,0 +1,624 @@
+// 3x3 / stride 1 / pad 1 convolution for the WIDE models (filters = 128: the width train_model.py:17 trains; the
+// 128- and 256-channel blocks of models/SSD.py:164-189), 64*gin -> 128 output channels per launch, as an implicit GEMM
+// on the sm_100a tensor cores with the two SMs of a TPC working as ONE (tcgen05.mma.cta_group::2).
+//
+// Replaces aten::conv2d (+ leaky_relu / dropout2d / residual add) at models/PoolResnet.py:35-40 and -- with
+// dgrad-packed weights -- the input-gradient half of its backward, for channel counts above the 64-channel kernels
+// (conv3x3_tc.cu), on the channel-PLANE layout of engine_planar.py (every tensor = planes of [B,H,W,64] bf16).
+//
+// Why a kernel of its own instead of four 64 -> 64 launches per layer:
+//   * N = 128 halves the A-operand shared-memory traffic per FLOP.  A M=128,N=64,K=16 MMA reads 6 KB of operands for
+//     32 clk of tensor work (128 B/clk of smem bandwidth => 48 clk: operand bound); here one CTA reads A (4 KB) and
+//     HALF of B (2 KB) per 64 clk of tensor work: the pair's B operand (128 couts x 16 cin) is split between the two
+//     CTAs' shared memories (each holds 64 couts), so the tensor pipe, not shared memory, is the bound.
+//   * The partial sums over input planes accumulate in TMEM (fp32) instead of travelling through HBM as bf16
+//     between chained launches, and the activation / mask / dropout / skip epilogue is fused (no fd_act_mask pass).
+//   * 288 KB of weights per 128 couts do not fit in shared memory: they STREAM from L2 through a ring of
+//     (input plane, tap) chunks -- 8 KB per CTA and chunk -- once per pair of 256-row tiles.
+//
+// Halo-tile formulation as in conv3x3_tc.cu: one TMA box per input plane lands the zero-padded (R+2) x Wp patch;
+// GEMM row m = y*Wp + x; tap (ky,kx) reads the same tile through a descriptor shifted by (ky*Wp + kx)*128 bytes.
+// A tile has up to two 128-row blocks; its accumulators are 2 x 128 TMEM columns, double buffered (512 columns).
+//
+// CTA pair protocol (rank 0 = leader issues every MMA for both CTAs):
+//   in_full[b], w_full[s]  : leader's barriers; BOTH CTAs' TMA loads complete_tx on them (cta_group::2 loads)
+//   in_empty[b], w_empty[s], acc_full[a] : per-CTA barriers, signalled by MULTICAST tcgen05.commit
+//   acc_empty[a]           : leader's barrier, 2 arrivals (each CTA's epilogue; the peer arrives remotely)
+// Warp roles (640 threads): 0 = input / residual loads, 1 = MMA issuer + TMEM owner, 2..17 = epilogue, 18 = TMA
+// stores, 19 = weight stream.
+#include "fd_host.h"
+#include "fd_ptx.cuh"
+#include <cstdlib>
+
+namespace fd {
+namespace {
+
+constexpr int kC = 64;                       // channels per plane
+constexpr int kNOut = 128;                   // output channels per launch (two planes)
+constexpr int kInBufs = 3;                   // ring of input-plane tiles
+constexpr int kWSlots = 4;                   // ring of weight chunks
+constexpr int kEpiWarpsW = 16;
+constexpr int kEpiThreadsW = kEpiWarpsW * 32;
+constexpr int kStoreWarpW = 2 + kEpiWarpsW;  // 18
+constexpr int kWeightWarp = kStoreWarpW + 1; // 19
+constexpr int kThreadsW = (kWeightWarp + 1) * 32;   // 640
+constexpr int kMaxGin = 4;
+
+struct WideMaps {
+  CUtensorMap in[kMaxGin];
+  CUtensorMap res[2];
+  CUtensorMap out[2];
+  CUtensorMap w;
+};
+
+struct WideParams {
+  int B, H, W, R, TW, Wp, nblk, tiles_w, tiles_h, num_tiles, gin;
+  int tap_lo, tap_hi;           // taps issued: [0,9) for 3x3, [4,5) for the centre-tap (1x1) mode
+  uint32_t in_bytes;            // bytes of one input-plane TMA box
+  uint32_t in_buf_bytes;        // bytes reserved per input ring buffer
+  uint32_t stg_bytes, stg_buf_bytes;
+  uint32_t inv_wp;
+  int flags, has_res, staged_out2;
+  float slope;
+  const float* bias;            // [128]
+  const float* chan_scale[2];   // per output plane [B,64] or null
+  const float* chan_scale2[2];
+  const uint16_t* mask_in[2];   // per output plane, [pixel][4] 16-channel units
+  uint16_t* mask_out[2];
+};
+
+__device__ __forceinline__ void bar_sync_epi_w() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreadsW) : "memory"); }
+
+// ---- cta_group-dependent primitives (kCg = 1: one CTA on its own; kCg = 2: the CTA pair) ----
+template <int kCg>
+__device__ __forceinline__ void tmem_alloc_g(uint32_t* smem_dst, uint32_t ncols) {
+  if (kCg == 2)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+}
+template <int kCg>
+__device__ __forceinline__ void tmem_relinquish_g() {
+  if (kCg == 2) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCg>
+__device__ __forceinline__ void tmem_dealloc_g(uint32_t taddr, uint32_t ncols) {
+  if (kCg == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <int kCg>
+__device__ __forceinline__ void umma_g(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (kCg == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+// arrive on the barrier at this shared-memory offset in EVERY CTA of the group once the MMAs issued so far are done
+template <int kCg>
+__device__ __forceinline__ void umma_commit_g(uint64_t* bar) {
+  if (kCg == 2)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+  else
+    umma_commit(bar);
+}
+// the leader CTA's copy of a barrier (shared::cluster address of the same offset in CTA rank 0)
+template <int kCg>
+__device__ __forceinline__ uint32_t leader_bar(uint64_t* bar) {
+  return kCg == 2 ? mapa_shared(smem_u32(bar), 0) : smem_u32(bar);
+}
+template <int kCg>
+__device__ __forceinline__ void tma_load_2d_g(void* smem_dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1) {
+  if (kCg == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+template <int kCg>
+__device__ __forceinline__ void tma_load_4d_g(void* smem_dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1, int c2,
+                                              int c3) {
+  if (kCg == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+template <int kCg>
+__global__ void __launch_bounds__(kThreadsW, 1)
+conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant__ WideParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  // Layout: input ring | weight ring | staging 0 | staging 1 | constants | barriers.  Junk GEMM rows of the last block read a
+  // few rows BEHIND their input buffer (into the next ring buffer / the weight ring): harmless, they are never stored.
+  constexpr uint32_t kChunkBytes = (kCg == 2 ? 64u : 128u) * 128u;         // this CTA's part of one (plane, tap) weight chunk
+  uint8_t* sIn = smem;
+  uint8_t* sW = sIn + ((kInBufs * p.in_buf_bytes + 1023u) & ~1023u);
+  uint8_t* sStg = sW + kWSlots * kChunkBytes;
+  float* sConst = reinterpret_cast<float*>(sStg + 2 * p.stg_buf_bytes);     // bias[128] | chan_scale[128] | chan_scale2[128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sConst + 3 * kNOut);
+  uint64_t* in_full = bars;                       // [3]  (leader's copy is the live one)
+  uint64_t* in_empty = bars + 3;                  // [3]
+  uint64_t* w_full = bars + 6;                    // [4]  (leader)
+  uint64_t* w_empty = bars + 10;                  // [4]
+  uint64_t* acc_full = bars + 14;                 // [2]
+  uint64_t* acc_empty = bars + 16;                // [2]  (leader, 2 arrivals)
+  uint64_t* res_full = bars + 18;                 // [2]
+  uint64_t* stg_free = bars + 20;                 // [2]
+  uint64_t* stg_ready = bars + 22;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = kCg == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int g = 0; g < p.gin; ++g) tma_prefetch_desc(&maps.in[g]);
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.out[0]);
+    tma_prefetch_desc(&maps.out[1]);
+    for (int i = 0; i < kInBufs; ++i) {
+      mbar_init(in_full + i, 1);
+      mbar_init(in_empty + i, 1);
+    }
+    for (int i = 0; i < kWSlots; ++i) {
+      mbar_init(w_full + i, 1);
+      mbar_init(w_empty + i, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full + s, 1);
+      mbar_init(acc_empty + s, kCg);
+      mbar_init(res_full + s, 1);
+      mbar_init(stg_free + s, 1);
+      mbar_init(stg_ready + s, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_g<kCg>(tmem_slot, 512);
+    tmem_relinquish_g<kCg>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kCg == 2) cluster_sync_all();           // the peer's barriers exist before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  // work items: a pair-tile j covers tiles kCg*j + rank; this group handles j = group, group + ngroups, ...
+  const int ngroups = static_cast<int>(gridDim.x) / kCg;
+  const int group = static_cast<int>(blockIdx.x) / kCg;
+  const int njobs = (p.num_tiles + kCg - 1) / kCg;
+  pdl_trigger();
+  pdl_wait();
+
+  auto tile_coords = [&](int tile, int& n, int& h0, int& w0) {
+    n = tile / tiles_per_img;
+    const int rem = tile - n * tiles_per_img;
+    const int th = rem / p.tiles_w;
+    h0 = th * p.R;
+    w0 = (rem - th * p.tiles_w) * p.TW;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ input + residual loads
+    if (elect_one_sync()) {
+      uint32_t P = 0;                      // running input-plane counter (ring position)
+      int it = 0;
+      for (int j = group; j < njobs; j += ngroups, ++it) {
+        const int tile = j * kCg + static_cast<int>(rank);        // >= num_tiles: dummy (every coordinate out of bounds -> zeros)
+        int n, h0, w0;
+        tile_coords(tile, n, h0, w0);
+        for (int kh = 0; kh < p.gin; ++kh, ++P) {
+          const uint32_t b = P % kInBufs, ph = (P / kInBufs) & 1u;
+          mbar_wait_sleep(in_empty + b, ph ^ 1u);
+          if (leader) mbar_expect_tx(in_full + b, p.in_bytes * kCg);
+          tma_load_4d_g<kCg>(sIn + b * p.in_buf_bytes, &maps.in[kh], leader_bar<kCg>(in_full + b), 0, w0 - 1, h0 - 1, n);
+        }
+        if (p.has_res) {
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t q = static_cast<uint32_t>(it) * 2u + g, sb = q & 1u, ph = (q >> 1) & 1u;
+            mbar_wait_sleep(stg_free + sb, ph ^ 1u);          // the store two plane-tiles ago has drained this buffer
+            mbar_expect_tx(res_full + sb, p.stg_bytes);
+            tma_load_4d(sStg + sb * p.stg_buf_bytes, &maps.res[g], res_full + sb, 0, w0, h0, n);
+          }
+        }
+      }
+    }
+  } else if (warp == kWeightWarp) {
+    // ------------------------------------------------------------------ weight stream: chunk (kh, tap) = [128 cout][64 cin]
+    if (elect_one_sync()) {
+      uint32_t c = 0;
+      for (int j = group; j < njobs; j += ngroups) {
+        for (int kh = 0; kh < p.gin; ++kh) {
+          for (int t = p.tap_lo; t < p.tap_hi; ++t, ++c) {
+            const uint32_t s = c % kWSlots, ph = (c / kWSlots) & 1u;
+            mbar_wait_sleep(w_empty + s, ph ^ 1u);
+            if (leader) mbar_expect_tx(w_full + s, kChunkBytes * kCg);
+            tma_load_2d_g<kCg>(sW + s * kChunkBytes, &maps.w, leader_bar<kCg>(w_full + s), 0,
+                               (kh * 9 + t) * kNOut + static_cast<int>(rank) * 64);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader && elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128 * kCg, kNOut, 0, 0);
+      const uint32_t wp_units = static_cast<uint32_t>(p.Wp) * 8u;
+      const bool centre = p.tap_lo != 0;
+      uint32_t P = 0, c = 0;
+      int it = 0;
+      for (int j = group; j < njobs; j += ngroups, ++it) {
+        const uint32_t a = static_cast<uint32_t>(it) & 1u, aph = (static_cast<uint32_t>(it) >> 1) & 1u;
+        mbar_wait_cluster(acc_empty + a, aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * 256u;
+        uint32_t accum = 0;
+        for (int kh = 0; kh < p.gin; ++kh, ++P) {
+          const uint32_t b = P % kInBufs, ph = (P / kInBufs) & 1u;
+          mbar_wait(in_full + b, ph);
+          tc_fence_after();
+          uint32_t a_lo = sdesc_lo(smem_u32(sIn + b * p.in_buf_bytes), 16);
+          if (centre) a_lo += wp_units + 8u;
+          int t = p.tap_lo;
+#pragma unroll 1
+          for (int ky = 0; ky < 3 && t < p.tap_hi; ++ky) {
+#pragma unroll 1
+            for (int kx = 0; kx < 3 && t < p.tap_hi; ++kx, ++t, ++c) {
+              const uint32_t s = c % kWSlots, wph = (c / kWSlots) & 1u;
+              mbar_wait(w_full + s, wph);
+              tc_fence_after();
+              const uint32_t b_lo = sdesc_lo(smem_u32(sW + s * kChunkBytes), 16);
+#pragma unroll 1
+              for (int mb = 0; mb < p.nblk; ++mb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_g<kCg>(d_tmem + static_cast<uint32_t>(mb) * kNOut, sdesc_sw128(a_lo + static_cast<uint32_t>(mb) * 1024u + 2 * k),
+                              sdesc_sw128(b_lo + 2 * k), idesc, (k != 0) ? 1u : accum);
+              }
+              accum = 1;                             // the tile's first chunk overwrites the accumulators of EVERY block
+              umma_commit_g<kCg>(w_empty + s);       // weight slot free (in both CTAs) once these MMAs have read it
+              a_lo += 8;
+            }
+            a_lo += wp_units - 24;
+          }
+          umma_commit_g<kCg>(in_empty + b);          // input plane buffer free
+        }
+        umma_commit_g<kCg>(acc_full + a);            // the tile's accumulators are final
+      }
+    }
+    __syncwarp();
+  } else if (warp == kStoreWarpW) {
+    // ------------------------------------------------------------------ TMA store issuer
+    if (elect_one_sync()) {
+      int it = 0;
+      for (int j = group; j < njobs; j += ngroups, ++it) {
+        const int tile = j * kCg + static_cast<int>(rank);
+        int n, h0, w0;
+        tile_coords(tile, n, h0, w0);
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t q = static_cast<uint32_t>(it) * 2u + g, sb = q & 1u, ph = (q >> 1) & 1u;
+          mbar_wait_sleep(stg_ready + sb, ph);
+          if (tile < p.num_tiles) {
+            tma_store_4d(&maps.out[g], sStg + sb * p.stg_buf_bytes, 0, w0, h0, n);    // beyond the image: clipped
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          mbar_arrive(stg_free + sb);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (16)
+    // One thread = one GEMM row (pixel) x 16 channels of one output plane.  TMEM lane quadrant = warp % 4,
+    // channel quarter = (warp - 2) / 4; the two output planes (TMEM column halves) are processed one after the other.
+    const int q4 = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    const int c0 = cq * 16;
+    const int et = threadIdx.x - 64;
+    const uint64_t slope2 = pk2(p.slope, p.slope);
+    const bool lrelu = (p.flags & FD_EPI_LRELU) != 0;
+    const bool has_cs = p.chan_scale[0] != nullptr, has_cs2 = p.chan_scale2[0] != nullptr;
+    if (et < kNOut) sConst[et] = p.bias ? __ldg(p.bias + et) : 0.f;
+    int it = 0, last_n = -1;
+    for (int j = group; j < njobs; j += ngroups, ++it) {
+      const int tile = j * kCg + static_cast<int>(rank);
+      const bool live = tile < p.num_tiles;
+      int n, h0, w0;
+      tile_coords(tile, n, h0, w0);
+      if (n != last_n) {          // per-image Dropout2d multipliers (uniform branch)
+        bar_sync_epi_w();
+        if (live && et >= kNOut && et < 2 * kNOut) {
+          const int ch = et - kNOut;
+          sConst[et] = has_cs ? __ldg(p.chan_scale[ch >> 6] + n * kC + (ch & 63)) : 1.f;
+        } else if (live && et >= 2 * kNOut && et < 3 * kNOut) {
+          const int ch = et - 2 * kNOut;
+          sConst[et] = has_cs2 ? __ldg(p.chan_scale2[ch >> 6] + n * kC + (ch & 63)) : 1.f;
+        }
+        bar_sync_epi_w();
+        last_n = n;
+      }
+      const uint32_t a = static_cast<uint32_t>(it) & 1u, aph = (static_cast<uint32_t>(it) >> 1) & 1u;
+      for (int g = 0; g < 2; ++g) {
+        const uint32_t qq = static_cast<uint32_t>(it) * 2u + g, sb = qq & 1u, sph = (qq >> 1) & 1u;
+        uint8_t* stg = sStg + sb * p.stg_buf_bytes;
+        if (p.has_res) mbar_wait_sleep(res_full + sb, sph);
+        else mbar_wait_sleep(stg_free + sb, sph ^ 1u);
+        if (g == 0) {
+          mbar_wait_sleep(acc_full + a, aph, 1000);
+          tc_fence_after();
+        }
+        const uint16_t* mask_in = p.mask_in[g];
+        uint16_t* mask_out = p.mask_out[g];
+#pragma unroll 1
+        for (int mb = 0; mb < p.nblk; ++mb) {
+          const int m = mb * 128 + q4 * 32 + lane;
+          const int y = static_cast<int>((static_cast<uint32_t>(m) * p.inv_wp) >> 16);
+          const int x = m - y * p.Wp;
+          const int oy = h0 + y, ox = w0 + x;
+          const bool valid = live && (y < p.R) && (x < p.TW) && (oy < p.H) && (ox < p.W);
+          const size_t pix = (static_cast<size_t>(n) * p.H + oy) * p.W + ox;
+          uint32_t mbits = 0xffffu;
+          if (valid && mask_in) mbits = __ldg(mask_in + pix * 4 + cq);
+          const uint32_t d = static_cast<uint32_t>(y * p.TW + x);
+          uint8_t* row = stg + d * 128u;
+          const uint32_t ch0 = ((static_cast<uint32_t>(cq) * 2u) ^ (d & 7u)) << 4;
+          const uint32_t ch1 = ((static_cast<uint32_t>(cq) * 2u + 1u) ^ (d & 7u)) << 4;
+          uint32_t acc[16];
+          tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * 256u +
+                                 static_cast<uint32_t>(mb * kNOut + g * kC + c0),
+                             acc);
+          tmem_ld_wait();
+          if (valid) {
+            uint64_t v2[8];
+            epi_bias_act16(acc, sConst + g * kC + c0, sConst + kNOut + g * kC + c0, lrelu, has_cs, slope2, v2);
+            if (mask_out) mask_out[pix * 4 + cq] = static_cast<uint16_t>(epi_sign_bits16(v2));
+            if (p.has_res)
+              epi_add_bf16x16(v2, *reinterpret_cast<const uint4*>(row + ch0), *reinterpret_cast<const uint4*>(row + ch1));
+            uint4 u0, u1;
+            if (!p.staged_out2) {
+              epi_pack16(v2, u0, u1);
+            } else {
+              uint64_t o2[8];
+              epi_masked16(v2, mbits, p.slope, sConst + 2 * kNOut + g * kC + c0, has_cs2, o2);
+              epi_pack16(o2, u0, u1);
+            }
+            *reinterpret_cast<uint4*>(row + ch0) = u0;
+            *reinterpret_cast<uint4*>(row + ch1) = u1;
+          }
+        }
+        fence_proxy_async();       // staging writes (generic proxy) -> visible to the TMA store
+        if (g == 1) tc_fence_before();
+        bar_sync_epi_w();
+        if (et == 0) {
+          if (g == 1) {            // both column halves of this tile's accumulators have been read by every warp
+            if (kCg == 2 && !leader) mbar_arrive_remote(mapa_shared(smem_u32(acc_empty + a), 0));
+            else mbar_arrive(acc_empty + a);
+          }
+          mbar_arrive(stg_ready + sb);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (kCg == 2) cluster_sync_all();           // nobody exits (or frees TMEM) while the pair's MMAs / commits may still touch it
+  if (warp == 1) tmem_dealloc_g<kCg>(tmem_base, 512);
+}
+
+inline size_t wide_in_buf_bytes(int R, int Wp) { return static_cast<size_t>((R + 2) * Wp) * 128; }
+inline size_t wide_stg_buf_bytes(int R, int TW) { return (static_cast<size_t>(R) * TW * 128 + 1023) / 1024 * 1024; }
+inline size_t wide_smem_for(int cg, int R, int Wp, int TW) {
+  const size_t in = (kInBufs * wide_in_buf_bytes(R, Wp) + 1023) / 1024 * 1024;
+  const size_t w = static_cast<size_t>(kWSlots) * (cg == 2 ? 64 : 128) * 128;
+  return in + w + 2 * wide_stg_buf_bytes(R, TW) + 3 * kNOut * 4 + 256 + 1024;
+}
+
+template <int kCg>
+int launch_wide(const WideMaps& maps, const WideParams& p, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_wide_kernel<kCg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int nsm = sm_count();
+  const int njobs = (p.num_tiles + kCg - 1) / kCg;
+  const int max_groups = nsm / kCg;
+  const int groups = njobs < max_groups ? njobs : max_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * kCg);
+  cfg.blockDim = dim3(kThreadsW);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (kCg == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  e = cudaLaunchKernelEx(&cfg, conv3x3_wide_kernel<kCg>, maps, p);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  count_launch();
+  return launch_status();
+}
+
+// [Cout, Cin, 3, 3] fp32 (torch) -> the two streamed bf16 packings.  One thread per output element.
+//   forward : wf[(co / 128)][ci / 64][tap][co % 128][ci % 64]
+//   dgrad   : wd[(ci / 128)][co / 64][8 - tap][ci % 128][co % 64]        (flipped taps, roles of ci / co swapped)
+__global__ void __launch_bounds__(256)
+pack_conv3x3_wide_kernel(const float* __restrict__ w, int n_layers, int Cout, int Cin, __nv_bfloat16* __restrict__ wf,
+                         __nv_bfloat16* __restrict__ wd) {
+  pdl_trigger();
+  pdl_wait();
+  const long per_layer = static_cast<long>(Cout) * Cin * 9;
+  const long total = per_layer * n_layers;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * 256L) {
+    const long l = i / per_layer;
+    const long r = i - l * per_layer;
+    if (wf) {        // i enumerates the DESTINATION order of wf: coalesced writes, gathered reads (weights are L2 resident)
+      const int ci_lo = static_cast<int>(r % 64);
+      const int co_lo = static_cast<int>((r / 64) % 128);
+      const int t = static_cast<int>((r / (64 * 128)) % 9);
+      const int gi = static_cast<int>((r / (64 * 128 * 9)) % (Cin / 64));
+      const int go = static_cast<int>(r / (64L * 128 * 9 * (Cin / 64)));
+      const int co = go * 128 + co_lo, ci = gi * 64 + ci_lo;
+      wf[i] = __float2bfloat16(__ldg(w + l * per_layer + (static_cast<long>(co) * Cin + ci) * 9 + t));
+    }
+    if (wd) {
+      const int co_lo = static_cast<int>(r % 64);
+      const int ci_lo = static_cast<int>((r / 64) % 128);
+      const int t = static_cast<int>((r / (64 * 128)) % 9);
+      const int go = static_cast<int>((r / (64 * 128 * 9)) % (Cout / 64));
+      const int gi = static_cast<int>(r / (64L * 128 * 9 * (Cout / 64)));
+      const int co = go * 64 + co_lo, ci = gi * 128 + ci_lo;
+      wd[i] = __float2bfloat16(__ldg(w + l * per_layer + (static_cast<long>(co) * Cin + ci) * 9 + (8 - t)));
+    }
+  }
+}
+
+}  // namespace
+}  // namespace fd
+
+extern "C" int fd_pack_conv3x3_wide(const float* w, int n_layers, int Cout, int Cin, fd_bf16* w_fwd, fd_bf16* w_dgrad,
+                                    void* stream) {
+  using namespace fd;
+  if (!w || n_layers <= 0 || (!w_fwd && !w_dgrad)) return FD_EINVAL;
+  if (Cout <= 0 || Cin <= 0 || Cout % 64 != 0 || Cin % 64 != 0) return FD_EUNSUPPORTED;
+  if ((w_fwd && Cout % 128 != 0) || (w_dgrad && Cin % 128 != 0)) return FD_EUNSUPPORTED;
+  const long total = static_cast<long>(n_layers) * Cout * Cin * 9;
+  const long blocks = (total + 255) / 256;
+  launch_k(pack_conv3x3_wide_kernel, dim3(static_cast<unsigned>(blocks < 148 * 16 ? blocks : 148 * 16)), dim3(256), 0,
+           static_cast<cudaStream_t>(stream), w, n_layers, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(w_fwd),
+           reinterpret_cast<__nv_bfloat16*>(w_dgrad));
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* w_packed, int B, int H, int W,
+                               const float* bias, float slope, const float* const* chan_scale,
+                               const fd_bf16* const* residual, uint32_t* const* mask_out, fd_bf16* const* out,
+                               const uint32_t* const* mask_in, const float* const* chan_scale2, fd_bf16* const* out2,
+                               int flags, void* stream) {
+  using namespace fd;
+  if (!x || !w_packed || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
+  if (gin < 1 || gin > kMaxGin) return FD_EUNSUPPORTED;
+  for (int g = 0; g < gin; ++g)
+    if (!x[g]) return FD_EINVAL;
+  const bool has_out = out && out[0] && out[1], has_out2 = out2 && out2[0] && out2[1];
+  if (has_out == has_out2) return FD_EINVAL;                 // exactly one staged output (both planes)
+  if (mask_in && !has_out2) return FD_EINVAL;
+  if (has_out2 && !(mask_in && mask_in[0] && mask_in[1])) return FD_EINVAL;
+  if (!(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;
+  static const int cg_env = [] { const char* e = getenv("FD_WIDE_CTA_GROUP"); return e ? atoi(e) : 2; }();
+  const int cg = cg_env == 1 ? 1 : 2;
+  const int nsm = sm_count();
+  const size_t smem_cap = 227 * 1024;
+
+  // Tiling: TW <= 62 output columns, R rows with R * (TW + 2) <= 256 GEMM rows (two 128-row blocks = 2 x 128 TMEM columns,
+  // double buffered).  Cost model: tensor time of the padded blocks times the number of waves over the CTA groups.
+  int bestR = 0, bestTW = 0;
+  double best = 1e30;
+  const int min_tw_tiles = (W + 61) / 62;
+  for (int tw_tiles = min_tw_tiles; tw_tiles <= min_tw_tiles + 2; ++tw_tiles) {
+    const int TW = (W + tw_tiles - 1) / tw_tiles;
+    if (TW > 62 || TW < 1) continue;
+    const int Wp = TW + 2;
+    for (int R = 1; R <= H && R + 2 <= 256; ++R) {
+      const int nblk = (R * Wp + 127) / 128;
+      if (nblk > 2) break;
+      if (wide_smem_for(cg, R, Wp, TW) > smem_cap) break;
+      const long tiles = static_cast<long>(B) * ((H + R - 1) / R) * tw_tiles;
+      const long waves = (tiles + nsm - 1) / nsm;
+      const double cost = waves * (2400.0 * nblk + 600.0);
+      if (cost < best) { best = cost; bestR = R; bestTW = TW; }
+    }
+  }
+  if (bestR == 0) return FD_EUNSUPPORTED;
+
+  WideParams p;
+  p.B = B; p.H = H; p.W = W; p.R = bestR; p.TW = bestTW; p.Wp = bestTW + 2;
+  p.nblk = (bestR * p.Wp + 127) / 128;
+  p.tiles_w = (W + bestTW - 1) / bestTW;
+  p.tiles_h = (H + bestR - 1) / bestR;
+  p.num_tiles = B * p.tiles_w * p.tiles_h;
+  p.gin = gin;
+  p.tap_lo = (flags & FD_CONV_1X1) ? 4 : 0;
+  p.tap_hi = (flags & FD_CONV_1X1) ? 5 : 9;
+  p.in_bytes = static_cast<uint32_t>((bestR + 2) * p.Wp * 128);
+  p.in_buf_bytes = static_cast<uint32_t>(wide_in_buf_bytes(bestR, p.Wp));
+  p.stg_bytes = static_cast<uint32_t>(bestR * bestTW * 128);
+  p.stg_buf_bytes = static_cast<uint32_t>(wide_stg_buf_bytes(bestR, bestTW));
+  p.inv_wp = static_cast<uint32_t>((65536 + p.Wp - 1) / p.Wp);
+  p.flags = flags;
+  p.slope = slope;
+  p.bias = bias;
+  p.has_res = (residual && residual[0] && residual[1]) ? 1 : 0;
+  p.staged_out2 = has_out2 ? 1 : 0;
+  for (int g = 0; g < 2; ++g) {
+    p.chan_scale[g] = chan_scale ? chan_scale[g] : nullptr;
+    p.chan_scale2[g] = chan_scale2 ? chan_scale2[g] : nullptr;
+    p.mask_in[g] = mask_in ? reinterpret_cast<const uint16_t*>(mask_in[g]) : nullptr;
+    p.mask_out[g] = mask_out ? reinterpret_cast<uint16_t*>(mask_out[g]) : nullptr;
+  }
+  if ((p.chan_scale[0] == nullptr) != (p.chan_scale[1] == nullptr)) return FD_EINVAL;
+  if ((p.chan_scale2[0] == nullptr) != (p.chan_scale2[1] == nullptr)) return FD_EINVAL;
+  if ((p.mask_out[0] == nullptr) != (p.mask_out[1] == nullptr)) return FD_EINVAL;
+
+  WideMaps maps;
+  int rc;
+  for (int g = 0; g < kMaxGin; ++g) {
+    rc = make_tmap_nhwc_bf16(&maps.in[g], x[g < gin ? g : 0], B, H, W, kC, p.Wp, bestR + 2);
+    if (rc != FD_OK) return rc;
+  }
+  rc = make_tmap_2d_bf16(&maps.w, w_packed, gin * 9 * kNOut, kC, cg == 2 ? 64 : 128, kC);
+  if (rc != FD_OK) return rc;
+  fd_bf16* const* staged = has_out ? out : out2;
+  for (int g = 0; g < 2; ++g) {
+    rc = make_tmap_nhwc_bf16(&maps.out[g], staged[g], B, H, W, kC, bestTW, bestR);
+    if (rc != FD_OK) return rc;
+    rc = make_tmap_nhwc_bf16(&maps.res[g], p.has_res ? residual[g] : x[0], B, H, W, kC, bestTW, bestR);
+    if (rc != FD_OK) return rc;
+  }
+  const size_t smem = wide_smem_for(cg, bestR, p.Wp, bestTW);
+  return cg == 2 ? launch_wide<2>(maps, p, smem, static_cast<cudaStream_t>(stream))
+                 : launch_wide<1>(maps, p, smem, static_cast<cudaStream_t>(stream));
+}

@@ -37,6 +37,37 @@ def conv3x3_pool(x, w_packed, pooled, *, bias=None, slope=0.2, lrelu=True, chan_
                                 dptr(argmax, torch.int16), fl, cur_stream()), "fd_conv3x3_pool")
 
 
+def _plane_ptrs(tensors, dtype):
+    """ctypes array of per-plane device pointers (None -> NULL array)."""
+    if tensors is None:
+        return None
+    return (ctypes.c_void_p * len(tensors))(*[dptr(t, dtype) for t in tensors])
+
+
+def conv3x3_wide(x_planes, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_scale=None, residual=None, mask_out=None,
+                 out=None, mask_in=None, chan_scale2=None, out2=None, flags=0):
+    """fd_conv3x3_wide: 64*len(x_planes) -> 128 channels on [B,H,W,64] planes; every per-plane argument is a list of two
+    tensors (x_planes: gin tensors).  w_packed: [gin,9,128,64] bf16 (ops.pack_conv3x3_wide, one group of 128 couts)."""
+    B, H, W, C = x_planes[0].shape
+    assert C == 64
+    fl = flags | (EPI_LRELU if lrelu else 0)
+    keep = [_plane_ptrs(x_planes, BF16), _plane_ptrs(chan_scale, F32), _plane_ptrs(residual, BF16), _plane_ptrs(mask_out, I32),
+            _plane_ptrs(out, BF16), _plane_ptrs(mask_in, I32), _plane_ptrs(chan_scale2, F32), _plane_ptrs(out2, BF16)]
+    cast = [ctypes.cast(a, ctypes.c_void_p) if a is not None else None for a in keep]
+    check(lib().fd_conv3x3_wide(cast[0], len(x_planes), dptr(w_packed, BF16), B, H, W, dptr(bias, F32), slope, cast[1],
+                                cast[2], cast[3], cast[4], cast[5], cast[6], cast[7], fl, cur_stream()), "fd_conv3x3_wide")
+
+
+def pack_conv3x3_wide(w, w_fwd, w_dgrad):
+    """w: [L,Cout,Cin,3,3] (or [Cout,Cin,3,3]) fp32 -> w_fwd [L,Cout/128,Cin/64,9,128,64], w_dgrad [L,Cin/128,Cout/64,9,128,64]."""
+    if w.dim() == 5:
+        n, Cout, Cin = w.shape[0], w.shape[1], w.shape[2]
+    else:
+        n, Cout, Cin = 1, w.shape[0], w.shape[1]
+    check(lib().fd_pack_conv3x3_wide(dptr(w, F32), n, Cout, Cin, dptr(w_fwd, BF16), dptr(w_dgrad, BF16), cur_stream()),
+          "fd_pack_conv3x3_wide")
+
+
 def conv3x3_wgrad(x, g, dw_packed, dbias, flags=0):
     B, H, W, C = x.shape
     check(lib().fd_conv3x3_wgrad(dptr(x, BF16), dptr(g, BF16), B, H, W, C, dptr(dw_packed, F32), dptr(dbias, F32),

@@ -1,0 +1,116 @@
+"""GPU parity of fd_conv3x3_wide (64*gin -> 128 channels on [B,H,W,64] planes, tcgen05.mma.cta_group::2, weights streamed
+from L2) through the C ABI against torch fp32 on the same bf16-rounded operands (models/PoolResnet.py:35-40 at
+filters = 128, train_model.py:17; the 128 / 256-channel blocks of models/SSD.py:164-189).  Tolerances as in
+test_gpu_layers.py: outputs are bf16 (rel. 2^-8 per element), accumulation fp32 over up to 9*256 products."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import fd, rel_err, require_cuda
+from tests.test_gpu_layers import _bits, _close
+
+pytestmark = pytest.mark.gpu
+
+
+def _planes(t):
+    """[B,H,W,64*G] -> list of G contiguous [B,H,W,64] planes"""
+    return [t[..., 64 * g:64 * (g + 1)].contiguous() for g in range(t.shape[-1] // 64)]
+
+
+def _cat(planes):
+    return torch.cat([p.float() for p in planes], dim=-1)
+
+
+@pytest.mark.parametrize("B,H,W,gin", [(2, 15, 15, 2), (1, 15, 15, 2), (3, 30, 30, 2), (2, 60, 60, 2), (1, 7, 9, 1), (5, 16, 8, 4),
+                                       (1, 64, 125, 2), (150, 15, 15, 2), (9, 60, 60, 1)])
+def test_conv3x3_wide_forward_and_dgrad(B, H, W, gin):
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(B * 100 + H + gin)
+    dev = "cuda"
+    Cin, Cout = 64 * gin, 128
+    x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
+    res = torch.randn(B, H, W, Cout, device=dev).bfloat16()
+    msk = torch.randn(B, H, W, Cout, device=dev).bfloat16()
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) * (0.05 / gin ** 0.5)
+    bias = torch.randn(Cout, device=dev)
+    cs = (torch.rand(B, Cout, device=dev) < 0.75).float() / 0.75
+    cs2 = (torch.rand(B, Cout, device=dev) < 0.75).float() / 0.75
+    wf = torch.empty(1, 1, gin, 9, 128, 64, dtype=torch.bfloat16, device=dev)
+    ops.pack_conv3x3_wide(w, wf, None)
+    wq = w.bfloat16().float()
+    xp = _planes(x)
+    xn = x.float().permute(0, 3, 1, 2)
+    nhwc = lambda t: t.permute(0, 2, 3, 1)
+    csp = [cs[:, :64].contiguous(), cs[:, 64:].contiguous()]
+    cs2p = [cs2[:, :64].contiguous(), cs2[:, 64:].contiguous()]
+    # (1) conv + bias + lrelu
+    out = [torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    ops.conv3x3_wide(xp, wf[0, 0], bias=bias, lrelu=True, out=out)
+    ref1 = nhwc(F.leaky_relu(F.conv2d(xn, wq, bias, padding=1), 0.2))
+    _close(_cat(out), ref1, "conv+bias+lrelu")
+    # (2) + dropout multiplier, sign bits of the pre-residual value, residual add
+    mo = [torch.zeros(B, H, W, 2, dtype=torch.int32, device=dev) for _ in range(2)]
+    out = [torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    ops.conv3x3_wide(xp, wf[0, 0], bias=bias, lrelu=True, chan_scale=csp, residual=_planes(res), mask_out=mo, out=out)
+    refb = ref1 * cs[:, None, None, :]
+    _close(_cat(out), refb + res.float(), "residual out")
+    got_bits = torch.cat([((m.to(torch.int64)[..., None] >> torch.arange(32, device=dev)) & 1).reshape(B, H, W, 64) for m in mo],
+                         dim=-1).bool()
+    sure = refb.abs() > 1e-3
+    assert torch.equal(got_bits[sure], (refb > 0)[sure]) and sure.float().mean().item() > 0.5
+    # (3) the input gradient: a convolution Cout -> Cin with the dgrad packing (needs Cin = 128 output channels here)
+    if gin == 2:
+        g = torch.randn(B, H, W, Cout, device=dev).bfloat16()
+        wd = torch.empty(1, 1, Cout // 64, 9, 128, 64, dtype=torch.bfloat16, device=dev)
+        ops.pack_conv3x3_wide(w, None, wd)
+        xin = torch.zeros(B, Cin, H, W, device=dev, requires_grad=True)
+        (gref,) = torch.autograd.grad(F.conv2d(xin, wq, None, padding=1), xin, g.float().permute(0, 3, 1, 2))
+        G = nhwc(gref) + res.float()
+        out = [torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        ops.conv3x3_wide(_planes(g), wd[0, 0], residual=_planes(res), out=out)
+        _close(_cat(out), G, "dgrad + residual")
+        out2 = [torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        ops.conv3x3_wide(_planes(g), wd[0, 0], residual=_planes(res), mask_in=[_bits(m) for m in _planes(msk)], chan_scale2=cs2p,
+                         out2=out2)
+        G2 = G * cs2[:, None, None, :] * torch.where(msk.float() > 0, 1.0, 0.2)
+        _close(_cat(out2), G2, "masked out2", rel=6e-3)
+
+
+def test_conv3x3_wide_centre_tap_is_pointwise():
+    """FD_CONV_1X1: only the centre tap of the packed weights = a 1x1 convolution (models/SeparableCNN.py:13-19 at 128 filters)"""
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(5)
+    dev = "cuda"
+    B, H, W = 4, 30, 30
+    x = torch.randn(B, H, W, 128, device=dev).bfloat16()
+    w1 = torch.randn(128, 128, device=dev) * 0.1
+    w = torch.zeros(128, 128, 3, 3, device=dev)
+    w[:, :, 1, 1] = w1
+    wf = torch.empty(1, 1, 2, 9, 128, 64, dtype=torch.bfloat16, device=dev)
+    ops.pack_conv3x3_wide(w, wf, None)
+    out = [torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    ops.conv3x3_wide(_planes(x), wf[0, 0], lrelu=True, out=out, flags=ops.CONV_1X1)
+    ref = F.leaky_relu(x.float() @ w1.bfloat16().float().t(), 0.2)
+    _close(_cat(out), ref, "1x1")
+
+
+def test_conv3x3_wide_256_outputs_two_groups():
+    """Cout = 256 = two launches over the two 128-cout groups of the packing (models/SSD.py:173-181: 128 -> 256)"""
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(6)
+    dev = "cuda"
+    B, H, W = 2, 30, 30
+    x = torch.randn(B, H, W, 128, device=dev).bfloat16()
+    w = torch.randn(256, 128, 3, 3, device=dev) * 0.04
+    wf = torch.empty(1, 2, 2, 9, 128, 64, dtype=torch.bfloat16, device=dev)
+    ops.pack_conv3x3_wide(w, wf, None)
+    outs = []
+    for go in range(2):
+        out = [torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        ops.conv3x3_wide(_planes(x), wf[0, go], out=out)
+        outs += out
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), None, padding=1).permute(0, 2, 3, 1)
+    _close(_cat(outs), ref, "256 outputs")
