@@ -24,8 +24,11 @@
 //   in_full[b], w_full[s]  : leader's barriers; BOTH CTAs' TMA loads complete_tx on them (cta_group::2 loads)
 //   in_empty[b], w_empty[s], acc_full[a] : per-CTA barriers, signalled by MULTICAST tcgen05.commit
 //   acc_empty[a]           : leader's barrier, 2 arrivals (each CTA's epilogue; the peer arrives remotely)
-// Warp roles (640 threads): 0 = input / residual loads, 1 = MMA issuer + TMEM owner, 2..17 = epilogue, 18 = TMA
-// stores, 19 = weight stream.
+// Warp roles (672 threads): 0 = input loads, 1 = MMA issuer + TMEM owner, 2..17 = epilogue, 18 = TMA stores,
+// 19 = weight stream, 20 = residual loads (each stream of loads waits on its own barriers: none delays another).
+// Weights are handed over one KERNEL ROW (3 taps, 24 KB per CTA) at a time: the MMA thread's queue is only ~2 MMAs deep,
+// so every barrier test (~100-250 clk even when the data is long there) drains the tensor pipe; 6 tests per tile
+// instead of 18 (measured: 4400 -> ~1500 clk of stall per 9200-clk tile).
 #include "fd_host.h"
 #include "fd_ptx.cuh"
 #include <cstdlib>
@@ -36,12 +39,13 @@ namespace {
 constexpr int kC = 64;                       // channels per plane
 constexpr int kNOut = 128;                   // output channels per launch (two planes)
 constexpr int kInBufs = 3;                   // ring of input-plane tiles
-constexpr int kWSlots = 4;                   // ring of weight chunks
+constexpr int kMaxWSlots = 8;                // ring of weight chunks (kernel rows): as many as fit (WideParams::wslots)
 constexpr int kEpiWarpsW = 16;
 constexpr int kEpiThreadsW = kEpiWarpsW * 32;
 constexpr int kStoreWarpW = 2 + kEpiWarpsW;  // 18
 constexpr int kWeightWarp = kStoreWarpW + 1; // 19
-constexpr int kThreadsW = (kWeightWarp + 1) * 32;   // 640
+constexpr int kResWarp = kWeightWarp + 1;    // 20
+constexpr int kThreadsW = (kResWarp + 1) * 32;      // 672
 constexpr int kMaxGin = 4;
 
 struct WideMaps {
@@ -56,9 +60,12 @@ struct WideParams {
   int tap_lo, tap_hi;           // taps issued: [0,9) for 3x3, [4,5) for the centre-tap (1x1) mode
   uint32_t in_bytes;            // bytes of one input-plane TMA box
   uint32_t in_buf_bytes;        // bytes reserved per input ring buffer
-  uint32_t stg_bytes, stg_buf_bytes;
+  uint32_t stg_bytes, stg_buf_bytes;   // one staging UNIT: a whole plane-tile, or (split) the rows of one 128-row block
+  int wslots;                   // weight ring depth
+  int tpg, ngrp;                // taps per weight chunk (3: a kernel row; 1: centre-tap mode) and chunks per input plane
+  int split, rpb, units;        // split: 128 % Wp == 0, a block = rpb whole tile rows = one staging unit; units per plane-tile
   uint32_t inv_wp;
-  int flags, has_res, staged_out2;
+  int flags, has_res, staged_out2, dbg;
   float slope;
   const float* bias;            // [128]
   const float* chan_scale[2];   // per output plane [B,64] or null
@@ -66,6 +73,12 @@ struct WideParams {
   const uint16_t* mask_in[2];   // per output plane, [pixel][4] 16-channel units
   uint16_t* mask_out[2];
 };
+
+// FD_WIDE_TIMING=1: cycles the MMA thread of CTA 0 spent waiting for [0] free accumulators, [1] input planes, [2] weight
+// chunks, [3] total loop cycles, [4] tiles; epilogue thread 0: [5] waiting for acc_full, [6] waiting for staging, [7] total
+__device__ unsigned long long g_wide_dbg[16];   // [8] kernel entry -> MMA loop start, [9] MMA loop end -> CTA exit, [10] entry -> after pdl_wait, [11] launches
+#define FD_WTE(slot, expr) do { if (p.dbg && blockIdx.x == 0 && et == 0) { const long long t0_ = clock64(); expr; g_wide_dbg[slot] += clock64() - t0_; } else { expr; } } while (0)
+#define FD_WT(slot, expr) do { if (p.dbg && blockIdx.x == 0) { const long long t0_ = clock64(); expr; g_wide_dbg[slot] += clock64() - t0_; } else { expr; } } while (0)
 
 __device__ __forceinline__ void bar_sync_epi_w() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreadsW) : "memory"); }
 
@@ -153,27 +166,30 @@ template <int kCg>
 __global__ void __launch_bounds__(kThreadsW, 1)
 conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant__ WideParams p) {
   extern __shared__ uint8_t smem_raw[];
+  const long long t_entry = clock64();
+  __shared__ long long s_mma_end, s_after_wait;
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   // Layout: input ring | weight ring | staging 0 | staging 1 | constants | barriers.  Junk GEMM rows of the last block read a
   // few rows BEHIND their input buffer (into the next ring buffer / the weight ring): harmless, they are never stored.
-  constexpr uint32_t kChunkBytes = (kCg == 2 ? 64u : 128u) * 128u;         // this CTA's part of one (plane, tap) weight chunk
+  constexpr uint32_t kTapBytes = (kCg == 2 ? 64u : 128u) * 128u;           // this CTA's part of one (plane, tap): 64 couts x 64 cins
+  const uint32_t kChunkBytes = kTapBytes * static_cast<uint32_t>(p.tpg);  // one ring slot = one kernel row of taps
   uint8_t* sIn = smem;
   uint8_t* sW = sIn + ((kInBufs * p.in_buf_bytes + 1023u) & ~1023u);
-  uint8_t* sStg = sW + kWSlots * kChunkBytes;
+  uint8_t* sStg = sW + p.wslots * kChunkBytes;
   float* sConst = reinterpret_cast<float*>(sStg + 2 * p.stg_buf_bytes);     // bias[128] | chan_scale[128] | chan_scale2[128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sConst + 3 * kNOut);
   uint64_t* in_full = bars;                       // [3]  (leader's copy is the live one)
   uint64_t* in_empty = bars + 3;                  // [3]
-  uint64_t* w_full = bars + 6;                    // [4]  (leader)
-  uint64_t* w_empty = bars + 10;                  // [4]
-  uint64_t* acc_full = bars + 14;                 // [2]
-  uint64_t* acc_empty = bars + 16;                // [2]  (leader, 2 arrivals)
-  uint64_t* res_full = bars + 18;                 // [2]
-  uint64_t* stg_free = bars + 20;                 // [2]
-  uint64_t* stg_ready = bars + 22;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* w_full = bars + 6;                    // [8]  (leader)
+  uint64_t* w_empty = bars + 14;                  // [8]
+  uint64_t* acc_full = bars + 22;                 // [2]
+  uint64_t* acc_empty = bars + 24;                // [2]  (leader, 2 arrivals)
+  uint64_t* res_full = bars + 26;                 // [2]
+  uint64_t* stg_free = bars + 28;                 // [2]
+  uint64_t* stg_ready = bars + 30;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -189,7 +205,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
       mbar_init(in_full + i, 1);
       mbar_init(in_empty + i, 1);
     }
-    for (int i = 0; i < kWSlots; ++i) {
+    for (int i = 0; i < kMaxWSlots; ++i) {
       mbar_init(w_full + i, 1);
       mbar_init(w_empty + i, 1);
     }
@@ -218,6 +234,8 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
   const int njobs = (p.num_tiles + kCg - 1) / kCg;
   pdl_trigger();
   pdl_wait();
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { g_wide_dbg[10] += clock64() - t_entry; g_wide_dbg[11] += 1; }
+  if (p.dbg && threadIdx.x == 0) s_after_wait = clock64();
 
   auto tile_coords = [&](int tile, int& n, int& h0, int& w0) {
     n = tile / tiles_per_img;
@@ -228,26 +246,35 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ input + residual loads
+    // ------------------------------------------------------------------ input loads
     if (elect_one_sync()) {
-      uint32_t P = 0;                      // running input-plane counter (ring position)
-      int it = 0;
-      for (int j = group; j < njobs; j += ngroups, ++it) {
+      uint32_t b = 0, ph = 0;              // ring buffer and its phase
+      for (int j = group; j < njobs; j += ngroups) {
         const int tile = j * kCg + static_cast<int>(rank);        // >= num_tiles: dummy (every coordinate out of bounds -> zeros)
         int n, h0, w0;
         tile_coords(tile, n, h0, w0);
-        for (int kh = 0; kh < p.gin; ++kh, ++P) {
-          const uint32_t b = P % kInBufs, ph = (P / kInBufs) & 1u;
+        for (int kh = 0; kh < p.gin; ++kh) {
           mbar_wait_sleep(in_empty + b, ph ^ 1u);
           if (leader) mbar_expect_tx(in_full + b, p.in_bytes * kCg);
           tma_load_4d_g<kCg>(sIn + b * p.in_buf_bytes, &maps.in[kh], leader_bar<kCg>(in_full + b), 0, w0 - 1, h0 - 1, n);
+          if (++b == kInBufs) { b = 0; ph ^= 1u; }
         }
-        if (p.has_res) {
-          for (int g = 0; g < 2; ++g) {
-            const uint32_t q = static_cast<uint32_t>(it) * 2u + g, sb = q & 1u, ph = (q >> 1) & 1u;
-            mbar_wait_sleep(stg_free + sb, ph ^ 1u);          // the store two plane-tiles ago has drained this buffer
+      }
+    }
+  } else if (warp == kResWarp) {
+    // ------------------------------------------------------------------ residual loads into the staging units
+    if (p.has_res && elect_one_sync()) {
+      uint32_t q = 0;
+      for (int j = group; j < njobs; j += ngroups) {
+        const int tile = j * kCg + static_cast<int>(rank);
+        int n, h0, w0;
+        tile_coords(tile, n, h0, w0);
+        for (int g = 0; g < 2; ++g) {
+          for (int u = 0; u < p.units; ++u, ++q) {
+            const uint32_t sb = q & 1u, ph = (q >> 1) & 1u;
+            mbar_wait_sleep(stg_free + sb, ph ^ 1u);        // the store two units ago has drained this buffer
             mbar_expect_tx(res_full + sb, p.stg_bytes);
-            tma_load_4d(sStg + sb * p.stg_buf_bytes, &maps.res[g], res_full + sb, 0, w0, h0, n);
+            tma_load_4d(sStg + sb * p.stg_buf_bytes, &maps.res[g], res_full + sb, 0, w0, h0 + u * p.rpb, n);
           }
         }
       }
@@ -255,15 +282,16 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
   } else if (warp == kWeightWarp) {
     // ------------------------------------------------------------------ weight stream: chunk (kh, tap) = [128 cout][64 cin]
     if (elect_one_sync()) {
-      uint32_t c = 0;
+      uint32_t s = 0, ph = 0;              // ring slot and its phase
       for (int j = group; j < njobs; j += ngroups) {
         for (int kh = 0; kh < p.gin; ++kh) {
-          for (int t = p.tap_lo; t < p.tap_hi; ++t, ++c) {
-            const uint32_t s = c % kWSlots, ph = (c / kWSlots) & 1u;
+          for (int r = 0; r < p.ngrp; ++r) {
             mbar_wait_sleep(w_empty + s, ph ^ 1u);
             if (leader) mbar_expect_tx(w_full + s, kChunkBytes * kCg);
-            tma_load_2d_g<kCg>(sW + s * kChunkBytes, &maps.w, leader_bar<kCg>(w_full + s), 0,
-                               (kh * 9 + t) * kNOut + static_cast<int>(rank) * 64);
+            for (int i = 0; i < p.tpg; ++i)
+              tma_load_2d_g<kCg>(sW + s * kChunkBytes + i * kTapBytes, &maps.w, leader_bar<kCg>(w_full + s), 0,
+                                 (kh * 9 + p.tap_lo + r * p.tpg + i) * kNOut + static_cast<int>(rank) * 64);
+            if (++s == static_cast<uint32_t>(p.wslots)) { s = 0; ph ^= 1u; }
           }
         }
       }
@@ -271,32 +299,30 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
     if (leader && elect_one_sync()) {
+      const long long t_start = clock64();
       constexpr uint32_t idesc = make_idesc_bf16(128 * kCg, kNOut, 0, 0);
       const uint32_t wp_units = static_cast<uint32_t>(p.Wp) * 8u;
-      const bool centre = p.tap_lo != 0;
-      uint32_t P = 0, c = 0;
+      uint32_t ib = 0, iph = 0;            // input ring buffer and its phase
+      uint32_t s = 0, wph = 0;             // weight ring slot and its phase
       int it = 0;
       for (int j = group; j < njobs; j += ngroups, ++it) {
         const uint32_t a = static_cast<uint32_t>(it) & 1u, aph = (static_cast<uint32_t>(it) >> 1) & 1u;
-        mbar_wait_cluster(acc_empty + a, aph ^ 1u);
+        FD_WT(0, mbar_wait_cluster(acc_empty + a, aph ^ 1u));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * 256u;
         uint32_t accum = 0;
-        for (int kh = 0; kh < p.gin; ++kh, ++P) {
-          const uint32_t b = P % kInBufs, ph = (P / kInBufs) & 1u;
-          mbar_wait(in_full + b, ph);
+        for (int kh = 0; kh < p.gin; ++kh) {
+          FD_WT(1, mbar_wait(in_full + ib, iph));
           tc_fence_after();
-          uint32_t a_lo = sdesc_lo(smem_u32(sIn + b * p.in_buf_bytes), 16);
-          if (centre) a_lo += wp_units + 8u;
-          int t = p.tap_lo;
+          // first tap: (0,0), or the centre tap (1,1) in 1x1 mode
+          uint32_t a_lo = sdesc_lo(smem_u32(sIn + ib * p.in_buf_bytes), 16) + (p.tap_lo != 0 ? wp_units + 8u : 0u);
 #pragma unroll 1
-          for (int ky = 0; ky < 3 && t < p.tap_hi; ++ky) {
+          for (int r = 0; r < p.ngrp; ++r) {
+            FD_WT(2, mbar_wait(w_full + s, wph));
+            tc_fence_after();
+            uint32_t b_lo = sdesc_lo(smem_u32(sW + s * kChunkBytes), 16);
 #pragma unroll 1
-            for (int kx = 0; kx < 3 && t < p.tap_hi; ++kx, ++t, ++c) {
-              const uint32_t s = c % kWSlots, wph = (c / kWSlots) & 1u;
-              mbar_wait(w_full + s, wph);
-              tc_fence_after();
-              const uint32_t b_lo = sdesc_lo(smem_u32(sW + s * kChunkBytes), 16);
+            for (int i = 0; i < p.tpg; ++i) {
 #pragma unroll 1
               for (int mb = 0; mb < p.nblk; ++mb) {
 #pragma unroll
@@ -304,16 +330,20 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
                   umma_g<kCg>(d_tmem + static_cast<uint32_t>(mb) * kNOut, sdesc_sw128(a_lo + static_cast<uint32_t>(mb) * 1024u + 2 * k),
                               sdesc_sw128(b_lo + 2 * k), idesc, (k != 0) ? 1u : accum);
               }
-              accum = 1;                             // the tile's first chunk overwrites the accumulators of EVERY block
-              umma_commit_g<kCg>(w_empty + s);       // weight slot free (in both CTAs) once these MMAs have read it
-              a_lo += 8;
+              accum = 1;                             // the tile's first tap overwrites the accumulators of EVERY block
+              a_lo += 8u;                            // next column
+              b_lo += kTapBytes >> 4;
             }
-            a_lo += wp_units - 24;
+            umma_commit_g<kCg>(w_empty + s);         // weight slot free (in both CTAs) once these MMAs have read it
+            if (++s == static_cast<uint32_t>(p.wslots)) { s = 0; wph ^= 1u; }
+            a_lo += wp_units - 24u;                  // next kernel row
           }
-          umma_commit_g<kCg>(in_empty + b);          // input plane buffer free
+          umma_commit_g<kCg>(in_empty + ib);         // input plane buffer free
+          if (++ib == kInBufs) { ib = 0; iph ^= 1u; }
         }
         umma_commit_g<kCg>(acc_full + a);            // the tile's accumulators are final
       }
+      if (p.dbg && blockIdx.x == 0) { g_wide_dbg[3] += clock64() - t_start; g_wide_dbg[4] += it; g_wide_dbg[8] += t_start - t_entry; s_mma_end = clock64(); }
     }
     __syncwarp();
   } else if (warp == kStoreWarpW) {
@@ -324,15 +354,18 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         const int tile = j * kCg + static_cast<int>(rank);
         int n, h0, w0;
         tile_coords(tile, n, h0, w0);
+        uint32_t q = static_cast<uint32_t>(it) * 2u * static_cast<uint32_t>(p.units);
         for (int g = 0; g < 2; ++g) {
-          const uint32_t q = static_cast<uint32_t>(it) * 2u + g, sb = q & 1u, ph = (q >> 1) & 1u;
-          mbar_wait_sleep(stg_ready + sb, ph);
-          if (tile < p.num_tiles) {
-            tma_store_4d(&maps.out[g], sStg + sb * p.stg_buf_bytes, 0, w0, h0, n);    // beyond the image: clipped
-            tma_store_commit();
-            tma_store_wait_read<0>();
+          for (int u = 0; u < p.units; ++u, ++q) {
+            const uint32_t sb = q & 1u, ph = (q >> 1) & 1u;
+            mbar_wait_sleep(stg_ready + sb, ph);
+            if (tile < p.num_tiles && h0 + u * p.rpb < p.H) {
+              tma_store_4d(&maps.out[g], sStg + sb * p.stg_buf_bytes, 0, w0, h0 + u * p.rpb, n);    // beyond the image: clipped
+              tma_store_commit();
+              tma_store_wait_read<0>();
+            }
+            mbar_arrive(stg_free + sb);
           }
-          mbar_arrive(stg_free + sb);
         }
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -350,6 +383,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
     const bool lrelu = (p.flags & FD_EPI_LRELU) != 0;
     const bool has_cs = p.chan_scale[0] != nullptr, has_cs2 = p.chan_scale2[0] != nullptr;
     if (et < kNOut) sConst[et] = p.bias ? __ldg(p.bias + et) : 0.f;
+    const long long t_epi0 = clock64();
     int it = 0, last_n = -1;
     for (int j = group; j < njobs; j += ngroups, ++it) {
       const int tile = j * kCg + static_cast<int>(rank);
@@ -369,19 +403,25 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         last_n = n;
       }
       const uint32_t a = static_cast<uint32_t>(it) & 1u, aph = (static_cast<uint32_t>(it) >> 1) & 1u;
+      uint32_t qq = static_cast<uint32_t>(it) * 2u * static_cast<uint32_t>(p.units);
       for (int g = 0; g < 2; ++g) {
-        const uint32_t qq = static_cast<uint32_t>(it) * 2u + g, sb = qq & 1u, sph = (qq >> 1) & 1u;
-        uint8_t* stg = sStg + sb * p.stg_buf_bytes;
-        if (p.has_res) mbar_wait_sleep(res_full + sb, sph);
-        else mbar_wait_sleep(stg_free + sb, sph ^ 1u);
-        if (g == 0) {
-          mbar_wait_sleep(acc_full + a, aph, 1000);
-          tc_fence_after();
-        }
         const uint16_t* mask_in = p.mask_in[g];
         uint16_t* mask_out = p.mask_out[g];
+        uint8_t* stg = nullptr;
+        uint32_t sb = 0;
 #pragma unroll 1
         for (int mb = 0; mb < p.nblk; ++mb) {
+          if (p.split || mb == 0) {          // a staging unit begins: its residual has landed / the store two units ago has drained it
+            sb = qq & 1u;
+            const uint32_t sph = (qq >> 1) & 1u;
+            stg = sStg + sb * p.stg_buf_bytes;
+            if (p.has_res) FD_WTE(6, mbar_wait_sleep(res_full + sb, sph));
+            else FD_WTE(6, mbar_wait_sleep(stg_free + sb, sph ^ 1u));
+          }
+          if (g == 0 && mb == 0) {
+            FD_WTE(5, mbar_wait_sleep(acc_full + a, aph, 1000));
+            tc_fence_after();
+          }
           const int m = mb * 128 + q4 * 32 + lane;
           const int y = static_cast<int>((static_cast<uint32_t>(m) * p.inv_wp) >> 16);
           const int x = m - y * p.Wp;
@@ -390,7 +430,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
           const size_t pix = (static_cast<size_t>(n) * p.H + oy) * p.W + ox;
           uint32_t mbits = 0xffffu;
           if (valid && mask_in) mbits = __ldg(mask_in + pix * 4 + cq);
-          const uint32_t d = static_cast<uint32_t>(y * p.TW + x);
+          const uint32_t d = static_cast<uint32_t>((p.split ? y - mb * p.rpb : y) * p.TW + x);    // row of the dense staging unit
           uint8_t* row = stg + d * 128u;
           const uint32_t ch0 = ((static_cast<uint32_t>(cq) * 2u) ^ (d & 7u)) << 4;
           const uint32_t ch1 = ((static_cast<uint32_t>(cq) * 2u + 1u) ^ (d & 7u)) << 4;
@@ -416,33 +456,55 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
             *reinterpret_cast<uint4*>(row + ch0) = u0;
             *reinterpret_cast<uint4*>(row + ch1) = u1;
           }
-        }
-        fence_proxy_async();       // staging writes (generic proxy) -> visible to the TMA store
-        if (g == 1) tc_fence_before();
-        bar_sync_epi_w();
-        if (et == 0) {
-          if (g == 1) {            // both column halves of this tile's accumulators have been read by every warp
-            if (kCg == 2 && !leader) mbar_arrive_remote(mapa_shared(smem_u32(acc_empty + a), 0));
-            else mbar_arrive(acc_empty + a);
+          if (p.split || mb == p.nblk - 1) {     // the unit is complete
+            const bool tile_done = g == 1 && mb == p.nblk - 1;
+            fence_proxy_async();       // staging writes (generic proxy) -> visible to the TMA store
+            if (tile_done) tc_fence_before();
+            bar_sync_epi_w();
+            if (et == 0) {
+              if (tile_done) {         // every column of this tile's accumulators has been read by every warp
+                if (kCg == 2 && !leader) mbar_arrive_remote(mapa_shared(smem_u32(acc_empty + a), 0));
+                else mbar_arrive(acc_empty + a);
+              }
+              mbar_arrive(stg_ready + sb);
+            }
+            ++qq;
           }
-          mbar_arrive(stg_ready + sb);
         }
       }
     }
+    if (p.dbg && blockIdx.x == 0 && et == 0) g_wide_dbg[7] += clock64() - t_epi0;
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) g_wide_dbg[9] += clock64() - s_mma_end;
+  if (p.dbg && threadIdx.x == 0) {       // slowest CTA of the launch: after pdl_wait -> exit, and entry -> exit
+    atomicMax(&g_wide_dbg[12], static_cast<unsigned long long>(clock64() - s_after_wait));
+    atomicMax(&g_wide_dbg[13], static_cast<unsigned long long>(clock64() - t_entry));
+  }
   if (kCg == 2) cluster_sync_all();           // nobody exits (or frees TMEM) while the pair's MMAs / commits may still touch it
   if (warp == 1) tmem_dealloc_g<kCg>(tmem_base, 512);
 }
 
 inline size_t wide_in_buf_bytes(int R, int Wp) { return static_cast<size_t>((R + 2) * Wp) * 128; }
-inline size_t wide_stg_buf_bytes(int R, int TW) { return (static_cast<size_t>(R) * TW * 128 + 1023) / 1024 * 1024; }
-inline size_t wide_smem_for(int cg, int R, int Wp, int TW) {
+inline bool wide_split(int R, int Wp) { return 128 % Wp == 0 && (R * Wp) % 128 == 0; }
+inline int wide_unit_rows(int R, int Wp) { return wide_split(R, Wp) ? 128 / Wp : R; }
+inline size_t wide_stg_buf_bytes(int R, int Wp, int TW) {
+  return (static_cast<size_t>(wide_unit_rows(R, Wp)) * TW * 128 + 1023) / 1024 * 1024;
+}
+constexpr int kMinWSlots = 2;
+// shared memory without the weight ring
+inline size_t wide_smem_fixed(int R, int Wp, int TW) {
   const size_t in = (kInBufs * wide_in_buf_bytes(R, Wp) + 1023) / 1024 * 1024;
-  const size_t w = static_cast<size_t>(kWSlots) * (cg == 2 ? 64 : 128) * 128;
-  return in + w + 2 * wide_stg_buf_bytes(R, TW) + 3 * kNOut * 4 + 256 + 1024;
+  return in + 2 * wide_stg_buf_bytes(R, Wp, TW) + 3 * kNOut * 4 + 512 + 1024;
+}
+inline size_t wide_chunk_bytes(int cg, int tpg) { return static_cast<size_t>(cg == 2 ? 64 : 128) * 128 * tpg; }
+inline int wide_slots(int cg, int tpg, int R, int Wp, int TW, size_t cap) {
+  const size_t fixed = wide_smem_fixed(R, Wp, TW);
+  if (fixed + kMinWSlots * wide_chunk_bytes(cg, tpg) > cap) return 0;
+  const size_t n = (cap - fixed) / wide_chunk_bytes(cg, tpg);
+  return n > kMaxWSlots ? kMaxWSlots : static_cast<int>(n);
 }
 
 template <int kCg>
@@ -518,6 +580,13 @@ pack_conv3x3_wide_kernel(const float* __restrict__ w, int n_layers, int Cout, in
 }  // namespace
 }  // namespace fd
 
+extern "C" FD_API int fd_debug_wide_timing(unsigned long long* out, int reset) {
+  unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  cudaError_t e = cudaMemcpyFromSymbol(out, fd::g_wide_dbg, sizeof(z));
+  if (e == cudaSuccess && reset) e = cudaMemcpyToSymbol(fd::g_wide_dbg, z, sizeof(z));
+  return static_cast<int>(e);
+}
+
 extern "C" int fd_pack_conv3x3_wide(const float* w, int n_layers, int Cout, int Cin, fd_bf16* w_fwd, fd_bf16* w_dgrad,
                                     void* stream) {
   using namespace fd;
@@ -555,6 +624,7 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
 
   // Tiling: TW <= 62 output columns, R rows with R * (TW + 2) <= 256 GEMM rows (two 128-row blocks = 2 x 128 TMEM columns,
   // double buffered).  Cost model: tensor time of the padded blocks times the number of waves over the CTA groups.
+  const int tpg = (flags & FD_CONV_1X1) ? 1 : 3;
   int bestR = 0, bestTW = 0;
   double best = 1e30;
   const int min_tw_tiles = (W + 61) / 62;
@@ -565,7 +635,7 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
     for (int R = 1; R <= H && R + 2 <= 256; ++R) {
       const int nblk = (R * Wp + 127) / 128;
       if (nblk > 2) break;
-      if (wide_smem_for(cg, R, Wp, TW) > smem_cap) break;
+      if (wide_slots(cg, tpg, R, Wp, TW, smem_cap) == 0) break;
       const long tiles = static_cast<long>(B) * ((H + R - 1) / R) * tw_tiles;
       const long waves = (tiles + nsm - 1) / nsm;
       const double cost = waves * (2400.0 * nblk + 600.0);
@@ -585,10 +655,17 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
   p.tap_hi = (flags & FD_CONV_1X1) ? 5 : 9;
   p.in_bytes = static_cast<uint32_t>((bestR + 2) * p.Wp * 128);
   p.in_buf_bytes = static_cast<uint32_t>(wide_in_buf_bytes(bestR, p.Wp));
-  p.stg_bytes = static_cast<uint32_t>(bestR * bestTW * 128);
-  p.stg_buf_bytes = static_cast<uint32_t>(wide_stg_buf_bytes(bestR, bestTW));
+  p.split = wide_split(bestR, p.Wp) ? 1 : 0;
+  p.rpb = wide_unit_rows(bestR, p.Wp);
+  p.units = p.split ? p.nblk : 1;
+  p.stg_bytes = static_cast<uint32_t>(p.rpb * bestTW * 128);
+  p.stg_buf_bytes = static_cast<uint32_t>(wide_stg_buf_bytes(bestR, p.Wp, bestTW));
+  p.tpg = tpg;
+  p.ngrp = (flags & FD_CONV_1X1) ? 1 : 3;
+  p.wslots = wide_slots(cg, tpg, bestR, p.Wp, bestTW, smem_cap);
   p.inv_wp = static_cast<uint32_t>((65536 + p.Wp - 1) / p.Wp);
   p.flags = flags;
+  { static const int dbg = [] { const char* d = getenv("FD_WIDE_TIMING"); return d ? atoi(d) : 0; }(); p.dbg = dbg; }
   p.slope = slope;
   p.bias = bias;
   p.has_res = (residual && residual[0] && residual[1]) ? 1 : 0;
@@ -613,12 +690,12 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
   if (rc != FD_OK) return rc;
   fd_bf16* const* staged = has_out ? out : out2;
   for (int g = 0; g < 2; ++g) {
-    rc = make_tmap_nhwc_bf16(&maps.out[g], staged[g], B, H, W, kC, bestTW, bestR);
+    rc = make_tmap_nhwc_bf16(&maps.out[g], staged[g], B, H, W, kC, bestTW, p.rpb);
     if (rc != FD_OK) return rc;
-    rc = make_tmap_nhwc_bf16(&maps.res[g], p.has_res ? residual[g] : x[0], B, H, W, kC, bestTW, bestR);
+    rc = make_tmap_nhwc_bf16(&maps.res[g], p.has_res ? residual[g] : x[0], B, H, W, kC, bestTW, p.rpb);
     if (rc != FD_OK) return rc;
   }
-  const size_t smem = wide_smem_for(cg, bestR, p.Wp, bestTW);
+  const size_t smem = wide_smem_fixed(bestR, p.Wp, bestTW) + p.wslots * wide_chunk_bytes(cg, tpg);
   return cg == 2 ? launch_wide<2>(maps, p, smem, static_cast<cudaStream_t>(stream))
                  : launch_wide<1>(maps, p, smem, static_cast<cudaStream_t>(stream));
 }

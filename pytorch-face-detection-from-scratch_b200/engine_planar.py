@@ -13,9 +13,11 @@ they are:
 * the stem runs once per output plane (the bf16 image cache is written by the first launch), the head on the
   64-channel head kernels plane by plane (partial logits summed before the sigmoid; tensor-core backward per plane).
 
-This is the FUNCTIONAL path for the wide models (same parity bar as the 64-channel engine; one more bf16 rounding per
-convolution for the chained partial sum) -- about 4x the launches of the fused 64-channel step and no fused block
-chain.  A native 128-channel instantiation (N = 128 MMAs, streamed weights) is the next kernel.
+For G = 2 or 4 the forward and input-gradient convolutions run on the NATIVE wide kernel instead (``fd_conv3x3_wide``:
+one launch per layer and group of 128 output channels, tcgen05.mma.cta_group::2 with N = 128, partial sums over the input
+planes in TMEM, activation / mask / dropout / skip fused into its epilogue -- ``use_wide``); the chained 64-channel path
+above stays as the fallback for other widths (one more bf16 rounding per convolution for the chained partial sum).  The
+weight gradients still run per (gradient plane, input plane) pair on ``fd_conv3x3_wgrad_multi``.
 Parameters stay ordinary ``nn.Parameter`` tensors; gradients land in one flat fp32 buffer (``gflat``, the all-reduce
 unit) of which every ``p.grad`` is a view.
 """
@@ -86,7 +88,7 @@ class _PPlan:
             b.inp = cur
             k0 = run_of[k]
             i = k - k0
-            b.T, b.T2 = planes(H, W), planes(H, W)
+            b.T, b.T2 = (planes(H, W), planes(H, W)) if not eng.use_wide else (None, None)
             b.a = [self.XA[k0][g][2 * i + 1] for g in range(G)]
             b.ma = masks(H, W) if train else [None] * G
             b.mb = masks(H, W) if train else [None] * G
@@ -106,7 +108,7 @@ class _PPlan:
                 b.gs = planes(b.H, b.W) if b.pool else None
                 b.gp1 = [self.GP[k0][g][2 * i] for g in range(G)]
                 b.gp2 = [self.GP[k0][g][2 * i + 1] for g in range(G)]
-                b.U = planes(b.H, b.W)
+                b.U = planes(b.H, b.W) if not eng.use_wide else None
             self.blocks.append(b)
             cur = b.out
         self.y = torch.empty((B, 5, eng.So_h, eng.So_w), dtype=F32, device=device)
@@ -159,6 +161,7 @@ class PlanarEngine:
         self.n_flat = off
         self.device = None
         self.gflat = None
+        self.use_wide = self.G in (2, 4)      # fd_conv3x3_wide: groups of 128 output channels, <= 4 input planes
         self.plans: Dict[tuple, _PPlan] = {}
 
     # ------------------------------------------------------------------ parameters / gradients
@@ -193,6 +196,9 @@ class PlanarEngine:
             self.gb3 = torch.zeros((L, G, 64), dtype=F32, device=dev)
             self.w_fwd = torch.empty((L * G * G, 9, 64, 64), dtype=BF16, device=dev)
             self.w_dgrad = torch.empty((L * G * G, 9, 64, 64), dtype=BF16, device=dev)
+            if self.use_wide:             # [layer][group of 128 couts][input plane][tap][128][64]
+                self.w_fwd_wide = torch.empty((L, G // 2, G, 9, 128, 64), dtype=BF16, device=dev)
+                self.w_dgrad_wide = torch.empty((L, G // 2, G, 9, 128, 64), dtype=BF16, device=dev)
             self.sides = [torch.cuda.Stream(device=dev) for _ in range(self.G - 1)]
             self.plans.clear()
         self.params = params
@@ -231,8 +237,12 @@ class PlanarEngine:
             for c in ("conv1", "conv2"):
                 ws.append(P[f"residual_blocks.{k}.{c}.weight"].detach())
                 bs.append(P[f"residual_blocks.{k}.{c}.bias"].detach())
-        w3 = torch.stack(ws).float().view(L, G, 64, G, 64, 3, 3).permute(0, 1, 3, 2, 4, 5, 6).contiguous()
-        ops.pack_conv3x3(w3.view(L * G * G, 64, 64, 3, 3), self.w_fwd, self.w_dgrad)
+        w_all = torch.stack(ws).float()
+        if self.use_wide:
+            ops.pack_conv3x3_wide(w_all, self.w_fwd_wide, self.w_dgrad_wide)
+        else:
+            w3 = w_all.view(L, G, 64, G, 64, 3, 3).permute(0, 1, 3, 2, 4, 5, 6).contiguous()
+            ops.pack_conv3x3(w3.view(L * G * G, 64, 64, 3, 3), self.w_fwd, self.w_dgrad)
         self.b3 = torch.stack(bs).float().view(L, G, 64).contiguous()
 
     # ------------------------------------------------------------------ forward
@@ -251,6 +261,27 @@ class PlanarEngine:
             ops.conv3x3(srcs[h], wsel[self._sub(layer, g, h)], **kw)
             prev = dst
         return prev
+
+    def _pairs(self, planes, go):
+        return None if planes is None or planes[0] is None else [planes[2 * go], planes[2 * go + 1]]
+
+    def _block_forward_wide(self, pl, k, blk, cur):
+        """models/PoolResnet.py:35-42 for one block on fd_conv3x3_wide: one launch per convolution and group of 128 couts."""
+        G = self.G
+        drop = [pl.drop[k, g] for g in range(G)] if pl.drop is not None else None
+        for go in range(G // 2):
+            ops.conv3x3_wide(cur, self.w_fwd_wide[2 * k, go], bias=self.b3[2 * k, 2 * go:2 * go + 2].reshape(-1),
+                             slope=self.slope, lrelu=True, mask_out=self._pairs(blk.ma, go), out=self._pairs(blk.a, go))
+        for go in range(G // 2):
+            ops.conv3x3_wide(blk.a, self.w_fwd_wide[2 * k + 1, go], bias=self.b3[2 * k + 1, 2 * go:2 * go + 2].reshape(-1),
+                             slope=self.slope, lrelu=True, chan_scale=self._pairs(drop, go), residual=self._pairs(cur, go),
+                             mask_out=self._pairs(blk.mb, go), out=self._pairs(blk.s, go))
+        if blk.pool:
+            main = self._fork()
+            for g in range(G):
+                with self._on(main, g):
+                    ops.maxpool2x2_fwd(blk.s[g], blk.out[g], blk.amax[g])
+            self._join(main)
 
     def forward(self, x, train: bool, dropout: bool = False):
         B = x.shape[0]
@@ -272,6 +303,10 @@ class PlanarEngine:
                          x_cache=pl.x_cache if g == 0 else None)
         cur = pl.act0
         for k, blk in enumerate(pl.blocks):
+            if self.use_wide:
+                self._block_forward_wide(pl, k, blk, cur)
+                cur = blk.out
+                continue
             main = self._fork()
             for g in range(G):
                 with self._on(main, g):
@@ -333,33 +368,17 @@ class PlanarEngine:
                         ops.grad_mask(blk.G[g], self.slope, blk.mb[g], cs, blk.gp2[g])
             self._join(main)
             GS = blk.gs if blk.pool else blk.G
-            # gp1[h] = (sum_g dgrad(gp2[g], W2[g][h])) * lrelu'(a[h])
-            main = self._fork()
-            for h in range(G):
-                with self._on(main, h):
-                    prev = None
-                    for g in range(G):
-                        w = self.w_dgrad[self._sub(L2, g, h)]
-                        if g < G - 1:
-                            dst = blk.U[h] if (g % 2 == 0) else blk.T[h]
-                            ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, out=dst)
-                            prev = dst
-                        else:
-                            ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, mask_in=blk.ma[h],
-                                        out2=blk.gp1[h])
-            self._join(main)
-            # G_{k-1}[h] = sum_g dgrad(gp1[g], W1[g][h]) + GS[h]
             gprev = pl.blocks[k - 1].G if k > 0 else pl.g_stem
-            main = self._fork()
-            for h in range(G):
-                with self._on(main, h):
-                    prev = GS[h]
-                    for g in range(G):
-                        w = self.w_dgrad[self._sub(L1, g, h)]
-                        dst = gprev[h] if g == G - 1 else (blk.U[h] if (g % 2 == 0) else blk.T[h])
-                        ops.conv3x3(blk.gp1[g], w, slope=self.slope, residual=prev, out=dst)
-                        prev = dst
-            self._join(main)
+            if self.use_wide:
+                # gp1 = dgrad(gp2, W2) * lrelu'(a);  G_{k-1} = dgrad(gp1, W1) + GS  -- one launch per group of 128 channels
+                for go in range(G // 2):
+                    ops.conv3x3_wide(blk.gp2, self.w_dgrad_wide[L2, go], slope=self.slope, mask_in=self._pairs(blk.ma, go),
+                                     out2=self._pairs(blk.gp1, go))
+                for go in range(G // 2):
+                    ops.conv3x3_wide(blk.gp1, self.w_dgrad_wide[L1, go], slope=self.slope, residual=self._pairs(GS, go),
+                                     out=self._pairs(gprev, go))
+            else:
+                self._block_dgrad_planes(blk, L1, L2, GS, gprev)
             # weight / bias gradients: once per run, when the gp1 / gp2 of all its blocks are final
             if k in pl.XA:
                 n3 = 9 * 64 * 64
@@ -378,6 +397,35 @@ class PlanarEngine:
         self.section(self.gflat, "w3").copy_(
             self.dw_sub.view(L, G, G, 64, 64, 3, 3).permute(0, 1, 3, 2, 4, 5, 6).reshape(L, self.F, self.F, 3, 3))
         self.section(self.gflat, "b3").copy_(self.gb3.view(L, self.F))
+
+    def _block_dgrad_planes(self, blk, L1, L2, GS, gprev):
+        G = self.G
+        # gp1[h] = (sum_g dgrad(gp2[g], W2[g][h])) * lrelu'(a[h])
+        main = self._fork()
+        for h in range(G):
+            with self._on(main, h):
+                prev = None
+                for g in range(G):
+                    w = self.w_dgrad[self._sub(L2, g, h)]
+                    if g < G - 1:
+                        dst = blk.U[h] if (g % 2 == 0) else blk.T[h]
+                        ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, out=dst)
+                        prev = dst
+                    else:
+                        ops.conv3x3(blk.gp2[g], w, slope=self.slope, residual=prev, mask_in=blk.ma[h],
+                                    out2=blk.gp1[h])
+        self._join(main)
+        # G_{k-1}[h] = sum_g dgrad(gp1[g], W1[g][h]) + GS[h]
+        main = self._fork()
+        for h in range(G):
+            with self._on(main, h):
+                prev = GS[h]
+                for g in range(G):
+                    w = self.w_dgrad[self._sub(L1, g, h)]
+                    dst = gprev[h] if g == G - 1 else (blk.U[h] if (g % 2 == 0) else blk.T[h])
+                    ops.conv3x3(blk.gp1[g], w, slope=self.slope, residual=prev, out=dst)
+                    prev = dst
+        self._join(main)
 
     def train_step(self, x, gt, dropout: bool = True, allreduce=None, optimizer=None):
         pl = self.forward(x, train=True, dropout=dropout)
