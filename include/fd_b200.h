@@ -105,6 +105,22 @@ FD_API int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* w_pa
  * Either output may be NULL.  Cout (w_fwd) / Cin (w_dgrad) must be multiples of 128, the other a multiple of 64. */
 FD_API int fd_pack_conv3x3_wide(const float* w, int n_layers, int Cout, int Cin, fd_bf16* w_fwd, fd_bf16* w_dgrad,
                          void* stream);
+/* The same for 1x1 convolutions, w: [n_layers][Cout][Cin][1][1] (models/SSD.py:23-30 skip, models/SeparableCNN.py:13-19):
+ * only the centre tap (tap 4) of the packed layouts is written, the others are left as they are -- for FD_CONV_1X1. */
+FD_API int fd_pack_conv1x1_wide(const float* w, int n_layers, int Cout, int Cin, fd_bf16* w_fwd, fd_bf16* w_dgrad,
+                         void* stream);
+
+/* Weight gradient of the wide convolution: ONE 128 x 128 channel block of dW per call -- input planes x0, x1 (channels
+ * 128hh .. 128hh+127) against gradient planes g0, g1 (output channels 128gg .. 128gg+127), each holding `nprob` stacked
+ * [B,H,W,64] bf16 tensors (problem q = layer q of a run of equal-shape layers).  tcgen05.mma.cta_group::2: a CTA pair loads
+ * one x plane and one g plane each and issues M=256, N=128 instructions (two passes: taps 0..7, then tap 8 -- TMEM holds
+ * eight taps of a 128 x 64 block).  The four 64 x 64 sub-blocks are ACCUMULATED into the packed layout of fd_conv3x3_wgrad:
+ * dw_packed + sub_off[2*r + c] (+ q * dw_stride) is the [9][64 ci][64 co] fp32 block of (x plane r, g plane c); sub_off is a
+ * HOST array of 4 element offsets (multiples of 64).  dbias0 / dbias1 (nullable): [64] fp32 bias gradients of g0 / g1
+ * (+ q * dbias_stride), accumulated. */
+FD_API int fd_conv3x3_wgrad_wide(const fd_bf16* x0, const fd_bf16* x1, const fd_bf16* g0, const fd_bf16* g1, int nprob, int B,
+                          int H, int W, float* dw_packed, const long* sub_off, long dw_stride, float* dbias0,
+                          float* dbias1, long dbias_stride, int flags, void* stream);
 
 /* Weight gradient of the same convolution (replaces the wgrad half of autograd's
  * conv2d backward for models/PoolResnet.py:35,37).

@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libfd_b200.so")
-SOURCES = ["fd_host.cu", "conv3x3_tc.cu", "conv3x3_wide.cu", "resblock_chain.cu", "wgrad3x3_tc.cu", "layers.cu", "yolo_kernels.cu", "ssd_kernels.cu", "stem_tc.cu", "comm.cu", "sepblock.cu", "stem_s2_tc.cu", "head_tc.cu", "pw_gemm_tc.cu", "mbv3_kernels.cu", "mbv3_stem_tc.cu", "misc_kernels.cu", "ssd_head.cu"]
+SOURCES = ["fd_host.cu", "conv3x3_tc.cu", "conv3x3_wide.cu", "resblock_chain.cu", "wgrad3x3_tc.cu", "wgrad3x3_wide.cu", "layers.cu", "yolo_kernels.cu", "ssd_kernels.cu", "stem_tc.cu", "comm.cu", "sepblock.cu", "stem_s2_tc.cu", "head_tc.cu", "pw_gemm_tc.cu", "mbv3_kernels.cu", "mbv3_stem_tc.cu", "misc_kernels.cu", "ssd_head.cu"]
 HEADERS = ["fd_host.h", "fd_ptx.cuh", os.path.join("..", "..", "include", "fd_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

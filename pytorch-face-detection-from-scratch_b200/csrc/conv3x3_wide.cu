@@ -543,36 +543,43 @@ int launch_wide(const WideMaps& maps, const WideParams& p, size_t smem, cudaStre
   return launch_status();
 }
 
-// [Cout, Cin, 3, 3] fp32 (torch) -> the two streamed bf16 packings.  One thread per output element.
+// [Cout, Cin, k, k] fp32 (torch; k = 3, or k = 1: only the centre tap is written) -> the two streamed bf16 packings.
+// One thread per destination element (coalesced writes, gathered reads: the weights are L2 resident).
 //   forward : wf[(co / 128)][ci / 64][tap][co % 128][ci % 64]
 //   dgrad   : wd[(ci / 128)][co / 64][8 - tap][ci % 128][co % 64]        (flipped taps, roles of ci / co swapped)
 __global__ void __launch_bounds__(256)
-pack_conv3x3_wide_kernel(const float* __restrict__ w, int n_layers, int Cout, int Cin, __nv_bfloat16* __restrict__ wf,
-                         __nv_bfloat16* __restrict__ wd) {
+pack_conv_wide_kernel(const float* __restrict__ w, int n_layers, int Cout, int Cin, int ksize, __nv_bfloat16* __restrict__ wf,
+                      __nv_bfloat16* __restrict__ wd) {
   pdl_trigger();
   pdl_wait();
-  const long per_layer = static_cast<long>(Cout) * Cin * 9;
-  const long total = per_layer * n_layers;
+  const int kk = ksize * ksize;
+  const long src_layer = static_cast<long>(Cout) * Cin * kk;
+  const long dst_layer = static_cast<long>(Cout) * Cin * 9;
+  const long total = static_cast<long>(Cout) * Cin * kk * n_layers;
   for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * 256L) {
-    const long l = i / per_layer;
-    const long r = i - l * per_layer;
-    if (wf) {        // i enumerates the DESTINATION order of wf: coalesced writes, gathered reads (weights are L2 resident)
+    const long l = i / src_layer;
+    const long r = i - l * src_layer;
+    if (wf) {
       const int ci_lo = static_cast<int>(r % 64);
       const int co_lo = static_cast<int>((r / 64) % 128);
-      const int t = static_cast<int>((r / (64 * 128)) % 9);
-      const int gi = static_cast<int>((r / (64 * 128 * 9)) % (Cin / 64));
-      const int go = static_cast<int>(r / (64L * 128 * 9 * (Cin / 64)));
+      const int tt = static_cast<int>((r / (64 * 128)) % kk);
+      const int gi = static_cast<int>((r / (64L * 128 * kk)) % (Cin / 64));
+      const int go = static_cast<int>(r / (64L * 128 * kk * (Cin / 64)));
       const int co = go * 128 + co_lo, ci = gi * 64 + ci_lo;
-      wf[i] = __float2bfloat16(__ldg(w + l * per_layer + (static_cast<long>(co) * Cin + ci) * 9 + t));
+      const int t = ksize == 3 ? tt : 4;
+      wf[l * dst_layer + (((static_cast<long>(go) * (Cin / 64) + gi) * 9 + t) * 128 + co_lo) * 64 + ci_lo] =
+          __float2bfloat16(__ldg(w + l * src_layer + (static_cast<long>(co) * Cin + ci) * kk + tt));
     }
     if (wd) {
       const int co_lo = static_cast<int>(r % 64);
       const int ci_lo = static_cast<int>((r / 64) % 128);
-      const int t = static_cast<int>((r / (64 * 128)) % 9);
-      const int go = static_cast<int>((r / (64 * 128 * 9)) % (Cout / 64));
-      const int gi = static_cast<int>(r / (64L * 128 * 9 * (Cout / 64)));
+      const int tt = static_cast<int>((r / (64 * 128)) % kk);
+      const int go = static_cast<int>((r / (64L * 128 * kk)) % (Cout / 64));
+      const int gi = static_cast<int>(r / (64L * 128 * kk * (Cout / 64)));
       const int co = go * 64 + co_lo, ci = gi * 128 + ci_lo;
-      wd[i] = __float2bfloat16(__ldg(w + l * per_layer + (static_cast<long>(co) * Cin + ci) * 9 + (8 - t)));
+      const int t = ksize == 3 ? tt : 4;               // destination tap; the source tap is the flipped one
+      wd[l * dst_layer + (((static_cast<long>(gi) * (Cout / 64) + go) * 9 + t) * 128 + ci_lo) * 64 + co_lo] =
+          __float2bfloat16(__ldg(w + l * src_layer + (static_cast<long>(co) * Cin + ci) * kk + (ksize == 3 ? 8 - tt : 0)));
     }
   }
 }
@@ -587,19 +594,29 @@ extern "C" FD_API int fd_debug_wide_timing(unsigned long long* out, int reset) {
   return static_cast<int>(e);
 }
 
-extern "C" int fd_pack_conv3x3_wide(const float* w, int n_layers, int Cout, int Cin, fd_bf16* w_fwd, fd_bf16* w_dgrad,
-                                    void* stream) {
+static int pack_conv_wide(const float* w, int n_layers, int Cout, int Cin, int ksize, fd_bf16* w_fwd, fd_bf16* w_dgrad,
+                          void* stream) {
   using namespace fd;
   if (!w || n_layers <= 0 || (!w_fwd && !w_dgrad)) return FD_EINVAL;
   if (Cout <= 0 || Cin <= 0 || Cout % 64 != 0 || Cin % 64 != 0) return FD_EUNSUPPORTED;
   if ((w_fwd && Cout % 128 != 0) || (w_dgrad && Cin % 128 != 0)) return FD_EUNSUPPORTED;
-  const long total = static_cast<long>(n_layers) * Cout * Cin * 9;
+  const long total = static_cast<long>(n_layers) * Cout * Cin * ksize * ksize;
   const long blocks = (total + 255) / 256;
-  launch_k(pack_conv3x3_wide_kernel, dim3(static_cast<unsigned>(blocks < 148 * 16 ? blocks : 148 * 16)), dim3(256), 0,
-           static_cast<cudaStream_t>(stream), w, n_layers, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(w_fwd),
+  launch_k(pack_conv_wide_kernel, dim3(static_cast<unsigned>(blocks < 148 * 16 ? blocks : 148 * 16)), dim3(256), 0,
+           static_cast<cudaStream_t>(stream), w, n_layers, Cout, Cin, ksize, reinterpret_cast<__nv_bfloat16*>(w_fwd),
            reinterpret_cast<__nv_bfloat16*>(w_dgrad));
   count_launch();
   return launch_status();
+}
+
+extern "C" int fd_pack_conv3x3_wide(const float* w, int n_layers, int Cout, int Cin, fd_bf16* w_fwd, fd_bf16* w_dgrad,
+                                    void* stream) {
+  return pack_conv_wide(w, n_layers, Cout, Cin, 3, w_fwd, w_dgrad, stream);
+}
+
+extern "C" int fd_pack_conv1x1_wide(const float* w, int n_layers, int Cout, int Cin, fd_bf16* w_fwd, fd_bf16* w_dgrad,
+                                    void* stream) {
+  return pack_conv_wide(w, n_layers, Cout, Cin, 1, w_fwd, w_dgrad, stream);
 }
 
 extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* w_packed, int B, int H, int W,
@@ -620,7 +637,7 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
   static const int cg_env = [] { const char* e = getenv("FD_WIDE_CTA_GROUP"); return e ? atoi(e) : 2; }();
   const int cg = cg_env == 1 ? 1 : 2;
   const int nsm = sm_count();
-  const size_t smem_cap = 227 * 1024;
+  const size_t smem_cap = 227 * 1024 - 64;     // dynamic shared memory: the kernel also has 16 bytes of static (timing) state
 
   // Tiling: TW <= 62 output columns, R rows with R * (TW + 2) <= 256 GEMM rows (two 128-row blocks = 2 x 128 TMEM columns,
   // double buffered).  Cost model: tensor time of the padded blocks times the number of waves over the CTA groups.

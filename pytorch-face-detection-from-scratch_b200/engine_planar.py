@@ -383,6 +383,16 @@ class PlanarEngine:
             if k in pl.XA:
                 n3 = 9 * 64 * 64
                 dwp_flat, gb3_flat = self.dwp.view(-1), self.gb3.view(-1)
+                if self.use_wide:       # one 128 x 128 channel block of dW per call (fd_conv3x3_wgrad_wide)
+                    for gg in range(G // 2):
+                        for hh in range(G // 2):
+                            sub_off = [self._sub(2 * k, 2 * gg + c, 2 * hh + r) * n3 for r in range(2) for c in range(2)]
+                            ops.conv3x3_wgrad_wide(pl.XA[k][2 * hh], pl.XA[k][2 * hh + 1], pl.GP[k][2 * gg], pl.GP[k][2 * gg + 1],
+                                                   dwp_flat, sub_off, dw_stride=G * G * n3,
+                                                   dbias0=gb3_flat[(2 * k * G + 2 * gg) * 64:] if hh == 0 else None,
+                                                   dbias1=gb3_flat[(2 * k * G + 2 * gg + 1) * 64:] if hh == 0 else None,
+                                                   dbias_stride=G * 64)
+                    continue
                 for g in range(G):
                     for h in range(G):
                         first = self._sub(2 * k, g, h)

@@ -13,6 +13,10 @@ tcgen05 kernels instantiated for 64 channels are reused unchanged:
   ``fd_act_mask`` / ``fd_grad_mask``;
 * the 1x1 skip convolutions are ``fd_conv3x3`` in centre-tap mode (``FD_CONV_1X1``), their weight gradients the centre
   tap of ``fd_conv3x3_wgrad``;
+* layers with at least 128 output channels (the four ``continue_layers`` blocks: 64 -> 128, 128 -> 256, 256 -> 256 -- 80 %
+  of the model's FLOPs) run on ``fd_conv3x3_wide`` instead: one launch per group of 128 output channels
+  (tcgen05.mma.cta_group::2, N = 128, the sum over input planes in TMEM, epilogue fused), packed straight from the
+  un-padded parameter views (``use_wide``); their weight gradients stay on the 64-channel ``fd_conv3x3_wgrad``;
 * parameters live un-padded in ONE flat fp32 buffer ``pflat`` (the optimizer / data-parallel all-reduce unit; every
   ``nn.Parameter`` is a view), scattered into the zero-padded packing buffer by one ``fd_index_copy_f32``; gradients are
   gathered back by one ``fd_index_copy_f32`` into ``gflat`` (every ``p.grad`` is a view).
@@ -131,6 +135,7 @@ class SSDEngine:
         self.n_pad = self.pad_stem_b_off + 64 + 4      # + a spare zero the alignment gaps of the un-padded buffer map to
         self.device = None
         self.pflat = self.gflat = None
+        self.use_wide = True           # fd_conv3x3_wide for layers whose output (forward) / input (dgrad) is 128k channels
         self.plans: Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------ parameters
@@ -188,6 +193,13 @@ class SSDEngine:
             self.dwp = torch.zeros((self.n_sub, 9 * 64 * 64), dtype=F32, device=dev)
             self.w_fwd = torch.empty((self.n_sub, 9, 64, 64), dtype=BF16, device=dev)
             self.w_dgrad = torch.empty((self.n_sub, 9, 64, 64), dtype=BF16, device=dev)
+            # wide packings [group of 128][input plane][tap][128][64] of the layers the wide kernel serves
+            self.wide_f, self.wide_d = {}, {}
+            for (pre, cout, cin, go, gi, first, is1) in self.conv_layers:
+                if go % 2 == 0 and gi <= 4:
+                    self.wide_f[pre] = torch.zeros((go // 2, gi, 9, 128, 64), dtype=BF16, device=dev)
+                if gi % 2 == 0 and go <= 4:
+                    self.wide_d[pre] = torch.zeros((gi // 2, go, 9, 128, 64), dtype=BF16, device=dev)
             self._build_index(dev)
             self.pconv = torch.zeros(self.conv_pos.numel(), dtype=F32, device=dev)
             self.gconv = torch.zeros(self.conv_pos.numel(), dtype=F32, device=dev)
@@ -211,6 +223,19 @@ class SSDEngine:
         ops.index_copy(self.pconv, self.pflat, self.conv_pos, scatter=False)
         ops.index_copy(self.ppad, self.pconv, self.index_conv, scatter=True)
         ops.pack_conv3x3(self.ppad[:self.pad_b3_off].view(self.n_sub, 64, 64, 3, 3), self.w_fwd, self.w_dgrad)
+        if self.use_wide:
+            for (pre, cout, cin, go, gi, first, is1) in self.conv_layers:
+                if pre in self.wide_f or pre in self.wide_d:
+                    ops.pack_conv3x3_wide(self._view(self.pflat, pre + ".weight"), self.wide_f.get(pre), self.wide_d.get(pre))
+
+    def _bias2(self, pre, gg):
+        """bias of output planes 2gg, 2gg+1 (128 contiguous floats of the padded buffer)"""
+        r = self.bias_row[pre] + 2 * gg
+        return self.ppad[self.pad_b3_off + r * 64:self.pad_b3_off + (r + 2) * 64]
+
+    @staticmethod
+    def _pair(planes, gg):
+        return None if planes is None or planes[0] is None else [planes[2 * gg], planes[2 * gg + 1]]
 
     def _bias(self, pre, g):
         r = self.bias_row[pre] + g
@@ -317,6 +342,30 @@ class SSDEngine:
             drop = pl["drop"][i] if pl["drop"] is not None else [None] * b.go
             ma = d.get("ma") or [None] * b.go
             mb = d.get("mb") or [None] * b.go
+            pre1, pre2, pres = b.name + ".conv1", b.name + ".conv2", b.name + ".pointwise_conv_skip"
+            if self.use_wide and pre1 in self.wide_f and pre2 in self.wide_f:
+                for gg in range(b.go // 2):
+                    if b.has_skip_conv:
+                        ops.conv3x3_wide(cur, self.wide_f[pres][gg], bias=self._bias2(pres, gg), slope=self.slope,
+                                         out=self._pair(d["skip"], gg), flags=ops.CONV_1X1)
+                    ops.conv3x3_wide(cur, self.wide_f[pre1][gg], bias=self._bias2(pre1, gg), slope=self.slope, lrelu=True,
+                                     mask_out=self._pair(ma, gg), out=self._pair(d["a"], gg))
+                skip = d["skip"] if b.has_skip_conv else cur
+                for gg in range(b.go // 2):
+                    ops.conv3x3_wide(d["a"], self.wide_f[pre2][gg], bias=self._bias2(pre2, gg), slope=self.slope, lrelu=True,
+                                     chan_scale=self._pair(drop, gg), residual=self._pair(skip, gg),
+                                     mask_out=self._pair(mb, gg), out=self._pair(d["s"], gg))
+                if b.pool:
+                    for g in range(b.go):
+                        ops.maxpool2x2_fwd(d["s"][g], d["out"][g], d["amax"][g] if train else None)
+                cur = d["out"]
+                if i >= self.n_fe:
+                    w = self._view(self.pflat, f"extracting_layers.{hi}.0.weight")
+                    bb = self._view(self.pflat, f"extracting_layers.{hi}.0.bias")
+                    ops.ssd_head_fwd(cur, w, bb, mult, priors, off, pl["y"])
+                    off += self.head_hw[hi][0] * self.head_hw[hi][1]
+                    hi += 1
+                continue
             if b.has_skip_conv:
                 for g in range(b.go):
                     self._conv_sum(cur, self.w_fwd, b.name + ".pointwise_conv_skip", g, b.gi,
@@ -392,7 +441,11 @@ class SSDEngine:
                 GS = G
             # ---- gp1[h] = (sum_g dgrad(gp2[g], W2[g][h])) * lrelu'(a[h])
             pre2, pre1, pres = b.name + ".conv2", b.name + ".conv1", b.name + ".pointwise_conv_skip"
-            for h in range(b.go):
+            wide2 = self.use_wide and pre2 in self.wide_d
+            for hh in range(b.go // 2 if wide2 else 0):
+                ops.conv3x3_wide(d["gp2"], self.wide_d[pre2][hh], slope=self.slope, mask_in=self._pair(d["ma"], hh),
+                                 out2=self._pair(d["gp1"], hh))
+            for h in range(0 if wide2 else b.go):
                 prev = None
                 for g in range(b.go):
                     wd = self.w_dgrad[self._sub(pre2, g, h)]
@@ -409,7 +462,19 @@ class SSDEngine:
                 extra = pl["head_dx"][i - 1 - self.n_fe] if (i - 1) >= self.n_fe else None
             else:
                 target, extra = pl["g_stem"], None
-            for h in range(b.gi):
+            wide1 = self.use_wide and pre1 in self.wide_d and (not b.has_skip_conv or pres in self.wide_d)
+            for hh in range(b.gi // 2 if wide1 else 0):
+                final = self._pair(target, hh) if extra is None else self._pair(d["U"], hh)
+                if b.has_skip_conv:
+                    ops.conv3x3_wide(d["gp1"], self.wide_d[pre1][hh], slope=self.slope, out=self._pair(d["U2"], hh))
+                    ops.conv3x3_wide(GS, self.wide_d[pres][hh], slope=self.slope, residual=self._pair(d["U2"], hh), out=final,
+                                     flags=ops.CONV_1X1)
+                else:
+                    ops.conv3x3_wide(d["gp1"], self.wide_d[pre1][hh], slope=self.slope, residual=self._pair(GS, hh), out=final)
+                if extra is not None:       # + head gradient of the previous scale
+                    for h in (2 * hh, 2 * hh + 1):
+                        ops.act_mask(d["U"][h], 1.0, None, extra[h], None, target[h])
+            for h in range(0 if wide1 else b.gi):
                 chain = [(d["gp1"][g], self.w_dgrad[self._sub(pre1, g, h)], 0) for g in range(b.go)]
                 if b.has_skip_conv:
                     chain += [(GS[g], self.w_dgrad[self._sub(pres, g, h)], ops.CONV_1X1) for g in range(b.go)]
@@ -427,11 +492,31 @@ class SSDEngine:
                 if extra is not None:       # + head gradient of the previous scale: G_prev = prev + head_dx
                     ops.act_mask(prev, 1.0, None, extra[h], None, target[h])
             # ---- weight / bias gradients of the block
+            n3 = 9 * 64 * 64
+            dwp_flat = self.dwp.view(-1)
+
+            def wgrad_wide(pre, xs, gs, gi_, go_):
+                """128 x 128 channel blocks of the weight gradient of layer `pre` (fd_conv3x3_wgrad_wide)"""
+                for gg in range(go_ // 2):
+                    for hh in range(gi_ // 2):
+                        sub_off = [self._sub(pre, 2 * gg + c, 2 * hh + r) * n3 for r in range(2) for c in range(2)]
+                        ops.conv3x3_wgrad_wide(xs[2 * hh], xs[2 * hh + 1], gs[2 * gg], gs[2 * gg + 1], dwp_flat, sub_off,
+                                               dbias0=self._gbias(pre, 2 * gg) if hh == 0 else None,
+                                               dbias1=self._gbias(pre, 2 * gg + 1) if hh == 0 else None)
+
+            wide_w2 = self.use_wide and b.go % 2 == 0
+            wide_w1 = wide_w2 and b.gi % 2 == 0
+            if wide_w2:
+                wgrad_wide(pre2, d["a"], d["gp2"], b.go, b.go)
+            if wide_w1:
+                wgrad_wide(pre1, cur, d["gp1"], b.gi, b.go)
+                if b.has_skip_conv:
+                    wgrad_wide(pres, cur, GS, b.gi, b.go)
             for g in range(b.go):
-                for h in range(b.go):
+                for h in range(0 if wide_w2 else b.go):
                     ops.conv3x3_wgrad(d["a"][h], d["gp2"][g], self.dwp[self._sub(pre2, g, h)],
                                       self._gbias(pre2, g) if h == 0 else None)
-                for h in range(b.gi):
+                for h in range(0 if wide_w1 else b.gi):
                     ops.conv3x3_wgrad(cur[h], d["gp1"][g], self.dwp[self._sub(pre1, g, h)],
                                       self._gbias(pre1, g) if h == 0 else None)
                     if b.has_skip_conv:

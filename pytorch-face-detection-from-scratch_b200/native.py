@@ -25,6 +25,8 @@ SIGNATURES = {
     "fd_conv3x3_pool": [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _I, _P],
     "fd_conv3x3_wide": [_P, _I, _P, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "fd_pack_conv3x3_wide": [_P, _I, _I, _I, _P, _P, _P],
+    "fd_pack_conv1x1_wide": [_P, _I, _I, _I, _P, _P, _P],
+    "fd_conv3x3_wgrad_wide": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _c.c_long, _P, _P, _c.c_long, _I, _P],
     "fd_conv3x3_wgrad": [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
     "fd_conv3x3_wgrad_multi": [_P, _P, _I, _I, _I, _I, _I, _P, _c.c_long, _P, _c.c_long, _I, _P],
     "fd_resblock_chain_shape_ok": [_I, _I, _I],

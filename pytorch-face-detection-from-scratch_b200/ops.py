@@ -59,13 +59,31 @@ def conv3x3_wide(x_planes, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_
 
 
 def pack_conv3x3_wide(w, w_fwd, w_dgrad):
-    """w: [L,Cout,Cin,3,3] (or [Cout,Cin,3,3]) fp32 -> w_fwd [L,Cout/128,Cin/64,9,128,64], w_dgrad [L,Cin/128,Cout/64,9,128,64]."""
+    """w: [L,Cout,Cin,k,k] (or [Cout,Cin,k,k]) fp32, k = 3 or 1 -> w_fwd [L,Cout/128,Cin/64,9,128,64], w_dgrad
+    [L,Cin/128,Cout/64,9,128,64] (k = 1: only the centre tap is written -- for CONV_1X1)."""
     if w.dim() == 5:
-        n, Cout, Cin = w.shape[0], w.shape[1], w.shape[2]
+        n, Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2], w.shape[3]
     else:
-        n, Cout, Cin = 1, w.shape[0], w.shape[1]
-    check(lib().fd_pack_conv3x3_wide(dptr(w, F32), n, Cout, Cin, dptr(w_fwd, BF16), dptr(w_dgrad, BF16), cur_stream()),
-          "fd_pack_conv3x3_wide")
+        n, Cout, Cin, k = 1, w.shape[0], w.shape[1], w.shape[2]
+    fn = lib().fd_pack_conv3x3_wide if k == 3 else lib().fd_pack_conv1x1_wide
+    check(fn(dptr(w, F32), n, Cout, Cin, dptr(w_fwd, BF16), dptr(w_dgrad, BF16), cur_stream()), "fd_pack_conv_wide")
+
+
+def conv3x3_wgrad_wide(x0, x1, g0, g1, dw_packed, sub_off, dw_stride=0, dbias0=None, dbias1=None, dbias_stride=0, flags=0):
+    """fd_conv3x3_wgrad_wide: the 128 x 128 channel block (x planes x0, x1) x (gradient planes g0, g1) of the weight
+    gradient; tensors [B,H,W,64] or stacked [nprob,B,H,W,64].  sub_off: 4 element offsets into dw_packed of the packed
+    [9,64,64] sub-blocks (x0,g0), (x0,g1), (x1,g0), (x1,g1)."""
+    if x0.dim() == 5:
+        nprob, B, H, W, C = x0.shape
+    else:
+        nprob = 1
+        B, H, W, C = x0.shape
+    assert C == 64 and len(sub_off) == 4
+    offs = (ctypes.c_long * 4)(*[int(o) for o in sub_off])
+    check(lib().fd_conv3x3_wgrad_wide(dptr(x0, BF16), dptr(x1, BF16), dptr(g0, BF16), dptr(g1, BF16), nprob, B, H, W,
+                                      dptr(dw_packed, F32), ctypes.cast(offs, ctypes.c_void_p), int(dw_stride),
+                                      dptr(dbias0, F32), dptr(dbias1, F32), int(dbias_stride), flags, cur_stream()),
+          "fd_conv3x3_wgrad_wide")
 
 
 def conv3x3_wgrad(x, g, dw_packed, dbias, flags=0):

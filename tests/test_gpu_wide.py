@@ -114,3 +114,35 @@ def test_conv3x3_wide_256_outputs_two_groups():
         outs += out
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), None, padding=1).permute(0, 2, 3, 1)
     _close(_cat(outs), ref, "256 outputs")
+
+
+@pytest.mark.parametrize("nprob,B,H,W", [(1, 2, 15, 15), (3, 5, 15, 15), (1, 3, 30, 30), (2, 2, 60, 60), (1, 1, 64, 125), (1, 70, 15, 15)])
+def test_conv3x3_wgrad_wide_vs_autograd(nprob, B, H, W):
+    """fd_conv3x3_wgrad_wide (one 128 x 128 channel block of dW per call, tcgen05.mma.cta_group::2, taps 0..7 + tap 8 in two
+    passes, TMA reduce-stores) against the weight / bias gradient of torch conv2d in fp32 on the bf16-rounded operands;
+    accumulates on top of what the buffers hold."""
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(nprob * 1000 + B * 10 + H)
+    dev = "cuda"
+    x = torch.randn(nprob, B, H, W, 128, device=dev).bfloat16()
+    g = (torch.randn(nprob, B, H, W, 128, device=dev) * 0.5).bfloat16()
+    xp = [x[..., :64].contiguous(), x[..., 64:].contiguous()]
+    gp = [g[..., :64].contiguous(), g[..., 64:].contiguous()]
+    n3 = 9 * 64 * 64
+    # packed sub-blocks per problem: [(g plane c, x plane r)] -> index c * 2 + r (the PlanarEngine order (g, h))
+    dwp = torch.full((nprob, 4, n3), 0.5, dtype=torch.float32, device=dev)
+    db = torch.full((nprob, 2, 64), 0.25, dtype=torch.float32, device=dev)
+    sub_off = [(c * 2 + r) * n3 for r in range(2) for c in range(2)]
+    ops.conv3x3_wgrad_wide(xp[0], xp[1], gp[0], gp[1], dwp.view(-1), sub_off, dw_stride=4 * n3, dbias0=db.view(-1),
+                           dbias1=db.view(-1)[64:], dbias_stride=128)
+    dw = torch.empty(nprob * 4, 64, 64, 3, 3, device=dev)
+    ops.unpack_wgrad3x3((dwp - 0.5).view(nprob * 4, 9, 64, 64), dw)
+    for q in range(nprob):
+        w = torch.zeros(128, 128, 3, 3, device=dev, requires_grad=True)
+        bias = torch.zeros(128, device=dev, requires_grad=True)
+        y = F.conv2d(x[q].float().permute(0, 3, 1, 2), w, bias, padding=1)
+        gw, gb = torch.autograd.grad(y, (w, bias), g[q].float().permute(0, 3, 1, 2))
+        got = dw[q * 4:(q + 1) * 4].view(2, 2, 64, 64, 3, 3).permute(0, 2, 1, 3, 4, 5).reshape(128, 128, 3, 3)   # [(c,co),(r,ci)]
+        assert rel_err(got, gw) <= 2e-3, (q, rel_err(got, gw))
+        assert rel_err((db[q] - 0.25).reshape(-1), gb) <= 2e-3
