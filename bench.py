@@ -462,7 +462,7 @@ def main():
                           "kept_boxes_batch": int(inf_counts.sum().item())}
         model.train()
         for name, fn in (("infer_separable", separable_infer), ("infer_mobilenet", mobilenet_infer),
-                         ("train_ssd", ssd_train)):
+                         ("train_ssd", ssd_train), ("train_f128", f128_train)):
             try:      # a secondary leg must not lose the headline line
                 extra[name] = fn(fd, dev, world, args, barrier, par, peaks)
             except Exception as exc:  # noqa: BLE001
@@ -619,6 +619,71 @@ def ssd_train(fd, dev, world, args, barrier, par, peaks):
     if not hasattr(fd.models, "SSD"):
         return {"error": "models.SSD not built"}
     return fd.models.SSD.bench_train_step(fd, dev, world, args, barrier, par, timed_graph_region, capture, synth_batch)
+
+
+def f128_train(fd, dev, world, args, barrier, par, peaks):
+    """PoolResnet(filters=128): the width train_model.py:17 trains (SURVEY 8d config C2, F = 128) -- forward + summed
+    YoloLoss + backward + Adam, batch 64 per GPU, train-mode dropout, one CUDA graph.  Its 3x3 convolutions run on the
+    cta_group::2 kernels (fd_conv3x3_wide forward / input gradient, fd_conv3x3_wgrad_wide); their rooflines are measured
+    by re-issuing the step's launches of each kernel back to back in one graph (as conv_roofline does)."""
+    if world > 1:
+        return {"skipped": "single-GPU leg (the data-parallel exchange is benchmarked on the headline configuration)"}
+    ops = fd.ops
+    B = B_PER_GPU
+    torch.manual_seed(4)
+    m = fd.models.PoolResnet.PoolResnet(filters=128, input_shape=(3, 480, 480), num_of_patches=S).to(dev).train()
+    eng = m.engine
+    eng.bind(dict(m.named_parameters()))
+    x_cpu, boxes = synth_batch(B, seed_img=20, seed_box=21)
+    gt = fd.datasets.WIDERFace.dataset.convert_bbx_to_feature_map_batch(boxes, S, (480, 480), device=dev)
+    x = x_cpu.to(dev)
+    topt = torch.optim.Adam(m.parameters(), lr=LR, capturable=True)
+    for name, prm in m.named_parameters():
+        prm.grad = eng.grad_view(name)
+    calls = {"conv": [], "wgrad": []}
+    o_conv, o_wgrad = ops.conv3x3_wide, ops.conv3x3_wgrad_wide
+
+    def rec_conv(xp, w, **kw):
+        calls["conv"].append((xp, w, kw))
+        o_conv(xp, w, **kw)
+
+    def rec_wgrad(*a, **kw):
+        calls["wgrad"].append((a, kw))
+        o_wgrad(*a, **kw)
+
+    ops.conv3x3_wide, ops.conv3x3_wgrad_wide = rec_conv, rec_wgrad
+    try:
+        eng.train_step(x, gt, dropout=True)
+        torch.cuda.synchronize()
+    finally:
+        ops.conv3x3_wide, ops.conv3x3_wgrad_wide = o_conv, o_wgrad
+    g, _, launches = capture(lambda: eng.train_step(x, gt, dropout=True, optimizer=topt))
+    ms, _, _ = timed_graph_region(g.replay, max(3, min(args.steps, 20)), 3, barrier, par, dev)
+    burst = peaks.get("bf16_tflops") or 1590.0
+
+    def roof(sel, run_one, flops_of, kernel):
+        if not sel:
+            return None
+        us = _time_graph(lambda: [run_one(c) for c in sel], 10)
+        fl = sum(flops_of(c) for c in sel)
+        return {"kernel": kernel, "bound": "tensor", "achieved": fl / us / 1e6, "peak": burst, "unit": "TFLOP/s",
+                "frac": fl / us / 1e6 / burst, "launches": len(sel), "avg_launch_us": us / len(sel), "traffic": None}
+
+    big = [c for c in calls["conv"] if c[0][0].shape[1] == 60]
+    conv_fl = lambda c: 2.0 * c[0][0].shape[0] * c[0][0].shape[1] * c[0][0].shape[2] * 9 * 64 * len(c[0]) * 128
+    wg_fl = lambda c: 2.0 * c[0][0].numel() / 64 * 9 * 128 * 128
+    return {"metric": "train_images_per_sec", "value": B / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
+            "launches_per_step": launches, "cuda_graph": True,
+            "achieved_tflops_algorithmic": 3 * 3.997e9 * B / (ms * 1e-3) / 1e12,
+            "workload": "PoolResnet(filters=128, S=10, 10 blocks, 480x480; the width train_model.py:17 trains) train step: "
+                        "forward + summed YoloLoss + backward + Adam (torch, capturable), batch 64, train-mode Dropout2d",
+            "roofline_conv_wide_60x60": roof(big, lambda c: o_conv(c[0], c[1], **c[2]), conv_fl,
+                                             "conv3x3_wide_kernel<2> (tcgen05.mma.cta_group::2, M=256 N=128; the 60x60 forward + "
+                                             "input-gradient launches of one step)"),
+            "roofline_conv_wide_all": roof(calls["conv"], lambda c: o_conv(c[0], c[1], **c[2]), conv_fl,
+                                           "conv3x3_wide_kernel<2>, all 40 launches of one step (32 of them on 15x15 maps: 64 tiles)"),
+            "roofline_wgrad_wide": roof(calls["wgrad"], lambda c: o_wgrad(*c[0], **c[1]), wg_fl,
+                                        "wgrad3x3_wide_kernel (cta_group::2, two passes per call)")}
 
 
 def gpu_library_baseline(dev, x, gt):
