@@ -24,6 +24,9 @@
 //   in_full[b], w_full[s]  : leader's barriers; BOTH CTAs' TMA loads complete_tx on them (cta_group::2 loads)
 //   in_empty[b], w_empty[s], acc_full[a] : per-CTA barriers, signalled by MULTICAST tcgen05.commit
 //   acc_empty[a]           : leader's barrier, 2 arrivals (each CTA's epilogue; the peer arrives remotely)
+// Maps with fewer tiles than SM pairs (15x15 at batch 64: 64 two-block tiles) run in SHARED-TILE mode: the pair works on
+// ONE tile, CTA r owns 128-row block r -- its copy of the halo tile is loaded 128 rows (16 KB) lower in shared memory, so the
+// pair's common A descriptor addresses block 0 in CTA 0 and block 1 in CTA 1 -- and twice as many SMs are busy.
 // Warp roles (672 threads): 0 = input loads, 1 = MMA issuer + TMEM owner, 2..17 = epilogue, 18 = TMA stores,
 // 19 = weight stream, 20 = residual loads (each stream of loads waits on its own barriers: none delays another).
 // Weights are handed over one KERNEL ROW (3 taps, 24 KB per CTA) at a time: the MMA thread's queue is only ~2 MMAs deep,
@@ -62,6 +65,10 @@ struct WideParams {
   uint32_t in_buf_bytes;        // bytes reserved per input ring buffer
   uint32_t stg_bytes, stg_buf_bytes;   // one staging UNIT: a whole plane-tile, or (split) the rows of one 128-row block
   int wslots;                   // weight ring depth
+  int share;                    // SHARED-TILE mode (fewer tiles than SM pairs): the pair works on ONE two-block tile, CTA r
+                                // owns block r; outputs / residual through plain vector loads / stores, no staging
+  const __nv_bfloat16* res_ptr[2];
+  __nv_bfloat16* out_ptr[2];
   int tpg, ngrp;                // taps per weight chunk (3: a kernel row; 1: centre-tap mode) and chunks per input plane
   int split, rpb, units;        // split: 128 % Wp == 0, a block = rpb whole tile rows = one staging unit; units per plane-tile
   uint32_t inv_wp;
@@ -175,7 +182,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
   // few rows BEHIND their input buffer (into the next ring buffer / the weight ring): harmless, they are never stored.
   constexpr uint32_t kTapBytes = (kCg == 2 ? 64u : 128u) * 128u;           // this CTA's part of one (plane, tap): 64 couts x 64 cins
   const uint32_t kChunkBytes = kTapBytes * static_cast<uint32_t>(p.tpg);  // one ring slot = one kernel row of taps
-  uint8_t* sIn = smem;
+  uint8_t* sIn = smem + (p.share ? 16384u : 0u);      // shared-tile mode: CTA 1 loads its tile 16 KB lower (guard space)
   uint8_t* sW = sIn + ((kInBufs * p.in_buf_bytes + 1023u) & ~1023u);
   uint8_t* sStg = sW + p.wslots * kChunkBytes;
   float* sConst = reinterpret_cast<float*>(sStg + 2 * p.stg_buf_bytes);     // bias[128] | chan_scale[128] | chan_scale2[128]
@@ -231,7 +238,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
   // work items: a pair-tile j covers tiles kCg*j + rank; this group handles j = group, group + ngroups, ...
   const int ngroups = static_cast<int>(gridDim.x) / kCg;
   const int group = static_cast<int>(blockIdx.x) / kCg;
-  const int njobs = (p.num_tiles + kCg - 1) / kCg;
+  const int njobs = p.share ? p.num_tiles : (p.num_tiles + kCg - 1) / kCg;
   pdl_trigger();
   pdl_wait();
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { g_wide_dbg[10] += clock64() - t_entry; g_wide_dbg[11] += 1; }
@@ -250,23 +257,24 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
     if (elect_one_sync()) {
       uint32_t b = 0, ph = 0;              // ring buffer and its phase
       for (int j = group; j < njobs; j += ngroups) {
-        const int tile = j * kCg + static_cast<int>(rank);        // >= num_tiles: dummy (every coordinate out of bounds -> zeros)
+        const int tile = p.share ? j : j * kCg + static_cast<int>(rank);   // >= num_tiles: dummy (all coordinates out of bounds -> zeros)
         int n, h0, w0;
         tile_coords(tile, n, h0, w0);
         for (int kh = 0; kh < p.gin; ++kh) {
           mbar_wait_sleep(in_empty + b, ph ^ 1u);
           if (leader) mbar_expect_tx(in_full + b, p.in_bytes * kCg);
-          tma_load_4d_g<kCg>(sIn + b * p.in_buf_bytes, &maps.in[kh], leader_bar<kCg>(in_full + b), 0, w0 - 1, h0 - 1, n);
+          tma_load_4d_g<kCg>(sIn + b * p.in_buf_bytes - (p.share ? rank * 16384u : 0u), &maps.in[kh], leader_bar<kCg>(in_full + b),
+                             0, w0 - 1, h0 - 1, n);
           if (++b == kInBufs) { b = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == kResWarp) {
     // ------------------------------------------------------------------ residual loads into the staging units
-    if (p.has_res && elect_one_sync()) {
+    if (p.has_res && !p.share && elect_one_sync()) {
       uint32_t q = 0;
       for (int j = group; j < njobs; j += ngroups) {
-        const int tile = j * kCg + static_cast<int>(rank);
+        const int tile = p.share ? j : j * kCg + static_cast<int>(rank);
         int n, h0, w0;
         tile_coords(tile, n, h0, w0);
         for (int g = 0; g < 2; ++g) {
@@ -302,6 +310,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
       const long long t_start = clock64();
       constexpr uint32_t idesc = make_idesc_bf16(128 * kCg, kNOut, 0, 0);
       const uint32_t wp_units = static_cast<uint32_t>(p.Wp) * 8u;
+      const int mma_blocks = p.share ? 1 : p.nblk;     // shared-tile mode: one instruction covers block 0 (CTA 0) and block 1 (CTA 1)
       uint32_t ib = 0, iph = 0;            // input ring buffer and its phase
       uint32_t s = 0, wph = 0;             // weight ring slot and its phase
       int it = 0;
@@ -324,7 +333,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
 #pragma unroll 1
             for (int i = 0; i < p.tpg; ++i) {
 #pragma unroll 1
-              for (int mb = 0; mb < p.nblk; ++mb) {
+              for (int mb = 0; mb < mma_blocks; ++mb) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_g<kCg>(d_tmem + static_cast<uint32_t>(mb) * kNOut, sdesc_sw128(a_lo + static_cast<uint32_t>(mb) * 1024u + 2 * k),
@@ -348,10 +357,10 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
     __syncwarp();
   } else if (warp == kStoreWarpW) {
     // ------------------------------------------------------------------ TMA store issuer
-    if (elect_one_sync()) {
+    if (!p.share && elect_one_sync()) {
       int it = 0;
       for (int j = group; j < njobs; j += ngroups, ++it) {
-        const int tile = j * kCg + static_cast<int>(rank);
+        const int tile = p.share ? j : j * kCg + static_cast<int>(rank);
         int n, h0, w0;
         tile_coords(tile, n, h0, w0);
         uint32_t q = static_cast<uint32_t>(it) * 2u * static_cast<uint32_t>(p.units);
@@ -386,7 +395,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
     const long long t_epi0 = clock64();
     int it = 0, last_n = -1;
     for (int j = group; j < njobs; j += ngroups, ++it) {
-      const int tile = j * kCg + static_cast<int>(rank);
+      const int tile = p.share ? j : j * kCg + static_cast<int>(rank);
       const bool live = tile < p.num_tiles;
       int n, h0, w0;
       tile_coords(tile, n, h0, w0);
@@ -403,6 +412,56 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         last_n = n;
       }
       const uint32_t a = static_cast<uint32_t>(it) & 1u, aph = (static_cast<uint32_t>(it) >> 1) & 1u;
+      if (p.share) {
+        // shared-tile mode: this CTA owns GEMM rows [128 * rank, 128 * rank + 128) of the tile (TMEM block 0); residual and
+        // output go through 16-byte vector loads / stores (a 15x15 map is 29 KB per plane: no staging, no TMA round trip)
+        const int m = static_cast<int>(rank) * 128 + q4 * 32 + lane;
+        const int y = static_cast<int>((static_cast<uint32_t>(m) * p.inv_wp) >> 16);
+        const int x = m - y * p.Wp;
+        const int oy = h0 + y, ox = w0 + x;
+        const bool valid = live && (y < p.R) && (x < p.TW) && (oy < p.H) && (ox < p.W);
+        const size_t pix = (static_cast<size_t>(n) * p.H + oy) * p.W + ox;
+        FD_WTE(5, mbar_wait_sleep(acc_full + a, aph, 1000));
+        tc_fence_after();
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+          uint32_t mbits = 0xffffu;
+          if (valid && p.has_res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res_ptr[g] + pix * kC + c0);
+            r0 = __ldg(rp);
+            r1 = __ldg(rp + 1);
+          }
+          if (valid && p.mask_in[g]) mbits = __ldg(p.mask_in[g] + pix * 4 + cq);
+          uint32_t acc[16];
+          tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * 256u + static_cast<uint32_t>(g * kC + c0), acc);
+          tmem_ld_wait();
+          if (valid) {
+            uint64_t v2[8];
+            epi_bias_act16(acc, sConst + g * kC + c0, sConst + kNOut + g * kC + c0, lrelu, has_cs, slope2, v2);
+            if (p.mask_out[g]) p.mask_out[g][pix * 4 + cq] = static_cast<uint16_t>(epi_sign_bits16(v2));
+            if (p.has_res) epi_add_bf16x16(v2, r0, r1);
+            uint4 u0, u1;
+            if (!p.staged_out2) {
+              epi_pack16(v2, u0, u1);
+            } else {
+              uint64_t o2[8];
+              epi_masked16(v2, mbits, p.slope, sConst + 2 * kNOut + g * kC + c0, has_cs2, o2);
+              epi_pack16(o2, u0, u1);
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out_ptr[g] + pix * kC + c0);
+            op[0] = u0;
+            op[1] = u1;
+          }
+        }
+        tc_fence_before();
+        bar_sync_epi_w();
+        if (et == 0) {             // every column of this tile's accumulators has been read by every warp
+          if (kCg == 2 && !leader) mbar_arrive_remote(mapa_shared(smem_u32(acc_empty + a), 0));
+          else mbar_arrive(acc_empty + a);
+        }
+        continue;
+      }
       uint32_t qq = static_cast<uint32_t>(it) * 2u * static_cast<uint32_t>(p.units);
       for (int g = 0; g < 2; ++g) {
         const uint16_t* mask_in = p.mask_in[g];
@@ -513,7 +572,7 @@ int launch_wide(const WideMaps& maps, const WideParams& p, size_t smem, cudaStre
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int nsm = sm_count();
-  const int njobs = (p.num_tiles + kCg - 1) / kCg;
+  const int njobs = p.share ? p.num_tiles : (p.num_tiles + kCg - 1) / kCg;
   const int max_groups = nsm / kCg;
   const int groups = njobs < max_groups ? njobs : max_groups;
   cudaLaunchConfig_t cfg = {};
@@ -642,6 +701,7 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
   // Tiling: TW <= 62 output columns, R rows with R * (TW + 2) <= 256 GEMM rows (two 128-row blocks = 2 x 128 TMEM columns,
   // double buffered).  Cost model: tensor time of the padded blocks times the number of waves over the CTA groups.
   const int tpg = (flags & FD_CONV_1X1) ? 1 : 3;
+  const bool share_ok = cg == 2 && !getenv("FD_WIDE_NO_SHARE");
   int bestR = 0, bestTW = 0;
   double best = 1e30;
   const int min_tw_tiles = (W + 61) / 62;
@@ -655,7 +715,8 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
       if (wide_slots(cg, tpg, R, Wp, TW, smem_cap) == 0) break;
       const long tiles = static_cast<long>(B) * ((H + R - 1) / R) * tw_tiles;
       const long waves = (tiles + nsm - 1) / nsm;
-      const double cost = waves * (2400.0 * nblk + 600.0);
+      double cost = waves * (2400.0 * nblk + 600.0);
+      if (share_ok && nblk == 2 && tiles <= nsm / 2) cost = 2400.0 + 600.0;     // shared-tile mode: one block per CTA
       if (cost < best) { best = cost; bestR = R; bestTW = TW; }
     }
   }
@@ -677,6 +738,13 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
   p.units = p.split ? p.nblk : 1;
   p.stg_bytes = static_cast<uint32_t>(p.rpb * bestTW * 128);
   p.stg_buf_bytes = static_cast<uint32_t>(wide_stg_buf_bytes(bestR, p.Wp, bestTW));
+  // shared-tile mode: two-block tiles, fewer of them than SM pairs, and the pair kernel
+  p.share = (share_ok && p.nblk == 2 && p.num_tiles <= nsm / 2) ? 1 : 0;
+  fd_bf16* const* staged_planes = has_out ? out : out2;
+  for (int g = 0; g < 2; ++g) {
+    p.res_ptr[g] = (residual && residual[0] && residual[1]) ? reinterpret_cast<const __nv_bfloat16*>(residual[g]) : nullptr;
+    p.out_ptr[g] = reinterpret_cast<__nv_bfloat16*>(staged_planes[g]);
+  }
   p.tpg = tpg;
   p.ngrp = (flags & FD_CONV_1X1) ? 1 : 3;
   p.wslots = wide_slots(cg, tpg, bestR, p.Wp, bestTW, smem_cap);
@@ -712,7 +780,16 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
     rc = make_tmap_nhwc_bf16(&maps.res[g], p.has_res ? residual[g] : x[0], B, H, W, kC, bestTW, p.rpb);
     if (rc != FD_OK) return rc;
   }
-  const size_t smem = wide_smem_fixed(bestR, p.Wp, bestTW) + p.wslots * wide_chunk_bytes(cg, tpg);
+  size_t smem = wide_smem_fixed(bestR, p.Wp, bestTW) + p.wslots * wide_chunk_bytes(cg, tpg);
+  if (p.share) {
+    // no staging buffers (outputs leave through plain stores); 16 KB of guard space below the input ring instead
+    const size_t fixed = wide_smem_fixed(bestR, p.Wp, bestTW) - 2 * wide_stg_buf_bytes(bestR, p.Wp, bestTW) + 16384;
+    size_t nslots = (smem_cap - fixed) / wide_chunk_bytes(cg, tpg);
+    if (nslots > kMaxWSlots) nslots = kMaxWSlots;
+    p.wslots = static_cast<int>(nslots);
+    p.stg_buf_bytes = 0;
+    smem = fixed + nslots * wide_chunk_bytes(cg, tpg);
+  }
   return cg == 2 ? launch_wide<2>(maps, p, smem, static_cast<cudaStream_t>(stream))
                  : launch_wide<1>(maps, p, smem, static_cast<cudaStream_t>(stream));
 }

@@ -208,4 +208,5 @@ def bench_train_step(fd, dev, world, args, barrier, par, timed_graph_region, cap
             "achieved_tflops_algorithmic": flops_img * Bs / (ms * 1e-3) / 1e12,
             "workload": "SSD(filters=16, 480x480; BASELINE config 5) train step: forward + ssd_loss(neg_pos_ratio 10) + "
                         "backward" + (" + num_pos and gradient all-reduce (NCCL)" if world > 1 else "") + " + Adam, 16 "
-                        "images per GPU, 64-channel-plane engine (channel counts 16/32 zero-padded to 64)"}
+                        "images per GPU; 64-channel planes (channel counts 16/32 zero-padded), the 128 / 256-channel blocks on the "
+                        "cta_group::2 wide kernels"}
