@@ -352,7 +352,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         }
         umma_commit_g<kCg>(acc_full + a);            // the tile's accumulators are final
       }
-      if (p.dbg && blockIdx.x == 0) { g_wide_dbg[3] += clock64() - t_start; g_wide_dbg[4] += it; g_wide_dbg[8] += t_start - t_entry; s_mma_end = clock64(); }
+      if (p.dbg && blockIdx.x == 0) { g_wide_dbg[3] += clock64() - t_start; g_wide_dbg[4] += it; g_wide_dbg[8] += t_start - t_entry; s_mma_end = clock64(); g_wide_dbg[6] += s_mma_end - t_entry; }
     }
     __syncwarp();
   } else if (warp == kStoreWarpW) {
@@ -423,6 +423,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         const size_t pix = (static_cast<size_t>(n) * p.H + oy) * p.W + ox;
         FD_WTE(5, mbar_wait_sleep(acc_full + a, aph, 1000));
         tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && et == 0) g_wide_dbg[14] += clock64() - t_entry;     // entry -> accumulators seen by the epilogue
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
           uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
@@ -456,6 +457,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         }
         tc_fence_before();
         bar_sync_epi_w();
+        if (p.dbg && blockIdx.x == 0 && et == 0) g_wide_dbg[15] += clock64() - t_entry;     // entry -> epilogue of the tile done
         if (et == 0) {             // every column of this tile's accumulators has been read by every warp
           if (kCg == 2 && !leader) mbar_arrive_remote(mapa_shared(smem_u32(acc_empty + a), 0));
           else mbar_arrive(acc_empty + a);

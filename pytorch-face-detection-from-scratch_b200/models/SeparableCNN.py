@@ -161,6 +161,8 @@ class SeparablePlanarEngine:
     centre-tap (``FD_CONV_1X1``) mode whose raw partial sums ride on the residual input (the skip connection is the
     first addend of the pw2 chain); LeakyReLU after pw1 in ``fd_act_mask``, depthwise 3x3 + LeakyReLU per plane in
     ``fd_dwconv3x3_lrelu``, pooling, stem and head (partial logits per plane) as in engine_planar.PlanarEngine.
+    For G = 2 or 4 the pointwise convolutions run on ``fd_conv3x3_wide`` in centre-tap mode instead (one launch per
+    convolution and group of 128 output channels, tcgen05.mma.cta_group::2, LeakyReLU / skip add fused: ``use_wide``).
     Functional path (the fused ``fd_sepblock_fwd`` is the 64-channel fast path); inference only."""
 
     def __init__(self, filters, in_ch, in_h, in_w, num_blocks, stem_k, stem_s, stem_pad, head_k, head_pad,
@@ -182,6 +184,8 @@ class SeparablePlanarEngine:
                 H, W = H // 2, W // 2
         self.So_h, self.So_w = H + 2 * head_pad - head_k + 1, W + 2 * head_pad - head_k + 1
         self.device, self.params, self.plans = None, None, {}
+        self.use_wide = self.G in (2, 4)
+        self.w_wide = None
 
     def bind(self, params):
         dev = params["conv1.weight"].device
@@ -235,9 +239,14 @@ class SeparablePlanarEngine:
             pw += [P[pre + "pointwise_conv1.weight"].detach(), P[pre + "pointwise_conv2.weight"].detach()]
             dw.append(P[pre + "depthwise_conv.weight"].detach())
         L = 2 * nb
-        sub = torch.stack(pw).float().view(L, G, 64, G, 64).permute(0, 1, 3, 2, 4).reshape(L * G * G, 64, 64)
-        self.w_pk = torch.zeros((L * G * G, 9, 64, 64), dtype=BF16, device=self.device)      # only the centre tap is read
-        self.w_pk[:, 4] = sub.to(BF16)
+        if self.use_wide:       # [layer][group of 128 couts][input plane][tap][128][64]; only the centre tap is written / read
+            if self.w_wide is None or self.w_wide.device != self.device:
+                self.w_wide = torch.zeros((L, G // 2, G, 9, 128, 64), dtype=BF16, device=self.device)
+            ops.pack_conv3x3_wide(torch.stack(pw).float().contiguous(), self.w_wide, None)
+        else:
+            sub = torch.stack(pw).float().view(L, G, 64, G, 64).permute(0, 1, 3, 2, 4).reshape(L * G * G, 64, 64)
+            self.w_pk = torch.zeros((L * G * G, 9, 64, 64), dtype=BF16, device=self.device)      # only the centre tap is read
+            self.w_pk[:, 4] = sub.to(BF16)
         self.w_dw = torch.stack(dw).float().view(nb, G, 64, 9).permute(0, 1, 3, 2).contiguous()     # [nb, G, 9, 64]
 
     def _pw_chain(self, srcs, layer, g, first_residual, dst_a, dst_b):
@@ -258,6 +267,27 @@ class SeparablePlanarEngine:
             ops.stem_fwd(x, w1[g * 64:(g + 1) * 64], b1[g * 64:(g + 1) * 64], pl["act0"][g], self.stem_s, self.stem_pad)
         cur = pl["act0"]
         for k, b in enumerate(pl["blocks"]):
+            if self.use_wide:
+                for go in range(G // 2):       # pw1 + LeakyReLU (models/SeparableCNN.py:42-43)
+                    ops.conv3x3_wide(cur, self.w_wide[2 * k, go], slope=self.slope, lrelu=True,
+                                     out=[b["t1"][2 * go], b["t1"][2 * go + 1]], flags=ops.CONV_1X1)
+                main = self._fork()
+                for g in range(G):
+                    with self._on(main, g):
+                        ops.dwconv3x3_lrelu(b["t1"][g], self.w_dw[k, g], self.slope, b["t2"][g])
+                self._join(main)
+                for go in range(G // 2):       # pw2 + skip (:46-48; Dropout2d is the identity in eval mode)
+                    ops.conv3x3_wide(b["t2"], self.w_wide[2 * k + 1, go], slope=self.slope,
+                                     residual=[cur[2 * go], cur[2 * go + 1]], out=[b["s"][2 * go], b["s"][2 * go + 1]],
+                                     flags=ops.CONV_1X1)
+                if self.pools[k]:
+                    main = self._fork()
+                    for g in range(G):
+                        with self._on(main, g):
+                            ops.maxpool2x2_fwd(b["s"][g], b["out"][g])
+                    self._join(main)
+                cur = b["out"]
+                continue
             main = self._fork()
             for g in range(G):
                 with self._on(main, g):

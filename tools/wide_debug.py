@@ -90,6 +90,7 @@ if os.environ.get("FD_WIDE_TIMING"):
     tiles = max(1, v[4])
     print(f"  CTA0 MMA thread per tile (clk): total {v[3] / tiles:.0f} = wait acc_empty {v[0] / tiles:.0f} + wait input {v[1] / tiles:.0f} + wait weights {v[2] / tiles:.0f} + issue/other {(v[3] - v[0] - v[1] - v[2]) / tiles:.0f};"
           f" per launch: entry->after pdl_wait {v[10] / max(1, v[11]):.0f}, entry->MMA loop {v[8] / max(1, v[11]):.0f}, MMA loop end->exit {v[9] / max(1, v[11]):.0f}, tiles/launch {tiles / max(1, v[11]):.1f};"
+          f" share-mode timeline from entry (clk/launch): MMA loop end {v[6] / max(1, v[11]):.0f}, epilogue sees accumulators {v[14] / max(1, v[11]):.0f}, epilogue done {v[15] / max(1, v[11]):.0f};"
           f" slowest CTA (max over launches): pdl_wait->exit {v[12]}, entry->exit {v[13]};"
           f" epilogue thread: total {v[7] / tiles:.0f}, wait acc_full {v[5] / tiles:.0f}, wait staging/residual {v[6] / tiles:.0f}  ({tiles} tiles)")
 print(f"B={B} {H}x{W} gin={gin}: {us:.1f} us/launch, {fl / us / 1e6:.0f} TFLOP/s (cta_group={os.environ.get('FD_WIDE_CTA_GROUP', '2')})")
