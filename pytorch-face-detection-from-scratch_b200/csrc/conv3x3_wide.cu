@@ -421,19 +421,25 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         const int oy = h0 + y, ox = w0 + x;
         const bool valid = live && (y < p.R) && (x < p.TW) && (oy < p.H) && (ox < p.W);
         const size_t pix = (static_cast<size_t>(n) * p.H + oy) * p.W + ox;
+        // residual / mask operands of both planes are fetched BEFORE the accumulators are awaited: their global-memory
+        // latency hides behind the tile's MMAs (with one tile per CTA nothing else would)
+        uint4 rr[2][2];
+        uint32_t mb2[2] = {0xffffu, 0xffffu};
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          rr[g][0] = rr[g][1] = make_uint4(0, 0, 0, 0);
+          if (valid && p.has_res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res_ptr[g] + pix * kC + c0);
+            rr[g][0] = __ldg(rp);
+            rr[g][1] = __ldg(rp + 1);
+          }
+          if (valid && p.mask_in[g]) mb2[g] = __ldg(p.mask_in[g] + pix * 4 + cq);
+        }
         FD_WTE(5, mbar_wait_sleep(acc_full + a, aph, 1000));
         tc_fence_after();
         if (p.dbg && blockIdx.x == 0 && et == 0) g_wide_dbg[14] += clock64() - t_entry;     // entry -> accumulators seen by the epilogue
-#pragma unroll 1
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
-          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-          uint32_t mbits = 0xffffu;
-          if (valid && p.has_res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res_ptr[g] + pix * kC + c0);
-            r0 = __ldg(rp);
-            r1 = __ldg(rp + 1);
-          }
-          if (valid && p.mask_in[g]) mbits = __ldg(p.mask_in[g] + pix * 4 + cq);
           uint32_t acc[16];
           tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * 256u + static_cast<uint32_t>(g * kC + c0), acc);
           tmem_ld_wait();
@@ -441,13 +447,13 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
             uint64_t v2[8];
             epi_bias_act16(acc, sConst + g * kC + c0, sConst + kNOut + g * kC + c0, lrelu, has_cs, slope2, v2);
             if (p.mask_out[g]) p.mask_out[g][pix * 4 + cq] = static_cast<uint16_t>(epi_sign_bits16(v2));
-            if (p.has_res) epi_add_bf16x16(v2, r0, r1);
+            if (p.has_res) epi_add_bf16x16(v2, rr[g][0], rr[g][1]);
             uint4 u0, u1;
             if (!p.staged_out2) {
               epi_pack16(v2, u0, u1);
             } else {
               uint64_t o2[8];
-              epi_masked16(v2, mbits, p.slope, sConst + 2 * kNOut + g * kC + c0, has_cs2, o2);
+              epi_masked16(v2, mb2[g], p.slope, sConst + 2 * kNOut + g * kC + c0, has_cs2, o2);
               epi_pack16(o2, u0, u1);
             }
             uint4* op = reinterpret_cast<uint4*>(p.out_ptr[g] + pix * kC + c0);

@@ -78,6 +78,9 @@ int stem_s2_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Ci
 int mbv3_stem_tc(const void* x, int x_is_u8, const float* w, const float* bias, int B, int H, int W, int pad_t, int pad_l,
                  int Ho, int Wo, fd_bf16* out, cudaStream_t st);
 
+// depthwise 3x3 pad 1 + LeakyReLU on a 64-channel plane through the strip kernel of mbv3_kernels.cu (w: [9][64] tap-major)
+int dwconv3x3_lrelu_strips(const fd_bf16* x, const float* w, int B, int H, int W, float slope, fd_bf16* out, cudaStream_t st);
+
 // tcgen05 backward of the 64 -> 5 head (head_tc.cu); FD_EUNSUPPORTED = shape not instantiated
 int head_bwd_tc(const fd_bf16* x, const float* chan_scale, const float* w, const float* y, const float* dy, int B, int H,
                 int W, int C, int K, int pad, fd_bf16* dx, const uint32_t* mask_bits, const float* chan_scale2, float slope,

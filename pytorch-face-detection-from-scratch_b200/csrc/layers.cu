@@ -1072,6 +1072,15 @@ extern "C" int fd_dwconv3x3_lrelu(const fd_bf16* x, const float* w_dw, int B, in
                                  void* stream) {
   if (!x || !w_dw || !out || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
   if (C != 64 || !(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;
+  {
+    // strip kernel (4 pixels x 8 channels per thread, window rows loaded once); FD_DW_PIXEL_KERNEL=1 keeps the
+    // thread-per-pixel kernel below for A/B runs
+    static const bool pixel = getenv("FD_DW_PIXEL_KERNEL") != nullptr;
+    if (!pixel) {
+      const int rc = dwconv3x3_lrelu_strips(x, w_dw, B, H, W, slope, out, static_cast<cudaStream_t>(stream));
+      if (rc != FD_EUNSUPPORTED) return rc;
+    }
+  }
   launch_k(dwconv3x3_lrelu_kernel, dim3(grid_for(static_cast<long>(B) * H, 1, 16)), dim3(256), 0,
            static_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), w_dw, B, H, W, slope,
            reinterpret_cast<__nv_bfloat16*>(out));

@@ -101,7 +101,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(256, 2)
 mbv3_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int H,
                int W, int C, int Ho, int Wo, int pad_t, int pad_l, int act, __nv_bfloat16* __restrict__ out,
-               float* __restrict__ se_partial) {
+               float* __restrict__ se_partial, float lrelu_slope) {
   pdl_trigger();
   pdl_wait();
   constexpr int T = kDwT, NX = (T - 1) * S + K;
@@ -169,7 +169,7 @@ mbv3_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
         float r[8];
         upk2(acc[t][0], r[0], r[1]); upk2(acc[t][1], r[2], r[3]); upk2(acc[t][2], r[4], r[5]); upk2(acc[t][3], r[6], r[7]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = act_apply(r[i], act);
+        for (int i = 0; i < 8; ++i) r[i] = act == 3 ? fmaxf(r[i], r[i] * lrelu_slope) : act_apply(r[i], act);
         uint4 o;
         o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]);
         o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
@@ -407,12 +407,28 @@ extern "C" int fd_dwconv(const fd_bf16* x, const float* w_packed, const float* b
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
 #define FD_DW(KK, SS) launch_k(mbv3_dw_kernel<KK, SS>, grid, dim3(256), smem, st, xp, w_packed, bias, H, W, C, Ho, Wo, \
-                               pad_t, pad_l, act, op, se_sum)
+                               pad_t, pad_l, act, op, se_sum, 0.f)
   if (K == 3 && stride == 1) FD_DW(3, 1);
   else if (K == 3) FD_DW(3, 2);
   else if (stride == 1) FD_DW(5, 1);
   else FD_DW(5, 2);
 #undef FD_DW
+  count_launch();
+  return launch_status();
+}
+
+// Depthwise 3x3 pad 1 + LeakyReLU (0 <= slope <= 1) on a 64-channel plane, no bias (fd_dwconv3x3_lrelu of layers.cu):
+// the strip kernel above with act code 3.
+__device__ float g_dw_zero_bias[64];
+int fd::dwconv3x3_lrelu_strips(const fd_bf16* x, const float* w, int B, int H, int W, float slope, fd_bf16* out, cudaStream_t st) {
+  if (B > 65535) return FD_EUNSUPPORTED;
+  float* zb = nullptr;
+  if (cudaGetSymbolAddress(reinterpret_cast<void**>(&zb), g_dw_zero_bias) != cudaSuccess) return FD_EUNSUPPORTED;
+  const long items = static_cast<long>(H) * ((W + kDwT - 1) / kDwT) * 8;
+  const dim3 grid(static_cast<unsigned>((items + 255) / 256), B);
+  launch_k(mbv3_dw_kernel<3, 1>, grid, dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), w,
+           static_cast<const float*>(zb), H, W, 64, H, W, 1, 1, 3, reinterpret_cast<__nv_bfloat16*>(out),
+           static_cast<float*>(nullptr), slope);
   count_launch();
   return launch_status();
 }

@@ -94,7 +94,7 @@ def main():
         prm.grad = eng.grad_view([n for n, q in m.named_parameters() if q is prm][0])
     us, n = timed(lambda: eng.train_step(x, gt, dropout=True, optimizer=topt), reps=10)
     emit(row="1,2", what="PoolResnet(filters=128, S=10) train step: forward + summed YoloLoss + backward + torch Adam, batch 64, "
-                         "train-mode dropout (PlanarEngine: 64-channel kernels on two channel planes)", us=us, launches=n,
+                         "train-mode dropout (PlanarEngine: two channel planes, cta_group::2 wide kernels for the 3x3 convolutions)", us=us, launches=n,
          images_per_s=B / us * 1e6, tflops=3 * 3.997e9 * B / us / 1e6)
     m.eval()
     red = m.reduce_bounding_boxes
@@ -120,8 +120,8 @@ def main():
     sm = fd.models.SeparableCNN.SeparableCNN(filters=128, input_shape=(3, 480, 480)).cuda().eval()
     sm.engine.bind(dict(sm.named_parameters()))
     us, n = timed(lambda: red.batch_forward(sm.engine.forward(x)), reps=5)
-    emit(row=9, what="SeparableCNN(filters=128) inference + decode + NMS, batch 256 (channel planes: 1x1-mode fd_conv3x3 "
-                     "chains + fd_dwconv3x3_lrelu)", us=us, launches=n, images_per_s=B / us * 1e6)
+    emit(row=9, what="SeparableCNN(filters=128) inference + decode + NMS, batch 256 (channel planes: pointwise convolutions on "
+                     "fd_conv3x3_wide in centre-tap mode + fd_dwconv3x3_lrelu)", us=us, launches=n, images_per_s=B / us * 1e6)
     w_pw = (torch.randn(2, 64, 64, device=dev) * 0.1).bfloat16()
     w_dw = torch.randn(9, 64, device=dev) * 0.3
     for H in (60, 30, 15):

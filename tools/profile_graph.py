@@ -15,7 +15,7 @@ if which == "mbv3":
     B = 256
     m = fd.models.MobilenetV3Backbone.MobilenetV3Backbone(576, (3, 480, 480), 15).to(dev).eval()
     x = torch.rand(B, 3, 480, 480, device=dev)
-    fn = lambda: m.engine.forward(x)
+    fn = lambda: m(x)
 elif which in ("sep", "sep128"):
     B = 256
     m = fd.models.SeparableCNN.SeparableCNN(filters=64 if which == "sep" else 128, input_shape=(3, 480, 480)).to(dev).eval()
