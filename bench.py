@@ -661,13 +661,21 @@ def f128_train(fd, dev, world, args, barrier, par, peaks):
     ms, _, _ = timed_graph_region(g.replay, max(3, min(args.steps, 20)), 3, barrier, par, dev)
     burst = peaks.get("bf16_tflops") or 1590.0
 
-    def roof(sel, run_one, flops_of, kernel):
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    except Exception:  # noqa: BLE001
+        tj = {}
+
+    def roof(sel, run_one, flops_of, kernel, tkey):
         if not sel:
             return None
         us = _time_graph(lambda: [run_one(c) for c in sel], 10)
         fl = sum(flops_of(c) for c in sel)
+        t = tj.get(tkey, {})
         return {"kernel": kernel, "bound": "tensor", "achieved": fl / us / 1e6, "peak": burst, "unit": "TFLOP/s",
-                "frac": fl / us / 1e6 / burst, "launches": len(sel), "avg_launch_us": us / len(sel), "traffic": None}
+                "frac": fl / us / 1e6 / burst, "launches": len(sel), "avg_launch_us": us / len(sel),
+                "traffic": t.get("dram_bytes_per_launch"), "traffic_unit": "bytes/launch", "traffic_source": t.get("source"),
+                "tensor_pipe_active_pct_ncu": t.get("tensor_pipe_active_pct")}
 
     big = [c for c in calls["conv"] if c[0][0].shape[1] == 60]
     conv_fl = lambda c: 2.0 * c[0][0].shape[0] * c[0][0].shape[1] * c[0][0].shape[2] * 9 * 64 * len(c[0]) * 128
@@ -679,11 +687,12 @@ def f128_train(fd, dev, world, args, barrier, par, peaks):
                         "forward + summed YoloLoss + backward + Adam (torch, capturable), batch 64, train-mode Dropout2d",
             "roofline_conv_wide_60x60": roof(big, lambda c: o_conv(c[0], c[1], **c[2]), conv_fl,
                                              "conv3x3_wide_kernel<2> (tcgen05.mma.cta_group::2, M=256 N=128; the 60x60 forward + "
-                                             "input-gradient launches of one step)"),
+                                             "input-gradient launches of one step)", "conv3x3_wide_kernel_60x60"),
             "roofline_conv_wide_all": roof(calls["conv"], lambda c: o_conv(c[0], c[1], **c[2]), conv_fl,
-                                           "conv3x3_wide_kernel<2>, all 40 launches of one step (32 of them on 15x15 maps: 64 tiles)"),
+                                           "conv3x3_wide_kernel<2>, all 40 launches of one step (32 of them on 15x15 maps: 64 tiles)",
+                                           "conv3x3_wide_kernel_all"),
             "roofline_wgrad_wide": roof(calls["wgrad"], lambda c: o_wgrad(*c[0], **c[1]), wg_fl,
-                                        "wgrad3x3_wide_kernel (cta_group::2, two passes per call)")}
+                                        "wgrad3x3_wide_kernel (cta_group::2, two passes per call)", "wgrad3x3_wide_kernel")}
 
 
 def gpu_library_baseline(dev, x, gt):

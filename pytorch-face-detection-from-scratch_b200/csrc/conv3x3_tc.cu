@@ -475,8 +475,7 @@ static int conv3x3_impl(const fd_bf16* x, const fd_bf16* w_packed, int B, int H,
   rc = make_tmap_nhwc_bf16(&tm_res, residual ? residual : x, B, H, W, C, bestTW, bestR);
   if (rc != FD_OK) return rc;
 
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+  cudaError_t e = set_max_dyn_smem(conv3x3_tc_kernel, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = p.num_tiles < nsm ? p.num_tiles : nsm;
   e = launch_k(conv3x3_tc_kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), tm_in, tm_w, tm_res,

@@ -576,8 +576,7 @@ inline int wide_slots(int cg, int tpg, int R, int Wp, int TW, size_t cap) {
 
 template <int kCg>
 int launch_wide(const WideMaps& maps, const WideParams& p, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_wide_kernel<kCg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+  cudaError_t e = set_max_dyn_smem(conv3x3_wide_kernel<kCg>, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int nsm = sm_count();
   const int njobs = p.share ? p.num_tiles : (p.num_tiles + kCg - 1) / kCg;

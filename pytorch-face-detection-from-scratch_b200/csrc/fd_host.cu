@@ -1,9 +1,11 @@
 // Host-side plumbing of libfd_b200.so: driver entry point for TMA descriptors, launch counter,
 // error strings.
+#include <mutex>
+#include <unordered_map>
+
 #include "fd_host.h"
 
 #include <cstdlib>
-#include <mutex>
 
 namespace fd {
 
@@ -111,6 +113,17 @@ int make_tmap_3d(CUtensorMap* m, const void* ptr, int elem_bytes, int is_u8, int
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? FD_OK : FD_EINVAL;
+}
+
+cudaError_t raise_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> high;
+  std::lock_guard<std::mutex> lock(mu);
+  int& h = high[func];
+  if (bytes <= h) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) h = bytes;
+  return e;
 }
 
 bool pdl_enabled() {

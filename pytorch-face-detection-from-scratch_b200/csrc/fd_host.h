@@ -39,6 +39,15 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Opt-in dynamic shared memory of a kernel, as a HIGH-WATER MARK: the attribute belongs to the function, not to a launch, so
+// lowering it for a later, smaller launch would invalidate kernel nodes already captured into CUDA graphs with the larger
+// size (seen as LaunchFailed when a graph is replayed under a profiler).  Only ever raised; thread safe.
+cudaError_t raise_dyn_smem(const void* func, int bytes);
+template <typename K>
+inline cudaError_t set_max_dyn_smem(K kern, int bytes) {
+  return raise_dyn_smem(reinterpret_cast<const void*>(kern), bytes);
+}
+
 // [B,H,W,C] bf16 tensor as a 4-D tiled TMA map with box {C, boxW, boxH, 1}, 128B swizzle, zero OOB fill.
 int make_tmap_nhwc_bf16(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int boxW, int boxH);
 // a W-window [B,H,Wext,C] of a [B,H,Wfull,C] bf16 tensor (ptr = first pixel of the window): columns >= Wext are

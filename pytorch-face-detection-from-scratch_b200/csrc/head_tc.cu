@@ -306,11 +306,11 @@ int head_bwd_tc(const fd_bf16* x, const float* chan_scale, const float* w, const
   const int grid = B < sm_count() ? B : sm_count();
   cudaError_t e;
   if (K == 6) {
-    e = cudaFuncSetAttribute(head_bwd_tc_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(head_bwd_tc_kernel<6, 0>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(head_bwd_tc_kernel<6, 0>, dim3(grid), dim3(kThreads), smem, st, tm_x, p);
   } else {
-    e = cudaFuncSetAttribute(head_bwd_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(head_bwd_tc_kernel<3, 1>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(head_bwd_tc_kernel<3, 1>, dim3(grid), dim3(kThreads), smem, st, tm_x, p);
   }

@@ -1148,13 +1148,13 @@ extern "C" int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (x_is_u8) {
-    e = cudaFuncSetAttribute(stem_fwd_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_fwd_kernel<uint8_t>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     stem_fwd_kernel<uint8_t><<<grid, kStemThreads, smem, st>>>(static_cast<const uint8_t*>(x), w, bias, B, Cin, Hin, Win,
                                                                C, K, stride, pad, Ho, Wo,
                                                                reinterpret_cast<__nv_bfloat16*>(y));
   } else {
-    e = cudaFuncSetAttribute(stem_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_fwd_kernel<float>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     stem_fwd_kernel<float><<<grid, kStemThreads, smem, st>>>(static_cast<const float*>(x), w, bias, B, Cin, Hin, Win, C,
                                                              K, stride, pad, Ho, Wo,
@@ -1187,13 +1187,13 @@ extern "C" int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (x_is_u8) {
-    e = cudaFuncSetAttribute(stem_wgrad_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_wgrad_kernel<uint8_t>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     stem_wgrad_kernel<uint8_t><<<grid, kStemThreads, smem, st>>>(static_cast<const uint8_t*>(x),
                                                                  reinterpret_cast<const __nv_bfloat16*>(g), B, Cin, Hin,
                                                                  Win, C, K, stride, pad, Ho, Wo, dw, dbias);
   } else {
-    e = cudaFuncSetAttribute(stem_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_wgrad_kernel<float>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     stem_wgrad_kernel<float><<<grid, kStemThreads, smem, st>>>(static_cast<const float*>(x),
                                                                reinterpret_cast<const __nv_bfloat16*>(g), B, Cin, Hin,
@@ -1227,7 +1227,7 @@ extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const floa
     const size_t sm2 = static_cast<size_t>(K) * K * 5 * C * 4 + static_cast<size_t>(rows_per_cta + K - 1) * W * C * 2;
     if (sm2 <= 227 * 1024 && rows_per_cta >= 1) {
       auto kern = (K == 6) ? head_fwd_c64_kernel<6, 0> : head_fwd_c64_kernel<3, 1>;
-      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      cudaError_t e2 = set_max_dyn_smem(kern, (int)sm2);
       if (e2 != cudaSuccess) return (int)e2;
       launch_k(kern, dim3(B, parts), dim3(rows_per_cta * strips * 32), sm2, static_cast<cudaStream_t>(stream),
                reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w_t, bias, H, W, Ho, Wo, rows_per_cta, y);
@@ -1237,7 +1237,7 @@ extern "C" int fd_head_fwd(const fd_bf16* x, const float* chan_scale, const floa
   }
   const size_t smem = static_cast<size_t>((K * K * 5 * (C + 1) + 3) & ~3) * 4 + static_cast<size_t>(H) * W * C * 2;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_dyn_smem(head_fwd_kernel, (int)smem);
   if (e != cudaSuccess) return (int)e;
   head_fwd_kernel<<<dim3(B, kHeadSplit), kHeadThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, bias, B, H, W, C, K, pad, Ho, Wo, y);
@@ -1276,7 +1276,7 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
     const size_t sm2 = sm_dx > sm_dw ? sm_dx : sm_dw;
     if (sm2 <= 227 * 1024 && threads <= 512) {
       auto kern = (K == 6) ? head_bwd_c64_kernel<6, 0> : head_bwd_c64_kernel<3, 1>;
-      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      cudaError_t e2 = set_max_dyn_smem(kern, (int)sm2);
       if (e2 != cudaSuccess) return (int)e2;
       launch_k(kern, dim3(B, dx_parts + dw_parts), dim3(threads), sm2, static_cast<cudaStream_t>(stream),
                reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w_t, y, dy, H, W, Ho, Wo, rows_per_cta, dx_parts,
@@ -1289,7 +1289,7 @@ extern "C" int fd_head_bwd(const fd_bf16* x, const float* chan_scale, const floa
   const size_t smem = static_cast<size_t>((K * K * 5 * (C + 1) + 3) & ~3) * 4 + static_cast<size_t>((5 * Ho * Wo + 3) & ~3) * 4 +
                       static_cast<size_t>(H) * W * C * 2;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_dyn_smem(head_bwd_kernel, (int)smem);
   if (e != cudaSuccess) return (int)e;
   head_bwd_kernel<<<min(B, sm_count()), kHeadThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), chan_scale, w, y, dy, B, H, W, C, K, pad, Ho, Wo,

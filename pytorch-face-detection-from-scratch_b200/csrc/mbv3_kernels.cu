@@ -460,7 +460,7 @@ extern "C" int fd_head3x3_fwd(const fd_bf16* x, const float* w, const float* bia
   if (C % 64 || B > 65535) return FD_EUNSUPPORTED;
   const size_t smem = static_cast<size_t>(9) * 5 * C * 2;
   if (smem > 200 * 1024) return FD_EUNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(mbv3_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = set_max_dyn_smem(mbv3_head_kernel, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int parts = 2;
   launch_k(mbv3_head_kernel, dim3(B, parts), dim3(256), smem, static_cast<cudaStream_t>(stream),

@@ -215,7 +215,7 @@ int mbv3_stem_tc(const void* x, int x_is_u8, const float* w, const float* bias, 
   if (rc != FD_OK) return rc;
   const size_t smem = 2048 + 2 * 16384 + 4 * static_cast<size_t>(p.patch_stride) + 256 + 1024;
   auto kern = x_is_u8 ? mbv3_stem_tc_kernel<true> : mbv3_stem_tc_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = set_max_dyn_smem(kern, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const long cap = 2L * sm_count();
   const int grid = static_cast<int>(p.num_tiles < cap ? p.num_tiles : cap);

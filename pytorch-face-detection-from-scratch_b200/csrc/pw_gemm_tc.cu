@@ -314,7 +314,7 @@ extern "C" int fd_pw_conv(const fd_bf16* x, const fd_bf16* w_packed, const float
   if (rc != FD_OK) return rc;
   rc = make_tmap_2d_bf16(&tm_out, out, static_cast<int>(M), N, 128, 64);
   if (rc != FD_OK) return rc;
-  cudaError_t e = cudaFuncSetAttribute(pw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = set_max_dyn_smem(pw_gemm_kernel, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int nsm = sm_count();
   const int grid = p.num_tiles < nsm ? static_cast<int>(p.num_tiles) : nsm;

@@ -394,8 +394,7 @@ int launch_chain(ChainBuilder& cb, const fd_bf16* w, int w_layers, const fd_bf16
   p.rows_per_blk = 128 / Wp;
   const int nsm = sm_count();
   if (chain_split_ok(H, W)) {
-    cudaError_t e = cudaFuncSetAttribute(resblock_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    cudaError_t e = set_max_dyn_smem(resblock_chain_kernel<true>, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     const int nclusters = B < nsm / 2 ? B : nsm / 2;
     cudaLaunchConfig_t cfg = {};
@@ -415,8 +414,7 @@ int launch_chain(ChainBuilder& cb, const fd_bf16* w, int w_layers, const fd_bf16
     e = cudaLaunchKernelEx(&cfg, resblock_chain_kernel<true>, tm_w, tm_in0, tm_in1, p);
     if (e != cudaSuccess) return static_cast<int>(e);
   } else {
-    cudaError_t e = cudaFuncSetAttribute(resblock_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    cudaError_t e = set_max_dyn_smem(resblock_chain_kernel<false>, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     const int grid = B < nsm ? B : nsm;
     e = launch_k(resblock_chain_kernel<false>, dim3(grid), dim3(kThreads), smem, st, tm_w, tm_in0, tm_in1, p);

@@ -485,8 +485,7 @@ extern "C" int fd_sepblock_fwd(const fd_bf16* x, const fd_bf16* w_pw1, const flo
             : make_tmap_nhwc_bf16(&tm_out, out, B, H, W, C, bestTW, bestR);
   if (rc != FD_OK) return rc;
 
-  cudaError_t e = cudaFuncSetAttribute(sepblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+  cudaError_t e = set_max_dyn_smem(sepblock_fwd_kernel, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = p.num_tiles < 2 * nsm ? p.num_tiles : 2 * nsm;
   e = launch_k(sepblock_fwd_kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), tm_x, tm_w1, tm_w2,

@@ -349,7 +349,7 @@ extern "C" int fd_ssd_grid_encode(const float* boxes, const int32_t* box_offsets
   if (rc != FD_OK) return rc;
   const size_t smem = static_cast<size_t>(sc.base[sc.n]) * sizeof(int);
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(ssd_grid_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_dyn_smem(ssd_grid_encode_kernel, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ssd_grid_encode_kernel<<<B, kSsdThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       boxes, box_offsets, sc, static_cast<float>(width), static_cast<float>(height), out);
@@ -368,7 +368,7 @@ extern "C" int fd_ssd_decode_nms(const float* x, int B, const int* patch_sizes, 
   const size_t P = sc.base[sc.n];
   const size_t smem = P * (5 * sizeof(float) + 2 * sizeof(int) + 1) + 16;
   if (smem > 227 * 1024) return FD_EUNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(ssd_decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_dyn_smem(ssd_decode_nms_kernel, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ssd_decode_nms_kernel<<<B, kSsdThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       x, sc, p_thr, iou_thr, static_cast<float>(width), static_cast<float>(height), with_priors, out_boxes, out_count);
@@ -384,7 +384,7 @@ extern "C" int fd_ssd_loss(const float* conf, const float* loc, const float* lab
     return FD_EINVAL;
   const size_t smem = static_cast<size_t>(P) * sizeof(uint32_t);
   if (smem > 200 * 1024) return FD_EUNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(ssd_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_dyn_smem(ssd_loss_kernel, (int)smem);
   if (e != cudaSuccess) return (int)e;
   // SSDLoss.py:13-14: epsilon = 10**-7 (python float), clamp bounds rounded to f32 by torch
   const float lo = static_cast<float>(1e-7), hi = static_cast<float>(1.0 - 1e-7);

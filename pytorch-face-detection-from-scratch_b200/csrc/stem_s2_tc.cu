@@ -405,11 +405,11 @@ int stem_s2_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias
   const int grid = min(p.ntask, 2 * sm_count());
   cudaError_t e;
   if (x_is_u8) {
-    e = cudaFuncSetAttribute(stem_s2_fwd_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_s2_fwd_kernel<uint8_t>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(stem_s2_fwd_kernel<uint8_t>, dim3(grid), dim3(kThreads), smem, st, tm_y, p);
   } else {
-    e = cudaFuncSetAttribute(stem_s2_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_s2_fwd_kernel<float>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(stem_s2_fwd_kernel<float>, dim3(grid), dim3(kThreads), smem, st, tm_y, p);
   }
@@ -430,11 +430,11 @@ int stem_s2_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Ci
   const int grid = min(p.ntask, 2 * sm_count());
   cudaError_t e;
   if (x_is_u8) {
-    e = cudaFuncSetAttribute(stem_s2_wgrad_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_s2_wgrad_kernel<uint8_t>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(stem_s2_wgrad_kernel<uint8_t>, dim3(grid), dim3(kThreads), smem, st, tm_g, p);
   } else {
-    e = cudaFuncSetAttribute(stem_s2_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_s2_wgrad_kernel<float>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(stem_s2_wgrad_kernel<float>, dim3(grid), dim3(kThreads), smem, st, tm_g, p);
   }

@@ -812,11 +812,11 @@ int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, i
   const int grid = min(p.ntask, sm_count());
   cudaError_t e;
   if (x_is_u8) {
-    e = cudaFuncSetAttribute(stem_fwd_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_fwd_tc_kernel<uint8_t>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(stem_fwd_tc_kernel<uint8_t>, dim3(grid), dim3(kFwdThreads), smem, st, tm_x, p);
   } else {
-    e = cudaFuncSetAttribute(stem_fwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_fwd_tc_kernel<float>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(stem_fwd_tc_kernel<float>, dim3(grid), dim3(kFwdThreads), smem, st, tm_x, p);
   }
@@ -838,7 +838,7 @@ int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, 
     if (rc != FD_OK) return rc;
     const size_t smem2 = 2 * static_cast<size_t>(p.a_bytes) + 1024 + 2 * 128 * 128 + 1024 + 1024;
     if (smem2 > 227 * 1024) return FD_EUNSUPPORTED;
-    cudaError_t e2 = cudaFuncSetAttribute(stem_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    cudaError_t e2 = set_max_dyn_smem(stem_wgrad_bf16_kernel, (int)smem2);
     if (e2 != cudaSuccess) return (int)e2;
     const int grid2 = min(p.ntask, sm_count());
     e2 = launch_k(stem_wgrad_bf16_kernel, dim3(grid2), dim3(kWg2Threads), smem2, st, tm_xb, tm_g, p);
@@ -862,11 +862,11 @@ int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, 
   const int grid = min(p.ntask, sm_count());
   cudaError_t e;
   if (x_is_u8) {
-    e = cudaFuncSetAttribute(stem_wgrad_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_wgrad_tc_kernel<uint8_t>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(stem_wgrad_tc_kernel<uint8_t>, dim3(grid), dim3(kThreads), smem, st, tm_x, tm_g, p);
   } else {
-    e = cudaFuncSetAttribute(stem_wgrad_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dyn_smem(stem_wgrad_tc_kernel<float>, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_k(stem_wgrad_tc_kernel<float>, dim3(grid), dim3(kThreads), smem, st, tm_x, tm_g, p);
   }

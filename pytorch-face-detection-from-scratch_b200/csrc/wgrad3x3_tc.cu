@@ -328,8 +328,7 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
   p.bar_off = static_cast<uint32_t>(stages > drain ? stages : drain);
   const size_t smem = p.bar_off + 1024 + 1024;
   if (smem > smem_cap) return FD_EUNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+  cudaError_t e = set_max_dyn_smem(wgrad3x3_tc_kernel, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = nprob * p.ctas_per_prob;
   e = launch_k(wgrad3x3_tc_kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), tm_x, gmaps, tm_dw, p);

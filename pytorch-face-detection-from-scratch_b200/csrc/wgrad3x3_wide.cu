@@ -348,7 +348,7 @@ extern "C" int fd_conv3x3_wgrad_wide(const fd_bf16* x0, const fd_bf16* x1, const
   rc = make_tmap_2d_f32(&maps.dw, dw_packed, static_cast<long>(nprob - 1) * p.dw_rows_per_prob + max_row + 9 * kC, kC, 128, 32);
   if (rc != FD_OK) return rc;
 
-  cudaError_t e = cudaFuncSetAttribute(wgrad3x3_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = set_max_dyn_smem(wgrad3x3_wide_kernel, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   // pass 1: taps 0..7 as four pairs (4 x 128 TMEM columns); pass 2: tap 8 as the pair (7, 8) with the tap-7 half dropped
   for (int pass = 0; pass < 2; ++pass) {

@@ -332,7 +332,7 @@ extern "C" int fd_decode_nms(const float* pred, int B, int S1, int S2, float p_t
   if (ncell > 1024) return FD_EUNSUPPORTED;
   const int nw = (ncell + 31) / 32;
   const size_t smem = static_cast<size_t>(ncell) * (5 * 4 + 2 * 4) + static_cast<size_t>(ncell) * nw * 4;
-  cudaError_t e = cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_dyn_smem(decode_nms_kernel, (int)smem);
   if (e != cudaSuccess) return (int)e;
   // utils.py:108-109: python floats width/num_of_patches, rounded to f32 when they meet the f32 tensor
   const float psx = static_cast<float>(static_cast<double>(width) / num_of_patches);
