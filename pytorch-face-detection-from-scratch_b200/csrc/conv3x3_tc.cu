@@ -414,6 +414,26 @@ static int conv3x3_impl(const fd_bf16* x, const fd_bf16* w_packed, int B, int H,
   const bool pool = pooled != nullptr;
   if (mask_in && !out2) return FD_EINVAL;
   if (!(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;   // LeakyReLU is evaluated as max(v, slope*v)
+  {
+    // CTA-PAIR instantiation (conv3x3_wide.cu with 64 outputs: tcgen05.mma.cta_group::2, M = 256, the B operand split between
+    // the two shared memories -- 5 KB instead of 6 KB of operand reads per MMA): one staged output, no fused pooling.
+    // FD_CONV_PAIR=0 keeps this kernel (A/B runs); maps with fewer than two waves of tiles stay here as well.
+    static const int pair_env = [] { const char* e = getenv("FD_CONV_PAIR"); return e ? atoi(e) : 0; }();
+    if (pair_env && !pool && !(out && out2) && static_cast<long>(B) * H * W >= pair_env) {
+      const fd_bf16* xs[1] = {x};
+      const float* cs[1] = {chan_scale};
+      const float* cs2[1] = {chan_scale2};
+      const fd_bf16* rs[1] = {residual};
+      uint32_t* mo[1] = {mask_out};
+      const uint32_t* mi[1] = {mask_in};
+      fd_bf16* o1[1] = {out};
+      fd_bf16* o2[1] = {out2};
+      const int rc = conv3x3_pairs(64, xs, 1, w_packed, B, H, W, bias, slope, chan_scale ? cs : nullptr, residual ? rs : nullptr,
+                                   mask_out ? mo : nullptr, out ? o1 : nullptr, mask_in ? mi : nullptr,
+                                   chan_scale2 ? cs2 : nullptr, out2 ? o2 : nullptr, flags & ~FD_CONV_ONE_TAP, stream);
+      if (rc != FD_EUNSUPPORTED) return rc;
+    }
+  }
   const int nsm = sm_count();
   const size_t smem_cap = 227 * 1024;
 

@@ -40,7 +40,7 @@ namespace fd {
 namespace {
 
 constexpr int kC = 64;                       // channels per plane
-constexpr int kNOut = 128;                   // output channels per launch (two planes)
+constexpr int kNOut = 128;                   // TMEM / constant-table stride of one block: the widest instantiation (kN = 128)
 constexpr int kInBufs = 3;                   // ring of input-plane tiles
 constexpr int kMaxWSlots = 8;                // ring of weight chunks (kernel rows): as many as fit (WideParams::wslots)
 constexpr int kEpiWarpsW = 16;
@@ -169,7 +169,8 @@ __device__ __forceinline__ void tma_load_4d_g(void* smem_dst, const CUtensorMap*
         : "memory");
 }
 
-template <int kCg>
+// kN = output channels per launch: 128 (two planes) or 64 (one plane: the 64-channel layers on CTA pairs)
+template <int kCg, int kN>
 __global__ void __launch_bounds__(kThreadsW, 1)
 conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant__ WideParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -180,7 +181,8 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
 
   // Layout: input ring | weight ring | staging 0 | staging 1 | constants | barriers.  Junk GEMM rows of the last block read a
   // few rows BEHIND their input buffer (into the next ring buffer / the weight ring): harmless, they are never stored.
-  constexpr uint32_t kTapBytes = (kCg == 2 ? 64u : 128u) * 128u;           // this CTA's part of one (plane, tap): 64 couts x 64 cins
+  constexpr int kNP = kN / 64;                                              // output planes
+  constexpr uint32_t kTapBytes = static_cast<uint32_t>(kCg == 2 ? kN / 2 : kN) * 128u;   // this CTA's part of one (plane, tap)
   const uint32_t kChunkBytes = kTapBytes * static_cast<uint32_t>(p.tpg);  // one ring slot = one kernel row of taps
   uint8_t* sIn = smem + (p.share ? 16384u : 0u);      // shared-tile mode: CTA 1 loads its tile 16 KB lower (guard space)
   uint8_t* sW = sIn + ((kInBufs * p.in_buf_bytes + 1023u) & ~1023u);
@@ -207,7 +209,6 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
     for (int g = 0; g < p.gin; ++g) tma_prefetch_desc(&maps.in[g]);
     tma_prefetch_desc(&maps.w);
     tma_prefetch_desc(&maps.out[0]);
-    tma_prefetch_desc(&maps.out[1]);
     for (int i = 0; i < kInBufs; ++i) {
       mbar_init(in_full + i, 1);
       mbar_init(in_empty + i, 1);
@@ -277,7 +278,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         const int tile = p.share ? j : j * kCg + static_cast<int>(rank);
         int n, h0, w0;
         tile_coords(tile, n, h0, w0);
-        for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < kNP; ++g) {
           for (int u = 0; u < p.units; ++u, ++q) {
             const uint32_t sb = q & 1u, ph = (q >> 1) & 1u;
             mbar_wait_sleep(stg_free + sb, ph ^ 1u);        // the store two units ago has drained this buffer
@@ -298,7 +299,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
             if (leader) mbar_expect_tx(w_full + s, kChunkBytes * kCg);
             for (int i = 0; i < p.tpg; ++i)
               tma_load_2d_g<kCg>(sW + s * kChunkBytes + i * kTapBytes, &maps.w, leader_bar<kCg>(w_full + s), 0,
-                                 (kh * 9 + p.tap_lo + r * p.tpg + i) * kNOut + static_cast<int>(rank) * 64);
+                                 (kh * 9 + p.tap_lo + r * p.tpg + i) * kN + static_cast<int>(rank) * (kN / 2));
             if (++s == static_cast<uint32_t>(p.wslots)) { s = 0; ph ^= 1u; }
           }
         }
@@ -308,7 +309,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
     if (leader && elect_one_sync()) {
       const long long t_start = clock64();
-      constexpr uint32_t idesc = make_idesc_bf16(128 * kCg, kNOut, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(128 * kCg, kN, 0, 0);
       const uint32_t wp_units = static_cast<uint32_t>(p.Wp) * 8u;
       const int mma_blocks = p.share ? 1 : p.nblk;     // shared-tile mode: one instruction covers block 0 (CTA 0) and block 1 (CTA 1)
       uint32_t ib = 0, iph = 0;            // input ring buffer and its phase
@@ -363,8 +364,8 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         const int tile = p.share ? j : j * kCg + static_cast<int>(rank);
         int n, h0, w0;
         tile_coords(tile, n, h0, w0);
-        uint32_t q = static_cast<uint32_t>(it) * 2u * static_cast<uint32_t>(p.units);
-        for (int g = 0; g < 2; ++g) {
+        uint32_t q = static_cast<uint32_t>(it) * static_cast<uint32_t>(kNP) * static_cast<uint32_t>(p.units);
+        for (int g = 0; g < kNP; ++g) {
           for (int u = 0; u < p.units; ++u, ++q) {
             const uint32_t sb = q & 1u, ph = (q >> 1) & 1u;
             mbar_wait_sleep(stg_ready + sb, ph);
@@ -391,7 +392,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
     const uint64_t slope2 = pk2(p.slope, p.slope);
     const bool lrelu = (p.flags & FD_EPI_LRELU) != 0;
     const bool has_cs = p.chan_scale[0] != nullptr, has_cs2 = p.chan_scale2[0] != nullptr;
-    if (et < kNOut) sConst[et] = p.bias ? __ldg(p.bias + et) : 0.f;
+    if (et < kN) sConst[et] = p.bias ? __ldg(p.bias + et) : 0.f;
     const long long t_epi0 = clock64();
     int it = 0, last_n = -1;
     for (int j = group; j < njobs; j += ngroups, ++it) {
@@ -401,10 +402,10 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
       tile_coords(tile, n, h0, w0);
       if (n != last_n) {          // per-image Dropout2d multipliers (uniform branch)
         bar_sync_epi_w();
-        if (live && et >= kNOut && et < 2 * kNOut) {
+        if (live && et >= kNOut && et < kNOut + kN) {
           const int ch = et - kNOut;
           sConst[et] = has_cs ? __ldg(p.chan_scale[ch >> 6] + n * kC + (ch & 63)) : 1.f;
-        } else if (live && et >= 2 * kNOut && et < 3 * kNOut) {
+        } else if (live && et >= 2 * kNOut && et < 2 * kNOut + kN) {
           const int ch = et - 2 * kNOut;
           sConst[et] = has_cs2 ? __ldg(p.chan_scale2[ch >> 6] + n * kC + (ch & 63)) : 1.f;
         }
@@ -426,7 +427,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         uint4 rr[2][2];
         uint32_t mb2[2] = {0xffffu, 0xffffu};
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < kNP; ++g) {
           rr[g][0] = rr[g][1] = make_uint4(0, 0, 0, 0);
           if (valid && p.has_res) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res_ptr[g] + pix * kC + c0);
@@ -439,7 +440,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         tc_fence_after();
         if (p.dbg && blockIdx.x == 0 && et == 0) g_wide_dbg[14] += clock64() - t_entry;     // entry -> accumulators seen by the epilogue
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < kNP; ++g) {
           uint32_t acc[16];
           tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * 256u + static_cast<uint32_t>(g * kC + c0), acc);
           tmem_ld_wait();
@@ -470,8 +471,8 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
         }
         continue;
       }
-      uint32_t qq = static_cast<uint32_t>(it) * 2u * static_cast<uint32_t>(p.units);
-      for (int g = 0; g < 2; ++g) {
+      uint32_t qq = static_cast<uint32_t>(it) * static_cast<uint32_t>(kNP) * static_cast<uint32_t>(p.units);
+      for (int g = 0; g < kNP; ++g) {
         const uint16_t* mask_in = p.mask_in[g];
         uint16_t* mask_out = p.mask_out[g];
         uint8_t* stg = nullptr;
@@ -524,7 +525,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
             *reinterpret_cast<uint4*>(row + ch1) = u1;
           }
           if (p.split || mb == p.nblk - 1) {     // the unit is complete
-            const bool tile_done = g == 1 && mb == p.nblk - 1;
+            const bool tile_done = g == kNP - 1 && mb == p.nblk - 1;
             fence_proxy_async();       // staging writes (generic proxy) -> visible to the TMA store
             if (tile_done) tc_fence_before();
             bar_sync_epi_w();
@@ -566,17 +567,17 @@ inline size_t wide_smem_fixed(int R, int Wp, int TW) {
   const size_t in = (kInBufs * wide_in_buf_bytes(R, Wp) + 1023) / 1024 * 1024;
   return in + 2 * wide_stg_buf_bytes(R, Wp, TW) + 3 * kNOut * 4 + 512 + 1024;
 }
-inline size_t wide_chunk_bytes(int cg, int tpg) { return static_cast<size_t>(cg == 2 ? 64 : 128) * 128 * tpg; }
-inline int wide_slots(int cg, int tpg, int R, int Wp, int TW, size_t cap) {
+inline size_t wide_chunk_bytes(int cg, int tpg, int nout = 128) { return static_cast<size_t>(cg == 2 ? nout / 2 : nout) * 128 * tpg; }
+inline int wide_slots(int cg, int tpg, int R, int Wp, int TW, size_t cap, int nout = 128) {
   const size_t fixed = wide_smem_fixed(R, Wp, TW);
-  if (fixed + kMinWSlots * wide_chunk_bytes(cg, tpg) > cap) return 0;
-  const size_t n = (cap - fixed) / wide_chunk_bytes(cg, tpg);
+  if (fixed + kMinWSlots * wide_chunk_bytes(cg, tpg, nout) > cap) return 0;
+  const size_t n = (cap - fixed) / wide_chunk_bytes(cg, tpg, nout);
   return n > kMaxWSlots ? kMaxWSlots : static_cast<int>(n);
 }
 
-template <int kCg>
+template <int kCg, int kN>
 int launch_wide(const WideMaps& maps, const WideParams& p, size_t smem, cudaStream_t st) {
-  cudaError_t e = set_max_dyn_smem(conv3x3_wide_kernel<kCg>, static_cast<int>(smem));
+  cudaError_t e = set_max_dyn_smem(conv3x3_wide_kernel<kCg, kN>, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int nsm = sm_count();
   const int njobs = p.share ? p.num_tiles : (p.num_tiles + kCg - 1) / kCg;
@@ -603,7 +604,7 @@ int launch_wide(const WideMaps& maps, const WideParams& p, size_t smem, cudaStre
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  e = cudaLaunchKernelEx(&cfg, conv3x3_wide_kernel<kCg>, maps, p);
+  e = cudaLaunchKernelEx(&cfg, conv3x3_wide_kernel<kCg, kN>, maps, p);
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   return launch_status();
@@ -685,20 +686,28 @@ extern "C" int fd_pack_conv1x1_wide(const float* w, int n_layers, int Cout, int 
   return pack_conv_wide(w, n_layers, Cout, Cin, 1, w_fwd, w_dgrad, stream);
 }
 
-extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* w_packed, int B, int H, int W,
-                               const float* bias, float slope, const float* const* chan_scale,
-                               const fd_bf16* const* residual, uint32_t* const* mask_out, fd_bf16* const* out,
-                               const uint32_t* const* mask_in, const float* const* chan_scale2, fd_bf16* const* out2,
-                               int flags, void* stream) {
+// nout = 128: the wide API below; nout = 64: one output plane -- the 64-channel layers of conv3x3_tc.cu on CTA pairs
+// (w_packed = the tap-major [9][64][64] packing of fd_pack_conv3x3, every per-plane array has ONE entry)
+int fd::conv3x3_pairs(int nout, const fd_bf16* const* x, int gin, const fd_bf16* w_packed, int B, int H, int W,
+                      const float* bias, float slope, const float* const* chan_scale, const fd_bf16* const* residual,
+                      uint32_t* const* mask_out, fd_bf16* const* out, const uint32_t* const* mask_in,
+                      const float* const* chan_scale2, fd_bf16* const* out2, int flags, void* stream) {
   using namespace fd;
   if (!x || !w_packed || B <= 0 || H <= 0 || W <= 0) return FD_EINVAL;
-  if (gin < 1 || gin > kMaxGin) return FD_EUNSUPPORTED;
+  if (gin < 1 || gin > kMaxGin || (nout != 64 && nout != 128)) return FD_EUNSUPPORTED;
+  const int np = nout / 64;
   for (int g = 0; g < gin; ++g)
     if (!x[g]) return FD_EINVAL;
-  const bool has_out = out && out[0] && out[1], has_out2 = out2 && out2[0] && out2[1];
-  if (has_out == has_out2) return FD_EINVAL;                 // exactly one staged output (both planes)
+  auto all_set = [np](auto arr) {
+    if (!arr) return false;
+    for (int g = 0; g < np; ++g)
+      if (!arr[g]) return false;
+    return true;
+  };
+  const bool has_out = all_set(out), has_out2 = all_set(out2);
+  if (has_out == has_out2) return FD_EINVAL;                 // exactly one staged output (every plane)
   if (mask_in && !has_out2) return FD_EINVAL;
-  if (has_out2 && !(mask_in && mask_in[0] && mask_in[1])) return FD_EINVAL;
+  if (has_out2 && !all_set(mask_in)) return FD_EINVAL;
   if (!(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;
   static const int cg_env = [] { const char* e = getenv("FD_WIDE_CTA_GROUP"); return e ? atoi(e) : 2; }();
   const int cg = cg_env == 1 ? 1 : 2;
@@ -719,7 +728,7 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
     for (int R = 1; R <= H && R + 2 <= 256; ++R) {
       const int nblk = (R * Wp + 127) / 128;
       if (nblk > 2) break;
-      if (wide_slots(cg, tpg, R, Wp, TW, smem_cap) == 0) break;
+      if (wide_slots(cg, tpg, R, Wp, TW, smem_cap, nout) == 0) break;
       const long tiles = static_cast<long>(B) * ((H + R - 1) / R) * tw_tiles;
       const long waves = (tiles + nsm - 1) / nsm;
       double cost = waves * (2400.0 * nblk + 600.0);
@@ -748,25 +757,28 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
   // shared-tile mode: two-block tiles, fewer of them than SM pairs, and the pair kernel
   p.share = (share_ok && p.nblk == 2 && p.num_tiles <= nsm / 2) ? 1 : 0;
   fd_bf16* const* staged_planes = has_out ? out : out2;
+  const bool has_res = all_set(residual);
   for (int g = 0; g < 2; ++g) {
-    p.res_ptr[g] = (residual && residual[0] && residual[1]) ? reinterpret_cast<const __nv_bfloat16*>(residual[g]) : nullptr;
-    p.out_ptr[g] = reinterpret_cast<__nv_bfloat16*>(staged_planes[g]);
+    const int gs = g < np ? g : 0;
+    p.res_ptr[g] = has_res ? reinterpret_cast<const __nv_bfloat16*>(residual[gs]) : nullptr;
+    p.out_ptr[g] = reinterpret_cast<__nv_bfloat16*>(staged_planes[gs]);
   }
   p.tpg = tpg;
   p.ngrp = (flags & FD_CONV_1X1) ? 1 : 3;
-  p.wslots = wide_slots(cg, tpg, bestR, p.Wp, bestTW, smem_cap);
+  p.wslots = wide_slots(cg, tpg, bestR, p.Wp, bestTW, smem_cap, nout);
   p.inv_wp = static_cast<uint32_t>((65536 + p.Wp - 1) / p.Wp);
   p.flags = flags;
   { static const int dbg = [] { const char* d = getenv("FD_WIDE_TIMING"); return d ? atoi(d) : 0; }(); p.dbg = dbg; }
   p.slope = slope;
   p.bias = bias;
-  p.has_res = (residual && residual[0] && residual[1]) ? 1 : 0;
+  p.has_res = has_res ? 1 : 0;
   p.staged_out2 = has_out2 ? 1 : 0;
   for (int g = 0; g < 2; ++g) {
-    p.chan_scale[g] = chan_scale ? chan_scale[g] : nullptr;
-    p.chan_scale2[g] = chan_scale2 ? chan_scale2[g] : nullptr;
-    p.mask_in[g] = mask_in ? reinterpret_cast<const uint16_t*>(mask_in[g]) : nullptr;
-    p.mask_out[g] = mask_out ? reinterpret_cast<uint16_t*>(mask_out[g]) : nullptr;
+    const int gs = g < np ? g : 0;
+    p.chan_scale[g] = chan_scale ? chan_scale[gs] : nullptr;
+    p.chan_scale2[g] = chan_scale2 ? chan_scale2[gs] : nullptr;
+    p.mask_in[g] = mask_in ? reinterpret_cast<const uint16_t*>(mask_in[gs]) : nullptr;
+    p.mask_out[g] = mask_out ? reinterpret_cast<uint16_t*>(mask_out[gs]) : nullptr;
   }
   if ((p.chan_scale[0] == nullptr) != (p.chan_scale[1] == nullptr)) return FD_EINVAL;
   if ((p.chan_scale2[0] == nullptr) != (p.chan_scale2[1] == nullptr)) return FD_EINVAL;
@@ -778,25 +790,36 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
     rc = make_tmap_nhwc_bf16(&maps.in[g], x[g < gin ? g : 0], B, H, W, kC, p.Wp, bestR + 2);
     if (rc != FD_OK) return rc;
   }
-  rc = make_tmap_2d_bf16(&maps.w, w_packed, gin * 9 * kNOut, kC, cg == 2 ? 64 : 128, kC);
+  rc = make_tmap_2d_bf16(&maps.w, w_packed, gin * 9 * nout, kC, cg == 2 ? nout / 2 : nout, kC);
   if (rc != FD_OK) return rc;
   fd_bf16* const* staged = has_out ? out : out2;
   for (int g = 0; g < 2; ++g) {
-    rc = make_tmap_nhwc_bf16(&maps.out[g], staged[g], B, H, W, kC, bestTW, p.rpb);
+    const int gs = g < np ? g : 0;
+    rc = make_tmap_nhwc_bf16(&maps.out[g], staged[gs], B, H, W, kC, bestTW, p.rpb);
     if (rc != FD_OK) return rc;
-    rc = make_tmap_nhwc_bf16(&maps.res[g], p.has_res ? residual[g] : x[0], B, H, W, kC, bestTW, p.rpb);
+    rc = make_tmap_nhwc_bf16(&maps.res[g], p.has_res ? residual[gs] : x[0], B, H, W, kC, bestTW, p.rpb);
     if (rc != FD_OK) return rc;
   }
-  size_t smem = wide_smem_fixed(bestR, p.Wp, bestTW) + p.wslots * wide_chunk_bytes(cg, tpg);
+  size_t smem = wide_smem_fixed(bestR, p.Wp, bestTW) + p.wslots * wide_chunk_bytes(cg, tpg, nout);
   if (p.share) {
     // no staging buffers (outputs leave through plain stores); 16 KB of guard space below the input ring instead
     const size_t fixed = wide_smem_fixed(bestR, p.Wp, bestTW) - 2 * wide_stg_buf_bytes(bestR, p.Wp, bestTW) + 16384;
-    size_t nslots = (smem_cap - fixed) / wide_chunk_bytes(cg, tpg);
+    size_t nslots = (smem_cap - fixed) / wide_chunk_bytes(cg, tpg, nout);
     if (nslots > kMaxWSlots) nslots = kMaxWSlots;
     p.wslots = static_cast<int>(nslots);
     p.stg_buf_bytes = 0;
-    smem = fixed + nslots * wide_chunk_bytes(cg, tpg);
+    smem = fixed + nslots * wide_chunk_bytes(cg, tpg, nout);
   }
-  return cg == 2 ? launch_wide<2>(maps, p, smem, static_cast<cudaStream_t>(stream))
-                 : launch_wide<1>(maps, p, smem, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nout == 64) return cg == 2 ? launch_wide<2, 64>(maps, p, smem, st) : launch_wide<1, 64>(maps, p, smem, st);
+  return cg == 2 ? launch_wide<2, 128>(maps, p, smem, st) : launch_wide<1, 128>(maps, p, smem, st);
+}
+
+extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* w_packed, int B, int H, int W,
+                               const float* bias, float slope, const float* const* chan_scale,
+                               const fd_bf16* const* residual, uint32_t* const* mask_out, fd_bf16* const* out,
+                               const uint32_t* const* mask_in, const float* const* chan_scale2, fd_bf16* const* out2,
+                               int flags, void* stream) {
+  return fd::conv3x3_pairs(128, x, gin, w_packed, B, H, W, bias, slope, chan_scale, residual, mask_out, out, mask_in,
+                           chan_scale2, out2, flags, stream);
 }

@@ -87,6 +87,12 @@ int stem_s2_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Ci
 int mbv3_stem_tc(const void* x, int x_is_u8, const float* w, const float* bias, int B, int H, int W, int pad_t, int pad_l,
                  int Ho, int Wo, fd_bf16* out, cudaStream_t st);
 
+// conv3x3_wide.cu: the cta_group::2 convolution for nout = 128 (fd_conv3x3_wide) or 64 output channels (one plane)
+int conv3x3_pairs(int nout, const fd_bf16* const* x, int gin, const fd_bf16* w_packed, int B, int H, int W, const float* bias,
+                  float slope, const float* const* chan_scale, const fd_bf16* const* residual, uint32_t* const* mask_out,
+                  fd_bf16* const* out, const uint32_t* const* mask_in, const float* const* chan_scale2, fd_bf16* const* out2,
+                  int flags, void* stream);
+
 // depthwise 3x3 pad 1 + LeakyReLU on a 64-channel plane through the strip kernel of mbv3_kernels.cu (w: [9][64] tap-major)
 int dwconv3x3_lrelu_strips(const fd_bf16* x, const float* w, int B, int H, int W, float slope, fd_bf16* out, cudaStream_t st);
 
