@@ -59,7 +59,8 @@ __device__ __forceinline__ void cta_barrier_across_ranks(const Peers& pp, int ph
   __syncthreads();
   if (static_cast<int>(threadIdx.x) < world) {
     const int peer = threadIdx.x;
-    __threadfence_system();
+    // no separate __threadfence_system(): st.release.sys below IS the (cumulative) system-scope release of everything
+    // that happened before the bar.sync; a second fence only added another NVLink round trip per barrier
     const size_t slot = (static_cast<size_t>(phase) * kCommBlocks + blockIdx.x) * kMaxPeers;
     st_release_sys(reinterpret_cast<unsigned*>(pp.win[peer]) + slot + rank, epoch);
     const unsigned* mine = reinterpret_cast<const unsigned*>(pp.win[rank]) + slot + peer;
