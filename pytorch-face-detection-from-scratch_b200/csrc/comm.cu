@@ -17,6 +17,8 @@
 // all ranks only -- no grid-wide synchronisation and no co-residency requirement.  No barrier is needed at entry:
 // a peer's scatter window is free once the previous call's second barrier passed, and its result window is only
 // written after the next call's first barrier, by which time that peer finished its phase 3.
+#include <cstdlib>
+
 #include "fd_host.h"
 #include "fd_ptx.cuh"
 
@@ -136,7 +138,56 @@ allreduce_sum_kernel(Peers pp, float* __restrict__ data, long n4, long chunk4, i
   }
 }
 
+// ONE-SHOT variant for small buffers (the "late" region of the split exchange: ~0.7 MB): every rank pushes its WHOLE
+// buffer into slot `rank` of every peer, ONE cross-rank barrier, then every rank sums the `world` contributions locally in
+// rank order (bit-identical on all ranks).  One barrier instead of two and no second push / copy-back; (world - 1) x the
+// bytes on the wire, which is why it is only used below kOneShotMaxN.  The slots are double buffered by call parity: a
+// fast peer's pushes of call k+1 land in the other buffer while this rank may still be summing call k, and buffer k & 1 is
+// only reused by call k+2, whose pushes follow barrier k+1 -- which this rank reaches after it finished call k.
+constexpr long kOneShotMaxN = 256 * 1024;      // floats (1 MB)
+__global__ void __launch_bounds__(kCommThreads)
+allreduce_oneshot_kernel(Peers pp, float* __restrict__ data, long n4, int rank, int world) {
+  pdl_trigger();
+  pdl_wait();                        // the local gradient is complete
+  __shared__ unsigned s_epoch, s_bad;
+  unsigned char* my = pp.win[rank];
+  if (threadIdx.x == 0) {
+    unsigned* ctr = reinterpret_cast<unsigned*>(my) + 2 * kCommBlocks * kMaxPeers + blockIdx.x;
+    s_epoch = *ctr + 1;
+    *ctr = s_epoch;
+    s_bad = *reinterpret_cast<volatile unsigned*>(reinterpret_cast<unsigned*>(my) + kErrWord);
+  }
+  __syncthreads();
+  const unsigned epoch = s_epoch;
+  const long t0 = static_cast<long>(blockIdx.x) * kCommThreads + threadIdx.x;
+  const long stride = static_cast<long>(gridDim.x) * kCommThreads;
+  float4* data4 = reinterpret_cast<float4*>(data);
+  const long buf = static_cast<long>(epoch & 1u) * world * n4;          // float4 offset of this call's slot set
+  for (int k = 1; k < world; ++k) {
+    const int p = (rank + k) % world;
+    float4* dst = reinterpret_cast<float4*>(pp.win[p] + kFlagBytes) + buf + rank * n4;
+    for (long j = t0; j < n4; j += stride) dst[j] = data4[j];
+  }
+  cta_barrier_across_ranks(pp, 0, rank, world, epoch, &s_bad);
+  const float4* slots = reinterpret_cast<const float4*>(my + kFlagBytes) + buf;
+  const bool bad = s_bad != 0u;
+  const float qnan = __int_as_float(0x7fc00000);
+  for (long j = t0; j < n4; j += stride) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < world; ++q) {
+      const float4 v = q == rank ? data4[j] : ld_peer_written(slots + q * n4 + j);
+      if (q == 0) acc = v;
+      else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    }
+    data4[j] = bad ? make_float4(qnan, qnan, qnan, qnan) : acc;
+  }
+}
+
 inline long chunk4_of(long n, int world) { return ((n / 4) + world - 1) / world; }
+inline bool use_oneshot(long n) {
+  static const bool off = getenv("FD_COMM_TWO_SHOT") != nullptr;
+  return !off && n <= kOneShotMaxN;
+}
 
 }  // namespace
 }  // namespace fd
@@ -145,6 +196,7 @@ using namespace fd;
 
 extern "C" long fd_comm_window_bytes(long n, int world) {
   if (n <= 0 || n % 4 != 0 || world < 1 || world > kMaxPeers) return -1;
+  if (use_oneshot(n)) return static_cast<long>(kFlagBytes) + 2L * world * n * 4;      // two slot sets of world x n floats
   return static_cast<long>(kFlagBytes) + 2L * world * chunk4_of(n, world) * 16;
 }
 
@@ -227,8 +279,12 @@ extern "C" int fd_allreduce_sum_f32_blocks(void* const* windows, int rank, int w
     if (!windows[i]) return FD_EINVAL;
     pp.win[i] = static_cast<unsigned char*>(windows[i]);
   }
-  launch_k(allreduce_sum_kernel, dim3(blocks), dim3(kCommThreads), 0, static_cast<cudaStream_t>(stream), pp, data,
-           n / 4, chunk4_of(n, world), rank, world);
+  if (use_oneshot(n))
+    launch_k(allreduce_oneshot_kernel, dim3(blocks), dim3(kCommThreads), 0, static_cast<cudaStream_t>(stream), pp, data, n / 4,
+             rank, world);
+  else
+    launch_k(allreduce_sum_kernel, dim3(blocks), dim3(kCommThreads), 0, static_cast<cudaStream_t>(stream), pp, data,
+             n / 4, chunk4_of(n, world), rank, world);
   count_launch();
   return launch_status();
 }

@@ -39,36 +39,38 @@ def _worker(rank, world, port, ndev, q):
         dev = torch.device("cuda", rank % ndev)
         torch.cuda.set_device(dev)
         dist.init_process_group(backend="gloo", rank=rank, world_size=world)
-        n = 769352                                           # the PoolResnet-medium flat gradient buffer
-        ar = par.PeerAllReduce.create(n, dev)
-        if ar is None:
+        ok = True
+        # the PoolResnet-medium flat gradient buffer (two-shot scatter / reduce / broadcast kernel) and a buffer of the size
+        # of the split exchange's "late" region (one-shot kernel: every rank pushes everything, one barrier, local sum)
+        for n in (769352, 180224):
+          ar = par.PeerAllReduce.create(n, dev)
+          if ar is None:
             q.put((rank, "unavailable"))
             return
-        flat = torch.empty(n, device=dev)
-        ok = True
-        for call in range(4):                                # eager calls: epochs advance
-            flat.copy_(_data(rank, call, n))
-            ar(flat)
-            want = _data(0, call, n)
-            for r in range(1, world):
-                want = want + _data(r, call, n)
-            ok = ok and torch.equal(flat.cpu(), want)
-        side = torch.cuda.Stream()                           # the same launch replayed from a CUDA graph
-        side.wait_stream(torch.cuda.current_stream())
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(graph, stream=side):
-                ar(flat)
-        torch.cuda.current_stream().wait_stream(side)
-        for call in range(4, 7):
-            flat.copy_(_data(rank, call, n))
-            graph.replay()
-            want = _data(0, call, n)
-            for r in range(1, world):
-                want = want + _data(r, call, n)
-            ok = ok and torch.equal(flat.cpu(), want)
-        ok = ok and ar.status() == 0
-        ar.close()
+          flat = torch.empty(n, device=dev)
+          for call in range(4):                                # eager calls: epochs advance
+              flat.copy_(_data(rank, call, n))
+              ar(flat)
+              want = _data(0, call, n)
+              for r in range(1, world):
+                  want = want + _data(r, call, n)
+              ok = ok and torch.equal(flat.cpu(), want)
+          side = torch.cuda.Stream()                           # the same launch replayed from a CUDA graph
+          side.wait_stream(torch.cuda.current_stream())
+          graph = torch.cuda.CUDAGraph()
+          with torch.cuda.stream(side):
+              with torch.cuda.graph(graph, stream=side):
+                  ar(flat)
+          torch.cuda.current_stream().wait_stream(side)
+          for call in range(4, 7):
+              flat.copy_(_data(rank, call, n))
+              graph.replay()
+              want = _data(0, call, n)
+              for r in range(1, world):
+                  want = want + _data(r, call, n)
+              ok = ok and torch.equal(flat.cpu(), want)
+          ok = ok and ar.status() == 0
+          ar.close()
         dist.destroy_process_group()
         q.put((rank, "ok" if ok else "mismatch"))
     except Exception as e:  # noqa: BLE001
