@@ -34,6 +34,9 @@ def test_sass_uses_tcgen05_and_tma():
     sass = subprocess.run([cuobjdump, "-sass", fd.native.LIB_PATH], capture_output=True, text=True).stdout
     for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnem in sass, mnem
+    # the wide kernels are CTA-pair kernels: tcgen05.mma.cta_group::2, multicast commit, cta_group::2 TMA loads
+    for mnem in ("UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "UTMALDG.4D.2CTA"):
+        assert mnem in sass, mnem
 
 
 def test_reference_interface_and_state_dict_keys():
