@@ -65,6 +65,7 @@ struct WideParams {
   uint32_t in_buf_bytes;        // bytes reserved per input ring buffer
   uint32_t stg_bytes, stg_buf_bytes;   // one staging UNIT: a whole plane-tile, or (split) the rows of one 128-row block
   int wslots;                   // weight ring depth
+  int resident;                 // every weight chunk of a tile has its own slot: loaded ONCE per CTA, no ring hand-shake
   int share;                    // SHARED-TILE mode (fewer tiles than SM pairs): the pair works on ONE two-block tile, CTA r
                                 // owns block r; outputs / residual through plain vector loads / stores, no staging
   const __nv_bfloat16* res_ptr[2];
@@ -293,9 +294,10 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
     if (elect_one_sync()) {
       uint32_t s = 0, ph = 0;              // ring slot and its phase
       for (int j = group; j < njobs; j += ngroups) {
+        if (p.resident && j != group) break;          // resident weights: the first tile's loads serve every tile
         for (int kh = 0; kh < p.gin; ++kh) {
           for (int r = 0; r < p.ngrp; ++r) {
-            mbar_wait_sleep(w_empty + s, ph ^ 1u);
+            if (!p.resident) mbar_wait_sleep(w_empty + s, ph ^ 1u);
             if (leader) mbar_expect_tx(w_full + s, kChunkBytes * kCg);
             for (int i = 0; i < p.tpg; ++i)
               tma_load_2d_g<kCg>(sW + s * kChunkBytes + i * kTapBytes, &maps.w, leader_bar<kCg>(w_full + s), 0,
@@ -328,8 +330,10 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
           uint32_t a_lo = sdesc_lo(smem_u32(sIn + ib * p.in_buf_bytes), 16) + (p.tap_lo != 0 ? wp_units + 8u : 0u);
 #pragma unroll 1
           for (int r = 0; r < p.ngrp; ++r) {
-            FD_WT(2, mbar_wait(w_full + s, wph));
-            tc_fence_after();
+            if (!p.resident || it == 0) {
+              FD_WT(2, mbar_wait(w_full + s, wph));
+              tc_fence_after();
+            }
             uint32_t b_lo = sdesc_lo(smem_u32(sW + s * kChunkBytes), 16);
 #pragma unroll 1
             for (int i = 0; i < p.tpg; ++i) {
@@ -344,7 +348,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
               a_lo += 8u;                            // next column
               b_lo += kTapBytes >> 4;
             }
-            umma_commit_g<kCg>(w_empty + s);         // weight slot free (in both CTAs) once these MMAs have read it
+            if (!p.resident) umma_commit_g<kCg>(w_empty + s);     // weight slot free (in both CTAs) once these MMAs have read it
             if (++s == static_cast<uint32_t>(p.wslots)) { s = 0; wph ^= 1u; }
             a_lo += wp_units - 24u;                  // next kernel row
           }
@@ -799,6 +803,16 @@ int fd::conv3x3_pairs(int nout, const fd_bf16* const* x, int gin, const fd_bf16*
     if (rc != FD_OK) return rc;
     rc = make_tmap_nhwc_bf16(&maps.res[g], p.has_res ? residual[gs] : x[0], B, H, W, kC, bestTW, p.rpb);
     if (rc != FD_OK) return rc;
+  }
+  p.resident = 0;
+  {
+    // all gin x ngrp chunks fit beside the buffers: keep them resident (the 64-output instantiation: 36 KB per CTA)
+    const int all = gin * p.ngrp;
+    if (!p.share && all <= kMaxWSlots && wide_smem_fixed(bestR, p.Wp, bestTW) + all * wide_chunk_bytes(cg, tpg, nout) <= smem_cap &&
+        !getenv("FD_WIDE_NO_RESIDENT")) {
+      p.resident = 1;
+      p.wslots = all;
+    }
   }
   size_t smem = wide_smem_fixed(bestR, p.Wp, bestTW) + p.wslots * wide_chunk_bytes(cg, tpg, nout);
   if (p.share) {

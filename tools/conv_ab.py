@@ -22,7 +22,7 @@ for (B, H, W) in [(64, 60, 60), (64, 30, 30), (64, 15, 15), (16, 240, 240), (16,
     for name, fl in (("fused", 0), ("one_tap", ops.CONV_ONE_TAP)):
         def run():
             for i in range(nbuf):
-                ops.conv3x3(xs[i], wf, bias=bias, lrelu=True, residual=rs[i], mask_out=mo, out=os_[i], flags=fl)
+                ops.conv3x3(xs[i], wf, bias=bias, lrelu=True, residual=None if os.environ.get('AB_NO_RES') else rs[i], mask_out=mo, out=os_[i], flags=fl)
         side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             run()
@@ -39,4 +39,15 @@ for (B, H, W) in [(64, 60, 60), (64, 30, 30), (64, 15, 15), (16, 240, 240), (16,
         us = a.elapsed_time(b) / 10 / nbuf * 1e3
         tf = 2.0 * B * H * W * C * C * 9 / us / 1e6
         line += f" | {name}: {us:7.1f} us {tf:7.1f} TF/s"
+        if name == "fused" and os.environ.get("FD_WIDE_TIMING") and os.environ.get("FD_CONV_PAIR"):
+            import ctypes
+            L = fd.native.lib()
+            buf = (ctypes.c_ulonglong * 16)()
+            L.fd_debug_wide_timing(buf, 1)
+            g.replay(); torch.cuda.synchronize()
+            L.fd_debug_wide_timing(buf, 1)
+            v = list(buf); tiles = max(1, v[4]); nl = max(1, v[11])
+            print(f"    pair kernel, CTA0 per tile (clk): MMA thread total {v[3] / tiles:.0f} = acc_empty {v[0] / tiles:.0f} + input {v[1] / tiles:.0f} + weights {v[2] / tiles:.0f} + issue {(v[3] - v[0] - v[1] - v[2]) / tiles:.0f}; "
+                  f"epilogue total {v[7] / tiles:.0f}, wait acc_full {v[5] / tiles:.0f}, wait staging {v[6] / tiles:.0f}; per launch: entry->MMA loop {v[8] / nl:.0f}, MMA end->exit {v[9] / nl:.0f}, tiles {tiles / nl:.1f}")
+
     print(line, flush=True)
