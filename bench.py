@@ -637,7 +637,8 @@ def f128_train(fd, dev, world, args, barrier, par, peaks):
     x_cpu, boxes = synth_batch(B, seed_img=20, seed_box=21)
     gt = fd.datasets.WIDERFace.dataset.convert_bbx_to_feature_map_batch(boxes, S, (480, 480), device=dev)
     x = x_cpu.to(dev)
-    topt = torch.optim.Adam(m.parameters(), lr=LR, capturable=True)
+    topt = m.flat_optimizer(lr=LR, capturable=True)      # fd_adam_flat over the engine's flat buffers: one launch
+    topt._ensure_state()
     for name, prm in m.named_parameters():
         prm.grad = eng.grad_view(name)
     calls = {"conv": [], "wgrad": []}
@@ -684,7 +685,7 @@ def f128_train(fd, dev, world, args, barrier, par, peaks):
             "launches_per_step": launches, "cuda_graph": True,
             "achieved_tflops_algorithmic": 3 * 3.997e9 * B / (ms * 1e-3) / 1e12,
             "workload": "PoolResnet(filters=128, S=10, 10 blocks, 480x480; the width train_model.py:17 trains) train step: "
-                        "forward + summed YoloLoss + backward + Adam (torch, capturable), batch 64, train-mode Dropout2d",
+                        "forward + summed YoloLoss + backward + Adam (fd_adam_flat), batch 64, train-mode Dropout2d",
             "roofline_conv_wide_60x60": roof(big, lambda c: o_conv(c[0], c[1], **c[2]), conv_fl,
                                              "conv3x3_wide_kernel<2> (tcgen05.mma.cta_group::2, M=256 N=128; the 60x60 forward + "
                                              "input-gradient launches of one step)", "conv3x3_wide_kernel_60x60"),

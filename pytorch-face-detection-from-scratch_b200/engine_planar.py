@@ -176,12 +176,22 @@ class PlanarEngine:
         off, n, shape = self.offsets[name]
         return flat[off:off + n].view(shape)
 
-    def grad_view(self, name: str) -> torch.Tensor:
+    def _view(self, flat, name: str) -> torch.Tensor:
         if name.startswith("residual_blocks."):
             _, k, c, kind = name.split(".")
             layer = 2 * int(k) + (0 if c == "conv1" else 1)
-            return self.section(self.gflat, "w3" if kind == "weight" else "b3")[layer]
-        return self.section(self.gflat, name)
+            return self.section(flat, "w3" if kind == "weight" else "b3")[layer]
+        return self.section(flat, name)
+
+    def grad_view(self, name: str) -> torch.Tensor:
+        return self._view(self.gflat, name)
+
+    # flat fp32 parameter / gradient buffers: the unit of the one-kernel Adam (optim.FlatAdam) and of the data-parallel exchange
+    def opt_params(self) -> torch.Tensor:
+        return self.pflat
+
+    def opt_grads(self) -> torch.Tensor:
+        return self.gflat
 
     def bind(self, params):
         dev = params["conv1.weight"].device
@@ -191,6 +201,7 @@ class PlanarEngine:
             self.device = dev
             G, L = self.G, 2 * self.num_blocks
             self.gflat = torch.zeros(self.n_flat, dtype=F32, device=dev)
+            self.pflat = torch.zeros(self.n_flat, dtype=F32, device=dev)
             self.dwp = torch.zeros((L * G * G, 9 * 64 * 64), dtype=F32, device=dev)        # packed accumulators
             self.dw_sub = torch.empty((L * G * G, 64, 64, 3, 3), dtype=F32, device=dev)
             self.gb3 = torch.zeros((L, G, 64), dtype=F32, device=dev)
@@ -201,6 +212,15 @@ class PlanarEngine:
                 self.w_dgrad_wide = torch.empty((L, G // 2, G, 9, 128, 64), dtype=BF16, device=dev)
             self.sides = [torch.cuda.Stream(device=dev) for _ in range(self.G - 1)]
             self.plans.clear()
+        # every nn.Parameter becomes a view of the flat buffer (values preserved): the stacked [L,F,F,3,3] weights the pack
+        # kernel reads and the buffer FlatAdam updates are then the parameters themselves
+        for name in self.param_names():
+            prm = params[name]
+            v = self._view(self.pflat, name)
+            if prm.data_ptr() != v.data_ptr():
+                with torch.no_grad():
+                    v.copy_(prm.data.to(device=dev, dtype=F32))
+                prm.data = v
         self.params = params
 
     def plan(self, B, train):
@@ -231,19 +251,13 @@ class PlanarEngine:
     def pack_weights(self):
         """[L,64G,64G,3,3] fp32 -> sub-blocks [(L,g,h),64,64,3,3] (torch data movement) -> bf16 forward / dgrad packing."""
         G, L = self.G, 2 * self.num_blocks
-        P = self.params
-        ws, bs = [], []
-        for k in range(self.num_blocks):
-            for c in ("conv1", "conv2"):
-                ws.append(P[f"residual_blocks.{k}.{c}.weight"].detach())
-                bs.append(P[f"residual_blocks.{k}.{c}.bias"].detach())
-        w_all = torch.stack(ws).float()
+        w_all = self.section(self.pflat, "w3")          # [L,F,F,3,3]: the parameters themselves (bind)
         if self.use_wide:
             ops.pack_conv3x3_wide(w_all, self.w_fwd_wide, self.w_dgrad_wide)
         else:
             w3 = w_all.view(L, G, 64, G, 64, 3, 3).permute(0, 1, 3, 2, 4, 5, 6).contiguous()
             ops.pack_conv3x3(w3.view(L * G * G, 64, 64, 3, 3), self.w_fwd, self.w_dgrad)
-        self.b3 = torch.stack(bs).float().view(L, G, 64).contiguous()
+        self.b3 = self.section(self.pflat, "b3").view(L, G, 64)
 
     # ------------------------------------------------------------------ forward
     def _conv_sum(self, srcs, wsel, layer, g, bias, dst_a, dst_b, **last_kw):

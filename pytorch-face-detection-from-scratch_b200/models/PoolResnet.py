@@ -170,9 +170,9 @@ class GridBackbone(BaseModel):
     def flat_optimizer(self, lr: float = 1e-4, capturable: bool = False):
         """One-kernel Adam over the flat parameter buffer (optim.FlatAdam); lr default = ModelMeta's (ModelMeta.py:86)."""
         from ..optim import FlatAdam
-        if not isinstance(self.engine, BackboneEngine):        # PaddedBackboneEngine is a BackboneEngine
-            raise NotImplementedError("flat_optimizer needs the flat parameter buffer of the 64-channel engine; use "
-                                      "torch.optim.Adam(model.parameters()) (ModelMeta.configure_optimizers) for wider models")
+        if not hasattr(self.engine, "opt_params"):
+            raise NotImplementedError("flat_optimizer needs an engine with a flat parameter buffer; use "
+                                      "torch.optim.Adam(model.parameters()) (ModelMeta.configure_optimizers)")
         self.engine.bind(dict(self.named_parameters()))
         return FlatAdam(self.engine, lr=lr, capturable=capturable)
 

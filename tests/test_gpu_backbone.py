@@ -281,6 +281,37 @@ def test_train_step_with_flat_adam_matches_torch_adam_and_graph_replay():
     assert e <= 2e-2, e
 
 
+def test_filters128_flat_adam_matches_torch_adam():
+    """PoolResnet(filters=128) (PlanarEngine): the parameters are views of one flat buffer, so the fused step runs the
+    one-kernel Adam (fd_adam_flat) -- after every step the flat buffer equals torch.optim.Adam fed with the same
+    gradients and the nn.Parameters see the update."""
+    require_cuda()
+    pkg = fd()
+    gen = torch.Generator().manual_seed(7)
+    B, S = 2, 10
+    x = torch.rand(B, 3, 480, 480, generator=gen).cuda()
+    boxes = [synth_boxes(gen, 1, 30) for _ in range(B)]
+    gt = pkg.datasets.WIDERFace.dataset.convert_bbx_to_feature_map_batch(boxes, S, (480, 480), device=torch.device("cuda"))
+    torch.manual_seed(3)
+    m = pkg.models.PoolResnet.PoolResnet(filters=128, input_shape=(3, 480, 480), num_of_patches=S).cuda().eval()
+    opt = m.flat_optimizer(lr=1e-3)
+    eng = m.engine
+    assert type(eng).__name__ == "PlanarEngine"
+    assert m.residual_blocks[3].conv2.weight.data_ptr() == eng._view(eng.pflat, "residual_blocks.3.conv2.weight").data_ptr()
+    mirror = eng.pflat.clone().requires_grad_(True)
+    p_start = eng.pflat.clone()
+    topt = torch.optim.Adam([mirror], lr=1e-3)
+    losses = []
+    for _ in range(3):
+        pl = eng.train_step(x, gt, dropout=False, optimizer=opt)
+        losses.append(pl.loss.sum().item())
+        mirror.grad = eng.gflat.clone()
+        topt.step()
+        assert (eng.pflat - mirror.detach()).abs().max().item() <= 2e-6
+    assert all(l == l for l in losses)                    # finite; the update itself is pinned against torch.optim.Adam above
+    assert (eng.pflat - p_start).abs().max().item() > 0
+
+
 def _flat_of(model, eng):
     flat = torch.zeros(eng.n_flat, device="cuda")
     for name, p in model.named_parameters():
