@@ -92,7 +92,8 @@ FD_API int fd_conv3x3_pool(const fd_bf16* x, const fd_bf16* w_packed, int B, int
  * tcgen05.mma.cta_group::2 (the two SMs of a TPC on one M=256, N=128 tile, B operand split between their shared
  * memories), partial sums over input planes in TMEM, weights streamed from L2.  Epilogue exactly as fd_conv3x3, per
  * output plane: x[gin], residual[2], mask_out[2], out[2], mask_in[2], chan_scale[2] ([B,64] each), chan_scale2[2],
- * out2[2] are arrays of per-plane device pointers (NULL array = absent); bias is [128].  Exactly one of out / out2.
+ * out2[2] are arrays of per-plane device pointers (NULL array = absent); bias is [128].  One of out / out2 (both: see
+ * fd_conv3x3_wide_shared_tile).
  * w_packed: bf16 [gin][9][128][64] (tap-major chunks of 128 couts x 64 cins) as written by fd_pack_conv3x3_wide for
  * this launch's group of 128 output channels.  FD_CONV_1X1: centre tap only (pointwise convolution). */
 FD_API int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* w_packed, int B, int H, int W,
@@ -100,6 +101,11 @@ FD_API int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* w_pa
                     const fd_bf16* const* residual, uint32_t* const* mask_out, fd_bf16* const* out,
                     const uint32_t* const* mask_in, const float* const* chan_scale2, fd_bf16* const* out2,
                     int flags, void* stream);
+/* 1 when fd_conv3x3_wide runs this map in SHARED-TILE mode (fewer two-block tiles than SM pairs: a CTA pair works on ONE
+ * tile, outputs through plain stores).  Only in that mode may out AND out2 both be given: out = the (residual-added) sum,
+ * out2 = its LeakyReLU'-masked, chan_scale2-scaled copy -- the input gradient of a block and the gradient entering the
+ * previous block's conv2 in one launch (models/PoolResnet.py:35-40 backward).  Otherwise both -> FD_EUNSUPPORTED. */
+FD_API int fd_conv3x3_wide_shared_tile(int B, int H, int W, int flags);
 /* w: [n_layers][Cout][Cin][3][3] fp32 (torch layout) -> w_fwd [n_layers][Cout/128][Cin/64][9][128][64] bf16 (forward)
  * and w_dgrad [n_layers][Cin/128][Cout/64][9][128][64] bf16 (input gradient: taps flipped, channel roles swapped).
  * Either output may be NULL.  Cout (w_fwd) / Cin (w_dgrad) must be multiples of 128, the other a multiple of 64. */

@@ -70,6 +70,7 @@ struct WideParams {
                                 // owns block r; outputs / residual through plain vector loads / stores, no staging
   const __nv_bfloat16* res_ptr[2];
   __nv_bfloat16* out_ptr[2];
+  __nv_bfloat16* out2_ptr[2];   // shared-tile mode only: BOTH outputs (out = the sum, out2 = its masked / scaled copy)
   int tpg, ngrp;                // taps per weight chunk (3: a kernel row; 1: centre-tap mode) and chunks per input plane
   int split, rpb, units;        // split: 128 % Wp == 0, a block = rpb whole tile rows = one staging unit; units per plane-tile
   uint32_t inv_wp;
@@ -454,16 +455,20 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
             if (p.mask_out[g]) p.mask_out[g][pix * 4 + cq] = static_cast<uint16_t>(epi_sign_bits16(v2));
             if (p.has_res) epi_add_bf16x16(v2, rr[g][0], rr[g][1]);
             uint4 u0, u1;
-            if (!p.staged_out2) {
+            if (!p.staged_out2 || p.out2_ptr[g]) {
               epi_pack16(v2, u0, u1);
-            } else {
+              uint4* op = reinterpret_cast<uint4*>(p.out_ptr[g] + pix * kC + c0);
+              op[0] = u0;
+              op[1] = u1;
+            }
+            if (p.staged_out2 || p.out2_ptr[g]) {
               uint64_t o2[8];
               epi_masked16(v2, mb2[g], p.slope, sConst + 2 * kNOut + g * kC + c0, has_cs2, o2);
               epi_pack16(o2, u0, u1);
+              uint4* op = reinterpret_cast<uint4*>((p.out2_ptr[g] ? p.out2_ptr[g] : p.out_ptr[g]) + pix * kC + c0);
+              op[0] = u0;
+              op[1] = u1;
             }
-            uint4* op = reinterpret_cast<uint4*>(p.out_ptr[g] + pix * kC + c0);
-            op[0] = u0;
-            op[1] = u1;
           }
         }
         tc_fence_before();
@@ -690,6 +695,58 @@ extern "C" int fd_pack_conv1x1_wide(const float* w, int n_layers, int Cout, int 
   return pack_conv_wide(w, n_layers, Cout, Cin, 1, w_fwd, w_dgrad, stream);
 }
 
+namespace fd {
+namespace {
+constexpr size_t kWideSmemCap = 227 * 1024 - 64;     // dynamic shared memory: the kernel also has 16 bytes of static (timing) state
+inline int wide_cta_group() {
+  static const int cg_env = [] { const char* e = getenv("FD_WIDE_CTA_GROUP"); return e ? atoi(e) : 2; }();
+  return cg_env == 1 ? 1 : 2;
+}
+inline bool wide_share_allowed(int cg) { return cg == 2 && !getenv("FD_WIDE_NO_SHARE"); }
+// Tiling: TW <= 62 output columns, R rows with R * (TW + 2) <= 256 GEMM rows (two 128-row blocks = 2 x 128 TMEM columns,
+// double buffered).  Cost model: tensor time of the padded blocks times the number of waves over the CTA groups; a map
+// with fewer two-block tiles than SM pairs runs in shared-tile mode (one block per CTA).
+inline void wide_pick_tiling(int cg, int nout, int tpg, int B, int H, int W, int* bestR, int* bestTW) {
+  const int nsm = sm_count();
+  const bool share_ok = wide_share_allowed(cg);
+  double best = 1e30;
+  *bestR = *bestTW = 0;
+  const int min_tw_tiles = (W + 61) / 62;
+  for (int tw_tiles = min_tw_tiles; tw_tiles <= min_tw_tiles + 2; ++tw_tiles) {
+    const int TW = (W + tw_tiles - 1) / tw_tiles;
+    if (TW > 62 || TW < 1) continue;
+    const int Wp = TW + 2;
+    for (int R = 1; R <= H && R + 2 <= 256; ++R) {
+      const int nblk = (R * Wp + 127) / 128;
+      if (nblk > 2) break;
+      if (wide_slots(cg, tpg, R, Wp, TW, kWideSmemCap, nout) == 0) break;
+      const long tiles = static_cast<long>(B) * ((H + R - 1) / R) * tw_tiles;
+      const long waves = (tiles + nsm - 1) / nsm;
+      double cost = waves * (2400.0 * nblk + 600.0);
+      if (share_ok && nblk == 2 && tiles <= nsm / 2) cost = 2400.0 + 600.0;     // shared-tile mode: one block per CTA
+      if (cost < best) { best = cost; *bestR = R; *bestTW = TW; }
+    }
+  }
+}
+inline bool wide_is_shared_tile(int cg, int nout, int tpg, int B, int H, int W) {
+  int R = 0, TW = 0;
+  wide_pick_tiling(cg, nout, tpg, B, H, W, &R, &TW);
+  if (R == 0) return false;
+  const int Wp = TW + 2, nblk = (R * Wp + 127) / 128;
+  const long tiles = static_cast<long>(B) * ((H + R - 1) / R) * ((W + TW - 1) / TW);
+  return wide_share_allowed(cg) && nblk == 2 && tiles <= sm_count() / 2;
+}
+}  // namespace
+}  // namespace fd
+
+// 1 when fd_conv3x3_wide will run this shape in SHARED-TILE mode (fewer two-block tiles than SM pairs: the pair works on one
+// tile) -- the mode in which it can write BOTH outputs (out and out2) in one launch.
+extern "C" int fd_conv3x3_wide_shared_tile(int B, int H, int W, int flags) {
+  using namespace fd;
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return wide_is_shared_tile(wide_cta_group(), 128, (flags & FD_CONV_1X1) ? 1 : 3, B, H, W) ? 1 : 0;
+}
+
 // nout = 128: the wide API below; nout = 64: one output plane -- the 64-channel layers of conv3x3_tc.cu on CTA pairs
 // (w_packed = the tap-major [9][64][64] packing of fd_pack_conv3x3, every per-plane array has ONE entry)
 int fd::conv3x3_pairs(int nout, const fd_bf16* const* x, int gin, const fd_bf16* w_packed, int B, int H, int W,
@@ -708,38 +765,20 @@ int fd::conv3x3_pairs(int nout, const fd_bf16* const* x, int gin, const fd_bf16*
       if (!arr[g]) return false;
     return true;
   };
-  const bool has_out = all_set(out), has_out2 = all_set(out2);
-  if (has_out == has_out2) return FD_EINVAL;                 // exactly one staged output (every plane)
+  bool has_out = all_set(out), has_out2 = all_set(out2);
+  if (!has_out && !has_out2) return FD_EINVAL;
+  const bool dual = has_out && has_out2;                     // both outputs: the shared-tile mode only (checked below)
   if (mask_in && !has_out2) return FD_EINVAL;
   if (has_out2 && !all_set(mask_in)) return FD_EINVAL;
+  if (dual) has_out2 = false;                                // `out` is the primary (staged) output
   if (!(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;
-  static const int cg_env = [] { const char* e = getenv("FD_WIDE_CTA_GROUP"); return e ? atoi(e) : 2; }();
-  const int cg = cg_env == 1 ? 1 : 2;
+  const int cg = wide_cta_group();
   const int nsm = sm_count();
-  const size_t smem_cap = 227 * 1024 - 64;     // dynamic shared memory: the kernel also has 16 bytes of static (timing) state
-
-  // Tiling: TW <= 62 output columns, R rows with R * (TW + 2) <= 256 GEMM rows (two 128-row blocks = 2 x 128 TMEM columns,
-  // double buffered).  Cost model: tensor time of the padded blocks times the number of waves over the CTA groups.
+  const size_t smem_cap = kWideSmemCap;
   const int tpg = (flags & FD_CONV_1X1) ? 1 : 3;
-  const bool share_ok = cg == 2 && !getenv("FD_WIDE_NO_SHARE");
+  const bool share_ok = wide_share_allowed(cg);
   int bestR = 0, bestTW = 0;
-  double best = 1e30;
-  const int min_tw_tiles = (W + 61) / 62;
-  for (int tw_tiles = min_tw_tiles; tw_tiles <= min_tw_tiles + 2; ++tw_tiles) {
-    const int TW = (W + tw_tiles - 1) / tw_tiles;
-    if (TW > 62 || TW < 1) continue;
-    const int Wp = TW + 2;
-    for (int R = 1; R <= H && R + 2 <= 256; ++R) {
-      const int nblk = (R * Wp + 127) / 128;
-      if (nblk > 2) break;
-      if (wide_slots(cg, tpg, R, Wp, TW, smem_cap, nout) == 0) break;
-      const long tiles = static_cast<long>(B) * ((H + R - 1) / R) * tw_tiles;
-      const long waves = (tiles + nsm - 1) / nsm;
-      double cost = waves * (2400.0 * nblk + 600.0);
-      if (share_ok && nblk == 2 && tiles <= nsm / 2) cost = 2400.0 + 600.0;     // shared-tile mode: one block per CTA
-      if (cost < best) { best = cost; bestR = R; bestTW = TW; }
-    }
-  }
+  wide_pick_tiling(cg, nout, tpg, B, H, W, &bestR, &bestTW);
   if (bestR == 0) return FD_EUNSUPPORTED;
 
   WideParams p;
@@ -762,10 +801,12 @@ int fd::conv3x3_pairs(int nout, const fd_bf16* const* x, int gin, const fd_bf16*
   p.share = (share_ok && p.nblk == 2 && p.num_tiles <= nsm / 2) ? 1 : 0;
   fd_bf16* const* staged_planes = has_out ? out : out2;
   const bool has_res = all_set(residual);
+  if (dual && !p.share) return FD_EUNSUPPORTED;              // fd_conv3x3_wide_shared_tile() tells the caller beforehand
   for (int g = 0; g < 2; ++g) {
     const int gs = g < np ? g : 0;
     p.res_ptr[g] = has_res ? reinterpret_cast<const __nv_bfloat16*>(residual[gs]) : nullptr;
     p.out_ptr[g] = reinterpret_cast<__nv_bfloat16*>(staged_planes[gs]);
+    p.out2_ptr[g] = dual ? reinterpret_cast<__nv_bfloat16*>(out2[gs]) : nullptr;
   }
   p.tpg = tpg;
   p.ngrp = (flags & FD_CONV_1X1) ? 1 : 3;

@@ -368,19 +368,21 @@ class PlanarEngine:
             ops.head_bwd(pl.head_in[g], drop[nb, g] if drop is not None else None, pl.w_head[g], pl.y, dy, self.head_pad,
                          last.G[g], None, None, self.slope, None, dwg, dbg)
             gw_out[:, g * 64:(g + 1) * 64].copy_(dwg)
+        fused_gp2 = set()
         for k in range(nb - 1, -1, -1):
             blk = pl.blocks[k]
             L1, L2 = 2 * k, 2 * k + 1
-            main = self._fork()
-            for g in range(G):
-                with self._on(main, g):
-                    cs = drop[k, g] if drop is not None else None
-                    if blk.pool:
-                        ops.maxpool2x2_bwd(blk.s[g], blk.G[g], blk.gs[g], blk.mb[g], cs, self.slope, blk.gp2[g],
-                                           argmax=blk.amax[g])
-                    else:
-                        ops.grad_mask(blk.G[g], self.slope, blk.mb[g], cs, blk.gp2[g])
-            self._join(main)
+            if not (k in fused_gp2):        # gp2 of this block was already written by the previous iteration's dual-output launch
+                main = self._fork()
+                for g in range(G):
+                    with self._on(main, g):
+                        cs = drop[k, g] if drop is not None else None
+                        if blk.pool:
+                            ops.maxpool2x2_bwd(blk.s[g], blk.G[g], blk.gs[g], blk.mb[g], cs, self.slope, blk.gp2[g],
+                                               argmax=blk.amax[g])
+                        else:
+                            ops.grad_mask(blk.G[g], self.slope, blk.mb[g], cs, blk.gp2[g])
+                self._join(main)
             GS = blk.gs if blk.pool else blk.G
             gprev = pl.blocks[k - 1].G if k > 0 else pl.g_stem
             if self.use_wide:
@@ -388,9 +390,21 @@ class PlanarEngine:
                 for go in range(G // 2):
                     ops.conv3x3_wide(blk.gp2, self.w_dgrad_wide[L2, go], slope=self.slope, mask_in=self._pairs(blk.ma, go),
                                      out2=self._pairs(blk.gp1, go))
+                # the previous block's conv2 gradient (gp2 = G * lrelu'(b) * dropout) rides on the same launch when the map
+                # runs in shared-tile mode and the previous block does not pool (its G is exactly this launch's output)
+                prev = pl.blocks[k - 1] if k > 0 else None
+                dual = prev is not None and not prev.pool and ops.conv3x3_wide_shared_tile(pl.B, blk.H, blk.W)
                 for go in range(G // 2):
-                    ops.conv3x3_wide(blk.gp1, self.w_dgrad_wide[L1, go], slope=self.slope, residual=self._pairs(GS, go),
-                                     out=self._pairs(gprev, go))
+                    if dual:
+                        cs2 = [drop[k - 1, 2 * go], drop[k - 1, 2 * go + 1]] if drop is not None else None
+                        ops.conv3x3_wide(blk.gp1, self.w_dgrad_wide[L1, go], slope=self.slope, residual=self._pairs(GS, go),
+                                         out=self._pairs(gprev, go), mask_in=self._pairs(prev.mb, go), chan_scale2=cs2,
+                                         out2=self._pairs(prev.gp2, go))
+                    else:
+                        ops.conv3x3_wide(blk.gp1, self.w_dgrad_wide[L1, go], slope=self.slope, residual=self._pairs(GS, go),
+                                         out=self._pairs(gprev, go))
+                if dual:
+                    fused_gp2.add(k - 1)
             else:
                 self._block_dgrad_planes(blk, L1, L2, GS, gprev)
             # weight / bias gradients: once per run, when the gp1 / gp2 of all its blocks are final

@@ -24,6 +24,7 @@ SIGNATURES = {
     "fd_conv3x3": [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "fd_conv3x3_pool": [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _I, _P],
     "fd_conv3x3_wide": [_P, _I, _P, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "fd_conv3x3_wide_shared_tile": [_I, _I, _I, _I],
     "fd_pack_conv3x3_wide": [_P, _I, _I, _I, _P, _P, _P],
     "fd_pack_conv1x1_wide": [_P, _I, _I, _I, _P, _P, _P],
     "fd_conv3x3_wgrad_wide": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _c.c_long, _P, _P, _c.c_long, _I, _P],

@@ -58,6 +58,11 @@ def conv3x3_wide(x_planes, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_
                                 cast[2], cast[3], cast[4], cast[5], cast[6], cast[7], fl, cur_stream()), "fd_conv3x3_wide")
 
 
+def conv3x3_wide_shared_tile(B, H, W, flags=0):
+    """True when fd_conv3x3_wide runs this map in shared-tile mode, i.e. may write out AND out2 in one launch."""
+    return bool(lib().fd_conv3x3_wide_shared_tile(int(B), int(H), int(W), int(flags)))
+
+
 def pack_conv3x3_wide(w, w_fwd, w_dgrad):
     """w: [L,Cout,Cin,k,k] (or [Cout,Cin,k,k]) fp32, k = 3 or 1 -> w_fwd [L,Cout/128,Cin/64,9,128,64], w_dgrad
     [L,Cin/128,Cout/64,9,128,64] (k = 1: only the centre tap is written -- for CONV_1X1)."""

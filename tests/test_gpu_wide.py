@@ -75,6 +75,13 @@ def test_conv3x3_wide_forward_and_dgrad(B, H, W, gin):
                          out2=out2)
         G2 = G * cs2[:, None, None, :] * torch.where(msk.float() > 0, 1.0, 0.2)
         _close(_cat(out2), G2, "masked out2", rel=6e-3)
+        # shared-tile mode (fewer two-block tiles than SM pairs) writes BOTH outputs in one launch, bit-identical
+        if ops.conv3x3_wide_shared_tile(B, H, W):
+            oa = [torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+            ob = [torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+            ops.conv3x3_wide(_planes(g), wd[0, 0], residual=_planes(res), out=oa, mask_in=[_bits(m) for m in _planes(msk)],
+                             chan_scale2=cs2p, out2=ob)
+            assert all(torch.equal(a, b) for a, b in zip(oa, out)) and all(torch.equal(a, b) for a, b in zip(ob, out2))
 
 
 def test_conv3x3_wide_centre_tap_is_pointwise():
