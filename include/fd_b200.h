@@ -151,6 +151,9 @@ FD_API int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int nprob,
 FD_API int fd_pack_conv3x3(const float* w, int n_layers, int C, fd_bf16* w_fwd, fd_bf16* w_dgrad, void* stream);
 /* dw_packed [n_layers][9][ci][co] fp32 -> dw [n_layers][co][ci][3][3] fp32 (overwrites). */
 FD_API int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, float* dw, void* stream);
+/* Channel-plane engines: packed sub-blocks [n_layers][G (g)][G (h)][9][64 ci][64 co] fp32 -> the wide torch tensor
+ * dw [n_layers][64 G][64 G][3][3] fp32 (overwrites), in one pass. */
+FD_API int fd_unpack_wgrad3x3_planes(const float* dw_packed, int n_layers, int G, float* dw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A run of `n_blocks` residual blocks of ONE spatial shape without pooling (blocks 2..9 of the

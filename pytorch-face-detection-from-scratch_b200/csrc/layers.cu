@@ -62,6 +62,30 @@ unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, float* __res
   for (int i = threadIdx.x; i < kPackCo * row; i += 256) dst[i] = sm[(i / row) * pitch + i % row];
 }
 
+// The same for the channel-plane engines: packed 64 x 64 sub-blocks [layer][g][h][t][ci][co] -> the torch tensor of the WIDE
+// layer [layer][64 G (co)][64 G (ci)][ky][kx] directly (row of 576 floats per (co, h) at its place in the wide row): no
+// intermediate sub-block tensor and no permuting copy afterwards.
+__global__ void __launch_bounds__(256)
+unpack_wgrad3x3_planes_kernel(const float* __restrict__ dwp, int G, float* __restrict__ dw) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int C = 64, row = C * 9, pitch = row + 1, tiles = C / kPackCo;
+  __shared__ float sm[kPackCo * pitch];
+  const int sub = blockIdx.x / tiles, co0 = (blockIdx.x % tiles) * kPackCo;
+  const int h = sub % G, g = (sub / G) % G, l = sub / (G * G);
+  const long sbase = static_cast<long>(sub) * 9 * C * C;
+  for (int i = threadIdx.x; i < 9 * kPackCo * C; i += 256) {
+    const int co = i % kPackCo, ci = (i / kPackCo) % C, t = i / (C * kPackCo);
+    sm[co * pitch + ci * 9 + t] = __ldg(dwp + sbase + (static_cast<long>(t) * C + ci) * C + co0 + co);
+  }
+  __syncthreads();
+  const long F = static_cast<long>(G) * C;
+  for (int i = threadIdx.x; i < kPackCo * row; i += 256) {
+    const int co = i / row, r = i % row;
+    dw[((static_cast<long>(l) * F + g * C + co0 + co) * F + h * C) * 9 + r] = sm[co * pitch + r];
+  }
+}
+
 // Adam on the flat parameter / gradient buffers (models/ModelMeta.py:104-112: the reference's SAMSGD never
 // recomputes gradients, i.e. it is plain torch Adam).  Same update as torch.optim.Adam (no amsgrad, L2 weight decay):
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
@@ -1054,6 +1078,14 @@ extern "C" int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, f
     unpack_wgrad3x3_kernel<128><<<n_layers * (128 / kPackCo), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, n_layers, dw);
   else
     return FD_EUNSUPPORTED;
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int fd_unpack_wgrad3x3_planes(const float* dw_packed, int n_layers, int G, float* dw, void* stream) {
+  if (!dw_packed || !dw || n_layers <= 0 || G <= 0) return FD_EINVAL;
+  launch_k(unpack_wgrad3x3_planes_kernel, dim3(n_layers * G * G * (64 / kPackCo)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+           dw_packed, G, dw);
   count_launch();
   return launch_status();
 }

@@ -203,8 +203,7 @@ class PlanarEngine:
             self.gflat = torch.zeros(self.n_flat, dtype=F32, device=dev)
             self.pflat = torch.zeros(self.n_flat, dtype=F32, device=dev)
             self.dwp = torch.zeros((L * G * G, 9 * 64 * 64), dtype=F32, device=dev)        # packed accumulators
-            self.dw_sub = torch.empty((L * G * G, 64, 64, 3, 3), dtype=F32, device=dev)
-            self.gb3 = torch.zeros((L, G, 64), dtype=F32, device=dev)
+            self.gb3 = self.section(self.gflat, "b3").view(L, G, 64)       # bias gradients accumulate in place (gflat is zeroed per step)
             self.w_fwd = torch.empty((L * G * G, 9, 64, 64), dtype=BF16, device=dev)
             self.w_dgrad = torch.empty((L * G * G, 9, 64, 64), dtype=BF16, device=dev)
             if self.use_wide:             # [layer][group of 128 couts][input plane][tap][128][64]
@@ -359,7 +358,6 @@ class PlanarEngine:
         drop = pl.drop
         self.gflat.zero_()
         self.dwp.zero_()
-        self.gb3.zero_()
         last = pl.blocks[nb - 1]
         gw_out = self.section(self.gflat, "out.weight")
         for g in range(G):          # tensor-core head backward per plane; dbias is the same for every plane: count it once
@@ -431,10 +429,8 @@ class PlanarEngine:
             ops.stem_wgrad(pl.x, pl.g_stem[g], gw1[g * 64:(g + 1) * 64], gb1[g * 64:(g + 1) * 64], self.stem_s,
                            self.stem_pad, x_cache=pl.x_cache)
         L = 2 * nb
-        ops.unpack_wgrad3x3(self.dwp.view(L * G * G, 9, 64, 64), self.dw_sub)
-        self.section(self.gflat, "w3").copy_(
-            self.dw_sub.view(L, G, G, 64, 64, 3, 3).permute(0, 1, 3, 2, 4, 5, 6).reshape(L, self.F, self.F, 3, 3))
-        self.section(self.gflat, "b3").copy_(self.gb3.view(L, self.F))
+        # packed sub-blocks -> the [L,F,F,3,3] gradient section in one pass; the bias gradients were accumulated in place
+        ops.unpack_wgrad3x3_planes(self.dwp.view(L * G * G, 9, 64, 64), G, self.section(self.gflat, "w3"))
 
     def _block_dgrad_planes(self, blk, L1, L2, GS, gprev):
         G = self.G

@@ -35,6 +35,7 @@ SIGNATURES = {
     "fd_resblock_chain_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "fd_pack_conv3x3": [_P, _I, _I, _P, _P, _P],
     "fd_unpack_wgrad3x3": [_P, _I, _I, _P, _P],
+    "fd_unpack_wgrad3x3_planes": [_P, _I, _I, _P, _P],
     "fd_adam_flat": [_P, _P, _P, _P, _c.c_long, _F, _F, _F, _F, _F, _I, _P, _P],
     "fd_comm_window_bytes": [_c.c_long, _I],
     "fd_comm_error_offset": [],

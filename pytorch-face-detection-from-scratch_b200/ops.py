@@ -105,6 +105,12 @@ def conv3x3_wgrad_multi(x, g, dw_packed, dw_stride, dbias, dbias_stride, flags=0
           "fd_conv3x3_wgrad_multi")
 
 
+def unpack_wgrad3x3_planes(dw_packed, G, dw):
+    """dw_packed: [L*G*G, 9, 64, 64] fp32 sub-blocks (g-major, then h) -> dw: [L, 64G, 64G, 3, 3] fp32."""
+    check(lib().fd_unpack_wgrad3x3_planes(dptr(dw_packed, F32), dw.shape[0], int(G), dptr(dw, F32), cur_stream()),
+          "fd_unpack_wgrad3x3_planes")
+
+
 def resblock_chain_ok(H, W, C):
     return bool(lib().fd_resblock_chain_shape_ok(int(H), int(W), int(C)))
 
