@@ -89,11 +89,10 @@ def main():
     x = torch.rand(B, 3, 480, 480, generator=gen).cuda()
     gt = fd.datasets.WIDERFace.dataset.convert_bbx_to_feature_map_batch([synth_boxes(gen, 1, 100) for _ in range(B)], 10,
                                                                         (480, 480), device=dev)
-    topt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
-    for prm in m.parameters():
-        prm.grad = eng.grad_view([n for n, q in m.named_parameters() if q is prm][0])
+    topt = m.flat_optimizer(lr=1e-4, capturable=True)
+    topt._ensure_state()
     us, n = timed(lambda: eng.train_step(x, gt, dropout=True, optimizer=topt), reps=10)
-    emit(row="1,2", what="PoolResnet(filters=128, S=10) train step: forward + summed YoloLoss + backward + torch Adam, batch 64, "
+    emit(row="1,2", what="PoolResnet(filters=128, S=10) train step: forward + summed YoloLoss + backward + Adam (fd_adam_flat), batch 64, "
                          "train-mode dropout (PlanarEngine: two channel planes, cta_group::2 wide kernels for the 3x3 convolutions)", us=us, launches=n,
          images_per_s=B / us * 1e6, tflops=3 * 3.997e9 * B / us / 1e6)
     m.eval()
