@@ -284,6 +284,16 @@ FD_API int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const float* 
 /* dw[C][Cin][K][K] += x (*) g ; dbias[C] += sum g.  g: [B,Ho,Wo,C] bf16. */
 FD_API int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C, int K,
                   int stride, int pad, float* dw, float* dbias, const fd_bf16* x_cache, void* stream);
+/* Models wider than 64 filters (train_model.py:17 trains filters = 128) run the stem once per 64-channel output plane.
+ * The first plane's fd_stem_fwd (with x_cache) reads the images; the other planes read the bf16 copy it left behind:
+ *   fd_stem_fwd_cached      y[B,Ho,Wo,64] = conv(x_cache, w[64][Cin][K][K]) + bias, same arithmetic as fd_stem_fwd;
+ *   fd_stem_wgrad_pair      the weight gradients of TWO planes from one pass over the copy:
+ *                           dw[128][Cin][K][K] += x (*) {g0, g1}, dbias[128] += sum {g0, g1}.
+ * Both return FD_EUNSUPPORTED for shapes fd_stem_cache_elems reports 0 for. */
+FD_API int fd_stem_fwd_cached(const fd_bf16* x_cache, const float* w, const float* bias, int B, int Cin, int Hin, int Win,
+                       int K, int stride, int pad, fd_bf16* y, void* stream);
+FD_API int fd_stem_wgrad_pair(const fd_bf16* x_cache, const fd_bf16* g0, const fd_bf16* g1, int B, int Cin, int Hin, int Win,
+                       int K, int stride, int pad, float* dw, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Head (models/PoolResnet.py:83-89,100-102): Dropout2d multiplier, KxK stride-1 conv C -> 5 with

@@ -76,6 +76,10 @@ int stem_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, i
                 int C, int K, int stride, int pad, fd_bf16* y, fd_bf16* xbf, cudaStream_t st);
 int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C, int K,
                   int stride, int pad, float* dw, float* dbias, const fd_bf16* xbf, cudaStream_t st);
+int stem_fwd_cached(const fd_bf16* xbf, const float* w, const float* bias, int B, int Cin, int Hin, int Win, int C, int K,
+                    int stride, int pad, fd_bf16* y, cudaStream_t st);
+int stem_wgrad_pair_cached(const fd_bf16* xbf, const fd_bf16* g0, const fd_bf16* g1, int B, int Cin, int Hin, int Win,
+                           int K, int stride, int pad, float* dw, float* dbias, cudaStream_t st);
 
 // tcgen05 stem of the standard Resnet (3x3, stride 2, pad 1, 3 -> 64; stem_s2_tc.cu); FD_EUNSUPPORTED = other shape
 int stem_s2_fwd_tc(const void* x, int x_is_u8, const float* w, const float* bias, int B, int Cin, int Hin, int Win, int C,

@@ -65,24 +65,26 @@ unpack_wgrad3x3_kernel(const float* __restrict__ dwp, int n_layers, float* __res
 // The same for the channel-plane engines: packed 64 x 64 sub-blocks [layer][g][h][t][ci][co] -> the torch tensor of the WIDE
 // layer [layer][64 G (co)][64 G (ci)][ky][kx] directly (row of 576 floats per (co, h) at its place in the wide row): no
 // intermediate sub-block tensor and no permuting copy afterwards.
+constexpr int kUnpT = 32;     // (co, ci) tile: 128-byte runs of the packed source, 1152-byte runs of the destination
 __global__ void __launch_bounds__(256)
 unpack_wgrad3x3_planes_kernel(const float* __restrict__ dwp, int G, float* __restrict__ dw) {
   pdl_trigger();
   pdl_wait();
-  constexpr int C = 64, row = C * 9, pitch = row + 1, tiles = C / kPackCo;
-  __shared__ float sm[kPackCo * pitch];
-  const int sub = blockIdx.x / tiles, co0 = (blockIdx.x % tiles) * kPackCo;
+  constexpr int C = 64, row = kUnpT * 9, pitch = row + 1, tiles = C / kUnpT;
+  __shared__ float sm[kUnpT * pitch];
+  const int sub = blockIdx.x / (tiles * tiles), rem = blockIdx.x % (tiles * tiles);
+  const int co0 = (rem / tiles) * kUnpT, ci0 = (rem % tiles) * kUnpT;
   const int h = sub % G, g = (sub / G) % G, l = sub / (G * G);
   const long sbase = static_cast<long>(sub) * 9 * C * C;
-  for (int i = threadIdx.x; i < 9 * kPackCo * C; i += 256) {
-    const int co = i % kPackCo, ci = (i / kPackCo) % C, t = i / (C * kPackCo);
-    sm[co * pitch + ci * 9 + t] = __ldg(dwp + sbase + (static_cast<long>(t) * C + ci) * C + co0 + co);
+  for (int i = threadIdx.x; i < 9 * kUnpT * kUnpT; i += 256) {
+    const int co = i % kUnpT, ci = (i / kUnpT) % kUnpT, t = i / (kUnpT * kUnpT);
+    sm[co * pitch + ci * 9 + t] = __ldg(dwp + sbase + (static_cast<long>(t) * C + ci0 + ci) * C + co0 + co);
   }
   __syncthreads();
   const long F = static_cast<long>(G) * C;
-  for (int i = threadIdx.x; i < kPackCo * row; i += 256) {
+  for (int i = threadIdx.x; i < kUnpT * row; i += 256) {
     const int co = i / row, r = i % row;
-    dw[((static_cast<long>(l) * F + g * C + co0 + co) * F + h * C) * 9 + r] = sm[co * pitch + r];
+    dw[((static_cast<long>(l) * F + g * C + co0 + co) * F + h * C + ci0) * 9 + r] = sm[co * pitch + r];
   }
 }
 
@@ -1084,8 +1086,8 @@ extern "C" int fd_unpack_wgrad3x3(const float* dw_packed, int n_layers, int C, f
 
 extern "C" int fd_unpack_wgrad3x3_planes(const float* dw_packed, int n_layers, int G, float* dw, void* stream) {
   if (!dw_packed || !dw || n_layers <= 0 || G <= 0) return FD_EINVAL;
-  launch_k(unpack_wgrad3x3_planes_kernel, dim3(n_layers * G * G * (64 / kPackCo)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-           dw_packed, G, dw);
+  launch_k(unpack_wgrad3x3_planes_kernel, dim3(n_layers * G * G * (64 / kUnpT) * (64 / kUnpT)), dim3(256), 0,
+           static_cast<cudaStream_t>(stream), dw_packed, G, dw);
   count_launch();
   return launch_status();
 }
@@ -1194,6 +1196,19 @@ extern "C" int fd_stem_fwd(const void* x, int x_is_u8, const float* w, const flo
   }
   count_launch();
   return launch_status();
+}
+
+extern "C" int fd_stem_fwd_cached(const fd_bf16* x_cache, const float* w, const float* bias, int B, int Cin, int Hin,
+                                  int Win, int K, int stride, int pad, fd_bf16* y, void* stream) {
+  if (!x_cache || !w || !bias || !y || B <= 0) return FD_EINVAL;
+  return stem_fwd_cached(x_cache, w, bias, B, Cin, Hin, Win, 64, K, stride, pad, y, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fd_stem_wgrad_pair(const fd_bf16* x_cache, const fd_bf16* g0, const fd_bf16* g1, int B, int Cin, int Hin,
+                                  int Win, int K, int stride, int pad, float* dw, float* dbias, void* stream) {
+  if (!x_cache || !g0 || !g1 || !dw || B <= 0) return FD_EINVAL;
+  return stem_wgrad_pair_cached(x_cache, g0, g1, B, Cin, Hin, Win, K, stride, pad, dw, dbias,
+                                static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int fd_stem_wgrad(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, int Hin, int Win, int C,

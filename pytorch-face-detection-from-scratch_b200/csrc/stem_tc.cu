@@ -286,6 +286,44 @@ __device__ __forceinline__ void convert_chunks(const StemParams& p, uint8_t* abu
 
 struct StrideSched { int begin, end, step; };
 
+// bf16 B operand of the forward in shared memory, per (c,ky): [k1 2][co 64][k0 8] (K-major, no swizzle: LBO = 1024,
+// SBO = 128; kx = 8 k1 + k0, zero for kx >= K) from w[co][c][ky][kx] fp32.  Reads are coalesced float4s in SOURCE order
+// and scattered into the operand: the element-per-thread gather it replaces (stride K*CK floats between lanes) cost
+// ~45 dependent L2 round trips per thread in the prologue of every stem launch.
+__device__ __forceinline__ void build_stem_weights(uint8_t* sW, const StemParams& p, int tid, int nthreads) {
+  __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(sW);
+  const int KK = p.CK * p.K;
+  if ((reinterpret_cast<uintptr_t>(p.w) & 15u) != 0 || ((kCo * KK) & 3) != 0) {       // unaligned view: plain gather
+    for (int i = tid; i < p.CK * 1024; i += nthreads) {
+      const int k0 = i & 7, co = (i >> 3) & 63, k1 = (i >> 9) & 1, cky = i >> 10;
+      const int kx = k1 * 8 + k0;
+      w16[i] = __float2bfloat16(kx < p.K ? p.w[static_cast<size_t>(co) * KK + cky * p.K + kx] : 0.f);
+    }
+    return;
+  }
+  for (int i = tid; i < p.CK * 512; i += nthreads)      // the padding kx >= K: k1 = 1, k0 >= K - 8 (disjoint from the scatter)
+    if (8 + (i & 7) >= p.K) w16[(i >> 9) * 1024 + 512 + (i & 511)] = __float2bfloat16(0.f);
+  const float4* w4 = reinterpret_cast<const float4*>(p.w);
+  const int n4 = (kCo * KK) >> 2;
+#pragma unroll 4
+  for (int f = tid; f < n4; f += nthreads) {
+    const float4 v = __ldg(w4 + f);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    const int e = f * 4;
+    int co = e / KK;
+    const int rem = e - co * KK;
+    int cky = rem / p.K, kx = rem - cky * p.K;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w16[cky * 1024 + (kx >> 3) * 512 + co * 8 + (kx & 7)] = __float2bfloat16(vv[j]);
+      if (++kx == p.K) {
+        kx = 0;
+        if (++cky == p.CK) { cky = 0; ++co; }
+      }
+    }
+  }
+}
+
 
 // ------------------------------------------------------------------------------------- forward
 // smem: [weights CK*2048][A tile (single stage)][slack 128][16 staging slots][barriers]
@@ -319,17 +357,7 @@ stem_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const StemParams p)
   // one-time: zero the A stages (pad columns stay zero forever) and build the bf16 weight operand
   for (uint32_t i = threadIdx.x * 16u; i < p.a_bytes + 128; i += kFwdThreads * 16u)
     *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
-  {
-    // B operand per (c,ky): [k1 2][co 64][k0 8] bf16  (K-major, no swizzle: LBO = 1024, SBO = 128)
-    __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(sW);
-    const int KK = p.CK * p.K;
-    for (int i = threadIdx.x; i < p.CK * 1024; i += kFwdThreads) {
-      const int k0 = i & 7, co = (i >> 3) & 63, k1 = (i >> 9) & 1, cky = i >> 10;
-      const int kx = k1 * 8 + k0;
-      const float v = kx < p.K ? p.w[static_cast<size_t>(co) * KK + cky * p.K + kx] : 0.f;
-      w16[i] = __float2bfloat16(v);
-    }
-  }
+  build_stem_weights(sW, p, threadIdx.x, kFwdThreads);
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
@@ -562,7 +590,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     for (int task = t_begin; task < t_end; ++task, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       mbar_wait(full + s, ph);
-      if (p.dbias) {
+      if (p.dbias && !(p.dbg & 2)) {
         const uint8_t* g = sG + s * kGBytes;
         for (int r = rpar; r < 128; r += 2) {
           const uint32_t off = r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1));
@@ -608,29 +636,34 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 // plane (pair, c)) straight from the bf16 image copy the forward wrote: no fp32 re-read, no converter warps, no
 // staging ring.  Warps: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = bias sums + drain.
 constexpr int kWg2Threads = 6 * 32;
+// kNP = 2: the weight gradients of TWO 64-channel output planes (the stem of a 128-filter model) from one pass over the
+// image rows -- a second gradient tile per stage, 8 accumulators (all 512 TMEM columns); dw / dbias of plane 1 follow
+// those of plane 0 (rows 64..127 of the [128][Cin][K][K] gradient).
+template <int kNP>
 __global__ void __launch_bounds__(kWg2Threads, 1)
 stem_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tm_xb, const __grid_constant__ CUtensorMap tm_g,
-                       const StemParams p) {
+                       const __grid_constant__ CUtensorMap tm_g1, const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   constexpr uint32_t kGBytes = 128 * 128;
   uint8_t* sA = smem;                                   // 2 stages x a_bytes
-  uint8_t* sG = sA + 2 * p.a_bytes + 1024;              // 2 stages x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * kGBytes);
+  uint8_t* sG = sA + 2 * p.a_bytes + 1024;              // 2 stages x kNP planes x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * kNP * kGBytes);
   uint64_t* full = bars + 0;     // [2]
   uint64_t* empty = bars + 2;    // [2] count = 1 (MMA commit) + 4 (bias warps)
   uint64_t* acc_full = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  float* sBias = reinterpret_cast<float*>(bars + 6);    // [128]
+  float* sBias = reinterpret_cast<float*>(bars + 6);    // [kNP][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // g rows Wo..63 of each 64-row slot and the slack behind the A stages are never written by TMA: keep them zero
-  for (uint32_t i = threadIdx.x * 16u; i < 2 * p.a_bytes + 1024 + 2 * kGBytes; i += kWg2Threads * 16u)
+  for (uint32_t i = threadIdx.x * 16u; i < 2 * p.a_bytes + 1024 + 2 * kNP * kGBytes; i += kWg2Threads * 16u)
     *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_g);
+    if (kNP > 1) tma_prefetch_desc(&tm_g1);
     tma_prefetch_desc(&tm_xb);
     for (int s = 0; s < 2; ++s) {
       mbar_init(full + s, 1);
@@ -661,16 +694,20 @@ stem_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tm_xb, const __grid_c
         const int s = it & 1, ph = (it >> 1) & 1;
         const int pair = task / p.Ho, oy = task - pair * p.Ho;
         mbar_wait(empty + s, ph ^ 1);
-        mbar_expect_tx(full + s, p.a_bytes + 2u * p.Wo * 128u);
-        for (int c = 0; c < p.Cin; ++c)       // {256 e, 2 halves, 2 img, K rows, 1 plane}; rows above the image: zero fill
+        mbar_expect_tx(full + s, ((p.dbg & 8) ? 0u : p.a_bytes) + kNP * 2u * p.Wo * 128u);
+        for (int c = 0; c < ((p.dbg & 8) ? 0 : p.Cin); ++c)       // {256 e, 2 halves, 2 img, K rows, 1 plane}; rows above the image: zero fill
           asm volatile(
               "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
               "[%2];" ::"r"(smem_u32(sA + s * p.a_bytes + c * p.K * 2 * kRowBytes)),
               "l"(reinterpret_cast<uint64_t>(&tm_xb)), "r"(smem_u32(full + s)), "r"(0), "r"(0), "r"(0),
               "r"(oy * p.stride - p.pad), "r"(pair * p.Cin + c)
               : "memory");
-        tma_load_4d(sG + s * kGBytes, &tm_g, full + s, 0, 0, oy, pair * 2);
-        tma_load_4d(sG + s * kGBytes + 64 * 128, &tm_g, full + s, 0, 0, oy, pair * 2 + 1);
+#pragma unroll
+        for (int pl = 0; pl < kNP; ++pl) {
+          const CUtensorMap* tg = pl == 0 ? &tm_g : &tm_g1;
+          tma_load_4d(sG + (s * kNP + pl) * kGBytes, tg, full + s, 0, 0, oy, pair * 2);
+          tma_load_4d(sG + (s * kNP + pl) * kGBytes + 64 * 128, tg, full + s, 0, 0, oy, pair * 2 + 1);
+        }
       }
     }
   } else if (warp == 1) {
@@ -687,17 +724,20 @@ stem_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tm_xb, const __grid_c
         const int s = it & 1, ph = (it >> 1) & 1;
         mbar_wait(full + s, ph);
         tc_fence_after();
-        const uint64_t bd0 = make_sdesc_sw128(smem_u32(sG + s * kGBytes), 1024, 1024, 0);
+        const uint64_t bd0 = make_sdesc_sw128(smem_u32(sG + s * kNP * kGBytes), 1024, 1024, 0);
         const uint32_t a_addr = smem_u32(sA + s * p.a_bytes);
 #pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = 0; ks < ((p.dbg & 1) ? 0 : 8); ++ks) {
           const uint64_t bd = bd0 + static_cast<uint64_t>(ks * 128);          // +2048 B: 16 positions
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
             const int blk = a >> 1, chunk = a & 1;
             const uint64_t ad = make_sdesc_none(a_addr + blk * 16 * 2 * kRowBytes + chunk * 16 + ks * 256, 128,
                                                 2 * kRowBytes);
-            umma_bf16(tmem_base + a * kCo, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int pl = 0; pl < kNP; ++pl)       // + 16 KB (address field + 1024): the gradient tile of plane pl
+              umma_bf16(tmem_base + (pl * 4 + a) * kCo, ad, bd + static_cast<uint64_t>(pl * (kGBytes >> 4)), idesc,
+                        (it | ks) != 0 ? 1u : 0u);
           }
         }
         umma_commit(empty + s);
@@ -708,16 +748,20 @@ stem_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tm_xb, const __grid_c
   } else {
     const int et = threadIdx.x - 64;   // 0..127
     const int c = et & 63, rpar = et >> 6;
-    float bsum = 0.f;
+    float bsum[kNP];
+#pragma unroll
+    for (int pl = 0; pl < kNP; ++pl) bsum[pl] = 0.f;
     int it = 0;
     for (int task = t_begin; task < t_end; ++task, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       mbar_wait(full + s, ph);
-      if (p.dbias) {
-        const uint8_t* g = sG + s * kGBytes;
+      if (p.dbias && !(p.dbg & 2)) {
+        const uint8_t* g = sG + s * kNP * kGBytes;
         for (int r = rpar; r < 128; r += 2) {
           const uint32_t off = r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1));
-          bsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(g + off));
+#pragma unroll
+          for (int pl = 0; pl < kNP; ++pl)
+            bsum[pl] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(g + pl * kGBytes + off));
         }
       }
       __syncwarp();
@@ -731,25 +775,29 @@ stem_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tm_xb, const __grid_c
       const int r = q * 32 + lane;
       const int KK = p.CK * p.K;
 #pragma unroll 1
-      for (int a = 0; a < 4; ++a) {
+      for (int pa = 0; pa < 4 * kNP; ++pa) {
+        const int a = pa & 3, pl = pa >> 2;
         const int cky = (a >> 1) * 16 + (r >> 3), kx = (a & 1) * 8 + (r & 7);
         const bool valid = cky < p.CK && kx < p.K;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t acc[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * kCo + half * 32, acc);
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + pa * kCo + half * 32, acc);
           tmem_ld_wait();
-          if (valid) {
-            float* dst = p.dw + static_cast<size_t>(half * 32) * KK + cky * p.K + kx;
+          if (valid && !(p.dbg & 4)) {
+            float* dst = p.dw + static_cast<size_t>(pl * kCo + half * 32) * KK + cky * p.K + kx;
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(dst + static_cast<size_t>(j) * KK, __uint_as_float(acc[j]));
           }
         }
       }
       if (p.dbias) {
-        sBias[et] = bsum;
+#pragma unroll
+        for (int pl = 0; pl < kNP; ++pl) sBias[pl * 128 + et] = bsum[pl];
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et < 64) atomicAdd(p.dbias + et, sBias[et] + sBias[et + 64]);
+#pragma unroll
+        for (int pl = 0; pl < kNP; ++pl)
+          if (et < 64) atomicAdd(p.dbias + pl * kCo + et, sBias[pl * 128 + et] + sBias[pl * 128 + et + 64]);
       }
     }
   }
@@ -757,6 +805,138 @@ stem_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tm_xb, const __grid_c
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
+
+// ------------------------------------------------------------------------------------- forward from the bf16 copy
+// The stem of a model wider than 64 filters runs once per 64-channel output plane.  The first plane's launch
+// (stem_fwd_tc_kernel) reads the fp32 / uint8 images and leaves the bf16 copy behind; every further plane takes its A
+// tile from that copy -- three TMA boxes per task, the loads of the bf16 weight-gradient kernel, and the 30 MMAs and the
+// epilogue of the forward kernel: 2 B instead of 4 B per pixel from HBM, no converter warps.
+// smem: [weights CK*2048][A stage 0][A stage 1][barriers].  Warps: 0 = TMA producer, 1 = MMA issuer + TMEM owner,
+// 2..5 = epilogue.
+__global__ void __launch_bounds__(kWg2Threads, 1)
+stem_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tm_xb, const StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sW = smem;
+  uint8_t* sA = sW + p.CK * 2048;                        // 2 stages x a_bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 2 * p.a_bytes + 128);
+  uint64_t* full = bars + 0;       // [2]
+  uint64_t* empty = bars + 2;      // [2]
+  uint64_t* acc_full = bars + 4;   // [2]
+  uint64_t* acc_empty = bars + 6;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (uint32_t i = threadIdx.x * 16u; i < 2 * p.a_bytes + 128; i += kWg2Threads * 16u)
+    *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
+  build_stem_weights(sW, p, threadIdx.x, kWg2Threads);
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_xb);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+      mbar_init(acc_full + s, 1);
+      mbar_init(acc_empty + s, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int it = 0;
+      for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        const int pair = task / p.Ho, oy = task - pair * p.Ho;
+        mbar_wait(empty + s, ph ^ 1);
+        if (p.dbg & 8) { mbar_arrive(full + s); continue; }       // timing switch: no loads
+        mbar_expect_tx(full + s, p.a_bytes);
+        for (int c = 0; c < p.Cin; ++c)       // {256 e, 2 halves, 2 img, K rows, 1 plane}; rows outside the image: zero fill
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+              "[%2];" ::"r"(smem_u32(sA + s * p.a_bytes + c * p.K * 2 * kRowBytes)),
+              "l"(reinterpret_cast<uint64_t>(&tm_xb)), "r"(smem_u32(full + s)), "r"(0), "r"(0), "r"(0),
+              "r"(oy * p.stride - p.pad), "r"(pair * p.Cin + c)
+              : "memory");
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, kCo, 0, 0);
+    const uint64_t bd0 = make_sdesc_none(smem_u32(sW), 1024, 128);
+    int it = 0;
+    for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(acc_empty + s, ph ^ 1);
+      mbar_wait(full + s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t ad0 = make_sdesc_none(smem_u32(sA + s * p.a_bytes), 16, 128);
+#pragma unroll 2
+        for (int cky = 0; cky < ((p.dbg & 1) ? 0 : p.CK); ++cky)    // +2048 B per (c,ky) on both operands = +128 in the address field
+          umma_bf16(tmem_base + s * kCo, ad0 + static_cast<uint64_t>(cky * 128), bd0 + static_cast<uint64_t>(cky * 128),
+                    idesc, cky != 0 ? 1u : 0u);
+        umma_commit(empty + s);
+        umma_commit(acc_full + s);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (int task = blockIdx.x; task < p.ntask; task += gridDim.x, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      const int pair = task / p.Ho, oy = task - pair * p.Ho;
+      mbar_wait(acc_full + s, ph);
+      tc_fence_after();
+      const int r = q * 32 + lane;
+      const int img = r >> 6, ox = r & 63;
+      const int n = pair * 2 + img;
+      const bool valid = ox < p.Wo && n < p.B;
+      __nv_bfloat16* dst = p.y + ((static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox) * kCo;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * kCo + half * 32, acc);
+        tmem_ld_wait();
+        if (valid && !(p.dbg & 4)) {
+          uint4* d = reinterpret_cast<uint4*>(dst + half * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c0 = half * 32 + i * 8;
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(acc[8 * i + 0]) + __ldg(p.bias + c0 + 0),
+                              __uint_as_float(acc[8 * i + 1]) + __ldg(p.bias + c0 + 1));
+            u.y = pack_bf16x2(__uint_as_float(acc[8 * i + 2]) + __ldg(p.bias + c0 + 2),
+                              __uint_as_float(acc[8 * i + 3]) + __ldg(p.bias + c0 + 3));
+            u.z = pack_bf16x2(__uint_as_float(acc[8 * i + 4]) + __ldg(p.bias + c0 + 4),
+                              __uint_as_float(acc[8 * i + 5]) + __ldg(p.bias + c0 + 5));
+            u.w = pack_bf16x2(__uint_as_float(acc[8 * i + 6]) + __ldg(p.bias + c0 + 6),
+                              __uint_as_float(acc[8 * i + 7]) + __ldg(p.bias + c0 + 7));
+            d[i] = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + s);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
 
 bool tc_shape_ok(int Cin, int Win, int C, int K, int stride, int pad, int Wo) {
   static const bool force_generic = std::getenv("FD_STEM_GENERIC") != nullptr;   // A/B testing only
@@ -781,6 +961,34 @@ StemParams make_params(const void* x, int B, int Cin, int Hin, int Win, int K, i
 // [B*Cin, Hin, Win] image (fp32 or uint8) as a 3-D tiled map, box {Win/2, K/2, 1}, no swizzle, zero OOB fill
 int make_tmap_image(CUtensorMap* m, const void* x, int is_u8, int planes, int Hin, int Win, int K) {
   return make_tmap_3d(m, x, is_u8 ? 1 : 4, is_u8, Win, Hin, planes, Win / 2, K / 2);
+}
+
+// Weight gradient of one (g1 == nullptr) or two 64-channel planes from the bf16 image copy.
+int stem_wgrad_cached(const StemParams& p, const fd_bf16* xbf, const fd_bf16* g0, const fd_bf16* g1, cudaStream_t st) {
+  CUtensorMap tm_g, tm_g1, tm_xb;
+  int rc = make_tmap_nhwc_bf16(&tm_g, g0, p.B, p.Ho, p.Wo, kCo, p.Wo, 1);
+  if (rc != FD_OK) return rc;
+  rc = make_tmap_nhwc_bf16(&tm_g1, g1 ? g1 : g0, p.B, p.Ho, p.Wo, kCo, p.Wo, 1);
+  if (rc != FD_OK) return rc;
+  rc = make_tmap_xbf(&tm_xb, xbf, p.npairs * p.Cin, p.Hin, p.K);
+  if (rc != FD_OK) return rc;
+  const int np = g1 ? 2 : 1;
+  const size_t smem = 2 * static_cast<size_t>(p.a_bytes) + 1024 + 2 * np * 128 * 128 + 2048 + 1024;
+  if (smem > 227 * 1024) return FD_EUNSUPPORTED;
+  const int grid = min(p.ntask, sm_count());
+  cudaError_t e;
+  if (np == 2) {
+    e = set_max_dyn_smem(stem_wgrad_bf16_kernel<2>, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_k(stem_wgrad_bf16_kernel<2>, dim3(grid), dim3(kWg2Threads), smem, st, tm_xb, tm_g, tm_g1, p);
+  } else {
+    e = set_max_dyn_smem(stem_wgrad_bf16_kernel<1>, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_k(stem_wgrad_bf16_kernel<1>, dim3(grid), dim3(kWg2Threads), smem, st, tm_xb, tm_g, tm_g1, p);
+  }
+  if (e != cudaSuccess) return (int)e;
+  count_launch();
+  return launch_status();
 }
 
 }  // namespace
@@ -829,22 +1037,10 @@ int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, 
   StemParams p = make_params(x, B, Cin, Hin, Win, K, stride, pad);
   if (!tc_shape_ok(Cin, Win, C, K, stride, pad, p.Wo)) return FD_EUNSUPPORTED;
   p.dw = dw; p.dbias = dbias;
+  { const char* d = getenv("FD_STEM_WG_DBG"); p.dbg = d ? atoi(d) : 0; }     // A/B switches of the bf16 kernel (tools/stem_wgrad_debug.py)
   if (xbf != nullptr) {
     // fast path: operand rows come from the bf16 copy written by the forward pass
-    CUtensorMap tm_g, tm_xb;
-    int rc = make_tmap_nhwc_bf16(&tm_g, g, B, p.Ho, p.Wo, C, p.Wo, 1);
-    if (rc != FD_OK) return rc;
-    rc = make_tmap_xbf(&tm_xb, xbf, p.npairs * Cin, Hin, K);
-    if (rc != FD_OK) return rc;
-    const size_t smem2 = 2 * static_cast<size_t>(p.a_bytes) + 1024 + 2 * 128 * 128 + 1024 + 1024;
-    if (smem2 > 227 * 1024) return FD_EUNSUPPORTED;
-    cudaError_t e2 = set_max_dyn_smem(stem_wgrad_bf16_kernel, (int)smem2);
-    if (e2 != cudaSuccess) return (int)e2;
-    const int grid2 = min(p.ntask, sm_count());
-    e2 = launch_k(stem_wgrad_bf16_kernel, dim3(grid2), dim3(kWg2Threads), smem2, st, tm_xb, tm_g, p);
-    if (e2 != cudaSuccess) return (int)e2;
-    count_launch();
-    return launch_status();
+    return stem_wgrad_cached(p, xbf, g, nullptr, st);
   }
   p.elem_bytes = x_is_u8 ? 1 : 4;
   CUtensorMap tm_g, tm_x;
@@ -872,6 +1068,36 @@ int stem_wgrad_tc(const void* x, int x_is_u8, const fd_bf16* g, int B, int Cin, 
   }
   count_launch();
   return launch_status();
+}
+
+// Forward of one 64-channel plane from the bf16 image copy an earlier stem_fwd_tc launch of the same step wrote.
+int stem_fwd_cached(const fd_bf16* xbf, const float* w, const float* bias, int B, int Cin, int Hin, int Win, int C, int K,
+                    int stride, int pad, fd_bf16* y, cudaStream_t st) {
+  StemParams p = make_params(nullptr, B, Cin, Hin, Win, K, stride, pad);
+  if (!tc_shape_ok(Cin, Win, C, K, stride, pad, p.Wo)) return FD_EUNSUPPORTED;
+  p.w = w; p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  { const char* d = getenv("FD_STEM_WG_DBG"); p.dbg = d ? atoi(d) : 0; }     // timing switches (tools/stem_planes_ab.py)
+  CUtensorMap tm_xb;
+  const int rc = make_tmap_xbf(&tm_xb, xbf, p.npairs * Cin, Hin, K);
+  if (rc != FD_OK) return rc;
+  const size_t smem = static_cast<size_t>(p.CK) * 2048 + 2 * static_cast<size_t>(p.a_bytes) + 128 + 256 + 1024;
+  if (smem > 227 * 1024) return FD_EUNSUPPORTED;
+  cudaError_t e = set_max_dyn_smem(stem_fwd_bf16_kernel, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  e = launch_k(stem_fwd_bf16_kernel, dim3(min(p.ntask, sm_count())), dim3(kWg2Threads), smem, st, tm_xb, p);
+  if (e != cudaSuccess) return (int)e;
+  count_launch();
+  return launch_status();
+}
+
+// Weight gradients of two 64-channel planes (dw [128][Cin][K][K], dbias [128], accumulated) in one pass over the copy.
+int stem_wgrad_pair_cached(const fd_bf16* xbf, const fd_bf16* g0, const fd_bf16* g1, int B, int Cin, int Hin, int Win,
+                           int K, int stride, int pad, float* dw, float* dbias, cudaStream_t st) {
+  StemParams p = make_params(nullptr, B, Cin, Hin, Win, K, stride, pad);
+  if (!tc_shape_ok(Cin, Win, kCo, K, stride, pad, p.Wo)) return FD_EUNSUPPORTED;
+  p.dw = dw; p.dbias = dbias;
+  { const char* d = getenv("FD_STEM_WG_DBG"); p.dbg = d ? atoi(d) : 0; }
+  return stem_wgrad_cached(p, xbf, g0, g1, st);
 }
 
 }  // namespace fd

@@ -112,14 +112,14 @@ class _PPlan:
             self.blocks.append(b)
             cur = b.out
         self.y = torch.empty((B, 5, eng.So_h, eng.So_w), dtype=F32, device=device)
+        # bf16 image copy: read by the stem weight gradient and by the forward of every plane after the first
+        self.x_cache = None
+        if train or G > 1:
+            self.x_cache = ops.stem_cache(B, (eng.in_ch, eng.in_h, eng.in_w), (eng.stem_k, eng.stem_s, eng.stem_pad), device)
         if train:
-            n_cache = ops.stem_cache_elems(B, eng.in_ch, eng.in_h, eng.in_w, 64, eng.stem_k, eng.stem_s, eng.stem_pad)
-            self.x_cache = torch.zeros(n_cache, dtype=BF16, device=device) if n_cache else None
             self.g_stem = planes(eng.H0, eng.W0)
             self.loss = torch.empty((B,), dtype=F32, device=device)
             self.dy = torch.empty_like(self.y)
-        else:
-            self.x_cache = None
         self.drop = None
         self.generation = 0
         self.x = self.head_in = self.w_head = None
@@ -311,9 +311,7 @@ class PlanarEngine:
             pl.drop = None
         pl.x = x
         w1, b1 = P["conv1.weight"].detach().float(), P["conv1.bias"].detach().float()
-        for g in range(G):
-            ops.stem_fwd(x, w1[g * 64:(g + 1) * 64], b1[g * 64:(g + 1) * 64], pl.act0[g], self.stem_s, self.stem_pad,
-                         x_cache=pl.x_cache if g == 0 else None)
+        ops.stem_planes_fwd(x, w1, b1, pl.act0, self.stem_s, self.stem_pad, x_cache=pl.x_cache)
         cur = pl.act0
         for k, blk in enumerate(pl.blocks):
             if self.use_wide:
@@ -425,9 +423,7 @@ class PlanarEngine:
                         ops.conv3x3_wgrad_multi(pl.XA[k][h], pl.GP[k][g], dwp_flat[first * n3:], G * G * n3,
                                                 gb3_flat[(2 * k * G + g) * 64:] if h == 0 else None, G * 64)
         gw1, gb1 = self.section(self.gflat, "conv1.weight"), self.section(self.gflat, "conv1.bias")
-        for g in range(G):
-            ops.stem_wgrad(pl.x, pl.g_stem[g], gw1[g * 64:(g + 1) * 64], gb1[g * 64:(g + 1) * 64], self.stem_s,
-                           self.stem_pad, x_cache=pl.x_cache)
+        ops.stem_planes_wgrad(pl.x, pl.g_stem, gw1, gb1, self.stem_s, self.stem_pad, x_cache=pl.x_cache)
         L = 2 * nb
         # packed sub-blocks -> the [L,F,F,3,3] gradient section in one pass; the bias gradients were accumulated in place
         ops.unpack_wgrad3x3_planes(self.dwp.view(L * G * G, 9, 64, 64), G, self.section(self.gflat, "w3"))

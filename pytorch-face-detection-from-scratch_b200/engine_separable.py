@@ -118,6 +118,7 @@ class SeparableTrainEngine:
             return [torch.empty((B, h, w, 64), dtype=BF16, device=dev) for _ in range(G)]
 
         pl = {"act0": planes(self.H0, self.W0), "g_stem": planes(self.H0, self.W0), "blocks": [], "generation": 0}
+        pl["x_cache"] = ops.stem_cache(B, (self.in_ch, self.in_h, self.in_w), (self.stem_k, self.stem_s, self.stem_pad), dev)
         for (h, w), pool in zip(self.shapes, self.pools):
             b = {"T": planes(h, w), "T2": planes(h, w), "t1": planes(h, w), "t2": planes(h, w), "s": planes(h, w),
                  "gy": planes(h, w), "gu": planes(h, w), "gt1": planes(h, w), "gr1": planes(h, w)}
@@ -166,9 +167,7 @@ class SeparableTrainEngine:
             pl["drop"] = None
         pl["x"] = x
         w1, b1 = P["conv1.weight"].detach().float(), P["conv1.bias"].detach().float()
-        for g in range(G):
-            ops.stem_fwd(x, w1[g * 64:(g + 1) * 64].contiguous(), b1[g * 64:(g + 1) * 64].contiguous(), pl["act0"][g],
-                         self.stem_s, self.stem_pad)
+        ops.stem_planes_fwd(x, w1, b1, pl["act0"], self.stem_s, self.stem_pad, x_cache=pl["x_cache"])
         cur = pl["act0"]
         for k, b in enumerate(pl["blocks"]):
             b["inp"] = cur
@@ -257,9 +256,7 @@ class SeparableTrainEngine:
             for h in range(G):
                 self._chain(b["gr1"], self.w_dgrad, 2 * k, h, GS[h], b["T"][h], b["T2"][h], final=target[h], transposed=True)
         gw1, gb1 = self.grad_view("conv1.weight"), self.grad_view("conv1.bias")
-        for g in range(G):
-            ops.stem_wgrad(pl["x"], pl["g_stem"][g], gw1[g * 64:(g + 1) * 64], gb1[g * 64:(g + 1) * 64], self.stem_s,
-                           self.stem_pad)
+        ops.stem_planes_wgrad(pl["x"], pl["g_stem"], gw1, gb1, self.stem_s, self.stem_pad, x_cache=pl["x_cache"])
         L = 2 * nb
         ops.unpack_wgrad3x3(self.dwp.view(L * G * G, 9, 64, 64), self.dw_sub)
         centre = self.dw_sub[:, :, :, 1, 1].view(L, G, G, 64, 64).permute(0, 1, 3, 2, 4).reshape(L, self.F, self.F)

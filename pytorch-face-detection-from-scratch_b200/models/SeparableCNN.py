@@ -219,6 +219,8 @@ class SeparablePlanarEngine:
                 return [torch.empty((B, h, w, 64), dtype=BF16, device=dev) for _ in range(G)]
             H0, W0 = self.shapes[0]
             pl = {"act0": planes(H0, W0), "blocks": []}
+            pl["x_cache"] = ops.stem_cache(B, (self.in_ch, self.in_h, self.in_w), (self.stem_k, self.stem_s, self.stem_pad),
+                                           dev) if G > 1 else None
             for (h, w), pool in zip(self.shapes, self.pools):
                 b = {"T": planes(h, w), "T2": planes(h, w), "t1": planes(h, w), "t2": planes(h, w)}
                 b["s"] = planes(h, w)
@@ -263,8 +265,7 @@ class SeparablePlanarEngine:
         pl = self.plan(x.shape[0])
         self.pack_weights()
         w1, b1 = P["conv1.weight"].detach().float(), P["conv1.bias"].detach().float()
-        for g in range(G):
-            ops.stem_fwd(x, w1[g * 64:(g + 1) * 64], b1[g * 64:(g + 1) * 64], pl["act0"][g], self.stem_s, self.stem_pad)
+        ops.stem_planes_fwd(x, w1, b1, pl["act0"], self.stem_s, self.stem_pad, x_cache=pl["x_cache"])
         cur = pl["act0"]
         for k, b in enumerate(pl["blocks"]):
             if self.use_wide:

@@ -56,6 +56,8 @@ SIGNATURES = {
     "fd_stem_cache_elems": [_I, _I, _I, _I, _I, _I, _I, _I],
     "fd_stem_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "fd_stem_wgrad": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "fd_stem_fwd_cached": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fd_stem_wgrad_pair": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "fd_head_pack": [_P, _I, _I, _P, _P],
     "fd_head_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "fd_head_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],

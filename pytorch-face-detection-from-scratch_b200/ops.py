@@ -220,6 +220,56 @@ def stem_wgrad(x, g, dw, dbias, stride, pad, x_cache=None):
                               dptr(dw, F32), dptr(dbias, F32), dptr(x_cache, BF16), cur_stream()), "fd_stem_wgrad")
 
 
+def stem_fwd_cached(x_cache, in_shape, w, bias, y, stride, pad):
+    """Forward of one 64-channel plane from the bf16 image copy a stem_fwd(..., x_cache=) of the same images wrote."""
+    B, Cin, Hin, Win = in_shape
+    K = w.shape[2]
+    assert w.shape[0] == 64
+    check(lib().fd_stem_fwd_cached(dptr(x_cache, BF16), dptr(w, F32), dptr(bias, F32), B, Cin, Hin, Win, K, stride, pad,
+                                   dptr(y, BF16), cur_stream()), "fd_stem_fwd_cached")
+
+
+def stem_wgrad_pair(x_cache, in_shape, g0, g1, dw, dbias, stride, pad):
+    """dw[128][Cin][K][K], dbias[128] += the stem weight gradients of the two planes g0, g1, one pass over the copy."""
+    B, Cin, Hin, Win = in_shape
+    K = dw.shape[2]
+    assert dw.shape[0] == 128 and dbias.shape[0] == 128
+    check(lib().fd_stem_wgrad_pair(dptr(x_cache, BF16), dptr(g0, BF16), dptr(g1, BF16), B, Cin, Hin, Win, K, stride, pad,
+                                   dptr(dw, F32), dptr(dbias, F32), cur_stream()), "fd_stem_wgrad_pair")
+
+
+def stem_cache(B, in_shape3, stride_k_pad, device):
+    """Zero-initialised bf16 image copy for the stride-8 tensor-core stem, or None for shapes that do not use one."""
+    Cin, Hin, Win = in_shape3
+    K, stride, pad = stride_k_pad
+    n = stem_cache_elems(B, Cin, Hin, Win, 64, K, stride, pad)
+    return torch.zeros(n, dtype=BF16, device=device) if n else None
+
+
+def stem_planes_fwd(x, w, bias, planes, stride, pad, x_cache=None):
+    """Stem of a model with 64 * len(planes) filters: plane 0 from the images (filling x_cache), the others from the copy."""
+    for g, y in enumerate(planes):
+        wg, bg = w[g * 64:(g + 1) * 64], bias[g * 64:(g + 1) * 64]
+        if g > 0 and x_cache is not None:
+            stem_fwd_cached(x_cache, x.shape, wg, bg, y, stride, pad)
+        else:
+            stem_fwd(x, wg, bg, y, stride, pad, x_cache=x_cache if g == 0 else None)
+
+
+def stem_planes_wgrad(x, g_planes, dw, dbias, stride, pad, x_cache=None):
+    """dw[64 G][Cin][K][K], dbias[64 G] += stem weight gradients of the G gradient planes (two planes per pass with a copy)."""
+    G = len(g_planes)
+    g = 0
+    while g < G:
+        if g + 1 < G and x_cache is not None:
+            stem_wgrad_pair(x_cache, x.shape, g_planes[g], g_planes[g + 1], dw[g * 64:(g + 2) * 64], dbias[g * 64:(g + 2) * 64],
+                            stride, pad)
+            g += 2
+        else:
+            stem_wgrad(x, g_planes[g], dw[g * 64:(g + 1) * 64], dbias[g * 64:(g + 1) * 64], stride, pad, x_cache=x_cache)
+            g += 1
+
+
 def head_pack(w, w_t):
     C, K = w.shape[1], w.shape[2]
     check(lib().fd_head_pack(dptr(w, F32), C, K, dptr(w_t, F32), cur_stream()), "fd_head_pack")

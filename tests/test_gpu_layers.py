@@ -170,6 +170,27 @@ def test_stem_fwd_wgrad(u8):
     dw2 = torch.zeros_like(dw); dbias2 = torch.zeros_like(dbias)
     ops.stem_wgrad(x, g, dw2, dbias2, 8, 2, x_cache=cache)
     assert rel_err(dw2, dw) <= 1e-5 and rel_err(dbias2, dbias) <= 1e-5     # same MMAs, fp32 atomics reorder sums
+    # second 64-channel plane of a 128-filter stem: forward from the bf16 copy, both weight gradients in one pass
+    wb = (torch.randn(C, 3, 10, 10, device=dev) * 0.05)
+    bb = torch.randn(C, device=dev)
+    yb = torch.zeros_like(y); yb_ref = torch.zeros_like(y)
+    ops.stem_fwd(x, wb, bb, yb_ref, 8, 2)
+    ops.stem_fwd_cached(cache, x.shape, wb, bb, yb, 8, 2)
+    assert torch.equal(yb, yb_ref)                                          # same A tile, same MMAs, same epilogue
+    gb = (torch.randn(B, 60, 60, C, device=dev) * 0.1).bfloat16()
+    dwb = torch.zeros_like(dw); dbiasb = torch.zeros_like(dbias)
+    ops.stem_wgrad(x, gb, dwb, dbiasb, 8, 2, x_cache=cache)
+    dwp = torch.zeros(2 * C, 3, 10, 10, device=dev); dbp = torch.zeros(2 * C, device=dev)
+    ops.stem_wgrad_pair(cache, x.shape, g, gb, dwp, dbp, 8, 2)
+    assert rel_err(dwp[:C], dw2) <= 1e-5 and rel_err(dwp[C:], dwb) <= 1e-5
+    assert rel_err(dbp[:C], dbias2) <= 1e-5 and rel_err(dbp[C:], dbiasb) <= 1e-5
+    ya = [torch.zeros_like(y), torch.zeros_like(y)]
+    cache2 = torch.zeros_like(cache)
+    ops.stem_planes_fwd(x, torch.cat([w.detach(), wb]), torch.cat([b.detach(), bb]), ya, 8, 2, x_cache=cache2)
+    assert torch.equal(ya[0], y) and torch.equal(ya[1], yb_ref) and torch.equal(cache2, cache)
+    dwq = torch.zeros_like(dwp); dbq = torch.zeros_like(dbp)
+    ops.stem_planes_wgrad(x, [g, gb], dwq, dbq, 8, 2, x_cache=cache2)
+    assert rel_err(dwq, dwp) <= 1e-5 and rel_err(dbq, dbp) <= 1e-5
 
 
 def test_conv3x3_wgrad_multi_problem():
