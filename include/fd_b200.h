@@ -106,6 +106,29 @@ FD_API int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* w_pa
  * out2 = its LeakyReLU'-masked, chan_scale2-scaled copy -- the input gradient of a block and the gradient entering the
  * previous block's conv2 in one launch (models/PoolResnet.py:35-40 backward).  Otherwise both -> FD_EUNSUPPORTED. */
 FD_API int fd_conv3x3_wide_shared_tile(int B, int H, int W, int flags);
+
+/* A RUN of wide 3x3 convolutions in ONE launch, for maps small enough that a CTA pair holds a whole image
+ * (fd_conv3x3_wide_chain_ok: H * (W + 2) <= 256 and B <= #SM / 2 -- the 15x15 maps of PoolResnet(filters = 128), where
+ * models/PoolResnet.py:78-81 stacks 8 residual blocks = 16 convolutions).  Layer l reads slab `in_index` of the two stacked
+ * input planes x_stack[g] = [n_stack][B][H][W][64] (bf16) and layer `w_index` of w_packed ([n_w_layers][2][9][128][64], the
+ * fd_pack_conv3x3_wide packing); its outputs / skip / masks / dropout multipliers are those of fd_conv3x3_wide (per-plane
+ * pointers; `out` and `out2` may both be given).  A layer may read what an earlier layer of the same call wrote (that is the
+ * point): layer l + 1 starts when layer l's outputs are complete for the image.  Results are bit-identical to the same
+ * sequence of fd_conv3x3_wide calls. */
+typedef struct fd_wide_chain_layer {
+  int in_index, w_index, flags, reserved;   /* flags: FD_EPI_LRELU */
+  const float* bias;                         /* [128] or NULL */
+  const fd_bf16* residual[2];
+  fd_bf16* out[2];
+  fd_bf16* out2[2];
+  const float* chan_scale[2];
+  const float* chan_scale2[2];
+  const uint32_t* mask_in[2];
+  uint32_t* mask_out[2];
+} fd_wide_chain_layer;
+FD_API int fd_conv3x3_wide_chain_ok(int B, int H, int W);
+FD_API int fd_conv3x3_wide_chain(const fd_bf16* const* x_stack, int n_stack, const fd_bf16* w_packed, int n_w_layers, int B,
+                          int H, int W, float slope, const fd_wide_chain_layer* layers, int n_layers, void* stream);
 /* w: [n_layers][Cout][Cin][3][3] fp32 (torch layout) -> w_fwd [n_layers][Cout/128][Cin/64][9][128][64] bf16 (forward)
  * and w_dgrad [n_layers][Cin/128][Cout/64][9][128][64] bf16 (input gradient: taps flipped, channel roles swapped).
  * Either output may be NULL.  Cout (w_fwd) / Cin (w_dgrad) must be multiples of 128, the other a multiple of 64. */

@@ -564,6 +564,267 @@ conv3x3_wide_kernel(const __grid_constant__ WideMaps maps, const __grid_constant
   if (warp == 1) tmem_dealloc_g<kCg>(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// A RUN of 3x3 convolutions in one launch (fd_conv3x3_wide_chain).  On maps small enough that one CTA pair holds a whole
+// image (15x15 at filters = 128: 16 of the 20 convolutions of a PoolResnet pass, each only ~2.5 us of tensor work) a
+// launch per layer spends more time leaving and entering the GPU than computing: exit + cluster tear-down, the
+// grid-wide dependency, the next launch's set-up, and only then the first TMA round trip (measured 17.5 k clk per layer for
+// 5.7 k clk of MMAs).  Here the pair keeps its image: after the epilogue of layer l has written its planes (plain stores,
+// L2-resident) the two CTAs meet on a cluster-scope mbarrier and load them back as layer l + 1's halo tiles; barriers,
+// TMEM and the weight ring stay alive, and the weight stream runs ahead through the ring while the epilogue works.
+// No grid-wide synchronisation: images are independent.  Same MMAs and the same epilogue arithmetic as the one-layer kernel
+// in shared-tile mode (bit-identical outputs, tests/test_gpu_wide.py).
+// Inputs of every layer are slabs of two STACKED plane buffers [n_stack][B][H][W][64] (engine_planar.py keeps a run's
+// activations / gradients that way for the multi-problem weight-gradient kernel); everything else is a per-layer pointer.
+constexpr int kMaxChain = 16;
+constexpr int kChainInBufs = 2;              // one layer's two input planes: the next layer's cannot start before they are free
+struct ChainLayer {
+  int in_n0;            // first image of this layer's input slab in the stacked planes (slab index * B)
+  int w_row0;           // first row of its packed weights in the weight map
+  int lrelu, has_res;
+  const float* bias;    // [128] or null
+  const __nv_bfloat16* res_ptr[2];
+  __nv_bfloat16* out_ptr[2];        // nullable: conv (+ bias, activation, dropout, skip)
+  __nv_bfloat16* out2_ptr[2];       // nullable: the masked / scaled copy (input-gradient chains)
+  const float* chan_scale[2];
+  const float* chan_scale2[2];
+  const uint16_t* mask_in[2];
+  uint16_t* mask_out[2];
+};
+struct ChainParams {
+  int B, H, W, Wp, nlayers, wslots;
+  uint32_t in_bytes, in_buf_bytes, inv_wp;
+  float slope;
+  ChainLayer layer[kMaxChain];
+};
+struct ChainMaps {
+  CUtensorMap in[2];
+  CUtensorMap w;
+};
+
+__global__ void __launch_bounds__(kThreadsW, 1)
+conv3x3_wide_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int kCg = 2, kN = 128, kNP = 2;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr uint32_t kTapBytes = (kN / 2) * 128u;          // this CTA's 64 couts of one (plane, tap)
+  constexpr uint32_t kChunkBytes = kTapBytes * 3u;         // one ring slot = one kernel row of taps
+  uint8_t* sIn = smem + 16384u;                            // CTA 1 loads its tile 16 KB lower (guard space)
+  uint8_t* sW = sIn + ((kChainInBufs * p.in_buf_bytes + 1023u) & ~1023u);
+  float* sConst = reinterpret_cast<float*>(sW + p.wslots * kChunkBytes);    // bias[128] | chan_scale[128] | chan_scale2[128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sConst + 3 * kNOut);
+  uint64_t* in_full = bars;                       // [2]  (leader's copy is the live one)
+  uint64_t* in_empty = bars + 2;                  // [2]
+  uint64_t* w_full = bars + 4;                    // [8]  (leader)
+  uint64_t* w_empty = bars + 12;                  // [8]
+  uint64_t* acc_full = bars + 20;                 // [2]
+  uint64_t* acc_empty = bars + 22;                // [2]  (leader, 2 arrivals)
+  uint64_t* layer_done = bars + 24;               // [1]  both CTAs' epilogues have written (and fenced) a layer's outputs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n = static_cast<int>(blockIdx.x) / kCg;         // the pair's image
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.in[0]);
+    tma_prefetch_desc(&maps.in[1]);
+    tma_prefetch_desc(&maps.w);
+    for (int i = 0; i < kChainInBufs; ++i) {
+      mbar_init(in_full + i, 1);
+      mbar_init(in_empty + i, 1);
+    }
+    for (int i = 0; i < kMaxWSlots; ++i) {
+      mbar_init(w_full + i, 1);
+      mbar_init(w_empty + i, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full + s, 1);
+      mbar_init(acc_empty + s, kCg);
+    }
+    mbar_init(layer_done, kCg);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_g<kCg>(tmem_slot, 512);
+    tmem_relinquish_g<kCg>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // the peer's barriers exist before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ input loads: layer l's planes, once layer l - 1 is out
+    if (elect_one_sync()) {
+      uint32_t b = 0, ph = 0;
+      for (int l = 0; l < p.nlayers; ++l) {
+        if (l > 0) mbar_wait_cluster(layer_done, static_cast<uint32_t>(l - 1) & 1u);
+        for (int kh = 0; kh < 2; ++kh) {
+          mbar_wait_sleep(in_empty + b, ph ^ 1u);
+          if (leader) mbar_expect_tx(in_full + b, p.in_bytes * kCg);
+          tma_load_4d_g<kCg>(sIn + b * p.in_buf_bytes - rank * 16384u, &maps.in[kh], leader_bar<kCg>(in_full + b), 0, -1, -1,
+                             p.layer[l].in_n0 + n);
+          if (++b == kChainInBufs) { b = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kWeightWarp) {
+    // ------------------------------------------------------------------ weight stream, running ahead through the ring
+    if (elect_one_sync()) {
+      uint32_t s = 0, ph = 0;
+      for (int l = 0; l < p.nlayers; ++l) {
+        const int row0 = p.layer[l].w_row0 + static_cast<int>(rank) * (kN / 2);
+        for (int c = 0; c < 6; ++c) {           // chunk = (input plane c / 3, kernel row c % 3): taps 3c .. 3c + 2 of the [2][9] list
+          mbar_wait_sleep(w_empty + s, ph ^ 1u);
+          if (leader) mbar_expect_tx(w_full + s, kChunkBytes * kCg);
+          for (int i = 0; i < 3; ++i)
+            tma_load_2d_g<kCg>(sW + s * kChunkBytes + i * kTapBytes, &maps.w, leader_bar<kCg>(w_full + s), 0,
+                               row0 + (c * 3 + i) * kN);
+          if (++s == static_cast<uint32_t>(p.wslots)) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader && elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128 * kCg, kN, 0, 0);
+      const uint32_t wp_units = static_cast<uint32_t>(p.Wp) * 8u;
+      uint32_t ib = 0, iph = 0, s = 0, wph = 0;
+      for (int l = 0; l < p.nlayers; ++l) {
+        const uint32_t a = static_cast<uint32_t>(l) & 1u, aph = (static_cast<uint32_t>(l) >> 1) & 1u;
+        mbar_wait_cluster(acc_empty + a, aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * 256u;
+        uint32_t accum = 0;
+        for (int kh = 0; kh < 2; ++kh) {
+          mbar_wait(in_full + ib, iph);
+          tc_fence_after();
+          uint32_t a_lo = sdesc_lo(smem_u32(sIn + ib * p.in_buf_bytes), 16);
+#pragma unroll 1
+          for (int r = 0; r < 3; ++r) {
+            mbar_wait(w_full + s, wph);
+            tc_fence_after();
+            uint32_t b_lo = sdesc_lo(smem_u32(sW + s * kChunkBytes), 16);
+#pragma unroll 1
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_g<kCg>(d_tmem, sdesc_sw128(a_lo + 2 * k), sdesc_sw128(b_lo + 2 * k), idesc, (k != 0) ? 1u : accum);
+              accum = 1;
+              a_lo += 8u;                            // next column
+              b_lo += kTapBytes >> 4;
+            }
+            umma_commit_g<kCg>(w_empty + s);         // weight slot free (in both CTAs) once these MMAs have read it
+            if (++s == static_cast<uint32_t>(p.wslots)) { s = 0; wph ^= 1u; }
+            a_lo += wp_units - 24u;                  // next kernel row
+          }
+          umma_commit_g<kCg>(in_empty + ib);         // input plane buffer free
+          if (++ib == kChainInBufs) { ib = 0; iph ^= 1u; }
+        }
+        umma_commit_g<kCg>(acc_full + a);            // the layer's accumulators are final
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 2 && warp < 2 + kEpiWarpsW) {
+    // ------------------------------------------------------------------ epilogue warps (16): as the one-layer kernel's
+    // shared-tile branch -- this CTA owns GEMM rows [128 rank, 128 rank + 128), one thread = one pixel x 16 channels per plane
+    const int q4 = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    const int c0 = cq * 16;
+    const int et = threadIdx.x - 64;
+    const uint64_t slope2 = pk2(p.slope, p.slope);
+    const int m = static_cast<int>(rank) * 128 + q4 * 32 + lane;
+    const int y = static_cast<int>((static_cast<uint32_t>(m) * p.inv_wp) >> 16);
+    const int x = m - y * p.Wp;
+    const bool valid = (y < p.H) && (x < p.W);
+    const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+    for (int l = 0; l < p.nlayers; ++l) {
+      const ChainLayer& L = p.layer[l];
+      const bool has_cs = L.chan_scale[0] != nullptr, has_cs2 = L.chan_scale2[0] != nullptr;
+      bar_sync_epi_w();               // nobody still reads the previous layer's constants
+      if (et < kN) {
+        sConst[et] = L.bias ? __ldg(L.bias + et) : 0.f;
+      } else if (et < 2 * kN) {
+        const int ch = et - kN;
+        sConst[et] = has_cs ? __ldg(L.chan_scale[ch >> 6] + n * kC + (ch & 63)) : 1.f;
+      } else if (et < 3 * kN) {
+        const int ch = et - 2 * kN;
+        sConst[et] = has_cs2 ? __ldg(L.chan_scale2[ch >> 6] + n * kC + (ch & 63)) : 1.f;
+      }
+      bar_sync_epi_w();
+      // skip / mask operands before the accumulators are awaited.  The skip planes may have been written earlier in THIS
+      // launch (by this very thread: same pixel, same channels): plain loads, not the read-only path.
+      uint4 rr[2][2];
+      uint32_t mb2[2] = {0xffffu, 0xffffu};
+#pragma unroll
+      for (int g = 0; g < kNP; ++g) {
+        rr[g][0] = rr[g][1] = make_uint4(0, 0, 0, 0);
+        if (valid && L.has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(L.res_ptr[g] + pix * kC + c0);
+          rr[g][0] = rp[0];
+          rr[g][1] = rp[1];
+        }
+        if (valid && L.mask_in[g]) mb2[g] = __ldg(L.mask_in[g] + pix * 4 + cq);
+      }
+      const uint32_t a = static_cast<uint32_t>(l) & 1u, aph = (static_cast<uint32_t>(l) >> 1) & 1u;
+      mbar_wait_sleep(acc_full + a, aph, 1000);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < kNP; ++g) {
+        uint32_t acc[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * 256u + static_cast<uint32_t>(g * kC + c0), acc);
+        tmem_ld_wait();
+        if (valid) {
+          uint64_t v2[8];
+          epi_bias_act16(acc, sConst + g * kC + c0, sConst + kNOut + g * kC + c0, L.lrelu != 0, has_cs, slope2, v2);
+          if (L.mask_out[g]) L.mask_out[g][pix * 4 + cq] = static_cast<uint16_t>(epi_sign_bits16(v2));
+          if (L.has_res) epi_add_bf16x16(v2, rr[g][0], rr[g][1]);
+          uint4 u0, u1;
+          if (L.out_ptr[g]) {
+            epi_pack16(v2, u0, u1);
+            uint4* op = reinterpret_cast<uint4*>(L.out_ptr[g] + pix * kC + c0);
+            op[0] = u0;
+            op[1] = u1;
+          }
+          if (L.out2_ptr[g]) {
+            uint64_t o2[8];
+            epi_masked16(v2, mb2[g], p.slope, sConst + 2 * kNOut + g * kC + c0, has_cs2, o2);
+            epi_pack16(o2, u0, u1);
+            uint4* op = reinterpret_cast<uint4*>(L.out2_ptr[g] + pix * kC + c0);
+            op[0] = u0;
+            op[1] = u1;
+          }
+        }
+      }
+      // this thread's stores: ordered at GPU scope and against the async proxy (the next layer's TMA loads, either CTA's)
+      __threadfence();
+      fence_proxy_async_all();
+      tc_fence_before();
+      bar_sync_epi_w();
+      if (et == 0) {
+        if (!leader) mbar_arrive_remote(mapa_shared(smem_u32(acc_empty + a), 0));
+        else mbar_arrive(acc_empty + a);
+        if (l + 1 < p.nlayers) {
+          mbar_arrive_remote(mapa_shared(smem_u32(layer_done), rank ^ 1u));
+          mbar_arrive_remote(mapa_shared(smem_u32(layer_done), rank));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // nobody exits (or frees TMEM) while the pair's MMAs / commits / arrives may still touch it
+  if (warp == 1) tmem_dealloc_g<kCg>(tmem_base, 512);
+}
+
 inline size_t wide_in_buf_bytes(int R, int Wp) { return static_cast<size_t>((R + 2) * Wp) * 128; }
 inline bool wide_split(int R, int Wp) { return 128 % Wp == 0 && (R * Wp) % 128 == 0; }
 inline int wide_unit_rows(int R, int Wp) { return wide_split(R, Wp) ? 128 / Wp : R; }
@@ -926,4 +1187,101 @@ extern "C" int fd_conv3x3_wide(const fd_bf16* const* x, int gin, const fd_bf16* 
                                int flags, void* stream) {
   return fd::conv3x3_pairs(128, x, gin, w_packed, B, H, W, bias, slope, chan_scale, residual, mask_out, out, mask_in,
                            chan_scale2, out2, flags, stream);
+}
+
+// ---- fd_conv3x3_wide_chain: host side ----
+namespace fd {
+namespace {
+// the chain kernel needs a whole image per CTA pair (one two-block tile) and a pair per image
+inline bool wide_chain_ok(int B, int H, int W) {
+  if (wide_cta_group() != 2 || !wide_share_allowed(2) || getenv("FD_WIDE_NO_CHAIN")) return false;
+  const int rows = H * (W + 2);
+  return B >= 1 && B <= sm_count() / 2 && rows > 128 && rows <= 256;
+}
+}  // namespace
+}  // namespace fd
+
+extern "C" int fd_conv3x3_wide_chain_ok(int B, int H, int W) { return fd::wide_chain_ok(B, H, W) ? 1 : 0; }
+
+extern "C" int fd_conv3x3_wide_chain(const fd_bf16* const* x_stack, int n_stack, const fd_bf16* w_packed, int n_w_layers, int B,
+                                     int H, int W, float slope, const fd_wide_chain_layer* layers, int n_layers, void* stream) {
+  using namespace fd;
+  if (!x_stack || !x_stack[0] || !x_stack[1] || !w_packed || !layers || B <= 0 || H <= 0 || W <= 0 || n_stack <= 0 ||
+      n_w_layers <= 0 || n_layers <= 0)
+    return FD_EINVAL;
+  if (n_layers > kMaxChain || !wide_chain_ok(B, H, W) || !(slope >= 0.f && slope <= 1.f)) return FD_EUNSUPPORTED;
+  ChainParams p;
+  p.B = B; p.H = H; p.W = W; p.Wp = W + 2; p.nlayers = n_layers;
+  p.in_bytes = static_cast<uint32_t>((H + 2) * p.Wp * 128);
+  p.in_buf_bytes = static_cast<uint32_t>(wide_in_buf_bytes(H, p.Wp));
+  p.inv_wp = static_cast<uint32_t>((65536 + p.Wp - 1) / p.Wp);
+  p.slope = slope;
+  for (int l = 0; l < n_layers; ++l) {
+    const fd_wide_chain_layer& s = layers[l];
+    ChainLayer& d = p.layer[l];
+    if (s.in_index < 0 || s.in_index >= n_stack || s.w_index < 0 || s.w_index >= n_w_layers) return FD_EINVAL;
+    const bool has_out = s.out[0] && s.out[1], has_out2 = s.out2[0] && s.out2[1], has_res = s.residual[0] && s.residual[1];
+    if (!has_out && !has_out2) return FD_EINVAL;
+    if ((s.out[0] == nullptr) != (s.out[1] == nullptr) || (s.out2[0] == nullptr) != (s.out2[1] == nullptr) ||
+        (s.residual[0] == nullptr) != (s.residual[1] == nullptr) || (s.chan_scale[0] == nullptr) != (s.chan_scale[1] == nullptr) ||
+        (s.chan_scale2[0] == nullptr) != (s.chan_scale2[1] == nullptr) || (s.mask_out[0] == nullptr) != (s.mask_out[1] == nullptr) ||
+        (s.mask_in[0] == nullptr) != (s.mask_in[1] == nullptr))
+      return FD_EINVAL;
+    if (has_out2 && !s.mask_in[0]) return FD_EINVAL;          // the second output is the MASKED copy
+    d.in_n0 = s.in_index * B;
+    d.w_row0 = s.w_index * 2 * 9 * 128;
+    d.lrelu = (s.flags & FD_EPI_LRELU) ? 1 : 0;
+    d.has_res = has_res ? 1 : 0;
+    d.bias = s.bias;
+    for (int g = 0; g < 2; ++g) {
+      d.res_ptr[g] = reinterpret_cast<const __nv_bfloat16*>(s.residual[g]);
+      d.out_ptr[g] = reinterpret_cast<__nv_bfloat16*>(s.out[g]);
+      d.out2_ptr[g] = reinterpret_cast<__nv_bfloat16*>(s.out2[g]);
+      d.chan_scale[g] = s.chan_scale[g];
+      d.chan_scale2[g] = s.chan_scale2[g];
+      d.mask_in[g] = reinterpret_cast<const uint16_t*>(s.mask_in[g]);
+      d.mask_out[g] = reinterpret_cast<uint16_t*>(s.mask_out[g]);
+    }
+  }
+  const size_t fixed = 16384 + ((kChainInBufs * static_cast<size_t>(p.in_buf_bytes) + 1023) / 1024 * 1024) + 3 * kNOut * 4 + 512 + 1024;
+  const size_t chunk = wide_chunk_bytes(2, 3, 128);
+  if (fixed + kMinWSlots * chunk > kWideSmemCap) return FD_EUNSUPPORTED;
+  size_t nslots = (kWideSmemCap - fixed) / chunk;
+  if (nslots > kMaxWSlots) nslots = kMaxWSlots;
+  p.wslots = static_cast<int>(nslots);
+  const size_t smem = fixed + nslots * chunk;
+
+  ChainMaps maps;
+  int rc;
+  for (int g = 0; g < 2; ++g) {
+    rc = make_tmap_nhwc_bf16(&maps.in[g], x_stack[g], n_stack * B, H, W, kC, p.Wp, H + 2);
+    if (rc != FD_OK) return rc;
+  }
+  rc = make_tmap_2d_bf16(&maps.w, w_packed, n_w_layers * 2 * 9 * 128, kC, 64, kC);
+  if (rc != FD_OK) return rc;
+  cudaError_t e = set_max_dyn_smem(conv3x3_wide_chain_kernel, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * B);
+  cfg.blockDim = dim3(kThreadsW);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  e = cudaLaunchKernelEx(&cfg, conv3x3_wide_chain_kernel, maps, p);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  count_launch();
+  return launch_status();
 }

@@ -25,6 +25,8 @@ SIGNATURES = {
     "fd_conv3x3_pool": [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _I, _P],
     "fd_conv3x3_wide": [_P, _I, _P, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "fd_conv3x3_wide_shared_tile": [_I, _I, _I, _I],
+    "fd_conv3x3_wide_chain_ok": [_I, _I, _I],
+    "fd_conv3x3_wide_chain": [_P, _I, _P, _I, _I, _I, _I, _F, _P, _I, _P],
     "fd_pack_conv3x3_wide": [_P, _I, _I, _I, _P, _P, _P],
     "fd_pack_conv1x1_wide": [_P, _I, _I, _I, _P, _P, _P],
     "fd_conv3x3_wgrad_wide": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _c.c_long, _P, _P, _c.c_long, _I, _P],
@@ -101,6 +103,13 @@ class ChainBwdBlock(_c.Structure):
     """fd_chain_bwd_block of include/fd_b200.h"""
     _fields_ = [("mask_a", _P), ("gp1", _P), ("g_in", _P), ("mask_b_prev", _P), ("chan_scale_prev", _P),
                 ("gp2_prev", _P)]
+
+
+class WideChainLayer(_c.Structure):
+    """fd_wide_chain_layer of include/fd_b200.h"""
+    _fields_ = [("in_index", _I), ("w_index", _I), ("flags", _I), ("reserved", _I), ("bias", _P), ("residual", _P * 2),
+                ("out", _P * 2), ("out2", _P * 2), ("chan_scale", _P * 2), ("chan_scale2", _P * 2), ("mask_in", _P * 2),
+                ("mask_out", _P * 2)]
 
 
 _lib = None

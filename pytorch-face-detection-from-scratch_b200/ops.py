@@ -6,7 +6,7 @@ import torch
 
 import ctypes
 
-from .native import ChainBwdBlock, ChainFwdBlock, check, cur_stream, dptr, lib
+from .native import ChainBwdBlock, ChainFwdBlock, WideChainLayer, check, cur_stream, dptr, lib
 
 BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
 
@@ -61,6 +61,37 @@ def conv3x3_wide(x_planes, w_packed, *, bias=None, slope=0.2, lrelu=False, chan_
 def conv3x3_wide_shared_tile(B, H, W, flags=0):
     """True when fd_conv3x3_wide runs this map in shared-tile mode, i.e. may write out AND out2 in one launch."""
     return bool(lib().fd_conv3x3_wide_shared_tile(int(B), int(H), int(W), int(flags)))
+
+
+def conv3x3_wide_chain_ok(B, H, W):
+    """True when a run of wide convolutions on this map can go out as ONE launch (a CTA pair holds a whole image)."""
+    return bool(lib().fd_conv3x3_wide_chain_ok(int(B), int(H), int(W)))
+
+
+def wide_chain_layer(in_index, w_index, *, bias=None, lrelu=False, chan_scale=None, residual=None, mask_out=None, out=None,
+                     mask_in=None, chan_scale2=None, out2=None):
+    """One fd_wide_chain_layer; per-plane arguments are lists of two tensors as in conv3x3_wide."""
+    L = WideChainLayer()
+    L.in_index, L.w_index, L.flags, L.reserved = int(in_index), int(w_index), (EPI_LRELU if lrelu else 0), 0
+    L.bias = dptr(bias, F32)
+    for name, planes, dt in (("residual", residual, BF16), ("out", out, BF16), ("out2", out2, BF16), ("chan_scale", chan_scale, F32),
+                             ("chan_scale2", chan_scale2, F32), ("mask_in", mask_in, I32), ("mask_out", mask_out, I32)):
+        arr = getattr(L, name)
+        for g in range(2):
+            arr[g] = dptr(planes[g], dt) if planes is not None else None
+    return L
+
+
+def conv3x3_wide_chain(x_stack, w_packed, layers, slope=0.2):
+    """fd_conv3x3_wide_chain.  x_stack: two stacked plane buffers [n_stack,B,H,W,64] bf16; w_packed: [n_w_layers,1,2,9,128,64]
+    (or [n_w_layers,2,9,128,64]) bf16; layers: wide_chain_layer(...) records, executed in order by one launch."""
+    n_stack, B, H, W, C = x_stack[0].shape
+    assert C == 64 and x_stack[1].shape == x_stack[0].shape and w_packed.numel() % (2 * 9 * 128 * 64) == 0
+    arr = (WideChainLayer * len(layers))(*layers)
+    ptrs = (ctypes.c_void_p * 2)(dptr(x_stack[0], BF16), dptr(x_stack[1], BF16))
+    check(lib().fd_conv3x3_wide_chain(ctypes.cast(ptrs, ctypes.c_void_p), n_stack, dptr(w_packed, BF16),
+                                      w_packed.numel() // (2 * 9 * 128 * 64), B, H, W, slope, ctypes.cast(arr, ctypes.c_void_p),
+                                      len(layers), cur_stream()), "fd_conv3x3_wide_chain")
 
 
 def pack_conv3x3_wide(w, w_fwd, w_dgrad):

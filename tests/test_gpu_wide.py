@@ -153,3 +153,85 @@ def test_conv3x3_wgrad_wide_vs_autograd(nprob, B, H, W):
         got = dw[q * 4:(q + 1) * 4].view(2, 2, 64, 64, 3, 3).permute(0, 2, 1, 3, 4, 5).reshape(128, 128, 3, 3)   # [(c,co),(r,ci)]
         assert rel_err(got, gw) <= 2e-3, (q, rel_err(got, gw))
         assert rel_err((db[q] - 0.25).reshape(-1), gb) <= 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,nblocks", [(3, 15, 15, 2), (64, 15, 15, 8), (5, 12, 14, 1)])
+def test_conv3x3_wide_chain_is_bit_identical_to_single_launches(B, H, W, nblocks):
+    """fd_conv3x3_wide_chain (a whole run of residual blocks in ONE launch, the pair keeps its image and re-loads what it just
+    wrote) against the same layers as individual fd_conv3x3_wide launches: forward (models/PoolResnet.py:35-42 -- conv, bias,
+    LeakyReLU, sign masks, Dropout2d multiplier, skip) and the input-gradient run (masked / scaled second outputs)."""
+    require_cuda()
+    ops = fd().ops
+    if not ops.conv3x3_wide_chain_ok(B, H, W):
+        pytest.skip("map does not fit a CTA pair")
+    torch.manual_seed(B + H + nblocks)
+    dev = "cuda"
+    nl = 2 * nblocks
+    bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
+    w = torch.randn(nl, 128, 128, 3, 3, device=dev) * 0.03
+    bias = torch.randn(nl, 128, device=dev) * 0.1
+    wf = torch.empty(nl, 1, 2, 9, 128, 64, dtype=torch.bfloat16, device=dev)
+    wd = torch.empty(nl, 1, 2, 9, 128, 64, dtype=torch.bfloat16, device=dev)
+    ops.pack_conv3x3_wide(w, wf, wd)
+    drop = (torch.rand(nblocks, 2, B, 64, device=dev) < 0.75).float() / 0.75
+    x0 = torch.randn(B, H, W, 128, device=dev).bfloat16()
+
+    def forward(chain):
+        XA = [bf(nl + 1, B, H, W, 64) for _ in range(2)]
+        masks = [[torch.zeros(B, H, W, 2, dtype=torch.int32, device=dev) for _ in range(2)] for _ in range(nl)]
+        for g in range(2):
+            XA[g][0].copy_(x0[..., 64 * g:64 * g + 64])
+        layers = []
+        for i in range(nblocks):
+            a = dict(bias=bias[2 * i], lrelu=True, mask_out=masks[2 * i], out=[XA[g][2 * i + 1] for g in range(2)])
+            b = dict(bias=bias[2 * i + 1], lrelu=True, chan_scale=[drop[i, 0], drop[i, 1]], residual=[XA[g][2 * i] for g in range(2)],
+                     mask_out=masks[2 * i + 1], out=[XA[g][2 * i + 2] for g in range(2)])
+            if chain:
+                layers += [ops.wide_chain_layer(2 * i, 2 * i, **a), ops.wide_chain_layer(2 * i + 1, 2 * i + 1, **b)]
+            else:
+                ops.conv3x3_wide([XA[g][2 * i] for g in range(2)], wf[2 * i, 0], **a)
+                ops.conv3x3_wide([XA[g][2 * i + 1] for g in range(2)], wf[2 * i + 1, 0], **b)
+        if chain:
+            ops.conv3x3_wide_chain(XA, wf, layers)
+        return XA, masks
+
+    XA_c, m_c = forward(True)
+    XA_s, m_s = forward(False)
+    for g in range(2):
+        assert torch.equal(XA_c[g].view(torch.int16), XA_s[g].view(torch.int16))
+    assert all(torch.equal(a, b) for la, lb in zip(m_c, m_s) for a, b in zip(la, lb))
+    assert XA_s[0][nl].float().abs().max() > 0
+
+    g_top = (torch.randn(B, H, W, 128, device=dev) * 0.1).bfloat16()
+
+    def backward(chain):
+        GP = [bf(nl, B, H, W, 64) for _ in range(2)]                    # [2 i] = gp1 of block i, [2 i + 1] = gp2
+        Gb = [[bf(B, H, W, 64) for _ in range(2)] for _ in range(nblocks + 1)]      # [i + 1] = gradient of block i's output
+        for g in range(2):
+            Gb[nblocks][g].copy_(g_top[..., 64 * g:64 * g + 64])
+            GP[g][nl - 1].copy_(g_top[..., 64 * g:64 * g + 64])         # stand-in for the head's masked gradient
+        layers = []
+        for i in range(nblocks - 1, -1, -1):
+            d2 = dict(mask_in=m_s[2 * i], out2=[GP[g][2 * i] for g in range(2)])
+            d1 = dict(residual=Gb[i + 1], out=Gb[i])
+            if i > 0:
+                d1.update(mask_in=m_s[2 * i - 1], chan_scale2=[drop[i - 1, 0], drop[i - 1, 1]], out2=[GP[g][2 * i - 1] for g in range(2)])
+            if chain:
+                layers += [ops.wide_chain_layer(2 * i + 1, 2 * i + 1, **d2), ops.wide_chain_layer(2 * i, 2 * i, **d1)]
+            else:
+                ops.conv3x3_wide([GP[g][2 * i + 1] for g in range(2)], wd[2 * i + 1, 0], **d2)
+                if "out2" in d1 and not ops.conv3x3_wide_shared_tile(B, H, W):     # both outputs: shared-tile launches only
+                    d1b = {k: v for k, v in d1.items() if k != "out"}
+                    ops.conv3x3_wide([GP[g][2 * i] for g in range(2)], wd[2 * i, 0], **d1b)
+                    d1 = dict(residual=d1["residual"], out=d1["out"])
+                ops.conv3x3_wide([GP[g][2 * i] for g in range(2)], wd[2 * i, 0], **d1)
+        if chain:
+            ops.conv3x3_wide_chain(GP, wd, layers)
+        return GP, Gb
+
+    GP_c, G_c = backward(True)
+    GP_s, G_s = backward(False)
+    for g in range(2):
+        assert torch.equal(GP_c[g].view(torch.int16), GP_s[g].view(torch.int16))
+    assert all(torch.equal(a.view(torch.int16), b.view(torch.int16)) for la, lb in zip(G_c, G_s) for a, b in zip(la, lb))
+    assert G_s[0][0].float().abs().max() > 0
