@@ -641,8 +641,12 @@ def f128_train(fd, dev, world, args, barrier, par, peaks):
     topt._ensure_state()
     for name, prm in m.named_parameters():
         prm.grad = eng.grad_view(name)
-    calls = {"conv": [], "wgrad": []}
-    o_conv, o_wgrad = ops.conv3x3_wide, ops.conv3x3_wgrad_wide
+    calls = {"conv": [], "wgrad": [], "chain": []}
+    o_conv, o_wgrad, o_chain = ops.conv3x3_wide, ops.conv3x3_wgrad_wide, ops.conv3x3_wide_chain
+
+    def rec_chain(xs, w, layers, **kw):
+        calls["chain"].append((xs, w, layers, kw))
+        o_chain(xs, w, layers, **kw)
 
     def rec_conv(xp, w, **kw):
         calls["conv"].append((xp, w, kw))
@@ -652,12 +656,12 @@ def f128_train(fd, dev, world, args, barrier, par, peaks):
         calls["wgrad"].append((a, kw))
         o_wgrad(*a, **kw)
 
-    ops.conv3x3_wide, ops.conv3x3_wgrad_wide = rec_conv, rec_wgrad
+    ops.conv3x3_wide, ops.conv3x3_wgrad_wide, ops.conv3x3_wide_chain = rec_conv, rec_wgrad, rec_chain
     try:
         eng.train_step(x, gt, dropout=True)
         torch.cuda.synchronize()
     finally:
-        ops.conv3x3_wide, ops.conv3x3_wgrad_wide = o_conv, o_wgrad
+        ops.conv3x3_wide, ops.conv3x3_wgrad_wide, ops.conv3x3_wide_chain = o_conv, o_wgrad, o_chain
     g, _, launches = capture(lambda: eng.train_step(x, gt, dropout=True, optimizer=topt))
     ms, _, _ = timed_graph_region(g.replay, max(3, min(args.steps, 20)), 3, barrier, par, dev)
     burst = peaks.get("bf16_tflops") or 1590.0
@@ -681,6 +685,8 @@ def f128_train(fd, dev, world, args, barrier, par, peaks):
     big = [c for c in calls["conv"] if c[0][0].shape[1] == 60]
     conv_fl = lambda c: 2.0 * c[0][0].shape[0] * c[0][0].shape[1] * c[0][0].shape[2] * 9 * 64 * len(c[0]) * 128
     wg_fl = lambda c: 2.0 * c[0][0].numel() / 64 * 9 * 128 * 128
+    chain_fl = lambda c: 2.0 * len(c[2]) * c[0][0].shape[1] * c[0][0].shape[2] * c[0][0].shape[3] * 9 * 128 * 128
+    n_chain_layers = sum(len(c[2]) for c in calls["chain"])
     return {"metric": "train_images_per_sec", "value": B / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
             "launches_per_step": launches, "cuda_graph": True,
             "achieved_tflops_algorithmic": 3 * 3.997e9 * B / (ms * 1e-3) / 1e12,
@@ -690,8 +696,13 @@ def f128_train(fd, dev, world, args, barrier, par, peaks):
                                              "conv3x3_wide_kernel<2> (tcgen05.mma.cta_group::2, M=256 N=128; the 60x60 forward + "
                                              "input-gradient launches of one step)", "conv3x3_wide_kernel_60x60"),
             "roofline_conv_wide_all": roof(calls["conv"], lambda c: o_conv(c[0], c[1], **c[2]), conv_fl,
-                                           "conv3x3_wide_kernel<2>, all 40 launches of one step (32 of them on 15x15 maps: 64 tiles)",
-                                           "conv3x3_wide_kernel_all"),
+                                           f"conv3x3_wide_kernel<2>, the {len(calls['conv'])} single-layer launches of one step "
+                                           "(60x60 and 30x30 maps)", "conv3x3_wide_kernel_all"),
+            "roofline_conv_wide_chain": roof(calls["chain"], lambda c: o_chain(c[0], c[1], c[2], **c[3]), chain_fl,
+                                             f"conv3x3_wide_chain_kernel: the {n_chain_layers} convolutions on 15x15 maps (8 residual "
+                                             f"blocks forward, 8 backward) in {len(calls['chain'])} launches -- one CTA pair per image, "
+                                             "64 of 74 pairs busy, each layer's MMAs wait for the previous layer's epilogue",
+                                             "conv3x3_wide_chain_kernel"),
             "roofline_wgrad_wide": roof(calls["wgrad"], lambda c: o_wgrad(*c[0], **c[1]), wg_fl,
                                         "wgrad3x3_wide_kernel (cta_group::2, two passes per call)", "wgrad3x3_wide_kernel")}
 

@@ -278,6 +278,58 @@ class PlanarEngine:
     def _pairs(self, planes, go):
         return None if planes is None or planes[0] is None else [planes[2 * go], planes[2 * go + 1]]
 
+    kChainBlocks = 8        # fd_conv3x3_wide_chain takes up to 16 layers
+
+    def _chain_runs(self, pl):
+        """{k0: k1} of the runs of >= 2 blocks whose maps fit a CTA pair (fd_conv3x3_wide_chain): 128-filter models only."""
+        if not (self.use_wide and self.G == 2):
+            return {}
+        return {k0: k1 for (k0, k1) in pl.runs
+                if k1 > k0 and ops.conv3x3_wide_chain_ok(pl.B, pl.blocks[k0].H, pl.blocks[k0].W)}
+
+    def _run_forward_chain(self, pl, k0, k1):
+        """models/PoolResnet.py:35-42 for the blocks k0..k1 of one run: 2 (k1 - k0 + 1) convolutions, one launch per 8 blocks."""
+        for c0 in range(k0, k1 + 1, self.kChainBlocks):
+            layers = []
+            for k in range(c0, min(c0 + self.kChainBlocks, k1 + 1)):
+                blk, i = pl.blocks[k], k - k0
+                drop = [pl.drop[k, g] for g in range(2)] if pl.drop is not None else None
+                layers.append(ops.wide_chain_layer(2 * i, 2 * k, bias=self.b3[2 * k].reshape(-1), lrelu=True,
+                                                   mask_out=self._pairs(blk.ma, 0), out=blk.a))
+                layers.append(ops.wide_chain_layer(2 * i + 1, 2 * k + 1, bias=self.b3[2 * k + 1].reshape(-1), lrelu=True,
+                                                   chan_scale=drop, residual=blk.inp, mask_out=self._pairs(blk.mb, 0), out=blk.s))
+            ops.conv3x3_wide_chain(pl.XA[k0], self.w_fwd_wide, layers, slope=self.slope)
+        last = pl.blocks[k1]
+        if last.pool:
+            main = self._fork()
+            for g in range(self.G):
+                with self._on(main, g):
+                    ops.maxpool2x2_fwd(last.s[g], last.out[g], last.amax[g])
+            self._join(main)
+
+    def _run_dgrad_chain(self, pl, k0, k1, drop, fused_gp2):
+        """Input-gradient pass of the run k0..k1 (gp2 of block k1 is final): per block gp1 = dgrad(gp2, W2) * lrelu'(a), then
+        G_{k-1} = dgrad(gp1, W1) + GS together with the previous block's gp2 = G_{k-1} * lrelu'(b) * dropout."""
+        k = k1
+        while k >= k0:
+            c0 = max(k0, k - self.kChainBlocks + 1)
+            layers = []
+            for kk in range(k, c0 - 1, -1):
+                blk, i = pl.blocks[kk], kk - k0
+                GS = blk.gs if blk.pool else blk.G
+                gprev = pl.blocks[kk - 1].G if kk > 0 else pl.g_stem
+                layers.append(ops.wide_chain_layer(2 * i + 1, 2 * kk + 1, mask_in=blk.ma, out2=blk.gp1))
+                if kk > k0:
+                    prev = pl.blocks[kk - 1]
+                    cs2 = [drop[kk - 1, 0], drop[kk - 1, 1]] if drop is not None else None
+                    layers.append(ops.wide_chain_layer(2 * i, 2 * kk, residual=GS, out=gprev, mask_in=prev.mb, chan_scale2=cs2,
+                                                       out2=prev.gp2))
+                    fused_gp2.add(kk - 1)
+                else:
+                    layers.append(ops.wide_chain_layer(2 * i, 2 * kk, residual=GS, out=gprev))
+            ops.conv3x3_wide_chain(pl.GP[k0], self.w_dgrad_wide, layers, slope=self.slope)
+            k = c0 - 1
+
     def _block_forward_wide(self, pl, k, blk, cur):
         """models/PoolResnet.py:35-42 for one block on fd_conv3x3_wide: one launch per convolution and group of 128 couts."""
         G = self.G
@@ -313,9 +365,15 @@ class PlanarEngine:
         w1, b1 = P["conv1.weight"].detach().float(), P["conv1.bias"].detach().float()
         ops.stem_planes_fwd(x, w1, b1, pl.act0, self.stem_s, self.stem_pad, x_cache=pl.x_cache)
         cur = pl.act0
+        chain_end = self._chain_runs(pl)
+        skip_until = -1
         for k, blk in enumerate(pl.blocks):
             if self.use_wide:
-                self._block_forward_wide(pl, k, blk, cur)
+                if k in chain_end:                  # the whole run k .. chain_end[k] in one launch per 8 blocks
+                    self._run_forward_chain(pl, k, chain_end[k])
+                    skip_until = chain_end[k]
+                if k > skip_until:
+                    self._block_forward_wide(pl, k, blk, cur)
                 cur = blk.out
                 continue
             main = self._fork()
@@ -365,6 +423,8 @@ class PlanarEngine:
                          last.G[g], None, None, self.slope, None, dwg, dbg)
             gw_out[:, g * 64:(g + 1) * 64].copy_(dwg)
         fused_gp2 = set()
+        chain_start = {k1: k0 for k0, k1 in self._chain_runs(pl).items()}
+        chained = set()
         for k in range(nb - 1, -1, -1):
             blk = pl.blocks[k]
             L1, L2 = 2 * k, 2 * k + 1
@@ -381,7 +441,12 @@ class PlanarEngine:
                 self._join(main)
             GS = blk.gs if blk.pool else blk.G
             gprev = pl.blocks[k - 1].G if k > 0 else pl.g_stem
-            if self.use_wide:
+            if k in chain_start:                # last block of a chained run: its gp2 is final -> the run's whole dgrad pass
+                self._run_dgrad_chain(pl, chain_start[k], k, drop, fused_gp2)
+                chained.update(range(chain_start[k], k + 1))
+            if k in chained:
+                pass
+            elif self.use_wide:
                 # gp1 = dgrad(gp2, W2) * lrelu'(a);  G_{k-1} = dgrad(gp1, W1) + GS  -- one launch per group of 128 channels
                 for go in range(G // 2):
                     ops.conv3x3_wide(blk.gp2, self.w_dgrad_wide[L2, go], slope=self.slope, mask_in=self._pairs(blk.ma, go),

@@ -4,7 +4,7 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 T=${1:-r2n}
-KS='regex:conv3x3_tc_kernel|wgrad3x3_tc_kernel|resblock_chain_kernel|conv3x3_wide_kernel|wgrad3x3_wide_kernel|stem_fwd_tc_kernel|stem_wgrad_bf16|sepblock_fwd_kernel|pw_gemm_kernel|dwconv|mbv3_stem_tc'
+KS='regex:conv3x3_tc_kernel|wgrad3x3_tc_kernel|resblock_chain_kernel|conv3x3_wide_kernel|conv3x3_wide_chain_kernel|wgrad3x3_wide_kernel|stem_fwd_tc_kernel|stem_fwd_bf16_kernel|stem_wgrad_bf16|sepblock_fwd_kernel|pw_gemm_kernel|dwconv|mbv3_stem_tc'
 timeout 300 python tools/ncu_r2.py all > gpurun_out/${T}_plain.log 2>&1; echo "plain rc=$?"
 timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k "$KS" -c 70 -o gpurun_out/${T}_full -f python tools/ncu_r2.py all > gpurun_out/${T}_ncu.log 2>&1; echo "ncu rc=$?"
 ncu -i gpurun_out/${T}_full.ncu-rep --page raw --csv > gpurun_out/${T}_raw.csv 2> gpurun_out/${T}_raw.err; echo "raw rc=$?"
