@@ -396,14 +396,19 @@ class PlanarEngine:
         wo = P["out.weight"].detach().float()
         pl.head_in = cur
         pl.w_head = [wo[:, g * 64:(g + 1) * 64].contiguous() for g in range(G)]
-        logits = None
+        # the per-plane head kernels fill less than half of the SMs each: run them side by side (buffers from the main stream)
+        wts = [torch.empty(self.head_k * self.head_k * 5 * 64, dtype=F32, device=x.device) for _ in range(G)]
+        parts = [torch.empty_like(pl.y) for _ in range(G)]
+        main = self._fork()
         for g in range(G):
-            wt = torch.empty(self.head_k * self.head_k * 5 * 64, dtype=F32, device=x.device)
-            ops.head_pack(pl.w_head[g], wt)
-            part = torch.empty_like(pl.y)
-            ops.head_fwd(cur[g], pl.drop[nb, g] if pl.drop is not None else None, pl.w_head[g], None, part, self.head_pad,
-                         w_t=wt)
-            logits = part if logits is None else logits + part
+            with self._on(main, g):
+                ops.head_pack(pl.w_head[g], wts[g])
+                ops.head_fwd(cur[g], pl.drop[nb, g] if pl.drop is not None else None, pl.w_head[g], None, parts[g], self.head_pad,
+                             w_t=wts[g])
+        self._join(main)
+        logits = parts[0]
+        for g in range(1, G):
+            logits = logits + parts[g]
         torch.sigmoid(logits + P["out.bias"].detach().float().view(1, 5, 1, 1), out=pl.y)
         return pl
 
@@ -416,12 +421,16 @@ class PlanarEngine:
         self.dwp.zero_()
         last = pl.blocks[nb - 1]
         gw_out = self.section(self.gflat, "out.weight")
-        for g in range(G):          # tensor-core head backward per plane; dbias is the same for every plane: count it once
-            dwg = torch.zeros_like(pl.w_head[g])
-            dbg = self.section(self.gflat, "out.bias") if g == 0 else torch.zeros(5, dtype=F32, device=dy.device)
-            ops.head_bwd(pl.head_in[g], drop[nb, g] if drop is not None else None, pl.w_head[g], pl.y, dy, self.head_pad,
-                         last.G[g], None, None, self.slope, None, dwg, dbg)
-            gw_out[:, g * 64:(g + 1) * 64].copy_(dwg)
+        # tensor-core head backward per plane, side by side; dbias is the same for every plane: count it once
+        dwgs = [torch.zeros_like(pl.w_head[g]) for g in range(G)]
+        dbgs = [self.section(self.gflat, "out.bias") if g == 0 else torch.zeros(5, dtype=F32, device=dy.device) for g in range(G)]
+        main = self._fork()
+        for g in range(G):
+            with self._on(main, g):
+                ops.head_bwd(pl.head_in[g], drop[nb, g] if drop is not None else None, pl.w_head[g], pl.y, dy, self.head_pad,
+                             last.G[g], None, None, self.slope, None, dwgs[g], dbgs[g])
+                gw_out[:, g * 64:(g + 1) * 64].copy_(dwgs[g])
+        self._join(main)
         fused_gp2 = set()
         chain_start = {k1: k0 for k0, k1 in self._chain_runs(pl).items()}
         chained = set()
