@@ -34,7 +34,7 @@ struct WgradWideParams {
   int nprob, tiles_per_prob, pairs_per_prob, per;
   int npairs;                 // tap pairs of this pass
   int pair_t0[4];             // first tap of every pair (the second is t0 + 1)
-  int drop_first;             // the first tap of the pairs is a duplicate (pass 2): its rows are reduced as zeros
+  int drop_first;             // bit j: the first tap of pair j is a duplicate (the pair (7, 8)): its rows are reduced as zeros
   int sub_row[2][2];          // [r][c]: row of sub-block (g = 2gg + c, h = 2hh + r) in the [., 64] fp32 view of dw, problem 0
   int dw_rows_per_prob;
   float* dbias[2];            // [r]: bias gradient of g plane 2gg + r, problem 0 (nullable)
@@ -205,9 +205,9 @@ wgrad3x3_wide_kernel(const __grid_constant__ WgradWideMaps maps, const __grid_co
       tc_fence_after();
       const int row = q * 32 + lane;           // = tsel * 64 + ci
       const uint32_t sw = static_cast<uint32_t>(row) & 7u;
-      const bool dup = p.drop_first && row < 64;
 #pragma unroll 1
       for (int j = 0; j < p.npairs; ++j) {
+        const bool dup = ((p.drop_first >> j) & 1) && row < 64;
         uint8_t* base = sStage + static_cast<size_t>(j & 1) * (4 * 128 * 128);
         if (j >= 2) {          // the reduce-stores of pair j - 2 must have read this half
           if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -350,16 +350,22 @@ extern "C" int fd_conv3x3_wgrad_wide(const fd_bf16* x0, const fd_bf16* x1, const
 
   cudaError_t e = set_max_dyn_smem(wgrad3x3_wide_kernel, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  // pass 1: taps 0..7 as four pairs (4 x 128 TMEM columns); pass 2: tap 8 as the pair (7, 8) with the tap-7 half dropped
+  // Nine taps = five tap PAIRS (M = 256 = 2 taps x 128 cin), the last one (7, 8) with its tap-7 half dropped; TMEM holds four
+  // pair accumulators, so two passes: 4 + 1 pairs.  The second pass re-reads x and g for a single MMA per 16 pixels (memory
+  // bound); a balanced 3 + 2 split (FD_WGRAD_WIDE_SPLIT=32) was measured and is SLOWER: 140.1 vs 136.4 us at 60x60, 54.4 vs
+  // 50.5 at 30x30, equal at 15x15 (batch 64) -- the first pass is not purely tensor-bound, so shortening it gains less than
+  // the second MMA of pass 2 costs.
+  static const bool split41 = [] { const char* e = getenv("FD_WGRAD_WIDE_SPLIT"); return !(e && atoi(e) == 32); }();
   for (int pass = 0; pass < 2; ++pass) {
     if (pass == 0) {
-      p.npairs = 4;
+      p.npairs = split41 ? 4 : 3;
       for (int j = 0; j < 4; ++j) p.pair_t0[j] = 2 * j;
       p.drop_first = 0;
     } else {
-      p.npairs = 1;
-      p.pair_t0[0] = 7; p.pair_t0[1] = p.pair_t0[2] = p.pair_t0[3] = 7;
-      p.drop_first = 1;
+      p.npairs = split41 ? 1 : 2;
+      p.pair_t0[0] = split41 ? 7 : 6;
+      p.pair_t0[1] = p.pair_t0[2] = p.pair_t0[3] = 7;
+      p.drop_first = split41 ? 1 : 2;
       p.dbias[0] = p.dbias[1] = nullptr;        // counted in pass 1
     }
     cudaLaunchConfig_t cfg = {};
