@@ -432,7 +432,9 @@ class SSDEngine:
         if getattr(self, "_wg_sides", None) is None:
             n_side = int(os.environ.get("FD_SSD_WGRAD_STREAMS", "4"))
             self._wg_sides = [torch.cuda.Stream(device=dy.device) for _ in range(n_side)]
-        sides, rr = self._wg_sides, [0]
+        # only as branches of a captured graph: in eager mode the extra event records / waits cost more host time than the
+        # overlap returns (the eager 2-GPU step, which is launch-bound, went from 4.1 to 5.3 ms with them)
+        sides, rr = (self._wg_sides if torch.cuda.is_current_stream_capturing() else []), [0]
 
         def side():
             if not sides:
