@@ -241,6 +241,182 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------- N = 192 formulation
+// All nine taps from TWO instructions per 16 pixels.  Moving the column shift of a tap onto the GRADIENT operand,
+//   dW[dy][dx][ci][co] = sum_q xpad[q + dy*Wp + dx][ci] g[q][co] = sum_q' xpad[q' + dy*Wp][ci] g[q' - dx][co],
+// makes the M side the row shifts (atoms of 64 cin, Wp rows apart) and the N side the column shifts (atoms of 64 cout, ONE
+// row apart): D[(dy, ci), (dx, co)] with M = 128 = 2 row shifts and N = 192 = 3 column shifts.  Instruction 1 = dy 0, 1;
+// instruction 2 = dy 2 (its second atom is a fourth row shift: computed, never drained).  Per 16 pixels: 2 x 96 clk of tensor
+// work for 9 taps (75 % useful) and 10 KB of operand reads per instruction (107 B/clk: below the shared-memory bound), where
+// the tap-pair form issues five M=128, N=64 instructions of ~73 clk (6 KB each: operand bound, 10 tap slots for 9 taps).
+// The gradient tile is loaded two pixels further right (TMA box starts at x = -2: zero filled), so g[q' - dx] is the tile read
+// (2 - dx) rows from its start; the K range grows by two pixels.  Accumulators: 2 x 192 TMEM columns across all tiles of the CTA.
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad3x3_n192_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ GMaps gmaps,
+                     const __grid_constant__ CUtensorMap tm_dw, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const uint32_t stage_bytes = p.x_buf_bytes + p.g_buf_bytes;
+  uint8_t* sStage = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* full = bars + 0;      // [2]
+  uint64_t* empty = bars + 2;     // [2]
+  uint64_t* acc_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* sBias = reinterpret_cast<float*>(bars + 6);  // [128]
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // K-padding rows of g and the over-read tail of x are never written by TMA and must stay zero.
+  for (uint32_t i = threadIdx.x * 16u; i < 2 * stage_bytes; i += kThreads * 16u)
+    *reinterpret_cast<uint4*>(sStage + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&gmaps.m[0]);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1 + 4);  // MMA commit + the four column-sum warps
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  const int prob = blockIdx.x / p.ctas_per_prob;
+  const int chunk = blockIdx.x - prob * p.ctas_per_prob;
+  const int tile_begin = prob * p.tiles_per_prob + min(p.tiles_per_prob, chunk * p.per);
+  const int tile_end = prob * p.tiles_per_prob + min(p.tiles_per_prob, (chunk + 1) * p.per);
+  float* const dbias_out = p.dbias ? p.dbias + prob * p.dbias_stride : nullptr;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int it = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        const int n = tile / p.tiles_per_img;
+        const int rem = tile - n * p.tiles_per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        const int h0 = th * p.R, w0 = tw * p.TW;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, p.x_bytes + p.g_bytes);
+        tma_load_4d(sStage + s * stage_bytes, &tm_x, full + s, 0, w0 - 1, h0 - 1, n);
+        tma_load_4d(sStage + s * stage_bytes + p.x_buf_bytes, &gmaps.m[tw], full + s, 0, -2, h0, n);   // two zero pixels first
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 3 * kC, 1, 1);  // both operands MN-major
+    int it = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(full + s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t x_addr = smem_u32(sStage + s * stage_bytes);
+        // N atom j = column shift dx = 2 - j: the tile read j rows from its start, atoms 128 B apart (LBO)
+        const uint32_t g_lo = sdesc_lo(x_addr + p.x_buf_bytes, 128);
+        // M atoms = row shifts dy, dy + 1: Wp rows apart
+        const uint32_t a_lo0 = sdesc_lo(x_addr, static_cast<uint32_t>(p.Wp) * 128u);
+        const uint32_t a_lo1 = sdesc_lo(x_addr + static_cast<uint32_t>(2 * p.Wp) * 128u, static_cast<uint32_t>(p.Wp) * 128u);
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          const uint64_t bd = sdesc_sw128(g_lo + ks * 128);      // 16 pixel rows = 2048 B per K step
+          const uint32_t acc = (it | ks) != 0 ? 1u : 0u;
+          umma_bf16(tmem_base, sdesc_sw128(a_lo0 + ks * 128), bd, idesc, acc);
+          umma_bf16(tmem_base + 3 * kC, sdesc_sw128(a_lo1 + ks * 128), bd, idesc, acc);
+        }
+        umma_commit(empty + s);
+        if (tile + 1 == tile_end) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue warps: (1) bias gradient from the smem g tiles while the MMAs run (zero rows add nothing)
+    const int et = threadIdx.x - 64;      // 0..127
+    const int c = et & 63, rpar = et >> 6;
+    float bsum = 0.f;
+    int it = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(full + s, ph);
+      if (p.dbias) {
+        const uint8_t* g = sStage + s * stage_bytes + p.x_buf_bytes;
+        const int rows = p.R * p.Wp;
+        for (int r = rpar; r < rows; r += 2) {
+          const uint32_t off = r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1));
+          bsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(g + off));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+    // (2) drain: accumulator a (rows dy = 2a, 2a + 1), column block j (dx = 2 - j) -> tap (dy, dx); 18 staging tiles
+    // [64 ci][32 fp32] (tap, column half) with the 128B swizzle of the tensor map, then TMA reduce-stores into [9][ci][co]
+    if (tile_begin < tile_end) {
+      const int q = warp & 3;
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const int row = q * 32 + lane;           // = (dy & 1) * 64 + ci
+      const int ci = row & 63;
+      const uint32_t sw = static_cast<uint32_t>(ci) & 7u;
+#pragma unroll 1
+      for (int a = 0; a < 2; ++a) {
+        const int dy = 2 * a + (row >> 6);
+        if (dy < 3) {                          // warp-uniform: a warp is one lane quadrant = one row shift
+#pragma unroll 1
+          for (int j = 0; j < 3; ++j) {
+            const int tap = dy * 3 + (2 - j);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t acc[32];
+              tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                     static_cast<uint32_t>(a * 3 * kC + j * kC + half * 32),
+                                 acc);
+              tmem_ld_wait();
+              uint8_t* tile = sStage + static_cast<size_t>(tap * 2 + half) * (64 * 128) + ci * 128;
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                *reinterpret_cast<uint4*>(tile + ((static_cast<uint32_t>(v) ^ sw) << 4)) =
+                    make_uint4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const int grow = p.dw_row0 + prob * p.dw_rows_per_prob;
+        for (int t2 = 0; t2 < 18; ++t2)
+          asm volatile(
+              "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                  reinterpret_cast<uint64_t>(&tm_dw)),
+              "r"(smem_u32(sStage + static_cast<size_t>(t2) * (64 * 128))), "r"((t2 & 1) * 32), "r"(grow + (t2 >> 1) * kC)
+              : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+      if (p.dbias) {
+        sBias[et] = bsum;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et < 64) atomicAdd(dbias_out + et, sBias[et] + sBias[et + 64]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 }  // namespace
 }  // namespace fd
 
@@ -261,6 +437,9 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
   const int TW = (W + tiles_w - 1) / tiles_w;
   const int Wp = TW + 2;
   const size_t smem_cap = 227 * 1024;
+  // N = 192 formulation (two instructions per 16 pixels) unless FD_WGRAD_TAPPAIR=1 asks for the five tap-pair instructions
+  static const bool n192 = getenv("FD_WGRAD_TAPPAIR") == nullptr;
+  const int g_extra = n192 ? 2 : 0;            // the column-shifted reads of the gradient tile reach two rows further
 
   // Rows per tile: among the heights whose two stages of (x halo tile + g tile) fit in shared memory, pick the
   // one that minimises the work of the busiest CTA (tiles per CTA x max(MMA time, TMA fill time) per tile).
@@ -270,14 +449,14 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
   for (int R = 1; R <= H && R + 2 <= 256; ++R) {
     const int ksteps = (R * Wp + 15) / 16;
     const size_t xb = (static_cast<size_t>(ksteps * 16 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024;
-    const size_t gb = (static_cast<size_t>(ksteps * 16) * 128 + 1023) / 1024 * 1024;
+    const size_t gb = (static_cast<size_t>(ksteps * 16 + g_extra) * 128 + 1023) / 1024 * 1024;
     if (2 * (xb + gb) + 1024 + 1024 > smem_cap) break;
     const long tiles_per_prob = static_cast<long>(B) * ((H + R - 1) / R) * tiles_w;
     long cpp = nsm / nprob;
     if (cpp < 1) cpp = 1;
     if (cpp > tiles_per_prob) cpp = tiles_per_prob;
     const long per = (tiles_per_prob + cpp - 1) / cpp;
-    const double mma = ksteps * 5 * 73.0;
+    const double mma = n192 ? ksteps * 2 * 110.0 : ksteps * 5 * 73.0;
     const double fill = static_cast<double>(2 * R + 2) * Wp * 128 / 48.0;
     const double cost = per * ((mma > fill ? mma : fill) + 1500.0);   // + per-tile pipeline bubble (measured)
     if (cost < best) { best = cost; bestR = R; }
@@ -292,7 +471,7 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
   p.x_bytes = static_cast<uint32_t>((bestR + 2) * Wp * 128);
   p.g_bytes = static_cast<uint32_t>(bestR * Wp * 128);
   p.x_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.ksteps * 16 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024);
-  p.g_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.ksteps * 16) * 128 + 1023) / 1024 * 1024);
+  p.g_buf_bytes = static_cast<uint32_t>((static_cast<size_t>(p.ksteps * 16 + g_extra) * 128 + 1023) / 1024 * 1024);
   p.dw = dw_packed; p.dbias = dbias; p.flags = flags;
   { const char* d = getenv("FD_WGRAD_TIMING"); p.dbg = d ? atoi(d) : 0; }
   p.nprob = nprob;
@@ -321,17 +500,19 @@ extern "C" int fd_conv3x3_wgrad_multi(const fd_bf16* x, const fd_bf16* g, int np
   CUtensorMap tm_dw;
   p.dw_row0 = 0;
   p.dw_rows_per_prob = static_cast<int>(dw_stride / kC);
-  rc = make_tmap_2d_f32(&tm_dw, dw_packed, static_cast<long>(nprob - 1) * p.dw_rows_per_prob + 9 * kC, kC, 128, 32);
+  rc = make_tmap_2d_f32(&tm_dw, dw_packed, static_cast<long>(nprob - 1) * p.dw_rows_per_prob + 9 * kC, kC, n192 ? 64 : 128, 32);
   if (rc != FD_OK) return rc;
   const size_t stages = 2 * static_cast<size_t>(p.x_buf_bytes + p.g_buf_bytes);
-  const size_t drain = 10 * 128 * 128;          // 5 tap pairs x 2 column halves x [128 rows][128 B]
+  const size_t drain = n192 ? 18 * 64 * 128     // 9 taps x 2 column halves x [64 rows][128 B]
+                            : 10 * 128 * 128;   // 5 tap pairs x 2 column halves x [128 rows][128 B]
   p.bar_off = static_cast<uint32_t>(stages > drain ? stages : drain);
   const size_t smem = p.bar_off + 1024 + 1024;
   if (smem > smem_cap) return FD_EUNSUPPORTED;
-  cudaError_t e = set_max_dyn_smem(wgrad3x3_tc_kernel, static_cast<int>(smem));
+  auto kern = n192 ? wgrad3x3_n192_kernel : wgrad3x3_tc_kernel;
+  cudaError_t e = set_max_dyn_smem(kern, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = nprob * p.ctas_per_prob;
-  e = launch_k(wgrad3x3_tc_kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), tm_x, gmaps, tm_dw, p);
+  e = launch_k(kern, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), tm_x, gmaps, tm_dw, p);
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   return launch_status();
