@@ -199,6 +199,12 @@ def test_conv3x3_wide_chain_is_bit_identical_to_single_launches(B, H, W, nblocks
     XA_s, m_s = forward(False)
     for g in range(2):
         assert torch.equal(XA_c[g].view(torch.int16), XA_s[g].view(torch.int16))
+    # the layer hand-over (plain stores -> fence -> cluster barrier -> TMA loads of either CTA) must hold every time:
+    # a visibility race would show up as an occasional stale halo row
+    for rep in range(12 if B >= 64 else 3):
+        XA_r, _ = forward(True)
+        for g in range(2):
+            assert torch.equal(XA_r[g].view(torch.int16), XA_s[g].view(torch.int16)), f"repetition {rep}"
     assert all(torch.equal(a, b) for la, lb in zip(m_c, m_s) for a, b in zip(la, lb))
     assert XA_s[0][nl].float().abs().max() > 0
 
