@@ -184,6 +184,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       if (et == 0) FD_WTS(2);
       mbar_wait(acc_full, 0);
       tc_fence_after();
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // all column sums done before the staging tiles overwrite the stages
       if (et == 0) FD_WTS(3);
       // TMEM -> registers -> fp32 staging tiles in shared memory (the stage buffers are free now) -> TMA tensor
       // REDUCE-stores (cp.reduce.async.bulk.tensor .add: the fp32 adds happen in L2, 16 KB per instruction)
@@ -365,6 +366,9 @@ wgrad3x3_n192_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       const int q = warp & 3;
       mbar_wait(acc_full, 0);
       tc_fence_after();
+      // the staging tiles below overwrite the stage buffers: every warp must have finished its column sums of the LAST tile
+      // first (with the faster MMAs a warp can get here while a sibling still reads the gradient tile: NaN bias gradients)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int row = q * 32 + lane;           // = (dy & 1) * 64 + ci
       const int ci = row & 63;
       const uint32_t sw = static_cast<uint32_t>(ci) & 7u;

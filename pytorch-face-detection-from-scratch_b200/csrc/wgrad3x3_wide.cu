@@ -203,6 +203,8 @@ wgrad3x3_wide_kernel(const __grid_constant__ WgradWideMaps maps, const __grid_co
       const int q = warp & 3;
       mbar_wait(acc_full, 0);
       tc_fence_after();
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // every warp's column sums of the last tile are done: the staging
+                                                           // tiles below overwrite the stage buffers
       const int row = q * 32 + lane;           // = tsel * 64 + ci
       const uint32_t sw = static_cast<uint32_t>(row) & 7u;
 #pragma unroll 1

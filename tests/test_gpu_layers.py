@@ -378,3 +378,23 @@ def test_stem_stride2_tensor_core_fwd_wgrad(u8, B, Hin, Win):
     assert rel_err(dw, dref) <= 1e-4
     ops.stem_wgrad(x, g, dw, dbias, 2, 1)            # accumulates
     assert rel_err(dw, 2 * dref) <= 1e-4
+
+
+@pytest.mark.parametrize("nprob,B,H", [(2, 64, 60), (2, 16, 120)])
+def test_conv3x3_wgrad_bias_sums_at_full_size(nprob, B, H):
+    """Several tiles per CTA at the sizes the bench runs: the bias gradient (column sums of the gradient tiles by the
+    epilogue warps) must be complete before the drain's staging tiles overwrite the stage buffers -- a warp that got ahead
+    once produced NaN / garbage sums at batch 64 while every small-batch test passed."""
+    require_cuda()
+    ops = fd().ops
+    torch.manual_seed(nprob + B)
+    dev = "cuda"
+    x = torch.randn(nprob, B, H, H, C, device=dev).bfloat16()
+    g = (torch.randn(nprob, B, H, H, C, device=dev) * 0.1).bfloat16()
+    n3 = 9 * C * C
+    for rep in range(3):
+        dw = torch.zeros(nprob, n3, device=dev); db = torch.zeros(nprob, C, device=dev)
+        ops.conv3x3_wgrad_multi(x, g, dw.view(-1), n3, db.view(-1), C)
+        ref = g.float().sum(dim=(1, 2, 3))
+        assert torch.isfinite(db).all() and torch.isfinite(dw).all()
+        assert (db - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
