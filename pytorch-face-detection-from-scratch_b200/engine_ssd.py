@@ -25,6 +25,7 @@ from __future__ import annotations
 
 from typing import Dict, List
 
+import contextlib
 import os
 
 import torch
@@ -438,7 +439,7 @@ class SSDEngine:
 
         def side():
             if not sides:
-                return torch.cuda.stream(main_stream)
+                return contextlib.nullcontext()       # eager: no stream switch at all (a context enter costs host time)
             rr[0] += 1
             return torch.cuda.stream(sides[rr[0] % len(sides)])
 
