@@ -137,3 +137,18 @@ def test_torchscript_export_roundtrip_without_gpu(tmp_path):
     for cls, args in ((fd.models.SSD.SSD, (16, (3, 480, 480))), (fd.models.MobilenetV3Backbone.MobilenetV3Backbone, (576, (3, 480, 480), 15))):
         s2 = cls(*args).to_torchscript()
         assert "fd_b200.detector_forward" in s2.code
+
+
+def test_new_entry_points_reject_bad_arguments_before_touching_the_device():
+    """fd_conv3x3_wide_chain / fd_stem_fwd_cached / fd_stem_wgrad_pair: null operands are FD_EINVAL (-1) -- checked before
+    any CUDA call, so this runs without a GPU; the ctypes record of a chain layer has the C layout (4 ints + 15 pointers)."""
+    import ctypes
+    lib = fd.native.lib()
+    assert ctypes.sizeof(fd.native.WideChainLayer) == 4 * 4 + 15 * 8
+    assert lib.fd_conv3x3_wide_chain(None, 1, None, 1, 1, 15, 15, 0.2, None, 1, None) == -1
+    assert lib.fd_stem_fwd_cached(None, None, None, 1, 3, 480, 480, 10, 8, 2, None, None) == -1
+    assert lib.fd_stem_wgrad_pair(None, None, None, 1, 3, 480, 480, 10, 8, 2, None, None, None) == -1
+    assert lib.fd_error_string(-1).decode() != ""
+    L = fd.ops.WideChainLayer()
+    L.in_index, L.w_index = 3, 5
+    assert (L.in_index, L.w_index, L.flags) == (3, 5, 0) and L.out[0] is None
